@@ -1,0 +1,155 @@
+"""Generates tests/golden/*.npz by RUNNING THE UNMODIFIED REFERENCE CLASSES from
+/root/reference (build container only).  Usage:  python tests/golden/make_golden.py
+
+Each file holds the inputs of one or more control ticks (path, x0, nominal U, carried
+waypoint index, injected noise) and what the reference class produced (S, w, weighted
+noise before/after the filter, the shifted nominal, the returned u0, the index after).
+Noise is drawn once, rounded to float32 and stored, so the reference, the oracle and
+the CUDA path all consume bit-identical values.  numpy's version is recorded (Q12).
+"""
+import json
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "..", ".."))
+from oracle import ref_loader  # noqa: E402
+
+
+def spline_path(ref):
+    cx, cy, cyaw, _, _ = ref["calc_spline_course"]([0.0, 0.5, 1.0, 3.0, 3.0, 1.0, -4.0],
+                                                   [0.0, 1.0, 1.0, 2.0, 5.0, 1.0, -1.0], ds=0.1)
+    return np.array([cx, cy, cyaw]).T
+
+
+def draw_eps(rng, sigma, K, T):
+    return rng.multivariate_normal(np.zeros(2), sigma, (K, T)).astype(np.float32)
+
+
+def run_ticks(ctrl, idx_attr, states, eps_list, plant=None):
+    """Steps `ctrl` through len(eps_list) ticks.  `states` is a list of observed states, or
+    a single initial state when `plant` (closed loop) is given."""
+    cap = ref_loader.instrument(ctrl, [e.astype(ctrl.u_prev.dtype) for e in eps_list])
+    rec = {k: [] for k in ("x0", "U0", "idx0", "S", "w", "w_eps", "w_eps_filt", "U_after", "u0", "idx_after")}
+    x = np.array(states[0], dtype=float)
+    for i in range(len(eps_list)):
+        if plant is None:
+            x = np.array(states[i], dtype=float)
+        rec["x0"].append(x.copy())
+        rec["U0"].append(np.array(ctrl.u_prev, copy=True))
+        rec["idx0"].append(int(getattr(ctrl, idx_attr)))
+        with ref_loader.quiet():
+            step = ctrl._calc_input_control if hasattr(ctrl, "_calc_input_control") else ctrl._calc_control_input
+            u0, useq, _, _ = step(x)
+        for k in ("S", "w", "w_eps", "w_eps_filt"):
+            rec[k].append(cap[k])
+        rec["U_after"].append(np.array(ctrl.u_prev, copy=True))
+        rec["u0"].append(np.array(u0, copy=True))
+        rec["idx_after"].append(int(getattr(ctrl, idx_attr)))
+        if plant is not None:
+            x = plant(x, np.array(u0, dtype=float))
+    return {k: np.array(v) for k, v in rec.items()}
+
+
+def save(name, meta, path, eps_list, rec, obstacles=None):
+    meta = dict(meta, numpy=np.__version__, generator="tests/golden/make_golden.py",
+                source="unmodified reference classes executed in the build container")
+    out = dict(meta=json.dumps(meta), path=path, eps=np.array(eps_list, dtype=np.float32), **rec)
+    if obstacles is not None:
+        out["obstacles"] = np.asarray(obstacles, float)
+    fn = os.path.join(HERE, name + ".npz")
+    np.savez_compressed(fn, **out)
+    print("wrote", fn, "%.1f KB" % (os.path.getsize(fn) / 1024))
+
+
+def main():
+    ref = ref_loader.load_reference()
+    path = spline_path(ref)
+    sigma_dd = np.array([[0.1, 0.0], [0.0, 0.01]])
+    w_dd = np.array([5.0, 5.0, 10.0])
+
+    def plant_dd(dt):
+        def f(x, u):
+            d = ref["DifferentialDrive"](x)
+            return d.update_state(dt, x, u)
+        return f
+
+    # ---- diff-drive literal class: open-loop ticks from several states, 2 temperatures
+    for tag, pe in (("pe1e-4", 1e-4), ("pe0.05", 0.05)):
+        K, T = 256, 30
+        kw = dict(delta_t=0.1, max_speed=5.0, max_omega=3.14, num_samples_K=K, num_horizons_T=T,
+                  param_exploration=pe, param_lambda=1.0, param_alpha=0.2)
+        ctrl = ref["MPPIAlgorithms"](ref_path=path, sigma=sigma_dd, stage_cost_weight=w_dd,
+                                     terminal_cost_weight=w_dd, visualize_optimal_traj=False,
+                                     visualze_sampled_trajs=False, **kw)
+        rng = np.random.default_rng(0)
+        eps_list = [draw_eps(rng, sigma_dd, K, T) for _ in range(4)]
+        rec = run_ticks(ctrl, "prev_way_point_idx", [[0, 0, 0]], eps_list, plant=plant_dd(0.1))
+        save("diffdrive_" + tag, dict(kind="diffdrive", **kw), path, eps_list, rec)
+
+    # ---- diff-drive closed loop, longer (small K), temperature 0.05 and the ratchet
+    K, T = 64, 12
+    kw = dict(delta_t=0.1, max_speed=5.0, max_omega=3.14, num_samples_K=K, num_horizons_T=T,
+              param_exploration=0.05, param_lambda=1.0, param_alpha=0.2)
+    ctrl = ref["MPPIAlgorithms"](ref_path=path, sigma=sigma_dd, stage_cost_weight=w_dd,
+                                 terminal_cost_weight=w_dd, visualize_optimal_traj=False,
+                                 visualze_sampled_trajs=False, **kw)
+    rng = np.random.default_rng(1)
+    eps_list = [draw_eps(rng, sigma_dd, K, T) for _ in range(40)]
+    rec = run_ticks(ctrl, "prev_way_point_idx", [[0, 0, 0]], eps_list, plant=plant_dd(0.1))
+    save("diffdrive_closed_loop", dict(kind="diffdrive", **kw), path, eps_list, rec)
+
+    # ---- diff-drive + circular obstacles (the obs script's own parameters)
+    K, T = 200, 20
+    obs = np.array([[2.0, 2.0, 0.4], [3.0, 3.5, 0.4]])
+    sigma_obs = np.array([[0.1, 0.0], [0.0, 0.01]])
+    w_obs = 10 * np.array([5.0, 6.0, 9.0])
+    kw = dict(delta_t=0.1, max_speed=5.0, max_omega=3.14, num_samples_K=K, num_horizons_T=T,
+              param_exploration=0.05, param_lambda=10.0, param_alpha=0.98, safety_margin_rate=0.8)
+    ctrl = ref["MPPIObs"](ref_path=path, sigma=sigma_obs, stage_cost_weight=w_obs,
+                          terminal_cost_weight=w_obs, obstacle_circles=obs,
+                          visualize_optimal_traj=False, visualze_sampled_trajs=False, **kw)
+    rng = np.random.default_rng(2)
+    eps_list = [draw_eps(rng, sigma_obs, K, T) for _ in range(4)]
+    states = [[0, 0, 0], [1.6, 1.5, 0.6], [2.3, 1.9, 0.9], [2.9, 2.6, 1.4]]
+    rec = run_ticks(ctrl, "prev_way_point_idx", states, eps_list)
+    save("diffdrive_obs", dict(kind="diffdrive_obs", **kw), path, eps_list, rec, obstacles=obs)
+
+    # ---- race-car + obstacles, constructor defaults, states = ref_path[i] (+ perturbed)
+    from oracle.mppi_oracle import lemniscate_path
+    sigma_rc = np.array([[0.5, 0.0], [0.0, 0.1]])
+    for tag, alpha, nobs in (("default", 1.0, True), ("alpha0.9", 0.9, True), ("noobs", 1.0, False)):
+        K, T = 128, 50 if nobs else 20
+        cls = ref["MPPIRacecarController"] if nobs else ref["MPPIRacecarNoObs"]
+        ctrl = cls(horizon_step_T=T, number_of_samples_K=K, param_alpha=alpha,
+                   visualize_optimal_traj=False, visualze_sampled_trajs=False)
+        lp = ctrl.generate_lemniscate_trajectory(100, 10.0) if nobs else lemniscate_path()
+        assert np.array_equal(lp.astype(np.float32), lemniscate_path()), "lemniscate restatement drifted"
+        ctrl.ref_path = lp.astype(np.float32)
+        rng = np.random.default_rng(3)
+        eps_list = [draw_eps(rng, sigma_rc, K, T) for _ in range(6)]
+        pert = rng.normal(0, [0.3, 0.3, 0.05, 0.5], (6, 4))
+        # ticks 0-2 teleport along the path like the reference main (:336-339); 3-5 perturbed
+        states = [lp[0], lp[1], lp[2], lp[8] + pert[3], lp[9] + pert[4], lp[10] + pert[5]]
+        states = [np.asarray(s, dtype=np.float32) for s in states]
+        rec = run_ticks(ctrl, "prev_waypoints_idx", states, eps_list)
+        meta = dict(kind="racecar" if nobs else "racecar_noobs", horizon_step_T=T,
+                    number_of_samples_K=K, param_alpha=alpha)
+        save("racecar_" + tag, meta, lp.astype(np.float32), eps_list, rec,
+             obstacles=ctrl.obstacle_circles if nobs else None)
+
+    # ---- literal filter operators as matrices (Q7)
+    Ms = {}
+    for T in (10, 12, 20, 30, 50):
+        Ms["diffdrive_T%d" % T] = ref["MPPIAlgorithms"]._moving_average_filter(None, np.eye(T), 10)
+        Ms["racecar_T%d" % T] = ref["MPPIRacecarController"]._moving_average_filter(
+            None, np.eye(T, dtype=np.float32), 10)
+    np.savez_compressed(os.path.join(HERE, "filter_matrices.npz"), **Ms)
+    np.savez_compressed(os.path.join(HERE, "paths.npz"), spline=path, lemniscate=lemniscate_path())
+    print("done")
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,55 @@
+"""Loads tests/golden/*.npz (made by tests/golden/make_golden.py from the unmodified
+reference classes) and maps each file's recorded constructor kwargs to an oracle spec."""
+import json
+import os
+
+import numpy as np
+
+from oracle import mppi_oracle as orc
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+DIFFDRIVE_CASES = ["diffdrive_pe1e-4", "diffdrive_pe0.05", "diffdrive_closed_loop", "diffdrive_obs"]
+RACECAR_CASES = ["racecar_default", "racecar_alpha0.9", "racecar_noobs"]
+ALL_CASES = DIFFDRIVE_CASES + RACECAR_CASES
+
+
+class Golden:
+    def __init__(self, name):
+        z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+        self.name = name
+        self.meta = json.loads(str(z["meta"]))
+        self.path = z["path"]
+        self.eps = z["eps"]                       # (ticks, K, T, 2) float32
+        self.obstacles = z["obstacles"] if "obstacles" in z.files else None
+        self.rec = {k: z[k] for k in ("x0", "U0", "idx0", "S", "w", "w_eps", "w_eps_filt",
+                                      "U_after", "u0", "idx_after")}
+        self.n_ticks = self.eps.shape[0]
+
+    def spec(self, **override):
+        m = self.meta
+        if m["kind"].startswith("diffdrive"):
+            s = orc.diffdrive_spec(
+                K=m["num_samples_K"], T=m["num_horizons_T"], dt=m["delta_t"],
+                max_speed=m["max_speed"], max_omega=m["max_omega"],
+                param_exploration=m["param_exploration"], param_lambda=m["param_lambda"],
+                param_alpha=m["param_alpha"],
+                stage_w=(10 * np.array([5.0, 6.0, 9.0]) if m["kind"] == "diffdrive_obs" else None),
+                term_w=(10 * np.array([5.0, 6.0, 9.0]) if m["kind"] == "diffdrive_obs" else None),
+                obstacles=self.obstacles, margin=m.get("safety_margin_rate", 1.0))
+        else:
+            s = orc.racecar_spec(K=m["number_of_samples_K"], T=m["horizon_step_T"],
+                                 param_alpha=m["param_alpha"], obstacles=self.obstacles)
+        for k, v in override.items():
+            setattr(s, k, v)
+        return s
+
+    def tick_inputs(self, i):
+        r = self.rec
+        return dict(path=self.path, U=r["U0"][i], idx=int(r["idx0"][i]), x0=r["x0"][i], eps=self.eps[i])
+
+
+def rel_err(a, b, floor=1e-12):
+    a = np.asarray(a, np.float64)
+    b = np.asarray(b, np.float64)
+    return float(np.max(np.abs(a - b) / np.maximum(np.abs(b), floor))) if a.size else 0.0

@@ -1,0 +1,346 @@
+#!/usr/bin/env python
+"""Benchmark of the MPPI hot path (BASELINE.json metric: MPPI sample-steps/s and p50 control-step
+latency at K samples x H horizon).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+
+Headline workload (config.workload): differential-drive MPPI, K = 1M samples PER GPU, H = 50,
+Philox noise generated in-kernel, `sum` cost / frozen window (the parallel modes of the reference
+tick), dense weights (temperature chosen so every sample's noise is re-generated
+for the weighted sum).  One "step" = one control tick = K*H sample-steps.  Multi-GPU runs shard the
+samples (weak scaling: K per GPU fixed) with one NCCL all-gather of (min, sum w, sum w*eps) per tick.
+
+Prints ONE JSON line (rank 0).  `value` is device-timed (CUDA events on the launching stream, inputs
+resident); `e2e` goes through the drop-in class `MPPIAlgorithms._calc_input_control` with a host
+state in and a host control out every tick.  `--impl reference` times the CPU restatement of the
+reference tick (oracle/, the one place bench.py may execute it) on the host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "dnn-mppi-mpc_b200"), os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+K_PER_GPU = 1 << 20
+T_H = 50
+# algorithmic work per sample-step, diff-drive `sum` mode, window 20
+FLOP_PER_SAMPLE_STEP = 133.0
+SM_COUNT, FP32_LANES = 148, 128
+
+
+def spline_path():
+    return np.load(os.path.join(ROOT, "tests", "golden", "paths.npz"))["spline"]
+
+
+def diffdrive_kwargs(K, T, temperature):
+    return dict(delta_t=0.1, ref_path=spline_path(), max_speed=5.0, max_omega=3.14, num_samples_K=K,
+                num_horizons_T=T, param_exploration=0.05, param_lambda=1.0, param_alpha=0.2,
+                sigma=np.array([[0.1, 0.0], [0.0, 0.01]]), stage_cost_weight=np.array([5.0, 5.0, 10.0]),
+                terminal_cost_weight=np.array([5.0, 5.0, 10.0]), visualize_optimal_traj=False,
+                visualze_sampled_trajs=False, cost_mode="sum", waypoint_mode="frozen", temperature=temperature)
+
+
+class ClockSampler(threading.Thread):
+    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu_index):
+        super().__init__(daemon=True)
+        self.gpu = gpu_index
+        self.rows = []
+        self._stop = threading.Event()
+
+    def run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                parts = [p.strip() for p in out.strip().split(",")]
+                if len(parts) >= 7:
+                    self.rows.append(parts)
+            except Exception:
+                pass
+            self._stop.wait(0.15)
+
+    def stop(self):
+        self._stop.set()
+        self.join(timeout=5)
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        sm = sorted(float(r[0]) for r in self.rows)
+        reasons = []
+        for name, col in (("hw_slowdown", 3), ("hw_thermal_slowdown", 4), ("sw_thermal_slowdown", 5), ("sw_power_cap", 6)):
+            if any(r[col].lower().startswith("active") for r in self.rows):
+                reasons.append(name)
+        pw = [float(r[2]) for r in self.rows if r[2].replace(".", "").isdigit()]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons,
+                "samples": len(self.rows), "power_w_max": max(pw) if pw else None}
+
+
+def measured_peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        return None
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the oracle restatement of the reference tick on the host cores
+# ------------------------------------------------------------------------------------------------
+def cpu_port_run(ticks, K, T, temperature, nthreads=0):
+    """C restatement (oracle/mppi_oracle.c), Philox noise, all host threads: sample-steps/s."""
+    from oracle import c_oracle as co
+    from oracle import mppi_oracle as orc
+    sp = orc.diffdrive_spec(K=K, T=T, param_exploration=0.05, cost_mode="sum", waypoint_mode="frozen")
+    sp.temperature = temperature
+    path = spline_path()
+    U = np.zeros((T, 2))
+    idx = 0
+    x0 = np.zeros(3)
+    times = []
+    for i in range(ticks):
+        t0 = time.perf_counter()
+        o = co.tick(sp, path, U, idx, x0, eps=None, seed=1, tick=i, nthreads=nthreads)
+        times.append(time.perf_counter() - t0)
+        U, idx = o["U_after"], o["idx_after"]
+    return times, co.max_threads()
+
+
+def cpu_python_loops_rate(K=64, T=50):
+    """The reference's own formulation -- scalar Python loops over samples and horizon
+    (oracle.tick_loops restates controllers/mppi_differential_drive.py:111-141) -- one core."""
+    from oracle import mppi_oracle as orc
+    sp = orc.diffdrive_spec(K=K, T=T, param_exploration=0.05, cost_mode="sum", waypoint_mode="frozen")
+    eps = np.random.default_rng(0).multivariate_normal(np.zeros(2), sp.sigma, (K, T))
+    t0 = time.perf_counter()
+    orc.tick_loops(sp, spline_path(), np.zeros((T, 2)), 0, np.zeros(3), eps)
+    return K * T / (time.perf_counter() - t0)
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    K_s = 1 << 16                           # bounded sample of the K=1M workload: 65,536 samples x H=50 per step
+    cpu_port_run(max(1, min(args.warmup, 2)), K_s, T_H, 10.0)
+    times, nthr = cpu_port_run(args.steps, K_s, T_H, 10.0)
+    ms = 1e3 * float(np.mean(times))
+    val = K_s * T_H / float(np.mean(times))
+    py_rate = cpu_python_loops_rate()
+    line = {
+        "impl": "reference", "metric": "mppi_sample_steps_per_sec", "value": val, "unit": "sample-steps/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "diffdrive_K1M_H50_sum_frozen_philox (CPU sample: K=65536 per step)",
+                   "K_sample": K_s, "H": T_H},
+        "cpu_baseline": {"value": val, "unit": "sample-steps/s", "cores": nthr, "kind": "port",
+                         "sample": "K=65536 x H=50 per tick, %d ticks, oracle/mppi_oracle.c (OpenMP)" % args.steps,
+                         "python_loops_1core_value": py_rate,
+                         "note": "the reference itself is scalar Python loops (python_loops_1core_value); the C port is a best-effort CPU line"},
+        "e2e": {"value": val, "unit": "sample-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------
+# B200 arm
+# ------------------------------------------------------------------------------------------------
+def run_b200_arm(args):
+    import torch
+    import torch.distributed as dist
+    from mppi_b200.mppi_differential_drive import MPPIAlgorithms
+    from mppi_b200.mppi_race_car_obstacle import MPPIRacecarController
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    K_global = K_PER_GPU * world
+    temperature = 10.0
+    ctrl = MPPIAlgorithms(**diffdrive_kwargs(K_global, T_H, temperature), seed=7, device=local_rank,
+                          rank=rank, world=world)
+    if world > 1:
+        ctrl.comm_init_from_torch()
+    eng = ctrl.engine
+    stream = torch.cuda.Stream()
+    eng.set_stream(stream.cuda_stream)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")   # > 126 MB L2
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    x0 = np.zeros(3)
+    # ---- device-timed throughput: per-step CUDA events on the launching stream, L2 flushed between steps
+    tick = 0
+    for _ in range(args.warmup):
+        eng.step_async(x0, None, 7, tick); tick += 1
+    barrier()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    launches0 = eng.timings()["launches"]
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    t_wall0 = time.perf_counter()
+    with torch.cuda.stream(stream):
+        for i in range(args.steps):
+            flush.zero_()
+            ev[i][0].record(stream)
+            eng.step_async(x0, None, 7, tick); tick += 1
+            ev[i][1].record(stream)
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    clocks = sampler.stop()
+    launches = eng.timings()["launches"] - launches0
+    step_ms = np.array([a.elapsed_time(b) for a, b in ev])
+    local_ms = float(step_ms.sum())
+    if world > 1:
+        t = torch.tensor([local_ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+    else:
+        total_ms = local_ms
+    ms_per_step = total_ms / args.steps
+    value = K_global * T_H / (ms_per_step * 1e-3)
+    stats = eng.stats()
+
+    # ---- end to end through the drop-in class: host state in, host control out, every tick
+    for _ in range(max(3, args.warmup)):
+        ctrl._calc_input_control(x0)
+    barrier()
+    lat = []
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        t1 = time.perf_counter()
+        u0, u, _, _ = ctrl._calc_input_control(x0)
+        lat.append(time.perf_counter() - t1)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e_value = K_global * T_H * args.steps / e2e_s
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    extras = {}
+    if world == 1:
+        # literal diff-drive temperature (= param_exploration, quirk Q2): sparse weights
+        c2 = MPPIAlgorithms(**diffdrive_kwargs(K_PER_GPU, T_H, None), seed=7)
+        c2.engine.set_stream(stream.cuda_stream)
+        for _ in range(3):
+            c2.engine.step_async(x0, None, 7, 0)
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n2 = max(5, args.steps // 4)
+        with torch.cuda.stream(stream):
+            a.record(stream)
+            for i in range(n2):
+                c2.engine.step_async(x0, None, 7, i)
+            b.record(stream)
+        torch.cuda.synchronize()
+        extras["literal_temperature_value"] = K_PER_GPU * T_H / (a.elapsed_time(b) / n2 * 1e-3)
+        c2.engine.close()
+        # config[1]: race-car + obstacles, K=16384, H=50 -- p50 control-step latency, host to host
+        rc = MPPIRacecarController(horizon_step_T=50, number_of_samples_K=16384,
+                                   visualize_optimal_traj=False, visualze_sampled_trajs=False, seed=3)
+        lp = rc.generate_lemniscate_trajectory(100, 10.0).astype(np.float32)
+        rc.ref_path = lp
+        for i in range(20):
+            rc._calc_control_input(lp[i % 100])
+        rl = []
+        for i in range(300):
+            rc.prev_waypoints_idx = 0
+            t1 = time.perf_counter()
+            rc._calc_control_input(lp[i % 50])
+            rl.append(time.perf_counter() - t1)
+        rl = np.sort(np.array(rl))
+        extras["racecar_K16384_H50"] = {"p50_ms": 1e3 * float(rl[len(rl) // 2]), "p90_ms": 1e3 * float(rl[int(len(rl) * 0.9)]),
+                                        "sample_steps_per_sec": 16384 * 50 / float(rl[len(rl) // 2])}
+        rc.engine.close()
+
+    # ---- roofline of the dominant kernel (mppi_tick_kernel): FP32 issue-bound, not HBM-bound
+    peaks = measured_peaks()
+    f_mhz = clocks.get("sm_mhz") or (peaks or {}).get("sm_max_mhz") or 1965.0
+    kern_ms = float(np.mean(step_ms))
+    flops = FLOP_PER_SAMPLE_STEP * K_PER_GPU * T_H
+    achieved_tf = flops / (kern_ms * 1e-3) / 1e12
+    peak_tf_max = SM_COUNT * FP32_LANES * 2 * ((peaks or {}).get("sm_max_mhz", 1965.0)) * 1e6 / 1e12
+    hbm_bytes = 4.0 * (K_PER_GPU / 256) * (4 + 2 * T_H) / 4 + 4 * (8 + 4 * 128)       # partial writes + out record
+    roofline = {
+        "bound": "fp32", "achieved": achieved_tf, "peak": peak_tf_max, "unit": "TFLOP/s",
+        "frac": achieved_tf / peak_tf_max, "traffic": None,
+        "peak_source": "derived 148 SM x 128 lanes x 2 x clocks.max.sm (FP32 peak is not in MEASURED_PEAKS.json)",
+        "algorithmic_flop_per_sample_step": FLOP_PER_SAMPLE_STEP,
+        "sm_mhz_during_run": f_mhz,
+        "hbm_view": {"algorithmic_bytes_per_launch": hbm_bytes,
+                     "achieved_GBps": hbm_bytes / (kern_ms * 1e-3) / 1e9,
+                     "peak_GBps": (peaks or {}).get("hbm_gbs", 6650.0),
+                     "peak_kind": "measured" if peaks else "fallback"},
+    }
+
+    # ---- CPU baseline beside it: bounded sample of the same workload
+    cpu_port_run(1, 1 << 16, T_H, temperature)
+    times, nthr = cpu_port_run(3, 1 << 16, T_H, temperature)
+    cpu_val = (1 << 16) * T_H / float(np.mean(times))
+    cpu_baseline = {"value": cpu_val, "unit": "sample-steps/s", "cores": nthr, "kind": "port",
+                    "sample": "K=65536 x H=50 per tick, 3 ticks, oracle/mppi_oracle.c (OpenMP, FP64)",
+                    "python_loops_1core_value": cpu_python_loops_rate()}
+
+    lat = np.sort(np.array(lat))
+    line = {
+        "metric": "mppi_sample_steps_per_sec", "value": value, "unit": "sample-steps/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "diffdrive_K1M_H50_sum_frozen_philox", "K_per_gpu": K_PER_GPU, "K_global": K_global,
+                   "H": T_H, "temperature": temperature, "path": "168-point cubic spline (tests/golden/paths.npz)",
+                   "l2": "flushed between timed steps (256 MiB memset, outside the per-step event pair)",
+                   "parallelism": "samples sharded, %d rank(s)" % world},
+        "e2e": {"value": e2e_value, "unit": "sample-steps/s", "h2d_bytes_per_step": 16,
+                "d2h_bytes_per_step": 4 * (8 + 2 * T_H), "p50_ms": 1e3 * float(lat[len(lat) // 2]),
+                "api": "MPPIAlgorithms._calc_input_control(host x0) -> host u0, u_seq"},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": roofline,
+        "cpu_baseline": cpu_baseline,
+        "extras": dict(extras, ess=stats["ess"], wall_s_timed_region=t_wall),
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    args = ap.parse_args()
+    args.warmup = max(3, args.warmup)
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_b200_arm(args)
+
+
+if __name__ == "__main__":
+    main()

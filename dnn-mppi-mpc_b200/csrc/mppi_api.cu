@@ -1,0 +1,649 @@
+// C ABI of libmppi_b200.so (include/mppi_b200.h): handle management, launch orchestration,
+// strict-mode multi-pass driver, NCCL sample sharding.  Host code only; kernels live in
+// mppi_kernels.cu / mppi_mlp.cu.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "mppi_device.cuh"
+#include "mppi_launch.h"
+#include "mppi_mlp.h"
+
+namespace {
+
+struct NcclApi {
+    void *lib = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    const char *(*GetErrorString)(ncclResult_t) = nullptr;
+    bool load() {
+        if (lib) return true;
+        // Reuse the copy torch already mapped when there is one (same soname), else the system one.
+        lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (!lib) return false;
+        GetUniqueId = (decltype(GetUniqueId))dlsym(lib, "ncclGetUniqueId");
+        CommInitRank = (decltype(CommInitRank))dlsym(lib, "ncclCommInitRank");
+        AllGather = (decltype(AllGather))dlsym(lib, "ncclAllGather");
+        CommDestroy = (decltype(CommDestroy))dlsym(lib, "ncclCommDestroy");
+        GetErrorString = (decltype(GetErrorString))dlsym(lib, "ncclGetErrorString");
+        return GetUniqueId && CommInitRank && AllGather && CommDestroy && GetErrorString;
+    }
+};
+NcclApi g_nccl;
+
+}  // namespace
+
+struct mppi_handle_s {
+    mppi_config_t cfg{};
+    TickArgs args{};
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    int n_sm = 148, occ = 1, nx = 3;
+    int grid_x = 1;
+    bool sum = false, strict = false;
+    bool have_path = false;
+    std::vector<double> path_h;          // host copy for the strict-mode step 1 (literal FP64)
+    int n_path = 0, path_cols = 0;
+    // device buffers
+    float4 *d_path = nullptr;
+    float *d_U = nullptr, *d_M = nullptr, *d_S = nullptr, *d_part = nullptr, *d_out = nullptr;
+    float *d_x0 = nullptr;
+    int *d_idx = nullptr;
+    unsigned *d_ticket = nullptr;
+    float *h_out = nullptr, *h_out_dev = nullptr;     // mapped pinned record of robot 0
+    // strict mode
+    unsigned *d_bp_n = nullptr;
+    int *d_bp_s = nullptr;
+    unsigned long long *d_first = nullptr, *h_first = nullptr;
+    // multi-GPU
+    ncclComm_t comm = nullptr;
+    int rank = 0, world = 1;
+    float *d_send = nullptr, *d_recv = nullptr;
+    // MLP dynamics
+    MlpState *mlp = nullptr;
+    // timing / bookkeeping
+    bool timing = false;
+    cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+    mppi_timings_t tm{};
+    std::string err;
+};
+
+#define CK(h, call)                                                                         \
+    do {                                                                                    \
+        cudaError_t e_ = (call);                                                            \
+        if (e_ != cudaSuccess) {                                                            \
+            if (h) (h)->err = std::string(#call) + ": " + cudaGetErrorString(e_);           \
+            return MPPI_E_CUDA;                                                             \
+        }                                                                                   \
+    } while (0)
+
+static int fail(mppi_handle_t h, int code, const char *msg) {
+    if (h) h->err = msg;
+    return code;
+}
+
+extern "C" {
+
+int mppi_abi_version(void) { return MPPI_ABI_VERSION; }
+
+const char *mppi_strerror(int s) {
+    switch (s) {
+        case MPPI_OK: return "ok";
+        case MPPI_E_BADARG: return "invalid argument or configuration";
+        case MPPI_E_CUDA: return "CUDA error (see mppi_last_error)";
+        case MPPI_E_NCCL: return "NCCL error (see mppi_last_error)";
+        case MPPI_E_STATE: return "call order: reference path / nominal / weights not set";
+        case MPPI_E_UNSUPPORTED: return "mode combination not supported";
+        case MPPI_E_NOMEM: return "out of memory";
+        default: return "unknown status";
+    }
+}
+
+const char *mppi_last_error(mppi_handle_t h) { return h ? h->err.c_str() : "null handle"; }
+
+void mppi_default_config(mppi_config_t *c) {
+    // defaults of controllers/mppi_differential_drive.py:400-410 with the perf modes off
+    std::memset(c, 0, sizeof(*c));
+    c->abi_version = MPPI_ABI_VERSION;
+    c->model = MPPI_MODEL_DIFFDRIVE;
+    c->K = 1000; c->T = 30; c->n_robots = 1; c->window = 20;
+    c->cost_mode = MPPI_COST_LAST; c->waypoint_mode = MPPI_WP_STRICT;
+    c->filter_kind = MPPI_FILTER_DIFFDRIVE; c->yaw_wrap = 0; c->collision = MPPI_COLLISION_NONE;
+    c->K_global = 0; c->k_offset = 0;
+    c->dt = 0.1; c->wheel_base = 2.5; c->u_max[0] = 5.0; c->u_max[1] = 3.14;
+    c->param_exploration = 1e-4; c->param_lambda = 1.0; c->param_alpha = 0.2; c->temperature = 1e-4;
+    c->sigma[0] = 0.1; c->sigma[3] = 0.01;
+    c->stage_w[0] = 5; c->stage_w[1] = 5; c->stage_w[2] = 10;
+    c->term_w[0] = 5; c->term_w[1] = 5; c->term_w[2] = 10;
+    c->margin = 1.0; c->robot_radius = 0.5; c->vehicle_l = 4.0; c->vehicle_w = 3.0;
+}
+
+// The fixed filter operators (A14 / Q7) as T x T matrices, float64 then rounded once.
+static void build_filter(int T, int kind, std::vector<float> &M) {
+    std::vector<double> m((size_t)T * T, 0.0);
+    if (kind == MPPI_FILTER_DIFFDRIVE) {
+        // 'same' box convolution of width 10: y[n] = 0.1 * sum_{m=n-5}^{n+4} x[m]; head rows i<5
+        // rescaled by 10/(i+5); the tail rescale lands on the last row for i=1..4 (the bug is kept)
+        for (int n = 0; n < T; ++n)
+            for (int j = n - 5; j <= n + 4; ++j)
+                if (j >= 0 && j < T) m[(size_t)n * T + j] = 0.1;
+        for (int i = 0; i < 5 && i < T; ++i)
+            for (int j = 0; j < T; ++j) m[(size_t)i * T + j] *= 10.0 / (i + 5);
+        for (int i = 1; i < 5; ++i)
+            for (int j = 0; j < T; ++j) m[(size_t)(T - 1) * T + j] *= 10.0 / (i + 5);
+    } else {
+        // pad with the first 5 and the last 5 rows, 'same' box convolution, crop
+        for (int n = 0; n < T; ++n)
+            for (int j = n; j <= n + 9; ++j) {
+                const int src = j < 5 ? j : (j < T + 5 ? j - 5 : j - 10);
+                m[(size_t)n * T + src] += 0.1;
+            }
+    }
+    M.resize((size_t)T * T);
+    for (size_t i = 0; i < M.size(); ++i) M[i] = (float)m[i];
+}
+
+static void refresh_obstacle_args(mppi_handle_t h, const double *xyr, int m) {
+    TickArgs &a = h->args;
+    const mppi_config_t &c = h->cfg;
+    a.n_obs = m;
+    const double hl = 0.5 * c.vehicle_l * c.margin, hw = 0.5 * c.vehicle_w * c.margin;
+    a.fp_hl = (float)hl; a.fp_hw = (float)hw;
+    const double diag = std::sqrt(hl * hl + hw * hw);
+    for (int i = 0; i < m; ++i) {
+        a.obs_x[i] = (float)xyr[3 * i]; a.obs_y[i] = (float)xyr[3 * i + 1];
+        const double r = xyr[3 * i + 2];
+        if (c.collision == MPPI_COLLISION_CIRCLE) {
+            const double rr = c.robot_radius * c.margin + r;
+            a.obs_r2[i] = (float)(rr * rr);
+        } else {
+            a.obs_r2[i] = (float)(r * r);
+        }
+        const double far = (diag + r) * 1.001 + 1e-3;
+        a.obs_far2[i] = (float)(far * far);
+    }
+}
+
+int mppi_create(const mppi_config_t *cfg, mppi_handle_t *out) {
+    if (!cfg || !out) return MPPI_E_BADARG;
+    *out = nullptr;
+    if (cfg->abi_version != MPPI_ABI_VERSION) return MPPI_E_BADARG;
+    if (cfg->K < 1 || cfg->T < 1 || cfg->T > MPPI_MAX_T || cfg->n_robots < 1) return MPPI_E_BADARG;
+    if (cfg->window < 1 || cfg->window > MPPI_MAX_WINDOW) return MPPI_E_BADARG;
+    if (cfg->model < 0 || cfg->model > MPPI_MODEL_DIFFDRIVE_MLP) return MPPI_E_BADARG;
+    if (cfg->filter_kind == MPPI_FILTER_DIFFDRIVE && cfg->T < 10) return MPPI_E_BADARG;   // the reference raises (:263)
+    if (cfg->filter_kind == MPPI_FILTER_RACECAR && cfg->T < 5) return MPPI_E_BADARG;
+    if (cfg->temperature <= 0.0 || cfg->dt <= 0.0) return MPPI_E_BADARG;
+    const double det = cfg->sigma[0] * cfg->sigma[3] - cfg->sigma[1] * cfg->sigma[2];
+    if (!(cfg->sigma[0] > 0.0) || !(det > 0.0)) return MPPI_E_BADARG;
+    if (cfg->collision == MPPI_COLLISION_FOOTPRINT && cfg->model != MPPI_MODEL_BICYCLE) return MPPI_E_UNSUPPORTED;
+    if (cfg->model == MPPI_MODEL_DIFFDRIVE_MLP &&
+        (cfg->waypoint_mode != MPPI_WP_FROZEN || cfg->n_robots != 1 || cfg->collision != MPPI_COLLISION_NONE))
+        return MPPI_E_UNSUPPORTED;
+    if (cfg->waypoint_mode == MPPI_WP_STRICT && cfg->n_robots != 1) return MPPI_E_UNSUPPORTED;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || cfg->device >= ndev) return MPPI_E_CUDA;
+
+    mppi_handle_t h = new (std::nothrow) mppi_handle_s();
+    if (!h) return MPPI_E_NOMEM;
+    h->cfg = *cfg;
+    mppi_config_t &c = h->cfg;
+    if (c.K_global <= 0) c.K_global = c.K;
+    h->nx = (c.model == MPPI_MODEL_BICYCLE) ? 4 : 3;
+    h->sum = c.cost_mode == MPPI_COST_SUM;
+    h->strict = c.waypoint_mode == MPPI_WP_STRICT;
+#define CKC(call)                                                                           \
+    do {                                                                                    \
+        cudaError_t e_ = (call);                                                            \
+        if (e_ != cudaSuccess) {                                                            \
+            std::fprintf(stderr, "mppi_create: %s: %s\n", #call, cudaGetErrorString(e_));  \
+            mppi_destroy(h);                                                                \
+            return MPPI_E_CUDA;                                                             \
+        }                                                                                   \
+    } while (0)
+    CKC(cudaSetDevice(c.device));
+    cudaDeviceProp prop;
+    CKC(cudaGetDeviceProperties(&prop, c.device));
+    h->n_sm = prop.multiProcessorCount;
+    CKC(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    h->own_stream = true;
+
+    const int R = c.n_robots, T = c.T, K = c.K;
+    h->occ = mppi_tick_occupancy(c.model, c.collision, h->sum);
+    const int chunks = (K + MPPI_BLOCK - 1) / MPPI_BLOCK;
+    int gx = (h->n_sm * h->occ + R - 1) / R;
+    gx = std::max(1, std::min(gx, chunks));
+    h->grid_x = gx;
+
+    CKC(cudaMalloc(&h->d_U, sizeof(float) * R * T * 2));
+    CKC(cudaMemset(h->d_U, 0, sizeof(float) * R * T * 2));
+    CKC(cudaMalloc(&h->d_M, sizeof(float) * T * T));
+    CKC(cudaMalloc(&h->d_S, sizeof(float) * (size_t)R * K));
+    CKC(cudaMalloc(&h->d_part, sizeof(float) * (size_t)R * gx * MPPI_NF(T)));
+    CKC(cudaMalloc(&h->d_out, sizeof(float) * (size_t)R * MPPI_OUT_STRIDE));
+    CKC(cudaMemset(h->d_out, 0, sizeof(float) * (size_t)R * MPPI_OUT_STRIDE));
+    CKC(cudaMalloc(&h->d_idx, sizeof(int) * R));
+    CKC(cudaMemset(h->d_idx, 0, sizeof(int) * R));
+    CKC(cudaMalloc(&h->d_ticket, sizeof(unsigned) * R));
+    CKC(cudaMemset(h->d_ticket, 0, sizeof(unsigned) * R));
+    CKC(cudaHostAlloc(&h->h_out, sizeof(float) * MPPI_OUT_STRIDE, cudaHostAllocMapped));
+    std::memset(h->h_out, 0, sizeof(float) * MPPI_OUT_STRIDE);
+    CKC(cudaHostGetDevicePointer(&h->h_out_dev, h->h_out, 0));
+    CKC(cudaMalloc(&h->d_first, sizeof(unsigned long long)));
+    CKC(cudaHostAlloc(&h->h_first, sizeof(unsigned long long), cudaHostAllocDefault));
+    for (auto &e : h->ev) CKC(cudaEventCreate(&e));
+    std::vector<float> M;
+    build_filter(T, c.filter_kind, M);
+    CKC(cudaMemcpy(h->d_M, M.data(), sizeof(float) * T * T, cudaMemcpyHostToDevice));
+
+    TickArgs &a = h->args;
+    std::memset(&a, 0, sizeof(a));
+    a.K = K; a.T = T; a.window = c.window; a.yaw_wrap = c.yaw_wrap;
+    a.k_offset = c.k_offset;
+    {   // Q6: number of global sample indices k with k < (1.0 - param_exploration) * K, in doubles
+        const double thr = (1.0 - c.param_exploration) * (double)c.K_global;
+        long long n = (long long)std::ceil(thr);
+        n = std::max(0LL, std::min((long long)c.K_global, n));
+        a.n_exploit = (int)n;
+    }
+    a.dt = (float)c.dt; a.dt_over_L = (float)(c.dt / c.wheel_base);
+    a.umax0 = (float)c.u_max[0]; a.umax1 = (float)c.u_max[1];
+    for (int i = 0; i < 4; ++i) { a.sw[i] = (float)c.stage_w[i]; a.tw[i] = (float)c.term_w[i]; }
+    const double gamma = c.param_lambda * (1.0 - c.param_alpha);       // :74
+    a.use_gamma = gamma != 0.0;
+    a.gq[0] = (float)(gamma * c.sigma[3] / det); a.gq[1] = (float)(-gamma * c.sigma[1] / det);
+    a.gq[2] = (float)(-gamma * c.sigma[2] / det); a.gq[3] = (float)(gamma * c.sigma[0] / det);
+    const double l00 = std::sqrt(c.sigma[0]), l10 = c.sigma[2] / l00;
+    a.chol[0] = (float)l00; a.chol[1] = (float)l10; a.chol[2] = (float)std::sqrt(c.sigma[3] - l10 * l10);
+    a.inv_temp = (float)(1.0 / c.temperature);
+    refresh_obstacle_args(h, nullptr, 0);
+    a.U = h->d_U; a.idx = h->d_idx; a.M = h->d_M; a.part = h->d_part; a.ticket = h->d_ticket;
+    a.out = h->d_out; a.out_host = h->h_out_dev;
+    if (c.model == MPPI_MODEL_DIFFDRIVE_MLP) {
+        h->mlp = mlp_create(K, T);
+        if (!h->mlp) { mppi_destroy(h); return MPPI_E_CUDA; }
+    }
+#undef CKC
+    *out = h;
+    return MPPI_OK;
+}
+
+int mppi_destroy(mppi_handle_t h) {
+    if (!h) return MPPI_E_BADARG;
+    cudaSetDevice(h->cfg.device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
+    if (h->mlp) mlp_destroy(h->mlp);
+    cudaFree(h->d_path); cudaFree(h->d_U); cudaFree(h->d_M); cudaFree(h->d_S); cudaFree(h->d_part);
+    cudaFree(h->d_out); cudaFree(h->d_idx); cudaFree(h->d_ticket); cudaFree(h->d_first);
+    cudaFree(h->d_bp_n); cudaFree(h->d_bp_s); cudaFree(h->d_send); cudaFree(h->d_recv); cudaFree(h->d_x0);
+    if (h->h_out) cudaFreeHost(h->h_out);
+    if (h->h_first) cudaFreeHost(h->h_first);
+    for (auto &e : h->ev) if (e) cudaEventDestroy(e);
+    if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+    return MPPI_OK;
+}
+
+int mppi_set_stream(mppi_handle_t h, void *st) {
+    if (!h) return MPPI_E_BADARG;
+    if (h->own_stream && h->stream) { cudaStreamSynchronize(h->stream); cudaStreamDestroy(h->stream); }
+    h->stream = (cudaStream_t)st;
+    h->own_stream = false;
+    return MPPI_OK;
+}
+
+int mppi_synchronize(mppi_handle_t h) {
+    if (!h) return MPPI_E_BADARG;
+    CK(h, cudaStreamSynchronize(h->stream));
+    return MPPI_OK;
+}
+
+int mppi_set_ref_path(mppi_handle_t h, const double *path, int32_t n, int32_t ncol) {
+    if (!h || !path || n < 1 || (ncol != 3 && ncol != 4)) return MPPI_E_BADARG;
+    if (h->cfg.model == MPPI_MODEL_BICYCLE && ncol != 4) return fail(h, MPPI_E_BADARG, "bicycle model needs (N,4) path");
+    CK(h, cudaSetDevice(h->cfg.device));
+    CK(h, cudaStreamSynchronize(h->stream));
+    std::vector<float4> p((size_t)n);
+    for (int i = 0; i < n; ++i) {
+        const double *r = path + (size_t)i * ncol;
+        p[i] = make_float4((float)r[0], (float)r[1], (float)r[2], ncol == 4 ? (float)r[3] : 0.f);
+    }
+    cudaFree(h->d_path); h->d_path = nullptr;
+    cudaFree(h->d_bp_n); cudaFree(h->d_bp_s); h->d_bp_n = nullptr; h->d_bp_s = nullptr;
+    CK(h, cudaMalloc(&h->d_path, sizeof(float4) * n));
+    CK(h, cudaMemcpy(h->d_path, p.data(), sizeof(float4) * n, cudaMemcpyHostToDevice));
+    CK(h, cudaMalloc(&h->d_bp_n, sizeof(unsigned) * (n + 2)));
+    CK(h, cudaMalloc(&h->d_bp_s, sizeof(int) * (n + 2)));
+    h->path_h.assign(path, path + (size_t)n * ncol);
+    h->n_path = n; h->path_cols = ncol;
+    h->args.path = h->d_path; h->args.n_path = n;
+    h->have_path = true;
+    return MPPI_OK;
+}
+
+int mppi_set_obstacles(mppi_handle_t h, const double *xyr, int32_t m) {
+    if (!h || m < 0 || m > MPPI_MAX_OBSTACLES || (m > 0 && !xyr)) return MPPI_E_BADARG;
+    refresh_obstacle_args(h, xyr, m);
+    return MPPI_OK;
+}
+
+int mppi_set_nominal(mppi_handle_t h, const float *u) {
+    if (!h || !u) return MPPI_E_BADARG;
+    CK(h, cudaSetDevice(h->cfg.device));
+    CK(h, cudaMemcpyAsync(h->d_U, u, sizeof(float) * h->cfg.n_robots * h->cfg.T * 2, cudaMemcpyHostToDevice, h->stream));
+    CK(h, cudaStreamSynchronize(h->stream));
+    return MPPI_OK;
+}
+
+int mppi_get_nominal(mppi_handle_t h, float *u) {
+    if (!h || !u) return MPPI_E_BADARG;
+    CK(h, cudaSetDevice(h->cfg.device));
+    CK(h, cudaMemcpyAsync(u, h->d_U, sizeof(float) * h->cfg.n_robots * h->cfg.T * 2, cudaMemcpyDeviceToHost, h->stream));
+    CK(h, cudaStreamSynchronize(h->stream));
+    return MPPI_OK;
+}
+
+int mppi_set_waypoint_idx(mppi_handle_t h, const int32_t *idx) {
+    if (!h || !idx) return MPPI_E_BADARG;
+    CK(h, cudaSetDevice(h->cfg.device));
+    CK(h, cudaMemcpyAsync(h->d_idx, idx, sizeof(int) * h->cfg.n_robots, cudaMemcpyHostToDevice, h->stream));
+    CK(h, cudaStreamSynchronize(h->stream));
+    return MPPI_OK;
+}
+
+int mppi_get_waypoint_idx(mppi_handle_t h, int32_t *idx) {
+    if (!h || !idx) return MPPI_E_BADARG;
+    CK(h, cudaSetDevice(h->cfg.device));
+    CK(h, cudaMemcpyAsync(idx, h->d_idx, sizeof(int) * h->cfg.n_robots, cudaMemcpyDeviceToHost, h->stream));
+    CK(h, cudaStreamSynchronize(h->stream));
+    return MPPI_OK;
+}
+
+int mppi_set_mlp(mppi_handle_t h, const float *const W[4], const float *const b[4]) {
+    if (!h || !W || !b) return MPPI_E_BADARG;
+    if (!h->mlp) return fail(h, MPPI_E_STATE, "handle was not created with MPPI_MODEL_DIFFDRIVE_MLP");
+    CK(h, cudaSetDevice(h->cfg.device));
+    if (mlp_set_weights(h->mlp, W, b, h->stream) != cudaSuccess) return fail(h, MPPI_E_CUDA, "mlp_set_weights failed");
+    return MPPI_OK;
+}
+
+int mppi_set_timing(mppi_handle_t h, int32_t on) {
+    if (!h) return MPPI_E_BADARG;
+    h->timing = on != 0;
+    return MPPI_OK;
+}
+
+int mppi_get_timings(mppi_handle_t h, mppi_timings_t *out) {
+    if (!h || !out) return MPPI_E_BADARG;
+    *out = h->tm;
+    return MPPI_OK;
+}
+
+int mppi_get_stats(mppi_handle_t h, mppi_stats_t *out) {
+    if (!h || !out) return MPPI_E_BADARG;
+    float hdr[MPPI_OUT_HDR];
+    CK(h, cudaSetDevice(h->cfg.device));
+    CK(h, cudaMemcpyAsync(hdr, h->d_out, sizeof(hdr), cudaMemcpyDeviceToHost, h->stream));
+    CK(h, cudaStreamSynchronize(h->stream));
+    out->rho = hdr[3]; std::memcpy(&out->min_collisions, &hdr[4], 4);
+    out->eta = hdr[5]; out->ess = hdr[6]; std::memcpy(&out->idx, &hdr[2], 4);
+    return MPPI_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+static void set_x0(mppi_handle_t h, const double *x0) {
+    for (int i = 0; i < 4; ++i) h->args.x0[i] = i < h->nx ? (float)x0[i] : 0.f;
+}
+
+static void set_seed(mppi_handle_t h, uint64_t seed, uint64_t tick) {
+    h->args.seed_lo = (uint32_t)seed; h->args.seed_hi = (uint32_t)(seed >> 32);
+    h->args.tick = (uint32_t)tick;
+}
+
+static int host_nearest(mppi_handle_t h, int s, double x, double y) {
+    // literal FP64 step 1 (mppi_differential_drive.py:96 -> :201-220), first minimum
+    const int end = std::min(s + h->cfg.window, h->n_path);
+    int best = s;
+    double bd = INFINITY;
+    for (int j = s; j < end; ++j) {
+        const double dx = x - h->path_h[(size_t)j * h->path_cols], dy = y - h->path_h[(size_t)j * h->path_cols + 1];
+        const double d = dx * dx + dy * dy;
+        if (d < bd) { bd = d; best = j; }
+    }
+    return best;
+}
+
+// Strict waypoint mode: host-driven multi-pass rollout.  Leaves the costs
+// in d_S (or dS_user) and returns the index after the tick.
+static int strict_costs(mppi_handle_t h, const double *x0, const float *d_eps, float *dS, int *idx_after) {
+    int idx0 = 0;
+    CK(h, cudaMemcpyAsync(&idx0, h->d_idx, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CK(h, cudaStreamSynchronize(h->stream));
+    const int s0 = host_nearest(h, idx0, x0[0], x0[1]);
+    std::vector<unsigned> bpn{0u};
+    std::vector<int> bps{s0};
+    TickArgs a = h->args;
+    a.S = dS; a.eps = d_eps;
+    const int T = h->cfg.T;
+    int k_first = 0;
+    unsigned check_from = 0;
+    int passes = 0;
+    const unsigned long long none = ~0ull;
+    while (true) {
+        CK(h, cudaMemcpyAsync(h->d_bp_n, bpn.data(), sizeof(unsigned) * bpn.size(), cudaMemcpyHostToDevice, h->stream));
+        CK(h, cudaMemcpyAsync(h->d_bp_s, bps.data(), sizeof(int) * bps.size(), cudaMemcpyHostToDevice, h->stream));
+        CK(h, cudaMemcpyAsync(h->d_first, &none, sizeof(none), cudaMemcpyHostToDevice, h->stream));
+        CK(h, mppi_launch_strict(a, h->cfg.model, h->cfg.collision, h->sum, d_eps != nullptr, h->d_bp_n, h->d_bp_s,
+                                 (int)bpn.size(), k_first, check_from, h->d_first, h->stream));
+        h->tm.launches++;
+        CK(h, cudaMemcpyAsync(h->h_first, h->d_first, sizeof(none), cudaMemcpyDeviceToHost, h->stream));
+        CK(h, cudaStreamSynchronize(h->stream));
+        ++passes;
+        const unsigned long long fc = *h->h_first;
+        if (fc == none) break;
+        const unsigned n_star = (unsigned)(fc >> 32);
+        const int s_new = (int)(fc & 0xffffffffu);
+        bpn.push_back(n_star + 1); bps.push_back(s_new);
+        check_from = n_star + 1;
+        k_first = (int)(check_from / (unsigned)(T + 1));
+        if ((int)bpn.size() > h->n_path + 1) return fail(h, MPPI_E_STATE, "strict mode: too many index changes");
+        if (k_first >= h->cfg.K) break;
+    }
+    h->tm.last_passes = passes;
+    *idx_after = bps.back();
+    return MPPI_OK;
+}
+
+static int launch_update(mppi_handle_t h, const TickArgs &a, bool inj) {
+    dim3 grid(h->grid_x, h->cfg.n_robots);
+    if (h->world > 1 && (a.flags & F_UPDATE)) {
+        TickArgs b = a;
+        b.flags |= F_TRIPLE_OUT;
+        b.triple_out = h->d_send;
+        CK(h, mppi_launch_tick(b, h->cfg.model, h->cfg.collision, h->sum, inj, grid, h->stream));
+        const size_t nf = MPPI_NF(h->cfg.T);
+        ncclResult_t r = g_nccl.AllGather(h->d_send, h->d_recv, nf, ncclFloat, h->comm, h->stream);
+        if (r != ncclSuccess) { h->err = g_nccl.GetErrorString(r); return MPPI_E_NCCL; }
+        CK(h, mppi_launch_merge(a, h->d_recv, h->world, h->stream));
+        h->tm.launches += 2;
+        return MPPI_OK;
+    }
+    CK(h, mppi_launch_tick(a, h->cfg.model, h->cfg.collision, h->sum, inj, grid, h->stream));
+    h->tm.launches++;
+    return MPPI_OK;
+}
+
+static int step_common(mppi_handle_t h, const double *x0, const float *d_eps, uint64_t seed, uint64_t tick, bool sync_out,
+                       float *u0_out, float *useq_out) {
+    if (!h || !x0) return MPPI_E_BADARG;
+    if (!h->have_path) return fail(h, MPPI_E_STATE, "mppi_set_ref_path has not been called");
+    if (h->cfg.n_robots != 1) return fail(h, MPPI_E_BADARG, "use mppi_step_batched for n_robots > 1");
+    CK(h, cudaSetDevice(h->cfg.device));
+    set_x0(h, x0);
+    set_seed(h, seed, tick);
+    if (h->timing) CK(h, cudaEventRecord(h->ev[0], h->stream));
+    if (h->mlp) {
+        int rc = mlp_rollout_costs(h->mlp, h->args, d_eps, h->d_S, h->stream);
+        if (rc != 0) return fail(h, MPPI_E_CUDA, "MLP rollout failed");
+        h->tm.launches += mlp_launches_per_tick(h->mlp);
+        if (h->timing) CK(h, cudaEventRecord(h->ev[1], h->stream));
+        TickArgs a = h->args;
+        a.S = h->d_S; a.eps = d_eps;
+        a.flags = F_UPDATE | F_FROM_S | F_KEEP_IDX | F_HOST_IDX;      // the MLP rollout persisted the index
+        a.idx_host = 0;
+        int rc2 = launch_update(h, a, d_eps != nullptr);
+        if (rc2 != MPPI_OK) return rc2;
+    } else if (h->strict) {
+        int idx_after = 0;
+        int rc = strict_costs(h, x0, d_eps, h->d_S, &idx_after);
+        if (rc != MPPI_OK) return rc;
+        if (h->timing) CK(h, cudaEventRecord(h->ev[1], h->stream));
+        TickArgs a = h->args;
+        a.S = h->d_S; a.eps = d_eps;
+        a.flags = F_UPDATE | F_FROM_S | F_HOST_IDX;
+        a.idx_host = idx_after;
+        rc = launch_update(h, a, d_eps != nullptr);
+        if (rc != MPPI_OK) return rc;
+    } else {
+        TickArgs a = h->args;
+        a.eps = d_eps; a.S = nullptr;
+        a.flags = F_UPDATE;
+        if (h->timing) CK(h, cudaEventRecord(h->ev[1], h->stream));
+        int rc = launch_update(h, a, d_eps != nullptr);
+        if (rc != MPPI_OK) return rc;
+    }
+    if (h->timing) CK(h, cudaEventRecord(h->ev[2], h->stream));
+    if (sync_out || h->timing) {
+        CK(h, cudaStreamSynchronize(h->stream));
+        if (h->timing) {
+            cudaEventElapsedTime(&h->tm.last_step_ms, h->ev[0], h->ev[2]);
+            cudaEventElapsedTime(&h->tm.last_rollout_ms, h->ev[0], h->ev[1]);
+            cudaEventElapsedTime(&h->tm.last_update_ms, h->ev[1], h->ev[2]);
+        }
+        if (u0_out) { u0_out[0] = h->h_out[0]; u0_out[1] = h->h_out[1]; }
+        if (useq_out) std::memcpy(useq_out, h->h_out + MPPI_OUT_HDR, sizeof(float) * 2 * h->cfg.T);
+    }
+    return MPPI_OK;
+}
+
+int mppi_step(mppi_handle_t h, const double *x0, const float *d_eps, uint64_t seed, uint64_t tick,
+              float *u0_out, float *useq_out) {
+    return step_common(h, x0, d_eps, seed, tick, true, u0_out, useq_out);
+}
+
+int mppi_step_async(mppi_handle_t h, const double *x0, const float *d_eps, uint64_t seed, uint64_t tick) {
+    return step_common(h, x0, d_eps, seed, tick, false, nullptr, nullptr);
+}
+
+int mppi_rollout_costs(mppi_handle_t h, const double *x0, const float *d_eps, uint64_t seed, uint64_t tick, float *d_S) {
+    if (!h || !x0 || !d_S) return MPPI_E_BADARG;
+    if (!h->have_path) return fail(h, MPPI_E_STATE, "mppi_set_ref_path has not been called");
+    if (h->cfg.n_robots != 1) return MPPI_E_BADARG;
+    CK(h, cudaSetDevice(h->cfg.device));
+    set_x0(h, x0);
+    set_seed(h, seed, tick);
+    if (h->mlp) {
+        if (mlp_rollout_costs(h->mlp, h->args, d_eps, d_S, h->stream) != 0) return fail(h, MPPI_E_CUDA, "MLP rollout failed");
+        h->tm.launches += mlp_launches_per_tick(h->mlp);
+    } else if (h->strict) {
+        int idx_after = 0;
+        int rc = strict_costs(h, x0, d_eps, d_S, &idx_after);
+        if (rc != MPPI_OK) return rc;
+        CK(h, cudaMemcpyAsync(h->d_idx, &idx_after, sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    } else {
+        TickArgs a = h->args;
+        a.eps = d_eps; a.S = d_S; a.flags = F_WRITE_S;
+        dim3 grid(h->grid_x, 1);
+        CK(h, mppi_launch_tick(a, h->cfg.model, h->cfg.collision, h->sum, d_eps != nullptr, grid, h->stream));
+        h->tm.launches++;
+    }
+    CK(h, cudaStreamSynchronize(h->stream));
+    return MPPI_OK;
+}
+
+int mppi_reduce_update(mppi_handle_t h, const float *d_S, const float *d_eps, uint64_t seed, uint64_t tick,
+                       float *u0_out, float *useq_out, float *w_eps_out) {
+    if (!h || !d_S) return MPPI_E_BADARG;
+    if (!h->have_path) return fail(h, MPPI_E_STATE, "mppi_set_ref_path has not been called");
+    if (h->cfg.n_robots != 1) return MPPI_E_BADARG;
+    CK(h, cudaSetDevice(h->cfg.device));
+    set_seed(h, seed, tick);
+    TickArgs a = h->args;
+    a.eps = d_eps; a.S = const_cast<float *>(d_S);
+    a.flags = F_UPDATE | F_FROM_S | F_KEEP_IDX | F_HOST_IDX;
+    a.idx_host = 0;
+    int rc = launch_update(h, a, d_eps != nullptr);
+    if (rc != MPPI_OK) return rc;
+    CK(h, cudaStreamSynchronize(h->stream));
+    if (u0_out) { u0_out[0] = h->h_out[0]; u0_out[1] = h->h_out[1]; }
+    if (useq_out) std::memcpy(useq_out, h->h_out + MPPI_OUT_HDR, sizeof(float) * 2 * h->cfg.T);
+    if (w_eps_out) std::memcpy(w_eps_out, h->h_out + MPPI_OUT_HDR + 2 * MPPI_MAX_T, sizeof(float) * 2 * h->cfg.T);
+    return MPPI_OK;
+}
+
+int mppi_generate_noise(mppi_handle_t h, uint64_t seed, uint64_t tick, float *d_eps_out) {
+    if (!h || !d_eps_out) return MPPI_E_BADARG;
+    CK(h, cudaSetDevice(h->cfg.device));
+    set_seed(h, seed, tick);
+    CK(h, mppi_launch_noise(h->args, d_eps_out, 0, h->stream));
+    h->tm.launches++;
+    CK(h, cudaStreamSynchronize(h->stream));
+    return MPPI_OK;
+}
+
+int mppi_step_batched(mppi_handle_t h, const float *d_x0, uint64_t seed, uint64_t tick, float *d_u0_out) {
+    if (!h || !d_x0) return MPPI_E_BADARG;
+    if (!h->have_path) return fail(h, MPPI_E_STATE, "mppi_set_ref_path has not been called");
+    if (h->strict || h->mlp) return MPPI_E_UNSUPPORTED;
+    CK(h, cudaSetDevice(h->cfg.device));
+    set_seed(h, seed, tick);
+    TickArgs a = h->args;
+    // (R, nx) -> padded (R, 4) staging so every robot's state is one aligned read
+    if (!h->d_x0) CK(h, cudaMalloc(&h->d_x0, sizeof(float) * 4 * h->cfg.n_robots));
+    CK(h, cudaMemcpy2DAsync(h->d_x0, 4 * sizeof(float), d_x0, h->nx * sizeof(float), h->nx * sizeof(float),
+                            h->cfg.n_robots, cudaMemcpyDeviceToDevice, h->stream));
+    a.x0_dev = h->d_x0; a.eps = nullptr; a.S = nullptr; a.flags = F_UPDATE; a.u0_out = d_u0_out;
+    a.out_host = nullptr;
+    dim3 grid(h->grid_x, h->cfg.n_robots);
+    CK(h, mppi_launch_tick(a, h->cfg.model, h->cfg.collision, h->sum, false, grid, h->stream));
+    h->tm.launches++;
+    return MPPI_OK;
+}
+
+int mppi_comm_get_unique_id(void *out128) {
+    if (!out128) return MPPI_E_BADARG;
+    if (!g_nccl.load()) return MPPI_E_NCCL;
+    ncclUniqueId id;
+    if (g_nccl.GetUniqueId(&id) != ncclSuccess) return MPPI_E_NCCL;
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+    std::memcpy(out128, &id, 128);
+    return MPPI_OK;
+}
+
+int mppi_comm_init(mppi_handle_t h, const void *uid, int32_t rank, int32_t world) {
+    if (!h || !uid || world < 1 || rank < 0 || rank >= world) return MPPI_E_BADARG;
+    if (h->cfg.n_robots != 1 || h->strict) return fail(h, MPPI_E_UNSUPPORTED, "sample sharding needs frozen mode, one robot");
+    if (!g_nccl.load()) return fail(h, MPPI_E_NCCL, "cannot load libnccl.so.2");
+    CK(h, cudaSetDevice(h->cfg.device));
+    ncclUniqueId id;
+    std::memcpy(&id, uid, 128);
+    ncclResult_t r = g_nccl.CommInitRank(&h->comm, world, id, rank);
+    if (r != ncclSuccess) { h->err = g_nccl.GetErrorString(r); return MPPI_E_NCCL; }
+    h->rank = rank; h->world = world;
+    const size_t nf = MPPI_NF(h->cfg.T);
+    CK(h, cudaMalloc(&h->d_send, sizeof(float) * nf));
+    CK(h, cudaMalloc(&h->d_recv, sizeof(float) * nf * world));
+    return MPPI_OK;
+}
+
+}  // extern "C"

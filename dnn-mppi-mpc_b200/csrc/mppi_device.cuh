@@ -1,0 +1,275 @@
+// Device-side building blocks of the MPPI tick for sm_100a: Philox noise, dynamics steps,
+// nearest-waypoint search, state costs, collision tests.  Reference semantics (file:line
+// relative to the reference tree) are cited per function; SURVEY.md Appendix A is the spec.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <math_constants.h>
+#include "../../include/mppi_b200.h"
+
+#define MPPI_BLOCK 256
+#define MPPI_WARPS (MPPI_BLOCK / 32)
+#define MPPI_PENALTY 1.0e10f           // mppi_race_car_obstacle.py:157
+#define MPPI_SENTINEL 1.0e18f          // padded window entries: distance^2 = 1e36, never the minimum
+#define MPPI_OUT_HDR 8
+#define MPPI_OUT_STRIDE (MPPI_OUT_HDR + 4 * MPPI_MAX_T)
+#define MPPI_NF(T) (4 + 2 * (T))       // floats per partial: ncoll_min, smooth_min, eta, sum w^2, N[T][2]
+
+enum : int {
+    F_WRITE_S = 1,       // store per-sample costs
+    F_UPDATE = 2,        // weights + weighted noise + merge
+    F_FROM_S = 4,        // skip the rollout, read costs from S_in (K2 alone)
+    F_HOST_IDX = 8,      // skip step 1, window starts at idx_host
+    F_TRIPLE_OUT = 16,   // multi-GPU: publish the merged per-GPU triple, do not finalize
+    F_KEEP_IDX = 32      // do not persist the waypoint index (K2 alone)
+};
+
+// Everything a tick needs, passed by value (kernel parameter = constant bank).
+struct TickArgs {
+    // static configuration
+    int K, T, window, n_path, n_obs, yaw_wrap, use_gamma;
+    int k_offset, n_exploit;          // global sample index of local sample 0; Q6 threshold on the global index
+    float dt, dt_over_L, umax0, umax1;
+    float sw[4], tw[4];
+    float gq[4];                      // gamma * Sigma^-1, row-major
+    float chol[3];                    // L00, L10, L11 of Sigma = L L^T
+    float inv_temp;
+    float obs_x[MPPI_MAX_OBSTACLES], obs_y[MPPI_MAX_OBSTACLES];
+    float obs_r2[MPPI_MAX_OBSTACLES];     // collision radius^2: r^2 (footprint) or (r_robot*margin + r)^2 (circle)
+    float obs_far2[MPPI_MAX_OBSTACLES];   // footprint quick reject: (half diagonal + r)^2, inflated
+    float fp_hl, fp_hw;                   // footprint half length / half width incl. margin
+    // per tick
+    float x0[4];
+    uint32_t seed_lo, seed_hi, tick;
+    int idx_host, flags;
+    // pointers (device)
+    const float4 *path;               // [n_path] (x, y, yaw, v)
+    const float *x0_dev;              // batched: [R][4], else null
+    float *U;                         // [R][T][2] nominal, updated in place
+    int *idx;                         // [R] carried waypoint index
+    const float *M;                   // [T][T] filter operator
+    const float *eps;                 // injected noise (K,T,2) or null
+    float *S;                         // [R][K] costs out (F_WRITE_S) / in (F_FROM_S)
+    float *part;                      // [R][B][NF]
+    unsigned *ticket;                 // [R]
+    float *out;                       // [R][MPPI_OUT_STRIDE]
+    float *out_host;                  // mapped pinned mirror of out (robot 0) or null
+    float *u0_out;                    // batched: [R][2] or null
+    float *triple_out;                // [NF] per-GPU triple (F_TRIPLE_OUT)
+};
+
+// ------------------------------------------------------------------------------------------
+// Philox4x32-10 (Salmon et al. SC'11) + Box-Muller.  Replaces np.random.multivariate_normal
+// in _calc_epsilon (mppi_differential_drive.py:273-283).  Spec: oracle/mppi_oracle.py:philox_noise.
+//   counter = (global sample k, timestep pair t/2, tick, robot), key = seed
+//   u_i = ((r_i >> 9) + 0.5) * 2^-23  in (0,1);  z = sqrt(-2 ln u_a) * (cos, sin)(2 pi u_b)
+//   outputs (r0,r1) -> timestep 2p, (r2,r3) -> timestep 2p+1;  eps = chol(Sigma) z
+// All float ops use explicit-rounding intrinsics so every kernel produces identical bits.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void philox4x32_10(uint32_t &c0, uint32_t &c1, uint32_t &c2, uint32_t &c3,
+                                              uint32_t k0, uint32_t k1) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t h0 = __umulhi(0xD2511F53u, c0), l0 = 0xD2511F53u * c0;
+        const uint32_t h1 = __umulhi(0xCD9E8D57u, c2), l1 = 0xCD9E8D57u * c2;
+        c0 = h1 ^ c1 ^ k0; c1 = l1;
+        c2 = h0 ^ c3 ^ k1; c3 = l0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+}
+
+__device__ __forceinline__ float u01_open(uint32_t r) {
+    // ((r >> 9) + 0.5) * 2^-23, exact: [1,2) mantissa trick minus (1 - 2^-24)
+    return __fadd_rn(__uint_as_float(0x3f800000u | (r >> 9)), -0.99999994f);
+}
+
+__device__ __forceinline__ void box_muller(uint32_t ra, uint32_t rb, float &z0, float &z1) {
+    const float ua = u01_open(ra), ub = u01_open(rb);
+    const float rad = __fsqrt_rn(__fmul_rn(-1.3862943611198906f, __log2f(ua)));   // sqrt(-2 ln ua)
+    const float ang = __fmul_rn(6.2831853071795865f, ub);
+    z0 = __fmul_rn(rad, __cosf(ang));
+    z1 = __fmul_rn(rad, __sinf(ang));
+}
+
+// eps for timesteps 2p (e[0],e[1]) and 2p+1 (e[2],e[3]) of global sample k
+__device__ __forceinline__ void philox_eps_pair(const TickArgs &a, uint32_t k, uint32_t p, uint32_t robot, float e[4]) {
+    uint32_t c0 = k, c1 = p, c2 = a.tick, c3 = robot;
+    philox4x32_10(c0, c1, c2, c3, a.seed_lo, a.seed_hi);
+    float z0, z1, z2, z3;
+    box_muller(c0, c1, z0, z1);
+    box_muller(c2, c3, z2, z3);
+    e[0] = __fmul_rn(a.chol[0], z0);
+    e[1] = __fmaf_rn(a.chol[1], z0, __fmul_rn(a.chol[2], z1));
+    e[2] = __fmul_rn(a.chol[0], z2);
+    e[3] = __fmaf_rn(a.chol[1], z2, __fmul_rn(a.chol[2], z3));
+}
+
+// ------------------------------------------------------------------------------------------
+// shared-memory view of one robot's tick constants
+// ------------------------------------------------------------------------------------------
+struct TickSmem {
+    float2 U[MPPI_MAX_T];                  // nominal
+    float2 Q[MPPI_MAX_T];                  // gamma * Sigma^-1 applied to U[t] (row vector u^T Sigma^-1)
+    __align__(16) float wx[MPPI_MAX_WINDOW];   // window SoA, padded with sentinels to a multiple of 4
+    __align__(16) float wy[MPPI_MAX_WINDOW];
+    float4 wref[MPPI_MAX_WINDOW];          // (x, y, yaw, v) for the lookup after the argmin
+    float x0[4];
+    int win_start, n_win4;                 // absolute index of window entry 0; padded length / 4
+};
+
+// A8: first-min argmin of squared xy distance over the window
+// (mppi_differential_drive.py:201-220, mppi_race_car_obstacle.py:173-191).
+template <int WIN>
+__device__ __forceinline__ int nearest_wp(const TickSmem &sm, float x, float y) {
+    const float4 *wx4 = reinterpret_cast<const float4 *>(sm.wx);
+    const float4 *wy4 = reinterpret_cast<const float4 *>(sm.wy);
+    float bd = CUDART_INF_F;
+    int bj = 0;
+    const int n4 = WIN > 0 ? WIN / 4 : sm.n_win4;
+#pragma unroll
+    for (int q = 0; q < n4; ++q) {
+        const float4 X = wx4[q], Y = wy4[q];
+        float dx, dy, d;
+        dx = x - X.x; dy = y - Y.x; d = dx * dx + dy * dy; if (d < bd) { bd = d; bj = 4 * q; }
+        dx = x - X.y; dy = y - Y.y; d = dx * dx + dy * dy; if (d < bd) { bd = d; bj = 4 * q + 1; }
+        dx = x - X.z; dy = y - Y.z; d = dx * dx + dy * dy; if (d < bd) { bd = d; bj = 4 * q + 2; }
+        dx = x - X.w; dy = y - Y.w; d = dx * dx + dy * dy; if (d < bd) { bd = d; bj = 4 * q + 3; }
+    }
+    return bj;
+}
+
+// exact (yaw + 2pi) mod 2pi with the sign of the divisor (race-car :151): the FMA remainder
+// of a correctly chosen quotient is exactly representable, so this equals fmodf + fix-up.
+__device__ __forceinline__ float wrap_2pi(float yaw) {
+    const float b = 6.2831855f;
+    const float y2 = yaw + b;
+    const float q = floorf(y2 * 0.15915494f);
+    float r = fmaf(-q, b, y2);
+    if (r < 0.f) r += b;
+    if (r >= b) r -= b;
+    return r;
+}
+
+// A10: collision tests.  Returns true if the state collides with any obstacle.
+template <int MODEL, int COLL>
+__device__ __forceinline__ bool collided(const TickArgs &a, float x, float y, float cs, float sn) {
+    bool hit = false;
+    if constexpr (COLL == MPPI_COLLISION_NONE) {
+        return false;
+    } else if constexpr (COLL == MPPI_COLLISION_CIRCLE) {        // mppi_differential_drive_obs.py:301-313
+        for (int m = 0; m < a.n_obs; ++m) {
+            const float dx = x - a.obs_x[m], dy = y - a.obs_y[m];
+            hit |= (dx * dx + dy * dy < a.obs_r2[m]);
+        }
+        return hit;
+    } else {
+    // footprint: 8 perimeter points of the (l*margin) x (w*margin) box rotated by the raw yaw
+    // (mppi_race_car_obstacle.py:255-274)
+    for (int m = 0; m < a.n_obs; ++m) {
+        const float ox = a.obs_x[m], oy = a.obs_y[m];
+        const float cx = x - ox, cy = y - oy;
+        if (cx * cx + cy * cy >= a.obs_far2[m]) continue;      // conservative reject
+        const float r2 = a.obs_r2[m];
+        const float ac = a.fp_hl * cs, as = a.fp_hl * sn, bc = a.fp_hw * cs, bs = a.fp_hw * sn;
+        float px, py;
+        px = cx - ac;      py = cy - as;      hit |= (px * px + py * py < r2);   // (-hl, 0)
+        px = cx - ac - bs; py = cy - as + bc; hit |= (px * px + py * py < r2);   // (-hl, +hw)
+        px = cx - bs;      py = cy + bc;      hit |= (px * px + py * py < r2);   // (0, +hw)
+        px = cx + ac - bs; py = cy + as + bc; hit |= (px * px + py * py < r2);   // (+hl, +hw)
+        px = cx + ac;      py = cy + as;      hit |= (px * px + py * py < r2);   // (+hl, 0)
+        px = cx + ac + bs; py = cy + as - bc; hit |= (px * px + py * py < r2);   // (+hl, -hw)
+        px = cx + bs;      py = cy - bc;      hit |= (px * px + py * py < r2);   // (0, -hw)
+        px = cx - ac + bs; py = cy - as - bc; hit |= (px * px + py * py < r2);   // (-hl, -hw)
+    }
+    return hit;
+    }
+}
+
+// A9: weighted squared error to a waypoint (mppi_differential_drive.py:222-249; race-car :147-171)
+template <int MODEL>
+__device__ __forceinline__ float tracking_cost(const float4 ref, const float z[4], float yaw_eff, const float w[4]) {
+    const float dx = z[0] - ref.x, dy = z[1] - ref.y, dyaw = yaw_eff - ref.z;
+    float c = w[0] * dx * dx + w[1] * dy * dy + w[2] * dyaw * dyaw;
+    if (MODEL == MPPI_MODEL_BICYCLE) { const float dv = z[3] - ref.w; c += w[3] * dv * dv; }
+    return c;
+}
+
+// A6 / A7: explicit-Euler dynamics; (cs, sn) = cos/sin of the CURRENT heading.
+template <int MODEL>
+__device__ __forceinline__ void dyn_step(const TickArgs &a, float z[4], float v0, float v1, float cs, float sn) {
+    if (MODEL == MPPI_MODEL_BICYCLE) {          // mppi_race_car_obstacle.py:200-214, v = [steer, accel]
+        const float vel = z[3];
+        z[0] += vel * cs * a.dt;
+        z[1] += vel * sn * a.dt;
+        z[2] += vel * a.dt_over_L * tanf(v0);
+        z[3] += v1 * a.dt;
+    } else {                                    // mppi_differential_drive.py:182-198
+        z[0] += v0 * cs * a.dt;
+        z[1] += v0 * sn * a.dt;
+        z[2] += v1 * a.dt;
+    }
+}
+
+__device__ __forceinline__ float clampf(float v, float lim) { return fminf(fmaxf(v, -lim), lim); }
+
+// One sample's rollout (frozen window).  Returns the smooth cost and the number of collided
+// evaluations separately so 1e10 * n never swallows the tracking cost.
+template <int MODEL, int COLL, bool SUM, bool INJ, int WIN>
+__device__ __forceinline__ void rollout_sample(const TickArgs &a, const TickSmem &sm, uint32_t kg, int klocal,
+                                               uint32_t robot, bool exploit, float &smooth, int &ncoll) {
+    const int T = a.T;
+    float z[4] = {sm.x0[0], sm.x0[1], sm.x0[2], sm.x0[3]};
+    float cs, sn;
+    sincosf(z[2], &sn, &cs);
+    float acc = 0.f;
+    int nc = 0;
+    float v0 = 0.f, v1 = 0.f;
+    const float2 *eps_k = INJ ? reinterpret_cast<const float2 *>(a.eps) + (size_t)klocal * T : nullptr;
+    for (int tp = 0; tp < T; tp += 2) {
+        float e[4];
+        if (INJ) {
+            const float2 ea = eps_k[tp];
+            e[0] = ea.x; e[1] = ea.y;
+            if (tp + 1 < T) { const float2 eb = eps_k[tp + 1]; e[2] = eb.x; e[3] = eb.y; }
+        } else {
+            philox_eps_pair(a, kg, (uint32_t)(tp >> 1), robot, e);
+        }
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int t = tp + h;
+            if (t < T) {
+                const float2 u = sm.U[t];
+                v0 = clampf(exploit ? __fadd_rn(u.x, e[2 * h]) : e[2 * h], a.umax0);       // A4, A5
+                v1 = clampf(exploit ? __fadd_rn(u.y, e[2 * h + 1]) : e[2 * h + 1], a.umax1);
+                dyn_step<MODEL>(a, z, v0, v1, cs, sn);
+                sincosf(z[2], &sn, &cs);
+                if (SUM) {
+                    const int j = nearest_wp<WIN>(sm, z[0], z[1]);
+                    const float4 ref = sm.wref[j];
+                    const float yaw_eff = a.yaw_wrap ? wrap_2pi(z[2]) : z[2];
+                    float c = tracking_cost<MODEL>(ref, z, yaw_eff, a.sw);
+                    if (a.use_gamma) { const float2 q = sm.Q[t]; c += q.x * v0 + q.y * v1; }
+                    const bool hit = collided<MODEL, COLL>(a, z[0], z[1], cs, sn);
+                    if (t == T - 1) {           // terminal cost: same state, same waypoint (A9)
+                        c += tracking_cost<MODEL>(ref, z, yaw_eff, a.tw);
+                        nc += hit ? 2 : 0;
+                    } else {
+                        nc += hit ? 1 : 0;
+                    }
+                    acc += c;
+                }
+            }
+        }
+    }
+    if (!SUM) {                                 // Q1: only the last stage cost survives, plus terminal
+        const int j = nearest_wp<WIN>(sm, z[0], z[1]);
+        const float4 ref = sm.wref[j];
+        const float yaw_eff = a.yaw_wrap ? wrap_2pi(z[2]) : z[2];
+        acc = tracking_cost<MODEL>(ref, z, yaw_eff, a.sw);
+        if (a.use_gamma) { const float2 q = sm.Q[T - 1]; acc += q.x * v0 + q.y * v1; }
+        acc += tracking_cost<MODEL>(ref, z, yaw_eff, a.tw);
+        nc = collided<MODEL, COLL>(a, z[0], z[1], cs, sn) ? 2 : 0;
+    }
+    smooth = acc;
+    ncoll = nc;
+}

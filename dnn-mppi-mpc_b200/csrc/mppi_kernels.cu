@@ -1,0 +1,481 @@
+// sm_100a kernels of the MPPI tick.
+//   mppi_tick_kernel   K1+K2 fused: step-1 index update, Philox noise, K x T rollout with state in
+//                      registers, costs, block-local soft-min, weighted-noise reduction, last-block
+//                      log-sum-exp merge, filter, nominal update and shift -- one launch per tick.
+//   mppi_strict_kernel literal waypoint-index mutation (quirk Q3) by the multi-pass rule.
+//   mppi_merge_kernel  merge of per-GPU triples after the all-gather + finalize.
+//   mppi_noise_kernel  exports the exact Philox noise tensor.
+#include "mppi_device.cuh"
+#include "mppi_launch.h"
+
+namespace {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// lexicographic (ncoll, smooth) minimum over a warp
+__device__ __forceinline__ void warp_lexmin(int &n, float &s) {
+    const int nmin = __reduce_min_sync(0xffffffffu, n);
+    float c = (n == nmin) ? s : CUDART_INF_F;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c = fminf(c, __shfl_xor_sync(0xffffffffu, c, o));
+    n = nmin; s = c;
+}
+
+// exp(-((n - n0) * 1e10 + (s - s0)) / temperature): the weight of a (ncoll, smooth) cost
+// relative to the reference cost (n0, s0), with the collision penalty kept out of the float sum.
+__device__ __forceinline__ float rel_weight(int n, float s, int n0, float s0, float inv_temp) {
+    const float d = (float)(n - n0) * MPPI_PENALTY + (s - s0);
+    return __expf(-d * inv_temp);
+}
+
+struct MergeSmem {
+    float red_s[MPPI_WARPS];
+    int red_n[MPPI_WARPS];
+    float col[4 + 2 * MPPI_MAX_T];      // merged triple (same layout as a partial)
+    float weps[2 * MPPI_MAX_T];
+    float upre[2 * MPPI_MAX_T];
+};
+
+// Merges P partials (layout MPPI_NF) into ms.col by the log-sum-exp rule of SURVEY.md 8e.
+__device__ void merge_partials(const TickArgs &a, const float *parts, int P, MergeSmem &ms) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int NF = MPPI_NF(a.T);
+    int n = INT_MAX;
+    float s = CUDART_INF_F;
+    for (int p = tid; p < P; p += MPPI_BLOCK) {
+        const int pn = __float_as_int(parts[(size_t)p * NF]);
+        const float ps = parts[(size_t)p * NF + 1];
+        if (pn < n || (pn == n && ps < s)) { n = pn; s = ps; }
+    }
+    warp_lexmin(n, s);
+    if (lane == 0) { ms.red_n[warp] = n; ms.red_s[warp] = s; }
+    __syncthreads();
+    n = ms.red_n[0]; s = ms.red_s[0];
+#pragma unroll
+    for (int w = 1; w < MPPI_WARPS; ++w) {
+        const int wn = ms.red_n[w]; const float ws = ms.red_s[w];
+        if (wn < n || (wn == n && ws < s)) { n = wn; s = ws; }
+    }
+    for (int c = 2 + tid; c < NF; c += MPPI_BLOCK) {
+        float acc = 0.f;
+        for (int p = 0; p < P; ++p) {
+            const float *pp = parts + (size_t)p * NF;
+            float sc = rel_weight(__float_as_int(pp[0]), pp[1], n, s, a.inv_temp);
+            if (c == 3) sc *= sc;                       // sum of squared weights scales with sc^2
+            acc += sc * pp[c];
+        }
+        ms.col[c] = acc;
+    }
+    if (tid == 0) { ms.col[0] = __int_as_float(n); ms.col[1] = s; }
+    __syncthreads();
+}
+
+// A13-A15 + Q8 from the merged triple in ms.col: normalise, filter, update, shift, publish.
+__device__ void finalize_tick(const TickArgs &a, int robot, int idx_new, MergeSmem &ms) {
+    const int tid = threadIdx.x, T = a.T;
+    const float eta = ms.col[2];
+    const float inv_eta = 1.f / eta;
+    float *U = a.U + (size_t)robot * T * 2;
+    float *out = a.out + (size_t)robot * MPPI_OUT_STRIDE;
+    for (int c = tid; c < 2 * T; c += MPPI_BLOCK) ms.weps[c] = ms.col[4 + c] * inv_eta;
+    __syncthreads();
+    for (int c = tid; c < 2 * T; c += MPPI_BLOCK) {
+        const int n = c >> 1, u = c & 1;
+        const float *Mrow = a.M + (size_t)n * T;
+        float f = 0.f;
+        for (int m = 0; m < T; ++m) f += Mrow[m] * ms.weps[2 * m + u];
+        ms.upre[c] = U[c] + f;                          // u += w_epsilon (:141)
+    }
+    __syncthreads();
+    float *oh = (robot == 0) ? a.out_host : nullptr;
+    for (int c = tid; c < 2 * T; c += MPPI_BLOCK) {
+        const int n = c >> 1, u = c & 1;
+        const float v = ms.upre[2 * (n + 1 < T ? n + 1 : T - 1) + u];      // shift, last row kept (:162-163)
+        U[c] = v;
+        out[MPPI_OUT_HDR + c] = v;
+        out[MPPI_OUT_HDR + 2 * MPPI_MAX_T + c] = ms.weps[c];
+        if (oh) { oh[MPPI_OUT_HDR + c] = v; oh[MPPI_OUT_HDR + 2 * MPPI_MAX_T + c] = ms.weps[c]; }
+    }
+    if (tid == 0) {
+        const float u0x = ms.upre[2 * (1 < T ? 1 : 0)], u0y = ms.upre[2 * (1 < T ? 1 : 0) + 1];   // Q8
+        float hdr[MPPI_OUT_HDR];
+        hdr[0] = u0x; hdr[1] = u0y; hdr[2] = __int_as_float(idx_new);
+        hdr[3] = ms.col[1]; hdr[4] = ms.col[0]; hdr[5] = eta;
+        hdr[6] = eta * eta / ms.col[3]; hdr[7] = 0.f;
+#pragma unroll
+        for (int i = 0; i < MPPI_OUT_HDR; ++i) { out[i] = hdr[i]; if (oh) oh[i] = hdr[i]; }
+        if (a.u0_out) { a.u0_out[2 * robot] = u0x; a.u0_out[2 * robot + 1] = u0y; }
+        if (!(a.flags & F_KEEP_IDX)) a.idx[robot] = idx_new;
+    }
+}
+
+struct RunSmem {
+    int n;                     // running lexicographic minimum
+    float s;
+    float eta, e2;
+    float N[2 * MPPI_MAX_T];
+    float warpN[MPPI_WARPS][2 * MPPI_MAX_T];
+    float warp_eta[MPPI_WARPS], warp_e2[MPPI_WARPS];
+    float red_s[MPPI_WARPS];
+    int red_n[MPPI_WARPS];
+    unsigned long long key[MPPI_WARPS];
+    unsigned ticket;
+};
+
+template <int MODEL, int COLL, bool SUM, bool INJ, int WIN>
+__global__ void __launch_bounds__(MPPI_BLOCK) mppi_tick_kernel(const __grid_constant__ TickArgs a) {
+    __shared__ TickSmem sm;
+    __shared__ RunSmem run;
+    __shared__ MergeSmem ms;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int robot = blockIdx.y, b = blockIdx.x, B = gridDim.x;
+    const int T = a.T, K = a.K;
+
+    // ---- prologue: observed state, step-1 index update (A8 with update=True), window, nominal
+    if (tid < 4) sm.x0[tid] = a.x0_dev ? a.x0_dev[robot * 4 + tid] : a.x0[tid];
+    __syncthreads();
+    int s_new;
+    if (a.flags & F_HOST_IDX) {
+        s_new = a.idx_host;
+    } else {
+        const int s_old = a.idx[robot];
+        unsigned long long key = ~0ull;
+        if (tid < a.window && s_old + tid < a.n_path) {
+            const float4 p = a.path[s_old + tid];
+            const float dx = sm.x0[0] - p.x, dy = sm.x0[1] - p.y;
+            key = ((unsigned long long)__float_as_uint(dx * dx + dy * dy) << 32) | (unsigned)tid;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const unsigned long long other = __shfl_xor_sync(0xffffffffu, key, o);
+            key = other < key ? other : key;
+        }
+        if (lane == 0) run.key[warp] = key;
+        __syncthreads();
+        key = run.key[0];
+#pragma unroll
+        for (int w = 1; w < MPPI_WARPS; ++w) key = run.key[w] < key ? run.key[w] : key;
+        s_new = s_old + (int)(key & 0xffffffffu);
+    }
+    {
+        int nw = a.n_path - s_new; nw = nw < a.window ? nw : a.window;
+        const int nw4 = (nw + 3) & ~3;
+        for (int j = tid; j < nw4; j += MPPI_BLOCK) {
+            if (j < nw) {
+                const float4 p = a.path[s_new + j];
+                sm.wx[j] = p.x; sm.wy[j] = p.y; sm.wref[j] = p;
+            } else {
+                sm.wx[j] = MPPI_SENTINEL; sm.wy[j] = MPPI_SENTINEL;
+                sm.wref[j] = make_float4(MPPI_SENTINEL, MPPI_SENTINEL, 0.f, 0.f);
+            }
+        }
+        if (tid == 0) { sm.win_start = s_new; sm.n_win4 = nw4 >> 2; }
+        const float *Ur = a.U + (size_t)robot * T * 2;
+        for (int t = tid; t < T; t += MPPI_BLOCK) {
+            const float u0 = Ur[2 * t], u1 = Ur[2 * t + 1];
+            sm.U[t] = make_float2(u0, u1);
+            sm.Q[t] = make_float2(u0 * a.gq[0] + u1 * a.gq[2], u0 * a.gq[1] + u1 * a.gq[3]);
+        }
+        if (tid == 0) { run.n = INT_MAX; run.s = CUDART_INF_F; run.eta = 0.f; run.e2 = 0.f; }
+        for (int c = tid; c < 2 * T; c += MPPI_BLOCK) run.N[c] = 0.f;
+    }
+    __syncthreads();
+
+    // ---- this block's contiguous sample range (balanced over the grid)
+    const int k_begin = (int)((long long)K * b / B), k_end = (int)((long long)K * (b + 1) / B);
+    float *Srow = a.S ? a.S + (size_t)robot * K : nullptr;
+    for (int base = k_begin; base < k_end; base += MPPI_BLOCK) {
+        const int k = base + tid;
+        const bool active = k < k_end;
+        const uint32_t kg = (uint32_t)(a.k_offset + k);
+        float smooth = CUDART_INF_F;
+        int ncoll = INT_MAX;
+        if (active) {
+            if (a.flags & F_FROM_S) {
+                smooth = Srow[k]; ncoll = 0;
+            } else {
+                rollout_sample<MODEL, COLL, SUM, INJ, WIN>(a, sm, kg, k, (uint32_t)robot,
+                                                           (int)kg < a.n_exploit, smooth, ncoll);
+                if (a.flags & F_WRITE_S) Srow[k] = smooth + MPPI_PENALTY * (float)ncoll;
+            }
+        }
+        if (!(a.flags & F_UPDATE)) continue;
+
+        // chunk minimum -> new running minimum
+        int cn = ncoll; float cs_ = smooth;
+        warp_lexmin(cn, cs_);
+        if (lane == 0) { run.red_n[warp] = cn; run.red_s[warp] = cs_; }
+        __syncthreads();
+        int mn = run.n; float mss = run.s;
+#pragma unroll
+        for (int w = 0; w < MPPI_WARPS; ++w) {
+            const int wn = run.red_n[w]; const float ws = run.red_s[w];
+            if (wn < mn || (wn == mn && ws < mss)) { mn = wn; mss = ws; }
+        }
+        const float rescale = (run.n == INT_MAX) ? 0.f : rel_weight(run.n, run.s, mn, mss, a.inv_temp);
+        const float w = active ? rel_weight(ncoll, smooth, mn, mss, a.inv_temp) : 0.f;
+
+        // weighted noise: regenerate (Philox) or re-read (injected) this sample's eps row
+        const bool any = __any_sync(0xffffffffu, w > 0.f);
+        if (any) {
+            const float2 *eps_k = INJ ? reinterpret_cast<const float2 *>(a.eps) + (size_t)(active ? k : k_begin) * T : nullptr;
+            for (int tp = 0; tp < T; tp += 2) {
+                float e[4] = {0.f, 0.f, 0.f, 0.f};
+                if (INJ) {
+                    const float2 ea = eps_k[tp];
+                    e[0] = ea.x; e[1] = ea.y;
+                    if (tp + 1 < T) { const float2 eb = eps_k[tp + 1]; e[2] = eb.x; e[3] = eb.y; }
+                } else {
+                    philox_eps_pair(a, kg, (uint32_t)(tp >> 1), (uint32_t)robot, e);
+                }
+                // 4 values x 32 lanes -> 4 sums: halving butterfly (6 shuffles instead of 20)
+                float p0 = w * e[0], p1 = w * e[1], p2 = w * e[2], p3 = w * e[3];
+                {
+                    const bool hi = lane & 16;
+                    const float s0 = hi ? p0 : p2, s1 = hi ? p1 : p3;       // send the half we do not keep
+                    const float r0 = __shfl_xor_sync(0xffffffffu, s0, 16), r1 = __shfl_xor_sync(0xffffffffu, s1, 16);
+                    p0 = (hi ? p2 : p0) + r0; p1 = (hi ? p3 : p1) + r1;      // lanes <16 hold (e0,e1), >=16 hold (e2,e3)
+                }
+                {
+                    const bool hi = lane & 8;
+                    const float s0 = hi ? p0 : p1;
+                    const float r0 = __shfl_xor_sync(0xffffffffu, s0, 8);
+                    p0 = (hi ? p1 : p0) + r0;                                 // lane bit3 selects component
+                }
+                p0 += __shfl_xor_sync(0xffffffffu, p0, 4);
+                p0 += __shfl_xor_sync(0xffffffffu, p0, 2);
+                p0 += __shfl_xor_sync(0xffffffffu, p0, 1);
+                // lane 0 -> e[0], lane 8 -> e[1], lane 16 -> e[2], lane 24 -> e[3]
+                if ((lane & 7) == 0) {
+                    const int c = 2 * tp + (lane >> 3);
+                    if (c < 2 * T) run.warpN[warp][c] = p0;
+                }
+            }
+        } else {
+            for (int c = lane; c < 2 * T; c += 32) run.warpN[warp][c] = 0.f;
+        }
+        const float we = warp_sum(w), we2 = warp_sum(w * w);
+        if (lane == 0) { run.warp_eta[warp] = we; run.warp_e2[warp] = we2; }
+        __syncthreads();
+        for (int c = tid; c < 2 * T; c += MPPI_BLOCK) {
+            float acc = run.N[c] * rescale;
+#pragma unroll
+            for (int wv = 0; wv < MPPI_WARPS; ++wv) acc += run.warpN[wv][c];
+            run.N[c] = acc;
+        }
+        if (tid == 0) {
+            float e1 = run.eta * rescale, e2 = run.e2 * rescale * rescale;
+#pragma unroll
+            for (int wv = 0; wv < MPPI_WARPS; ++wv) { e1 += run.warp_eta[wv]; e2 += run.warp_e2[wv]; }
+            run.eta = e1; run.e2 = e2; run.n = mn; run.s = mss;
+        }
+        __syncthreads();
+    }
+
+    // ---- publish the block partial, elect the last block
+    const int NF = MPPI_NF(T);
+    float *parts = a.part + (size_t)robot * B * NF;
+    if (a.flags & F_UPDATE) {
+        if (B > 1) {
+            float *mine = parts + (size_t)b * NF;
+            for (int c = tid; c < 2 * T; c += MPPI_BLOCK) mine[4 + c] = run.N[c];
+            if (tid == 0) { mine[0] = __int_as_float(run.n); mine[1] = run.s; mine[2] = run.eta; mine[3] = run.e2; }
+        }
+    }
+    if (B > 1) {
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) run.ticket = atomicAdd(&a.ticket[robot], 1u);
+        __syncthreads();
+        if (run.ticket != (unsigned)(B - 1)) return;
+        if (tid == 0) a.ticket[robot] = 0u;             // re-arm for the next launch
+        __threadfence();
+    }
+    if (!(a.flags & F_UPDATE)) {
+        if (tid == 0 && !(a.flags & F_KEEP_IDX)) a.idx[robot] = s_new;
+        return;
+    }
+    if (B > 1) {
+        merge_partials(a, parts, B, ms);
+    } else {
+        for (int c = tid; c < 2 * T; c += MPPI_BLOCK) ms.col[4 + c] = run.N[c];
+        if (tid == 0) { ms.col[0] = __int_as_float(run.n); ms.col[1] = run.s; ms.col[2] = run.eta; ms.col[3] = run.e2; }
+        __syncthreads();
+    }
+    if (a.flags & F_TRIPLE_OUT) {
+        for (int c = tid; c < NF; c += MPPI_BLOCK) a.triple_out[c] = ms.col[c];
+        if (tid == 0) a.out[2] = __int_as_float(s_new);   // stash the new index for the merge kernel
+        return;
+    }
+    finalize_tick(a, robot, s_new, ms);
+}
+
+// Merge of G per-GPU triples (after the all-gather) + finalize; identical on every rank.
+__global__ void __launch_bounds__(MPPI_BLOCK) mppi_merge_kernel(const __grid_constant__ TickArgs a,
+                                                                 const float *triples, int G) {
+    __shared__ MergeSmem ms;
+    merge_partials(a, triples, G, ms);
+    finalize_tick(a, 0, __float_as_int(a.out[2]), ms);
+}
+
+// (K,T,2) export of the Philox noise the tick kernel consumes
+__global__ void mppi_noise_kernel(const __grid_constant__ TickArgs a, float *out, int robot) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= a.K) return;
+    float2 *row = reinterpret_cast<float2 *>(out) + (size_t)k * a.T;
+    for (int tp = 0; tp < a.T; tp += 2) {
+        float e[4];
+        philox_eps_pair(a, (uint32_t)(a.k_offset + k), (uint32_t)(tp >> 1), (uint32_t)robot, e);
+        row[tp] = make_float2(e[0], e[1]);
+        if (tp + 1 < a.T) row[tp + 1] = make_float2(e[2], e[3]);
+    }
+}
+
+// ---- strict waypoint mode (Q3): literal evaluation order via the multi-pass rule ----------
+// Evaluation n = k*(T+1) + t (t = 0..T-1 stage, t = T terminal) uses the window start given by
+// the last breakpoint (bp_n <= n).  The first evaluation >= check_from whose argmin differs
+// from its window start is reported through first_change = min((n << 32) | argmin).
+template <int MODEL, int COLL, bool SUM, bool INJ>
+__global__ void __launch_bounds__(MPPI_BLOCK) mppi_strict_kernel(const __grid_constant__ TickArgs a,
+                                                                  const unsigned *bp_n, const int *bp_s, int nbp,
+                                                                  int k_first, unsigned check_from,
+                                                                  unsigned long long *first_change) {
+    const int k = k_first + blockIdx.x * MPPI_BLOCK + threadIdx.x;
+    if (k >= a.K) return;
+    const int T = a.T;
+    const uint32_t kg = (uint32_t)(a.k_offset + k);
+    const bool exploit = (int)kg < a.n_exploit;
+    float z[4] = {a.x0[0], a.x0[1], a.x0[2], a.x0[3]};
+    float cs, sn;
+    sincosf(z[2], &sn, &cs);
+    float acc = 0.f;
+    int nc = 0;
+    int bp = 0;
+    const float2 *eps_k = INJ ? reinterpret_cast<const float2 *>(a.eps) + (size_t)k * T : nullptr;
+    float e[4];
+    for (int t = 0; t <= T; ++t) {
+        float v0 = 0.f, v1 = 0.f;
+        if (t < T) {
+            if (INJ) { const float2 ea = eps_k[t]; e[2 * (t & 1)] = ea.x; e[2 * (t & 1) + 1] = ea.y; }
+            else if ((t & 1) == 0) philox_eps_pair(a, kg, (uint32_t)(t >> 1), 0u, e);
+            const float u0 = a.U[2 * t], u1 = a.U[2 * t + 1];
+            v0 = clampf(exploit ? __fadd_rn(u0, e[2 * (t & 1)]) : e[2 * (t & 1)], a.umax0);
+            v1 = clampf(exploit ? __fadd_rn(u1, e[2 * (t & 1) + 1]) : e[2 * (t & 1) + 1], a.umax1);
+            dyn_step<MODEL>(a, z, v0, v1, cs, sn);
+            sincosf(z[2], &sn, &cs);
+        }
+        const unsigned n = (unsigned)k * (unsigned)(T + 1) + (unsigned)t;
+        while (bp + 1 < nbp && bp_n[bp + 1] <= n) ++bp;
+        const int s = bp_s[bp];
+        int end = s + a.window; end = end < a.n_path ? end : a.n_path;
+        float bd = CUDART_INF_F; int bj = s;
+        for (int j = s; j < end; ++j) {
+            const float4 p = a.path[j];
+            const float dx = z[0] - p.x, dy = z[1] - p.y, d = dx * dx + dy * dy;
+            if (d < bd) { bd = d; bj = j; }
+        }
+        if (bj != s && n >= check_from) atomicMin(first_change, ((unsigned long long)n << 32) | (unsigned)bj);
+        const bool stage = t < T, last = (t == T - 1);
+        if ((stage && (SUM || last)) || t == T) {
+            const float4 ref = a.path[bj];
+            const float yaw_eff = a.yaw_wrap ? wrap_2pi(z[2]) : z[2];
+            float c = tracking_cost<MODEL>(ref, z, yaw_eff, stage ? a.sw : a.tw);
+            if (stage && a.use_gamma) {
+                const float u0 = a.U[2 * t], u1 = a.U[2 * t + 1];
+                c += (u0 * a.gq[0] + u1 * a.gq[2]) * v0 + (u0 * a.gq[1] + u1 * a.gq[3]) * v1;
+            }
+            const bool hit = collided<MODEL, COLL>(a, z[0], z[1], cs, sn);
+            if (stage && !SUM) { acc = c; nc = hit ? 1 : 0; }      // Q1: assignment
+            else { acc += c; nc += hit ? 1 : 0; }
+        }
+    }
+    a.S[k] = acc + MPPI_PENALTY * (float)nc;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------
+// dispatch
+// ------------------------------------------------------------------------------------------
+template <int MODEL, int COLL, bool SUM, bool INJ>
+static cudaError_t launch_tick_win(const TickArgs &a, dim3 grid, cudaStream_t st, int win_static) {
+    if (win_static == 20) mppi_tick_kernel<MODEL, COLL, SUM, INJ, 20><<<grid, MPPI_BLOCK, 0, st>>>(a);
+    else mppi_tick_kernel<MODEL, COLL, SUM, INJ, 0><<<grid, MPPI_BLOCK, 0, st>>>(a);
+    return cudaGetLastError();
+}
+
+template <int MODEL, int COLL>
+static cudaError_t launch_tick_mc(const TickArgs &a, dim3 grid, cudaStream_t st, bool sum, bool inj, int win_static) {
+    if (sum) return inj ? launch_tick_win<MODEL, COLL, true, true>(a, grid, st, win_static)
+                        : launch_tick_win<MODEL, COLL, true, false>(a, grid, st, win_static);
+    return inj ? launch_tick_win<MODEL, COLL, false, true>(a, grid, st, win_static)
+               : launch_tick_win<MODEL, COLL, false, false>(a, grid, st, win_static);
+}
+
+cudaError_t mppi_launch_tick(const TickArgs &a, int model, int coll, bool sum, bool inj, dim3 grid, cudaStream_t st) {
+    const int ws = (a.window == 20) ? 20 : 0;
+    if (model == MPPI_MODEL_DIFFDRIVE) {
+        if (coll == MPPI_COLLISION_NONE) return launch_tick_mc<MPPI_MODEL_DIFFDRIVE, MPPI_COLLISION_NONE>(a, grid, st, sum, inj, ws);
+        if (coll == MPPI_COLLISION_CIRCLE) return launch_tick_mc<MPPI_MODEL_DIFFDRIVE, MPPI_COLLISION_CIRCLE>(a, grid, st, sum, inj, ws);
+    } else if (model == MPPI_MODEL_BICYCLE) {
+        if (coll == MPPI_COLLISION_NONE) return launch_tick_mc<MPPI_MODEL_BICYCLE, MPPI_COLLISION_NONE>(a, grid, st, sum, inj, ws);
+        if (coll == MPPI_COLLISION_CIRCLE) return launch_tick_mc<MPPI_MODEL_BICYCLE, MPPI_COLLISION_CIRCLE>(a, grid, st, sum, inj, ws);
+        if (coll == MPPI_COLLISION_FOOTPRINT) return launch_tick_mc<MPPI_MODEL_BICYCLE, MPPI_COLLISION_FOOTPRINT>(a, grid, st, sum, inj, ws);
+    }
+    return cudaErrorInvalidValue;
+}
+
+template <int MODEL, int COLL>
+static cudaError_t launch_strict_mc(const TickArgs &a, bool sum, bool inj, const unsigned *bp_n, const int *bp_s,
+                                    int nbp, int k_first, unsigned check_from, unsigned long long *fc, cudaStream_t st) {
+    const int nblk = (a.K - k_first + MPPI_BLOCK - 1) / MPPI_BLOCK;
+    if (nblk <= 0) return cudaSuccess;
+    if (sum) {
+        if (inj) mppi_strict_kernel<MODEL, COLL, true, true><<<nblk, MPPI_BLOCK, 0, st>>>(a, bp_n, bp_s, nbp, k_first, check_from, fc);
+        else mppi_strict_kernel<MODEL, COLL, true, false><<<nblk, MPPI_BLOCK, 0, st>>>(a, bp_n, bp_s, nbp, k_first, check_from, fc);
+    } else {
+        if (inj) mppi_strict_kernel<MODEL, COLL, false, true><<<nblk, MPPI_BLOCK, 0, st>>>(a, bp_n, bp_s, nbp, k_first, check_from, fc);
+        else mppi_strict_kernel<MODEL, COLL, false, false><<<nblk, MPPI_BLOCK, 0, st>>>(a, bp_n, bp_s, nbp, k_first, check_from, fc);
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t mppi_launch_strict(const TickArgs &a, int model, int coll, bool sum, bool inj, const unsigned *bp_n,
+                               const int *bp_s, int nbp, int k_first, unsigned check_from,
+                               unsigned long long *first_change, cudaStream_t st) {
+    if (model == MPPI_MODEL_DIFFDRIVE) {
+        if (coll == MPPI_COLLISION_NONE) return launch_strict_mc<MPPI_MODEL_DIFFDRIVE, MPPI_COLLISION_NONE>(a, sum, inj, bp_n, bp_s, nbp, k_first, check_from, first_change, st);
+        if (coll == MPPI_COLLISION_CIRCLE) return launch_strict_mc<MPPI_MODEL_DIFFDRIVE, MPPI_COLLISION_CIRCLE>(a, sum, inj, bp_n, bp_s, nbp, k_first, check_from, first_change, st);
+    } else if (model == MPPI_MODEL_BICYCLE) {
+        if (coll == MPPI_COLLISION_NONE) return launch_strict_mc<MPPI_MODEL_BICYCLE, MPPI_COLLISION_NONE>(a, sum, inj, bp_n, bp_s, nbp, k_first, check_from, first_change, st);
+        if (coll == MPPI_COLLISION_FOOTPRINT) return launch_strict_mc<MPPI_MODEL_BICYCLE, MPPI_COLLISION_FOOTPRINT>(a, sum, inj, bp_n, bp_s, nbp, k_first, check_from, first_change, st);
+    }
+    return cudaErrorInvalidValue;
+}
+
+cudaError_t mppi_launch_merge(const TickArgs &a, const float *triples, int G, cudaStream_t st) {
+    mppi_merge_kernel<<<1, MPPI_BLOCK, 0, st>>>(a, triples, G);
+    return cudaGetLastError();
+}
+
+cudaError_t mppi_launch_noise(const TickArgs &a, float *d_out, int robot, cudaStream_t st) {
+    mppi_noise_kernel<<<(a.K + 255) / 256, 256, 0, st>>>(a, d_out, robot);
+    return cudaGetLastError();
+}
+
+int mppi_tick_occupancy(int model, int coll, bool sum) {
+    int nb = 0;
+    // representative instantiation; all variants share the same launch bounds and smem footprint
+    if (model == MPPI_MODEL_BICYCLE)
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, mppi_tick_kernel<MPPI_MODEL_BICYCLE, MPPI_COLLISION_FOOTPRINT, true, false, 0>, MPPI_BLOCK, 0);
+    else if (sum)
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, mppi_tick_kernel<MPPI_MODEL_DIFFDRIVE, MPPI_COLLISION_NONE, true, false, 20>, MPPI_BLOCK, 0);
+    else
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, mppi_tick_kernel<MPPI_MODEL_DIFFDRIVE, MPPI_COLLISION_NONE, false, false, 20>, MPPI_BLOCK, 0);
+    (void)coll;
+    return nb > 0 ? nb : 1;
+}

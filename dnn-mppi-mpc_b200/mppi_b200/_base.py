@@ -1,0 +1,98 @@
+"""Shared host logic of the drop-in controller classes (the reference's class surface,
+SURVEY.md 8b).  Everything numeric happens behind the C ABI; this file only marshals."""
+import warnings
+
+import numpy as np
+
+from .engine import MPPIEngine
+
+
+def _to_device_noise(noise, K, T, device):
+    """Accepts a (K,T,2) numpy array or torch tensor; returns a contiguous float32 CUDA tensor."""
+    import torch
+    if isinstance(noise, np.ndarray):
+        noise = torch.from_numpy(np.ascontiguousarray(noise, dtype=np.float32))
+    if tuple(noise.shape) != (K, T, 2):
+        raise ValueError("injected noise must have shape (K,T,2) = (%d,%d,2), got %s" % (K, T, tuple(noise.shape)))
+    return noise.to(device="cuda:%d" % device, dtype=torch.float32).contiguous()
+
+
+class ControllerBase:
+    """Holds one engine handle and mirrors the mutable public state callers touch in the
+    reference: `u_prev`, the waypoint index, `ref_path`, `obstacle_circles`."""
+
+    _out_dtype = np.float64
+    _idx_attr = "prev_way_point_idx"
+
+    def _init_engine(self, *, ref_path, seed, device, rank, world, **engine_kw):
+        self.seed = int(seed)
+        self._tick = 0
+        self._rank, self._world = int(rank), int(world)
+        K_global = engine_kw["K"]
+        if world > 1:
+            if K_global % world:
+                raise ValueError("num_samples_K must be divisible by the world size")
+            engine_kw = dict(engine_kw, K=K_global // world, K_global=K_global, k_offset=rank * (K_global // world))
+        self._engine = MPPIEngine(device=device, **engine_kw)
+        self._K_local = engine_kw["K"]
+        self._ref_path = None
+        self.ref_path = ref_path
+        self._u_cache = np.zeros((self.T, self.dim_u), dtype=self._out_dtype)
+        self._viz_warned = False
+
+    # -- reference attributes ----------------------------------------------------------------
+    @property
+    def ref_path(self):
+        return self._ref_path
+
+    @ref_path.setter
+    def ref_path(self, path):
+        # re-assigned after construction by the reference main (mppi_race_car_obstacle.py:332)
+        self._ref_path = np.asarray(path)
+        self._engine.set_ref_path(self._ref_path)
+
+    @property
+    def u_prev(self):
+        return self._u_cache
+
+    @u_prev.setter
+    def u_prev(self, u):
+        u = np.asarray(u, dtype=self._out_dtype).reshape(self.T, self.dim_u)
+        self._u_cache = u.copy()
+        self._engine.set_nominal(u)
+
+    def _get_idx(self):
+        return self._engine.get_waypoint_idx()
+
+    def _set_idx(self, v):
+        self._engine.set_waypoint_idx(int(v))
+
+    # -- one tick ----------------------------------------------------------------------------
+    def _tick_impl(self, observed_x, noise=None):
+        x = np.asarray(observed_x, dtype=np.float64 if self._out_dtype is np.float64 else np.float32)
+        d_eps = None
+        if noise is not None:
+            d_eps = _to_device_noise(noise, self._K_local, self.T, self._engine.device)
+        u0, useq = self._engine.step(x, d_eps, self.seed, self._tick)
+        self._tick += 1
+        self._u_cache = useq.astype(self._out_dtype)           # returned u aliases u_prev (A2)
+        u = self._u_cache
+        optimal_traj = np.zeros((self.T, self.dim_x), dtype=self._out_dtype)
+        # (K,T,nx) zeros like the reference returns when the flag is off, without allocating K*T*nx
+        sampled = np.broadcast_to(np.zeros((), dtype=self._out_dtype), (self.K, self.T, self.dim_x))
+        if (self.visualize_optimal_traj or self.visualze_sampled_trajs) and not self._viz_warned:
+            warnings.warn("visualisation trajectories are not produced by this build (zeros returned)")
+            self._viz_warned = True
+        return u[0], u, optimal_traj, sampled
+
+    def comm_init_from_torch(self):
+        """Sample sharding over torch.distributed ranks: rank 0 creates the NCCL id, broadcast, init."""
+        import torch
+        import torch.distributed as dist
+        ids = [MPPIEngine.comm_unique_id() if dist.get_rank() == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        self._engine.comm_init(ids[0], dist.get_rank(), dist.get_world_size())
+
+    @property
+    def engine(self):
+        return self._engine

@@ -1,0 +1,176 @@
+/* libmppi_b200.so -- C ABI of the B200-native MPPI engine.
+ *
+ * The reference (SokhengDin/DNN-MPPI-MPC) has no FFI layer: its boundary is the Python
+ * class surface of controllers/mppi_*.py.  Each entry point below names the reference
+ * code it replaces (file:line relative to the reference tree); the Python shim in
+ * dnn-mppi-mpc_b200/mppi_b200/ binds these with ctypes and re-exposes the reference's
+ * class/method names.
+ *
+ * Conventions
+ *   - plain C types only; no C++/torch types cross this boundary.
+ *   - pointers named d_* are DEVICE pointers (e.g. torch.Tensor.data_ptr()); all others
+ *     are HOST pointers.  The caller owns every pointer it passes in; the library owns
+ *     the handle's device scratch for the handle's lifetime.
+ *   - every call returns an int status (0 = MPPI_OK, <0 = MPPI_E_*); nothing throws or
+ *     aborts across the ABI.  mppi_last_error(h) returns the last CUDA/NCCL message.
+ *   - a handle is bound to one device and one stream and is not thread-safe; distinct
+ *     handles are independent.
+ *   - there is NO CPU fallback: without a CUDA device mppi_create fails with MPPI_E_CUDA.
+ */
+#ifndef MPPI_B200_H
+#define MPPI_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MPPI_ABI_VERSION 1
+
+typedef struct mppi_handle_s *mppi_handle_t;
+
+enum mppi_status {
+    MPPI_OK = 0,
+    MPPI_E_BADARG = -1,       /* invalid configuration / null pointer / size out of range */
+    MPPI_E_CUDA = -2,         /* CUDA runtime error (message via mppi_last_error) */
+    MPPI_E_NCCL = -3,         /* NCCL error */
+    MPPI_E_STATE = -4,        /* call order: path / nominal / MLP weights not set yet */
+    MPPI_E_UNSUPPORTED = -5,  /* mode combination not implemented by this build */
+    MPPI_E_NOMEM = -6
+};
+
+enum mppi_model {
+    MPPI_MODEL_DIFFDRIVE = 0,      /* controllers/mppi_differential_drive.py:182-198 */
+    MPPI_MODEL_BICYCLE = 1,        /* controllers/mppi_race_car_obstacle.py:200-214, u = [steer, accel] */
+    MPPI_MODEL_DIFFDRIVE_MLP = 2   /* unicycle + dnn/simple_mlp.py residual */
+};
+enum mppi_cost_mode { MPPI_COST_LAST = 0 /* :124 assigns (Q1) */, MPPI_COST_SUM = 1 /* race-car :94 */ };
+enum mppi_waypoint_mode { MPPI_WP_STRICT = 0 /* :228,:244 mutate the index (Q3) */, MPPI_WP_FROZEN = 1 };
+enum mppi_filter_kind { MPPI_FILTER_DIFFDRIVE = 0 /* :257-271 */, MPPI_FILTER_RACECAR = 1 /* race-car :228-239 */ };
+enum mppi_collision {
+    MPPI_COLLISION_NONE = 0,
+    MPPI_COLLISION_CIRCLE = 1,     /* controllers/mppi_differential_drive_obs.py:301-313 */
+    MPPI_COLLISION_FOOTPRINT = 2   /* controllers/mppi_race_car_obstacle.py:255-274 */
+};
+enum mppi_noise_layout { MPPI_NOISE_KTU = 0 /* (K,T,2) row-major, the reference's epsilon layout */ };
+
+#define MPPI_MAX_T 128
+#define MPPI_MAX_WINDOW 256
+#define MPPI_MAX_OBSTACLES 16
+
+/* Mirrors every constructor kwarg of the reference controllers plus the constants they
+ * hard-code (controllers/mppi_differential_drive.py:44-85,204; mppi_race_car_obstacle.py:11-62,175). */
+typedef struct {
+    int32_t abi_version;      /* = MPPI_ABI_VERSION */
+    int32_t device;           /* CUDA device ordinal */
+    int32_t model;            /* enum mppi_model */
+    int32_t K;                /* num_samples_K / number_of_samples_K: samples THIS handle rolls out */
+    int32_t T;                /* num_horizons_T / horizon_step_T, <= MPPI_MAX_T */
+    int32_t n_robots;         /* 1, or R independent controllers solved in one launch */
+    int32_t window;           /* SEARCH_IDX_LEN: 20 / 200, <= MPPI_MAX_WINDOW */
+    int32_t cost_mode;        /* enum mppi_cost_mode */
+    int32_t waypoint_mode;    /* enum mppi_waypoint_mode */
+    int32_t filter_kind;      /* enum mppi_filter_kind */
+    int32_t yaw_wrap;         /* 1: yaw = (yaw + 2pi) mod 2pi inside the cost (race-car :151) */
+    int32_t collision;        /* enum mppi_collision */
+    int32_t K_global;         /* total samples over all ranks (== K when not sharded) */
+    int32_t k_offset;         /* global index of this handle's first sample */
+    double dt;                /* delta_t */
+    double wheel_base;
+    double u_max[2];          /* (max_speed, max_omega) or (max_steer_abs, max_accel_abs) */
+    double param_exploration; /* explore/exploit split (Q6) */
+    double param_lambda;
+    double param_alpha;       /* gamma = lambda * (1 - alpha) */
+    double temperature;       /* softmax temperature: param_exploration (diff-drive, Q2) or param_lambda */
+    double sigma[4];          /* row-major 2x2 noise covariance */
+    double stage_w[4];
+    double term_w[4];
+    double margin;            /* safety_margin_rate / collision_safety_margin_rat */
+    double robot_radius;      /* 0.5 (mppi_differential_drive_obs.py:303) */
+    double vehicle_l;         /* 4.0 (mppi_race_car_obstacle.py:54) */
+    double vehicle_w;         /* 3.0 (mppi_race_car_obstacle.py:53) */
+} mppi_config_t;
+
+typedef struct {
+    float last_step_ms;       /* device time of the last mppi_step (CUDA events), timing enabled only */
+    float last_rollout_ms;
+    float last_update_ms;
+    int32_t last_passes;      /* strict mode: rollout passes of the last tick */
+    int32_t launches;         /* kernels launched by this handle since creation */
+} mppi_timings_t;
+
+typedef struct {
+    float rho;                /* min cost of the tick */
+    float eta;                /* sum of unnormalised weights */
+    float ess;                /* effective sample size (sum w)^2 / sum w^2 */
+    int32_t min_collisions;   /* fewest collided evaluations among the samples */
+    int32_t idx;              /* carried waypoint index after the tick */
+} mppi_stats_t;
+
+/* lifecycle -- replaces MPPIAlgorithms.__init__ (controllers/mppi_differential_drive.py:44-85)
+ * and MPPIRacecarController.__init__ (controllers/mppi_race_car_obstacle.py:11-62) */
+int mppi_create(const mppi_config_t *cfg, mppi_handle_t *out);
+int mppi_destroy(mppi_handle_t h);
+void mppi_default_config(mppi_config_t *cfg);
+const char *mppi_strerror(int status);
+const char *mppi_last_error(mppi_handle_t h);
+int mppi_set_stream(mppi_handle_t h, void *cuda_stream);
+int mppi_synchronize(mppi_handle_t h);
+
+/* `self.ref_path` (N,3) [x,y,yaw] or (N,4) [x,y,yaw,v], row-major doubles
+ * (mppi_differential_drive.py:64; re-assigned after construction at mppi_race_car_obstacle.py:332) */
+int mppi_set_ref_path(mppi_handle_t h, const double *path, int32_t n, int32_t ncol);
+/* `self.obstacle_circles` (M,3) [x,y,r] (mppi_race_car_obstacle.py:57) */
+int mppi_set_obstacles(mppi_handle_t h, const double *xyr, int32_t m);
+/* `self.u_prev` (T,2) per robot (mppi_differential_drive.py:82) -- host float arrays of n_robots*T*2 */
+int mppi_set_nominal(mppi_handle_t h, const float *u);
+int mppi_get_nominal(mppi_handle_t h, float *u);
+/* `self.prev_way_point_idx` / `prev_waypoints_idx` (mppi_differential_drive.py:85) -- n_robots ints */
+int mppi_set_waypoint_idx(mppi_handle_t h, const int32_t *idx);
+int mppi_get_waypoint_idx(mppi_handle_t h, int32_t *idx);
+/* weights of dnn/simple_mlp.py (3-512-512-512-3), row-major float32 [out][in] like nn.Linear */
+int mppi_set_mlp(mppi_handle_t h, const float *const W[4], const float *const b[4]);
+
+/* One control tick -- replaces the body of `_calc_input_control` (mppi_differential_drive.py:87-165)
+ * / `_calc_control_input` (mppi_race_car_obstacle.py:65-131): index update, noise, K x T rollout,
+ * costs, weights, weighted noise, filter, nominal update and shift.
+ *   x0        host, nx doubles (observed state)
+ *   d_eps     device (K,T,2) float32 injected noise, or NULL -> Philox4x32-10 with (seed, tick)
+ *   u0_out    host, 2 floats: the returned control (post-shift row 0, quirk Q8); may be NULL
+ *   useq_out  host, T*2 floats: the returned (shifted) sequence; may be NULL */
+int mppi_step(mppi_handle_t h, const double *x0, const float *d_eps, uint64_t seed, uint64_t tick,
+              float *u0_out, float *useq_out);
+/* Same tick without any host copy: results stay on the device (nominal, stats). */
+int mppi_step_async(mppi_handle_t h, const double *x0, const float *d_eps, uint64_t seed, uint64_t tick);
+/* K1 alone: index update + rollout + costs -> d_S (K float32, device).  Does not touch the nominal.
+ * Replaces the loop at mppi_differential_drive.py:111-126 / mppi_race_car_obstacle.py:82-96. */
+int mppi_rollout_costs(mppi_handle_t h, const double *x0, const float *d_eps, uint64_t seed,
+                       uint64_t tick, float *d_S);
+/* K2 alone: weights + weighted noise + filter + update + shift from given costs
+ * (mppi_differential_drive.py:129-141,162-163,167-180,257-271).  w_eps_out: host T*2 raw weighted noise. */
+int mppi_reduce_update(mppi_handle_t h, const float *d_S, const float *d_eps, uint64_t seed,
+                       uint64_t tick, float *u0_out, float *useq_out, float *w_eps_out);
+/* The exact noise tensor (K,T,2) the Philox path consumes for (seed, tick) -- replaces
+ * `_calc_epsilon` (mppi_differential_drive.py:273-283) and lets the oracle be fed the same noise. */
+int mppi_generate_noise(mppi_handle_t h, uint64_t seed, uint64_t tick, float *d_eps_out);
+int mppi_get_stats(mppi_handle_t h, mppi_stats_t *out);   /* robot 0 */
+
+/* Batched multi-robot tick: n_robots independent controllers in one launch (no reference
+ * equivalent; R copies of the loop at mppi_differential_drive.py:111-141).
+ *   d_x0  device (R, nx) float32;  d_u0_out device (R, 2) float32 (may be NULL) */
+int mppi_step_batched(mppi_handle_t h, const float *d_x0, uint64_t seed, uint64_t tick, float *d_u0_out);
+
+/* Sample sharding across GPUs: each rank owns K of K_global samples; one exchange of
+ * (min cost, sum w, sum w*eps) per tick.  `nccl_unique_id` is the 128-byte ncclUniqueId. */
+int mppi_comm_get_unique_id(void *out128);
+int mppi_comm_init(mppi_handle_t h, const void *nccl_unique_id, int32_t rank, int32_t world);
+
+int mppi_set_timing(mppi_handle_t h, int32_t enabled);
+int mppi_get_timings(mppi_handle_t h, mppi_timings_t *out);
+int mppi_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MPPI_B200_H */

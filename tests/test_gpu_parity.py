@@ -1,0 +1,252 @@
+"""Parity of the CUDA path (through the C ABI) with the golden vectors recorded from the
+unmodified reference classes and with the oracle.  Tolerances (FP32 device arithmetic vs the
+FP64 / FP32 reference): per-sample costs rtol 1e-5; nominal update atol 2e-5 given the same
+arg-min sample (SURVEY.md section 7 'softmax conditioning')."""
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+from golden_util import ALL_CASES, DIFFDRIVE_CASES, RACECAR_CASES, Golden, rel_err  # noqa: E402
+from gpu_util import cost_mismatch, engine_from_spec  # noqa: E402
+from oracle import c_oracle as co  # noqa: E402
+from oracle import mppi_oracle as orc  # noqa: E402
+
+COST_RTOL = 1e-5
+U_ATOL = 2e-5
+
+
+def _dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).cuda()
+
+
+@pytest.mark.parametrize("name", ALL_CASES)
+def test_rollout_costs_match_reference(name):
+    """K1: per-sample costs for every recorded tick, literal modes of each class."""
+    g = Golden(name)
+    sp = g.spec()
+    eng = engine_from_spec(sp, g.path)
+    S = torch.zeros(sp.K, dtype=torch.float32, device="cuda")
+    for i in range(g.n_ticks):
+        eng.set_nominal(g.rec["U0"][i])
+        eng.set_waypoint_idx(int(g.rec["idx0"][i]))
+        eng.rollout_costs(g.rec["x0"][i], S, _dev(g.eps[i]))
+        Sg = S.cpu().numpy()
+        Sr = g.rec["S"][i]
+        # identical collision pattern (multiples of 1e10), then the smooth part to rtol
+        assert np.array_equal(np.round(Sg / 1e10), np.round(Sr.astype(np.float64) / 1e10)), (name, i)
+        frac, worst = cost_mismatch(Sg, Sr, rtol=COST_RTOL)
+        assert frac == 0.0, (name, i, frac, worst)
+        assert eng.get_waypoint_idx() == int(g.rec["idx_after"][i]), (name, i)
+    eng.close()
+
+
+@pytest.mark.parametrize("name", ALL_CASES)
+def test_full_tick_matches_reference(name):
+    """K1+K2 through mppi_step: shifted nominal, returned u0 (Q8) and carried index."""
+    g = Golden(name)
+    sp = g.spec()
+    eng = engine_from_spec(sp, g.path)
+    for i in range(g.n_ticks):
+        eng.set_nominal(g.rec["U0"][i])
+        eng.set_waypoint_idx(int(g.rec["idx0"][i]))
+        u0, useq = eng.step(g.rec["x0"][i], _dev(g.eps[i]))
+        ref_U, ref_u0 = g.rec["U_after"][i], g.rec["u0"][i]
+        if g.rec["S"][i].dtype == np.float32 and g.rec["S"][i].min() >= 1e10:
+            # every sample collided: the FP32 reference's weights are rounding noise
+            # (ulp(1e10)=1024); the device keeps collision counts apart and must match FP64
+            o = co.tick(sp, **g.tick_inputs(i))
+            ref_U, ref_u0 = o["U_after"], o["u0"]
+        assert np.max(np.abs(useq - ref_U)) <= U_ATOL, (name, i, np.max(np.abs(useq - ref_U)))
+        assert np.max(np.abs(u0 - ref_u0)) <= U_ATOL
+        assert np.array_equal(u0, useq[0])                                    # Q8
+        assert np.array_equal(useq[-1], useq[-2])                             # last row duplicated
+        assert eng.get_waypoint_idx() == int(g.rec["idx_after"][i])
+        assert np.max(np.abs(eng.get_nominal() - useq)) == 0.0
+    eng.close()
+
+
+@pytest.mark.parametrize("name", ["diffdrive_pe0.05", "racecar_noobs", "diffdrive_obs"])
+def test_reduce_update_given_reference_costs(name):
+    """K2 alone: feed the reference's own S, compare weighted noise and update."""
+    g = Golden(name)
+    sp = g.spec()
+    eng = engine_from_spec(sp, g.path)
+    for i in range(g.n_ticks):
+        if g.rec["S"][i].min() >= 1e10:
+            continue
+        eng.set_nominal(g.rec["U0"][i])
+        u0, useq, w_eps = eng.reduce_update(_dev(g.rec["S"][i]), _dev(g.eps[i]))
+        scale = max(np.max(np.abs(g.rec["w_eps"][i])), 1e-6)
+        assert np.max(np.abs(w_eps - g.rec["w_eps"][i])) <= 1e-5 * scale + 1e-7, (name, i)
+        assert np.max(np.abs(useq - g.rec["U_after"][i])) <= U_ATOL
+    eng.close()
+
+
+@pytest.mark.parametrize("cost_mode", ["last", "sum"])
+@pytest.mark.parametrize("name", ["diffdrive_pe0.05", "diffdrive_obs", "racecar_default", "racecar_alpha0.9"])
+def test_frozen_modes_match_oracle(name, cost_mode):
+    """The throughput modes (frozen window x {last,sum}) have no literal reference class; they
+    are checked against the C oracle, itself pinned to the golden vectors."""
+    g = Golden(name)
+    sp = g.spec(cost_mode=cost_mode, waypoint_mode="frozen")
+    eng = engine_from_spec(sp, g.path)
+    S = torch.zeros(sp.K, dtype=torch.float32, device="cuda")
+    for i in range(min(g.n_ticks, 4)):
+        inp = g.tick_inputs(i)
+        o = co.tick(sp, **inp)
+        eng.set_nominal(inp["U"])
+        eng.set_waypoint_idx(inp["idx"])
+        eng.rollout_costs(inp["x0"], S, _dev(inp["eps"]))
+        frac, worst = cost_mismatch(S.cpu().numpy(), o["S"], rtol=COST_RTOL)
+        assert frac == 0.0, (name, cost_mode, i, worst)
+        eng.set_waypoint_idx(inp["idx"])
+        u0, useq = eng.step(inp["x0"], _dev(inp["eps"]))
+        assert np.max(np.abs(useq - o["U_after"])) <= U_ATOL, (name, cost_mode, i)
+        assert eng.get_waypoint_idx() == o["idx_after"]
+    eng.close()
+
+
+def test_closed_loop_tracks_reference_trajectory():
+    """40-tick closed loop on the spline path: the controller is driven by its OWN outputs
+    through the unicycle plant (mppi_differential_drive.py:33-40) and must stay within 1 cm of
+    the trajectory the reference class produced with the same noise."""
+    g = Golden("diffdrive_closed_loop")
+    sp = g.spec()
+    eng = engine_from_spec(sp, g.path)
+    x = g.rec["x0"][0].astype(np.float64).copy()
+    dev = 0.0
+    for i in range(g.n_ticks):
+        dev = max(dev, float(np.max(np.abs(x[:2] - g.rec["x0"][i][:2]))))
+        u0, _ = eng.step(x, _dev(g.eps[i]))
+        x = orc.plant_diffdrive(x, u0.astype(np.float64), sp.dt)
+    assert dev < 1e-2, dev
+    assert eng.get_waypoint_idx() == int(g.rec["idx_after"][-1])
+    eng.close()
+
+
+def test_philox_noise_matches_spec_and_statistics():
+    sigma = np.array([[0.1, 0.02], [0.02, 0.05]])
+    sp = orc.diffdrive_spec(K=8192, T=31, sigma=sigma, cost_mode="sum", waypoint_mode="frozen")
+    g = Golden("diffdrive_pe0.05")
+    eng = engine_from_spec(sp, g.path)
+    out = torch.zeros(sp.K, sp.T, 2, dtype=torch.float32, device="cuda")
+    eng.generate_noise(out, seed=0x1234567890ABCDEF, tick=17)
+    e = out.cpu().numpy().astype(np.float64)
+    ref = orc.philox_noise(0x1234567890ABCDEF, 17, sp.K, sp.T, sigma)
+    assert np.max(np.abs(e - ref)) < 5e-6                      # MUFU log2/sin/cos vs libm
+    flat = e.reshape(-1, 2)
+    assert np.all(np.abs(flat.mean(0)) < 4e-3)
+    assert np.max(np.abs(np.cov(flat.T) - sigma)) < 2e-3
+    eng.close()
+
+
+@pytest.mark.parametrize("model", ["diffdrive", "bicycle"])
+def test_philox_tick_matches_oracle_fed_the_exported_noise(model):
+    """Philox mode: export the exact noise the kernel consumes, feed it to the oracle."""
+    if model == "diffdrive":
+        g = Golden("diffdrive_pe0.05")
+        sp = orc.diffdrive_spec(K=4096, T=30, param_exploration=0.05, cost_mode="sum", waypoint_mode="frozen")
+        sp.temperature = 2.0
+        x0 = np.array([0.2, 0.1, 0.3])
+    else:
+        g = Golden("racecar_noobs")
+        sp = orc.racecar_spec(K=4096, T=50, dtype=np.float64)
+        x0 = g.rec["x0"][3].astype(np.float64)
+    eng = engine_from_spec(sp, g.path)
+    eps = torch.zeros(sp.K, sp.T, 2, dtype=torch.float32, device="cuda")
+    U = np.zeros((sp.T, 2), np.float32)
+    idx = 0
+    for tick in range(3):
+        eng.generate_noise(eps, seed=99, tick=tick)
+        o = co.tick(sp, g.path, U, idx, x0, eps.cpu().numpy())
+        u0, useq = eng.step(x0, None, seed=99, tick=tick)
+        assert np.max(np.abs(useq - o["U_after"])) <= U_ATOL, (model, tick, np.max(np.abs(useq - o["U_after"])))
+        st = eng.stats()
+        assert abs(st["rho"] - o["rho"]) <= 1e-5 * abs(o["rho"]) + 1e-6
+        assert abs(st["eta"] - o["eta"]) <= 2e-4 * o["eta"]
+        U, idx = useq.copy(), st["idx"]
+        assert idx == o["idx_after"]
+    eng.close()
+
+
+def test_grid_shape_does_not_change_the_result():
+    """Counter-based noise + balanced contiguous ranges: K not a multiple of the block size."""
+    g = Golden("diffdrive_pe0.05")
+    outs = []
+    for K in (1000, 1000):
+        sp = orc.diffdrive_spec(K=K, T=30, param_exploration=0.05, cost_mode="sum", waypoint_mode="frozen")
+        sp.temperature = 1.0
+        eng = engine_from_spec(sp, g.path)
+        eps = torch.zeros(sp.K, sp.T, 2, dtype=torch.float32, device="cuda")
+        eng.generate_noise(eps, seed=5, tick=0)
+        u0, useq = eng.step(np.zeros(3), None, seed=5, tick=0)
+        o = co.tick(sp, g.path, np.zeros((30, 2)), 0, np.zeros(3), eps.cpu().numpy())
+        assert np.max(np.abs(useq - o["U_after"])) <= U_ATOL
+        outs.append(useq.copy())
+        eng.close()
+    assert np.array_equal(outs[0], outs[1])                    # deterministic
+
+
+def test_large_K_full_size_property():
+    """BASELINE size K=1M, T=50 (diff-drive, sum/frozen, Philox): the device tick equals the C
+    oracle fed the exported noise; weights sum to one; update is invariant to a global cost shift."""
+    g = Golden("diffdrive_pe0.05")
+    K, T = 1 << 20, 50
+    sp = orc.diffdrive_spec(K=K, T=T, param_exploration=0.05, param_lambda=1.0, cost_mode="sum", waypoint_mode="frozen")
+    sp.temperature = 5.0
+    eng = engine_from_spec(sp, g.path)
+    x0 = np.array([0.5, 0.6, 0.7])
+    eps = torch.zeros(K, T, 2, dtype=torch.float32, device="cuda")
+    eng.generate_noise(eps, seed=2024, tick=3)
+    S = torch.zeros(K, dtype=torch.float32, device="cuda")
+    eng.rollout_costs(x0, S, None, seed=2024, tick=3)
+    eps_h = eps.cpu().numpy()
+    So, _, _ = co.costs(sp, g.path, np.zeros((T, 2)), 0, x0, eps_h)
+    frac, worst = cost_mismatch(S.cpu().numpy(), So, rtol=COST_RTOL)
+    assert frac <= 2e-6, (frac, worst)        # arg-min near-ties may flip for O(1) samples in a million
+    eng.set_waypoint_idx(0)
+    u0, useq = eng.step(x0, None, seed=2024, tick=3)
+    o = co.update(sp, g.path, np.zeros((T, 2)), So, eps_h)
+    assert np.max(np.abs(useq - o["U_after"])) <= U_ATOL
+    st = eng.stats()
+    assert abs(st["eta"] - o["eta"]) <= 1e-3 * o["eta"]
+    # shift invariance: K2 on S + c gives the same update
+    u0b, useqb, _ = eng.reduce_update(S + 123.0, None, seed=2024, tick=3)
+    eng.set_nominal(np.zeros((T, 2), np.float32))
+    u0a, useqa, _ = eng.reduce_update(S, None, seed=2024, tick=3)
+    assert np.max(np.abs(useqa - useqb)) <= 2e-4
+    eng.close()
+
+
+def test_drop_in_classes_mirror_the_reference_interface():
+    from mppi_b200.mppi_differential_drive import MPPIAlgorithms
+    from mppi_b200.mppi_race_car_obstacle import MPPIRacecarController
+    g = Golden("diffdrive_pe0.05")
+    m = g.meta
+    ctrl = MPPIAlgorithms(
+        delta_t=m["delta_t"], ref_path=g.path, max_speed=m["max_speed"], max_omega=m["max_omega"],
+        num_samples_K=m["num_samples_K"], num_horizons_T=m["num_horizons_T"],
+        param_exploration=m["param_exploration"], param_lambda=m["param_lambda"], param_alpha=m["param_alpha"],
+        sigma=np.array([[0.1, 0.0], [0.0, 0.01]]), stage_cost_weight=np.array([5.0, 5.0, 10.0]),
+        terminal_cost_weight=np.array([5.0, 5.0, 10.0]), visualize_optimal_traj=False, visualze_sampled_trajs=False)
+    x = g.rec["x0"][0]
+    for i in range(g.n_ticks):
+        u0, u, traj, samp = ctrl._calc_input_control(g.rec["x0"][i], noise=g.eps[i])
+        assert u.dtype == np.float64 and u.shape == (30, 2) and traj.shape == (30, 3) and samp.shape == (256, 30, 3)
+        assert u is ctrl.u_prev and np.array_equal(u0, u[0])                  # aliasing (A2, Q8)
+        assert np.max(np.abs(u - g.rec["U_after"][i])) <= U_ATOL
+        assert ctrl.prev_way_point_idx == int(g.rec["idx_after"][i])
+    g2 = Golden("racecar_alpha0.9")
+    rc = MPPIRacecarController(horizon_step_T=50, number_of_samples_K=128, param_alpha=0.9,
+                               visualize_optimal_traj=False, visualze_sampled_trajs=False)
+    rc.ref_path = g2.path                                                       # like the reference main (:332)
+    for i in range(2):
+        u0, u, traj, samp = rc._calc_control_input(g2.rec["x0"][i], noise=g2.eps[i])
+        assert u.dtype == np.float32 and traj.shape == (50, 4)
+        assert np.max(np.abs(u - g2.rec["U_after"][i])) <= U_ATOL
+        assert rc.prev_waypoints_idx == int(g2.rec["idx_after"][i])
+    # Philox path runs without injected noise and moves the nominal
+    u0, u, _, _ = rc._calc_control_input(g2.rec["x0"][2])
+    assert np.all(np.isfinite(u))

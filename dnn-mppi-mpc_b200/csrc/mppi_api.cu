@@ -57,7 +57,7 @@ struct mppi_handle_s {
     float4 *d_path = nullptr;
     float *d_U = nullptr, *d_M = nullptr, *d_S = nullptr, *d_part = nullptr, *d_out = nullptr;
     float *d_x0 = nullptr;
-    int *d_idx = nullptr;
+    int *d_idx = nullptr, *d_NC = nullptr;
     unsigned *d_ticket = nullptr;
     float *h_out = nullptr, *h_out_dev = nullptr;     // mapped pinned record of robot 0
     // strict mode
@@ -228,6 +228,7 @@ int mppi_create(const mppi_config_t *cfg, mppi_handle_t *out) {
     CKC(cudaMemset(h->d_U, 0, sizeof(float) * R * T * 2));
     CKC(cudaMalloc(&h->d_M, sizeof(float) * T * T));
     CKC(cudaMalloc(&h->d_S, sizeof(float) * (size_t)R * K));
+    CKC(cudaMalloc(&h->d_NC, sizeof(int) * (size_t)K));
     CKC(cudaMalloc(&h->d_part, sizeof(float) * (size_t)R * gx * MPPI_NF(T)));
     CKC(cudaMalloc(&h->d_out, sizeof(float) * (size_t)R * MPPI_OUT_STRIDE));
     CKC(cudaMemset(h->d_out, 0, sizeof(float) * (size_t)R * MPPI_OUT_STRIDE));
@@ -284,7 +285,7 @@ int mppi_destroy(mppi_handle_t h) {
     if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
     if (h->mlp) mlp_destroy(h->mlp);
     cudaFree(h->d_path); cudaFree(h->d_U); cudaFree(h->d_M); cudaFree(h->d_S); cudaFree(h->d_part);
-    cudaFree(h->d_out); cudaFree(h->d_idx); cudaFree(h->d_ticket); cudaFree(h->d_first);
+    cudaFree(h->d_out); cudaFree(h->d_idx); cudaFree(h->d_NC); cudaFree(h->d_ticket); cudaFree(h->d_first);
     cudaFree(h->d_bp_n); cudaFree(h->d_bp_s); cudaFree(h->d_send); cudaFree(h->d_recv); cudaFree(h->d_x0);
     if (h->h_out) cudaFreeHost(h->h_out);
     if (h->h_first) cudaFreeHost(h->h_first);
@@ -425,7 +426,7 @@ static int host_nearest(mppi_handle_t h, int s, double x, double y) {
 
 // Strict waypoint mode: host-driven multi-pass rollout.  Leaves the costs
 // in d_S (or dS_user) and returns the index after the tick.
-static int strict_costs(mppi_handle_t h, const double *x0, const float *d_eps, float *dS, int *idx_after) {
+static int strict_costs(mppi_handle_t h, const double *x0, const float *d_eps, float *dS_user, int *idx_after) {
     int idx0 = 0;
     CK(h, cudaMemcpyAsync(&idx0, h->d_idx, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     CK(h, cudaStreamSynchronize(h->stream));
@@ -433,7 +434,7 @@ static int strict_costs(mppi_handle_t h, const double *x0, const float *d_eps, f
     std::vector<unsigned> bpn{0u};
     std::vector<int> bps{s0};
     TickArgs a = h->args;
-    a.S = dS; a.eps = d_eps;
+    a.S = h->d_S; a.NC = h->d_NC; a.S_user = dS_user; a.eps = d_eps;
     const int T = h->cfg.T;
     int k_first = 0;
     unsigned check_from = 0;
@@ -505,11 +506,11 @@ static int step_common(mppi_handle_t h, const double *x0, const float *d_eps, ui
         if (rc2 != MPPI_OK) return rc2;
     } else if (h->strict) {
         int idx_after = 0;
-        int rc = strict_costs(h, x0, d_eps, h->d_S, &idx_after);
+        int rc = strict_costs(h, x0, d_eps, nullptr, &idx_after);
         if (rc != MPPI_OK) return rc;
         if (h->timing) CK(h, cudaEventRecord(h->ev[1], h->stream));
         TickArgs a = h->args;
-        a.S = h->d_S; a.eps = d_eps;
+        a.S = h->d_S; a.NC = h->d_NC; a.eps = d_eps;
         a.flags = F_UPDATE | F_FROM_S | F_HOST_IDX;
         a.idx_host = idx_after;
         rc = launch_update(h, a, d_eps != nullptr);

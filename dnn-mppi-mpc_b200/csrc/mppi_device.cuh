@@ -50,6 +50,8 @@ struct TickArgs {
     const float *M;                   // [T][T] filter operator
     const float *eps;                 // injected noise (K,T,2) or null
     float *S;                         // [R][K] costs out (F_WRITE_S) / in (F_FROM_S)
+    int *NC;                          // [K] collided-evaluation counts kept apart from S (strict path), or null
+    float *S_user;                    // [K] combined cost smooth + 1e10*n for the caller (strict path), or null
     float *part;                      // [R][B][NF]
     unsigned *ticket;                 // [R]
     float *out;                       // [R][MPPI_OUT_STRIDE]
@@ -62,7 +64,8 @@ struct TickArgs {
 // Philox4x32-10 (Salmon et al. SC'11) + Box-Muller.  Replaces np.random.multivariate_normal
 // in _calc_epsilon (mppi_differential_drive.py:273-283).  Spec: oracle/mppi_oracle.py:philox_noise.
 //   counter = (global sample k, timestep pair t/2, tick, robot), key = seed
-//   u_i = ((r_i >> 9) + 0.5) * 2^-23  in (0,1);  z = sqrt(-2 ln u_a) * (cos, sin)(2 pi u_b)
+//   u_i = ((r_i >> 9) + 0.5) * 2^-23  in (0,1);  z = sqrt(-2 ln u_a) * (cos, sin)(2 pi (u_b - 1/2))
+//   (angle in (-pi, pi): the range where MUFU.SIN/COS are most accurate)
 //   outputs (r0,r1) -> timestep 2p, (r2,r3) -> timestep 2p+1;  eps = chol(Sigma) z
 // All float ops use explicit-rounding intrinsics so every kernel produces identical bits.
 // ------------------------------------------------------------------------------------------
@@ -86,7 +89,7 @@ __device__ __forceinline__ float u01_open(uint32_t r) {
 __device__ __forceinline__ void box_muller(uint32_t ra, uint32_t rb, float &z0, float &z1) {
     const float ua = u01_open(ra), ub = u01_open(rb);
     const float rad = __fsqrt_rn(__fmul_rn(-1.3862943611198906f, __log2f(ua)));   // sqrt(-2 ln ua)
-    const float ang = __fmul_rn(6.2831853071795865f, ub);
+    const float ang = __fmul_rn(6.2831853071795865f, __fadd_rn(ub, -0.5f));
     z0 = __fmul_rn(rad, __cosf(ang));
     z1 = __fmul_rn(rad, __sinf(ang));
 }

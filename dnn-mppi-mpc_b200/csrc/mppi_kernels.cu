@@ -164,7 +164,8 @@ __global__ void __launch_bounds__(MPPI_BLOCK) mppi_tick_kernel(const __grid_cons
     {
         int nw = a.n_path - s_new; nw = nw < a.window ? nw : a.window;
         const int nw4 = (nw + 3) & ~3;
-        for (int j = tid; j < nw4; j += MPPI_BLOCK) {
+        const int fill = (a.window + 3) & ~3;            // static-window kernels read all of it
+        for (int j = tid; j < fill; j += MPPI_BLOCK) {
             if (j < nw) {
                 const float4 p = a.path[s_new + j];
                 sm.wx[j] = p.x; sm.wy[j] = p.y; sm.wref[j] = p;
@@ -196,7 +197,7 @@ __global__ void __launch_bounds__(MPPI_BLOCK) mppi_tick_kernel(const __grid_cons
         int ncoll = INT_MAX;
         if (active) {
             if (a.flags & F_FROM_S) {
-                smooth = Srow[k]; ncoll = 0;
+                smooth = Srow[k]; ncoll = a.NC ? a.NC[k] : 0;
             } else {
                 rollout_sample<MODEL, COLL, SUM, INJ, WIN>(a, sm, kg, k, (uint32_t)robot,
                                                            (int)kg < a.n_exploit, smooth, ncoll);
@@ -393,7 +394,9 @@ __global__ void __launch_bounds__(MPPI_BLOCK) mppi_strict_kernel(const __grid_co
             else { acc += c; nc += hit ? 1 : 0; }
         }
     }
-    a.S[k] = acc + MPPI_PENALTY * (float)nc;
+    a.S[k] = acc;
+    a.NC[k] = nc;
+    if (a.S_user) a.S_user[k] = acc + MPPI_PENALTY * (float)nc;
 }
 
 }  // namespace

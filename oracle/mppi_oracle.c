@@ -73,7 +73,7 @@ static inline void philox_eps(const oracle_cfg_t *c, uint64_t seed, uint32_t tic
     philox4x32_10(ctr, (uint32_t)seed, (uint32_t)(seed >> 32));
     int h = (t & 1) * 2;
     double u1 = ((ctr[h] >> 9) + 0.5) * 0x1p-23, u2 = ((ctr[h + 1] >> 9) + 0.5) * 0x1p-23;
-    double rad = sqrt(-2.0 * log(u1)), ang = 6.283185307179586476925 * u2;
+    double rad = sqrt(-2.0 * log(u1)), ang = 6.283185307179586476925 * (u2 - 0.5);
     double z0 = rad * cos(ang), z1 = rad * sin(ang);
     e[0] = c->chol[0] * z0;
     e[1] = c->chol[2] * z0 + c->chol[3] * z1;

@@ -48,7 +48,8 @@ struct mppi_handle_s {
     cudaStream_t stream = nullptr;
     bool own_stream = false;
     int n_sm = 148, occ = 1, nx = 3;
-    int grid_x = 1;
+    int grid_x = 1, grid_x_stash = 1;    // CTAs per robot: regenerate-noise kernels / stash kernels
+    bool stash = false;                  // Philox ticks keep the chunk's noise in shared memory
     bool sum = false, strict = false;
     bool have_path = false;
     std::vector<double> path_h;          // host copy for the strict-mode step 1 (literal FP64)
@@ -218,11 +219,17 @@ int mppi_create(const mppi_config_t *cfg, mppi_handle_t *out) {
     h->own_stream = true;
 
     const int R = c.n_robots, T = c.T, K = c.K;
-    h->occ = mppi_tick_occupancy(c.model, c.collision, h->sum);
     const int chunks = (K + MPPI_BLOCK - 1) / MPPI_BLOCK;
+    const int tick_model = (c.model == MPPI_MODEL_DIFFDRIVE_MLP) ? MPPI_MODEL_DIFFDRIVE : c.model;
+    h->occ = std::max(1, mppi_tick_occupancy(tick_model, c.collision, h->sum, false, c.window, T, false));
+    const int occ_stash = mppi_tick_occupancy(tick_model, c.collision, h->sum, false, c.window, T, true);
+    h->stash = occ_stash >= 2 && c.model != MPPI_MODEL_DIFFDRIVE_MLP;
     int gx = (h->n_sm * h->occ + R - 1) / R;
     gx = std::max(1, std::min(gx, chunks));
     h->grid_x = gx;
+    int gxs = (h->n_sm * std::max(1, occ_stash) + R - 1) / R;
+    h->grid_x_stash = std::max(1, std::min(gxs, chunks));
+    gx = std::max(h->grid_x, h->grid_x_stash);
 
     CKC(cudaMalloc(&h->d_U, sizeof(float) * R * T * 2));
     CKC(cudaMemset(h->d_U, 0, sizeof(float) * R * T * 2));
@@ -466,12 +473,14 @@ static int strict_costs(mppi_handle_t h, const double *x0, const float *d_eps, f
 }
 
 static int launch_update(mppi_handle_t h, const TickArgs &a, bool inj) {
-    dim3 grid(h->grid_x, h->cfg.n_robots);
+    const bool stash = h->stash && !inj && !(a.flags & F_FROM_S);
+    dim3 grid(stash ? h->grid_x_stash : h->grid_x, h->cfg.n_robots);
+    const int model = (h->cfg.model == MPPI_MODEL_DIFFDRIVE_MLP) ? MPPI_MODEL_DIFFDRIVE : h->cfg.model;
     if (h->world > 1 && (a.flags & F_UPDATE)) {
         TickArgs b = a;
         b.flags |= F_TRIPLE_OUT;
         b.triple_out = h->d_send;
-        CK(h, mppi_launch_tick(b, h->cfg.model, h->cfg.collision, h->sum, inj, grid, h->stream));
+        CK(h, mppi_launch_tick(b, model, h->cfg.collision, h->sum, inj, stash, grid, h->stream));
         const size_t nf = MPPI_NF(h->cfg.T);
         ncclResult_t r = g_nccl.AllGather(h->d_send, h->d_recv, nf, ncclFloat, h->comm, h->stream);
         if (r != ncclSuccess) { h->err = g_nccl.GetErrorString(r); return MPPI_E_NCCL; }
@@ -479,7 +488,7 @@ static int launch_update(mppi_handle_t h, const TickArgs &a, bool inj) {
         h->tm.launches += 2;
         return MPPI_OK;
     }
-    CK(h, mppi_launch_tick(a, h->cfg.model, h->cfg.collision, h->sum, inj, grid, h->stream));
+    CK(h, mppi_launch_tick(a, model, h->cfg.collision, h->sum, inj, stash, grid, h->stream));
     h->tm.launches++;
     return MPPI_OK;
 }
@@ -565,7 +574,7 @@ int mppi_rollout_costs(mppi_handle_t h, const double *x0, const float *d_eps, ui
         TickArgs a = h->args;
         a.eps = d_eps; a.S = d_S; a.flags = F_WRITE_S;
         dim3 grid(h->grid_x, 1);
-        CK(h, mppi_launch_tick(a, h->cfg.model, h->cfg.collision, h->sum, d_eps != nullptr, grid, h->stream));
+        CK(h, mppi_launch_tick(a, h->cfg.model, h->cfg.collision, h->sum, d_eps != nullptr, false, grid, h->stream));
         h->tm.launches++;
     }
     CK(h, cudaStreamSynchronize(h->stream));
@@ -615,8 +624,8 @@ int mppi_step_batched(mppi_handle_t h, const float *d_x0, uint64_t seed, uint64_
                             h->cfg.n_robots, cudaMemcpyDeviceToDevice, h->stream));
     a.x0_dev = h->d_x0; a.eps = nullptr; a.S = nullptr; a.flags = F_UPDATE; a.u0_out = d_u0_out;
     a.out_host = nullptr;
-    dim3 grid(h->grid_x, h->cfg.n_robots);
-    CK(h, mppi_launch_tick(a, h->cfg.model, h->cfg.collision, h->sum, false, grid, h->stream));
+    dim3 grid(h->stash ? h->grid_x_stash : h->grid_x, h->cfg.n_robots);
+    CK(h, mppi_launch_tick(a, h->cfg.model, h->cfg.collision, h->sum, false, h->stash, grid, h->stream));
     h->tm.launches++;
     return MPPI_OK;
 }

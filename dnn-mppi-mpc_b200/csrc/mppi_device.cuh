@@ -9,6 +9,9 @@
 
 #define MPPI_BLOCK 256
 #define MPPI_WARPS (MPPI_BLOCK / 32)
+#ifndef MPPI_MIN_BLOCKS
+#define MPPI_MIN_BLOCKS 3              // resident CTAs per SM the tick kernel is register-budgeted for
+#endif
 #define MPPI_PENALTY 1.0e10f           // mppi_race_car_obstacle.py:157
 #define MPPI_SENTINEL 1.0e18f          // padded window entries: distance^2 = 1e36, never the minimum
 #define MPPI_OUT_HDR 8
@@ -88,7 +91,8 @@ __device__ __forceinline__ float u01_open(uint32_t r) {
 
 __device__ __forceinline__ void box_muller(uint32_t ra, uint32_t rb, float &z0, float &z1) {
     const float ua = u01_open(ra), ub = u01_open(rb);
-    const float rad = __fsqrt_rn(__fmul_rn(-1.3862943611198906f, __log2f(ua)));   // sqrt(-2 ln ua)
+    float rad;                                                                     // sqrt(-2 ln ua)
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(rad) : "f"(__fmul_rn(-1.3862943611198906f, __log2f(ua))));
     const float ang = __fmul_rn(6.2831853071795865f, __fadd_rn(ub, -0.5f));
     z0 = __fmul_rn(rad, __cosf(ang));
     z1 = __fmul_rn(rad, __sinf(ang));
@@ -113,32 +117,133 @@ __device__ __forceinline__ void philox_eps_pair(const TickArgs &a, uint32_t k, u
 struct TickSmem {
     float2 U[MPPI_MAX_T];                  // nominal
     float2 Q[MPPI_MAX_T];                  // gamma * Sigma^-1 applied to U[t] (row vector u^T Sigma^-1)
-    __align__(16) float wx[MPPI_MAX_WINDOW];   // window SoA, padded with sentinels to a multiple of 4
-    __align__(16) float wy[MPPI_MAX_WINDOW];
-    float4 wref[MPPI_MAX_WINDOW];          // (x, y, yaw, v) for the lookup after the argmin
+    __align__(16) float wx[MPPI_MAX_WINDOW];   // window SoA of NEGATED coordinates, padded with sentinels
+    __align__(16) float wy[MPPI_MAX_WINDOW];   // to a multiple of 16 entries (static window 20: exactly 20)
+    float2 wyv[MPPI_MAX_WINDOW];           // (yaw, v) of each window entry, for the lookup after the argmin
     float x0[4];
-    int win_start, n_win4;                 // absolute index of window entry 0; padded length / 4
+    int win_start, n_win16;                // absolute index of window entry 0; padded length / 16
 };
+
+// ---- packed FP32 (Blackwell FADD2 / FMUL2 / FFMA2): two FP32 ops per issue slot ------------
+__device__ __forceinline__ float2 f2_add(float2 a, float2 b) {
+    unsigned long long ra = *reinterpret_cast<unsigned long long *>(&a), rb = *reinterpret_cast<unsigned long long *>(&b), rd;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(ra), "l"(rb));
+    return *reinterpret_cast<float2 *>(&rd);
+}
+__device__ __forceinline__ float2 f2_mul(float2 a, float2 b) {
+    unsigned long long ra = *reinterpret_cast<unsigned long long *>(&a), rb = *reinterpret_cast<unsigned long long *>(&b), rd;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(ra), "l"(rb));
+    return *reinterpret_cast<float2 *>(&rd);
+}
+__device__ __forceinline__ float2 f2_fma(float2 a, float2 b, float2 c) {
+    unsigned long long ra = *reinterpret_cast<unsigned long long *>(&a), rb = *reinterpret_cast<unsigned long long *>(&b),
+                       rc = *reinterpret_cast<unsigned long long *>(&c), rd;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
+    return *reinterpret_cast<float2 *>(&rd);
+}
+
+// First-min argmin over one chunk of CH window entries (CH % 4 == 0), branch-free and almost
+// entirely on the FMA pipe:  d_j = (x-px_j)^2 + (y-py_j)^2 as FFMA2 pairs;  m = min_j d_j (FMNMX3);
+// key_j = (d_j - m) * 2^100 + j, which is exactly j where d_j == m and >= 2^76 elsewhere, so
+// min_j key_j is the FIRST index attaining the minimum (the d.index(min(d)) / np.argmin rule).
+// The window arrays hold NEGATED coordinates so the differences are plain packed adds.
+#ifndef MPPI_ARGMIN_PACK
+#define MPPI_ARGMIN_PACK 2      // 2: all FP32 work packed (FFMA2); 1: differences scalar, rest packed; 0: all scalar
+#endif
+template <int CH>
+__device__ __forceinline__ void chunk_argmin(const float4 *nwx4, const float4 *nwy4, float x, float y,
+                                             float &m_out, float &key_out) {
+    const float2 xx = make_float2(x, x), yy = make_float2(y, y);
+    float2 d[CH / 2];
+#pragma unroll
+    for (int q = 0; q < CH / 4; ++q) {
+        const float4 X = nwx4[q], Y = nwy4[q];
+#if MPPI_ARGMIN_PACK == 2
+        const float2 dxa = f2_add(xx, make_float2(X.x, X.y)), dya = f2_add(yy, make_float2(Y.x, Y.y));
+        const float2 dxb = f2_add(xx, make_float2(X.z, X.w)), dyb = f2_add(yy, make_float2(Y.z, Y.w));
+        d[2 * q] = f2_fma(dya, dya, f2_mul(dxa, dxa));
+        d[2 * q + 1] = f2_fma(dyb, dyb, f2_mul(dxb, dxb));
+#elif MPPI_ARGMIN_PACK == 1
+        const float2 dxa = make_float2(x + X.x, x + X.y), dya = make_float2(y + Y.x, y + Y.y);
+        const float2 dxb = make_float2(x + X.z, x + X.w), dyb = make_float2(y + Y.z, y + Y.w);
+        d[2 * q] = f2_fma(dya, dya, f2_mul(dxa, dxa));
+        d[2 * q + 1] = f2_fma(dyb, dyb, f2_mul(dxb, dxb));
+#else
+        float dx, dy;
+        dx = x + X.x; dy = y + Y.x; d[2 * q].x = fmaf(dy, dy, dx * dx);
+        dx = x + X.y; dy = y + Y.y; d[2 * q].y = fmaf(dy, dy, dx * dx);
+        dx = x + X.z; dy = y + Y.z; d[2 * q + 1].x = fmaf(dy, dy, dx * dx);
+        dx = x + X.w; dy = y + Y.w; d[2 * q + 1].y = fmaf(dy, dy, dx * dx);
+#endif
+    }
+    float m = fminf(d[0].x, d[0].y);
+#pragma unroll
+    for (int i = 1; i < CH / 2; ++i) m = fminf(fminf(m, d[i].x), d[i].y);
+    const float2 nm = make_float2(-m, -m), huge = make_float2(1.2676506e30f, 1.2676506e30f);
+    float key = CUDART_INF_F;
+#pragma unroll
+    for (int i = 0; i < CH / 2; ++i) {
+#if MPPI_ARGMIN_PACK >= 1
+        const float2 k2 = f2_fma(f2_add(d[i], nm), huge, make_float2((float)(2 * i), (float)(2 * i + 1)));
+#else
+        const float2 k2 = make_float2(fmaf(d[i].x - m, 1.2676506e30f, (float)(2 * i)), fmaf(d[i].y - m, 1.2676506e30f, (float)(2 * i + 1)));
+#endif
+        key = fminf(fminf(key, k2.x), k2.y);
+    }
+    m_out = m;
+    key_out = key;
+}
 
 // A8: first-min argmin of squared xy distance over the window
 // (mppi_differential_drive.py:201-220, mppi_race_car_obstacle.py:173-191).
 template <int WIN>
 __device__ __forceinline__ int nearest_wp(const TickSmem &sm, float x, float y) {
-    const float4 *wx4 = reinterpret_cast<const float4 *>(sm.wx);
-    const float4 *wy4 = reinterpret_cast<const float4 *>(sm.wy);
-    float bd = CUDART_INF_F;
+    const float4 *nwx4 = reinterpret_cast<const float4 *>(sm.wx);
+    const float4 *nwy4 = reinterpret_cast<const float4 *>(sm.wy);
+    if (WIN == 20) {
+        float m, key;
+        chunk_argmin<20>(nwx4, nwy4, x, y, m, key);
+        return __float2int_rn(key);
+    }
+    // dynamic window: chunks of 16 entries (the window is padded with sentinels to a multiple of 16)
+    float bm = CUDART_INF_F;
     int bj = 0;
-    const int n4 = WIN > 0 ? WIN / 4 : sm.n_win4;
-#pragma unroll
-    for (int q = 0; q < n4; ++q) {
-        const float4 X = wx4[q], Y = wy4[q];
-        float dx, dy, d;
-        dx = x - X.x; dy = y - Y.x; d = dx * dx + dy * dy; if (d < bd) { bd = d; bj = 4 * q; }
-        dx = x - X.y; dy = y - Y.y; d = dx * dx + dy * dy; if (d < bd) { bd = d; bj = 4 * q + 1; }
-        dx = x - X.z; dy = y - Y.z; d = dx * dx + dy * dy; if (d < bd) { bd = d; bj = 4 * q + 2; }
-        dx = x - X.w; dy = y - Y.w; d = dx * dx + dy * dy; if (d < bd) { bd = d; bj = 4 * q + 3; }
+    const int nch = sm.n_win16;
+    for (int c = 0; c < nch; ++c) {
+        float m, key;
+        chunk_argmin<16>(nwx4 + 4 * c, nwy4 + 4 * c, x, y, m, key);
+        if (m < bm) { bm = m; bj = 16 * c + __float2int_rn(key); }       // strict <: the earlier chunk wins ties
     }
     return bj;
+}
+
+__device__ __forceinline__ float4 window_ref(const TickSmem &sm, int j) {
+    const float2 yv = sm.wyv[j];
+    return make_float4(-sm.wx[j], -sm.wy[j], yv.x, yv.y);
+}
+
+// sin and cos together, ~1.5 ulp for |x| < 1e4 (headings never leave that range): three-constant
+// Cody-Waite reduction by pi/2 with the quadrant taken from the magic-number rounding (no F2I, no
+// MUFU, no slow path), then the Cephes single-precision minimax polynomials on [-pi/4, pi/4].
+// Replaces np.cos / np.sin in _state_transition (mppi_differential_drive.py:194-195).
+__device__ __forceinline__ void sincos_cw(float x, float &s, float &c) {
+    const float t = fmaf(x, 0.636619772f, 12582912.f);
+    const int q = __float_as_int(t);
+    const float k = t - 12582912.f;
+    float r = fmaf(k, -1.5707963705062866f, x);          // pi/2 = hi + mid + lo (float32 pieces)
+    r = fmaf(k, 4.371138828673793e-08f, r);
+    r = fmaf(k, 1.7151245100058819e-15f, r);
+    const float r2 = r * r;
+    float sp = fmaf(r2, -1.9515295891e-4f, 8.3321608736e-3f);
+    sp = fmaf(sp, r2, -1.6666654611e-1f);
+    sp = fmaf(sp * r2, r, r);
+    float cp = fmaf(r2, 2.443315711809948e-5f, -1.388731625493765e-3f);
+    cp = fmaf(cp, r2, 4.166664568298827e-2f);
+    cp = fmaf(cp, r2, -0.5f);
+    cp = fmaf(cp, r2, 1.0f);
+    const float ss = (q & 1) ? cp : sp, cc = (q & 1) ? sp : cp;
+    s = __int_as_float(__float_as_int(ss) ^ ((q << 30) & 0x80000000));
+    c = __int_as_float(__float_as_int(cc) ^ (((q + 1) << 30) & 0x80000000));
 }
 
 // exact (yaw + 2pi) mod 2pi with the sign of the divisor (race-car :151): the FMA remainder
@@ -219,11 +324,11 @@ __device__ __forceinline__ float clampf(float v, float lim) { return fminf(fmaxf
 // evaluations separately so 1e10 * n never swallows the tracking cost.
 template <int MODEL, int COLL, bool SUM, bool INJ, int WIN>
 __device__ __forceinline__ void rollout_sample(const TickArgs &a, const TickSmem &sm, uint32_t kg, int klocal,
-                                               uint32_t robot, bool exploit, float &smooth, int &ncoll) {
+                                               uint32_t robot, bool exploit, float2 *stash, float &smooth, int &ncoll) {
     const int T = a.T;
     float z[4] = {sm.x0[0], sm.x0[1], sm.x0[2], sm.x0[3]};
     float cs, sn;
-    sincosf(z[2], &sn, &cs);
+    sincos_cw(z[2], sn, cs);
     float acc = 0.f;
     int nc = 0;
     float v0 = 0.f, v1 = 0.f;
@@ -241,14 +346,15 @@ __device__ __forceinline__ void rollout_sample(const TickArgs &a, const TickSmem
         for (int h = 0; h < 2; ++h) {
             const int t = tp + h;
             if (t < T) {
+                if (stash) stash[t * MPPI_BLOCK] = make_float2(e[2 * h], e[2 * h + 1]);
                 const float2 u = sm.U[t];
                 v0 = clampf(exploit ? __fadd_rn(u.x, e[2 * h]) : e[2 * h], a.umax0);       // A4, A5
                 v1 = clampf(exploit ? __fadd_rn(u.y, e[2 * h + 1]) : e[2 * h + 1], a.umax1);
                 dyn_step<MODEL>(a, z, v0, v1, cs, sn);
-                sincosf(z[2], &sn, &cs);
+                sincos_cw(z[2], sn, cs);
                 if (SUM) {
                     const int j = nearest_wp<WIN>(sm, z[0], z[1]);
-                    const float4 ref = sm.wref[j];
+                    const float4 ref = window_ref(sm, j);
                     const float yaw_eff = a.yaw_wrap ? wrap_2pi(z[2]) : z[2];
                     float c = tracking_cost<MODEL>(ref, z, yaw_eff, a.sw);
                     if (a.use_gamma) { const float2 q = sm.Q[t]; c += q.x * v0 + q.y * v1; }
@@ -266,7 +372,7 @@ __device__ __forceinline__ void rollout_sample(const TickArgs &a, const TickSmem
     }
     if (!SUM) {                                 // Q1: only the last stage cost survives, plus terminal
         const int j = nearest_wp<WIN>(sm, z[0], z[1]);
-        const float4 ref = sm.wref[j];
+        const float4 ref = window_ref(sm, j);
         const float yaw_eff = a.yaw_wrap ? wrap_2pi(z[2]) : z[2];
         acc = tracking_cost<MODEL>(ref, z, yaw_eff, a.sw);
         if (a.use_gamma) { const float2 q = sm.Q[T - 1]; acc += q.x * v0 + q.y * v1; }

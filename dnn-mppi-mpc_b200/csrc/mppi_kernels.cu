@@ -114,11 +114,11 @@ __device__ void finalize_tick(const TickArgs &a, int robot, int idx_new, MergeSm
 }
 
 struct RunSmem {
-    int n;                     // running lexicographic minimum
+    int n;                     // running lexicographic minimum of this block
     float s;
     float eta, e2;
-    float N[2 * MPPI_MAX_T];
-    float warpN[MPPI_WARPS][2 * MPPI_MAX_T];
+    float N[2 * MPPI_MAX_T];   // running sum of w * eps, relative to (n, s)
+    float w[MPPI_BLOCK];       // stash mode: this chunk's weights
     float warp_eta[MPPI_WARPS], warp_e2[MPPI_WARPS];
     float red_s[MPPI_WARPS];
     int red_n[MPPI_WARPS];
@@ -126,11 +126,20 @@ struct RunSmem {
     unsigned ticket;
 };
 
-template <int MODEL, int COLL, bool SUM, bool INJ, int WIN>
-__global__ void __launch_bounds__(MPPI_BLOCK) mppi_tick_kernel(const __grid_constant__ TickArgs a) {
+// Dynamic shared memory of the tick kernel:
+//   STASH = true : float2 eps[T][MPPI_BLOCK] -- the noise of the chunk being rolled out, written in
+//                  pass 1 and consumed by the weighted column sums, so Philox + Box-Muller run once.
+//   STASH = false: float warpN[MPPI_WARPS][2*MPPI_MAX_T] -- per-warp partial sums of the
+//                  regenerate-the-noise path (injected noise, K2 alone, horizons too long to stash).
+extern __shared__ __align__(16) unsigned char mppi_dyn_smem[];
+
+template <int MODEL, int COLL, bool SUM, bool INJ, int WIN, bool STASH>
+__global__ void __launch_bounds__(MPPI_BLOCK, MPPI_MIN_BLOCKS) mppi_tick_kernel(const __grid_constant__ TickArgs a) {
     __shared__ TickSmem sm;
     __shared__ RunSmem run;
     __shared__ MergeSmem ms;
+    float2 *stash = reinterpret_cast<float2 *>(mppi_dyn_smem);
+    float (*warpN)[2 * MPPI_MAX_T] = reinterpret_cast<float (*)[2 * MPPI_MAX_T]>(mppi_dyn_smem);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int robot = blockIdx.y, b = blockIdx.x, B = gridDim.x;
     const int T = a.T, K = a.K;
@@ -163,18 +172,17 @@ __global__ void __launch_bounds__(MPPI_BLOCK) mppi_tick_kernel(const __grid_cons
     }
     {
         int nw = a.n_path - s_new; nw = nw < a.window ? nw : a.window;
-        const int nw4 = (nw + 3) & ~3;
-        const int fill = (a.window + 3) & ~3;            // static-window kernels read all of it
+        // static-window kernels read exactly 20 entries, dynamic ones whole chunks of 16
+        const int fill = (WIN == 20) ? 20 : ((nw + 15) & ~15);
         for (int j = tid; j < fill; j += MPPI_BLOCK) {
             if (j < nw) {
                 const float4 p = a.path[s_new + j];
-                sm.wx[j] = p.x; sm.wy[j] = p.y; sm.wref[j] = p;
+                sm.wx[j] = -p.x; sm.wy[j] = -p.y; sm.wyv[j] = make_float2(p.z, p.w);
             } else {
-                sm.wx[j] = MPPI_SENTINEL; sm.wy[j] = MPPI_SENTINEL;
-                sm.wref[j] = make_float4(MPPI_SENTINEL, MPPI_SENTINEL, 0.f, 0.f);
+                sm.wx[j] = -MPPI_SENTINEL; sm.wy[j] = -MPPI_SENTINEL; sm.wyv[j] = make_float2(0.f, 0.f);
             }
         }
-        if (tid == 0) { sm.win_start = s_new; sm.n_win4 = nw4 >> 2; }
+        if (tid == 0) { sm.win_start = s_new; sm.n_win16 = fill >> 4; }
         const float *Ur = a.U + (size_t)robot * T * 2;
         for (int t = tid; t < T; t += MPPI_BLOCK) {
             const float u0 = Ur[2 * t], u1 = Ur[2 * t + 1];
@@ -199,12 +207,15 @@ __global__ void __launch_bounds__(MPPI_BLOCK) mppi_tick_kernel(const __grid_cons
             if (a.flags & F_FROM_S) {
                 smooth = Srow[k]; ncoll = a.NC ? a.NC[k] : 0;
             } else {
-                rollout_sample<MODEL, COLL, SUM, INJ, WIN>(a, sm, kg, k, (uint32_t)robot,
-                                                           (int)kg < a.n_exploit, smooth, ncoll);
+                rollout_sample<MODEL, COLL, SUM, INJ, WIN>(a, sm, kg, k, (uint32_t)robot, (int)kg < a.n_exploit,
+                                                           STASH ? stash + tid : nullptr, smooth, ncoll);
                 if (a.flags & F_WRITE_S) Srow[k] = smooth + MPPI_PENALTY * (float)ncoll;
             }
         }
         if (!(a.flags & F_UPDATE)) continue;
+        if (STASH && !active) {                     // tail chunk: idle lanes must not leave garbage (0 * NaN)
+            for (int t = 0; t < T; ++t) stash[t * MPPI_BLOCK + tid] = make_float2(0.f, 0.f);
+        }
 
         // chunk minimum -> new running minimum
         int cn = ncoll; float cs_ = smooth;
@@ -219,55 +230,85 @@ __global__ void __launch_bounds__(MPPI_BLOCK) mppi_tick_kernel(const __grid_cons
         }
         const float rescale = (run.n == INT_MAX) ? 0.f : rel_weight(run.n, run.s, mn, mss, a.inv_temp);
         const float w = active ? rel_weight(ncoll, smooth, mn, mss, a.inv_temp) : 0.f;
+        const float we = warp_sum(w), we2 = warp_sum(w * w);
+        if (lane == 0) { run.warp_eta[warp] = we; run.warp_e2[warp] = we2; }
 
-        // weighted noise: regenerate (Philox) or re-read (injected) this sample's eps row
-        const bool any = __any_sync(0xffffffffu, w > 0.f);
-        if (any) {
-            const float2 *eps_k = INJ ? reinterpret_cast<const float2 *>(a.eps) + (size_t)(active ? k : k_begin) * T : nullptr;
-            for (int tp = 0; tp < T; tp += 2) {
-                float e[4] = {0.f, 0.f, 0.f, 0.f};
-                if (INJ) {
-                    const float2 ea = eps_k[tp];
-                    e[0] = ea.x; e[1] = ea.y;
-                    if (tp + 1 < T) { const float2 eb = eps_k[tp + 1]; e[2] = eb.x; e[3] = eb.y; }
-                } else {
-                    philox_eps_pair(a, kg, (uint32_t)(tp >> 1), (uint32_t)robot, e);
+        if (STASH) {
+            // weighted column sums straight from the stash: warp `warp` owns rows t = warp, warp+8, ...
+            run.w[tid] = w;
+            __syncthreads();
+            float wr[MPPI_BLOCK / 32];
+#pragma unroll
+            for (int i = 0; i < MPPI_BLOCK / 32; ++i) wr[i] = run.w[lane + 32 * i];
+            for (int t = warp; t < T; t += MPPI_WARPS) {
+                const float2 *row = stash + t * MPPI_BLOCK;
+                float ax = 0.f, ay = 0.f;
+#pragma unroll
+                for (int i = 0; i < MPPI_BLOCK / 32; ++i) {
+                    const float2 e = row[lane + 32 * i];
+                    ax = fmaf(wr[i], e.x, ax); ay = fmaf(wr[i], e.y, ay);
                 }
-                // 4 values x 32 lanes -> 4 sums: halving butterfly (6 shuffles instead of 20)
-                float p0 = w * e[0], p1 = w * e[1], p2 = w * e[2], p3 = w * e[3];
-                {
-                    const bool hi = lane & 16;
-                    const float s0 = hi ? p0 : p2, s1 = hi ? p1 : p3;       // send the half we do not keep
-                    const float r0 = __shfl_xor_sync(0xffffffffu, s0, 16), r1 = __shfl_xor_sync(0xffffffffu, s1, 16);
-                    p0 = (hi ? p2 : p0) + r0; p1 = (hi ? p3 : p1) + r1;      // lanes <16 hold (e0,e1), >=16 hold (e2,e3)
-                }
-                {
-                    const bool hi = lane & 8;
-                    const float s0 = hi ? p0 : p1;
-                    const float r0 = __shfl_xor_sync(0xffffffffu, s0, 8);
-                    p0 = (hi ? p1 : p0) + r0;                                 // lane bit3 selects component
-                }
-                p0 += __shfl_xor_sync(0xffffffffu, p0, 4);
-                p0 += __shfl_xor_sync(0xffffffffu, p0, 2);
-                p0 += __shfl_xor_sync(0xffffffffu, p0, 1);
-                // lane 0 -> e[0], lane 8 -> e[1], lane 16 -> e[2], lane 24 -> e[3]
-                if ((lane & 7) == 0) {
-                    const int c = 2 * tp + (lane >> 3);
-                    if (c < 2 * T) run.warpN[warp][c] = p0;
+                // two sums over 32 lanes: exchange halves, then one butterfly (6 shuffles)
+                const bool hi = lane & 16;
+                const float other = __shfl_xor_sync(0xffffffffu, hi ? ax : ay, 16);
+                float p = (hi ? ay : ax) + other;
+                p += __shfl_xor_sync(0xffffffffu, p, 8);
+                p += __shfl_xor_sync(0xffffffffu, p, 4);
+                p += __shfl_xor_sync(0xffffffffu, p, 2);
+                p += __shfl_xor_sync(0xffffffffu, p, 1);
+                if ((lane & 15) == 0) {
+                    const int c = 2 * t + (lane >> 4);
+                    run.N[c] = run.N[c] * rescale + p;
                 }
             }
         } else {
-            for (int c = lane; c < 2 * T; c += 32) run.warpN[warp][c] = 0.f;
-        }
-        const float we = warp_sum(w), we2 = warp_sum(w * w);
-        if (lane == 0) { run.warp_eta[warp] = we; run.warp_e2[warp] = we2; }
-        __syncthreads();
-        for (int c = tid; c < 2 * T; c += MPPI_BLOCK) {
-            float acc = run.N[c] * rescale;
+            // regenerate (Philox) or re-read (injected) this sample's eps row
+            const bool any = __any_sync(0xffffffffu, w > 0.f);
+            if (any) {
+                const float2 *eps_k = INJ ? reinterpret_cast<const float2 *>(a.eps) + (size_t)(active ? k : k_begin) * T : nullptr;
+                for (int tp = 0; tp < T; tp += 2) {
+                    float e[4] = {0.f, 0.f, 0.f, 0.f};
+                    if (INJ) {
+                        const float2 ea = eps_k[tp];
+                        e[0] = ea.x; e[1] = ea.y;
+                        if (tp + 1 < T) { const float2 eb = eps_k[tp + 1]; e[2] = eb.x; e[3] = eb.y; }
+                    } else {
+                        philox_eps_pair(a, kg, (uint32_t)(tp >> 1), (uint32_t)robot, e);
+                    }
+                    // 4 values x 32 lanes -> 4 sums: halving butterfly (6 shuffles instead of 20)
+                    float p0 = w * e[0], p1 = w * e[1], p2 = w * e[2], p3 = w * e[3];
+                    {
+                        const bool hi = lane & 16;
+                        const float s0 = hi ? p0 : p2, s1 = hi ? p1 : p3;
+                        const float r0 = __shfl_xor_sync(0xffffffffu, s0, 16), r1 = __shfl_xor_sync(0xffffffffu, s1, 16);
+                        p0 = (hi ? p2 : p0) + r0; p1 = (hi ? p3 : p1) + r1;
+                    }
+                    {
+                        const bool hi = lane & 8;
+                        const float s0 = hi ? p0 : p1;
+                        const float r0 = __shfl_xor_sync(0xffffffffu, s0, 8);
+                        p0 = (hi ? p1 : p0) + r0;
+                    }
+                    p0 += __shfl_xor_sync(0xffffffffu, p0, 4);
+                    p0 += __shfl_xor_sync(0xffffffffu, p0, 2);
+                    p0 += __shfl_xor_sync(0xffffffffu, p0, 1);
+                    if ((lane & 7) == 0) {
+                        const int c = 2 * tp + (lane >> 3);
+                        if (c < 2 * T) warpN[warp][c] = p0;
+                    }
+                }
+            } else {
+                for (int c = lane; c < 2 * T; c += 32) warpN[warp][c] = 0.f;
+            }
+            __syncthreads();
+            for (int c = tid; c < 2 * T; c += MPPI_BLOCK) {
+                float acc = run.N[c] * rescale;
 #pragma unroll
-            for (int wv = 0; wv < MPPI_WARPS; ++wv) acc += run.warpN[wv][c];
-            run.N[c] = acc;
+                for (int wv = 0; wv < MPPI_WARPS; ++wv) acc += warpN[wv][c];
+                run.N[c] = acc;
+            }
         }
+        __syncthreads();
         if (tid == 0) {
             float e1 = run.eta * rescale, e2 = run.e2 * rescale * rescale;
 #pragma unroll
@@ -352,7 +393,7 @@ __global__ void __launch_bounds__(MPPI_BLOCK) mppi_strict_kernel(const __grid_co
     const bool exploit = (int)kg < a.n_exploit;
     float z[4] = {a.x0[0], a.x0[1], a.x0[2], a.x0[3]};
     float cs, sn;
-    sincosf(z[2], &sn, &cs);
+    sincos_cw(z[2], sn, cs);
     float acc = 0.f;
     int nc = 0;
     int bp = 0;
@@ -367,7 +408,7 @@ __global__ void __launch_bounds__(MPPI_BLOCK) mppi_strict_kernel(const __grid_co
             v0 = clampf(exploit ? __fadd_rn(u0, e[2 * (t & 1)]) : e[2 * (t & 1)], a.umax0);
             v1 = clampf(exploit ? __fadd_rn(u1, e[2 * (t & 1) + 1]) : e[2 * (t & 1) + 1], a.umax1);
             dyn_step<MODEL>(a, z, v0, v1, cs, sn);
-            sincosf(z[2], &sn, &cs);
+            sincos_cw(z[2], sn, cs);
         }
         const unsigned n = (unsigned)k * (unsigned)(T + 1) + (unsigned)t;
         while (bp + 1 < nbp && bp_n[bp + 1] <= n) ++bp;
@@ -404,32 +445,64 @@ __global__ void __launch_bounds__(MPPI_BLOCK) mppi_strict_kernel(const __grid_co
 // ------------------------------------------------------------------------------------------
 // dispatch
 // ------------------------------------------------------------------------------------------
-template <int MODEL, int COLL, bool SUM, bool INJ>
-static cudaError_t launch_tick_win(const TickArgs &a, dim3 grid, cudaStream_t st, int win_static) {
-    if (win_static == 20) mppi_tick_kernel<MODEL, COLL, SUM, INJ, 20><<<grid, MPPI_BLOCK, 0, st>>>(a);
-    else mppi_tick_kernel<MODEL, COLL, SUM, INJ, 0><<<grid, MPPI_BLOCK, 0, st>>>(a);
-    return cudaGetLastError();
+// Calls f(kernel pointer) for the instantiation selected by the runtime mode flags.
+template <int MODEL, int COLL, typename F>
+static cudaError_t with_tick_kernel_mc(bool sum, bool inj, bool win20, bool stash, F &&f) {
+#define MPPI_PICK(S, I, W, ST) return f(mppi_tick_kernel<MODEL, COLL, S, I, W, ST>)
+    if (sum) {
+        if (inj) { if (win20) MPPI_PICK(true, true, 20, false); else MPPI_PICK(true, true, 0, false); }
+        if (stash) { if (win20) MPPI_PICK(true, false, 20, true); else MPPI_PICK(true, false, 0, true); }
+        if (win20) MPPI_PICK(true, false, 20, false); else MPPI_PICK(true, false, 0, false);
+    } else {
+        if (inj) { if (win20) MPPI_PICK(false, true, 20, false); else MPPI_PICK(false, true, 0, false); }
+        if (stash) { if (win20) MPPI_PICK(false, false, 20, true); else MPPI_PICK(false, false, 0, true); }
+        if (win20) MPPI_PICK(false, false, 20, false); else MPPI_PICK(false, false, 0, false);
+    }
+#undef MPPI_PICK
 }
 
-template <int MODEL, int COLL>
-static cudaError_t launch_tick_mc(const TickArgs &a, dim3 grid, cudaStream_t st, bool sum, bool inj, int win_static) {
-    if (sum) return inj ? launch_tick_win<MODEL, COLL, true, true>(a, grid, st, win_static)
-                        : launch_tick_win<MODEL, COLL, true, false>(a, grid, st, win_static);
-    return inj ? launch_tick_win<MODEL, COLL, false, true>(a, grid, st, win_static)
-               : launch_tick_win<MODEL, COLL, false, false>(a, grid, st, win_static);
-}
-
-cudaError_t mppi_launch_tick(const TickArgs &a, int model, int coll, bool sum, bool inj, dim3 grid, cudaStream_t st) {
-    const int ws = (a.window == 20) ? 20 : 0;
+template <typename F>
+static cudaError_t with_tick_kernel(int model, int coll, bool sum, bool inj, bool win20, bool stash, F &&f) {
     if (model == MPPI_MODEL_DIFFDRIVE) {
-        if (coll == MPPI_COLLISION_NONE) return launch_tick_mc<MPPI_MODEL_DIFFDRIVE, MPPI_COLLISION_NONE>(a, grid, st, sum, inj, ws);
-        if (coll == MPPI_COLLISION_CIRCLE) return launch_tick_mc<MPPI_MODEL_DIFFDRIVE, MPPI_COLLISION_CIRCLE>(a, grid, st, sum, inj, ws);
+        if (coll == MPPI_COLLISION_NONE) return with_tick_kernel_mc<MPPI_MODEL_DIFFDRIVE, MPPI_COLLISION_NONE>(sum, inj, win20, stash, f);
+        if (coll == MPPI_COLLISION_CIRCLE) return with_tick_kernel_mc<MPPI_MODEL_DIFFDRIVE, MPPI_COLLISION_CIRCLE>(sum, inj, win20, stash, f);
     } else if (model == MPPI_MODEL_BICYCLE) {
-        if (coll == MPPI_COLLISION_NONE) return launch_tick_mc<MPPI_MODEL_BICYCLE, MPPI_COLLISION_NONE>(a, grid, st, sum, inj, ws);
-        if (coll == MPPI_COLLISION_CIRCLE) return launch_tick_mc<MPPI_MODEL_BICYCLE, MPPI_COLLISION_CIRCLE>(a, grid, st, sum, inj, ws);
-        if (coll == MPPI_COLLISION_FOOTPRINT) return launch_tick_mc<MPPI_MODEL_BICYCLE, MPPI_COLLISION_FOOTPRINT>(a, grid, st, sum, inj, ws);
+        if (coll == MPPI_COLLISION_NONE) return with_tick_kernel_mc<MPPI_MODEL_BICYCLE, MPPI_COLLISION_NONE>(sum, inj, win20, stash, f);
+        if (coll == MPPI_COLLISION_CIRCLE) return with_tick_kernel_mc<MPPI_MODEL_BICYCLE, MPPI_COLLISION_CIRCLE>(sum, inj, win20, stash, f);
+        if (coll == MPPI_COLLISION_FOOTPRINT) return with_tick_kernel_mc<MPPI_MODEL_BICYCLE, MPPI_COLLISION_FOOTPRINT>(sum, inj, win20, stash, f);
     }
     return cudaErrorInvalidValue;
+}
+
+size_t mppi_tick_dyn_smem(int T, bool stash) {
+    return stash ? sizeof(float2) * (size_t)T * MPPI_BLOCK : sizeof(float) * MPPI_WARPS * 2 * MPPI_MAX_T;
+}
+
+cudaError_t mppi_launch_tick(const TickArgs &a, int model, int coll, bool sum, bool inj, bool stash, dim3 grid, cudaStream_t st) {
+    const size_t dyn = mppi_tick_dyn_smem(a.T, stash);
+    return with_tick_kernel(model, coll, sum, inj, a.window == 20, stash, [&](auto kern) {
+        if (dyn > 48 * 1024) {
+            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+            if (e != cudaSuccess) return e;
+        }
+        kern<<<grid, MPPI_BLOCK, dyn, st>>>(a);
+        return cudaGetLastError();
+    });
+}
+
+// Resident CTAs per SM of the instantiation the given modes select (0 if it cannot launch).
+int mppi_tick_occupancy(int model, int coll, bool sum, bool inj, int window, int T, bool stash) {
+    int nb = 0;
+    const size_t dyn = mppi_tick_dyn_smem(T, stash);
+    cudaError_t e = with_tick_kernel(model, coll, sum, inj, window == 20, stash, [&](auto kern) {
+        if (dyn > 48 * 1024) {
+            cudaError_t e2 = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+            if (e2 != cudaSuccess) return e2;
+        }
+        return cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, MPPI_BLOCK, dyn);
+    });
+    if (e != cudaSuccess) { cudaGetLastError(); return 0; }
+    return nb;
 }
 
 template <int MODEL, int COLL>
@@ -468,17 +541,4 @@ cudaError_t mppi_launch_merge(const TickArgs &a, const float *triples, int G, cu
 cudaError_t mppi_launch_noise(const TickArgs &a, float *d_out, int robot, cudaStream_t st) {
     mppi_noise_kernel<<<(a.K + 255) / 256, 256, 0, st>>>(a, d_out, robot);
     return cudaGetLastError();
-}
-
-int mppi_tick_occupancy(int model, int coll, bool sum) {
-    int nb = 0;
-    // representative instantiation; all variants share the same launch bounds and smem footprint
-    if (model == MPPI_MODEL_BICYCLE)
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, mppi_tick_kernel<MPPI_MODEL_BICYCLE, MPPI_COLLISION_FOOTPRINT, true, false, 0>, MPPI_BLOCK, 0);
-    else if (sum)
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, mppi_tick_kernel<MPPI_MODEL_DIFFDRIVE, MPPI_COLLISION_NONE, true, false, 20>, MPPI_BLOCK, 0);
-    else
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, mppi_tick_kernel<MPPI_MODEL_DIFFDRIVE, MPPI_COLLISION_NONE, false, false, 20>, MPPI_BLOCK, 0);
-    (void)coll;
-    return nb > 0 ? nb : 1;
 }

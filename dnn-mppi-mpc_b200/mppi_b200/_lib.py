@@ -4,7 +4,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmppi_b200.so")
+LIB_PATH = os.environ.get("MPPI_B200_LIB", os.path.join(_HERE, "libmppi_b200.so"))   # override: kernel A/B builds
 
 MPPI_ABI_VERSION = 1
 MODEL = {"diffdrive": 0, "bicycle": 1, "diffdrive_mlp": 2}

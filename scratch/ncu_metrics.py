@@ -1,0 +1,10 @@
+import csv, sys, subprocess
+rep=sys.argv[1]
+out=subprocess.run(["ncu","-i",rep,"--page","raw","--csv"],capture_output=True,text=True).stdout
+rows=list(csv.reader(out.splitlines()))
+hdr=rows[0]; units=rows[1]; data=rows[2:]
+keys=['Kernel Name','gpu__time_duration.sum','launch__registers_per_thread','launch__grid_size','sm__warps_active.avg.pct_of_peak_sustained_active','smsp__inst_executed.sum','smsp__issue_active.avg.pct_of_peak_sustained_active','sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active','sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active','sm__pipe_fmaheavy_cycles_active.avg.pct_of_peak_sustained_active','sm__pipe_fmalite_cycles_active.avg.pct_of_peak_sustained_active','sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active','sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active','sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active','dram__bytes_read.sum','dram__bytes_write.sum','smsp__cycles_active.avg','sm__cycles_elapsed.avg','sm__throughput.avg.pct_of_peak_sustained_elapsed']
+keys += [h for h in hdr if h.startswith('smsp__average_warps_issue_stalled') and h.endswith('_per_issue_active.ratio')] + [h for h in hdr if h.startswith('smsp__average_warp_latency_issue_stalled')]
+for k in keys:
+    if k in hdr:
+        i=hdr.index(k); print(k, units[i], [r[i][:60] for r in data])

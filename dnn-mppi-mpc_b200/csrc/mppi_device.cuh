@@ -7,7 +7,9 @@
 #include <math_constants.h>
 #include "../../include/mppi_b200.h"
 
+#ifndef MPPI_BLOCK
 #define MPPI_BLOCK 256
+#endif
 #define MPPI_WARPS (MPPI_BLOCK / 32)
 #ifndef MPPI_MIN_BLOCKS
 #define MPPI_MIN_BLOCKS 3              // resident CTAs per SM the tick kernel is register-budgeted for
@@ -322,6 +324,11 @@ __device__ __forceinline__ float clampf(float v, float lim) { return fminf(fmaxf
 
 // One sample's rollout (frozen window).  Returns the smooth cost and the number of collided
 // evaluations separately so 1e10 * n never swallows the tracking cost.
+//
+// The loop is software-pipelined by hand: the noise of the NEXT timestep pair (Philox + Box-Muller:
+// integer/ALU + MUFU work) is generated in the same straight-line block as the two dynamics/cost
+// steps of the CURRENT pair (FMA-pipe work), so the scheduler can interleave independent chains and
+// the ALU, MUFU and FMA pipes are busy at the same time instead of in alternating phases.
 template <int MODEL, int COLL, bool SUM, bool INJ, int WIN>
 __device__ __forceinline__ void rollout_sample(const TickArgs &a, const TickSmem &sm, uint32_t kg, int klocal,
                                                uint32_t robot, bool exploit, float2 *stash, float &smooth, int &ncoll) {
@@ -332,50 +339,58 @@ __device__ __forceinline__ void rollout_sample(const TickArgs &a, const TickSmem
     float acc = 0.f;
     int nc = 0;
     float v0 = 0.f, v1 = 0.f;
+    float4 ref = make_float4(0.f, 0.f, 0.f, 0.f);
+    float yaw_eff = 0.f;
+    bool hit = false;
     const float2 *eps_k = INJ ? reinterpret_cast<const float2 *>(a.eps) + (size_t)klocal * T : nullptr;
-    for (int tp = 0; tp < T; tp += 2) {
-        float e[4];
+
+    auto fetch = [&](int tp, float e[4]) {
         if (INJ) {
-            const float2 ea = eps_k[tp];
-            e[0] = ea.x; e[1] = ea.y;
+            e[0] = e[1] = e[2] = e[3] = 0.f;
+            if (tp < T) { const float2 ea = eps_k[tp]; e[0] = ea.x; e[1] = ea.y; }
             if (tp + 1 < T) { const float2 eb = eps_k[tp + 1]; e[2] = eb.x; e[3] = eb.y; }
         } else {
             philox_eps_pair(a, kg, (uint32_t)(tp >> 1), robot, e);
         }
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            const int t = tp + h;
-            if (t < T) {
-                if (stash) stash[t * MPPI_BLOCK] = make_float2(e[2 * h], e[2 * h + 1]);
-                const float2 u = sm.U[t];
-                v0 = clampf(exploit ? __fadd_rn(u.x, e[2 * h]) : e[2 * h], a.umax0);       // A4, A5
-                v1 = clampf(exploit ? __fadd_rn(u.y, e[2 * h + 1]) : e[2 * h + 1], a.umax1);
-                dyn_step<MODEL>(a, z, v0, v1, cs, sn);
-                sincos_cw(z[2], sn, cs);
-                if (SUM) {
-                    const int j = nearest_wp<WIN>(sm, z[0], z[1]);
-                    const float4 ref = window_ref(sm, j);
-                    const float yaw_eff = a.yaw_wrap ? wrap_2pi(z[2]) : z[2];
-                    float c = tracking_cost<MODEL>(ref, z, yaw_eff, a.sw);
-                    if (a.use_gamma) { const float2 q = sm.Q[t]; c += q.x * v0 + q.y * v1; }
-                    const bool hit = collided<MODEL, COLL>(a, z[0], z[1], cs, sn);
-                    if (t == T - 1) {           // terminal cost: same state, same waypoint (A9)
-                        c += tracking_cost<MODEL>(ref, z, yaw_eff, a.tw);
-                        nc += hit ? 2 : 0;
-                    } else {
-                        nc += hit ? 1 : 0;
-                    }
-                    acc += c;
-                }
-            }
+    };
+    auto step = [&](int t, float e0, float e1) {
+        if (stash) stash[t * MPPI_BLOCK] = make_float2(e0, e1);
+        const float2 u = sm.U[t];
+        v0 = clampf(exploit ? __fadd_rn(u.x, e0) : e0, a.umax0);                   // A4, A5
+        v1 = clampf(exploit ? __fadd_rn(u.y, e1) : e1, a.umax1);
+        dyn_step<MODEL>(a, z, v0, v1, cs, sn);
+        sincos_cw(z[2], sn, cs);
+        if (SUM) {
+            const int j = nearest_wp<WIN>(sm, z[0], z[1]);
+            ref = window_ref(sm, j);
+            yaw_eff = (MODEL == MPPI_MODEL_BICYCLE && a.yaw_wrap) ? wrap_2pi(z[2]) : z[2];
+            const float2 q = sm.Q[t];                                                // zero when gamma == 0
+            acc += tracking_cost<MODEL>(ref, z, yaw_eff, a.sw) + (q.x * v0 + q.y * v1);
+            hit = collided<MODEL, COLL>(a, z[0], z[1], cs, sn);
+            nc += hit ? 1 : 0;
         }
+    };
+
+    float e[4];
+    fetch(0, e);
+    const int Tpairs = T & ~1;
+    for (int tp = 0; tp < Tpairs; tp += 2) {
+        float en[4];
+        fetch(tp + 2, en);              // independent of the two steps below (one surplus call at the end)
+        step(tp, e[0], e[1]);
+        step(tp + 1, e[2], e[3]);
+        e[0] = en[0]; e[1] = en[1]; e[2] = en[2]; e[3] = en[3];
     }
-    if (!SUM) {                                 // Q1: only the last stage cost survives, plus terminal
+    if (T & 1) step(T - 1, e[0], e[1]);
+    if (SUM) {                          // terminal cost: same state, same waypoint as the last stage cost (A9)
+        acc += tracking_cost<MODEL>(ref, z, yaw_eff, a.tw);
+        nc += hit ? 1 : 0;
+    } else {                            // Q1: only the last stage cost survives, plus terminal
         const int j = nearest_wp<WIN>(sm, z[0], z[1]);
-        const float4 ref = window_ref(sm, j);
-        const float yaw_eff = a.yaw_wrap ? wrap_2pi(z[2]) : z[2];
-        acc = tracking_cost<MODEL>(ref, z, yaw_eff, a.sw);
-        if (a.use_gamma) { const float2 q = sm.Q[T - 1]; acc += q.x * v0 + q.y * v1; }
+        ref = window_ref(sm, j);
+        yaw_eff = (MODEL == MPPI_MODEL_BICYCLE && a.yaw_wrap) ? wrap_2pi(z[2]) : z[2];
+        const float2 q = sm.Q[T - 1];
+        acc = tracking_cost<MODEL>(ref, z, yaw_eff, a.sw) + (q.x * v0 + q.y * v1);
         acc += tracking_cost<MODEL>(ref, z, yaw_eff, a.tw);
         nc = collided<MODEL, COLL>(a, z[0], z[1], cs, sn) ? 2 : 0;
     }

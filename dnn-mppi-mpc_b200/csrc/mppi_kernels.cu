@@ -134,7 +134,7 @@ struct RunSmem {
 extern __shared__ __align__(16) unsigned char mppi_dyn_smem[];
 
 template <int MODEL, int COLL, bool SUM, bool INJ, int WIN, bool STASH>
-__global__ void __launch_bounds__(MPPI_BLOCK, MPPI_MIN_BLOCKS) mppi_tick_kernel(const __grid_constant__ TickArgs a) {
+__global__ void __launch_bounds__(MPPI_BLOCK, STASH ? 2 : MPPI_MIN_BLOCKS) mppi_tick_kernel(const __grid_constant__ TickArgs a) {
     __shared__ TickSmem sm;
     __shared__ RunSmem run;
     __shared__ MergeSmem ms;
@@ -153,10 +153,11 @@ __global__ void __launch_bounds__(MPPI_BLOCK, MPPI_MIN_BLOCKS) mppi_tick_kernel(
     } else {
         const int s_old = a.idx[robot];
         unsigned long long key = ~0ull;
-        if (tid < a.window && s_old + tid < a.n_path) {
-            const float4 p = a.path[s_old + tid];
+        for (int j = tid; j < a.window && s_old + j < a.n_path; j += MPPI_BLOCK) {
+            const float4 p = a.path[s_old + j];
             const float dx = sm.x0[0] - p.x, dy = sm.x0[1] - p.y;
-            key = ((unsigned long long)__float_as_uint(dx * dx + dy * dy) << 32) | (unsigned)tid;
+            const unsigned long long kj = ((unsigned long long)__float_as_uint(dx * dx + dy * dy) << 32) | (unsigned)j;
+            key = kj < key ? kj : key;
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {

@@ -602,10 +602,14 @@ int mppi_reduce_update(mppi_handle_t h, const float *d_S, const float *d_eps, ui
 }
 
 int mppi_generate_noise(mppi_handle_t h, uint64_t seed, uint64_t tick, float *d_eps_out) {
-    if (!h || !d_eps_out) return MPPI_E_BADARG;
+    return mppi_generate_noise_robot(h, seed, tick, 0, d_eps_out);
+}
+
+int mppi_generate_noise_robot(mppi_handle_t h, uint64_t seed, uint64_t tick, int32_t robot, float *d_eps_out) {
+    if (!h || !d_eps_out || robot < 0 || robot >= h->cfg.n_robots) return MPPI_E_BADARG;
     CK(h, cudaSetDevice(h->cfg.device));
     set_seed(h, seed, tick);
-    CK(h, mppi_launch_noise(h->args, d_eps_out, 0, h->stream));
+    CK(h, mppi_launch_noise(h->args, d_eps_out, robot, h->stream));
     h->tm.launches++;
     CK(h, cudaStreamSynchronize(h->stream));
     return MPPI_OK;

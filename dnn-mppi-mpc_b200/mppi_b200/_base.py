@@ -14,7 +14,9 @@ def _to_device_noise(noise, K, T, device):
         noise = torch.from_numpy(np.ascontiguousarray(noise, dtype=np.float32))
     if tuple(noise.shape) != (K, T, 2):
         raise ValueError("injected noise must have shape (K,T,2) = (%d,%d,2), got %s" % (K, T, tuple(noise.shape)))
-    return noise.to(device="cuda:%d" % device, dtype=torch.float32).contiguous()
+    out = noise.to(device="cuda:%d" % device, dtype=torch.float32).contiguous()
+    torch.cuda.current_stream(device).synchronize()     # the engine runs on its own stream
+    return out
 
 
 class ControllerBase:

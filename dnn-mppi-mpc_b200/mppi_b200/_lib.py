@@ -63,6 +63,7 @@ SYMBOLS = {
     "mppi_rollout_costs": (C.c_int, [_H, _PD, C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p]),
     "mppi_reduce_update": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, _PF, _PF, _PF]),
     "mppi_generate_noise": (C.c_int, [_H, C.c_uint64, C.c_uint64, C.c_void_p]),
+    "mppi_generate_noise_robot": (C.c_int, [_H, C.c_uint64, C.c_uint64, C.c_int32, C.c_void_p]),
     "mppi_get_stats": (C.c_int, [_H, C.POINTER(MppiStats)]),
     "mppi_step_batched": (C.c_int, [_H, C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p]),
     "mppi_comm_get_unique_id": (C.c_int, [C.c_void_p]),

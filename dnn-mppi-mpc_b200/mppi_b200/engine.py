@@ -144,8 +144,8 @@ class MPPIEngine:
                                              w_eps.ctypes.data_as(_lib._PF)), "mppi_reduce_update")
         return self._u0_np.copy(), self._useq_np.copy(), w_eps
 
-    def generate_noise(self, d_out, seed=0, tick=0):
-        self._ck(self.lib.mppi_generate_noise(self._h, seed, tick, _dptr(d_out)), "mppi_generate_noise")
+    def generate_noise(self, d_out, seed=0, tick=0, robot=0):
+        self._ck(self.lib.mppi_generate_noise_robot(self._h, seed, tick, robot, _dptr(d_out)), "mppi_generate_noise")
 
     def step_batched(self, d_x0, d_u0_out=None, seed=0, tick=0):
         self._ck(self.lib.mppi_step_batched(self._h, _dptr(d_x0), seed, tick, _dptr(d_u0_out)), "mppi_step_batched")

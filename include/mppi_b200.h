@@ -154,6 +154,8 @@ int mppi_reduce_update(mppi_handle_t h, const float *d_S, const float *d_eps, ui
 /* The exact noise tensor (K,T,2) the Philox path consumes for (seed, tick) -- replaces
  * `_calc_epsilon` (mppi_differential_drive.py:273-283) and lets the oracle be fed the same noise. */
 int mppi_generate_noise(mppi_handle_t h, uint64_t seed, uint64_t tick, float *d_eps_out);
+/* Same for robot `robot` of a batched handle (its Philox stream is keyed by the robot index). */
+int mppi_generate_noise_robot(mppi_handle_t h, uint64_t seed, uint64_t tick, int32_t robot, float *d_eps_out);
 int mppi_get_stats(mppi_handle_t h, mppi_stats_t *out);   /* robot 0 */
 
 /* Batched multi-robot tick: n_robots independent controllers in one launch (no reference

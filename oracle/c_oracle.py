@@ -72,10 +72,13 @@ def _p(a, t):
     return a.ctypes.data_as(C.POINTER(t))
 
 
-def costs(spec, path, U, idx, x0, eps=None, seed=0, tick=0, k_offset=0, nthreads=0):
-    """Per-sample costs S (K,) float64, index after step 1, index after the tick."""
+def costs(spec, path, U, idx, x0, eps=None, seed=0, tick=0, k_offset=0, nthreads=0, n_exploit=None):
+    """Per-sample costs S (K,) float64, index after step 1, index after the tick.  For a shard of a
+    larger sample set pass `k_offset` and the GLOBAL explore/exploit threshold `n_exploit` (Q6)."""
     path = np.ascontiguousarray(path, np.float64)
     c = _cfg(spec, path)
+    if n_exploit is not None:
+        c.n_exploit = int(n_exploit)
     U = np.ascontiguousarray(U, np.float64)
     x0 = np.ascontiguousarray(x0, np.float64)
     obs = np.ascontiguousarray(spec.obstacles, np.float64).reshape(-1, 3)

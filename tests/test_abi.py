@@ -1,0 +1,72 @@
+"""CPU checks of the drop-in boundary: the C-ABI library loads without a GPU and exports every
+symbol include/mppi_b200.h declares; handle creation fails loudly (no CPU fallback)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    src = open(os.path.join(ROOT, "include", "mppi_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(mppi_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_symbols_are_exported_and_bound():
+    from mppi_b200 import _lib
+    lib = _lib.load()
+    names = declared_symbols()
+    assert len(names) >= 25
+    for n in names:
+        assert hasattr(lib, n), "libmppi_b200.so does not export %s" % n
+        assert n in _lib.SYMBOLS, "ctypes binding table misses %s" % n
+    assert sorted(_lib.SYMBOLS) == names
+    assert lib.mppi_abi_version() == 1
+
+
+def test_config_struct_layout_matches_header():
+    from mppi_b200 import _lib
+    # 14 int32 + 24 doubles, naturally aligned
+    assert C.sizeof(_lib.MppiConfig) == 14 * 4 + 24 * 8
+    c = _lib.MppiConfig()
+    _lib.load().mppi_default_config(C.byref(c))
+    assert (c.abi_version, c.K, c.T, c.window, c.n_robots) == (1, 1000, 30, 20, 1)
+    assert abs(c.dt - 0.1) < 1e-15 and abs(c.sigma[3] - 0.01) < 1e-15 and c.vehicle_l == 4.0
+
+
+def test_errors_are_status_codes_not_exceptions_across_the_abi():
+    from mppi_b200 import _lib
+    lib = _lib.load()
+    assert lib.mppi_create(None, None) == -1
+    assert lib.mppi_destroy(None) == -1
+    assert b"invalid" in lib.mppi_strerror(-1)
+    c = _lib.MppiConfig()
+    lib.mppi_default_config(C.byref(c))
+    c.T = 4                                     # the reference filter raises for T < 10 (:263)
+    h = C.c_void_p()
+    assert lib.mppi_create(C.byref(c), C.byref(h)) == -1 and not h.value
+
+
+def test_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from mppi_b200 import MppiError
+    from mppi_b200.mppi_differential_drive import MPPIAlgorithms
+    with pytest.raises(MppiError):
+        MPPIAlgorithms(0.1, np.zeros((30, 3)), 5.0, 3.14, 100, 10, 1e-4, 1.0, 0.2, np.diag([0.1, 0.01]),
+                       np.ones(3), np.ones(3))
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "dnn-mppi-mpc_b200")
+    for dp, _, fs in os.walk(pkg):
+        for f in fs:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(dp, f)).read()
+                assert "import oracle" not in txt and "from oracle" not in txt and "mppi_oracle" not in txt.replace(
+                    "oracle/mppi_oracle.py:philox_noise", ""), f

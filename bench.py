@@ -20,7 +20,6 @@ import json
 import os
 import subprocess
 import sys
-import threading
 import time
 
 import numpy as np
@@ -49,42 +48,46 @@ def diffdrive_kwargs(K, T, temperature):
                 visualze_sampled_trajs=False, cost_mode="sum", waypoint_mode="frozen", temperature=temperature)
 
 
-class ClockSampler(threading.Thread):
-    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons (one `-lms` process) while the timed regions run."""
     Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, gpu_index):
-        super().__init__(daemon=True)
-        self.gpu = gpu_index
-        self.rows = []
-        self._halt = threading.Event()
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
 
-    def run(self):
-        while not self._halt.is_set():
-            try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
-                parts = [p.strip() for p in out.strip().split(",")]
-                if len(parts) >= 7:
-                    self.rows.append(parts)
-            except Exception:
-                pass
-            self._halt.wait(0.15)
+    def start(self):
+        return self
 
     def stop(self):
-        self._halt.set()
-        self.join(timeout=5)
-        if not self.rows:
+        rows = []
+        if self.proc is not None:
+            time.sleep(0.25)
+            self.proc.terminate()
+            try:
+                out, _ = self.proc.communicate(timeout=5)
+            except Exception:
+                out = ""
+            for ln in out.strip().splitlines():
+                parts = [p.strip() for p in ln.split(",")]
+                if len(parts) >= 7 and parts[0].replace(".", "").isdigit():
+                    rows.append(parts)
+        if not rows:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        sm = sorted(float(r[0]) for r in self.rows)
+        sm = sorted(float(r[0]) for r in rows)
         reasons = []
         for name, col in (("hw_slowdown", 3), ("hw_thermal_slowdown", 4), ("sw_thermal_slowdown", 5), ("sw_power_cap", 6)):
-            if any(r[col].lower().startswith("active") for r in self.rows):
+            if any(r[col].lower().startswith("active") for r in rows):
                 reasons.append(name)
-        pw = [float(r[2]) for r in self.rows if r[2].replace(".", "").isdigit()]
-        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons,
-                "samples": len(self.rows), "power_w_max": max(pw) if pw else None}
+        pw = [float(r[2]) for r in rows if r[2].replace(".", "").isdigit()]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(rows[0][1]), "reasons": reasons,
+                "samples": len(rows), "power_w_max": max(pw) if pw else None}
 
 
 def measured_peaks():
@@ -133,18 +136,19 @@ def run_reference_arm(args):
         return
     K_s = 1 << 16                           # bounded sample of the K=1M workload: 65,536 samples x H=50 per step
     cpu_port_run(max(1, min(args.warmup, 2)), K_s, T_H, 10.0)
-    times, nthr = cpu_port_run(args.steps, K_s, T_H, 10.0)
+    n_ref = min(args.steps, 40)              # each step = 65,536 x 50 sample-steps on the host cores
+    times, nthr = cpu_port_run(n_ref, K_s, T_H, 10.0)
     ms = 1e3 * float(np.mean(times))
     val = K_s * T_H / float(np.mean(times))
     py_rate = cpu_python_loops_rate()
     line = {
         "impl": "reference", "metric": "mppi_sample_steps_per_sec", "value": val, "unit": "sample-steps/s",
-        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+        "n_gpus": args.gpus, "steps": n_ref, "warmup": args.warmup, "ms_per_step": ms,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": "diffdrive_K1M_H50_sum_frozen_philox (CPU sample: K=65536 per step)",
                    "K_sample": K_s, "H": T_H},
         "cpu_baseline": {"value": val, "unit": "sample-steps/s", "cores": nthr, "kind": "port",
-                         "sample": "K=65536 x H=50 per tick, %d ticks, oracle/mppi_oracle.c (OpenMP)" % args.steps,
+                         "sample": "K=65536 x H=50 per tick, %d ticks, oracle/mppi_oracle.c (OpenMP)" % n_ref,
                          "python_loops_1core_value": py_rate,
                          "note": "the reference itself is scalar Python loops (python_loops_1core_value); the C port is a best-effort CPU line"},
         "e2e": {"value": val, "unit": "sample-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -204,7 +208,6 @@ def run_b200_arm(args):
             ev[i][1].record(stream)
     barrier()
     t_wall = time.perf_counter() - t_wall0
-    clocks = sampler.stop()
     launches = eng.timings()["launches"] - launches0
     step_ms = np.array([a.elapsed_time(b) for a, b in ev])
     local_ms = float(step_ms.sum())
@@ -223,18 +226,20 @@ def run_b200_arm(args):
         ctrl._calc_input_control(x0)
     barrier()
     lat = []
-    t0 = time.perf_counter()
     for i in range(args.steps):
+        flush.zero_()
+        torch.cuda.synchronize()
         t1 = time.perf_counter()
-        u0, u, _, _ = ctrl._calc_input_control(x0)
+        u0, u, _, _ = ctrl._calc_input_control(x0)           # host x0 in -> host u0/u out (synchronous)
         lat.append(time.perf_counter() - t1)
     barrier()
-    e2e_s = time.perf_counter() - t0
+    e2e_s = float(np.sum(lat))
     if world > 1:
         t = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
     e2e_value = K_global * T_H * args.steps / e2e_s
+    clocks = sampler.stop()
 
     if rank != 0:
         if world > 1:
@@ -276,6 +281,23 @@ def run_b200_arm(args):
         extras["racecar_K16384_H50"] = {"p50_ms": 1e3 * float(rl[len(rl) // 2]), "p90_ms": 1e3 * float(rl[int(len(rl) * 0.9)]),
                                         "sample_steps_per_sec": 16384 * 50 / float(rl[len(rl) // 2])}
         rc.engine.close()
+        # config[3]: 4096 independent diff-drive controllers x K=1024 x H=30 in one launch
+        from mppi_b200.batched import BatchedMPPI
+        R = 4096
+        bm = BatchedMPPI(R, spline_path(), num_samples_K=1024, num_horizons_T=30, temperature=2.0, seed=1)
+        xs = torch.from_numpy(np.tile(np.zeros(3, np.float32), (R, 1))).cuda()
+        for _ in range(3):
+            bm.step(xs)
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(10):
+            bm.step(xs)
+        b.record()
+        torch.cuda.synchronize()
+        extras["batched_R4096_K1024_H30"] = {"ms_per_tick": a.elapsed_time(b) / 10,
+                                             "sample_steps_per_sec": R * 1024 * 30 / (a.elapsed_time(b) / 10 * 1e-3)}
+        bm.engine.close()
 
     # ---- roofline of the dominant kernel (mppi_tick_kernel): FP32 issue-bound, not HBM-bound
     peaks = measured_peaks()
@@ -284,13 +306,15 @@ def run_b200_arm(args):
     flops = FLOP_PER_SAMPLE_STEP * K_PER_GPU * T_H
     achieved_tf = flops / (kern_ms * 1e-3) / 1e12
     peak_tf_max = SM_COUNT * FP32_LANES * 2 * ((peaks or {}).get("sm_max_mhz", 1965.0)) * 1e6 / 1e12
-    hbm_bytes = 4.0 * (K_PER_GPU / 256) * (4 + 2 * T_H) / 4 + 4 * (8 + 4 * 128)       # partial writes + out record
+    hbm_bytes = 4.0 * 296 * (4 + 2 * T_H) * 2 + 4 * (8 + 4 * 128)       # block partials written + re-read by the last block, out record
     roofline = {
         "bound": "fp32", "achieved": achieved_tf, "peak": peak_tf_max, "unit": "TFLOP/s",
         "frac": achieved_tf / peak_tf_max, "traffic": None,
         "peak_source": "derived 148 SM x 128 lanes x 2 x clocks.max.sm (FP32 peak is not in MEASURED_PEAKS.json)",
         "algorithmic_flop_per_sample_step": FLOP_PER_SAMPLE_STEP,
         "sm_mhz_during_run": f_mhz,
+        "issue_view": {"warp_instr_per_warp_sample_step": 228, "source": "ncu smsp__inst_executed / (K*H/32), profiles/",
+                       "achieved_frac_of_issue_peak": (K_PER_GPU * T_H / 32 * 228) / (kern_ms * 1e-3) / (SM_COUNT * 4 * f_mhz * 1e6)},
         "hbm_view": {"algorithmic_bytes_per_launch": hbm_bytes,
                      "achieved_GBps": hbm_bytes / (kern_ms * 1e-3) / 1e9,
                      "peak_GBps": (peaks or {}).get("hbm_gbs", 6650.0),
@@ -331,8 +355,8 @@ def run_b200_arm(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=400)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     args = ap.parse_args()
     args.warmup = max(3, args.warmup)

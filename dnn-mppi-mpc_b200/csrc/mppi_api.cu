@@ -503,14 +503,13 @@ static int step_common(mppi_handle_t h, const double *x0, const float *d_eps, ui
     set_seed(h, seed, tick);
     if (h->timing) CK(h, cudaEventRecord(h->ev[0], h->stream));
     if (h->mlp) {
-        int rc = mlp_rollout_costs(h->mlp, h->args, d_eps, h->d_S, h->stream);
-        if (rc != 0) return fail(h, MPPI_E_CUDA, "MLP rollout failed");
+        int rc = mlp_rollout_costs(h->mlp, h->args, h->sum, d_eps, h->d_S, h->stream);
+        if (rc != 0) return fail(h, rc == -2 ? MPPI_E_STATE : MPPI_E_CUDA, rc == -2 ? "mppi_set_mlp has not been called" : "MLP rollout launch failed");
         h->tm.launches += mlp_launches_per_tick(h->mlp);
         if (h->timing) CK(h, cudaEventRecord(h->ev[1], h->stream));
         TickArgs a = h->args;
         a.S = h->d_S; a.eps = d_eps;
-        a.flags = F_UPDATE | F_FROM_S | F_KEEP_IDX | F_HOST_IDX;      // the MLP rollout persisted the index
-        a.idx_host = 0;
+        a.flags = F_UPDATE | F_FROM_S;      // K2 repeats step 1 (same result as in the MLP kernel) and persists the index
         int rc2 = launch_update(h, a, d_eps != nullptr);
         if (rc2 != MPPI_OK) return rc2;
     } else if (h->strict) {
@@ -563,8 +562,13 @@ int mppi_rollout_costs(mppi_handle_t h, const double *x0, const float *d_eps, ui
     set_x0(h, x0);
     set_seed(h, seed, tick);
     if (h->mlp) {
-        if (mlp_rollout_costs(h->mlp, h->args, d_eps, d_S, h->stream) != 0) return fail(h, MPPI_E_CUDA, "MLP rollout failed");
+        if (mlp_rollout_costs(h->mlp, h->args, h->sum, d_eps, d_S, h->stream) != 0) return fail(h, MPPI_E_CUDA, "MLP rollout failed");
         h->tm.launches += mlp_launches_per_tick(h->mlp);
+        TickArgs a = h->args;
+        a.flags = F_IDX_ONLY;
+        dim3 grid(1, 1);
+        CK(h, mppi_launch_tick(a, MPPI_MODEL_DIFFDRIVE, MPPI_COLLISION_NONE, h->sum, false, false, grid, h->stream));
+        h->tm.launches++;
     } else if (h->strict) {
         int idx_after = 0;
         int rc = strict_costs(h, x0, d_eps, d_S, &idx_after);

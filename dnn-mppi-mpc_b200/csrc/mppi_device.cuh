@@ -26,7 +26,9 @@ enum : int {
     F_FROM_S = 4,        // skip the rollout, read costs from S_in (K2 alone)
     F_HOST_IDX = 8,      // skip step 1, window starts at idx_host
     F_TRIPLE_OUT = 16,   // multi-GPU: publish the merged per-GPU triple, do not finalize
-    F_KEEP_IDX = 32      // do not persist the waypoint index (K2 alone)
+    F_KEEP_IDX = 32,     // do not persist the waypoint index (K2 alone)
+    F_IDX_ONLY = 64,     // only run step 1 and persist the index (MLP path, K1 alone)
+    F_COST_SUM = 0x10000 // MLP kernel: cost_mode == sum (the tick kernel takes it as a template argument)
 };
 
 // Everything a tick needs, passed by value (kernel parameter = constant bank).

@@ -196,7 +196,8 @@ __global__ void __launch_bounds__(MPPI_BLOCK, STASH ? 2 : MPPI_MIN_BLOCKS) mppi_
     __syncthreads();
 
     // ---- this block's contiguous sample range (balanced over the grid)
-    const int k_begin = (int)((long long)K * b / B), k_end = (int)((long long)K * (b + 1) / B);
+    const int k_begin = (int)((long long)K * b / B);
+    const int k_end = (a.flags & F_IDX_ONLY) ? k_begin : (int)((long long)K * (b + 1) / B);
     float *Srow = a.S ? a.S + (size_t)robot * K : nullptr;
     for (int base = k_begin; base < k_end; base += MPPI_BLOCK) {
         const int k = base + tid;

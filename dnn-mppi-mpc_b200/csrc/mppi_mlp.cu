@@ -1,8 +1,442 @@
-// K3 placeholder: filled in by the tcgen05 implementation.
+// K3: learned-dynamics rollout for BASELINE config 3 -- unicycle + dnn/simple_mlp.py residual,
+//     x+ = x + dt * ([v cos(th), v sin(th), w] + MLP(x))            
+// with MLP = Linear(3,512) -> tanh(Linear(512,512)) -> tanh(Linear(512,512)) -> Linear(512,3)
+// (dnn/simple_mlp.py:10-23).
+//
+// sm_100a mapping (one persistent CTA per SM, each owning 128-sample tiles for the whole horizon):
+//   * the input layer has NO activation (simple_mlp.py:19), so Linear(3,512) and the first hidden
+//     Linear(512,512) are folded on the host into one 3->512 map (W01 = W1 W0, b01 = W1 b0 + b1) that
+//     the compute warps evaluate in FP32 on the CUDA cores, apply tanh (MUFU tanh.approx.bf16x2) and
+//     write as the bf16 A operand straight into shared memory in the UMMA SWIZZLE_128B K-major layout;
+//   * the remaining 512x512 layer is the GEMM: D[128x512] (FP32, all 512 TMEM columns) =
+//     A[128x512] (smem) x W2^T, issued by ONE thread as tcgen05.mma.cta_group::1.kind::f16 (M=128,
+//     N=256, K=16), W2 streamed from L2 by TMA (cp.async.bulk.tensor, 256x64 bf16 boxes, 128B swizzle)
+//     through an mbarrier ring;
+//   * the epilogue warps read the accumulator with tcgen05.ld (32x32b.x32), add b2, apply tanh and
+//     contract with the 512x3 output layer in FP32 registers -- the output layer never touches memory;
+//   * the unicycle step, nearest-waypoint search and cost run in the same epilogue threads with the
+//     state in registers across the horizon.
+// Warp roles: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2..9 = 8 compute
+// warps (two per TMEM lane quarter, each owning half of the 512 columns).
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <vector>
+
+#include "mppi_device.cuh"
 #include "mppi_mlp.h"
-struct MlpState { int K, T; };
-MlpState *mlp_create(int, int) { return nullptr; }
-void mlp_destroy(MlpState *m) { delete m; }
-cudaError_t mlp_set_weights(MlpState *, const float *const[4], const float *const[4], cudaStream_t) { return cudaErrorNotSupported; }
-int mlp_rollout_costs(MlpState *, const TickArgs &, const float *, float *, cudaStream_t) { return -1; }
-int mlp_launches_per_tick(const MlpState *) { return 0; }
+
+namespace {
+
+constexpr int HID = 512;
+constexpr int TILE_M = 128;
+constexpr int KCH = 64;                   // K elements per 128-byte swizzle span (bf16)
+constexpr int N_HALF = 256;               // N per tcgen05.mma
+constexpr int B_STAGES = 2;
+constexpr int B_TILE_BYTES = N_HALF * KCH * 2;     // 32 KB
+constexpr int A_CHUNK_BYTES = TILE_M * KCH * 2;    // 16 KB per K chunk
+constexpr int A_BYTES = A_CHUNK_BYTES * (HID / KCH);   // 128 KB
+constexpr int MLP_THREADS = 320;
+constexpr int N_COMPUTE = 256;
+
+struct MlpSmem {                          // after the 1024-aligned A / B regions
+    float4 w01[HID];                      // (W01[j][0], W01[j][1], W01[j][2], b01[j])
+    float4 w3[HID];                       // (b2[j], W3[0][j], W3[1][j], W3[2][j])
+    float4 xs[TILE_M];                    // current state of each row for the partner thread
+    float4 res[TILE_M];                   // partner's partial output-layer sums
+    unsigned long long b_full[B_STAGES], b_empty[B_STAGES], a_ready, d_ready;
+    unsigned long long key[8];
+    uint32_t tmem_base;
+    float b3[3];
+};
+
+constexpr size_t MLP_DYN_SMEM = 1024 /*align slack*/ + A_BYTES + B_STAGES * B_TILE_BYTES + sizeof(TickSmem) + sizeof(MlpSmem);
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra.uni WAIT_DONE;\n\t"
+        "bra.uni WAIT_LOOP;\n\t"
+        "WAIT_DONE:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+
+__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, unsigned long long *bar, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+
+// UMMA shared-memory descriptor: K-major, SWIZZLE_128B, 8-row x 128-byte atoms 1024 bytes apart
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);              // start address
+    d |= (uint64_t)0 << 16;                              // leading byte offset (unused for swizzled K-major)
+    d |= (uint64_t)((1024 >> 4) & 0x3FFF) << 32;         // stride byte offset
+    d |= (uint64_t)1 << 46;                              // descriptor version (sm_100)
+    d |= (uint64_t)2 << 61;                              // SWIZZLE_128B
+    return d;
+}
+
+// kind::f16 instruction descriptor: BF16 x BF16 -> F32, K-major A and B, M=128, N=256
+constexpr uint32_t UMMA_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N_HALF >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
+
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(UMMA_IDESC), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(unsigned long long *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+}
+__device__ __forceinline__ float tanh_approx(float x) {
+    float y;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+// tanh of two FP32 pre-activations -> packed bf16x2 (one cvt + one MUFU for two elements)
+__device__ __forceinline__ uint32_t tanh_bf16x2(float lo, float hi) {
+    uint32_t p, y;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(p) : "f"(hi), "f"(lo));
+    asm("tanh.approx.bf16x2 %0, %1;" : "=r"(y) : "r"(p));
+    return y;
+}
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+__global__ void __launch_bounds__(MLP_THREADS, 1)
+mppi_mlp_rollout_kernel(const __grid_constant__ TickArgs a, const __grid_constant__ CUtensorMap w2_map,
+                        const float4 *__restrict__ g_w01, const float4 *__restrict__ g_w3, const float *__restrict__ g_b3,
+                        float *__restrict__ S_out, int n_tiles) {
+    extern __shared__ unsigned char dyn_raw[];
+    unsigned char *dyn = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(dyn_raw) + 1023) & ~(uintptr_t)1023);
+    unsigned char *smA = dyn;                                     // 8 chunks x [128 rows x 128 B]
+    unsigned char *smB = dyn + A_BYTES;                           // B_STAGES x [256 rows x 128 B]
+    TickSmem &sm = *reinterpret_cast<TickSmem *>(dyn + A_BYTES + B_STAGES * B_TILE_BYTES);
+    MlpSmem &ms = *reinterpret_cast<MlpSmem *>(dyn + A_BYTES + B_STAGES * B_TILE_BYTES + sizeof(TickSmem));
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int T = a.T;
+    const int my_tiles = (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+
+    // ---- one-time setup: constants, barriers, TMEM, step-1 index + window (same rule as the tick kernel)
+    for (int j = tid; j < HID; j += MLP_THREADS) { ms.w01[j] = g_w01[j]; ms.w3[j] = g_w3[j]; }
+    if (tid < 3) ms.b3[tid] = g_b3[tid];
+    if (tid < 4) sm.x0[tid] = a.x0[tid];
+    if (tid == 0) {
+        for (int s = 0; s < B_STAGES; ++s) { mbar_init(&ms.b_full[s], 1); mbar_init(&ms.b_empty[s], 1); }
+        mbar_init(&ms.a_ready, N_COMPUTE);
+        mbar_init(&ms.d_ready, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&ms.tmem_base)), "r"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    __syncthreads();
+    {
+        const int s_old = a.idx[0];
+        unsigned long long key = ~0ull;
+        for (int j = tid; j < a.window && s_old + j < a.n_path; j += MLP_THREADS) {
+            const float4 p = a.path[s_old + j];
+            const float dx = sm.x0[0] - p.x, dy = sm.x0[1] - p.y;
+            const unsigned long long kj = ((unsigned long long)__float_as_uint(dx * dx + dy * dy) << 32) | (unsigned)j;
+            key = kj < key ? kj : key;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const unsigned long long other = __shfl_xor_sync(0xffffffffu, key, o);
+            key = other < key ? other : key;
+        }
+        if (lane == 0 && warp < 8) ms.key[warp] = key;
+        __syncthreads();
+        if (warp >= 8) {                                     // warps 8,9 fold their candidates in serially
+            if (lane == 0) atomicMin(&ms.key[0], key);
+        }
+        __syncthreads();
+        key = ms.key[0];
+#pragma unroll
+        for (int w = 1; w < 8; ++w) key = ms.key[w] < key ? ms.key[w] : key;
+        const int s_new = s_old + (int)(key & 0xffffffffu);
+        int nw = a.n_path - s_new; nw = nw < a.window ? nw : a.window;
+        const int fill = (a.window == 20) ? 20 : ((nw + 15) & ~15);
+        for (int j = tid; j < fill; j += MLP_THREADS) {
+            if (j < nw) {
+                const float4 p = a.path[s_new + j];
+                sm.wx[j] = -p.x; sm.wy[j] = -p.y; sm.wyv[j] = make_float2(p.z, p.w);
+            } else {
+                sm.wx[j] = -MPPI_SENTINEL; sm.wy[j] = -MPPI_SENTINEL; sm.wyv[j] = make_float2(0.f, 0.f);
+            }
+        }
+        if (tid == 0) { sm.win_start = s_new; sm.n_win16 = fill >> 4; }
+        for (int t = tid; t < T; t += MLP_THREADS) {
+            const float u0 = a.U[2 * t], u1 = a.U[2 * t + 1];
+            sm.U[t] = make_float2(u0, u1);
+            sm.Q[t] = make_float2(u0 * a.gq[0] + u1 * a.gq[2], u0 * a.gq[1] + u1 * a.gq[3]);
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = ms.tmem_base;
+
+    if (warp == 0) {
+        // ===== TMA producer: the same 16 W2 boxes every timestep, through a B_STAGES ring =====
+        if (lane == 0) {
+            const int total = my_tiles * T * 2 * (HID / KCH);
+            int stage = 0; uint32_t phase = 0;
+            for (int it = 0; it < total; ++it) {
+                const int kb = it % (HID / KCH), nh = (it / (HID / KCH)) & 1;
+                mbar_wait(&ms.b_empty[stage], phase ^ 1);
+                mbar_expect_tx(&ms.b_full[stage], B_TILE_BYTES);
+                tma_load_2d(smB + stage * B_TILE_BYTES, &w2_map, &ms.b_full[stage], kb * KCH, nh * N_HALF);
+                if (++stage == B_STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer: one thread drives the tensor core =====
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0, a_phase = 0;
+            for (int step = 0; step < my_tiles * T; ++step) {
+                mbar_wait(&ms.a_ready, a_phase); a_phase ^= 1;
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                for (int nh = 0; nh < 2; ++nh) {
+                    for (int kb = 0; kb < HID / KCH; ++kb) {
+                        mbar_wait(&ms.b_full[stage], phase);
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                        const uint32_t a_base = smem_u32(smA + kb * A_CHUNK_BYTES);
+                        const uint32_t b_base = smem_u32(smB + stage * B_TILE_BYTES);
+#pragma unroll
+                        for (int k = 0; k < KCH / 16; ++k) {
+                            umma_bf16(tmem + nh * N_HALF, umma_desc_sw128(a_base + k * 32), umma_desc_sw128(b_base + k * 32),
+                                      (kb | k) ? 1u : 0u);
+                        }
+                        umma_commit(&ms.b_empty[stage]);          // frees the W2 slot when these MMAs retire
+                        if (++stage == B_STAGES) { stage = 0; phase ^= 1; }
+                    }
+                }
+                umma_commit(&ms.d_ready);                         // accumulator complete
+            }
+        }
+    } else {
+        // ===== compute warps: rows = TMEM lanes 32*(warp%4)..+31, column half hh =====
+        const int cw = warp - 2;
+        const int q = warp & 3, hh = cw >> 2;
+        const int row = q * 32 + lane;
+        const bool owner = hh == 0;
+        uint32_t d_phase = 0;
+        for (int tl = 0; tl < my_tiles; ++tl) {
+            const int tile = blockIdx.x + tl * gridDim.x;
+            const int k = tile * TILE_M + row;
+            const bool active = k < a.K;
+            const uint32_t kg = (uint32_t)(a.k_offset + k);
+            const bool exploit = (int)kg < a.n_exploit;
+            float z[4] = {sm.x0[0], sm.x0[1], sm.x0[2], 0.f};
+            float acc = 0.f, v0 = 0.f, v1 = 0.f, e[4] = {0.f, 0.f, 0.f, 0.f};
+            float4 ref = make_float4(0.f, 0.f, 0.f, 0.f);
+            const float2 *eps_k = a.eps ? reinterpret_cast<const float2 *>(a.eps) + (size_t)(active ? k : 0) * T : nullptr;
+            for (int t = 0; t < T; ++t) {
+                // (1) owner publishes the state; both halves evaluate their 256 columns of tanh(W01 x + b01)
+                if (owner) ms.xs[row] = make_float4(z[0], z[1], z[2], 0.f);
+                named_bar_sync(1, N_COMPUTE);
+                const float4 st = ms.xs[row];
+#pragma unroll 1
+                for (int c8 = 0; c8 < N_HALF / 8; ++c8) {            // 8 columns = one 16-byte chunk of a row
+                    const int col = hh * N_HALF + c8 * 8;
+                    uint32_t pk[4];
+#pragma unroll
+                    for (int p = 0; p < 4; ++p) {
+                        const float4 wa = ms.w01[col + 2 * p], wb = ms.w01[col + 2 * p + 1];
+                        const float pa = fmaf(wa.x, st.x, fmaf(wa.y, st.y, fmaf(wa.z, st.z, wa.w)));
+                        const float pb = fmaf(wb.x, st.x, fmaf(wb.y, st.y, fmaf(wb.z, st.z, wb.w)));
+                        pk[p] = tanh_bf16x2(pa, pb);
+                    }
+                    const int kb = col / KCH, ck = (col % KCH) / 8;      // K chunk, 16-byte chunk within the 128-byte row
+                    unsigned char *dst = smA + kb * A_CHUNK_BYTES + (row >> 3) * 1024 + (row & 7) * 128 + ((ck ^ (row & 7)) << 4);
+                    *reinterpret_cast<uint4 *>(dst) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy writes -> async proxy (UMMA)
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                mbar_arrive(&ms.a_ready);
+                // (2) owner overlaps the noise / control computation with the GEMM
+                if (owner) {
+                    if (eps_k) { const float2 ee = eps_k[t]; e[2 * (t & 1)] = ee.x; e[2 * (t & 1) + 1] = ee.y; }
+                    else if ((t & 1) == 0) philox_eps_pair(a, kg, (uint32_t)(t >> 1), 0u, e);
+                    const float2 u = sm.U[t];
+                    v0 = clampf(exploit ? __fadd_rn(u.x, e[2 * (t & 1)]) : e[2 * (t & 1)], a.umax0);
+                    v1 = clampf(exploit ? __fadd_rn(u.y, e[2 * (t & 1) + 1]) : e[2 * (t & 1) + 1], a.umax1);
+                }
+                // (3) epilogue: D -> +b2 -> tanh -> FP32 contraction with the 512x3 output layer
+                mbar_wait(&ms.d_ready, d_phase); d_phase ^= 1;
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                float r0 = 0.f, r1 = 0.f, r2 = 0.f;
+#pragma unroll 1
+                for (int c32 = 0; c32 < N_HALF / 32; ++c32) {
+                    const int col = hh * N_HALF + c32 * 32;
+                    uint32_t v[32];
+                    tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)col, v);
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        const float4 w = ms.w3[col + i];
+                        const float h = tanh_approx(__uint_as_float(v[i]) + w.x);
+                        r0 = fmaf(w.y, h, r0); r1 = fmaf(w.z, h, r1); r2 = fmaf(w.w, h, r2);
+                    }
+                }
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                if (!owner) ms.res[row] = make_float4(r0, r1, r2, 0.f);
+                named_bar_sync(1, N_COMPUTE);
+                // (4) owner: Euler step with the learned residual, nearest waypoint, stage cost
+                if (owner) {
+                    const float4 pr = ms.res[row];
+                    r0 += pr.x + ms.b3[0]; r1 += pr.y + ms.b3[1]; r2 += pr.z + ms.b3[2];
+                    float sn, cs;
+                    sincos_cw(z[2], sn, cs);
+                    z[0] = fmaf(fmaf(v0, cs, r0), a.dt, z[0]);
+                    z[1] = fmaf(fmaf(v0, sn, r1), a.dt, z[1]);
+                    z[2] = fmaf(v1 + r2, a.dt, z[2]);
+                    if (a.flags & F_COST_SUM) {                     // cost_mode == sum
+                        const int j = a.window == 20 ? nearest_wp<20>(sm, z[0], z[1]) : nearest_wp<0>(sm, z[0], z[1]);
+                        ref = window_ref(sm, j);
+                        const float2 qq = sm.Q[t];
+                        acc += tracking_cost<MPPI_MODEL_DIFFDRIVE>(ref, z, z[2], a.sw) + (qq.x * v0 + qq.y * v1);
+                    }
+                }
+            }
+            if (owner && active) {
+                if (a.flags & F_COST_SUM) {
+                    acc += tracking_cost<MPPI_MODEL_DIFFDRIVE>(ref, z, z[2], a.tw);
+                } else {
+                    const int j = a.window == 20 ? nearest_wp<20>(sm, z[0], z[1]) : nearest_wp<0>(sm, z[0], z[1]);
+                    ref = window_ref(sm, j);
+                    const float2 qq = sm.Q[T - 1];
+                    acc = tracking_cost<MPPI_MODEL_DIFFDRIVE>(ref, z, z[2], a.sw) + (qq.x * v0 + qq.y * v1) +
+                          tracking_cost<MPPI_MODEL_DIFFDRIVE>(ref, z, z[2], a.tw);
+                }
+                S_out[k] = acc;
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
+    }
+}
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                    const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+}  // namespace
+
+struct MlpState {
+    int K = 0, T = 0, n_sm = 148;
+    __nv_bfloat16 *d_w2 = nullptr;        // [512 out][512 in] bf16, K-major B operand
+    float4 *d_w01 = nullptr, *d_w3 = nullptr;
+    float *d_b3 = nullptr;
+    CUtensorMap w2_map;
+    bool ready = false;
+};
+
+MlpState *mlp_create(int K, int T) {
+    MlpState *m = new (std::nothrow) MlpState();
+    if (!m) return nullptr;
+    m->K = K; m->T = T;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&m->n_sm, cudaDevAttrMultiProcessorCount, dev);
+    if (cudaMalloc(&m->d_w2, sizeof(__nv_bfloat16) * HID * HID) != cudaSuccess ||
+        cudaMalloc(&m->d_w01, sizeof(float4) * HID) != cudaSuccess ||
+        cudaMalloc(&m->d_w3, sizeof(float4) * HID) != cudaSuccess ||
+        cudaMalloc(&m->d_b3, sizeof(float) * 4) != cudaSuccess) { mlp_destroy(m); return nullptr; }
+    if (cudaFuncSetAttribute(mppi_mlp_rollout_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MLP_DYN_SMEM) != cudaSuccess) {
+        mlp_destroy(m); return nullptr;
+    }
+    return m;
+}
+
+void mlp_destroy(MlpState *m) {
+    if (!m) return;
+    cudaFree(m->d_w2); cudaFree(m->d_w01); cudaFree(m->d_w3); cudaFree(m->d_b3);
+    delete m;
+}
+
+// Weights arrive as nn.Linear tensors [out][in] (dnn/simple_mlp.py:10-13).  Layer 0 has no activation,
+// so it is folded into layer 1 here (FP64 accumulation): W01 = W1 W0, b01 = W1 b0 + b1.
+cudaError_t mlp_set_weights(MlpState *m, const float *const W[4], const float *const b[4], cudaStream_t st) {
+    std::vector<float4> w01(HID), w3(HID);
+    for (int j = 0; j < HID; ++j) {
+        double s[3] = {0, 0, 0}, bb = b[1][j];
+        for (int i = 0; i < HID; ++i) {
+            const double w1 = W[1][(size_t)j * HID + i];
+            s[0] += w1 * W[0][i * 3 + 0]; s[1] += w1 * W[0][i * 3 + 1]; s[2] += w1 * W[0][i * 3 + 2];
+            bb += w1 * b[0][i];
+        }
+        w01[j] = make_float4((float)s[0], (float)s[1], (float)s[2], (float)bb);
+        w3[j] = make_float4(b[2][j], W[3][0 * HID + j], W[3][1 * HID + j], W[3][2 * HID + j]);
+    }
+    std::vector<__nv_bfloat16> w2((size_t)HID * HID);
+    for (size_t i = 0; i < w2.size(); ++i) w2[i] = __float2bfloat16(W[2][i]);
+    const float b3[4] = {b[3][0], b[3][1], b[3][2], 0.f};
+    cudaError_t e;
+    if ((e = cudaMemcpyAsync(m->d_w01, w01.data(), sizeof(float4) * HID, cudaMemcpyHostToDevice, st)) != cudaSuccess) return e;
+    if ((e = cudaMemcpyAsync(m->d_w3, w3.data(), sizeof(float4) * HID, cudaMemcpyHostToDevice, st)) != cudaSuccess) return e;
+    if ((e = cudaMemcpyAsync(m->d_b3, b3, sizeof(b3), cudaMemcpyHostToDevice, st)) != cudaSuccess) return e;
+    if ((e = cudaMemcpyAsync(m->d_w2, w2.data(), sizeof(__nv_bfloat16) * HID * HID, cudaMemcpyHostToDevice, st)) != cudaSuccess) return e;
+    if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return e;
+    // TMA descriptor of W2: inner dim = K (512 bf16, contiguous), outer dim = N (512 rows); 64 x 256 boxes, 128B swizzle
+    void *fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if ((e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres)) != cudaSuccess) return e;
+    if (!fn || qres != cudaDriverEntryPointSuccess) return cudaErrorNotSupported;
+    const cuuint64_t dims[2] = {HID, HID};
+    const cuuint64_t strides[1] = {HID * sizeof(__nv_bfloat16)};
+    const cuuint32_t box[2] = {KCH, N_HALF};
+    const cuuint32_t estr[2] = {1, 1};
+    CUresult r = ((PFN_encodeTiled)fn)(&m->w2_map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, m->d_w2, dims, strides, box, estr,
+                                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return cudaErrorInvalidValue;
+    m->ready = true;
+    return cudaSuccess;
+}
+
+int mlp_rollout_costs(MlpState *m, const TickArgs &args, bool sum, const float *d_eps, float *d_S, cudaStream_t st) {
+    if (!m || !m->ready) return -2;
+    TickArgs a = args;
+    a.eps = d_eps;
+    a.flags = sum ? F_COST_SUM : 0;
+    const int n_tiles = (a.K + TILE_M - 1) / TILE_M;
+    const int grid = n_tiles < m->n_sm ? n_tiles : m->n_sm;
+    mppi_mlp_rollout_kernel<<<grid, MLP_THREADS, MLP_DYN_SMEM, st>>>(a, m->w2_map, m->d_w01, m->d_w3, m->d_b3, d_S, n_tiles);
+    return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
+
+int mlp_launches_per_tick(const MlpState *) { return 1; }

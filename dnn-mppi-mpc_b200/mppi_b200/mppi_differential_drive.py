@@ -18,7 +18,8 @@ class MPPIAlgorithms(ControllerBase):
     def __init__(self, delta_t, ref_path, max_speed, max_omega, num_samples_K, num_horizons_T,
                  param_exploration, param_lambda, param_alpha, sigma, stage_cost_weight,
                  terminal_cost_weight, visualize_optimal_traj=True, visualze_sampled_trajs=True,
-                 *, seed=0, cost_mode="last", waypoint_mode="strict", temperature=None, device=0, rank=0, world=1,
+                 *, seed=0, cost_mode="last", waypoint_mode="strict", temperature=None, dynamics=None,
+                 device=0, rank=0, world=1,
                  _obstacles=None, _margin=1.0):
         self.delta_t = delta_t
         self.max_speed = max_speed
@@ -36,7 +37,7 @@ class MPPIAlgorithms(ControllerBase):
         self.visualze_sampled_trajs = visualze_sampled_trajs
         self._init_engine(
             ref_path=ref_path, seed=seed, device=device, rank=rank, world=world,
-            model="diffdrive", K=self.K, T=self.T, dt=delta_t, u_max=(max_speed, max_omega),
+            model="diffdrive" if dynamics is None else "diffdrive_mlp", K=self.K, T=self.T, dt=delta_t, u_max=(max_speed, max_omega),
             sigma=self.Sigma, stage_w=self.stage_cost_weight, term_w=self.terminal_cost_weight,
             param_exploration=param_exploration, param_lambda=param_lambda, param_alpha=param_alpha,
             temperature=param_exploration if temperature is None else temperature,   # Q2 (:175,:178)
@@ -44,7 +45,28 @@ class MPPIAlgorithms(ControllerBase):
             cost_mode=cost_mode, waypoint_mode=waypoint_mode, filter_kind="diffdrive",
             yaw_wrap=False, collision=self._collision, obstacles=_obstacles, margin=_margin)
 
+        if dynamics is not None:
+            self.set_dynamics(dynamics)
+
     prev_way_point_idx = property(ControllerBase._get_idx, ControllerBase._set_idx)
+
+    def set_dynamics(self, dynamics):
+        """Learned dynamics x+ = x + dt*([v cos th, v sin th, w] + MLP(x)).  `dynamics` is a
+        dnn/simple_mlp.py-shaped torch module (input_layer, hidden_layer[0..1], output_layer) or a dict
+        {'W0','b0',...,'W3','b3'} of nn.Linear-layout arrays.  Requires waypoint_mode='frozen'."""
+        if hasattr(dynamics, "state_dict"):
+            sd = {k: v.detach().cpu().numpy() for k, v in dynamics.state_dict().items()}
+            names = ["input_layer", "hidden_layer.0", "hidden_layer.1", "output_layer"]
+            W = [sd[n + ".weight"] for n in names]
+            b = [sd[n + ".bias"] for n in names]
+        else:
+            W = [np.asarray(dynamics["W%d" % i]) for i in range(4)]
+            b = [np.asarray(dynamics["b%d" % i]) for i in range(4)]
+        shapes = [(512, 3), (512, 512), (512, 512), (3, 512)]
+        for w, sh in zip(W, shapes):
+            if tuple(w.shape) != sh:
+                raise ValueError("MLP weights must have the dnn/simple_mlp.py shapes %s" % (shapes,))
+        self._engine.set_mlp(W, b)
 
     def _calc_input_control(self, observed_x, noise=None):
         """One control tick (reference :87-165).  `noise`: optional injected (K,T,2) epsilon."""

@@ -1,0 +1,96 @@
+"""Config 3: differential-drive MPPI whose rollout goes through the simple_mlp residual on the
+tcgen05 tensor cores.  There is no MPPI-through-MLP in the reference: the oracle is
+the reference tick with `_state_transition` replaced by explicit Euler on f + MLP (FP64 numpy).
+The device evaluates the hidden GEMM with bf16 operands / FP32 accumulation and MUFU tanh, so the
+parity bound is looser than for the analytic kernels and is stated here."""
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+from golden_util import Golden  # noqa: E402
+from gpu_util import engine_from_spec  # noqa: E402
+from oracle import mppi_oracle as orc  # noqa: E402
+
+# bf16 hidden activations + weights (2^-9 relative each) through a 512-wide layer whose output is scaled by 0.01:
+# observed per-sample cost error ~1e-4 relative; bound at 2e-3
+MLP_COST_RTOL = 2e-3
+MLP_U_ATOL = 2e-3
+
+
+def _spec(K, T, cost_mode, mlp):
+    sp = orc.diffdrive_spec(K=K, T=T, param_exploration=0.05, cost_mode=cost_mode, waypoint_mode="frozen",
+                            model="diffdrive_mlp", mlp=mlp)
+    sp.temperature = 2.0
+    return sp
+
+
+@pytest.mark.parametrize("cost_mode", ["sum", "last"])
+@pytest.mark.parametrize("K", [128, 300, 1024])
+def test_mlp_rollout_costs_match_fp64_oracle(K, cost_mode):
+    g = Golden("diffdrive_pe0.05")
+    T = 12
+    mlp = orc.make_mlp(seed=0, out_scale=0.01)
+    sp = _spec(K, T, cost_mode, mlp)
+    eng = engine_from_spec(sp, g.path)
+    eng.set_mlp([mlp["W%d" % i] for i in range(4)], [mlp["b%d" % i] for i in range(4)])
+    eps = torch.zeros(K, T, 2, dtype=torch.float32, device="cuda")
+    eng.generate_noise(eps, seed=3, tick=1)
+    S = torch.zeros(K, dtype=torch.float32, device="cuda")
+    x0 = np.array([0.4, 0.3, 0.5])
+    for src in ("philox", "injected"):
+        S.zero_()
+        eng.set_waypoint_idx(0)
+        eng.rollout_costs(x0, S, eps if src == "injected" else None, seed=3, tick=1)
+        So, _, s_end = orc.costs_vec(sp, g.path, np.zeros((T, 2)), 0, x0, eps.cpu().numpy().astype(np.float64))
+        Sg = S.cpu().numpy().astype(np.float64)
+        rel = np.abs(Sg - So) / np.maximum(np.abs(So), 1e-9)
+        assert rel.max() <= MLP_COST_RTOL, (K, cost_mode, src, rel.max())
+        assert eng.get_waypoint_idx() == s_end
+    eng.close()
+
+
+def test_mlp_residual_changes_the_rollout():
+    """The learned term is really applied: costs differ from the analytic model by far more than the bound."""
+    g = Golden("diffdrive_pe0.05")
+    K, T = 256, 12
+    mlp = orc.make_mlp(seed=0, out_scale=0.5)
+    sp = _spec(K, T, "sum", mlp)
+    eng = engine_from_spec(sp, g.path)
+    eng.set_mlp([mlp["W%d" % i] for i in range(4)], [mlp["b%d" % i] for i in range(4)])
+    eps = torch.zeros(K, T, 2, dtype=torch.float32, device="cuda")
+    eng.generate_noise(eps, seed=3, tick=1)
+    S = torch.zeros(K, dtype=torch.float32, device="cuda")
+    x0 = np.array([0.4, 0.3, 0.5])
+    eng.rollout_costs(x0, S, None, seed=3, tick=1)
+    So, _, _ = orc.costs_vec(sp, g.path, np.zeros((T, 2)), 0, x0, eps.cpu().numpy().astype(np.float64))
+    sp_plain = orc.diffdrive_spec(K=K, T=T, param_exploration=0.05, cost_mode="sum", waypoint_mode="frozen")
+    Sp, _, _ = orc.costs_vec(sp_plain, g.path, np.zeros((T, 2)), 0, x0, eps.cpu().numpy().astype(np.float64))
+    Sg = S.cpu().numpy().astype(np.float64)
+    assert np.median(np.abs(Sg - Sp) / Sp) > 0.05
+    assert np.max(np.abs(Sg - So) / So) <= 2e-2          # out_scale 50x larger -> bound 50x/5 looser
+    eng.close()
+
+
+def test_mlp_full_tick_and_drop_in_class():
+    from mppi_b200.mppi_differential_drive import MPPIAlgorithms
+    g = Golden("diffdrive_pe0.05")
+    K, T = 2048, 30
+    mlp = orc.make_mlp(seed=1, out_scale=0.01)
+    ctrl = MPPIAlgorithms(delta_t=0.1, ref_path=g.path, max_speed=5.0, max_omega=3.14, num_samples_K=K, num_horizons_T=T,
+                          param_exploration=0.05, param_lambda=1.0, param_alpha=0.2, sigma=np.array([[0.1, 0.0], [0.0, 0.01]]),
+                          stage_cost_weight=np.array([5.0, 5.0, 10.0]), terminal_cost_weight=np.array([5.0, 5.0, 10.0]),
+                          visualize_optimal_traj=False, visualze_sampled_trajs=False, cost_mode="sum",
+                          waypoint_mode="frozen", temperature=2.0, dynamics=mlp, seed=4)
+    sp = _spec(K, T, "sum", mlp)
+    eps = torch.zeros(K, T, 2, dtype=torch.float32, device="cuda")
+    x0 = np.array([0.2, 0.1, 0.3])
+    U, idx = np.zeros((T, 2)), 0
+    for tick in range(2):
+        ctrl.engine.generate_noise(eps, seed=4, tick=tick)
+        o = orc.tick_vec(sp, g.path, U, idx, x0, eps.cpu().numpy().astype(np.float64))
+        u0, u, _, _ = ctrl._calc_input_control(x0)
+        assert np.max(np.abs(u - o["U_after"])) <= MLP_U_ATOL, (tick, np.max(np.abs(u - o["U_after"])))
+        assert ctrl.prev_way_point_idx == o["idx_after"]
+        U, idx = u.copy(), o["idx_after"]

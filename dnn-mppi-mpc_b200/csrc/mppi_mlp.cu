@@ -10,14 +10,15 @@
 //     write as the bf16 A operand straight into shared memory in the UMMA SWIZZLE_128B K-major layout;
 //   * the remaining 512x512 layer is the GEMM: D[128x512] (FP32, all 512 TMEM columns) =
 //     A[128x512] (smem) x W2^T, issued by ONE thread as tcgen05.mma.cta_group::1.kind::f16 (M=128,
-//     N=256, K=16), W2 streamed from L2 by TMA (cp.async.bulk.tensor, 256x64 bf16 boxes, 128B swizzle)
-//     through an mbarrier ring;
+//     N=128, K=16), W2 streamed from L2 by TMA (cp.async.bulk.tensor, 128x64 bf16 boxes, 128B swizzle)
+//     through a 4-stage mbarrier ring; the four 128-column accumulator quarters complete (and are
+//     signalled) one after the other, so the epilogue of one quarter overlaps the MMAs of the next;
 //   * the epilogue warps read the accumulator with tcgen05.ld (32x32b.x32), add b2, apply tanh and
 //     contract with the 512x3 output layer in FP32 registers -- the output layer never touches memory;
 //   * the unicycle step, nearest-waypoint search and cost run in the same epilogue threads with the
 //     state in registers across the horizon.
-// Warp roles: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2..9 = 8 compute
-// warps (two per TMEM lane quarter, each owning half of the 512 columns).
+// Warp roles: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2..17 = 16 compute
+// warps (four per TMEM lane quarter; group g = (warp-2)/4 owns accumulator quarter g, 128 columns).
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
@@ -33,26 +34,30 @@ namespace {
 constexpr int HID = 512;
 constexpr int TILE_M = 128;
 constexpr int KCH = 64;                   // K elements per 128-byte swizzle span (bf16)
-constexpr int N_HALF = 256;               // N per tcgen05.mma
-constexpr int B_STAGES = 2;
-constexpr int B_TILE_BYTES = N_HALF * KCH * 2;     // 32 KB
+
+constexpr int N_MMA = 128;                // N per tcgen05.mma = one accumulator quarter
+constexpr int N_QUARTERS = HID / N_MMA;
+constexpr int B_STAGES = 4;
+constexpr int B_TILE_BYTES = N_MMA * KCH * 2;      // 16 KB
 constexpr int A_CHUNK_BYTES = TILE_M * KCH * 2;    // 16 KB per K chunk
 constexpr int A_BYTES = A_CHUNK_BYTES * (HID / KCH);   // 128 KB
-constexpr int MLP_THREADS = 320;
-constexpr int N_COMPUTE = 256;
+constexpr int N_GROUPS = 4;                // compute-warp groups: group g owns accumulator quarter g (128 columns)
+constexpr int N_COMPUTE = 128 * N_GROUPS;  // 16 compute warps: 4 per TMEM lane quarter
+constexpr int MLP_THREADS = 64 + N_COMPUTE;
+constexpr int COLS_PER_GROUP = HID / N_GROUPS;
 
 struct MlpSmem {                          // after the 1024-aligned A / B regions
     float4 w01[HID];                      // (W01[j][0], W01[j][1], W01[j][2], b01[j])
     float4 w3[HID];                       // (b2[j], W3[0][j], W3[1][j], W3[2][j])
     float4 xs[TILE_M];                    // current state of each row for the partner thread
-    float4 res[TILE_M];                   // partner's partial output-layer sums
-    unsigned long long b_full[B_STAGES], b_empty[B_STAGES], a_ready, d_ready;
+    float4 res[N_GROUPS - 1][TILE_M];     // partners' partial output-layer sums
+    unsigned long long b_full[B_STAGES], b_empty[B_STAGES], a_ready, d_ready[N_QUARTERS];
     unsigned long long key[8];
     uint32_t tmem_base;
     float b3[3];
 };
 
-constexpr size_t MLP_DYN_SMEM = 1024 /*align slack*/ + A_BYTES + B_STAGES * B_TILE_BYTES + sizeof(TickSmem) + sizeof(MlpSmem);
+constexpr size_t MLP_DYN_SMEM = A_BYTES + B_STAGES * B_TILE_BYTES + sizeof(TickSmem) + sizeof(MlpSmem);
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -91,8 +96,8 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
     return d;
 }
 
-// kind::f16 instruction descriptor: BF16 x BF16 -> F32, K-major A and B, M=128, N=256
-constexpr uint32_t UMMA_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N_HALF >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
+// kind::f16 instruction descriptor: BF16 x BF16 -> F32, K-major A and B, M=128, N=128
+constexpr uint32_t UMMA_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N_MMA >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
 
 __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t accumulate) {
     asm volatile(
@@ -135,8 +140,9 @@ __global__ void __launch_bounds__(MLP_THREADS, 1)
 mppi_mlp_rollout_kernel(const __grid_constant__ TickArgs a, const __grid_constant__ CUtensorMap w2_map,
                         const float4 *__restrict__ g_w01, const float4 *__restrict__ g_w3, const float *__restrict__ g_b3,
                         float *__restrict__ S_out, int n_tiles) {
-    extern __shared__ unsigned char dyn_raw[];
-    unsigned char *dyn = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(dyn_raw) + 1023) & ~(uintptr_t)1023);
+    // 1024-byte alignment is what SWIZZLE_128B needs; keeping every pointer derived from this symbol (no
+    // integer round-trips) lets the compiler emit LDS/STS instead of generic LD/ST
+    extern __shared__ __align__(1024) unsigned char dyn[];
     unsigned char *smA = dyn;                                     // 8 chunks x [128 rows x 128 B]
     unsigned char *smB = dyn + A_BYTES;                           // B_STAGES x [256 rows x 128 B]
     TickSmem &sm = *reinterpret_cast<TickSmem *>(dyn + A_BYTES + B_STAGES * B_TILE_BYTES);
@@ -152,7 +158,7 @@ mppi_mlp_rollout_kernel(const __grid_constant__ TickArgs a, const __grid_constan
     if (tid == 0) {
         for (int s = 0; s < B_STAGES; ++s) { mbar_init(&ms.b_full[s], 1); mbar_init(&ms.b_empty[s], 1); }
         mbar_init(&ms.a_ready, N_COMPUTE);
-        mbar_init(&ms.d_ready, 1);
+        for (int qd = 0; qd < N_QUARTERS; ++qd) mbar_init(&ms.d_ready[qd], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -209,13 +215,13 @@ mppi_mlp_rollout_kernel(const __grid_constant__ TickArgs a, const __grid_constan
     if (warp == 0) {
         // ===== TMA producer: the same 16 W2 boxes every timestep, through a B_STAGES ring =====
         if (lane == 0) {
-            const int total = my_tiles * T * 2 * (HID / KCH);
+            const int total = my_tiles * T * N_QUARTERS * (HID / KCH);
             int stage = 0; uint32_t phase = 0;
             for (int it = 0; it < total; ++it) {
-                const int kb = it % (HID / KCH), nh = (it / (HID / KCH)) & 1;
+                const int kb = it % (HID / KCH), nq = (it / (HID / KCH)) % N_QUARTERS;
                 mbar_wait(&ms.b_empty[stage], phase ^ 1);
                 mbar_expect_tx(&ms.b_full[stage], B_TILE_BYTES);
-                tma_load_2d(smB + stage * B_TILE_BYTES, &w2_map, &ms.b_full[stage], kb * KCH, nh * N_HALF);
+                tma_load_2d(smB + stage * B_TILE_BYTES, &w2_map, &ms.b_full[stage], kb * KCH, nq * N_MMA);
                 if (++stage == B_STAGES) { stage = 0; phase ^= 1; }
             }
         }
@@ -226,7 +232,7 @@ mppi_mlp_rollout_kernel(const __grid_constant__ TickArgs a, const __grid_constan
             for (int step = 0; step < my_tiles * T; ++step) {
                 mbar_wait(&ms.a_ready, a_phase); a_phase ^= 1;
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                for (int nh = 0; nh < 2; ++nh) {
+                for (int nq = 0; nq < N_QUARTERS; ++nq) {
                     for (int kb = 0; kb < HID / KCH; ++kb) {
                         mbar_wait(&ms.b_full[stage], phase);
                         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -234,22 +240,22 @@ mppi_mlp_rollout_kernel(const __grid_constant__ TickArgs a, const __grid_constan
                         const uint32_t b_base = smem_u32(smB + stage * B_TILE_BYTES);
 #pragma unroll
                         for (int k = 0; k < KCH / 16; ++k) {
-                            umma_bf16(tmem + nh * N_HALF, umma_desc_sw128(a_base + k * 32), umma_desc_sw128(b_base + k * 32),
+                            umma_bf16(tmem + nq * N_MMA, umma_desc_sw128(a_base + k * 32), umma_desc_sw128(b_base + k * 32),
                                       (kb | k) ? 1u : 0u);
                         }
                         umma_commit(&ms.b_empty[stage]);          // frees the W2 slot when these MMAs retire
                         if (++stage == B_STAGES) { stage = 0; phase ^= 1; }
                     }
+                    umma_commit(&ms.d_ready[nq]);                 // this accumulator quarter is complete
                 }
-                umma_commit(&ms.d_ready);                         // accumulator complete
             }
         }
     } else {
-        // ===== compute warps: rows = TMEM lanes 32*(warp%4)..+31, column half hh =====
+        // ===== compute warps: rows = TMEM lanes 32*(warp%4)..+31, column group grp =====
         const int cw = warp - 2;
-        const int q = warp & 3, hh = cw >> 2;
+        const int q = warp & 3, grp = cw >> 2;          // TMEM lane quarter (hardware: warp % 4), column group
         const int row = q * 32 + lane;
-        const bool owner = hh == 0;
+        const bool owner = grp == 0;
         uint32_t d_phase = 0;
         for (int tl = 0; tl < my_tiles; ++tl) {
             const int tile = blockIdx.x + tl * gridDim.x;
@@ -266,9 +272,9 @@ mppi_mlp_rollout_kernel(const __grid_constant__ TickArgs a, const __grid_constan
                 if (owner) ms.xs[row] = make_float4(z[0], z[1], z[2], 0.f);
                 named_bar_sync(1, N_COMPUTE);
                 const float4 st = ms.xs[row];
-#pragma unroll 1
-                for (int c8 = 0; c8 < N_HALF / 8; ++c8) {            // 8 columns = one 16-byte chunk of a row
-                    const int col = hh * N_HALF + c8 * 8;
+#pragma unroll 2
+                for (int c8 = 0; c8 < COLS_PER_GROUP / 8; ++c8) {    // 8 columns = one 16-byte chunk of a row
+                    const int col = grp * COLS_PER_GROUP + c8 * 8;
                     uint32_t pk[4];
 #pragma unroll
                     for (int p = 0; p < 4; ++p) {
@@ -293,12 +299,14 @@ mppi_mlp_rollout_kernel(const __grid_constant__ TickArgs a, const __grid_constan
                     v1 = clampf(exploit ? __fadd_rn(u.y, e[2 * (t & 1) + 1]) : e[2 * (t & 1) + 1], a.umax1);
                 }
                 // (3) epilogue: D -> +b2 -> tanh -> FP32 contraction with the 512x3 output layer
-                mbar_wait(&ms.d_ready, d_phase); d_phase ^= 1;
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 float r0 = 0.f, r1 = 0.f, r2 = 0.f;
 #pragma unroll 1
-                for (int c32 = 0; c32 < N_HALF / 32; ++c32) {
-                    const int col = hh * N_HALF + c32 * 32;
+                for (int c32 = 0; c32 < COLS_PER_GROUP / 32; ++c32) {
+                    const int col = grp * COLS_PER_GROUP + c32 * 32;
+                    if ((col & (N_MMA - 1)) == 0) {               // entering a new accumulator quarter: wait for its MMAs
+                        mbar_wait(&ms.d_ready[col / N_MMA], d_phase);
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    }
                     uint32_t v[32];
                     tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)col, v);
                     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
@@ -309,13 +317,15 @@ mppi_mlp_rollout_kernel(const __grid_constant__ TickArgs a, const __grid_constan
                         r0 = fmaf(w.y, h, r0); r1 = fmaf(w.z, h, r1); r2 = fmaf(w.w, h, r2);
                     }
                 }
+                d_phase ^= 1;
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                if (!owner) ms.res[row] = make_float4(r0, r1, r2, 0.f);
+                if (!owner) ms.res[grp - 1][row] = make_float4(r0, r1, r2, 0.f);
                 named_bar_sync(1, N_COMPUTE);
                 // (4) owner: Euler step with the learned residual, nearest waypoint, stage cost
                 if (owner) {
-                    const float4 pr = ms.res[row];
-                    r0 += pr.x + ms.b3[0]; r1 += pr.y + ms.b3[1]; r2 += pr.z + ms.b3[2];
+#pragma unroll
+                    for (int g = 0; g < N_GROUPS - 1; ++g) { const float4 pr = ms.res[g][row]; r0 += pr.x; r1 += pr.y; r2 += pr.z; }
+                    r0 += ms.b3[0]; r1 += ms.b3[1]; r2 += ms.b3[2];
                     float sn, cs;
                     sincos_cw(z[2], sn, cs);
                     z[0] = fmaf(fmaf(v0, cs, r0), a.dt, z[0]);
@@ -418,7 +428,7 @@ cudaError_t mlp_set_weights(MlpState *m, const float *const W[4], const float *c
     if (!fn || qres != cudaDriverEntryPointSuccess) return cudaErrorNotSupported;
     const cuuint64_t dims[2] = {HID, HID};
     const cuuint64_t strides[1] = {HID * sizeof(__nv_bfloat16)};
-    const cuuint32_t box[2] = {KCH, N_HALF};
+    const cuuint32_t box[2] = {KCH, N_MMA};
     const cuuint32_t estr[2] = {1, 1};
     CUresult r = ((PFN_encodeTiled)fn)(&m->w2_map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, m->d_w2, dims, strides, box, estr,
                                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,

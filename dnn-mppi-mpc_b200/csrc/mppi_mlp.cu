@@ -7,12 +7,14 @@
 //   * the input layer has NO activation (simple_mlp.py:19), so Linear(3,512) and the first hidden
 //     Linear(512,512) are folded on the host into one 3->512 map (W01 = W1 W0, b01 = W1 b0 + b1) that
 //     the compute warps evaluate in FP32 on the CUDA cores, apply tanh (MUFU tanh.approx.bf16x2) and
-//     write as the bf16 A operand straight into shared memory in the UMMA SWIZZLE_128B K-major layout;
-//   * the remaining 512x512 layer is the GEMM: D[128x512] (FP32, all 512 TMEM columns) =
-//     A[128x512] (smem) x W2^T, issued by ONE thread as tcgen05.mma.cta_group::1.kind::f16 (M=128,
-//     N=128, K=16), W2 streamed from L2 by TMA (cp.async.bulk.tensor, 128x64 bf16 boxes, 128B swizzle)
-//     through a 4-stage mbarrier ring; the four 128-column accumulator quarters complete (and are
-//     signalled) one after the other, so the epilogue of one quarter overlaps the MMAs of the next;
+//     store as the bf16 A operand straight into TENSOR MEMORY (tcgen05.st, 256 columns): the
+//     activations never touch shared memory, which leaves it all to the weight stream;
+//   * the remaining 512x512 layer is the GEMM: D[128x512] = A[128x512] (TMEM) x W2^T, issued by ONE
+//     thread as tcgen05.mma.cta_group::1.kind::f16 with the A operand in TMEM (M=128, N=128, K=16), W2
+//     streamed from L2 by TMA (cp.async.bulk.tensor, 128x64 bf16 boxes, 128B swizzle) through a
+//     12-stage mbarrier ring (192 KB in flight hides the L2 latency); the accumulator is produced in
+//     four 128-column quarters through two TMEM buffers (2 x 128 columns), so the epilogue of one
+//     quarter overlaps the MMAs of the next;
 //   * the epilogue warps read the accumulator with tcgen05.ld (32x32b.x32), add b2, apply tanh and
 //     contract with the 512x3 output layer in FP32 registers -- the output layer never touches memory;
 //   * the unicycle step, nearest-waypoint search and cost run in the same epilogue threads with the
@@ -37,10 +39,10 @@ constexpr int KCH = 64;                   // K elements per 128-byte swizzle spa
 
 constexpr int N_MMA = 128;                // N per tcgen05.mma = one accumulator quarter
 constexpr int N_QUARTERS = HID / N_MMA;
-constexpr int B_STAGES = 4;
+constexpr int B_STAGES = 12;
 constexpr int B_TILE_BYTES = N_MMA * KCH * 2;      // 16 KB
-constexpr int A_CHUNK_BYTES = TILE_M * KCH * 2;    // 16 KB per K chunk
-constexpr int A_BYTES = A_CHUNK_BYTES * (HID / KCH);   // 128 KB
+constexpr int TMEM_A_COL = 0;             // A operand: 512 bf16 per row = 256 packed 32-bit columns
+constexpr int TMEM_D_COL = 256;           // two accumulator buffers of 128 FP32 columns
 constexpr int N_GROUPS = 4;                // compute-warp groups: group g owns accumulator quarter g (128 columns)
 constexpr int N_COMPUTE = 128 * N_GROUPS;  // 16 compute warps: 4 per TMEM lane quarter
 constexpr int MLP_THREADS = 64 + N_COMPUTE;
@@ -51,13 +53,13 @@ struct MlpSmem {                          // after the 1024-aligned A / B region
     float4 w3[HID];                       // (b2[j], W3[0][j], W3[1][j], W3[2][j])
     float4 xs[TILE_M];                    // current state of each row for the partner thread
     float4 res[N_GROUPS - 1][TILE_M];     // partners' partial output-layer sums
-    unsigned long long b_full[B_STAGES], b_empty[B_STAGES], a_ready, d_ready[N_QUARTERS];
+    unsigned long long b_full[B_STAGES], b_empty[B_STAGES], a_ready, d_full[2], d_empty[2];
     unsigned long long key[8];
     uint32_t tmem_base;
     float b3[3];
 };
 
-constexpr size_t MLP_DYN_SMEM = A_BYTES + B_STAGES * B_TILE_BYTES + sizeof(TickSmem) + sizeof(MlpSmem);
+constexpr size_t MLP_DYN_SMEM = B_STAGES * B_TILE_BYTES + sizeof(TickSmem) + sizeof(MlpSmem);
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -106,6 +108,17 @@ __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(UMMA_IDESC), "r"(accumulate) : "memory");
 }
+// A operand in tensor memory (128 lanes x 8 packed bf16x2 columns per K=16 step), B in shared memory
+__device__ __forceinline__ void umma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, {%5, %5, %5, %5}, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(UMMA_IDESC), "r"(accumulate), "r"(0u) : "memory");
+}
+__device__ __forceinline__ void tmem_st4(uint32_t taddr, uint32_t r0, uint32_t r1, uint32_t r2, uint32_t r3) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(r0), "r"(r1), "r"(r2), "r"(r3) : "memory");
+}
 __device__ __forceinline__ void umma_commit(unsigned long long *bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -143,10 +156,9 @@ mppi_mlp_rollout_kernel(const __grid_constant__ TickArgs a, const __grid_constan
     // 1024-byte alignment is what SWIZZLE_128B needs; keeping every pointer derived from this symbol (no
     // integer round-trips) lets the compiler emit LDS/STS instead of generic LD/ST
     extern __shared__ __align__(1024) unsigned char dyn[];
-    unsigned char *smA = dyn;                                     // 8 chunks x [128 rows x 128 B]
-    unsigned char *smB = dyn + A_BYTES;                           // B_STAGES x [256 rows x 128 B]
-    TickSmem &sm = *reinterpret_cast<TickSmem *>(dyn + A_BYTES + B_STAGES * B_TILE_BYTES);
-    MlpSmem &ms = *reinterpret_cast<MlpSmem *>(dyn + A_BYTES + B_STAGES * B_TILE_BYTES + sizeof(TickSmem));
+    unsigned char *smB = dyn;                                     // B_STAGES x [128 rows x 128 B], 1024-aligned
+    TickSmem &sm = *reinterpret_cast<TickSmem *>(dyn + B_STAGES * B_TILE_BYTES);
+    MlpSmem &ms = *reinterpret_cast<MlpSmem *>(dyn + B_STAGES * B_TILE_BYTES + sizeof(TickSmem));
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int T = a.T;
     const int my_tiles = (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
@@ -158,7 +170,7 @@ mppi_mlp_rollout_kernel(const __grid_constant__ TickArgs a, const __grid_constan
     if (tid == 0) {
         for (int s = 0; s < B_STAGES; ++s) { mbar_init(&ms.b_full[s], 1); mbar_init(&ms.b_empty[s], 1); }
         mbar_init(&ms.a_ready, N_COMPUTE);
-        for (int qd = 0; qd < N_QUARTERS; ++qd) mbar_init(&ms.d_ready[qd], 1);
+        for (int bf = 0; bf < 2; ++bf) { mbar_init(&ms.d_full[bf], 1); mbar_init(&ms.d_empty[bf], N_COMPUTE); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -228,25 +240,28 @@ mppi_mlp_rollout_kernel(const __grid_constant__ TickArgs a, const __grid_constan
     } else if (warp == 1) {
         // ===== MMA issuer: one thread drives the tensor core =====
         if (lane == 0) {
-            int stage = 0; uint32_t phase = 0, a_phase = 0;
+            int stage = 0; uint32_t phase = 0, a_phase = 0, quarter = 0;
             for (int step = 0; step < my_tiles * T; ++step) {
                 mbar_wait(&ms.a_ready, a_phase); a_phase ^= 1;
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                for (int nq = 0; nq < N_QUARTERS; ++nq) {
+                for (int nq = 0; nq < N_QUARTERS; ++nq, ++quarter) {
+                    const uint32_t buf = quarter & 1;
+                    mbar_wait(&ms.d_empty[buf], ((quarter >> 1) & 1) ^ 1);      // epilogue drained this buffer
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t d_tmem = tmem + TMEM_D_COL + buf * N_MMA;
                     for (int kb = 0; kb < HID / KCH; ++kb) {
                         mbar_wait(&ms.b_full[stage], phase);
                         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                        const uint32_t a_base = smem_u32(smA + kb * A_CHUNK_BYTES);
                         const uint32_t b_base = smem_u32(smB + stage * B_TILE_BYTES);
 #pragma unroll
                         for (int k = 0; k < KCH / 16; ++k) {
-                            umma_bf16(tmem + nq * N_MMA, umma_desc_sw128(a_base + k * 32), umma_desc_sw128(b_base + k * 32),
-                                      (kb | k) ? 1u : 0u);
+                            umma_bf16_ts(d_tmem, tmem + TMEM_A_COL + (kb * (KCH / 16) + k) * 8, umma_desc_sw128(b_base + k * 32),
+                                         (kb | k) ? 1u : 0u);
                         }
                         umma_commit(&ms.b_empty[stage]);          // frees the W2 slot when these MMAs retire
                         if (++stage == B_STAGES) { stage = 0; phase ^= 1; }
                     }
-                    umma_commit(&ms.d_ready[nq]);                 // this accumulator quarter is complete
+                    umma_commit(&ms.d_full[buf]);                 // this accumulator quarter is complete
                 }
             }
         }
@@ -256,7 +271,7 @@ mppi_mlp_rollout_kernel(const __grid_constant__ TickArgs a, const __grid_constan
         const int q = warp & 3, grp = cw >> 2;          // TMEM lane quarter (hardware: warp % 4), column group
         const int row = q * 32 + lane;
         const bool owner = grp == 0;
-        uint32_t d_phase = 0;
+        uint32_t d_phase[2] = {0, 0};
         for (int tl = 0; tl < my_tiles; ++tl) {
             const int tile = blockIdx.x + tl * gridDim.x;
             const int k = tile * TILE_M + row;
@@ -264,7 +279,7 @@ mppi_mlp_rollout_kernel(const __grid_constant__ TickArgs a, const __grid_constan
             const uint32_t kg = (uint32_t)(a.k_offset + k);
             const bool exploit = (int)kg < a.n_exploit;
             float z[4] = {sm.x0[0], sm.x0[1], sm.x0[2], 0.f};
-            float acc = 0.f, v0 = 0.f, v1 = 0.f, e[4] = {0.f, 0.f, 0.f, 0.f};
+            float acc = 0.f, v0 = 0.f, v1 = 0.f, e[4] = {0.f, 0.f, 0.f, 0.f}, sn = 0.f, cs = 1.f;
             float4 ref = make_float4(0.f, 0.f, 0.f, 0.f);
             const float2 *eps_k = a.eps ? reinterpret_cast<const float2 *>(a.eps) + (size_t)(active ? k : 0) * T : nullptr;
             for (int t = 0; t < T; ++t) {
@@ -283,33 +298,40 @@ mppi_mlp_rollout_kernel(const __grid_constant__ TickArgs a, const __grid_constan
                         const float pb = fmaf(wb.x, st.x, fmaf(wb.y, st.y, fmaf(wb.z, st.z, wb.w)));
                         pk[p] = tanh_bf16x2(pa, pb);
                     }
-                    const int kb = col / KCH, ck = (col % KCH) / 8;      // K chunk, 16-byte chunk within the 128-byte row
-                    unsigned char *dst = smA + kb * A_CHUNK_BYTES + (row >> 3) * 1024 + (row & 7) * 128 + ((ck ^ (row & 7)) << 4);
-                    *reinterpret_cast<uint4 *>(dst) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                    tmem_st4(tmem + ((uint32_t)(q * 32) << 16) + TMEM_A_COL + (uint32_t)(col >> 1), pk[0], pk[1], pk[2], pk[3]);
                 }
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy writes -> async proxy (UMMA)
+                asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                 mbar_arrive(&ms.a_ready);
-                // (2) owner overlaps the noise / control computation with the GEMM
+                // (2) owner overlaps with the GEMM: stage cost of the state reached by the previous step, then the
+                //     noise and clamped control of this step
                 if (owner) {
+                    if (t > 0 && (a.flags & F_COST_SUM)) {
+                        const int j = a.window == 20 ? nearest_wp<20>(sm, z[0], z[1]) : nearest_wp<0>(sm, z[0], z[1]);
+                        ref = window_ref(sm, j);
+                        const float2 qq = sm.Q[t - 1];
+                        acc += tracking_cost<MPPI_MODEL_DIFFDRIVE>(ref, z, z[2], a.sw) + (qq.x * v0 + qq.y * v1);
+                    }
                     if (eps_k) { const float2 ee = eps_k[t]; e[2 * (t & 1)] = ee.x; e[2 * (t & 1) + 1] = ee.y; }
                     else if ((t & 1) == 0) philox_eps_pair(a, kg, (uint32_t)(t >> 1), 0u, e);
                     const float2 u = sm.U[t];
                     v0 = clampf(exploit ? __fadd_rn(u.x, e[2 * (t & 1)]) : e[2 * (t & 1)], a.umax0);
                     v1 = clampf(exploit ? __fadd_rn(u.y, e[2 * (t & 1) + 1]) : e[2 * (t & 1) + 1], a.umax1);
+                    sincos_cw(z[2], sn, cs);
                 }
                 // (3) epilogue: D -> +b2 -> tanh -> FP32 contraction with the 512x3 output layer
                 float r0 = 0.f, r1 = 0.f, r2 = 0.f;
 #pragma unroll 1
-                for (int c32 = 0; c32 < COLS_PER_GROUP / 32; ++c32) {
-                    const int col = grp * COLS_PER_GROUP + c32 * 32;
-                    if ((col & (N_MMA - 1)) == 0) {               // entering a new accumulator quarter: wait for its MMAs
-                        mbar_wait(&ms.d_ready[col / N_MMA], d_phase);
-                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    }
+                for (int nq = 0; nq < N_QUARTERS; ++nq) {         // every group takes 32 columns of EACH quarter, so the
+                    const int col = nq * N_MMA + grp * 32;        // work exposed after the last MMA is 32 columns, not 128
+                    const int buf = nq & 1;
+                    mbar_wait(&ms.d_full[buf], d_phase[buf]); d_phase[buf] ^= 1;
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     uint32_t v[32];
-                    tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)col, v);
+                    tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(TMEM_D_COL + buf * N_MMA + grp * 32), v);
                     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    mbar_arrive(&ms.d_empty[buf]);                // values are in registers: the buffer may be overwritten
 #pragma unroll
                     for (int i = 0; i < 32; ++i) {
                         const float4 w = ms.w3[col + i];
@@ -317,8 +339,6 @@ mppi_mlp_rollout_kernel(const __grid_constant__ TickArgs a, const __grid_constan
                         r0 = fmaf(w.y, h, r0); r1 = fmaf(w.z, h, r1); r2 = fmaf(w.w, h, r2);
                     }
                 }
-                d_phase ^= 1;
-                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                 if (!owner) ms.res[grp - 1][row] = make_float4(r0, r1, r2, 0.f);
                 named_bar_sync(1, N_COMPUTE);
                 // (4) owner: Euler step with the learned residual, nearest waypoint, stage cost
@@ -326,29 +346,19 @@ mppi_mlp_rollout_kernel(const __grid_constant__ TickArgs a, const __grid_constan
 #pragma unroll
                     for (int g = 0; g < N_GROUPS - 1; ++g) { const float4 pr = ms.res[g][row]; r0 += pr.x; r1 += pr.y; r2 += pr.z; }
                     r0 += ms.b3[0]; r1 += ms.b3[1]; r2 += ms.b3[2];
-                    float sn, cs;
-                    sincos_cw(z[2], sn, cs);
                     z[0] = fmaf(fmaf(v0, cs, r0), a.dt, z[0]);
                     z[1] = fmaf(fmaf(v0, sn, r1), a.dt, z[1]);
                     z[2] = fmaf(v1 + r2, a.dt, z[2]);
-                    if (a.flags & F_COST_SUM) {                     // cost_mode == sum
-                        const int j = a.window == 20 ? nearest_wp<20>(sm, z[0], z[1]) : nearest_wp<0>(sm, z[0], z[1]);
-                        ref = window_ref(sm, j);
-                        const float2 qq = sm.Q[t];
-                        acc += tracking_cost<MPPI_MODEL_DIFFDRIVE>(ref, z, z[2], a.sw) + (qq.x * v0 + qq.y * v1);
-                    }
                 }
             }
             if (owner && active) {
-                if (a.flags & F_COST_SUM) {
-                    acc += tracking_cost<MPPI_MODEL_DIFFDRIVE>(ref, z, z[2], a.tw);
-                } else {
-                    const int j = a.window == 20 ? nearest_wp<20>(sm, z[0], z[1]) : nearest_wp<0>(sm, z[0], z[1]);
-                    ref = window_ref(sm, j);
-                    const float2 qq = sm.Q[T - 1];
-                    acc = tracking_cost<MPPI_MODEL_DIFFDRIVE>(ref, z, z[2], a.sw) + (qq.x * v0 + qq.y * v1) +
-                          tracking_cost<MPPI_MODEL_DIFFDRIVE>(ref, z, z[2], a.tw);
-                }
+                // cost of the final state: last stage cost (+ terminal); in `last` mode nothing else survives (Q1)
+                const int j = a.window == 20 ? nearest_wp<20>(sm, z[0], z[1]) : nearest_wp<0>(sm, z[0], z[1]);
+                ref = window_ref(sm, j);
+                const float2 qq = sm.Q[T - 1];
+                const float last = tracking_cost<MPPI_MODEL_DIFFDRIVE>(ref, z, z[2], a.sw) + (qq.x * v0 + qq.y * v1) +
+                                   tracking_cost<MPPI_MODEL_DIFFDRIVE>(ref, z, z[2], a.tw);
+                acc = (a.flags & F_COST_SUM) ? acc + last : last;
                 S_out[k] = acc;
             }
         }

@@ -12,7 +12,9 @@
 //   * the remaining 512x512 layer is the GEMM: D[128x512] = A[128x512] (TMEM) x W2^T, issued by ONE
 //     thread as tcgen05.mma.cta_group::1.kind::f16 with the A operand in TMEM (M=128, N=128, K=16), W2
 //     streamed from L2 by TMA (cp.async.bulk.tensor, 128x64 bf16 boxes, 128B swizzle) through a
-//     12-stage mbarrier ring (192 KB in flight hides the L2 latency); the accumulator is produced in
+//     12-stage mbarrier ring (192 KB in flight hides the L2 latency).  CTAs run as clusters of two that
+//     walk the weight stream in lockstep: each CTA issues every other box with .multicast::cluster so
+//     both receive it -- L2 -> SM traffic per SM is halved; the accumulator is produced in
 //     four 128-column quarters through two TMEM buffers (2 x 128 columns), so the epilogue of one
 //     quarter overlaps the MMAs of the next;
 //   * the epilogue warps read the accumulator with tcgen05.ld (32x32b.x32), add b2, apply tanh and
@@ -20,11 +22,13 @@
 //   * the unicycle step, nearest-waypoint search and cost run in the same epilogue threads with the
 //     state in registers across the horizon.
 // Warp roles: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2..17 = 16 compute
-// warps (four per TMEM lane quarter; group g = (warp-2)/4 owns accumulator quarter g, 128 columns).
+// warps (four per TMEM lane quarter; group g = (warp-2)/4 takes 32 columns of every 128-column part of the
+// activations and of every accumulator quarter, so MMA start and epilogue tail are both short).
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cmath>
 #include <vector>
 
@@ -53,7 +57,7 @@ struct MlpSmem {                          // after the 1024-aligned A / B region
     float4 w3[HID];                       // (b2[j], W3[0][j], W3[1][j], W3[2][j])
     float4 xs[TILE_M];                    // current state of each row for the partner thread
     float4 res[N_GROUPS - 1][TILE_M];     // partners' partial output-layer sums
-    unsigned long long b_full[B_STAGES], b_empty[B_STAGES], a_ready, d_full[2], d_empty[2];
+    unsigned long long b_full[B_STAGES], b_empty[B_STAGES], a_ready[N_QUARTERS], d_full[2], d_empty[2];
     unsigned long long key[8];
     uint32_t tmem_base;
     float b3[3];
@@ -85,6 +89,20 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t pari
 __device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, unsigned long long *bar, int c0, int c1) {
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
                  ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+
+__device__ __forceinline__ void tma_load_2d_mc(void *dst, const CUtensorMap *map, unsigned long long *bar, int c0, int c1, uint16_t mask) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
+                 ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(mask) : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
 // UMMA shared-memory descriptor: K-major, SWIZZLE_128B, 8-row x 128-byte atoms 1024 bytes apart
@@ -122,6 +140,11 @@ __device__ __forceinline__ void tmem_st4(uint32_t taddr, uint32_t r0, uint32_t r
 __device__ __forceinline__ void umma_commit(unsigned long long *bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// arrive on the same barrier in every CTA of the cluster mask once the MMAs issued so far retire
+__device__ __forceinline__ void umma_commit_mc(unsigned long long *bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"(mask) : "memory");
+}
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -149,7 +172,7 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
-__global__ void __launch_bounds__(MLP_THREADS, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(MLP_THREADS, 1)
 mppi_mlp_rollout_kernel(const __grid_constant__ TickArgs a, const __grid_constant__ CUtensorMap w2_map,
                         const float4 *__restrict__ g_w01, const float4 *__restrict__ g_w3, const float *__restrict__ g_b3,
                         float *__restrict__ S_out, int n_tiles) {
@@ -161,15 +184,20 @@ mppi_mlp_rollout_kernel(const __grid_constant__ TickArgs a, const __grid_constan
     MlpSmem &ms = *reinterpret_cast<MlpSmem *>(dyn + B_STAGES * B_TILE_BYTES + sizeof(TickSmem));
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int T = a.T;
-    const int my_tiles = (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    // clusters of two CTAs advance in lockstep: cluster c owns tile pairs c, c + n_clusters, ...; both CTAs run
+    // the same number of tile-steps even when the last pair is half empty
+    const uint32_t cta_rank = cluster_ctarank();
+    const int n_clusters = (int)gridDim.x / 2, cluster_id = (int)blockIdx.x / 2;
+    const int n_pairs = (n_tiles + 1) / 2;
+    const int my_tiles = (n_pairs - cluster_id + n_clusters - 1) / n_clusters;
 
     // ---- one-time setup: constants, barriers, TMEM, step-1 index + window (same rule as the tick kernel)
     for (int j = tid; j < HID; j += MLP_THREADS) { ms.w01[j] = g_w01[j]; ms.w3[j] = g_w3[j]; }
     if (tid < 3) ms.b3[tid] = g_b3[tid];
     if (tid < 4) sm.x0[tid] = a.x0[tid];
     if (tid == 0) {
-        for (int s = 0; s < B_STAGES; ++s) { mbar_init(&ms.b_full[s], 1); mbar_init(&ms.b_empty[s], 1); }
-        mbar_init(&ms.a_ready, N_COMPUTE);
+        for (int s = 0; s < B_STAGES; ++s) { mbar_init(&ms.b_full[s], 1); mbar_init(&ms.b_empty[s], 2); }   // empty: both CTAs
+        for (int pa = 0; pa < N_QUARTERS; ++pa) mbar_init(&ms.a_ready[pa], N_COMPUTE);
         for (int bf = 0; bf < 2; ++bf) { mbar_init(&ms.d_full[bf], 1); mbar_init(&ms.d_empty[bf], N_COMPUTE); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -221,6 +249,7 @@ mppi_mlp_rollout_kernel(const __grid_constant__ TickArgs a, const __grid_constan
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    cluster_sync_all();                                   // the peer's barriers exist before anything is multicast
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = ms.tmem_base;
 
@@ -231,9 +260,10 @@ mppi_mlp_rollout_kernel(const __grid_constant__ TickArgs a, const __grid_constan
             int stage = 0; uint32_t phase = 0;
             for (int it = 0; it < total; ++it) {
                 const int kb = it % (HID / KCH), nq = (it / (HID / KCH)) % N_QUARTERS;
-                mbar_wait(&ms.b_empty[stage], phase ^ 1);
-                mbar_expect_tx(&ms.b_full[stage], B_TILE_BYTES);
-                tma_load_2d(smB + stage * B_TILE_BYTES, &w2_map, &ms.b_full[stage], kb * KCH, nq * N_MMA);
+                mbar_wait(&ms.b_empty[stage], phase ^ 1);               // both CTAs are done with this slot
+                mbar_expect_tx(&ms.b_full[stage], B_TILE_BYTES);        // every CTA arms its own barrier ...
+                if ((uint32_t)(it & 1) == cta_rank)                      // ... and issues every other box for both
+                    tma_load_2d_mc(smB + stage * B_TILE_BYTES, &w2_map, &ms.b_full[stage], kb * KCH, nq * N_MMA, (uint16_t)3);
                 if (++stage == B_STAGES) { stage = 0; phase ^= 1; }
             }
         }
@@ -242,14 +272,14 @@ mppi_mlp_rollout_kernel(const __grid_constant__ TickArgs a, const __grid_constan
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0, a_phase = 0, quarter = 0;
             for (int step = 0; step < my_tiles * T; ++step) {
-                mbar_wait(&ms.a_ready, a_phase); a_phase ^= 1;
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 for (int nq = 0; nq < N_QUARTERS; ++nq, ++quarter) {
                     const uint32_t buf = quarter & 1;
                     mbar_wait(&ms.d_empty[buf], ((quarter >> 1) & 1) ^ 1);      // epilogue drained this buffer
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     const uint32_t d_tmem = tmem + TMEM_D_COL + buf * N_MMA;
                     for (int kb = 0; kb < HID / KCH; ++kb) {
+                        // the activations arrive in four 128-column parts; the first quarter's K loop chases them
+                        if (nq == 0 && (kb & 1) == 0) mbar_wait(&ms.a_ready[kb >> 1], a_phase);
                         mbar_wait(&ms.b_full[stage], phase);
                         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                         const uint32_t b_base = smem_u32(smB + stage * B_TILE_BYTES);
@@ -258,11 +288,12 @@ mppi_mlp_rollout_kernel(const __grid_constant__ TickArgs a, const __grid_constan
                             umma_bf16_ts(d_tmem, tmem + TMEM_A_COL + (kb * (KCH / 16) + k) * 8, umma_desc_sw128(b_base + k * 32),
                                          (kb | k) ? 1u : 0u);
                         }
-                        umma_commit(&ms.b_empty[stage]);          // frees the W2 slot when these MMAs retire
+                        umma_commit_mc(&ms.b_empty[stage], (uint16_t)3);   // frees the W2 slot in BOTH CTAs when these MMAs retire
                         if (++stage == B_STAGES) { stage = 0; phase ^= 1; }
                     }
                     umma_commit(&ms.d_full[buf]);                 // this accumulator quarter is complete
                 }
+                a_phase ^= 1;
             }
         }
     } else {
@@ -273,7 +304,7 @@ mppi_mlp_rollout_kernel(const __grid_constant__ TickArgs a, const __grid_constan
         const bool owner = grp == 0;
         uint32_t d_phase[2] = {0, 0};
         for (int tl = 0; tl < my_tiles; ++tl) {
-            const int tile = blockIdx.x + tl * gridDim.x;
+            const int tile = 2 * (cluster_id + tl * n_clusters) + (int)cta_rank;
             const int k = tile * TILE_M + row;
             const bool active = k < a.K;
             const uint32_t kg = (uint32_t)(a.k_offset + k);
@@ -287,22 +318,25 @@ mppi_mlp_rollout_kernel(const __grid_constant__ TickArgs a, const __grid_constan
                 if (owner) ms.xs[row] = make_float4(z[0], z[1], z[2], 0.f);
                 named_bar_sync(1, N_COMPUTE);
                 const float4 st = ms.xs[row];
+#pragma unroll 1
+                for (int part = 0; part < N_QUARTERS; ++part) {      // 128-column parts of A, each signalled on its own
 #pragma unroll 2
-                for (int c8 = 0; c8 < COLS_PER_GROUP / 8; ++c8) {    // 8 columns = one 16-byte chunk of a row
-                    const int col = grp * COLS_PER_GROUP + c8 * 8;
-                    uint32_t pk[4];
+                    for (int c8 = 0; c8 < 4; ++c8) {                 // this group's 32 columns of the part, 8 at a time
+                        const int col = part * N_MMA + grp * 32 + c8 * 8;
+                        uint32_t pk[4];
 #pragma unroll
-                    for (int p = 0; p < 4; ++p) {
-                        const float4 wa = ms.w01[col + 2 * p], wb = ms.w01[col + 2 * p + 1];
-                        const float pa = fmaf(wa.x, st.x, fmaf(wa.y, st.y, fmaf(wa.z, st.z, wa.w)));
-                        const float pb = fmaf(wb.x, st.x, fmaf(wb.y, st.y, fmaf(wb.z, st.z, wb.w)));
-                        pk[p] = tanh_bf16x2(pa, pb);
+                        for (int p = 0; p < 4; ++p) {
+                            const float4 wa = ms.w01[col + 2 * p], wb = ms.w01[col + 2 * p + 1];
+                            const float pa = fmaf(wa.x, st.x, fmaf(wa.y, st.y, fmaf(wa.z, st.z, wa.w)));
+                            const float pb = fmaf(wb.x, st.x, fmaf(wb.y, st.y, fmaf(wb.z, st.z, wb.w)));
+                            pk[p] = tanh_bf16x2(pa, pb);
+                        }
+                        tmem_st4(tmem + ((uint32_t)(q * 32) << 16) + TMEM_A_COL + (uint32_t)(col >> 1), pk[0], pk[1], pk[2], pk[3]);
                     }
-                    tmem_st4(tmem + ((uint32_t)(q * 32) << 16) + TMEM_A_COL + (uint32_t)(col >> 1), pk[0], pk[1], pk[2], pk[3]);
+                    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    mbar_arrive(&ms.a_ready[part]);
                 }
-                asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                mbar_arrive(&ms.a_ready);
                 // (2) owner overlaps with the GEMM: stage cost of the state reached by the previous step, then the
                 //     noise and clamped control of this step
                 if (owner) {
@@ -365,6 +399,7 @@ mppi_mlp_rollout_kernel(const __grid_constant__ TickArgs a, const __grid_constan
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    cluster_sync_all();                                   // no CTA leaves while its peer may still signal its barriers
     if (warp == 1) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
     }
@@ -454,7 +489,7 @@ int mlp_rollout_costs(MlpState *m, const TickArgs &args, bool sum, const float *
     a.eps = d_eps;
     a.flags = sum ? F_COST_SUM : 0;
     const int n_tiles = (a.K + TILE_M - 1) / TILE_M;
-    const int grid = n_tiles < m->n_sm ? n_tiles : m->n_sm;
+    int grid = std::min(((n_tiles + 1) / 2) * 2, m->n_sm & ~1);       // whole clusters of 2
     mppi_mlp_rollout_kernel<<<grid, MLP_THREADS, MLP_DYN_SMEM, st>>>(a, m->w2_map, m->d_w01, m->d_w3, m->d_b3, d_S, n_tiles);
     return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }

@@ -298,6 +298,36 @@ def run_b200_arm(args):
         extras["batched_R4096_K1024_H30"] = {"ms_per_tick": a.elapsed_time(b) / 10,
                                              "sample_steps_per_sec": R * 1024 * 30 / (a.elapsed_time(b) / 10 * 1e-3)}
         bm.engine.close()
+        # config[2]: diff-drive + simple_mlp residual (random-init weights), K=65536, H=30, tcgen05 MLP rollout
+        rngw = np.random.default_rng(0)
+        mlp = {}
+        for i, (o, n) in enumerate([(512, 3), (512, 512), (512, 512), (3, 512)]):
+            bnd = 1.0 / np.sqrt(n)
+            sc = 0.01 if i == 3 else 1.0
+            mlp["W%d" % i] = (rngw.uniform(-bnd, bnd, (o, n)) * sc).astype(np.float32)
+            mlp["b%d" % i] = (rngw.uniform(-bnd, bnd, (o,)) * sc).astype(np.float32)
+        cm = MPPIAlgorithms(**diffdrive_kwargs(65536, 30, 2.0), seed=7, dynamics=mlp)
+        cm.engine.set_stream(stream.cuda_stream)
+        for i in range(3):
+            cm.engine.step_async(x0, None, 7, i)
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(stream):
+            a.record(stream)
+            for i in range(10):
+                cm.engine.step_async(x0, None, 7, 10 + i)
+            b.record(stream)
+        torch.cuda.synchronize()
+        ms_mlp = a.elapsed_time(b) / 10
+        pk = measured_peaks() or {}
+        extras["mlp_K65536_H30"] = {
+            "ms_per_tick": ms_mlp, "sample_steps_per_sec": 65536 * 30 / (ms_mlp * 1e-3),
+            "algorithmic_TFLOPs": 65536 * 30 * 1054720 / (ms_mlp * 1e-3) / 1e12,
+            "executed_gemm_TFLOPs": 65536 * 30 * 2 * 512 * 512 / (ms_mlp * 1e-3) / 1e12,
+            "tensor_peak_TFLOPs": pk.get("bf16_tflops", 1590.0), "tensor_peak_kind": "measured burst" if pk else "fallback",
+            "frac_of_tensor_peak_executed": 65536 * 30 * 2 * 512 * 512 / (ms_mlp * 1e-3) / 1e12 / pk.get("bf16_tflops", 1590.0),
+            "note": "Linear(3,512) has no activation and is folded into the first hidden layer on the host, so one 512x512 GEMM is executed per step"}
+        cm.engine.close()
 
     # ---- roofline of the dominant kernel (mppi_tick_kernel): FP32 issue-bound, not HBM-bound
     peaks = measured_peaks()
@@ -313,8 +343,8 @@ def run_b200_arm(args):
         "peak_source": "derived 148 SM x 128 lanes x 2 x clocks.max.sm (FP32 peak is not in MEASURED_PEAKS.json)",
         "algorithmic_flop_per_sample_step": FLOP_PER_SAMPLE_STEP,
         "sm_mhz_during_run": f_mhz,
-        "issue_view": {"warp_instr_per_warp_sample_step": 228, "source": "ncu smsp__inst_executed / (K*H/32), profiles/",
-                       "achieved_frac_of_issue_peak": (K_PER_GPU * T_H / 32 * 228) / (kern_ms * 1e-3) / (SM_COUNT * 4 * f_mhz * 1e6)},
+        "issue_view": {"warp_instr_per_warp_sample_step": 211, "source": "ncu smsp__inst_executed / (K*H/32), profiles/",
+                       "achieved_frac_of_issue_peak": (K_PER_GPU * T_H / 32 * 211) / (kern_ms * 1e-3) / (SM_COUNT * 4 * f_mhz * 1e6)},
         "hbm_view": {"algorithmic_bytes_per_launch": hbm_bytes,
                      "achieved_GBps": hbm_bytes / (kern_ms * 1e-3) / 1e9,
                      "peak_GBps": (peaks or {}).get("hbm_gbs", 6650.0),

@@ -100,12 +100,14 @@ def measured_peaks():
 # ------------------------------------------------------------------------------------------------
 # CPU arm: the oracle restatement of the reference tick on the host cores
 # ------------------------------------------------------------------------------------------------
-def cpu_port_run(ticks, K, T, temperature, nthreads=0):
+def cpu_port_run(ticks, K, T, temperature, nthreads=None):
     """C restatement (oracle/mppi_oracle.c), Philox noise, all host threads: sample-steps/s."""
     from oracle import c_oracle as co
     from oracle import mppi_oracle as orc
     sp = orc.diffdrive_spec(K=K, T=T, param_exploration=0.05, cost_mode="sum", waypoint_mode="frozen")
     sp.temperature = temperature
+    if nthreads is None:
+        nthreads = os.cpu_count() or 1        # torchrun exports OMP_NUM_THREADS=1: ask for every host core explicitly
     path = spline_path()
     U = np.zeros((T, 2))
     idx = 0
@@ -116,7 +118,7 @@ def cpu_port_run(ticks, K, T, temperature, nthreads=0):
         o = co.tick(sp, path, U, idx, x0, eps=None, seed=1, tick=i, nthreads=nthreads)
         times.append(time.perf_counter() - t0)
         U, idx = o["U_after"], o["idx_after"]
-    return times, co.max_threads()
+    return times, nthreads
 
 
 def cpu_python_loops_rate(K=64, T=50):

@@ -57,7 +57,7 @@ struct mppi_handle_s {
     // device buffers
     float4 *d_path = nullptr;
     float *d_U = nullptr, *d_M = nullptr, *d_S = nullptr, *d_part = nullptr, *d_out = nullptr;
-    float *d_x0 = nullptr;
+    float *d_x0 = nullptr, *d_opt = nullptr;
     int *d_idx = nullptr, *d_NC = nullptr;
     unsigned *d_ticket = nullptr;
     float *h_out = nullptr, *h_out_dev = nullptr;     // mapped pinned record of robot 0
@@ -255,7 +255,7 @@ int mppi_create(const mppi_config_t *cfg, mppi_handle_t *out) {
 
     TickArgs &a = h->args;
     std::memset(&a, 0, sizeof(a));
-    a.K = K; a.T = T; a.window = c.window; a.yaw_wrap = c.yaw_wrap;
+    a.K = K; a.T = T; a.window = c.window; a.yaw_wrap = c.yaw_wrap; a.clamp_nominal = c.clamp_nominal;
     a.k_offset = c.k_offset;
     {   // Q6: number of global sample indices k with k < (1.0 - param_exploration) * K, in doubles
         const double thr = (1.0 - c.param_exploration) * (double)c.K_global;
@@ -293,7 +293,7 @@ int mppi_destroy(mppi_handle_t h) {
     if (h->mlp) mlp_destroy(h->mlp);
     cudaFree(h->d_path); cudaFree(h->d_U); cudaFree(h->d_M); cudaFree(h->d_S); cudaFree(h->d_part);
     cudaFree(h->d_out); cudaFree(h->d_idx); cudaFree(h->d_NC); cudaFree(h->d_ticket); cudaFree(h->d_first);
-    cudaFree(h->d_bp_n); cudaFree(h->d_bp_s); cudaFree(h->d_send); cudaFree(h->d_recv); cudaFree(h->d_x0);
+    cudaFree(h->d_bp_n); cudaFree(h->d_bp_s); cudaFree(h->d_send); cudaFree(h->d_recv); cudaFree(h->d_x0); cudaFree(h->d_opt);
     if (h->h_out) cudaFreeHost(h->h_out);
     if (h->h_first) cudaFreeHost(h->h_first);
     for (auto &e : h->ev) if (e) cudaEventDestroy(e);
@@ -615,6 +615,24 @@ int mppi_generate_noise_robot(mppi_handle_t h, uint64_t seed, uint64_t tick, int
     set_seed(h, seed, tick);
     CK(h, mppi_launch_noise(h->args, d_eps_out, robot, h->stream));
     h->tm.launches++;
+    CK(h, cudaStreamSynchronize(h->stream));
+    return MPPI_OK;
+}
+
+int mppi_get_trajectories(mppi_handle_t h, const double *x0, const float *d_eps, uint64_t seed, uint64_t tick,
+                          float *optimal_out, float *d_sampled_out) {
+    if (!h || !x0) return MPPI_E_BADARG;
+    if (h->cfg.n_robots != 1 || h->mlp) return fail(h, MPPI_E_UNSUPPORTED, "trajectories: single-robot analytic models only");
+    CK(h, cudaSetDevice(h->cfg.device));
+    set_x0(h, x0);
+    set_seed(h, seed, tick);
+    TickArgs a = h->args;
+    a.eps = d_eps;
+    const int nx = h->nx, T = h->cfg.T;
+    if (optimal_out && !h->d_opt) CK(h, cudaMalloc(&h->d_opt, sizeof(float) * MPPI_MAX_T * 4));
+    CK(h, mppi_launch_traj(a, h->cfg.model, h->d_out, optimal_out ? h->d_opt : nullptr, d_sampled_out, h->stream));
+    h->tm.launches++;
+    if (optimal_out) CK(h, cudaMemcpyAsync(optimal_out, h->d_opt, sizeof(float) * T * nx, cudaMemcpyDeviceToHost, h->stream));
     CK(h, cudaStreamSynchronize(h->stream));
     return MPPI_OK;
 }

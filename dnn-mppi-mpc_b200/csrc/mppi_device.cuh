@@ -17,7 +17,9 @@
 #define MPPI_PENALTY 1.0e10f           // mppi_race_car_obstacle.py:157
 #define MPPI_SENTINEL 1.0e18f          // padded window entries: distance^2 = 1e36, never the minimum
 #define MPPI_OUT_HDR 8
-#define MPPI_OUT_STRIDE (MPPI_OUT_HDR + 4 * MPPI_MAX_T)
+#define MPPI_OUT_STRIDE (MPPI_OUT_HDR + 8 * MPPI_MAX_T)   // header, U shifted, w_eps, U pre-shift, U before the tick
+#define MPPI_OUT_UPRE (MPPI_OUT_HDR + 4 * MPPI_MAX_T)
+#define MPPI_OUT_UOLD (MPPI_OUT_HDR + 6 * MPPI_MAX_T)
 #define MPPI_NF(T) (4 + 2 * (T))       // floats per partial: ncoll_min, smooth_min, eta, sum w^2, N[T][2]
 
 enum : int {
@@ -34,7 +36,7 @@ enum : int {
 // Everything a tick needs, passed by value (kernel parameter = constant bank).
 struct TickArgs {
     // static configuration
-    int K, T, window, n_path, n_obs, yaw_wrap, use_gamma;
+    int K, T, window, n_path, n_obs, yaw_wrap, use_gamma, clamp_nominal;
     int k_offset, n_exploit;          // global sample index of local sample 0; Q6 threshold on the global index
     float dt, dt_over_L, umax0, umax1;
     float sw[4], tw[4];

@@ -88,7 +88,11 @@ __device__ void finalize_tick(const TickArgs &a, int robot, int idx_new, MergeSm
         const float *Mrow = a.M + (size_t)n * T;
         float f = 0.f;
         for (int m = 0; m < T; ++m) f += Mrow[m] * ms.weps[2 * m + u];
-        ms.upre[c] = U[c] + f;                          // u += w_epsilon (:141)
+        float up = U[c] + f;                            // u += w_epsilon (:141)
+        if (a.clamp_nominal) up = clampf(up, u ? a.umax1 : a.umax0);     // Q9: the visualisation replay clamps u in place
+        ms.upre[c] = up;
+        out[MPPI_OUT_UPRE + c] = up;                    // kept for mppi_get_trajectories
+        out[MPPI_OUT_UOLD + c] = U[c];
     }
     __syncthreads();
     float *oh = (robot == 0) ? a.out_host : nullptr;
@@ -366,6 +370,48 @@ __global__ void __launch_bounds__(MPPI_BLOCK) mppi_merge_kernel(const __grid_con
     finalize_tick(a, 0, __float_as_int(a.out[2]), ms);
 }
 
+// A16: visualisation replays of the last tick.  Thread k < K replays sample k's clamped controls, thread K the
+// updated nominal; both index the controls with t-1 (the last row first), as the reference does.
+template <int MODEL>
+__global__ void mppi_traj_kernel(const __grid_constant__ TickArgs a, const float *__restrict__ rec,
+                                 float *__restrict__ opt_out, float *__restrict__ samp_out) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k > a.K) return;
+    const bool nominal = k == a.K;
+    if (nominal ? opt_out == nullptr : samp_out == nullptr) return;
+    constexpr int NX = MODEL == MPPI_MODEL_BICYCLE ? 4 : 3;
+    const int T = a.T;
+    const float *upre = rec + MPPI_OUT_UPRE, *uold = rec + MPPI_OUT_UOLD;
+    const uint32_t kg = (uint32_t)(a.k_offset + k);
+    const bool exploit = (int)kg < a.n_exploit;
+    float z[4] = {a.x0[0], a.x0[1], a.x0[2], a.x0[3]};
+    float *dst = nominal ? opt_out : samp_out + (size_t)k * T * NX;
+    for (int t = 0; t < T; ++t) {
+        const int tc = (t + T - 1) % T;                                   // u[t-1] with Python's negative index
+        float v0, v1;
+        if (nominal) {
+            v0 = clampf(upre[2 * tc], a.umax0); v1 = clampf(upre[2 * tc + 1], a.umax1);
+        } else {
+            float e0, e1;
+            if (a.eps) {
+                const float2 ee = reinterpret_cast<const float2 *>(a.eps)[(size_t)k * T + tc];
+                e0 = ee.x; e1 = ee.y;
+            } else {
+                float e[4];
+                philox_eps_pair(a, kg, (uint32_t)(tc >> 1), 0u, e);
+                e0 = e[2 * (tc & 1)]; e1 = e[2 * (tc & 1) + 1];
+            }
+            v0 = clampf(exploit ? __fadd_rn(uold[2 * tc], e0) : e0, a.umax0);
+            v1 = clampf(exploit ? __fadd_rn(uold[2 * tc + 1], e1) : e1, a.umax1);
+        }
+        float sn, cs;
+        sincos_cw(z[2], sn, cs);
+        dyn_step<MODEL>(a, z, v0, v1, cs, sn);
+#pragma unroll
+        for (int i = 0; i < NX; ++i) dst[t * NX + i] = z[i];
+    }
+}
+
 // (K,T,2) export of the Philox noise the tick kernel consumes
 __global__ void mppi_noise_kernel(const __grid_constant__ TickArgs a, float *out, int robot) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
@@ -537,6 +583,13 @@ cudaError_t mppi_launch_strict(const TickArgs &a, int model, int coll, bool sum,
 
 cudaError_t mppi_launch_merge(const TickArgs &a, const float *triples, int G, cudaStream_t st) {
     mppi_merge_kernel<<<1, MPPI_BLOCK, 0, st>>>(a, triples, G);
+    return cudaGetLastError();
+}
+
+cudaError_t mppi_launch_traj(const TickArgs &a, int model, const float *rec, float *d_opt, float *d_samp, cudaStream_t st) {
+    const int n = a.K + 1;
+    if (model == MPPI_MODEL_BICYCLE) mppi_traj_kernel<MPPI_MODEL_BICYCLE><<<(n + 127) / 128, 128, 0, st>>>(a, rec, d_opt, d_samp);
+    else mppi_traj_kernel<MPPI_MODEL_DIFFDRIVE><<<(n + 127) / 128, 128, 0, st>>>(a, rec, d_opt, d_samp);
     return cudaGetLastError();
 }
 

@@ -8,5 +8,6 @@ cudaError_t mppi_launch_strict(const TickArgs &a, int model, int coll, bool sum,
                                const int *bp_s, int nbp, int k_first, unsigned check_from,
                                unsigned long long *first_change, cudaStream_t st);
 cudaError_t mppi_launch_merge(const TickArgs &a, const float *triples, int G, cudaStream_t st);
+cudaError_t mppi_launch_traj(const TickArgs &a, int model, const float *rec, float *d_opt, float *d_samp, cudaStream_t st);
 cudaError_t mppi_launch_noise(const TickArgs &a, float *d_out, int robot, cudaStream_t st);
 int mppi_tick_occupancy(int model, int coll, bool sum, bool inj, int window, int T, bool stash);

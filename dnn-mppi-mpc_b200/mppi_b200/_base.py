@@ -80,12 +80,28 @@ class ControllerBase:
         self._u_cache = useq.astype(self._out_dtype)           # returned u aliases u_prev (A2)
         u = self._u_cache
         optimal_traj = np.zeros((self.T, self.dim_x), dtype=self._out_dtype)
-        # (K,T,nx) zeros like the reference returns when the flag is off, without allocating K*T*nx
-        sampled = np.broadcast_to(np.zeros((), dtype=self._out_dtype), (self.K, self.T, self.dim_x))
-        if (self.visualize_optimal_traj or self.visualze_sampled_trajs) and not self._viz_warned:
-            warnings.warn("visualisation trajectories are not produced by this build (zeros returned)")
-            self._viz_warned = True
+        want_opt, want_samp = self._viz_gates()
+        if (want_opt or want_samp) and self._world == 1 and self._engine.model != "diffdrive_mlp":
+            import torch
+            d_samp = torch.empty(self.K, self.T, self.dim_x, dtype=torch.float32,
+                                 device="cuda:%d" % self._engine.device) if want_samp else None
+            opt = self._engine.trajectories(x, d_samp, want_opt, d_eps, self.seed, self._tick - 1)
+            if want_opt:
+                optimal_traj = opt.astype(self._out_dtype)
+            sampled = d_samp.cpu().numpy().astype(self._out_dtype) if want_samp else \
+                np.broadcast_to(np.zeros((), dtype=self._out_dtype), (self.K, self.T, self.dim_x))
+        else:
+            # (K,T,nx) zeros like the reference returns when the flag is off, without allocating K*T*nx
+            sampled = np.broadcast_to(np.zeros((), dtype=self._out_dtype), (self.K, self.T, self.dim_x))
+            if (want_opt or want_samp) and not self._viz_warned:
+                warnings.warn("visualisation trajectories are not produced for sharded / learned-dynamics controllers")
+                self._viz_warned = True
         return u[0], u, optimal_traj, sampled
+
+    def _viz_gates(self):
+        """(replay the nominal?, replay the samples?) -- the diff-drive class gates both on visualze_sampled_trajs
+        (mppi_differential_drive.py:145,154), the race-car class uses one flag each (:112,:121)."""
+        return bool(self.visualze_sampled_trajs), bool(self.visualze_sampled_trajs)
 
     def comm_init_from_torch(self):
         """Sample sharding over torch.distributed ranks: rank 0 creates the NCCL id, broadcast, init."""

@@ -18,7 +18,7 @@ MAX_T, MAX_WINDOW, MAX_OBSTACLES = 128, 256, 16
 class MppiConfig(C.Structure):
     _fields_ = [(n, C.c_int32) for n in (
         "abi_version", "device", "model", "K", "T", "n_robots", "window", "cost_mode",
-        "waypoint_mode", "filter_kind", "yaw_wrap", "collision", "K_global", "k_offset")] + [
+        "waypoint_mode", "filter_kind", "yaw_wrap", "collision", "K_global", "k_offset", "clamp_nominal", "reserved0")] + [
         ("dt", C.c_double), ("wheel_base", C.c_double), ("u_max", C.c_double * 2),
         ("param_exploration", C.c_double), ("param_lambda", C.c_double), ("param_alpha", C.c_double),
         ("temperature", C.c_double), ("sigma", C.c_double * 4), ("stage_w", C.c_double * 4),
@@ -64,6 +64,7 @@ SYMBOLS = {
     "mppi_reduce_update": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, _PF, _PF, _PF]),
     "mppi_generate_noise": (C.c_int, [_H, C.c_uint64, C.c_uint64, C.c_void_p]),
     "mppi_generate_noise_robot": (C.c_int, [_H, C.c_uint64, C.c_uint64, C.c_int32, C.c_void_p]),
+    "mppi_get_trajectories": (C.c_int, [_H, _PD, C.c_void_p, C.c_uint64, C.c_uint64, _PF, C.c_void_p]),
     "mppi_get_stats": (C.c_int, [_H, C.POINTER(MppiStats)]),
     "mppi_step_batched": (C.c_int, [_H, C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p]),
     "mppi_comm_get_unique_id": (C.c_int, [C.c_void_p]),

@@ -21,7 +21,7 @@ class MPPIEngine:
                  param_lambda, param_alpha, temperature, window, cost_mode, waypoint_mode,
                  filter_kind, yaw_wrap, collision="none", obstacles=None, margin=1.0,
                  wheel_base=2.5, robot_radius=0.5, vehicle_l=4.0, vehicle_w=3.0, n_robots=1,
-                 device=0, K_global=None, k_offset=0):
+                 device=0, K_global=None, k_offset=0, clamp_nominal=False):
         self.lib = _lib.load()
         c = _lib.MppiConfig()
         self.lib.mppi_default_config(C.byref(c))
@@ -35,6 +35,7 @@ class MPPIEngine:
         c.collision = _lib.COLLISION[collision]
         c.K_global = int(K_global) if K_global else int(K)
         c.k_offset = int(k_offset)
+        c.clamp_nominal = int(bool(clamp_nominal))
         c.dt, c.wheel_base = float(dt), float(wheel_base)
         c.u_max[:] = [float(u_max[0]), float(u_max[1])]
         c.param_exploration, c.param_lambda, c.param_alpha = float(param_exploration), float(param_lambda), float(param_alpha)
@@ -143,6 +144,16 @@ class MPPIEngine:
         self._ck(self.lib.mppi_reduce_update(self._h, _dptr(d_S), _dptr(d_eps), seed, tick, self._u0, self._useq,
                                              w_eps.ctypes.data_as(_lib._PF)), "mppi_reduce_update")
         return self._u0_np.copy(), self._useq_np.copy(), w_eps
+
+    def trajectories(self, x0, d_sampled=None, want_optimal=True, d_eps=None, seed=0, tick=0):
+        """Visualisation replays of the tick just stepped (same x0 / noise source).  Returns the (T,nx) optimal
+        trajectory (float32) or None; `d_sampled` (K,T,nx) CUDA tensor is filled when given."""
+        self._load_x0(x0)
+        opt = np.zeros((self.T, self.nx), dtype=np.float32) if want_optimal else None
+        self._ck(self.lib.mppi_get_trajectories(self._h, self._x0, _dptr(d_eps), seed, tick,
+                                                opt.ctypes.data_as(_lib._PF) if want_optimal else None, _dptr(d_sampled)),
+                 "mppi_get_trajectories")
+        return opt
 
     def generate_noise(self, d_out, seed=0, tick=0, robot=0):
         self._ck(self.lib.mppi_generate_noise_robot(self._h, seed, tick, robot, _dptr(d_out)), "mppi_generate_noise")

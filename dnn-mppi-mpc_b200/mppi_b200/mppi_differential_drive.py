@@ -43,7 +43,8 @@ class MPPIAlgorithms(ControllerBase):
             temperature=param_exploration if temperature is None else temperature,   # Q2 (:175,:178)
             window=20,                                                            # :204
             cost_mode=cost_mode, waypoint_mode=waypoint_mode, filter_kind="diffdrive",
-            yaw_wrap=False, collision=self._collision, obstacles=_obstacles, margin=_margin)
+            yaw_wrap=False, collision=self._collision, obstacles=_obstacles, margin=_margin,
+            clamp_nominal=bool(visualze_sampled_trajs))                           # Q9 (:145-148)
 
         if dynamics is not None:
             self.set_dynamics(dynamics)

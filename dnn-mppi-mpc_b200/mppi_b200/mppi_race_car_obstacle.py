@@ -51,9 +51,13 @@ class MPPIRacecarController(ControllerBase):
             cost_mode="sum", waypoint_mode="frozen", filter_kind="racecar", yaw_wrap=True,
             collision="footprint" if self._with_obstacles else "none",
             obstacles=self._obstacle_circles, margin=collision_safety_margin_rat,
-            wheel_base=wheel_base, vehicle_l=self.vehicle_l, vehicle_w=self.vehicle_w)
+            wheel_base=wheel_base, vehicle_l=self.vehicle_l, vehicle_w=self.vehicle_w,
+            clamp_nominal=bool(visualize_optimal_traj))                           # Q9 (:112-115)
 
     prev_waypoints_idx = property(ControllerBase._get_idx, ControllerBase._set_idx)
+
+    def _viz_gates(self):
+        return bool(self.visualize_optimal_traj), bool(self.visualze_sampled_trajs)
 
     @property
     def obstacle_circles(self):

@@ -76,6 +76,9 @@ typedef struct {
     int32_t collision;        /* enum mppi_collision */
     int32_t K_global;         /* total samples over all ranks (== K when not sharded) */
     int32_t k_offset;         /* global index of this handle's first sample */
+    int32_t clamp_nominal;    /* 1: clamp the updated nominal in place before the shift -- the side effect of the
+                                 visualisation replay (quirk Q9: mppi_differential_drive.py:145-148, race-car :112-115) */
+    int32_t reserved0;
     double dt;                /* delta_t */
     double wheel_base;
     double u_max[2];          /* (max_speed, max_omega) or (max_steer_abs, max_accel_abs) */
@@ -157,6 +160,12 @@ int mppi_generate_noise(mppi_handle_t h, uint64_t seed, uint64_t tick, float *d_
 /* Same for robot `robot` of a batched handle (its Philox stream is keyed by the robot index). */
 int mppi_generate_noise_robot(mppi_handle_t h, uint64_t seed, uint64_t tick, int32_t robot, float *d_eps_out);
 int mppi_get_stats(mppi_handle_t h, mppi_stats_t *out);   /* robot 0 */
+/* Visualisation outputs of the LAST tick (A16: mppi_differential_drive.py:144-159, mppi_race_car_obstacle.py:111-125):
+ * the replay of the updated (pre-shift) nominal and of every sample's clamped controls, both with the reference's
+ * `t-1` indexing.  Call right after mppi_step with the same x0 / d_eps / seed / tick.
+ *   optimal_out  host, T*nx floats, or NULL;   d_sampled_out  device, K*T*nx floats, or NULL */
+int mppi_get_trajectories(mppi_handle_t h, const double *x0, const float *d_eps, uint64_t seed, uint64_t tick,
+                          float *optimal_out, float *d_sampled_out);
 
 /* Batched multi-robot tick: n_robots independent controllers in one launch (no reference
  * equivalent; R copies of the loop at mppi_differential_drive.py:111-141).

@@ -28,7 +28,7 @@ def draw_eps(rng, sigma, K, T):
     return rng.multivariate_normal(np.zeros(2), sigma, (K, T)).astype(np.float32)
 
 
-def run_ticks(ctrl, idx_attr, states, eps_list, plant=None):
+def run_ticks(ctrl, idx_attr, states, eps_list, plant=None, keep_sampled=False):
     """Steps `ctrl` through len(eps_list) ticks.  `states` is a list of observed states, or
     a single initial state when `plant` (closed loop) is given."""
     cap = ref_loader.instrument(ctrl, [e.astype(ctrl.u_prev.dtype) for e in eps_list])
@@ -42,18 +42,23 @@ def run_ticks(ctrl, idx_attr, states, eps_list, plant=None):
         rec["idx0"].append(int(getattr(ctrl, idx_attr)))
         with ref_loader.quiet():
             step = ctrl._calc_input_control if hasattr(ctrl, "_calc_input_control") else ctrl._calc_control_input
-            u0, useq, _, _ = step(x)
+            u0, useq, out_traj, out_samp = step(x)
         for k in ("S", "w", "w_eps", "w_eps_filt"):
             rec[k].append(cap[k])
         rec["U_after"].append(np.array(ctrl.u_prev, copy=True))
         rec["u0"].append(np.array(u0, copy=True))
+        rec.setdefault("optimal_traj", []).append(np.array(out_traj, copy=True))
+        if keep_sampled:
+            rec.setdefault("sampled_traj", []).append(np.array(out_samp, copy=True))
         rec["idx_after"].append(int(getattr(ctrl, idx_attr)))
         if plant is not None:
             x = plant(x, np.array(u0, dtype=float))
     return {k: np.array(v) for k, v in rec.items()}
 
 
+
 def save(name, meta, path, eps_list, rec, obstacles=None):
+    rec = {k: np.array(v) if isinstance(v, list) else v for k, v in rec.items()}
     meta = dict(meta, numpy=np.__version__, generator="tests/golden/make_golden.py",
                 source="unmodified reference classes executed in the build container")
     out = dict(meta=json.dumps(meta), path=path, eps=np.array(eps_list, dtype=np.float32), **rec)
@@ -139,6 +144,30 @@ def main():
                     number_of_samples_K=K, param_alpha=alpha)
         save("racecar_" + tag, meta, lp.astype(np.float32), eps_list, rec,
              obstacles=ctrl.obstacle_circles if nobs else None)
+
+    # ---- visualisation outputs on (A16) incl. the in-place clamp of the nominal (Q9); large sigma so clamping bites
+    K, T = 48, 12
+    sig_big = np.array([[4.0, 0.0], [0.0, 2.0]])
+    kw = dict(delta_t=0.1, max_speed=1.0, max_omega=0.8, num_samples_K=K, num_horizons_T=T,
+              param_exploration=0.05, param_lambda=1.0, param_alpha=0.2)
+    ctrl = ref["MPPIAlgorithms"](ref_path=path, sigma=sig_big, stage_cost_weight=w_dd, terminal_cost_weight=w_dd,
+                                 visualize_optimal_traj=True, visualze_sampled_trajs=True, **kw)
+    rng = np.random.default_rng(7)
+    eps_list = [draw_eps(rng, sig_big, K, T) for _ in range(3)]
+    rec = run_ticks(ctrl, "prev_way_point_idx", [[0, 0, 0]], eps_list, plant=plant_dd(0.1), keep_sampled=True)
+    save("diffdrive_viz", dict(kind="diffdrive", viz=True, sigma=sig_big.tolist(), **kw), path, eps_list, rec)
+    K, T = 48, 12
+    ctrl = ref["MPPIRacecarController"](horizon_step_T=T, number_of_samples_K=K, max_steer_abs=0.1, max_accel_abs=0.5,
+                                        param_lambda=5.0, visualize_optimal_traj=True, visualze_sampled_trajs=True)
+    ctrl.ref_path = lemniscate_path()
+    rng = np.random.default_rng(8)
+    eps_list = [draw_eps(rng, sigma_rc, K, T) for _ in range(3)]
+    lp = lemniscate_path()
+    states = [np.asarray(lp[i] + np.array([0.0, 0.0, 0.0, 0.0]), dtype=np.float32) for i in (20, 21, 22)]
+    rec = run_ticks(ctrl, "prev_waypoints_idx", states, eps_list, keep_sampled=True)
+    save("racecar_viz", dict(kind="racecar", viz=True, horizon_step_T=T, number_of_samples_K=K, param_alpha=1.0,
+                             max_steer_abs=0.1, max_accel_abs=0.5, param_lambda=5.0), lp, eps_list, rec,
+         obstacles=ctrl.obstacle_circles)
 
     # ---- literal filter operators as matrices (Q7)
     Ms = {}

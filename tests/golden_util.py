@@ -11,6 +11,7 @@ GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 DIFFDRIVE_CASES = ["diffdrive_pe1e-4", "diffdrive_pe0.05", "diffdrive_closed_loop", "diffdrive_obs"]
 RACECAR_CASES = ["racecar_default", "racecar_alpha0.9", "racecar_noobs"]
+VIZ_CASES = ["diffdrive_viz", "racecar_viz"]
 ALL_CASES = DIFFDRIVE_CASES + RACECAR_CASES
 
 
@@ -23,7 +24,7 @@ class Golden:
         self.eps = z["eps"]                       # (ticks, K, T, 2) float32
         self.obstacles = z["obstacles"] if "obstacles" in z.files else None
         self.rec = {k: z[k] for k in ("x0", "U0", "idx0", "S", "w", "w_eps", "w_eps_filt",
-                                      "U_after", "u0", "idx_after")}
+                                      "U_after", "u0", "idx_after", "optimal_traj", "sampled_traj") if k in z.files}
         self.n_ticks = self.eps.shape[0]
 
     def spec(self, **override):
@@ -33,13 +34,17 @@ class Golden:
                 K=m["num_samples_K"], T=m["num_horizons_T"], dt=m["delta_t"],
                 max_speed=m["max_speed"], max_omega=m["max_omega"],
                 param_exploration=m["param_exploration"], param_lambda=m["param_lambda"],
-                param_alpha=m["param_alpha"],
+                param_alpha=m["param_alpha"], sigma=m.get("sigma"),
                 stage_w=(10 * np.array([5.0, 6.0, 9.0]) if m["kind"] == "diffdrive_obs" else None),
                 term_w=(10 * np.array([5.0, 6.0, 9.0]) if m["kind"] == "diffdrive_obs" else None),
                 obstacles=self.obstacles, margin=m.get("safety_margin_rate", 1.0))
         else:
             s = orc.racecar_spec(K=m["number_of_samples_K"], T=m["horizon_step_T"],
-                                 param_alpha=m["param_alpha"], obstacles=self.obstacles)
+                                 param_alpha=m["param_alpha"], obstacles=self.obstacles,
+                                 max_steer=m.get("max_steer_abs", 0.523), max_accel=m.get("max_accel_abs", 2.0),
+                                 param_lambda=m.get("param_lambda", 50.0))
+        if m.get("viz"):
+            s.viz_optimal = s.viz_sampled = True
         for k, v in override.items():
             setattr(s, k, v)
         return s

@@ -30,8 +30,8 @@ def test_header_symbols_are_exported_and_bound():
 
 def test_config_struct_layout_matches_header():
     from mppi_b200 import _lib
-    # 14 int32 + 24 doubles, naturally aligned
-    assert C.sizeof(_lib.MppiConfig) == 14 * 4 + 24 * 8
+    # 16 int32 + 24 doubles, naturally aligned
+    assert C.sizeof(_lib.MppiConfig) == 16 * 4 + 24 * 8
     c = _lib.MppiConfig()
     _lib.load().mppi_default_config(C.byref(c))
     assert (c.abi_version, c.K, c.T, c.window, c.n_robots) == (1, 1000, 30, 20, 1)

@@ -265,3 +265,36 @@ def test_drop_in_classes_mirror_the_reference_interface():
     # Philox path runs without injected noise and moves the nominal
     u0, u, _, _ = rc._calc_control_input(g2.rec["x0"][2])
     assert np.all(np.isfinite(u))
+
+
+@pytest.mark.parametrize("name", ["diffdrive_viz", "racecar_viz"])
+def test_visualisation_outputs_match_reference(name):
+    """A16 / Q9 through the drop-in classes with the reference's DEFAULT flags (both True): optimal and sampled
+    trajectories (t-1 indexing) and the in-place clamp of the stored nominal."""
+    from mppi_b200.mppi_differential_drive import MPPIAlgorithms
+    from mppi_b200.mppi_race_car_obstacle import MPPIRacecarController
+    g = Golden(name)
+    m = g.meta
+    if name == "diffdrive_viz":
+        ctrl = MPPIAlgorithms(delta_t=m["delta_t"], ref_path=g.path, max_speed=m["max_speed"], max_omega=m["max_omega"],
+                              num_samples_K=m["num_samples_K"], num_horizons_T=m["num_horizons_T"],
+                              param_exploration=m["param_exploration"], param_lambda=m["param_lambda"],
+                              param_alpha=m["param_alpha"], sigma=np.array(m["sigma"]),
+                              stage_cost_weight=np.array([5.0, 5.0, 10.0]), terminal_cost_weight=np.array([5.0, 5.0, 10.0]))
+        step = ctrl._calc_input_control
+    else:
+        ctrl = MPPIRacecarController(horizon_step_T=m["horizon_step_T"], number_of_samples_K=m["number_of_samples_K"],
+                                     max_steer_abs=m["max_steer_abs"], max_accel_abs=m["max_accel_abs"],
+                                     param_lambda=m["param_lambda"])
+        ctrl.ref_path = g.path
+        step = ctrl._calc_control_input
+    for i in range(g.n_ticks):
+        if name == "racecar_viz":
+            ctrl.u_prev = g.rec["U0"][i]
+            ctrl.prev_waypoints_idx = int(g.rec["idx0"][i])
+        u0, u, traj, samp = step(g.rec["x0"][i], noise=g.eps[i])
+        assert np.max(np.abs(u - g.rec["U_after"][i])) <= U_ATOL, (name, i)
+        assert traj.shape == g.rec["optimal_traj"][i].shape and samp.shape == g.rec["sampled_traj"][i].shape
+        scale = max(1.0, float(np.max(np.abs(g.rec["sampled_traj"][i]))))
+        assert np.max(np.abs(traj - g.rec["optimal_traj"][i])) <= 2e-5 * scale, (name, i)
+        assert np.max(np.abs(samp - g.rec["sampled_traj"][i])) <= 2e-5 * scale, (name, i)

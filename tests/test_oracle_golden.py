@@ -151,3 +151,18 @@ def test_reference_classes_still_match_golden():
         ctrl._calc_input_control(g.rec["x0"][0])
     assert np.array_equal(cap["S"], g.rec["S"][0])
     assert np.array_equal(ctrl.u_prev, g.rec["U_after"][0])
+
+
+@pytest.mark.parametrize("name", ["diffdrive_viz", "racecar_viz"])
+def test_visualisation_outputs_and_nominal_clamp(name):
+    """A16 / Q9: with the visualisation flags on, the reference replays the updated nominal and every sample
+    with t-1 indexing and clamps the stored nominal in place; the loop restatement is bit-exact."""
+    g = Golden(name)
+    sp = g.spec()
+    for i in range(g.n_ticks):
+        o = orc.tick_loops(sp, **g.tick_inputs(i))
+        assert np.array_equal(o["U_after"], g.rec["U_after"][i])
+        assert np.array_equal(o["optimal_traj"], g.rec["optimal_traj"][i])
+        assert np.array_equal(o["sampled_traj"], g.rec["sampled_traj"][i])
+    lim = np.asarray(sp.u_max)
+    assert np.all(np.abs(g.rec["U_after"]) <= lim + 1e-6) and np.any(np.abs(g.rec["U_after"]) >= lim - 1e-6)

@@ -282,6 +282,13 @@ def run_b200_arm(args):
         rl = np.sort(np.array(rl))
         extras["racecar_K16384_H50"] = {"p50_ms": 1e3 * float(rl[len(rl) // 2]), "p90_ms": 1e3 * float(rl[int(len(rl) * 0.9)]),
                                         "sample_steps_per_sec": 16384 * 50 / float(rl[len(rl) // 2])}
+        # the same controller closed-loop ON the device (ticks + Vehicle.update plant step, no host round trip)
+        rc.prev_waypoints_idx = 0
+        rc.engine.run_closed_loop(lp[0].astype(np.float64), 20, seed=3, tick0=0, plant=1)
+        rc.prev_waypoints_idx = 0
+        t1 = time.perf_counter()
+        rc.engine.run_closed_loop(lp[0].astype(np.float64), 200, seed=3, tick0=100, plant=1)
+        extras["racecar_K16384_H50"]["device_closed_loop_ms_per_tick"] = 1e3 * (time.perf_counter() - t1) / 200
         rc.engine.close()
         # config[3]: 4096 independent diff-drive controllers x K=1024 x H=30 in one launch
         from mppi_b200.batched import BatchedMPPI

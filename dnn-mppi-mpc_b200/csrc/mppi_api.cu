@@ -57,7 +57,8 @@ struct mppi_handle_s {
     // device buffers
     float4 *d_path = nullptr;
     float *d_U = nullptr, *d_M = nullptr, *d_S = nullptr, *d_part = nullptr, *d_out = nullptr;
-    float *d_x0 = nullptr, *d_opt = nullptr;
+    float *d_x0 = nullptr, *d_opt = nullptr, *d_plant_log = nullptr;
+    int plant_log_cap = 0;
     int *d_idx = nullptr, *d_NC = nullptr;
     unsigned *d_ticket = nullptr;
     float *h_out = nullptr, *h_out_dev = nullptr;     // mapped pinned record of robot 0
@@ -293,7 +294,7 @@ int mppi_destroy(mppi_handle_t h) {
     if (h->mlp) mlp_destroy(h->mlp);
     cudaFree(h->d_path); cudaFree(h->d_U); cudaFree(h->d_M); cudaFree(h->d_S); cudaFree(h->d_part);
     cudaFree(h->d_out); cudaFree(h->d_idx); cudaFree(h->d_NC); cudaFree(h->d_ticket); cudaFree(h->d_first);
-    cudaFree(h->d_bp_n); cudaFree(h->d_bp_s); cudaFree(h->d_send); cudaFree(h->d_recv); cudaFree(h->d_x0); cudaFree(h->d_opt);
+    cudaFree(h->d_bp_n); cudaFree(h->d_bp_s); cudaFree(h->d_send); cudaFree(h->d_recv); cudaFree(h->d_x0); cudaFree(h->d_opt); cudaFree(h->d_plant_log);
     if (h->h_out) cudaFreeHost(h->h_out);
     if (h->h_first) cudaFreeHost(h->h_first);
     for (auto &e : h->ev) if (e) cudaEventDestroy(e);
@@ -634,6 +635,44 @@ int mppi_get_trajectories(mppi_handle_t h, const double *x0, const float *d_eps,
     h->tm.launches++;
     if (optimal_out) CK(h, cudaMemcpyAsync(optimal_out, h->d_opt, sizeof(float) * T * nx, cudaMemcpyDeviceToHost, h->stream));
     CK(h, cudaStreamSynchronize(h->stream));
+    return MPPI_OK;
+}
+
+int mppi_run_closed_loop(mppi_handle_t h, const double *x0, int32_t n_ticks, uint64_t seed, uint64_t tick0,
+                         int32_t plant, float *states_out, float *controls_out) {
+    if (!h || !x0 || n_ticks < 1 || !states_out || plant < 0 || plant > 1) return MPPI_E_BADARG;
+    if (!h->have_path) return fail(h, MPPI_E_STATE, "mppi_set_ref_path has not been called");
+    if (h->cfg.n_robots != 1 || h->strict || h->mlp || h->world > 1)
+        return fail(h, MPPI_E_UNSUPPORTED, "closed loop: frozen waypoint mode, one robot, one GPU, analytic dynamics");
+    if (plant == 1 && h->cfg.model != MPPI_MODEL_BICYCLE) return MPPI_E_BADARG;
+    CK(h, cudaSetDevice(h->cfg.device));
+    const int nx = h->nx;
+    const size_t log_floats = (size_t)4 * (n_ticks + 1) + (size_t)2 * n_ticks;
+    if (h->plant_log_cap < n_ticks) {
+        cudaFree(h->d_plant_log); h->d_plant_log = nullptr;
+        CK(h, cudaMalloc(&h->d_plant_log, sizeof(float) * log_floats));
+        h->plant_log_cap = n_ticks;
+    }
+    if (!h->d_x0) CK(h, cudaMalloc(&h->d_x0, sizeof(float) * 4 * h->cfg.n_robots));
+    float xs[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int i = 0; i < nx; ++i) xs[i] = (float)x0[i];
+    CK(h, cudaMemcpyAsync(h->d_x0, xs, sizeof(xs), cudaMemcpyHostToDevice, h->stream));
+    CK(h, cudaMemcpyAsync(h->d_plant_log, xs, sizeof(xs), cudaMemcpyHostToDevice, h->stream));
+    CK(h, cudaStreamSynchronize(h->stream));                 // xs is a stack buffer
+    for (int i = 0; i < n_ticks; ++i) {
+        set_seed(h, seed, tick0 + (uint64_t)i);
+        TickArgs a = h->args;
+        a.x0_dev = h->d_x0; a.eps = nullptr; a.S = nullptr; a.flags = F_UPDATE;
+        a.plant_state = h->d_x0; a.plant_log = h->d_plant_log; a.plant_mode = plant; a.plant_tick = i; a.plant_n = n_ticks;
+        int rc = launch_update(h, a, false);
+        if (rc != MPPI_OK) return rc;
+    }
+    std::vector<float> log(log_floats);
+    CK(h, cudaMemcpyAsync(log.data(), h->d_plant_log, sizeof(float) * log_floats, cudaMemcpyDeviceToHost, h->stream));
+    CK(h, cudaStreamSynchronize(h->stream));
+    for (int i = 0; i <= n_ticks; ++i)
+        for (int j = 0; j < nx; ++j) states_out[(size_t)i * nx + j] = log[(size_t)4 * i + j];
+    if (controls_out) std::memcpy(controls_out, log.data() + (size_t)4 * (n_ticks + 1), sizeof(float) * 2 * n_ticks);
     return MPPI_OK;
 }
 

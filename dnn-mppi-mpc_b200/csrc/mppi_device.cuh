@@ -67,6 +67,9 @@ struct TickArgs {
     float *out_host;                  // mapped pinned mirror of out (robot 0) or null
     float *u0_out;                    // batched: [R][2] or null
     float *triple_out;                // [NF] per-GPU triple (F_TRIPLE_OUT)
+    float *plant_state;               // closed loop: [4] plant state, advanced by the last block after the update, or null
+    float *plant_log;                 // closed loop: [(n+1)][4] states and [n][2] controls behind them
+    int plant_mode, plant_tick, plant_n;
 };
 
 // ------------------------------------------------------------------------------------------

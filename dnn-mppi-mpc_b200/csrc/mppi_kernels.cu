@@ -113,6 +113,25 @@ __device__ void finalize_tick(const TickArgs &a, int robot, int idx_new, MergeSm
 #pragma unroll
         for (int i = 0; i < MPPI_OUT_HDR; ++i) { out[i] = hdr[i]; if (oh) oh[i] = hdr[i]; }
         if (a.u0_out) { a.u0_out[2 * robot] = u0x; a.u0_out[2 * robot + 1] = u0y; }
+        if (a.plant_state) {
+            // A17: plant step between ticks.  0: DifferentialDrive.update_state (mppi_differential_drive.py:33-40),
+            // unclamped u0; 1: Vehicle.update (models/vehicle.py:95-110), clamp then Euler bicycle.
+            float *ps = a.plant_state;
+            float px = ps[0], py = ps[1], pyaw = ps[2], pv = ps[3];
+            float sn, cs;
+            sincos_cw(pyaw, sn, cs);
+            if (a.plant_mode == 0) {
+                px += u0x * cs * a.dt; py += u0x * sn * a.dt; pyaw += u0y * a.dt;
+            } else {
+                const float steer = clampf(u0x, a.umax0), accel = clampf(u0y, a.umax1);
+                px += pv * cs * a.dt; py += pv * sn * a.dt; pyaw += pv * a.dt_over_L * tanf(steer); pv += accel * a.dt;
+            }
+            ps[0] = px; ps[1] = py; ps[2] = pyaw; ps[3] = pv;
+            float *lg = a.plant_log + 4 * (a.plant_tick + 1);
+            lg[0] = px; lg[1] = py; lg[2] = pyaw; lg[3] = pv;
+            float *lu = a.plant_log + 4 * (a.plant_n + 1) + 2 * a.plant_tick;
+            lu[0] = u0x; lu[1] = u0y;
+        }
         if (!(a.flags & F_KEEP_IDX)) a.idx[robot] = idx_new;
     }
 }

@@ -98,6 +98,17 @@ class ControllerBase:
                 self._viz_warned = True
         return u[0], u, optimal_traj, sampled
 
+    def run_closed_loop(self, x0, n_ticks):
+        """Closed loop on the device: tick, plant step (the reference's own plant for this controller), repeat.
+        Equivalent to the reference's `for i in range(n): u0,... = ctrl._calc_...(x); x = plant(x, u0)` loops
+        (mppi_differential_drive.py:305-367) without a host round trip per tick.  Needs waypoint_mode='frozen'."""
+        plant = 1 if self.dim_x == 4 else 0
+        states, controls = self._engine.run_closed_loop(np.asarray(x0, dtype=np.float64), int(n_ticks), self.seed,
+                                                        self._tick, plant)
+        self._tick += int(n_ticks)
+        self._u_cache = self._engine.get_nominal().astype(self._out_dtype)
+        return states.astype(self._out_dtype), controls.astype(self._out_dtype)
+
     def _viz_gates(self):
         """(replay the nominal?, replay the samples?) -- the diff-drive class gates both on visualze_sampled_trajs
         (mppi_differential_drive.py:145,154), the race-car class uses one flag each (:112,:121)."""

@@ -66,6 +66,7 @@ SYMBOLS = {
     "mppi_generate_noise_robot": (C.c_int, [_H, C.c_uint64, C.c_uint64, C.c_int32, C.c_void_p]),
     "mppi_get_trajectories": (C.c_int, [_H, _PD, C.c_void_p, C.c_uint64, C.c_uint64, _PF, C.c_void_p]),
     "mppi_get_stats": (C.c_int, [_H, C.POINTER(MppiStats)]),
+    "mppi_run_closed_loop": (C.c_int, [_H, _PD, C.c_int32, C.c_uint64, C.c_uint64, C.c_int32, _PF, _PF]),
     "mppi_step_batched": (C.c_int, [_H, C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p]),
     "mppi_comm_get_unique_id": (C.c_int, [C.c_void_p]),
     "mppi_comm_init": (C.c_int, [_H, C.c_void_p, C.c_int32, C.c_int32]),

@@ -158,6 +158,17 @@ class MPPIEngine:
     def generate_noise(self, d_out, seed=0, tick=0, robot=0):
         self._ck(self.lib.mppi_generate_noise_robot(self._h, seed, tick, robot, _dptr(d_out)), "mppi_generate_noise")
 
+    def run_closed_loop(self, x0, n_ticks, seed=0, tick0=0, plant=0):
+        """n_ticks control ticks with the plant step on the device between them.  Returns (states (n+1,nx),
+        controls (n,2)) float32."""
+        self._load_x0(x0)
+        states = np.zeros((n_ticks + 1, self.nx), dtype=np.float32)
+        controls = np.zeros((n_ticks, 2), dtype=np.float32)
+        self._ck(self.lib.mppi_run_closed_loop(self._h, self._x0, n_ticks, seed, tick0, plant,
+                                               states.ctypes.data_as(_lib._PF), controls.ctypes.data_as(_lib._PF)),
+                 "mppi_run_closed_loop")
+        return states, controls
+
     def step_batched(self, d_x0, d_u0_out=None, seed=0, tick=0):
         self._ck(self.lib.mppi_step_batched(self._h, _dptr(d_x0), seed, tick, _dptr(d_u0_out)), "mppi_step_batched")
 

@@ -167,6 +167,14 @@ int mppi_get_stats(mppi_handle_t h, mppi_stats_t *out);   /* robot 0 */
 int mppi_get_trajectories(mppi_handle_t h, const double *x0, const float *d_eps, uint64_t seed, uint64_t tick,
                           float *optimal_out, float *d_sampled_out);
 
+/* On-device closed loop (A17): n_ticks control ticks with the plant step applied on the device between them, no
+ * host round trip per tick.  plant 0 = DifferentialDrive.update_state (controllers/mppi_differential_drive.py:33-40,
+ * Euler unicycle, unclamped u0); plant 1 = Vehicle.update (models/vehicle.py:95-110, clamp then Euler bicycle).
+ * Tick i uses the Philox stream (seed, tick0 + i).  Frozen waypoint mode, one robot.
+ *   states_out  host, (n_ticks+1)*nx floats: x_0 .. x_n;   controls_out  host, n_ticks*2 floats (may be NULL) */
+int mppi_run_closed_loop(mppi_handle_t h, const double *x0, int32_t n_ticks, uint64_t seed, uint64_t tick0,
+                         int32_t plant, float *states_out, float *controls_out);
+
 /* Batched multi-robot tick: n_robots independent controllers in one launch (no reference
  * equivalent; R copies of the loop at mppi_differential_drive.py:111-141).
  *   d_x0  device (R, nx) float32;  d_u0_out device (R, 2) float32 (may be NULL) */

@@ -298,3 +298,36 @@ def test_visualisation_outputs_match_reference(name):
         scale = max(1.0, float(np.max(np.abs(g.rec["sampled_traj"][i]))))
         assert np.max(np.abs(traj - g.rec["optimal_traj"][i])) <= 2e-5 * scale, (name, i)
         assert np.max(np.abs(samp - g.rec["sampled_traj"][i])) <= 2e-5 * scale, (name, i)
+
+
+@pytest.mark.parametrize("model", ["diffdrive", "bicycle"])
+def test_on_device_closed_loop_matches_host_driven_oracle_loop(model):
+    """A17: ticks + plant step entirely on the device vs the oracle stepped from the host with the plant
+    formulas of the reference (DifferentialDrive.update_state / Vehicle.update) and the exported noise."""
+    n = 25
+    if model == "diffdrive":
+        g = Golden("diffdrive_pe0.05")
+        sp = orc.diffdrive_spec(K=2048, T=20, param_exploration=0.05, cost_mode="sum", waypoint_mode="frozen")
+        sp.temperature = 2.0
+        x0 = np.array([0.0, 0.0, 0.0])
+        plant = lambda x, u: orc.plant_diffdrive(x, u, sp.dt)          # noqa: E731
+    else:
+        g = Golden("racecar_noobs")
+        sp = orc.racecar_spec(K=2048, T=20, obstacles=None, dtype=np.float64)
+        x0 = g.path[0].astype(np.float64)
+        plant = lambda x, u: orc.plant_bicycle(x, u, sp.dt)            # noqa: E731
+    eng = engine_from_spec(sp, g.path)
+    states, controls = eng.run_closed_loop(x0, n, seed=31, tick0=0, plant=0 if model == "diffdrive" else 1)
+    eng2 = engine_from_spec(sp, g.path)
+    eps = torch.zeros(sp.K, sp.T, 2, dtype=torch.float32, device="cuda")
+    x, U, idx = x0.copy(), np.zeros((sp.T, 2)), 0
+    for i in range(n):
+        assert np.max(np.abs(states[i] - x)) <= 2e-4, (model, i, np.max(np.abs(states[i] - x)))
+        eng2.generate_noise(eps, seed=31, tick=i)
+        o = co.tick(sp, g.path, U, idx, x.astype(np.float32).astype(np.float64), eps.cpu().numpy())
+        assert np.max(np.abs(controls[i] - o["u0"])) <= 1e-4, (model, i)
+        U, idx = o["U_after"], o["idx_after"]
+        x = plant(x, o["u0"])
+    assert eng.get_waypoint_idx() == idx
+    assert np.max(np.abs(eng.get_nominal() - U)) <= 1e-3
+    eng.close(); eng2.close()

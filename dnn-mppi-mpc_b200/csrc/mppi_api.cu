@@ -70,6 +70,11 @@ struct mppi_handle_s {
     ncclComm_t comm = nullptr;
     int rank = 0, world = 1;
     float *d_send = nullptr, *d_recv = nullptr;
+    // fused peer-memory exchange
+    bool p2p = false;
+    float *d_xchg = nullptr;
+    float *peer_buf[MPPI_MAX_PEERS] = {nullptr};
+    unsigned p2p_seq = 0;
     // MLP dynamics
     MlpState *mlp = nullptr;
     // timing / bookkeeping
@@ -291,6 +296,10 @@ int mppi_destroy(mppi_handle_t h) {
     cudaSetDevice(h->cfg.device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
+    if (h->p2p)
+        for (int p = 0; p < h->world; ++p)
+            if (p != h->rank && h->peer_buf[p]) cudaIpcCloseMemHandle(h->peer_buf[p]);
+    cudaFree(h->d_xchg);
     if (h->mlp) mlp_destroy(h->mlp);
     cudaFree(h->d_path); cudaFree(h->d_U); cudaFree(h->d_M); cudaFree(h->d_S); cudaFree(h->d_part);
     cudaFree(h->d_out); cudaFree(h->d_idx); cudaFree(h->d_NC); cudaFree(h->d_ticket); cudaFree(h->d_first);
@@ -477,6 +486,15 @@ static int launch_update(mppi_handle_t h, const TickArgs &a, bool inj) {
     const bool stash = h->stash && !inj && !(a.flags & F_FROM_S);
     dim3 grid(stash ? h->grid_x_stash : h->grid_x, h->cfg.n_robots);
     const int model = (h->cfg.model == MPPI_MODEL_DIFFDRIVE_MLP) ? MPPI_MODEL_DIFFDRIVE : h->cfg.model;
+    if (h->world > 1 && h->p2p && (a.flags & F_UPDATE)) {
+        TickArgs b = a;                      // exchange fused into the tick kernel: ONE launch, no NCCL call
+        b.flags |= F_P2P;
+        for (int p = 0; p < h->world; ++p) b.peer_buf[p] = h->peer_buf[p];
+        b.p2p_rank = h->rank; b.p2p_world = h->world; b.p2p_seq = ++h->p2p_seq;
+        CK(h, mppi_launch_tick(b, model, h->cfg.collision, h->sum, inj, stash, grid, h->stream));
+        h->tm.launches++;
+        return MPPI_OK;
+    }
     if (h->world > 1 && (a.flags & F_UPDATE)) {
         TickArgs b = a;
         b.flags |= F_TRIPLE_OUT;
@@ -540,6 +558,7 @@ static int step_common(mppi_handle_t h, const double *x0, const float *d_eps, ui
             cudaEventElapsedTime(&h->tm.last_rollout_ms, h->ev[0], h->ev[1]);
             cudaEventElapsedTime(&h->tm.last_update_ms, h->ev[1], h->ev[2]);
         }
+        if (h->p2p && h->h_out[7] != 0.f) return fail(h, MPPI_E_NCCL, "peer-memory exchange timed out (a rank did not arrive)");
         if (u0_out) { u0_out[0] = h->h_out[0]; u0_out[1] = h->h_out[1]; }
         if (useq_out) std::memcpy(useq_out, h->h_out + MPPI_OUT_HDR, sizeof(float) * 2 * h->cfg.T);
     }
@@ -718,6 +737,38 @@ int mppi_comm_init(mppi_handle_t h, const void *uid, int32_t rank, int32_t world
     const size_t nf = MPPI_NF(h->cfg.T);
     CK(h, cudaMalloc(&h->d_send, sizeof(float) * nf));
     CK(h, cudaMalloc(&h->d_recv, sizeof(float) * nf * world));
+    return MPPI_OK;
+}
+
+int mppi_comm_p2p_export(mppi_handle_t h, int32_t world, void *out64) {
+    if (!h || !out64 || world < 2 || world > MPPI_MAX_PEERS) return MPPI_E_BADARG;
+    if (h->cfg.n_robots != 1 || h->strict) return fail(h, MPPI_E_UNSUPPORTED, "sample sharding needs frozen mode, one robot");
+    CK(h, cudaSetDevice(h->cfg.device));
+    if (!h->d_xchg) {
+        CK(h, cudaMalloc(&h->d_xchg, sizeof(float) * MPPI_XCHG_FLOATS));
+        CK(h, cudaMemset(h->d_xchg, 0, sizeof(float) * MPPI_XCHG_FLOATS));
+        CK(h, cudaDeviceSynchronize());
+    }
+    cudaIpcMemHandle_t ih;
+    CK(h, cudaIpcGetMemHandle(&ih, h->d_xchg));
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    std::memcpy(out64, &ih, 64);
+    return MPPI_OK;
+}
+
+int mppi_comm_p2p_open(mppi_handle_t h, const void *handles, int32_t rank, int32_t world) {
+    if (!h || !handles || world < 2 || world > MPPI_MAX_PEERS || rank < 0 || rank >= world) return MPPI_E_BADARG;
+    if (!h->d_xchg) return fail(h, MPPI_E_STATE, "call mppi_comm_p2p_export first");
+    CK(h, cudaSetDevice(h->cfg.device));
+    for (int p = 0; p < world; ++p) {
+        if (p == rank) { h->peer_buf[p] = h->d_xchg; continue; }
+        cudaIpcMemHandle_t ih;
+        std::memcpy(&ih, (const char *)handles + 64 * p, 64);
+        void *ptr = nullptr;
+        CK(h, cudaIpcOpenMemHandle(&ptr, ih, cudaIpcMemLazyEnablePeerAccess));
+        h->peer_buf[p] = (float *)ptr;
+    }
+    h->rank = rank; h->world = world; h->p2p = true; h->p2p_seq = 0;
     return MPPI_OK;
 }
 

@@ -20,7 +20,12 @@
 #define MPPI_OUT_STRIDE (MPPI_OUT_HDR + 8 * MPPI_MAX_T)   // header, U shifted, w_eps, U pre-shift, U before the tick
 #define MPPI_OUT_UPRE (MPPI_OUT_HDR + 4 * MPPI_MAX_T)
 #define MPPI_OUT_UOLD (MPPI_OUT_HDR + 6 * MPPI_MAX_T)
-#define MPPI_NF(T) (4 + 2 * (T))       // floats per partial: ncoll_min, smooth_min, eta, sum w^2, N[T][2]
+#define MPPI_NF(T) (4 + 2 * (T))
+#define MPPI_NF_MAX MPPI_NF(MPPI_MAX_T)
+// exchange buffer of one rank: 2 parities x [MPPI_MAX_PEERS triples of NF_MAX floats], then 2 x MPPI_MAX_PEERS flags
+#define MPPI_XCHG_SLOT(par, r) (((par) * MPPI_MAX_PEERS + (r)) * MPPI_NF_MAX)
+#define MPPI_XCHG_FLAGS (2 * MPPI_MAX_PEERS * MPPI_NF_MAX)
+#define MPPI_XCHG_FLOATS (MPPI_XCHG_FLAGS + 2 * MPPI_MAX_PEERS)       // floats per partial: ncoll_min, smooth_min, eta, sum w^2, N[T][2]
 
 enum : int {
     F_WRITE_S = 1,       // store per-sample costs
@@ -30,6 +35,7 @@ enum : int {
     F_TRIPLE_OUT = 16,   // multi-GPU: publish the merged per-GPU triple, do not finalize
     F_KEEP_IDX = 32,     // do not persist the waypoint index (K2 alone)
     F_IDX_ONLY = 64,     // only run step 1 and persist the index (MLP path, K1 alone)
+    F_P2P = 128,         // multi-GPU: exchange the per-GPU triples over peer memory inside this kernel
     F_COST_SUM = 0x10000 // MLP kernel: cost_mode == sum (the tick kernel takes it as a template argument)
 };
 
@@ -70,6 +76,10 @@ struct TickArgs {
     float *plant_state;               // closed loop: [4] plant state, advanced by the last block after the update, or null
     float *plant_log;                 // closed loop: [(n+1)][4] states and [n][2] controls behind them
     int plant_mode, plant_tick, plant_n;
+    // fused multi-GPU exchange (F_P2P): peer_buf[p] = rank p's exchange buffer (own buffer at index p2p_rank)
+    float *peer_buf[MPPI_MAX_PEERS];
+    int p2p_rank, p2p_world;
+    unsigned p2p_seq;
 };
 
 // ------------------------------------------------------------------------------------------

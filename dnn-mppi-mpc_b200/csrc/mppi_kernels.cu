@@ -41,14 +41,15 @@ struct MergeSmem {
 };
 
 // Merges P partials (layout MPPI_NF) into ms.col by the log-sum-exp rule of SURVEY.md 8e.
-__device__ void merge_partials(const TickArgs &a, const float *parts, int P, MergeSmem &ms) {
+__device__ void merge_partials(const TickArgs &a, const float *parts, int P, MergeSmem &ms, int stride = 0) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int NF = MPPI_NF(a.T);
+    if (stride == 0) stride = NF;
     int n = INT_MAX;
     float s = CUDART_INF_F;
     for (int p = tid; p < P; p += MPPI_BLOCK) {
-        const int pn = __float_as_int(parts[(size_t)p * NF]);
-        const float ps = parts[(size_t)p * NF + 1];
+        const int pn = __float_as_int(__ldcg(parts + (size_t)p * stride));
+        const float ps = __ldcg(parts + (size_t)p * stride + 1);
         if (pn < n || (pn == n && ps < s)) { n = pn; s = ps; }
     }
     warp_lexmin(n, s);
@@ -63,10 +64,10 @@ __device__ void merge_partials(const TickArgs &a, const float *parts, int P, Mer
     for (int c = 2 + tid; c < NF; c += MPPI_BLOCK) {
         float acc = 0.f;
         for (int p = 0; p < P; ++p) {
-            const float *pp = parts + (size_t)p * NF;
-            float sc = rel_weight(__float_as_int(pp[0]), pp[1], n, s, a.inv_temp);
+            const float *pp = parts + (size_t)p * stride;
+            float sc = rel_weight(__float_as_int(__ldcg(pp)), __ldcg(pp + 1), n, s, a.inv_temp);
             if (c == 3) sc *= sc;                       // sum of squared weights scales with sc^2
-            acc += sc * pp[c];
+            acc += sc * __ldcg(pp + c);
         }
         ms.col[c] = acc;
     }
@@ -109,7 +110,7 @@ __device__ void finalize_tick(const TickArgs &a, int robot, int idx_new, MergeSm
         float hdr[MPPI_OUT_HDR];
         hdr[0] = u0x; hdr[1] = u0y; hdr[2] = __int_as_float(idx_new);
         hdr[3] = ms.col[1]; hdr[4] = ms.col[0]; hdr[5] = eta;
-        hdr[6] = eta * eta / ms.col[3]; hdr[7] = 0.f;
+        hdr[6] = eta * eta / ms.col[3]; hdr[7] = (a.flags & F_P2P) ? out[7] : 0.f;     // sticky peer-timeout flag
 #pragma unroll
         for (int i = 0; i < MPPI_OUT_HDR; ++i) { out[i] = hdr[i]; if (oh) oh[i] = hdr[i]; }
         if (a.u0_out) { a.u0_out[2 * robot] = u0x; a.u0_out[2 * robot + 1] = u0y; }
@@ -372,6 +373,33 @@ __global__ void __launch_bounds__(MPPI_BLOCK, STASH ? 2 : MPPI_MIN_BLOCKS) mppi_
         for (int c = tid; c < 2 * T; c += MPPI_BLOCK) ms.col[4 + c] = run.N[c];
         if (tid == 0) { ms.col[0] = __int_as_float(run.n); ms.col[1] = run.s; ms.col[2] = run.eta; ms.col[3] = run.e2; }
         __syncthreads();
+    }
+    if (a.flags & F_P2P) {
+        // ---- fused exchange over NVLink peer memory: publish this GPU's triple to every rank, flag it, wait for
+        // the peers, merge in rank order (bit-identical on all ranks).  Double-buffered by the tick parity.
+        const int G = a.p2p_world, me = a.p2p_rank;
+        const unsigned par = a.p2p_seq & 1u;
+        for (int p = 0; p < G; ++p) {
+            float *dst = a.peer_buf[p] + MPPI_XCHG_SLOT(par, me);
+            for (int c = tid; c < NF; c += MPPI_BLOCK) dst[c] = ms.col[c];
+        }
+        __threadfence_system();
+        __syncthreads();
+        if (tid < G) {
+            unsigned *pf = reinterpret_cast<unsigned *>(a.peer_buf[tid] + MPPI_XCHG_FLAGS) + par * MPPI_MAX_PEERS + me;
+            asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(pf), "r"(a.p2p_seq) : "memory");
+            const unsigned *mf = reinterpret_cast<const unsigned *>(a.peer_buf[me] + MPPI_XCHG_FLAGS) + par * MPPI_MAX_PEERS + tid;
+            unsigned v = 0;
+            const long long t0 = clock64();
+            do {
+                asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(mf) : "memory");
+            } while (v != a.p2p_seq && clock64() - t0 < 4000000000LL);     // ~2 s guard against a dead peer
+            if (v != a.p2p_seq) a.out[7] = 1.f;                              // reported by the host as MPPI_E_NCCL
+        }
+        __syncthreads();
+        merge_partials(a, a.peer_buf[me] + MPPI_XCHG_SLOT(par, 0), G, ms, MPPI_NF_MAX);
+        finalize_tick(a, robot, s_new, ms);
+        return;
     }
     if (a.flags & F_TRIPLE_OUT) {
         for (int c = tid; c < NF; c += MPPI_BLOCK) a.triple_out[c] = ms.col[c];

@@ -114,13 +114,24 @@ class ControllerBase:
         (mppi_differential_drive.py:145,154), the race-car class uses one flag each (:112,:121)."""
         return bool(self.visualze_sampled_trajs), bool(self.visualze_sampled_trajs)
 
-    def comm_init_from_torch(self):
-        """Sample sharding over torch.distributed ranks: rank 0 creates the NCCL id, broadcast, init."""
-        import torch
+    def comm_init_from_torch(self, exchange="p2p"):
+        """Sample sharding over the torch.distributed ranks of one node.  exchange='p2p' (default): the
+        (min, sum w, sum w*eps) exchange is fused into the tick kernel over NVLink peer memory (CUDA IPC
+        handles all-gathered here); exchange='nccl': tick kernel, ncclAllGather, merge kernel."""
         import torch.distributed as dist
-        ids = [MPPIEngine.comm_unique_id() if dist.get_rank() == 0 else None]
-        dist.broadcast_object_list(ids, src=0)
-        self._engine.comm_init(ids[0], dist.get_rank(), dist.get_world_size())
+        rank, world = dist.get_rank(), dist.get_world_size()
+        if exchange == "p2p":
+            mine = self._engine.comm_p2p_export(world)
+            handles = [None] * world
+            dist.all_gather_object(handles, mine)
+            self._engine.comm_p2p_open(b"".join(handles), rank, world)
+            dist.barrier()
+        elif exchange == "nccl":
+            ids = [MPPIEngine.comm_unique_id() if rank == 0 else None]
+            dist.broadcast_object_list(ids, src=0)
+            self._engine.comm_init(ids[0], rank, world)
+        else:
+            raise ValueError("exchange must be 'p2p' or 'nccl'")
 
     @property
     def engine(self):

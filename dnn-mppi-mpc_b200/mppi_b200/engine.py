@@ -194,6 +194,15 @@ class MPPIEngine:
         buf = C.create_string_buffer(unique_id, 128)
         self._ck(self.lib.mppi_comm_init(self._h, buf, rank, world), "mppi_comm_init")
 
+    def comm_p2p_export(self, world: int) -> bytes:
+        buf = C.create_string_buffer(64)
+        self._ck(self.lib.mppi_comm_p2p_export(self._h, world, buf), "mppi_comm_p2p_export")
+        return buf.raw
+
+    def comm_p2p_open(self, handles: bytes, rank: int, world: int):
+        buf = C.create_string_buffer(handles, 64 * world)
+        self._ck(self.lib.mppi_comm_p2p_open(self._h, buf, rank, world), "mppi_comm_p2p_open")
+
     @staticmethod
     def comm_unique_id() -> bytes:
         lib = _lib.load()

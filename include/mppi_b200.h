@@ -184,6 +184,14 @@ int mppi_step_batched(mppi_handle_t h, const float *d_x0, uint64_t seed, uint64_
  * (min cost, sum w, sum w*eps) per tick.  `nccl_unique_id` is the 128-byte ncclUniqueId. */
 int mppi_comm_get_unique_id(void *out128);
 int mppi_comm_init(mppi_handle_t h, const void *nccl_unique_id, int32_t rank, int32_t world);
+/* The same exchange fused INTO the tick kernel over NVLink peer memory (no NCCL call, one launch per tick): every
+ * rank's last CTA stores its (min, sum w, sum w*eps) triple straight into every peer's exchange buffer, raises a
+ * sequence flag, waits for the peers' flags and finishes the merge.  Set-up: each rank exports its buffer with
+ * mppi_comm_p2p_export (64-byte cudaIpcMemHandle_t), the handles are all-gathered by the caller (any transport) and
+ * handed to mppi_comm_p2p_open as world*64 bytes in rank order.  One process per GPU, all GPUs on one NVLink domain. */
+#define MPPI_MAX_PEERS 8
+int mppi_comm_p2p_export(mppi_handle_t h, int32_t world, void *ipc_handle_out64);
+int mppi_comm_p2p_open(mppi_handle_t h, const void *ipc_handles, int32_t rank, int32_t world);
 
 int mppi_set_timing(mppi_handle_t h, int32_t enabled);
 int mppi_get_timings(mppi_handle_t h, mppi_timings_t *out);

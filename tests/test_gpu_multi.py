@@ -28,7 +28,7 @@ def _kwargs(K, T):
                 temperature=2.0, seed=21)
 
 
-def _worker(rank, world, port, K, T, ticks, out):
+def _worker(rank, world, port, K, T, ticks, out, exchange):
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     sys.path[:0] = [root, os.path.join(root, "dnn-mppi-mpc_b200"), os.path.join(root, "tests")]
@@ -38,7 +38,7 @@ def _worker(rank, world, port, K, T, ticks, out):
     torch.cuda.set_device(rank)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     ctrl = MPPIAlgorithms(**_kwargs(K, T), device=rank, rank=rank, world=world)
-    ctrl.comm_init_from_torch()
+    ctrl.comm_init_from_torch(exchange=exchange)
     x = np.array([0.1, 0.05, 0.2])
     res = []
     for _ in range(ticks):
@@ -50,14 +50,15 @@ def _worker(rank, world, port, K, T, ticks, out):
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
-def test_two_gpu_sharded_tick_equals_single_gpu():
+@pytest.mark.parametrize("exchange", ["p2p", "nccl"])
+def test_two_gpu_sharded_tick_equals_single_gpu(exchange):
     import torch.multiprocessing as mp
     from mppi_b200.mppi_differential_drive import MPPIAlgorithms
     K, T, ticks = 1 << 16, 50, 3
     ctx = mp.get_context("spawn")
     out = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, K, T, ticks, out)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, K, T, ticks, out, exchange)) for r in range(2)]
     for p in procs:
         p.start()
     got = dict(out.get(timeout=300) for _ in range(2))

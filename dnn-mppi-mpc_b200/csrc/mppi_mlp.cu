@@ -50,7 +50,6 @@ constexpr int TMEM_D_COL = 256;           // two accumulator buffers of 128 FP32
 constexpr int N_GROUPS = 4;                // compute-warp groups: group g owns accumulator quarter g (128 columns)
 constexpr int N_COMPUTE = 128 * N_GROUPS;  // 16 compute warps: 4 per TMEM lane quarter
 constexpr int MLP_THREADS = 64 + N_COMPUTE;
-constexpr int COLS_PER_GROUP = HID / N_GROUPS;
 
 struct MlpSmem {                          // after the 1024-aligned A / B regions
     float4 w01[HID];                      // (W01[j][0], W01[j][1], W01[j][2], b01[j])
@@ -86,11 +85,6 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t pari
         "WAIT_DONE:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
 
-__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, unsigned long long *bar, int c0, int c1) {
-    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-                 ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
-}
-
 __device__ __forceinline__ void tma_load_2d_mc(void *dst, const CUtensorMap *map, unsigned long long *bar, int c0, int c1, uint16_t mask) {
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
                  ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(mask) : "memory");
@@ -119,13 +113,6 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
 // kind::f16 instruction descriptor: BF16 x BF16 -> F32, K-major A and B, M=128, N=128
 constexpr uint32_t UMMA_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N_MMA >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
 
-__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(UMMA_IDESC), "r"(accumulate) : "memory");
-}
 // A operand in tensor memory (128 lanes x 8 packed bf16x2 columns per K=16 step), B in shared memory
 __device__ __forceinline__ void umma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t accumulate) {
     asm volatile(

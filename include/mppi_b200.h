@@ -53,7 +53,6 @@ enum mppi_collision {
     MPPI_COLLISION_CIRCLE = 1,     /* controllers/mppi_differential_drive_obs.py:301-313 */
     MPPI_COLLISION_FOOTPRINT = 2   /* controllers/mppi_race_car_obstacle.py:255-274 */
 };
-enum mppi_noise_layout { MPPI_NOISE_KTU = 0 /* (K,T,2) row-major, the reference's epsilon layout */ };
 
 #define MPPI_MAX_T 128
 #define MPPI_MAX_WINDOW 256

@@ -40,8 +40,12 @@ struct MergeSmem {
     float upre[2 * MPPI_MAX_T];
 };
 
-// Merges P partials (layout MPPI_NF) into ms.col by the log-sum-exp rule of SURVEY.md 8e.
-__device__ void merge_partials(const TickArgs &a, const float *parts, int P, MergeSmem &ms, int stride = 0) {
+// Merges P partials (layout MPPI_NF) into ms.col by the log-sum-exp rule of SURVEY.md 8e.  Runs in ONE CTA on the
+// critical path of every tick, so it is organised for memory-level parallelism: the P scale factors are computed
+// once (P exps, spread over the threads) into shared memory (`sc`, MPPI_MERGE_TILE floats lent by the caller), then each thread owns a column and streams the
+// partials with 8 independent coalesced loads in flight.
+#define MPPI_MERGE_TILE 1024
+__device__ void merge_partials(const TickArgs &a, const float *parts, int P, MergeSmem &ms, float *sc, int stride = 0) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int NF = MPPI_NF(a.T);
     if (stride == 0) stride = NF;
@@ -61,16 +65,35 @@ __device__ void merge_partials(const TickArgs &a, const float *parts, int P, Mer
         const int wn = ms.red_n[w]; const float ws = ms.red_s[w];
         if (wn < n || (wn == n && ws < s)) { n = wn; s = ws; }
     }
-    for (int c = 2 + tid; c < NF; c += MPPI_BLOCK) {
-        float acc = 0.f;
-        for (int p = 0; p < P; ++p) {
-            const float *pp = parts + (size_t)p * stride;
-            float sc = rel_weight(__float_as_int(__ldcg(pp)), __ldcg(pp + 1), n, s, a.inv_temp);
-            if (c == 3) sc *= sc;                       // sum of squared weights scales with sc^2
-            acc += sc * __ldcg(pp + c);
+    float acc0 = 0.f, acc1 = 0.f;                       // columns 2 + tid and 2 + tid + MPPI_BLOCK (NF <= 260)
+    const int c0 = 2 + tid, c1 = 2 + tid + MPPI_BLOCK;
+    for (int base = 0; base < P; base += MPPI_MERGE_TILE) {
+        const int np = min(MPPI_MERGE_TILE, P - base);
+        __syncthreads();
+        for (int p = tid; p < np; p += MPPI_BLOCK) {
+            const float *pp = parts + (size_t)(base + p) * stride;
+            sc[p] = rel_weight(__float_as_int(__ldcg(pp)), __ldcg(pp + 1), n, s, a.inv_temp);
         }
-        ms.col[c] = acc;
+        __syncthreads();
+        if (c0 < NF) {
+            const float *col = parts + (size_t)base * stride + c0;
+            int p = 0;
+            for (; p + 8 <= np; p += 8) {
+                float v[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) v[i] = __ldcg(col + (size_t)(p + i) * stride);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) { const float w = sc[p + i]; acc0 += (c0 == 3 ? w * w : w) * v[i]; }
+            }
+            for (; p < np; ++p) { const float w = sc[p]; acc0 += (c0 == 3 ? w * w : w) * __ldcg(col + (size_t)p * stride); }
+        }
+        if (c1 < NF) {
+            const float *col = parts + (size_t)base * stride + c1;
+            for (int p = 0; p < np; ++p) acc1 += sc[p] * __ldcg(col + (size_t)p * stride);
+        }
     }
+    if (c0 < NF) ms.col[c0] = acc0;
+    if (c1 < NF) ms.col[c1] = acc1;
     if (tid == 0) { ms.col[0] = __int_as_float(n); ms.col[1] = s; }
     __syncthreads();
 }
@@ -368,7 +391,7 @@ __global__ void __launch_bounds__(MPPI_BLOCK, STASH ? 2 : MPPI_MIN_BLOCKS) mppi_
         return;
     }
     if (B > 1) {
-        merge_partials(a, parts, B, ms);
+        merge_partials(a, parts, B, ms, reinterpret_cast<float *>(mppi_dyn_smem));   // the noise stash is free by now
     } else {
         for (int c = tid; c < 2 * T; c += MPPI_BLOCK) ms.col[4 + c] = run.N[c];
         if (tid == 0) { ms.col[0] = __int_as_float(run.n); ms.col[1] = run.s; ms.col[2] = run.eta; ms.col[3] = run.e2; }
@@ -397,7 +420,7 @@ __global__ void __launch_bounds__(MPPI_BLOCK, STASH ? 2 : MPPI_MIN_BLOCKS) mppi_
             if (v != a.p2p_seq) a.out[7] = 1.f;                              // reported by the host as MPPI_E_NCCL
         }
         __syncthreads();
-        merge_partials(a, a.peer_buf[me] + MPPI_XCHG_SLOT(par, 0), G, ms, MPPI_NF_MAX);
+        merge_partials(a, a.peer_buf[me] + MPPI_XCHG_SLOT(par, 0), G, ms, reinterpret_cast<float *>(mppi_dyn_smem), MPPI_NF_MAX);
         finalize_tick(a, robot, s_new, ms);
         return;
     }
@@ -413,7 +436,8 @@ __global__ void __launch_bounds__(MPPI_BLOCK, STASH ? 2 : MPPI_MIN_BLOCKS) mppi_
 __global__ void __launch_bounds__(MPPI_BLOCK) mppi_merge_kernel(const __grid_constant__ TickArgs a,
                                                                  const float *triples, int G) {
     __shared__ MergeSmem ms;
-    merge_partials(a, triples, G, ms);
+    __shared__ float sc[MPPI_MERGE_TILE];
+    merge_partials(a, triples, G, ms, sc);
     finalize_tick(a, 0, __float_as_int(a.out[2]), ms);
 }
 

@@ -266,6 +266,23 @@ def run_b200_arm(args):
         torch.cuda.synchronize()
         extras["literal_temperature_value"] = K_PER_GPU * T_H / (a.elapsed_time(b) / n2 * 1e-3)
         c2.engine.close()
+        # config[0]: the reference's own CPU-runnable case, literal class semantics (stage cost overwritten, index
+        # mutated during the rollouts -> strict multi-pass kernel), K=1000, H=30, closed loop on the spline path
+        kw0 = diffdrive_kwargs(1000, 30, None)
+        kw0.update(cost_mode="last", waypoint_mode="strict", param_exploration=0.05)
+        c0 = MPPIAlgorithms(**kw0, seed=11)
+        xs0 = np.zeros(3)
+        l0 = []
+        for i in range(150):
+            t1 = time.perf_counter()
+            u0_, _, _, _ = c0._calc_input_control(xs0)
+            l0.append(time.perf_counter() - t1)
+            xs0 = xs0 + 0.1 * np.array([u0_[0] * np.cos(xs0[2]), u0_[0] * np.sin(xs0[2]), u0_[1]])
+        l0 = np.sort(np.array(l0[20:]))
+        extras["literal_diffdrive_K1000_H30"] = {"p50_ms": 1e3 * float(l0[len(l0) // 2]), "p90_ms": 1e3 * float(l0[int(len(l0) * 0.9)]),
+                                                 "passes_last_tick": c0.engine.timings()["last_passes"],
+                                                 "sample_steps_per_sec": 1000 * 30 / float(l0[len(l0) // 2])}
+        c0.engine.close()
         # config[1]: race-car + obstacles, K=16384, H=50 -- p50 control-step latency, host to host
         rc = MPPIRacecarController(horizon_step_T=50, number_of_samples_K=16384,
                                    visualize_optimal_traj=False, visualze_sampled_trajs=False, seed=3)

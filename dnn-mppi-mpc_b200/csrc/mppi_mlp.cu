@@ -12,7 +12,8 @@
 //   * the remaining 512x512 layer is the GEMM: D[128x512] = A[128x512] (TMEM) x W2^T, issued by ONE
 //     thread as tcgen05.mma.cta_group::1.kind::f16 with the A operand in TMEM (M=128, N=128, K=16), W2
 //     streamed from L2 by TMA (cp.async.bulk.tensor, 128x64 bf16 boxes, 128B swizzle) through a
-//     12-stage mbarrier ring (192 KB in flight hides the L2 latency).  CTAs run as clusters of two that
+//     6-stage mbarrier ring of 32 KB stages (two boxes each: one barrier wait and one commit per 8 MMAs keeps the
+//     single issuing thread ahead of the tensor core; 192 KB in flight hides the L2 latency).  CTAs run as clusters of two that
 //     walk the weight stream in lockstep: each CTA issues every other box with .multicast::cluster so
 //     both receive it -- L2 -> SM traffic per SM is halved; the accumulator is produced in
 //     four 128-column quarters through two TMEM buffers (2 x 128 columns), so the epilogue of one
@@ -43,8 +44,11 @@ constexpr int KCH = 64;                   // K elements per 128-byte swizzle spa
 
 constexpr int N_MMA = 128;                // N per tcgen05.mma = one accumulator quarter
 constexpr int N_QUARTERS = HID / N_MMA;
-constexpr int B_STAGES = 12;
-constexpr int B_TILE_BYTES = N_MMA * KCH * 2;      // 16 KB
+constexpr int KCH_PER_STAGE = 2;          // K chunks (TMA boxes) per ring stage: one barrier wait + one commit per 8 MMAs,
+                                          // otherwise the single issuing thread (try_wait ~90 cycles) paces the tensor core
+constexpr int B_STAGES = 6;
+constexpr int B_BOX_BYTES = N_MMA * KCH * 2;       // 16 KB per TMA box
+constexpr int B_TILE_BYTES = KCH_PER_STAGE * B_BOX_BYTES;   // 32 KB per stage
 constexpr int TMEM_A_COL = 0;             // A operand: 512 bf16 per row = 256 packed 32-bit columns
 constexpr int TMEM_D_COL = 256;           // two accumulator buffers of 128 FP32 columns
 constexpr int N_GROUPS = 4;                // compute-warp groups: group g owns accumulator quarter g (128 columns)
@@ -243,14 +247,19 @@ mppi_mlp_rollout_kernel(const __grid_constant__ TickArgs a, const __grid_constan
     if (warp == 0) {
         // ===== TMA producer: the same 16 W2 boxes every timestep, through a B_STAGES ring =====
         if (lane == 0) {
-            const int total = my_tiles * T * N_QUARTERS * (HID / KCH);
+            constexpr int STAGES_PER_Q = HID / KCH / KCH_PER_STAGE;       // 4 stage loads per accumulator quarter
+            const int total = my_tiles * T * N_QUARTERS * STAGES_PER_Q;
             int stage = 0; uint32_t phase = 0;
             for (int it = 0; it < total; ++it) {
-                const int kb = it % (HID / KCH), nq = (it / (HID / KCH)) % N_QUARTERS;
+                const int kb2 = it % STAGES_PER_Q, nq = (it / STAGES_PER_Q) % N_QUARTERS;
                 mbar_wait(&ms.b_empty[stage], phase ^ 1);               // both CTAs are done with this slot
                 mbar_expect_tx(&ms.b_full[stage], B_TILE_BYTES);        // every CTA arms its own barrier ...
-                if ((uint32_t)(it & 1) == cta_rank)                      // ... and issues every other box for both
-                    tma_load_2d_mc(smB + stage * B_TILE_BYTES, &w2_map, &ms.b_full[stage], kb * KCH, nq * N_MMA, (uint16_t)3);
+                if ((uint32_t)(it & 1) == cta_rank) {                    // ... and issues every other stage for both
+#pragma unroll
+                    for (int j = 0; j < KCH_PER_STAGE; ++j)
+                        tma_load_2d_mc(smB + stage * B_TILE_BYTES + j * B_BOX_BYTES, &w2_map, &ms.b_full[stage],
+                                       (kb2 * KCH_PER_STAGE + j) * KCH, nq * N_MMA, (uint16_t)3);
+                }
                 if (++stage == B_STAGES) { stage = 0; phase ^= 1; }
             }
         }
@@ -264,16 +273,18 @@ mppi_mlp_rollout_kernel(const __grid_constant__ TickArgs a, const __grid_constan
                     mbar_wait(&ms.d_empty[buf], ((quarter >> 1) & 1) ^ 1);      // epilogue drained this buffer
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     const uint32_t d_tmem = tmem + TMEM_D_COL + buf * N_MMA;
-                    for (int kb = 0; kb < HID / KCH; ++kb) {
-                        // the activations arrive in four 128-column parts; the first quarter's K loop chases them
-                        if (nq == 0 && (kb & 1) == 0) mbar_wait(&ms.a_ready[kb >> 1], a_phase);
+                    for (int kb2 = 0; kb2 < HID / KCH / KCH_PER_STAGE; ++kb2) {
+                        // the activations arrive in four 128-column parts (= one stage's K range); the first
+                        // quarter's K loop chases them
+                        if (nq == 0) mbar_wait(&ms.a_ready[kb2], a_phase);
                         mbar_wait(&ms.b_full[stage], phase);
                         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                         const uint32_t b_base = smem_u32(smB + stage * B_TILE_BYTES);
 #pragma unroll
-                        for (int k = 0; k < KCH / 16; ++k) {
-                            umma_bf16_ts(d_tmem, tmem + TMEM_A_COL + (kb * (KCH / 16) + k) * 8, umma_desc_sw128(b_base + k * 32),
-                                         (kb | k) ? 1u : 0u);
+                        for (int k = 0; k < KCH_PER_STAGE * (KCH / 16); ++k) {
+                            const uint32_t b_addr = b_base + (k / (KCH / 16)) * B_BOX_BYTES + (k % (KCH / 16)) * 32;
+                            umma_bf16_ts(d_tmem, tmem + TMEM_A_COL + (kb2 * KCH_PER_STAGE * (KCH / 16) + k) * 8,
+                                         umma_desc_sw128(b_addr), (kb2 | k) ? 1u : 0u);
                         }
                         umma_commit_mc(&ms.b_empty[stage], (uint16_t)3);   // frees the W2 slot in BOTH CTAs when these MMAs retire
                         if (++stage == B_STAGES) { stage = 0; phase ^= 1; }

@@ -12,7 +12,7 @@
 //   * the remaining 512x512 layer is the GEMM: D[128x512] = A[128x512] (TMEM) x W2^T, issued by ONE
 //     thread as tcgen05.mma.cta_group::1.kind::f16 with the A operand in TMEM (M=128, N=128, K=16), W2
 //     streamed from L2 by TMA (cp.async.bulk.tensor, 128x64 bf16 boxes, 128B swizzle) through a
-//     6-stage mbarrier ring of 32 KB stages (two boxes each: one barrier wait and one commit per 8 MMAs keeps the
+//     3-stage mbarrier ring of 64 KB stages (four boxes each: one barrier wait and one commit per 16 MMAs keeps the
 //     single issuing thread ahead of the tensor core; 192 KB in flight hides the L2 latency).  CTAs run as clusters of two that
 //     walk the weight stream in lockstep: each CTA issues every other box with .multicast::cluster so
 //     both receive it -- L2 -> SM traffic per SM is halved; the accumulator is produced in
@@ -44,11 +44,11 @@ constexpr int KCH = 64;                   // K elements per 128-byte swizzle spa
 
 constexpr int N_MMA = 128;                // N per tcgen05.mma = one accumulator quarter
 constexpr int N_QUARTERS = HID / N_MMA;
-constexpr int KCH_PER_STAGE = 2;          // K chunks (TMA boxes) per ring stage: one barrier wait + one commit per 8 MMAs,
+constexpr int KCH_PER_STAGE = 4;          // K chunks (TMA boxes) per ring stage: one barrier wait + one commit per 16 MMAs,
                                           // otherwise the single issuing thread (try_wait ~90 cycles) paces the tensor core
-constexpr int B_STAGES = 6;
+constexpr int B_STAGES = 3;
 constexpr int B_BOX_BYTES = N_MMA * KCH * 2;       // 16 KB per TMA box
-constexpr int B_TILE_BYTES = KCH_PER_STAGE * B_BOX_BYTES;   // 32 KB per stage
+constexpr int B_TILE_BYTES = KCH_PER_STAGE * B_BOX_BYTES;   // 64 KB per stage
 constexpr int TMEM_A_COL = 0;             // A operand: 512 bf16 per row = 256 packed 32-bit columns
 constexpr int TMEM_D_COL = 256;           // two accumulator buffers of 128 FP32 columns
 constexpr int N_GROUPS = 4;                // compute-warp groups: group g owns accumulator quarter g (128 columns)
@@ -274,9 +274,12 @@ mppi_mlp_rollout_kernel(const __grid_constant__ TickArgs a, const __grid_constan
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     const uint32_t d_tmem = tmem + TMEM_D_COL + buf * N_MMA;
                     for (int kb2 = 0; kb2 < HID / KCH / KCH_PER_STAGE; ++kb2) {
-                        // the activations arrive in four 128-column parts (= one stage's K range); the first
+                        // the activations arrive in four 128-column parts (a stage spans two of them); the first
                         // quarter's K loop chases them
-                        if (nq == 0) mbar_wait(&ms.a_ready[kb2], a_phase);
+                        if (nq == 0) {
+#pragma unroll
+                            for (int pa = 0; pa < KCH_PER_STAGE / 2; ++pa) mbar_wait(&ms.a_ready[kb2 * (KCH_PER_STAGE / 2) + pa], a_phase);
+                        }
                         mbar_wait(&ms.b_full[stage], phase);
                         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                         const uint32_t b_base = smem_u32(smB + stage * B_TILE_BYTES);

@@ -282,12 +282,13 @@ mppi_mlp_rollout_kernel(const __grid_constant__ TickArgs a, const __grid_constan
                         }
                         mbar_wait(&ms.b_full[stage], phase);
                         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                        const uint32_t b_base = smem_u32(smB + stage * B_TILE_BYTES);
+                        // one descriptor per stage; the 16 K-steps only bump its 14-bit start-address field
+                        const uint64_t b_desc0 = umma_desc_sw128(smem_u32(smB + stage * B_TILE_BYTES));
+                        const uint32_t a_col0 = tmem + TMEM_A_COL + kb2 * KCH_PER_STAGE * (KCH / 16) * 8;
 #pragma unroll
                         for (int k = 0; k < KCH_PER_STAGE * (KCH / 16); ++k) {
-                            const uint32_t b_addr = b_base + (k / (KCH / 16)) * B_BOX_BYTES + (k % (KCH / 16)) * 32;
-                            umma_bf16_ts(d_tmem, tmem + TMEM_A_COL + (kb2 * KCH_PER_STAGE * (KCH / 16) + k) * 8,
-                                         umma_desc_sw128(b_addr), (kb2 | k) ? 1u : 0u);
+                            const uint64_t b_desc = b_desc0 + (uint64_t)(((k / (KCH / 16)) * B_BOX_BYTES + (k % (KCH / 16)) * 32) >> 4);
+                            umma_bf16_ts(d_tmem, a_col0 + k * 8, b_desc, (kb2 | k) ? 1u : 0u);
                         }
                         umma_commit_mc(&ms.b_empty[stage], (uint16_t)3);   // frees the W2 slot in BOTH CTAs when these MMAs retire
                         if (++stage == B_STAGES) { stage = 0; phase ^= 1; }

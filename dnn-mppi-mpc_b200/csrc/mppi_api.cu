@@ -132,6 +132,8 @@ void mppi_default_config(mppi_config_t *c) {
     c->stage_w[0] = 5; c->stage_w[1] = 5; c->stage_w[2] = 10;
     c->term_w[0] = 5; c->term_w[1] = 5; c->term_w[2] = 10;
     c->margin = 1.0; c->robot_radius = 0.5; c->vehicle_l = 4.0; c->vehicle_w = 3.0;
+    c->cost_kind = MPPI_COSTKIND_PATH;
+    c->ctrl_w[0] = c->ctrl_w[1] = 0.1; c->soft_obs_weight = 100.0; c->soft_obs_safety = 2.0;   // test/test_mppi_diff_obs.py:48,56-57
 }
 
 // The fixed filter operators (A14 / Q7) as T x T matrices, float64 then rounded once.
@@ -196,7 +198,12 @@ int mppi_create(const mppi_config_t *cfg, mppi_handle_t *out) {
     if (cfg->model == MPPI_MODEL_DIFFDRIVE_MLP &&
         (cfg->waypoint_mode != MPPI_WP_FROZEN || cfg->n_robots != 1 || cfg->collision != MPPI_COLLISION_NONE))
         return MPPI_E_UNSUPPORTED;
-    if (cfg->waypoint_mode == MPPI_WP_STRICT && cfg->n_robots != 1) return MPPI_E_UNSUPPORTED;
+    if (cfg->cost_kind < MPPI_COSTKIND_PATH || cfg->cost_kind > MPPI_COSTKIND_TARGET_SOFT) return MPPI_E_BADARG;
+    const bool pathless = cfg->cost_kind != MPPI_COSTKIND_PATH;
+    if (pathless && cfg->model != MPPI_MODEL_DIFFDRIVE) return MPPI_E_UNSUPPORTED;       // both scripts drive a unicycle
+    if (cfg->cost_kind == MPPI_COSTKIND_GOAL && cfg->collision == MPPI_COLLISION_FOOTPRINT) return MPPI_E_UNSUPPORTED;
+    if (cfg->cost_kind == MPPI_COSTKIND_TARGET_SOFT && cfg->collision != MPPI_COLLISION_NONE) return MPPI_E_UNSUPPORTED;
+    if (cfg->waypoint_mode == MPPI_WP_STRICT && cfg->n_robots != 1 && !pathless) return MPPI_E_UNSUPPORTED;
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || cfg->device >= ndev) return MPPI_E_CUDA;
 
@@ -207,7 +214,8 @@ int mppi_create(const mppi_config_t *cfg, mppi_handle_t *out) {
     if (c.K_global <= 0) c.K_global = c.K;
     h->nx = (c.model == MPPI_MODEL_BICYCLE) ? 4 : 3;
     h->sum = c.cost_mode == MPPI_COST_SUM;
-    h->strict = c.waypoint_mode == MPPI_WP_STRICT;
+    h->strict = c.waypoint_mode == MPPI_WP_STRICT && c.cost_kind == MPPI_COSTKIND_PATH;   // no waypoint index without a path
+    h->have_path = c.cost_kind != MPPI_COSTKIND_PATH;
 #define CKC(call)                                                                           \
     do {                                                                                    \
         cudaError_t e_ = (call);                                                            \
@@ -227,8 +235,8 @@ int mppi_create(const mppi_config_t *cfg, mppi_handle_t *out) {
     const int R = c.n_robots, T = c.T, K = c.K;
     const int chunks = (K + MPPI_BLOCK - 1) / MPPI_BLOCK;
     const int tick_model = (c.model == MPPI_MODEL_DIFFDRIVE_MLP) ? MPPI_MODEL_DIFFDRIVE : c.model;
-    h->occ = std::max(1, mppi_tick_occupancy(tick_model, c.collision, h->sum, false, c.window, T, false));
-    const int occ_stash = mppi_tick_occupancy(tick_model, c.collision, h->sum, false, c.window, T, true);
+    h->occ = std::max(1, mppi_tick_occupancy(tick_model, c.collision, c.cost_kind, h->sum, false, c.window, T, false));
+    const int occ_stash = mppi_tick_occupancy(tick_model, c.collision, c.cost_kind, h->sum, false, c.window, T, true);
     h->stash = occ_stash >= 2 && c.model != MPPI_MODEL_DIFFDRIVE_MLP;
     int gx = (h->n_sm * h->occ + R - 1) / R;
     gx = std::max(1, std::min(gx, chunks));
@@ -279,6 +287,9 @@ int mppi_create(const mppi_config_t *cfg, mppi_handle_t *out) {
     const double l00 = std::sqrt(c.sigma[0]), l10 = c.sigma[2] / l00;
     a.chol[0] = (float)l00; a.chol[1] = (float)l10; a.chol[2] = (float)std::sqrt(c.sigma[3] - l10 * l10);
     a.inv_temp = (float)(1.0 / c.temperature);
+    for (int i = 0; i < 4; ++i) a.goal[i] = (float)c.goal[i];
+    a.ctrl_w[0] = (float)c.ctrl_w[0]; a.ctrl_w[1] = (float)c.ctrl_w[1];
+    a.soft_w = (float)c.soft_obs_weight; a.soft_sd = (float)c.soft_obs_safety;
     refresh_obstacle_args(h, nullptr, 0);
     a.U = h->d_U; a.idx = h->d_idx; a.M = h->d_M; a.part = h->d_part; a.ticket = h->d_ticket;
     a.out = h->d_out; a.out_host = h->h_out_dev;
@@ -329,6 +340,7 @@ int mppi_synchronize(mppi_handle_t h) {
 int mppi_set_ref_path(mppi_handle_t h, const double *path, int32_t n, int32_t ncol) {
     if (!h || !path || n < 1 || (ncol != 3 && ncol != 4)) return MPPI_E_BADARG;
     if (h->cfg.model == MPPI_MODEL_BICYCLE && ncol != 4) return fail(h, MPPI_E_BADARG, "bicycle model needs (N,4) path");
+    if (h->cfg.cost_kind != MPPI_COSTKIND_PATH) return fail(h, MPPI_E_STATE, "goal / target cost kinds take no reference path");
     CK(h, cudaSetDevice(h->cfg.device));
     CK(h, cudaStreamSynchronize(h->stream));
     std::vector<float4> p((size_t)n);
@@ -351,7 +363,27 @@ int mppi_set_ref_path(mppi_handle_t h, const double *path, int32_t n, int32_t nc
 
 int mppi_set_obstacles(mppi_handle_t h, const double *xyr, int32_t m) {
     if (!h || m < 0 || m > MPPI_MAX_OBSTACLES || (m > 0 && !xyr)) return MPPI_E_BADARG;
+    if (h->cfg.cost_kind == MPPI_COSTKIND_TARGET_SOFT) return fail(h, MPPI_E_STATE, "TARGET_SOFT takes mppi_set_moving_obstacles");
     refresh_obstacle_args(h, xyr, m);
+    return MPPI_OK;
+}
+
+int mppi_set_goal(mppi_handle_t h, const double *goal, int32_t n) {
+    if (!h || !goal || n < 2 || n > 3) return MPPI_E_BADARG;
+    if (h->cfg.cost_kind == MPPI_COSTKIND_PATH) return fail(h, MPPI_E_STATE, "handle was not created with a goal / target cost kind");
+    for (int i = 0; i < n; ++i) { h->cfg.goal[i] = goal[i]; h->args.goal[i] = (float)goal[i]; }
+    return MPPI_OK;
+}
+
+int mppi_set_moving_obstacles(mppi_handle_t h, const double *pos, const double *vel, int32_t m) {
+    if (!h || m < 0 || m > MPPI_MAX_OBSTACLES || (m > 0 && (!pos || !vel))) return MPPI_E_BADARG;
+    if (h->cfg.cost_kind != MPPI_COSTKIND_TARGET_SOFT) return fail(h, MPPI_E_STATE, "handle was not created with MPPI_COSTKIND_TARGET_SOFT");
+    TickArgs &a = h->args;
+    a.n_obs = m;
+    for (int i = 0; i < m; ++i) {
+        a.obs_x[i] = (float)pos[2 * i]; a.obs_y[i] = (float)pos[2 * i + 1];
+        a.obs_vx[i] = (float)vel[2 * i]; a.obs_vy[i] = (float)vel[2 * i + 1];
+    }
     return MPPI_OK;
 }
 
@@ -491,7 +523,7 @@ static int launch_update(mppi_handle_t h, const TickArgs &a, bool inj) {
         b.flags |= F_P2P;
         for (int p = 0; p < h->world; ++p) b.peer_buf[p] = h->peer_buf[p];
         b.p2p_rank = h->rank; b.p2p_world = h->world; b.p2p_seq = ++h->p2p_seq;
-        CK(h, mppi_launch_tick(b, model, h->cfg.collision, h->sum, inj, stash, grid, h->stream));
+        CK(h, mppi_launch_tick(b, model, h->cfg.collision, h->cfg.cost_kind, h->sum, inj, stash, grid, h->stream));
         h->tm.launches++;
         return MPPI_OK;
     }
@@ -499,7 +531,7 @@ static int launch_update(mppi_handle_t h, const TickArgs &a, bool inj) {
         TickArgs b = a;
         b.flags |= F_TRIPLE_OUT;
         b.triple_out = h->d_send;
-        CK(h, mppi_launch_tick(b, model, h->cfg.collision, h->sum, inj, stash, grid, h->stream));
+        CK(h, mppi_launch_tick(b, model, h->cfg.collision, h->cfg.cost_kind, h->sum, inj, stash, grid, h->stream));
         const size_t nf = MPPI_NF(h->cfg.T);
         ncclResult_t r = g_nccl.AllGather(h->d_send, h->d_recv, nf, ncclFloat, h->comm, h->stream);
         if (r != ncclSuccess) { h->err = g_nccl.GetErrorString(r); return MPPI_E_NCCL; }
@@ -507,7 +539,7 @@ static int launch_update(mppi_handle_t h, const TickArgs &a, bool inj) {
         h->tm.launches += 2;
         return MPPI_OK;
     }
-    CK(h, mppi_launch_tick(a, model, h->cfg.collision, h->sum, inj, stash, grid, h->stream));
+    CK(h, mppi_launch_tick(a, model, h->cfg.collision, h->cfg.cost_kind, h->sum, inj, stash, grid, h->stream));
     h->tm.launches++;
     return MPPI_OK;
 }
@@ -587,7 +619,7 @@ int mppi_rollout_costs(mppi_handle_t h, const double *x0, const float *d_eps, ui
         TickArgs a = h->args;
         a.flags = F_IDX_ONLY;
         dim3 grid(1, 1);
-        CK(h, mppi_launch_tick(a, MPPI_MODEL_DIFFDRIVE, MPPI_COLLISION_NONE, h->sum, false, false, grid, h->stream));
+        CK(h, mppi_launch_tick(a, MPPI_MODEL_DIFFDRIVE, MPPI_COLLISION_NONE, MPPI_COSTKIND_PATH, h->sum, false, false, grid, h->stream));
         h->tm.launches++;
     } else if (h->strict) {
         int idx_after = 0;
@@ -598,7 +630,7 @@ int mppi_rollout_costs(mppi_handle_t h, const double *x0, const float *d_eps, ui
         TickArgs a = h->args;
         a.eps = d_eps; a.S = d_S; a.flags = F_WRITE_S;
         dim3 grid(h->grid_x, 1);
-        CK(h, mppi_launch_tick(a, h->cfg.model, h->cfg.collision, h->sum, d_eps != nullptr, false, grid, h->stream));
+        CK(h, mppi_launch_tick(a, h->cfg.model, h->cfg.collision, h->cfg.cost_kind, h->sum, d_eps != nullptr, false, grid, h->stream));
         h->tm.launches++;
     }
     CK(h, cudaStreamSynchronize(h->stream));
@@ -709,7 +741,7 @@ int mppi_step_batched(mppi_handle_t h, const float *d_x0, uint64_t seed, uint64_
     a.x0_dev = h->d_x0; a.eps = nullptr; a.S = nullptr; a.flags = F_UPDATE; a.u0_out = d_u0_out;
     a.out_host = nullptr;
     dim3 grid(h->stash ? h->grid_x_stash : h->grid_x, h->cfg.n_robots);
-    CK(h, mppi_launch_tick(a, h->cfg.model, h->cfg.collision, h->sum, false, h->stash, grid, h->stream));
+    CK(h, mppi_launch_tick(a, h->cfg.model, h->cfg.collision, h->cfg.cost_kind, h->sum, false, h->stash, grid, h->stream));
     h->tm.launches++;
     return MPPI_OK;
 }

@@ -53,6 +53,11 @@ struct TickArgs {
     float obs_r2[MPPI_MAX_OBSTACLES];     // collision radius^2: r^2 (footprint) or (r_robot*margin + r)^2 (circle)
     float obs_far2[MPPI_MAX_OBSTACLES];   // footprint quick reject: (half diagonal + r)^2, inflated
     float fp_hl, fp_hw;                   // footprint half length / half width incl. margin
+    // cost kinds without a reference path (template WIN = MPPI_WIN_GOAL / MPPI_WIN_TARGET)
+    float goal[4];                        // GOAL: (x, y); TARGET_SOFT: desired pose (x, y, yaw)
+    float ctrl_w[2];                      // TARGET_SOFT: diagonal of R
+    float soft_w, soft_sd;                // TARGET_SOFT: obstacle weight, safety distance
+    float obs_vx[MPPI_MAX_OBSTACLES], obs_vy[MPPI_MAX_OBSTACLES];   // TARGET_SOFT: obstacle velocities (position = obs + vel * t*dt)
     // per tick
     float x0[4];
     uint32_t seed_lo, seed_hi, tick;
@@ -321,6 +326,69 @@ __device__ __forceinline__ float tracking_cost(const float4 ref, const float z[4
     return c;
 }
 
+// The tick kernel's WIN template argument doubles as the cost-kind selector: 20 / 0 = path tracking with a static /
+// dynamic waypoint window, negative = no reference path at all.
+#define MPPI_WIN_GOAL (-1)
+#define MPPI_WIN_TARGET (-2)
+
+// Goal-point cost of test/mppi_differential_drive_obs.py:202-232: w0 * |xy - goal|^2 + w1 * wrap(atan2(dy, dx) - yaw)^2
+// with (dx, dy) = xy - goal (the bearing FROM the goal, as the reference writes it) and wrap(a) =
+// atan2(sin a, cos a) in (-pi, pi], evaluated as the FMA remainder a - 2pi*rint(a / 2pi) (only its square is used).
+__device__ __forceinline__ float goal_cost(const TickArgs &a, const float z[4], const float w[4]) {
+    const float dx = z[0] - a.goal[0], dy = z[1] - a.goal[1];
+    const float d2 = fmaf(dy, dy, dx * dx);
+    const float diff = atan2f(dy, dx) - z[2];
+    const float k = rintf(diff * 0.15915494309189535f);
+    float r = fmaf(k, -6.2831854820251465f, diff);          // 2pi = hi + lo (float32 pieces)
+    r = fmaf(k, 1.7484555314695172e-07f, r);
+    return w[0] * d2 + w[1] * r * r;
+}
+
+// Running cost of test/test_mppi_diff_obs.py:44-66 for the state reached by horizon step t (time t*dt) under the
+// clamped control (v0, v1): (z - target)^T Q (z - target) + v^T R v + W * sum_m exp(sd - d_m) [d_m < sd] with
+// d_m the distance to obstacle m at pos_m + vel_m * t*dt (:14-20).  `full` = false: the quadratic pose error only.
+__device__ __forceinline__ float target_soft_cost(const TickArgs &a, const float z[4], float v0, float v1, int t,
+                                                  const float w[4], bool full) {
+    const float ex = z[0] - a.goal[0], ey = z[1] - a.goal[1], eth = z[2] - a.goal[2];
+    float c = w[0] * ex * ex + w[1] * ey * ey + w[2] * eth * eth;
+    if (full) {
+        c += a.ctrl_w[0] * v0 * v0 + a.ctrl_w[1] * v1 * v1;
+        const float tt = (float)t * a.dt;
+        float soft = 0.f;
+        for (int m = 0; m < a.n_obs; ++m) {
+            const float dx = z[0] - fmaf(a.obs_vx[m], tt, a.obs_x[m]), dy = z[1] - fmaf(a.obs_vy[m], tt, a.obs_y[m]);
+            const float d = sqrtf(fmaf(dy, dy, dx * dx));
+            if (d < a.soft_sd) soft += expf(a.soft_sd - d);
+        }
+        c = fmaf(a.soft_w, soft, c);
+    }
+    return c;
+}
+
+// A9 for every cost kind: the cost of state z reached by horizon step t with weights w.  For the path kinds the
+// waypoint (ref, yaw_eff) found here is kept so the terminal cost of the same state can reuse it.
+template <int MODEL, int WIN>
+__device__ __forceinline__ float eval_state_cost(const TickArgs &a, const TickSmem &sm, const float z[4], float v0, float v1,
+                                                 int t, const float w[4], float4 &ref, float &yaw_eff) {
+    if constexpr (WIN == MPPI_WIN_GOAL) {
+        return goal_cost(a, z, w);
+    } else if constexpr (WIN == MPPI_WIN_TARGET) {
+        return target_soft_cost(a, z, v0, v1, t, w, true);
+    } else {
+        const int j = nearest_wp<WIN>(sm, z[0], z[1]);
+        ref = window_ref(sm, j);
+        yaw_eff = (MODEL == MPPI_MODEL_BICYCLE && a.yaw_wrap) ? wrap_2pi(z[2]) : z[2];
+        return tracking_cost<MODEL>(ref, z, yaw_eff, w);
+    }
+}
+// terminal cost of the SAME state the last stage cost was evaluated at (A9, :126)
+template <int MODEL, int WIN>
+__device__ __forceinline__ float eval_terminal_cost(const TickArgs &a, const float z[4], const float4 ref, float yaw_eff) {
+    if constexpr (WIN == MPPI_WIN_GOAL) return goal_cost(a, z, a.tw);
+    else if constexpr (WIN == MPPI_WIN_TARGET) return target_soft_cost(a, z, 0.f, 0.f, 0, a.tw, false);
+    else return tracking_cost<MODEL>(ref, z, yaw_eff, a.tw);
+}
+
 // A6 / A7: explicit-Euler dynamics; (cs, sn) = cos/sin of the CURRENT heading.
 template <int MODEL>
 __device__ __forceinline__ void dyn_step(const TickArgs &a, float z[4], float v0, float v1, float cs, float sn) {
@@ -378,11 +446,9 @@ __device__ __forceinline__ void rollout_sample(const TickArgs &a, const TickSmem
         dyn_step<MODEL>(a, z, v0, v1, cs, sn);
         sincos_cw(z[2], sn, cs);
         if (SUM) {
-            const int j = nearest_wp<WIN>(sm, z[0], z[1]);
-            ref = window_ref(sm, j);
-            yaw_eff = (MODEL == MPPI_MODEL_BICYCLE && a.yaw_wrap) ? wrap_2pi(z[2]) : z[2];
+            const float c = eval_state_cost<MODEL, WIN>(a, sm, z, v0, v1, t, a.sw, ref, yaw_eff);
             const float2 q = sm.Q[t];                                                // zero when gamma == 0
-            acc += tracking_cost<MODEL>(ref, z, yaw_eff, a.sw) + (q.x * v0 + q.y * v1);
+            acc += c + (q.x * v0 + q.y * v1);
             hit = collided<MODEL, COLL>(a, z[0], z[1], cs, sn);
             nc += hit ? 1 : 0;
         }
@@ -400,15 +466,12 @@ __device__ __forceinline__ void rollout_sample(const TickArgs &a, const TickSmem
     }
     if (T & 1) step(T - 1, e[0], e[1]);
     if (SUM) {                          // terminal cost: same state, same waypoint as the last stage cost (A9)
-        acc += tracking_cost<MODEL>(ref, z, yaw_eff, a.tw);
+        acc += eval_terminal_cost<MODEL, WIN>(a, z, ref, yaw_eff);
         nc += hit ? 1 : 0;
     } else {                            // Q1: only the last stage cost survives, plus terminal
-        const int j = nearest_wp<WIN>(sm, z[0], z[1]);
-        ref = window_ref(sm, j);
-        yaw_eff = (MODEL == MPPI_MODEL_BICYCLE && a.yaw_wrap) ? wrap_2pi(z[2]) : z[2];
         const float2 q = sm.Q[T - 1];
-        acc = tracking_cost<MODEL>(ref, z, yaw_eff, a.sw) + (q.x * v0 + q.y * v1);
-        acc += tracking_cost<MODEL>(ref, z, yaw_eff, a.tw);
+        acc = eval_state_cost<MODEL, WIN>(a, sm, z, v0, v1, T - 1, a.sw, ref, yaw_eff) + (q.x * v0 + q.y * v1);
+        acc += eval_terminal_cost<MODEL, WIN>(a, z, ref, yaw_eff);
         nc = collided<MODEL, COLL>(a, z[0], z[1], cs, sn) ? 2 : 0;
     }
     smooth = acc;

@@ -195,7 +195,9 @@ __global__ void __launch_bounds__(MPPI_BLOCK, STASH ? 2 : MPPI_MIN_BLOCKS) mppi_
     if (tid < 4) sm.x0[tid] = a.x0_dev ? a.x0_dev[robot * 4 + tid] : a.x0[tid];
     __syncthreads();
     int s_new;
-    if (a.flags & F_HOST_IDX) {
+    if (WIN < 0) {
+        s_new = 0;                                      // goal / target cost kinds: no reference path, no carried index
+    } else if (a.flags & F_HOST_IDX) {
         s_new = a.idx_host;
     } else {
         const int s_old = a.idx[robot];
@@ -221,7 +223,7 @@ __global__ void __launch_bounds__(MPPI_BLOCK, STASH ? 2 : MPPI_MIN_BLOCKS) mppi_
     {
         int nw = a.n_path - s_new; nw = nw < a.window ? nw : a.window;
         // static-window kernels read exactly 20 entries, dynamic ones whole chunks of 16
-        const int fill = (WIN == 20) ? 20 : ((nw + 15) & ~15);
+        const int fill = (WIN < 0) ? 0 : (WIN == 20) ? 20 : ((nw + 15) & ~15);
         for (int j = tid; j < fill; j += MPPI_BLOCK) {
             if (j < nw) {
                 const float4 p = a.path[s_new + j];
@@ -565,6 +567,21 @@ __global__ void __launch_bounds__(MPPI_BLOCK) mppi_strict_kernel(const __grid_co
 // dispatch
 // ------------------------------------------------------------------------------------------
 // Calls f(kernel pointer) for the instantiation selected by the runtime mode flags.
+// The path-free cost kinds (diff-drive only) have a handful of instantiations of their own.
+template <int COLL, int WIN, typename F>
+static cudaError_t with_tick_kernel_nopath(bool sum, bool inj, bool stash, F &&f) {
+#define MPPI_PICK(S, I, ST) return f(mppi_tick_kernel<MPPI_MODEL_DIFFDRIVE, COLL, S, I, WIN, ST>)
+    if (sum) {
+        if (inj) MPPI_PICK(true, true, false);
+        if (stash) MPPI_PICK(true, false, true);
+        MPPI_PICK(true, false, false);
+    }
+    if (inj) MPPI_PICK(false, true, false);
+    if (stash) MPPI_PICK(false, false, true);
+    MPPI_PICK(false, false, false);
+#undef MPPI_PICK
+}
+
 template <int MODEL, int COLL, typename F>
 static cudaError_t with_tick_kernel_mc(bool sum, bool inj, bool win20, bool stash, F &&f) {
 #define MPPI_PICK(S, I, W, ST) return f(mppi_tick_kernel<MODEL, COLL, S, I, W, ST>)
@@ -581,7 +598,17 @@ static cudaError_t with_tick_kernel_mc(bool sum, bool inj, bool win20, bool stas
 }
 
 template <typename F>
-static cudaError_t with_tick_kernel(int model, int coll, bool sum, bool inj, bool win20, bool stash, F &&f) {
+static cudaError_t with_tick_kernel(int model, int coll, int cost_kind, bool sum, bool inj, bool win20, bool stash, F &&f) {
+    if (cost_kind == MPPI_COSTKIND_GOAL) {              // test/mppi_differential_drive_obs.py: unicycle, circle obstacles
+        if (model != MPPI_MODEL_DIFFDRIVE) return cudaErrorInvalidValue;
+        if (coll == MPPI_COLLISION_NONE) return with_tick_kernel_nopath<MPPI_COLLISION_NONE, MPPI_WIN_GOAL>(sum, inj, stash, f);
+        if (coll == MPPI_COLLISION_CIRCLE) return with_tick_kernel_nopath<MPPI_COLLISION_CIRCLE, MPPI_WIN_GOAL>(sum, inj, stash, f);
+        return cudaErrorInvalidValue;
+    }
+    if (cost_kind == MPPI_COSTKIND_TARGET_SOFT) {       // test/test_mppi_diff_obs.py: unicycle, soft moving obstacles
+        if (model != MPPI_MODEL_DIFFDRIVE || coll != MPPI_COLLISION_NONE) return cudaErrorInvalidValue;
+        return with_tick_kernel_nopath<MPPI_COLLISION_NONE, MPPI_WIN_TARGET>(sum, inj, stash, f);
+    }
     if (model == MPPI_MODEL_DIFFDRIVE) {
         if (coll == MPPI_COLLISION_NONE) return with_tick_kernel_mc<MPPI_MODEL_DIFFDRIVE, MPPI_COLLISION_NONE>(sum, inj, win20, stash, f);
         if (coll == MPPI_COLLISION_CIRCLE) return with_tick_kernel_mc<MPPI_MODEL_DIFFDRIVE, MPPI_COLLISION_CIRCLE>(sum, inj, win20, stash, f);
@@ -597,9 +624,9 @@ size_t mppi_tick_dyn_smem(int T, bool stash) {
     return stash ? sizeof(float2) * (size_t)T * MPPI_BLOCK : sizeof(float) * MPPI_WARPS * 2 * MPPI_MAX_T;
 }
 
-cudaError_t mppi_launch_tick(const TickArgs &a, int model, int coll, bool sum, bool inj, bool stash, dim3 grid, cudaStream_t st) {
+cudaError_t mppi_launch_tick(const TickArgs &a, int model, int coll, int cost_kind, bool sum, bool inj, bool stash, dim3 grid, cudaStream_t st) {
     const size_t dyn = mppi_tick_dyn_smem(a.T, stash);
-    return with_tick_kernel(model, coll, sum, inj, a.window == 20, stash, [&](auto kern) {
+    return with_tick_kernel(model, coll, cost_kind, sum, inj, a.window == 20, stash, [&](auto kern) {
         if (dyn > 48 * 1024) {
             cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
             if (e != cudaSuccess) return e;
@@ -610,10 +637,10 @@ cudaError_t mppi_launch_tick(const TickArgs &a, int model, int coll, bool sum, b
 }
 
 // Resident CTAs per SM of the instantiation the given modes select (0 if it cannot launch).
-int mppi_tick_occupancy(int model, int coll, bool sum, bool inj, int window, int T, bool stash) {
+int mppi_tick_occupancy(int model, int coll, int cost_kind, bool sum, bool inj, int window, int T, bool stash) {
     int nb = 0;
     const size_t dyn = mppi_tick_dyn_smem(T, stash);
-    cudaError_t e = with_tick_kernel(model, coll, sum, inj, window == 20, stash, [&](auto kern) {
+    cudaError_t e = with_tick_kernel(model, coll, cost_kind, sum, inj, window == 20, stash, [&](auto kern) {
         if (dyn > 48 * 1024) {
             cudaError_t e2 = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
             if (e2 != cudaSuccess) return e2;

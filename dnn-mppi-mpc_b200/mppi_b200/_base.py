@@ -38,7 +38,8 @@ class ControllerBase:
         self._engine = MPPIEngine(device=device, **engine_kw)
         self._K_local = engine_kw["K"]
         self._ref_path = None
-        self.ref_path = ref_path
+        if ref_path is not None:                 # goal / target cost kinds have no reference path
+            self.ref_path = ref_path
         self._u_cache = np.zeros((self.T, self.dim_u), dtype=self._out_dtype)
         self._viz_warned = False
 

@@ -6,24 +6,26 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("MPPI_B200_LIB", os.path.join(_HERE, "libmppi_b200.so"))   # override: kernel A/B builds
 
-MPPI_ABI_VERSION = 1
+MPPI_ABI_VERSION = 2
 MODEL = {"diffdrive": 0, "bicycle": 1, "diffdrive_mlp": 2}
 COST_MODE = {"last": 0, "sum": 1}
 WAYPOINT_MODE = {"strict": 0, "frozen": 1}
 FILTER = {"diffdrive": 0, "racecar": 1}
 COLLISION = {"none": 0, "circle": 1, "footprint": 2}
+COST_KIND = {"path": 0, "goal": 1, "target_soft": 2}
 MAX_T, MAX_WINDOW, MAX_OBSTACLES = 128, 256, 16
 
 
 class MppiConfig(C.Structure):
     _fields_ = [(n, C.c_int32) for n in (
         "abi_version", "device", "model", "K", "T", "n_robots", "window", "cost_mode",
-        "waypoint_mode", "filter_kind", "yaw_wrap", "collision", "K_global", "k_offset", "clamp_nominal", "reserved0")] + [
+        "waypoint_mode", "filter_kind", "yaw_wrap", "collision", "K_global", "k_offset", "clamp_nominal", "cost_kind")] + [
         ("dt", C.c_double), ("wheel_base", C.c_double), ("u_max", C.c_double * 2),
         ("param_exploration", C.c_double), ("param_lambda", C.c_double), ("param_alpha", C.c_double),
         ("temperature", C.c_double), ("sigma", C.c_double * 4), ("stage_w", C.c_double * 4),
         ("term_w", C.c_double * 4), ("margin", C.c_double), ("robot_radius", C.c_double),
-        ("vehicle_l", C.c_double), ("vehicle_w", C.c_double)]
+        ("vehicle_l", C.c_double), ("vehicle_w", C.c_double), ("goal", C.c_double * 4),
+        ("ctrl_w", C.c_double * 2), ("soft_obs_weight", C.c_double), ("soft_obs_safety", C.c_double)]
 
 
 class MppiTimings(C.Structure):
@@ -53,6 +55,8 @@ SYMBOLS = {
     "mppi_synchronize": (C.c_int, [_H]),
     "mppi_set_ref_path": (C.c_int, [_H, _PD, C.c_int32, C.c_int32]),
     "mppi_set_obstacles": (C.c_int, [_H, _PD, C.c_int32]),
+    "mppi_set_goal": (C.c_int, [_H, _PD, C.c_int32]),
+    "mppi_set_moving_obstacles": (C.c_int, [_H, _PD, _PD, C.c_int32]),
     "mppi_set_nominal": (C.c_int, [_H, _PF]),
     "mppi_get_nominal": (C.c_int, [_H, _PF]),
     "mppi_set_waypoint_idx": (C.c_int, [_H, _PI]),

@@ -21,7 +21,8 @@ class MPPIEngine:
                  param_lambda, param_alpha, temperature, window, cost_mode, waypoint_mode,
                  filter_kind, yaw_wrap, collision="none", obstacles=None, margin=1.0,
                  wheel_base=2.5, robot_radius=0.5, vehicle_l=4.0, vehicle_w=3.0, n_robots=1,
-                 device=0, K_global=None, k_offset=0, clamp_nominal=False):
+                 device=0, K_global=None, k_offset=0, clamp_nominal=False, cost_kind="path", goal=None,
+                 ctrl_w=None, soft_obs_weight=None, soft_obs_safety=None):
         self.lib = _lib.load()
         c = _lib.MppiConfig()
         self.lib.mppi_default_config(C.byref(c))
@@ -36,6 +37,16 @@ class MPPIEngine:
         c.K_global = int(K_global) if K_global else int(K)
         c.k_offset = int(k_offset)
         c.clamp_nominal = int(bool(clamp_nominal))
+        c.cost_kind = _lib.COST_KIND[cost_kind]
+        if goal is not None:
+            g = np.zeros(4); g[:len(goal)] = np.asarray(goal, float)
+            c.goal[:] = list(g)
+        if ctrl_w is not None:
+            c.ctrl_w[:] = [float(ctrl_w[0]), float(ctrl_w[1])]
+        if soft_obs_weight is not None:
+            c.soft_obs_weight = float(soft_obs_weight)
+        if soft_obs_safety is not None:
+            c.soft_obs_safety = float(soft_obs_safety)
         c.dt, c.wheel_base = float(dt), float(wheel_base)
         c.u_max[:] = [float(u_max[0]), float(u_max[1])]
         c.param_exploration, c.param_lambda, c.param_alpha = float(param_exploration), float(param_lambda), float(param_alpha)
@@ -89,6 +100,18 @@ class MPPIEngine:
     def set_obstacles(self, obstacles):
         o = np.ascontiguousarray(obstacles, dtype=np.float64).reshape(-1, 3)
         self._ck(self.lib.mppi_set_obstacles(self._h, o.ctypes.data_as(_lib._PD), o.shape[0]), "mppi_set_obstacles")
+
+    def set_goal(self, goal):
+        g = np.ascontiguousarray(goal, dtype=np.float64).reshape(-1)
+        self._ck(self.lib.mppi_set_goal(self._h, g.ctypes.data_as(_lib._PD), g.shape[0]), "mppi_set_goal")
+
+    def set_moving_obstacles(self, pos_xy, vel_xy):
+        p = np.ascontiguousarray(pos_xy, dtype=np.float64).reshape(-1, 2)
+        v = np.ascontiguousarray(vel_xy, dtype=np.float64).reshape(-1, 2)
+        if p.shape != v.shape:
+            raise ValueError("positions and velocities must both be (M,2)")
+        self._ck(self.lib.mppi_set_moving_obstacles(self._h, p.ctypes.data_as(_lib._PD), v.ctypes.data_as(_lib._PD), p.shape[0]),
+                 "mppi_set_moving_obstacles")
 
     def set_nominal(self, u):
         u = np.ascontiguousarray(u, dtype=np.float32).reshape(self.R * self.T * 2)

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define MPPI_ABI_VERSION 1
+#define MPPI_ABI_VERSION 2
 
 typedef struct mppi_handle_s *mppi_handle_t;
 
@@ -48,6 +48,12 @@ enum mppi_model {
 enum mppi_cost_mode { MPPI_COST_LAST = 0 /* :124 assigns (Q1) */, MPPI_COST_SUM = 1 /* race-car :94 */ };
 enum mppi_waypoint_mode { MPPI_WP_STRICT = 0 /* :228,:244 mutate the index (Q3) */, MPPI_WP_FROZEN = 1 };
 enum mppi_filter_kind { MPPI_FILTER_DIFFDRIVE = 0 /* :257-271 */, MPPI_FILTER_RACECAR = 1 /* race-car :228-239 */ };
+/* What a state is scored against (A9).  PATH: nearest waypoint of `ref_path` (controllers/mppi_*.py).
+ * GOAL: squared distance to `goal` plus squared wrapped bearing error, the goal-point diff-drive MPPI of
+ * test/mppi_differential_drive_obs.py:202-232 (no waypoint search, no carried index).
+ * TARGET_SOFT: quadratic error to a target pose + control effort + exponential soft penalty around MOVING circular
+ * obstacles, the running cost of test/test_mppi_diff_obs.py:14-20,44-66 (summed over the horizon). */
+enum mppi_cost_kind { MPPI_COSTKIND_PATH = 0, MPPI_COSTKIND_GOAL = 1, MPPI_COSTKIND_TARGET_SOFT = 2 };
 enum mppi_collision {
     MPPI_COLLISION_NONE = 0,
     MPPI_COLLISION_CIRCLE = 1,     /* controllers/mppi_differential_drive_obs.py:301-313 */
@@ -77,7 +83,7 @@ typedef struct {
     int32_t k_offset;         /* global index of this handle's first sample */
     int32_t clamp_nominal;    /* 1: clamp the updated nominal in place before the shift -- the side effect of the
                                  visualisation replay (quirk Q9: mppi_differential_drive.py:145-148, race-car :112-115) */
-    int32_t reserved0;
+    int32_t cost_kind;        /* enum mppi_cost_kind */
     double dt;                /* delta_t */
     double wheel_base;
     double u_max[2];          /* (max_speed, max_omega) or (max_steer_abs, max_accel_abs) */
@@ -92,6 +98,11 @@ typedef struct {
     double robot_radius;      /* 0.5 (mppi_differential_drive_obs.py:303) */
     double vehicle_l;         /* 4.0 (mppi_race_car_obstacle.py:54) */
     double vehicle_w;         /* 3.0 (mppi_race_car_obstacle.py:53) */
+    double goal[4];           /* GOAL: goal_point (x, y) (test/mppi_differential_drive_obs.py:65);
+                                 TARGET_SOFT: desired pose (x, y, yaw) (test/test_mppi_diff_obs.py:45) */
+    double ctrl_w[2];         /* TARGET_SOFT: diagonal of R (test/test_mppi_diff_obs.py:48) */
+    double soft_obs_weight;   /* TARGET_SOFT: obstacle_weight 100.0 (:57) */
+    double soft_obs_safety;   /* TARGET_SOFT: safety_distance 2.0 (:56) */
 } mppi_config_t;
 
 typedef struct {
@@ -125,6 +136,12 @@ int mppi_synchronize(mppi_handle_t h);
 int mppi_set_ref_path(mppi_handle_t h, const double *path, int32_t n, int32_t ncol);
 /* `self.obstacle_circles` (M,3) [x,y,r] (mppi_race_car_obstacle.py:57) */
 int mppi_set_obstacles(mppi_handle_t h, const double *xyr, int32_t m);
+/* `self.goal_point` (x, y) of the goal-point controller (test/mppi_differential_drive_obs.py:65), or the desired
+ * pose (x, y, yaw) of the TARGET_SOFT cost (test/test_mppi_diff_obs.py:45); n = 2 or 3 doubles */
+int mppi_set_goal(mppi_handle_t h, const double *goal, int32_t n);
+/* TARGET_SOFT: circular soft obstacles moving at constant velocity, position at horizon step t (time t*dt) =
+ * pos + vel * (t*dt)  (`get_obstacle_positions`, test/test_mppi_diff_obs.py:14-20).  pos_xy, vel_xy: (M,2) doubles */
+int mppi_set_moving_obstacles(mppi_handle_t h, const double *pos_xy, const double *vel_xy, int32_t m);
 /* `self.u_prev` (T,2) per robot (mppi_differential_drive.py:82) -- host float arrays of n_robots*T*2 */
 int mppi_set_nominal(mppi_handle_t h, const float *u);
 int mppi_get_nominal(mppi_handle_t h, float *u);

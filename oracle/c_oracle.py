@@ -20,7 +20,8 @@ class _Cfg(C.Structure):
                 ("gamma", C.c_double), ("temperature", C.c_double), ("sig_inv", C.c_double * 4),
                 ("chol", C.c_double * 4), ("stage_w", C.c_double * 4), ("term_w", C.c_double * 4),
                 ("margin", C.c_double), ("robot_radius", C.c_double), ("vehicle_l", C.c_double),
-                ("vehicle_w", C.c_double)]
+                ("vehicle_w", C.c_double), ("goal", C.c_double * 3), ("ctrl_w", C.c_double * 2),
+                ("soft_w", C.c_double), ("soft_sd", C.c_double), ("obs_vel", C.c_double * 32), ("cost_kind", C.c_int)]
 
 
 def build(force=False):
@@ -53,7 +54,13 @@ def _cfg(spec: orc.MPPISpec, path):
     c.yaw_wrap = int(spec.yaw_wrap)
     c.collision = {"none": 0, "circle": 1, "footprint": 2}[spec.collision]
     c.n_obstacles = int(spec.obstacles.shape[0])
-    c.n_path, c.path_cols = path.shape
+    c.n_path, c.path_cols = path.shape if path is not None else (0, 3)
+    c.cost_kind = {"path": 0, "goal": 1, "target_soft": 2}[spec.cost_kind]
+    c.goal[:] = list(np.asarray(spec.goal, float).reshape(-1)[:3]) + [0.0] * (3 - min(3, np.asarray(spec.goal).size))
+    c.ctrl_w[:] = list(spec.ctrl_w)
+    c.soft_w, c.soft_sd = spec.soft_w, spec.soft_sd
+    ov = np.zeros(32); ov[:spec.obs_vel.size] = np.asarray(spec.obs_vel, float).reshape(-1)
+    c.obs_vel[:] = list(ov)
     c.dt, c.wheel_base = spec.dt, spec.wheel_base
     c.u_max[:] = spec.u_max
     c.gamma, c.temperature = spec.gamma, spec.temperature
@@ -75,13 +82,15 @@ def _p(a, t):
 def costs(spec, path, U, idx, x0, eps=None, seed=0, tick=0, k_offset=0, nthreads=0, n_exploit=None):
     """Per-sample costs S (K,) float64, index after step 1, index after the tick.  For a shard of a
     larger sample set pass `k_offset` and the GLOBAL explore/exploit threshold `n_exploit` (Q6)."""
-    path = np.ascontiguousarray(path, np.float64)
+    path = np.ascontiguousarray(path, np.float64) if path is not None else None
     c = _cfg(spec, path)
+    if path is None:
+        path = np.zeros((1, 3))
     if n_exploit is not None:
         c.n_exploit = int(n_exploit)
     U = np.ascontiguousarray(U, np.float64)
     x0 = np.ascontiguousarray(x0, np.float64)
-    obs = np.ascontiguousarray(spec.obstacles, np.float64).reshape(-1, 3)
+    obs = np.ascontiguousarray(spec.obstacles, np.float64).reshape(-1, 2 if spec.cost_kind == "target_soft" else 3)
     S = np.zeros(spec.K)
     i1, i2 = C.c_int(), C.c_int()
     if eps is not None:
@@ -96,8 +105,10 @@ def costs(spec, path, U, idx, x0, eps=None, seed=0, tick=0, k_offset=0, nthreads
 
 
 def update(spec, path, U, S, eps=None, seed=0, tick=0, k_offset=0, nthreads=0):
-    path = np.ascontiguousarray(path, np.float64)
+    path = np.ascontiguousarray(path, np.float64) if path is not None else None
     c = _cfg(spec, path)
+    if path is None:
+        path = np.zeros((1, 3))
     U = np.ascontiguousarray(U, np.float64)
     S = np.ascontiguousarray(S, np.float64)
     w_eps = np.zeros((spec.T, 2))

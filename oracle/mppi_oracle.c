@@ -8,6 +8,8 @@
  *   controllers/mppi_differential_drive.py:87-289      diff-drive tick
  *   controllers/mppi_differential_drive_obs.py:301-313 circle-circle collision
  *   controllers/mppi_race_car_obstacle.py:65-274       bicycle tick, footprint collision
+ *   test/mppi_differential_drive_obs.py:202-232        goal-point cost (cost_kind 1)
+ *   test/test_mppi_diff_obs.py:14-20,44-66,113-140     target pose + soft moving obstacles (cost_kind 2)
  * Semantics are those of Appendix A of SURVEY.md; the Python restatement
  * (oracle/mppi_oracle.py) is pinned bit-for-bit to the reference classes and this file
  * is pinned to the same golden vectors (tests/test_oracle_golden.py): diff-drive to
@@ -43,6 +45,10 @@ typedef struct {
     double chol[4];     /* row-major lower Cholesky factor of Sigma (Philox mode) */
     double stage_w[4], term_w[4];
     double margin, robot_radius, vehicle_l, vehicle_w;
+    double goal[3];     /* goal point (x,y) / desired pose (x,y,yaw) */
+    double ctrl_w[2], soft_w, soft_sd;
+    double obs_vel[32]; /* cost_kind 2: (vx,vy) per obstacle; `obs` then holds (x,y) pairs */
+    int cost_kind;      /* 0 path, 1 goal point, 2 target pose + soft moving obstacles */
 } oracle_cfg_t;
 
 #define PENALTY 1.0e10
@@ -115,6 +121,33 @@ static inline double collided(const oracle_cfg_t *c, const double *obs, const do
     return 0.0;
 }
 
+/* test/mppi_differential_drive_obs.py:202-232 */
+static inline double goal_cost(const oracle_cfg_t *c, const double *obs, const double *z, const double *w) {
+    double dx = z[0] - c->goal[0], dy = z[1] - c->goal[1];
+    double dist = sqrt(dx * dx + dy * dy);
+    double a = atan2(dy, dx) - z[2];
+    a = atan2(sin(a), cos(a));
+    return w[0] * dist * dist + w[1] * a * a + collided(c, obs, z) * PENALTY;
+}
+
+/* test/test_mppi_diff_obs.py:44-66; obstacle m at obs[2m..] + vel * (t*dt) (:14-20) */
+static inline double target_soft_cost(const oracle_cfg_t *c, const double *obs, const double *z, const double *v,
+                                      int t, const double *w, int full) {
+    double ex = z[0] - c->goal[0], ey = z[1] - c->goal[1], eth = z[2] - c->goal[2];
+    double cost = w[0] * ex * ex + w[1] * ey * ey + w[2] * eth * eth;
+    if (full) {
+        cost += c->ctrl_w[0] * v[0] * v[0] + c->ctrl_w[1] * v[1] * v[1];
+        double tt = t * c->dt, soft = 0.0;
+        for (int m = 0; m < c->n_obstacles; ++m) {
+            double dx = z[0] - (obs[2 * m] + c->obs_vel[2 * m] * tt), dy = z[1] - (obs[2 * m + 1] + c->obs_vel[2 * m + 1] * tt);
+            double d = sqrt(dx * dx + dy * dy);
+            if (d < c->soft_sd) soft += exp(c->soft_sd - d);
+        }
+        cost += c->soft_w * soft;
+    }
+    return cost;
+}
+
 static inline double state_cost(const oracle_cfg_t *c, const double *path, const double *obs,
                                 const double *z, int j, const double *w) {
     const double *r = path + (size_t)j * c->path_cols;
@@ -161,7 +194,16 @@ static double sample_cost(const oracle_cfg_t *c, const double *path, const doubl
         v[0] = clampd(exploit ? U[2 * t] + e[0] : e[0], c->u_max[0]);
         v[1] = clampd(exploit ? U[2 * t + 1] + e[1] : e[1], c->u_max[1]);
         dyn_step(c, z, v);
-        if (c->cost_mode == 1 || c->waypoint_mode == 0 || t == c->T - 1) {
+        if (c->cost_kind != 0) {
+            if (c->cost_mode == 1 || t == c->T - 1) {
+                double q0 = U[2 * t] * c->sig_inv[0] + U[2 * t + 1] * c->sig_inv[2];
+                double q1 = U[2 * t] * c->sig_inv[1] + U[2 * t + 1] * c->sig_inv[3];
+                double cst = (c->cost_kind == 1 ? goal_cost(c, obs, z, c->stage_w)
+                                                : target_soft_cost(c, obs, z, v, t, c->stage_w, 1)) +
+                             c->gamma * (q0 * v[0] + q1 * v[1]);
+                if (c->cost_mode == 1) S += cst; else S = cst;
+            }
+        } else if (c->cost_mode == 1 || c->waypoint_mode == 0 || t == c->T - 1) {
             int j = nearest(c, path, *s, z[0], z[1]);
             if (c->waypoint_mode == 0) *s = j;
             if (c->cost_mode == 1 || t == c->T - 1) {
@@ -172,6 +214,8 @@ static double sample_cost(const oracle_cfg_t *c, const double *path, const doubl
             }
         }
     }
+    if (c->cost_kind == 1) return S + goal_cost(c, obs, z, c->term_w);
+    if (c->cost_kind == 2) return S + target_soft_cost(c, obs, z, NULL, 0, c->term_w, 0);
     int j = nearest(c, path, *s, z[0], z[1]);
     if (c->waypoint_mode == 0) *s = j;
     return S + state_cost(c, path, obs, z, j, c->term_w);
@@ -184,7 +228,7 @@ int mppi_oracle_costs(const oracle_cfg_t *c, const double *path, const double *o
                       const double *U, int idx, const double *x0, const float *eps,
                       uint64_t seed, uint32_t tick, uint32_t k_offset, int nthreads,
                       double *S, int *idx_step1, int *idx_after) {
-    int s0 = nearest(c, path, idx, x0[0], x0[1]);
+    int s0 = c->cost_kind == 0 ? nearest(c, path, idx, x0[0], x0[1]) : 0;
     if (idx_step1) *idx_step1 = s0;
     size_t stride = (size_t)c->T * 2;
     if (c->waypoint_mode == 0) {                    /* strict: inherently sequential */

@@ -62,6 +62,33 @@ def load_reference():
     return _loaded
 
 
+def load_reference_extras():
+    """The two MPPI scripts under the reference's test/ directory that SURVEY.md 8f row 3 names:
+      * test/mppi_differential_drive_obs.py -- the goal-point diff-drive MPPI class (in-repo numpy loops);
+      * test/test_mppi_diff_obs.py -- `dynamics`, `running_cost` (moving soft obstacles) and the
+        `MPPIWrapper._compute_rollout_costs` loop.  That script subclasses pytorch_mppi.MPPI, a package that is
+        neither vendored nor pinned by the reference; a bare stand-in class lets the module import so its OWN
+        functions can be executed -- the pytorch_mppi update rule itself stays unavailable (parity unpinned)."""
+    if "GoalMPPI" in _loaded:
+        return _loaded
+    load_reference()
+    import importlib
+    pm = types.ModuleType("pytorch_mppi")
+
+    class MPPI:                                    # stand-in base class, never instantiated
+        pass
+    pm.MPPI = MPPI
+    sys.modules.setdefault("pytorch_mppi", pm)
+    goal_mod = importlib.import_module("test.mppi_differential_drive_obs")
+    dyn_mod = importlib.import_module("test.test_mppi_diff_obs")
+    _loaded.update(dict(GoalMPPI=goal_mod.MPPIAlgorithms, GoalPlant=goal_mod.DifferentialDrive,
+                        dynobs_dynamics=dyn_mod.dynamics, dynobs_running_cost=dyn_mod.running_cost,
+                        dynobs_wrapper=dyn_mod.MPPIWrapper,
+                        dynobs_positions=dyn_mod.initial_obstacle_positions.numpy().copy(),
+                        dynobs_velocities=dyn_mod.obstacle_velocities.numpy().copy()))
+    return _loaded
+
+
 def instrument(ctrl, eps_list):
     """Make a reference controller deterministic and observable without editing it.
 

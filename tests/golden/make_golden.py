@@ -69,6 +69,62 @@ def save(name, meta, path, eps_list, rec, obstacles=None):
     print("wrote", fn, "%.1f KB" % (os.path.getsize(fn) / 1024))
 
 
+def make_extras():
+    """the goal-point class and the moving-soft-obstacle running cost."""
+    import types
+    import torch
+    ref = ref_loader.load_reference_extras()
+    # ---- goal-point diff-drive MPPI (test/mppi_differential_drive_obs.py), the script's own parameters (:396-424)
+    K, T = 160, 20
+    sigma = np.array([[0.1, 0.0], [0.0, 0.01]])
+    w = 10 * np.array([5.0, 9.0])
+    obs = np.array([[5.0, 3.0, 0.5], [3.0, 2.5, 0.5]])
+    kw = dict(delta_t=0.1, max_speed=10.0, max_omega=5.0, num_samples_K=K, num_horizons_T=T, param_exploration=0.1,
+              param_lambda=1.0, param_alpha=0.98, safety_margin_rate=0.8)
+    goal = np.array([5.0, 5.0])
+    ctrl = ref["GoalMPPI"](goal_point=goal, sigma=sigma, stage_cost_weight=w, terminal_cost_weight=w,
+                           obstacle_circles=obs, visualize_optimal_traj=False, visualze_sampled_trajs=False, **kw)
+    ctrl.prev_way_point_idx = 0                       # the class carries no waypoint index; run_ticks records one
+    rng = np.random.default_rng(11)
+    eps_list = [draw_eps(rng, sigma, K, T) for _ in range(6)]
+    # ticks 0-2 closed loop from the origin, then states next to the obstacles / the goal (bearing wrap, collisions)
+    states = [[0, 0, 0], [0.4, 0.05, 0.2], [0.9, 0.3, 0.5], [2.4, 1.8, 0.7], [4.6, 2.2, 2.9], [5.2, 4.6, -2.8]]
+    rec = run_ticks(ctrl, "prev_way_point_idx", states, eps_list)
+    save("diffdrive_goal", dict(kind="diffdrive_goal", goal=goal.tolist(), **kw), np.zeros((1, 3)), eps_list, rec,
+         obstacles=obs)
+
+    # ---- moving soft obstacles (test/test_mppi_diff_obs.py): the script's dynamics + running_cost, executed by its
+    # own MPPIWrapper._compute_rollout_costs loop on clamped controls V = clip(U + eps)
+    K, T, dt = 192, 25, 0.05
+    sig = np.diag([0.5, 0.5])
+    rng = np.random.default_rng(12)
+    recs = dict(x0=[], U0=[], V=[], S=[])
+    eps_list = []
+    u_lim = np.array([1.0, 1.0], dtype=np.float32)
+    for x0 in ([3.0, 3.0, 0.3], [4.2, 3.1, 0.9], [4.9, 5.2, 1.4], [0.0, 0.0, 0.0]):
+        eps = draw_eps(rng, sig, K, T)
+        U = (rng.normal(0, 0.3, (T, 2))).astype(np.float32)
+        V = np.clip(U[None] + eps, -u_lim, u_lim).astype(np.float32)
+        # pytorch_mppi wraps the user callbacks so they see flat (N, nx) / (N, nu) batches; same glue here
+        def dyn(st, u, t):
+            return ref["dynobs_dynamics"](st.reshape(-1, 3), u.reshape(-1, 2), t).reshape(st.shape)
+
+        def cost(st, u, t):
+            return ref["dynobs_running_cost"](st.reshape(-1, 3), u.reshape(-1, 2), t).reshape(st.shape[:-1])
+        fake = types.SimpleNamespace(nu=2, nx=3, d="cpu", dtype=torch.float32, M=1, u_scale=1.0, delta_t=dt,
+                                     state=torch.tensor(x0, dtype=torch.float32), _dynamics=dyn,
+                                     _running_cost=cost, rollout_var_discount=1.0,
+                                     rollout_var_cost=0.0, terminal_state_cost=None)
+        cost_total, _, _ = ref["dynobs_wrapper"]._compute_rollout_costs(fake, torch.from_numpy(V))
+        eps_list.append(eps)
+        recs["x0"].append(np.array(x0)); recs["U0"].append(U); recs["V"].append(V); recs["S"].append(cost_total.numpy())
+    meta = dict(kind="diffdrive_target_soft", K=K, T=T, delta_t=dt, u_max=[1.0, 1.0], target=[6.0, 6.0, 1.57],
+                Q=[30.0, 5.0, 9.0], R=[0.1, 0.1], soft_w=100.0, soft_sd=2.0, sigma=sig.tolist(),
+                obs_pos=ref["dynobs_positions"].tolist(), obs_vel=ref["dynobs_velocities"].tolist(),
+                note="S = MPPIWrapper._compute_rollout_costs (test/test_mppi_diff_obs.py:113-151) on V; float32 torch")
+    save("diffdrive_target_soft", meta, np.zeros((1, 3)), eps_list, recs)
+
+
 def main():
     ref = ref_loader.load_reference()
     path = spline_path(ref)
@@ -169,6 +225,8 @@ def main():
                              max_steer_abs=0.1, max_accel_abs=0.5, param_lambda=5.0), lp, eps_list, rec,
          obstacles=ctrl.obstacle_circles)
 
+    make_extras()
+
     # ---- literal filter operators as matrices (Q7)
     Ms = {}
     for T in (10, 12, 20, 30, 50):
@@ -181,4 +239,7 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "extras":
+        make_extras()               # only the SURVEY 8f row-3 fixtures (the others stay byte-identical)
+    else:
+        main()

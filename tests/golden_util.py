@@ -12,7 +12,9 @@ GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 DIFFDRIVE_CASES = ["diffdrive_pe1e-4", "diffdrive_pe0.05", "diffdrive_closed_loop", "diffdrive_obs"]
 RACECAR_CASES = ["racecar_default", "racecar_alpha0.9", "racecar_noobs"]
 VIZ_CASES = ["diffdrive_viz", "racecar_viz"]
-ALL_CASES = DIFFDRIVE_CASES + RACECAR_CASES
+GOAL_CASES = ["diffdrive_goal"]                 # test/mppi_differential_drive_obs.py (goal-point class)
+TARGET_SOFT_CASE = "diffdrive_target_soft"       # test/test_mppi_diff_obs.py (running cost only; no class to pin)
+ALL_CASES = DIFFDRIVE_CASES + RACECAR_CASES + GOAL_CASES
 
 
 class Golden:
@@ -24,12 +26,23 @@ class Golden:
         self.eps = z["eps"]                       # (ticks, K, T, 2) float32
         self.obstacles = z["obstacles"] if "obstacles" in z.files else None
         self.rec = {k: z[k] for k in ("x0", "U0", "idx0", "S", "w", "w_eps", "w_eps_filt",
-                                      "U_after", "u0", "idx_after", "optimal_traj", "sampled_traj") if k in z.files}
+                                      "U_after", "u0", "idx_after", "optimal_traj", "sampled_traj", "V") if k in z.files}
         self.n_ticks = self.eps.shape[0]
 
     def spec(self, **override):
         m = self.meta
-        if m["kind"].startswith("diffdrive"):
+        if m["kind"] == "diffdrive_goal":
+            s = orc.goal_spec(K=m["num_samples_K"], T=m["num_horizons_T"], goal=m["goal"], dt=m["delta_t"],
+                              max_speed=m["max_speed"], max_omega=m["max_omega"],
+                              param_exploration=m["param_exploration"], param_lambda=m["param_lambda"],
+                              param_alpha=m["param_alpha"], obstacles=self.obstacles,
+                              margin=m["safety_margin_rate"])
+        elif m["kind"] == "diffdrive_target_soft":
+            s = orc.target_soft_spec(K=m["K"], T=m["T"], target=m["target"], Q=m["Q"], R=m["R"], dt=m["delta_t"],
+                                     u_max=m["u_max"], sigma=np.array(m["sigma"]), obs_pos=m["obs_pos"],
+                                     obs_vel=m["obs_vel"], soft_w=m["soft_w"], soft_sd=m["soft_sd"],
+                                     param_exploration=0.0)
+        elif m["kind"].startswith("diffdrive"):
             s = orc.diffdrive_spec(
                 K=m["num_samples_K"], T=m["num_horizons_T"], dt=m["delta_t"],
                 max_speed=m["max_speed"], max_omega=m["max_omega"],
@@ -51,7 +64,7 @@ class Golden:
 
     def tick_inputs(self, i):
         r = self.rec
-        return dict(path=self.path, U=r["U0"][i], idx=int(r["idx0"][i]), x0=r["x0"][i], eps=self.eps[i])
+        return dict(path=self.path, U=r["U0"][i], idx=int(r["idx0"][i]) if "idx0" in r else 0, x0=r["x0"][i], eps=self.eps[i])
 
 
 def rel_err(a, b, floor=1e-12):

@@ -12,10 +12,15 @@ def engine_from_spec(spec, path, n_robots=1, device=0, **kw):
         param_lambda=spec.param_lambda, param_alpha=spec.param_alpha, temperature=spec.temperature,
         window=spec.window, cost_mode=spec.cost_mode, waypoint_mode=spec.waypoint_mode,
         filter_kind=spec.filter_kind, yaw_wrap=spec.yaw_wrap, collision=spec.collision,
-        obstacles=spec.obstacles, margin=spec.margin, wheel_base=spec.wheel_base,
+        margin=spec.margin, wheel_base=spec.wheel_base,
         robot_radius=spec.robot_radius, vehicle_l=spec.vehicle_l, vehicle_w=spec.vehicle_w,
-        n_robots=n_robots, device=device, **kw)
-    eng.set_ref_path(path)
+        n_robots=n_robots, device=device, cost_kind=spec.cost_kind, goal=spec.goal, ctrl_w=spec.ctrl_w,
+        soft_obs_weight=spec.soft_w, soft_obs_safety=spec.soft_sd,
+        **dict(dict(obstacles=None if spec.cost_kind == "target_soft" else spec.obstacles), **kw))
+    if spec.cost_kind == "path":
+        eng.set_ref_path(path)
+    if spec.cost_kind == "target_soft":
+        eng.set_moving_obstacles(spec.obstacles, spec.obs_vel)
     return eng
 
 

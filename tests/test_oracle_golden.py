@@ -166,3 +166,25 @@ def test_visualisation_outputs_and_nominal_clamp(name):
         assert np.array_equal(o["sampled_traj"], g.rec["sampled_traj"][i])
     lim = np.asarray(sp.u_max)
     assert np.all(np.abs(g.rec["U_after"]) <= lim + 1e-6) and np.any(np.abs(g.rec["U_after"]) >= lim - 1e-6)
+
+
+def test_target_soft_running_cost_matches_reference_functions():
+    """the moving-soft-obstacle running cost.  The golden S is what the reference's own
+    `dynamics` + `running_cost` produce inside its `MPPIWrapper._compute_rollout_costs` loop
+    (test/test_mppi_diff_obs.py:28-66,113-151, float32 torch) for the stored clamped controls; the three
+    restatements must reproduce it (FP32 summation over 25 steps: 2e-6 relative)."""
+    from golden_util import TARGET_SOFT_CASE
+    g = Golden(TARGET_SOFT_CASE)
+    sp = g.spec()
+    for i in range(g.n_ticks):
+        inp = g.tick_inputs(i)
+        V, _ = orc.rollout_states(sp, np.asarray(inp["U"], np.float32), np.asarray(inp["x0"], np.float32), inp["eps"])
+        assert np.array_equal(V, g.rec["V"][i])                      # same clamped controls as the harness fed
+        S_vec, _, _ = orc.costs_vec(sp, None, inp["U"], 0, inp["x0"], inp["eps"])
+        assert rel_err(S_vec, g.rec["S"][i]) <= 2e-6, i
+        S_c, _, _ = co.costs(sp, None, inp["U"], 0, inp["x0"], inp["eps"])
+        assert rel_err(S_c, g.rec["S"][i]) <= 2e-6, i
+    sp_small = g.spec(K=24)
+    inp = g.tick_inputs(0)
+    a = orc.tick_loops(sp_small, None, inp["U"], 0, inp["x0"], inp["eps"][:24])
+    assert rel_err(a["S"], g.rec["S"][0][:24]) <= 2e-6

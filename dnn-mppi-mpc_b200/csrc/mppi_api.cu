@@ -77,6 +77,12 @@ struct mppi_handle_s {
     unsigned p2p_seq = 0;
     // MLP dynamics
     MlpState *mlp = nullptr;
+    // top-N viewer: per-sample costs of the last tick and their sorted order
+    bool keep_costs = false;
+    float *d_Sc = nullptr, *d_Ssorted = nullptr;
+    int *d_sorted_idx = nullptr, *d_iota = nullptr;
+    void *d_sort_temp = nullptr;
+    size_t sort_temp_bytes = 0;
     // timing / bookkeeping
     bool timing = false;
     cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
@@ -311,6 +317,7 @@ int mppi_destroy(mppi_handle_t h) {
         for (int p = 0; p < h->world; ++p)
             if (p != h->rank && h->peer_buf[p]) cudaIpcCloseMemHandle(h->peer_buf[p]);
     cudaFree(h->d_xchg);
+    cudaFree(h->d_Sc); cudaFree(h->d_Ssorted); cudaFree(h->d_sorted_idx); cudaFree(h->d_iota); cudaFree(h->d_sort_temp);
     if (h->mlp) mlp_destroy(h->mlp);
     cudaFree(h->d_path); cudaFree(h->d_U); cudaFree(h->d_M); cudaFree(h->d_S); cudaFree(h->d_part);
     cudaFree(h->d_out); cudaFree(h->d_idx); cudaFree(h->d_NC); cudaFree(h->d_ticket); cudaFree(h->d_first);
@@ -447,6 +454,7 @@ int mppi_get_stats(mppi_handle_t h, mppi_stats_t *out) {
     CK(h, cudaStreamSynchronize(h->stream));
     out->rho = hdr[3]; std::memcpy(&out->min_collisions, &hdr[4], 4);
     out->eta = hdr[5]; out->ess = hdr[6]; std::memcpy(&out->idx, &hdr[2], 4);
+    out->u_first[0] = hdr[8]; out->u_first[1] = hdr[9];
     return MPPI_OK;
 }
 
@@ -565,7 +573,7 @@ static int step_common(mppi_handle_t h, const double *x0, const float *d_eps, ui
         if (rc2 != MPPI_OK) return rc2;
     } else if (h->strict) {
         int idx_after = 0;
-        int rc = strict_costs(h, x0, d_eps, nullptr, &idx_after);
+        int rc = strict_costs(h, x0, d_eps, h->keep_costs ? h->d_Sc : nullptr, &idx_after);
         if (rc != MPPI_OK) return rc;
         if (h->timing) CK(h, cudaEventRecord(h->ev[1], h->stream));
         TickArgs a = h->args;
@@ -576,8 +584,8 @@ static int step_common(mppi_handle_t h, const double *x0, const float *d_eps, ui
         if (rc != MPPI_OK) return rc;
     } else {
         TickArgs a = h->args;
-        a.eps = d_eps; a.S = nullptr;
-        a.flags = F_UPDATE;
+        a.eps = d_eps; a.S = h->keep_costs ? h->d_Sc : nullptr;
+        a.flags = F_UPDATE | (h->keep_costs ? F_WRITE_S : 0);
         if (h->timing) CK(h, cudaEventRecord(h->ev[1], h->stream));
         int rc = launch_update(h, a, d_eps != nullptr);
         if (rc != MPPI_OK) return rc;
@@ -682,8 +690,49 @@ int mppi_get_trajectories(mppi_handle_t h, const double *x0, const float *d_eps,
     a.eps = d_eps;
     const int nx = h->nx, T = h->cfg.T;
     if (optimal_out && !h->d_opt) CK(h, cudaMalloc(&h->d_opt, sizeof(float) * MPPI_MAX_T * 4));
-    CK(h, mppi_launch_traj(a, h->cfg.model, h->d_out, optimal_out ? h->d_opt : nullptr, d_sampled_out, h->stream));
+    CK(h, mppi_launch_traj(a, h->cfg.model, h->d_out, optimal_out ? h->d_opt : nullptr, d_sampled_out, nullptr, 0, 1, h->stream));
     h->tm.launches++;
+    if (optimal_out) CK(h, cudaMemcpyAsync(optimal_out, h->d_opt, sizeof(float) * T * nx, cudaMemcpyDeviceToHost, h->stream));
+    CK(h, cudaStreamSynchronize(h->stream));
+    return MPPI_OK;
+}
+
+int mppi_set_keep_costs(mppi_handle_t h, int32_t on) {
+    if (!h) return MPPI_E_BADARG;
+    if (h->cfg.n_robots != 1) return fail(h, MPPI_E_UNSUPPORTED, "per-sample costs are kept for single-robot handles");
+    CK(h, cudaSetDevice(h->cfg.device));
+    if (on && !h->d_Sc) {
+        const int K = h->cfg.K;
+        CK(h, cudaMalloc(&h->d_Sc, sizeof(float) * K));
+        CK(h, cudaMalloc(&h->d_Ssorted, sizeof(float) * K));
+        CK(h, cudaMalloc(&h->d_sorted_idx, sizeof(int) * K));
+        CK(h, cudaMalloc(&h->d_iota, sizeof(int) * K));
+        h->sort_temp_bytes = mppi_sort_costs_temp_bytes(K);
+        CK(h, cudaMalloc(&h->d_sort_temp, h->sort_temp_bytes ? h->sort_temp_bytes : 16));
+    }
+    h->keep_costs = on != 0;
+    return MPPI_OK;
+}
+
+int mppi_get_top_trajectories(mppi_handle_t h, const double *x0, const float *d_eps, uint64_t seed, uint64_t tick,
+                              int32_t n_top, int32_t index_shift, float *optimal_out, float *d_traj_out,
+                              int32_t *d_idx_out, float *d_cost_out) {
+    if (!h || !x0 || n_top < 1 || n_top > h->cfg.K || !d_traj_out || index_shift < 0 || index_shift > 1) return MPPI_E_BADARG;
+    if (h->cfg.n_robots != 1 || h->mlp) return fail(h, MPPI_E_UNSUPPORTED, "trajectories: single-robot analytic models only");
+    if (!h->keep_costs || !h->d_Sc) return fail(h, MPPI_E_STATE, "call mppi_set_keep_costs(h, 1) before the tick");
+    CK(h, cudaSetDevice(h->cfg.device));
+    set_x0(h, x0);
+    set_seed(h, seed, tick);
+    TickArgs a = h->args;
+    a.eps = d_eps;
+    const int nx = h->nx, T = h->cfg.T;
+    CK(h, mppi_sort_costs(h->d_Sc, h->cfg.K, h->d_Ssorted, h->d_sorted_idx, h->d_iota, h->d_sort_temp, h->sort_temp_bytes, h->stream));
+    if (optimal_out && !h->d_opt) CK(h, cudaMalloc(&h->d_opt, sizeof(float) * MPPI_MAX_T * 4));
+    CK(h, mppi_launch_traj(a, h->cfg.model, h->d_out, optimal_out ? h->d_opt : nullptr, d_traj_out, h->d_sorted_idx, n_top,
+                           index_shift, h->stream));
+    h->tm.launches += 3;
+    if (d_idx_out) CK(h, cudaMemcpyAsync(d_idx_out, h->d_sorted_idx, sizeof(int) * n_top, cudaMemcpyDeviceToDevice, h->stream));
+    if (d_cost_out) CK(h, cudaMemcpyAsync(d_cost_out, h->d_Ssorted, sizeof(float) * n_top, cudaMemcpyDeviceToDevice, h->stream));
     if (optimal_out) CK(h, cudaMemcpyAsync(optimal_out, h->d_opt, sizeof(float) * T * nx, cudaMemcpyDeviceToHost, h->stream));
     CK(h, cudaStreamSynchronize(h->stream));
     return MPPI_OK;

@@ -16,7 +16,7 @@
 #endif
 #define MPPI_PENALTY 1.0e10f           // mppi_race_car_obstacle.py:157
 #define MPPI_SENTINEL 1.0e18f          // padded window entries: distance^2 = 1e36, never the minimum
-#define MPPI_OUT_HDR 8
+#define MPPI_OUT_HDR 10                // u0 (post-shift, Q8), idx, rho, ncoll, eta, ess, p2p flag, first row of the PRE-shift nominal
 #define MPPI_OUT_STRIDE (MPPI_OUT_HDR + 8 * MPPI_MAX_T)   // header, U shifted, w_eps, U pre-shift, U before the tick
 #define MPPI_OUT_UPRE (MPPI_OUT_HDR + 4 * MPPI_MAX_T)
 #define MPPI_OUT_UOLD (MPPI_OUT_HDR + 6 * MPPI_MAX_T)

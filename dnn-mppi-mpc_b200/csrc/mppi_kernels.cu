@@ -134,6 +134,7 @@ __device__ void finalize_tick(const TickArgs &a, int robot, int idx_new, MergeSm
         hdr[0] = u0x; hdr[1] = u0y; hdr[2] = __int_as_float(idx_new);
         hdr[3] = ms.col[1]; hdr[4] = ms.col[0]; hdr[5] = eta;
         hdr[6] = eta * eta / ms.col[3]; hdr[7] = (a.flags & F_P2P) ? out[7] : 0.f;     // sticky peer-timeout flag
+        hdr[8] = ms.upre[0]; hdr[9] = ms.upre[1];       // the textbook MPPI output: row 0 of the updated nominal before the shift
 #pragma unroll
         for (int i = 0; i < MPPI_OUT_HDR; ++i) { out[i] = hdr[i]; if (oh) oh[i] = hdr[i]; }
         if (a.u0_out) { a.u0_out[2 * robot] = u0x; a.u0_out[2 * robot + 1] = u0y; }
@@ -445,22 +446,27 @@ __global__ void __launch_bounds__(MPPI_BLOCK) mppi_merge_kernel(const __grid_con
 
 // A16: visualisation replays of the last tick.  Thread k < K replays sample k's clamped controls, thread K the
 // updated nominal; both index the controls with t-1 (the last row first), as the reference does.
+// With a selection list (`sel`, n_sel entries: the top-N viewer of test/test_mppi_diff_obs.py:102-110) row i of samp_out
+// replays sample sel[i]; `shift` = 1 indexes the controls with t-1 (the reference classes), 0 with t (that script, :108).
 template <int MODEL>
 __global__ void mppi_traj_kernel(const __grid_constant__ TickArgs a, const float *__restrict__ rec,
-                                 float *__restrict__ opt_out, float *__restrict__ samp_out) {
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k > a.K) return;
-    const bool nominal = k == a.K;
+                                 float *__restrict__ opt_out, float *__restrict__ samp_out,
+                                 const int *__restrict__ sel, int n_sel, int shift) {
+    const int row = blockIdx.x * blockDim.x + threadIdx.x;
+    const int n_rows = sel ? n_sel : a.K;
+    if (row > n_rows) return;
+    const bool nominal = row == n_rows;
     if (nominal ? opt_out == nullptr : samp_out == nullptr) return;
+    const int k = nominal ? a.K : (sel ? sel[row] : row);
     constexpr int NX = MODEL == MPPI_MODEL_BICYCLE ? 4 : 3;
     const int T = a.T;
     const float *upre = rec + MPPI_OUT_UPRE, *uold = rec + MPPI_OUT_UOLD;
     const uint32_t kg = (uint32_t)(a.k_offset + k);
     const bool exploit = (int)kg < a.n_exploit;
     float z[4] = {a.x0[0], a.x0[1], a.x0[2], a.x0[3]};
-    float *dst = nominal ? opt_out : samp_out + (size_t)k * T * NX;
+    float *dst = nominal ? opt_out : samp_out + (size_t)row * T * NX;
     for (int t = 0; t < T; ++t) {
-        const int tc = (t + T - 1) % T;                                   // u[t-1] with Python's negative index
+        const int tc = shift ? (t + T - 1) % T : t;                       // u[t-1] with Python's negative index
         float v0, v1;
         if (nominal) {
             v0 = clampf(upre[2 * tc], a.umax0); v1 = clampf(upre[2 * tc + 1], a.umax1);
@@ -684,10 +690,11 @@ cudaError_t mppi_launch_merge(const TickArgs &a, const float *triples, int G, cu
     return cudaGetLastError();
 }
 
-cudaError_t mppi_launch_traj(const TickArgs &a, int model, const float *rec, float *d_opt, float *d_samp, cudaStream_t st) {
-    const int n = a.K + 1;
-    if (model == MPPI_MODEL_BICYCLE) mppi_traj_kernel<MPPI_MODEL_BICYCLE><<<(n + 127) / 128, 128, 0, st>>>(a, rec, d_opt, d_samp);
-    else mppi_traj_kernel<MPPI_MODEL_DIFFDRIVE><<<(n + 127) / 128, 128, 0, st>>>(a, rec, d_opt, d_samp);
+cudaError_t mppi_launch_traj(const TickArgs &a, int model, const float *rec, float *d_opt, float *d_samp,
+                             const int *d_sel, int n_sel, int shift, cudaStream_t st) {
+    const int n = (d_sel ? n_sel : a.K) + 1;
+    if (model == MPPI_MODEL_BICYCLE) mppi_traj_kernel<MPPI_MODEL_BICYCLE><<<(n + 127) / 128, 128, 0, st>>>(a, rec, d_opt, d_samp, d_sel, n_sel, shift);
+    else mppi_traj_kernel<MPPI_MODEL_DIFFDRIVE><<<(n + 127) / 128, 128, 0, st>>>(a, rec, d_opt, d_samp, d_sel, n_sel, shift);
     return cudaGetLastError();
 }
 

@@ -8,6 +8,11 @@ cudaError_t mppi_launch_strict(const TickArgs &a, int model, int coll, bool sum,
                                const int *bp_s, int nbp, int k_first, unsigned check_from,
                                unsigned long long *first_change, cudaStream_t st);
 cudaError_t mppi_launch_merge(const TickArgs &a, const float *triples, int G, cudaStream_t st);
-cudaError_t mppi_launch_traj(const TickArgs &a, int model, const float *rec, float *d_opt, float *d_samp, cudaStream_t st);
+cudaError_t mppi_launch_traj(const TickArgs &a, int model, const float *rec, float *d_opt, float *d_samp,
+                             const int *d_sel, int n_sel, int shift, cudaStream_t st);
+// mppi_topn.cu: ascending (cost, sample index) order of K costs -- np.argsort(S) of the viewers
+size_t mppi_sort_costs_temp_bytes(int K);
+cudaError_t mppi_sort_costs(const float *d_S, int K, float *d_S_sorted, int *d_idx_sorted, int *d_iota, void *d_temp,
+                            size_t temp_bytes, cudaStream_t st);
 cudaError_t mppi_launch_noise(const TickArgs &a, float *d_out, int robot, cudaStream_t st);
 int mppi_tick_occupancy(int model, int coll, int cost_kind, bool sum, bool inj, int window, int T, bool stash);

@@ -42,6 +42,16 @@ class ControllerBase:
             self.ref_path = ref_path
         self._u_cache = np.zeros((self.T, self.dim_u), dtype=self._out_dtype)
         self._viz_warned = False
+        self._top_n = None
+        self.last_top_idx = self.last_top_cost = None
+
+    def set_sampled_top_n(self, n_top):
+        """Return only the `n_top` lowest-cost sampled trajectories, in ascending cost order, as the 4th element of the
+        tick tuple (None restores the reference's (K,T,nx) array).  The reference's viewers draw the samples in
+        `np.argsort(S)` order (mppi_differential_drive.py:153) and test/test_mppi_diff_obs.py:102 keeps the top
+        max(10, K/10); at K = 1M the full array is 600 MB per tick."""
+        self._top_n = None if n_top is None else max(1, min(int(n_top), self._K_local))
+        self._engine.set_keep_costs(self._top_n is not None)
 
     # -- reference attributes ----------------------------------------------------------------
     @property
@@ -82,7 +92,20 @@ class ControllerBase:
         u = self._u_cache
         optimal_traj = np.zeros((self.T, self.dim_x), dtype=self._out_dtype)
         want_opt, want_samp = self._viz_gates()
-        if (want_opt or want_samp) and self._world == 1 and self._engine.model != "diffdrive_mlp":
+        if (want_opt or want_samp) and self._top_n and self._engine.model != "diffdrive_mlp":
+            import torch
+            dev = "cuda:%d" % self._engine.device
+            d_samp = torch.empty(self._top_n, self.T, self.dim_x, dtype=torch.float32, device=dev)
+            d_idx = torch.empty(self._top_n, dtype=torch.int32, device=dev)
+            d_cost = torch.empty(self._top_n, dtype=torch.float32, device=dev)
+            opt = self._engine.top_trajectories(x, d_samp, self._top_n, d_idx, d_cost, want_opt, 1, d_eps, self.seed,
+                                                self._tick - 1)
+            if want_opt:
+                optimal_traj = opt.astype(self._out_dtype)
+            sampled = d_samp.cpu().numpy().astype(self._out_dtype)
+            self.last_top_idx = d_idx.cpu().numpy() + self._rank * self._K_local
+            self.last_top_cost = d_cost.cpu().numpy()
+        elif (want_opt or want_samp) and self._world == 1 and self._engine.model != "diffdrive_mlp":
             import torch
             d_samp = torch.empty(self.K, self.T, self.dim_x, dtype=torch.float32,
                                  device="cuda:%d" % self._engine.device) if want_samp else None

@@ -35,7 +35,7 @@ class MppiTimings(C.Structure):
 
 class MppiStats(C.Structure):
     _fields_ = [("rho", C.c_float), ("eta", C.c_float), ("ess", C.c_float),
-                ("min_collisions", C.c_int32), ("idx", C.c_int32)]
+                ("min_collisions", C.c_int32), ("idx", C.c_int32), ("u_first", C.c_float * 2)]
 
 
 class MppiError(RuntimeError):
@@ -69,6 +69,9 @@ SYMBOLS = {
     "mppi_generate_noise": (C.c_int, [_H, C.c_uint64, C.c_uint64, C.c_void_p]),
     "mppi_generate_noise_robot": (C.c_int, [_H, C.c_uint64, C.c_uint64, C.c_int32, C.c_void_p]),
     "mppi_get_trajectories": (C.c_int, [_H, _PD, C.c_void_p, C.c_uint64, C.c_uint64, _PF, C.c_void_p]),
+    "mppi_set_keep_costs": (C.c_int, [_H, C.c_int32]),
+    "mppi_get_top_trajectories": (C.c_int, [_H, _PD, C.c_void_p, C.c_uint64, C.c_uint64, C.c_int32, C.c_int32, _PF,
+                                            C.c_void_p, C.c_void_p, C.c_void_p]),
     "mppi_get_stats": (C.c_int, [_H, C.POINTER(MppiStats)]),
     "mppi_run_closed_loop": (C.c_int, [_H, _PD, C.c_int32, C.c_uint64, C.c_uint64, C.c_int32, _PF, _PF]),
     "mppi_step_batched": (C.c_int, [_H, C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p]),

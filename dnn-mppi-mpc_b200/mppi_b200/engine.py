@@ -178,6 +178,20 @@ class MPPIEngine:
                  "mppi_get_trajectories")
         return opt
 
+    def set_keep_costs(self, on=True):
+        self._ck(self.lib.mppi_set_keep_costs(self._h, int(on)), "mppi_set_keep_costs")
+
+    def top_trajectories(self, x0, d_traj, n_top, d_idx=None, d_cost=None, want_optimal=False, index_shift=1,
+                         d_eps=None, seed=0, tick=0):
+        """The n_top lowest-cost samples of the tick just stepped, replayed into `d_traj` (n_top,T,nx) in ascending cost
+        order; needs set_keep_costs(True) before the step.  Returns the (T,nx) optimal replay or None."""
+        self._load_x0(x0)
+        opt = np.zeros((self.T, self.nx), dtype=np.float32) if want_optimal else None
+        self._ck(self.lib.mppi_get_top_trajectories(self._h, self._x0, _dptr(d_eps), seed, tick, int(n_top), int(index_shift),
+                                                    opt.ctypes.data_as(_lib._PF) if want_optimal else None,
+                                                    _dptr(d_traj), _dptr(d_idx), _dptr(d_cost)), "mppi_get_top_trajectories")
+        return opt
+
     def generate_noise(self, d_out, seed=0, tick=0, robot=0):
         self._ck(self.lib.mppi_generate_noise_robot(self._h, seed, tick, robot, _dptr(d_out)), "mppi_generate_noise")
 
@@ -198,7 +212,8 @@ class MPPIEngine:
     def stats(self):
         s = _lib.MppiStats()
         self._ck(self.lib.mppi_get_stats(self._h, C.byref(s)), "mppi_get_stats")
-        return dict(rho=s.rho, eta=s.eta, ess=s.ess, min_collisions=s.min_collisions, idx=s.idx)
+        return dict(rho=s.rho, eta=s.eta, ess=s.ess, min_collisions=s.min_collisions, idx=s.idx,
+                    u_first=np.array([s.u_first[0], s.u_first[1]], dtype=np.float32))
 
     def set_timing(self, on=True):
         self._ck(self.lib.mppi_set_timing(self._h, int(on)), "mppi_set_timing")

@@ -119,6 +119,9 @@ typedef struct {
     float ess;                /* effective sample size (sum w)^2 / sum w^2 */
     int32_t min_collisions;   /* fewest collided evaluations among the samples */
     int32_t idx;              /* carried waypoint index after the tick */
+    float u_first[2];         /* row 0 of the updated nominal BEFORE the shift: what a textbook MPPI (pytorch_mppi's
+                                 `command`, test/test_mppi_diff_obs.py:80) applies; the reference classes return the
+                                 post-shift row 0 instead (quirk Q8), which is what mppi_step hands back */
 } mppi_stats_t;
 
 /* lifecycle -- replaces MPPIAlgorithms.__init__ (controllers/mppi_differential_drive.py:44-85)
@@ -182,6 +185,22 @@ int mppi_get_stats(mppi_handle_t h, mppi_stats_t *out);   /* robot 0 */
  *   optimal_out  host, T*nx floats, or NULL;   d_sampled_out  device, K*T*nx floats, or NULL */
 int mppi_get_trajectories(mppi_handle_t h, const double *x0, const float *d_eps, uint64_t seed, uint64_t tick,
                           float *optimal_out, float *d_sampled_out);
+
+/* Top-N viewer: the n_top lowest-cost samples of the LAST tick in ascending cost order
+ * (`sorted_idx = np.argsort(S)`, controllers/mppi_differential_drive.py:153; `torch.argsort(self.cost_total)
+ * [:num_top_samples]` with num_top_samples = max(10, K/10), test/test_mppi_diff_obs.py:102-104) replayed from x0,
+ * instead of all K trajectories (600 MB at K = 1M, H = 50).  mppi_set_keep_costs(h, 1) makes every following tick
+ * keep its per-sample costs (4 bytes per sample); call mppi_get_top_trajectories right after mppi_step with the same
+ * x0 / d_eps / seed / tick.
+ *   index_shift   1: controls indexed t-1, last row first, like the reference classes (A16);
+ *                 0: controls indexed t (test/test_mppi_diff_obs.py:94,108)
+ *   optimal_out   host T*nx floats, replay of the updated pre-shift nominal, or NULL
+ *   d_traj_out    device (n_top, T, nx) float32;  d_idx_out device n_top int32 sample indices or NULL;
+ *   d_cost_out    device n_top float32 costs (smooth + 1e10 * collided evaluations) or NULL */
+int mppi_set_keep_costs(mppi_handle_t h, int32_t enabled);
+int mppi_get_top_trajectories(mppi_handle_t h, const double *x0, const float *d_eps, uint64_t seed, uint64_t tick,
+                              int32_t n_top, int32_t index_shift, float *optimal_out, float *d_traj_out,
+                              int32_t *d_idx_out, float *d_cost_out);
 
 /* On-device closed loop (A17): n_ticks control ticks with the plant step applied on the device between them, no
  * host round trip per tick.  plant 0 = DifferentialDrive.update_state (controllers/mppi_differential_drive.py:33-40,

@@ -161,3 +161,74 @@ def test_cost_kind_argument_checks():
     sp.cost_kind = "goal"
     with pytest.raises(MppiError):
         engine_from_spec(sp, None)                         # goal cost is a diff-drive cost
+
+
+@pytest.mark.parametrize("name", ["diffdrive_viz", "racecar_viz"])
+def test_top_n_trajectories_match_reference_replays(name):
+    """the n lowest-cost samples in np.argsort(S) order.  The golden holds the reference class's
+    own (K,T,nx) replay array (t-1 indexing) and its costs, so row i of the top-N output must be the reference's
+    replay of sample argsort(S)[i]."""
+    from golden_util import Golden as G
+    g = G(name)
+    sp = g.spec()
+    eng = engine_from_spec(sp, g.path, clamp_nominal=True)
+    eng.set_keep_costs(True)
+    n_top = 7
+    nx = sp.nx
+    for i in range(g.n_ticks):
+        eng.set_nominal(g.rec["U0"][i])
+        eng.set_waypoint_idx(int(g.rec["idx0"][i]))
+        d_eps = _dev(g.eps[i])
+        eng.step(g.rec["x0"][i], d_eps)
+        traj = torch.zeros(n_top, sp.T, nx, dtype=torch.float32, device="cuda")
+        idx = torch.zeros(n_top, dtype=torch.int32, device="cuda")
+        cost = torch.zeros(n_top, dtype=torch.float32, device="cuda")
+        opt = eng.top_trajectories(g.rec["x0"][i], traj, n_top, idx, cost, want_optimal=True, index_shift=1, d_eps=d_eps)
+        Sref = g.rec["S"][i].astype(np.float64)
+        order = np.argsort(Sref, kind="stable")[:n_top]
+        got = idx.cpu().numpy()
+        c = cost.cpu().numpy()
+        assert np.all(np.diff(c) >= 0)
+        # same samples unless two costs are closer than the FP32 cost tolerance
+        gap_ok = np.abs(Sref[got] - Sref[order]) <= 2e-5 * np.abs(Sref[order]) + 1e-6
+        assert np.all(gap_ok), (name, i, got, order)
+        assert np.max(np.abs(c - Sref[got])) <= 2e-5 * np.max(np.abs(Sref[order])) + 1e-6
+        assert np.max(np.abs(traj.cpu().numpy() - g.rec["sampled_traj"][i][got])) <= 2e-5, (name, i)
+        assert np.max(np.abs(opt - g.rec["optimal_traj"][i])) <= 5e-5
+    eng.close()
+
+
+def test_dynamic_obstacle_controller_surface():
+    """MPPIDynamicObstacles: command() = row 0 of the updated nominal before the shift; get_trajectories() = optimal
+    rollout + the top max(10, K/10) samples by cost, controls indexed t (test/test_mppi_diff_obs.py:88-111)."""
+    from mppi_b200.mppi_diff_obs_dynamic import MPPIDynamicObstacles
+    g = Golden(TARGET_SOFT_CASE)
+    sp = g.spec()
+    m = g.meta
+    ctrl = MPPIDynamicObstacles(noise_sigma=np.array(m["sigma"]), num_samples=m["K"], horizon=m["T"], lambda_=sp.temperature,
+                                u_min=[-1.0, -1.0], u_max=[1.0, 1.0], delta_t=m["delta_t"], target=m["target"], Q=m["Q"],
+                                R=m["R"], obstacle_positions=m["obs_pos"], obstacle_velocities=m["obs_vel"],
+                                safety_distance=m["soft_sd"], obstacle_weight=m["soft_w"])
+    i = 1
+    ctrl.u_prev = g.rec["U0"][i]
+    u = ctrl.command(g.rec["x0"][i], noise=g.eps[i])
+    o = co.tick(sp, None, g.rec["U0"][i], 0, g.rec["x0"][i], g.eps[i])
+    Upre = np.concatenate([o["U_after"][:1] * 0, o["U_after"][:-1]])        # U_after is U_pre shifted up by one row
+    U_pre0 = g.rec["U0"][i][0] + (orc.filter_matrix(sp.T, "racecar") @ o["w_eps"])[0]
+    assert np.max(np.abs(u - U_pre0)) <= U_ATOL
+    assert np.max(np.abs(ctrl.u_prev - o["U_after"])) <= U_ATOL
+    opt, samp = ctrl.get_trajectories()
+    n_top = max(10, sp.K // 10)
+    assert samp.shape == (n_top, sp.T, 3) and opt.shape == (sp.T, 3)
+    order = np.argsort(o["S"], kind="stable")[:n_top]
+    got = ctrl.last_top_idx
+    assert np.all(np.abs(o["S"][got] - o["S"][order]) <= 2e-5 * np.abs(o["S"][order]) + 1e-6)
+    V, X = orc.rollout_states(g.spec(dtype=np.float64), g.rec["U0"][i].astype(np.float64), g.rec["x0"][i], g.eps[i].astype(np.float64))
+    assert np.max(np.abs(samp - X[got])) <= 2e-5
+    # optimal rollout: the clamped updated nominal applied with index t
+    Upre_full = np.vstack([U_pre0[None], o["U_after"][:-1]])
+    sp1 = g.spec(dtype=np.float64, K=1)
+    _, Xo = orc.rollout_states(sp1, np.zeros((sp.T, 2)), g.rec["x0"][i], np.clip(Upre_full, -1, 1)[None])
+    assert np.max(np.abs(opt - Xo[0])) <= 5e-5
+    with pytest.raises(ValueError):
+        MPPIDynamicObstacles(noise_sigma=np.eye(2), num_samples=64, horizon=20, lambda_=1.0, u_min=[-1, -2], u_max=[1, 1])

@@ -22,6 +22,11 @@
 //     contract with the 512x3 output layer in FP32 registers -- the output layer never touches memory;
 //   * the unicycle step, nearest-waypoint search and cost run in the same epilogue threads with the
 //     state in registers across the horizon.
+// Learned residuals with FIVE inputs (state + control, the shape of the reference's trained saved_models/mlp_diff*.pth:
+// simulation/bullet_differential_drive_dnn.py:37-60, train/train_diff_mlp.py:13-36) run through the same kernel
+// (template NIN = 5): the folded first layer takes (x, y, yaw, v, w), so the owner thread generates the control of step
+// t+1 while the GEMM of step t runs and publishes it with the state.  StandardScaler pre/post-processing
+// (test/test_diff_dyna_eval.py:54-56) is folded into the first / last layer on the host.
 // Warp roles: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2..17 = 16 compute
 // warps (four per TMEM lane quarter; group g = (warp-2)/4 takes 32 columns of every 128-column part of the
 // activations and of every accumulator quarter, so MMA start and epilogue tail are both short).
@@ -57,9 +62,11 @@ constexpr int MLP_THREADS = 64 + N_COMPUTE;
 
 struct MlpSmem {                          // after the 1024-aligned A / B regions
     float4 w01[HID];                      // (W01[j][0], W01[j][1], W01[j][2], b01[j])
+    __align__(16) float2 w01u[HID];       // NIN = 5: (W01[j][3], W01[j][4]) -- the control columns
+    float xw[TILE_M];                     // NIN = 5: second control component of each row (the first rides in xs.w)
     float4 w3[HID];                       // (b2[j], W3[0][j], W3[1][j], W3[2][j])
     float4 xs[TILE_M];                    // current state of each row for the partner thread
-    float4 res[N_GROUPS - 1][TILE_M];     // partners' partial output-layer sums
+    float res[N_GROUPS - 1][3][TILE_M];   // partners' partial output-layer sums (SoA: 4.5 KB instead of 6 KB as float4)
     unsigned long long b_full[B_STAGES], b_empty[B_STAGES], a_ready[N_QUARTERS], d_full[2], d_empty[2];
     unsigned long long key[8];
     uint32_t tmem_base;
@@ -67,6 +74,7 @@ struct MlpSmem {                          // after the 1024-aligned A / B region
 };
 
 constexpr size_t MLP_DYN_SMEM = B_STAGES * B_TILE_BYTES + sizeof(TickSmem) + sizeof(MlpSmem);
+static_assert(MLP_DYN_SMEM + 1024 <= 232448, "K3 shared memory exceeds the 227 KB per-CTA limit of sm_100a");
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -163,10 +171,11 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
+template <int NIN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(MLP_THREADS, 1)
 mppi_mlp_rollout_kernel(const __grid_constant__ TickArgs a, const __grid_constant__ CUtensorMap w2_map,
-                        const float4 *__restrict__ g_w01, const float4 *__restrict__ g_w3, const float *__restrict__ g_b3,
-                        float *__restrict__ S_out, int n_tiles) {
+                        const float4 *__restrict__ g_w01, const float2 *__restrict__ g_w01u, const float4 *__restrict__ g_w3,
+                        const float *__restrict__ g_b3, float *__restrict__ S_out, int n_tiles) {
     // 1024-byte alignment is what SWIZZLE_128B needs; keeping every pointer derived from this symbol (no
     // integer round-trips) lets the compiler emit LDS/STS instead of generic LD/ST
     extern __shared__ __align__(1024) unsigned char dyn[];
@@ -183,7 +192,10 @@ mppi_mlp_rollout_kernel(const __grid_constant__ TickArgs a, const __grid_constan
     const int my_tiles = (n_pairs - cluster_id + n_clusters - 1) / n_clusters;
 
     // ---- one-time setup: constants, barriers, TMEM, step-1 index + window (same rule as the tick kernel)
-    for (int j = tid; j < HID; j += MLP_THREADS) { ms.w01[j] = g_w01[j]; ms.w3[j] = g_w3[j]; }
+    for (int j = tid; j < HID; j += MLP_THREADS) {
+        ms.w01[j] = g_w01[j]; ms.w3[j] = g_w3[j];
+        if (NIN == 5) ms.w01u[j] = g_w01u[j];
+    }
     if (tid < 3) ms.b3[tid] = g_b3[tid];
     if (tid < 4) sm.x0[tid] = a.x0[tid];
     if (tid == 0) {
@@ -312,14 +324,29 @@ mppi_mlp_rollout_kernel(const __grid_constant__ TickArgs a, const __grid_constan
             const uint32_t kg = (uint32_t)(a.k_offset + k);
             const bool exploit = (int)kg < a.n_exploit;
             float z[4] = {sm.x0[0], sm.x0[1], sm.x0[2], 0.f};
-            float acc = 0.f, v0 = 0.f, v1 = 0.f, e[4] = {0.f, 0.f, 0.f, 0.f}, sn = 0.f, cs = 1.f;
+            float acc = 0.f, e[4] = {0.f, 0.f, 0.f, 0.f}, sn = 0.f, cs = 1.f;
+            float vp0 = 0.f, vp1 = 0.f, vc0 = 0.f, vc1 = 0.f, vn0 = 0.f, vn1 = 0.f;    // controls of steps t-1, t, t+1
             float4 ref = make_float4(0.f, 0.f, 0.f, 0.f);
             const float2 *eps_k = a.eps ? reinterpret_cast<const float2 *>(a.eps) + (size_t)(active ? k : 0) * T : nullptr;
+            // noise + clamped control of step t (A3-A5); called for t = 0, 1, 2, ... in order (a Philox call yields two steps)
+            auto control = [&](int t, float &o0, float &o1) {
+                if (eps_k) { const float2 ee = eps_k[t]; e[2 * (t & 1)] = ee.x; e[2 * (t & 1) + 1] = ee.y; }
+                else if ((t & 1) == 0) philox_eps_pair(a, kg, (uint32_t)(t >> 1), 0u, e);
+                const float2 u = sm.U[t];
+                o0 = clampf(exploit ? __fadd_rn(u.x, e[2 * (t & 1)]) : e[2 * (t & 1)], a.umax0);
+                o1 = clampf(exploit ? __fadd_rn(u.y, e[2 * (t & 1) + 1]) : e[2 * (t & 1) + 1], a.umax1);
+            };
+            if (owner) control(0, vc0, vc1);
             for (int t = 0; t < T; ++t) {
-                // (1) owner publishes the state; both halves evaluate their 256 columns of tanh(W01 x + b01)
-                if (owner) ms.xs[row] = make_float4(z[0], z[1], z[2], 0.f);
+                // (1) owner publishes the state (and, for the 5-input residual, this step's control); every group
+                //     evaluates its 128 columns of tanh(W01 [x; u] + b01)
+                if (owner) {
+                    ms.xs[row] = make_float4(z[0], z[1], z[2], vc0);
+                    if (NIN == 5) ms.xw[row] = vc1;
+                }
                 named_bar_sync(1, N_COMPUTE);
                 const float4 st = ms.xs[row];
+                const float su1 = NIN == 5 ? ms.xw[row] : 0.f;
 #pragma unroll 1
                 for (int part = 0; part < N_QUARTERS; ++part) {      // 128-column parts of A, each signalled on its own
 #pragma unroll 2
@@ -329,8 +356,13 @@ mppi_mlp_rollout_kernel(const __grid_constant__ TickArgs a, const __grid_constan
 #pragma unroll
                         for (int p = 0; p < 4; ++p) {
                             const float4 wa = ms.w01[col + 2 * p], wb = ms.w01[col + 2 * p + 1];
-                            const float pa = fmaf(wa.x, st.x, fmaf(wa.y, st.y, fmaf(wa.z, st.z, wa.w)));
-                            const float pb = fmaf(wb.x, st.x, fmaf(wb.y, st.y, fmaf(wb.z, st.z, wb.w)));
+                            float pa = fmaf(wa.x, st.x, fmaf(wa.y, st.y, fmaf(wa.z, st.z, wa.w)));
+                            float pb = fmaf(wb.x, st.x, fmaf(wb.y, st.y, fmaf(wb.z, st.z, wb.w)));
+                            if (NIN == 5) {
+                                const float4 wu = *reinterpret_cast<const float4 *>(&ms.w01u[col + 2 * p]);
+                                pa = fmaf(wu.x, st.w, fmaf(wu.y, su1, pa));
+                                pb = fmaf(wu.z, st.w, fmaf(wu.w, su1, pb));
+                            }
                             pk[p] = tanh_bf16x2(pa, pb);
                         }
                         tmem_st4(tmem + ((uint32_t)(q * 32) << 16) + TMEM_A_COL + (uint32_t)(col >> 1), pk[0], pk[1], pk[2], pk[3]);
@@ -340,19 +372,15 @@ mppi_mlp_rollout_kernel(const __grid_constant__ TickArgs a, const __grid_constan
                     mbar_arrive(&ms.a_ready[part]);
                 }
                 // (2) owner overlaps with the GEMM: stage cost of the state reached by the previous step, then the
-                //     noise and clamped control of this step
+                //     noise and clamped control of the NEXT step
                 if (owner) {
                     if (t > 0 && (a.flags & F_COST_SUM)) {
                         const int j = a.window == 20 ? nearest_wp<20>(sm, z[0], z[1]) : nearest_wp<0>(sm, z[0], z[1]);
                         ref = window_ref(sm, j);
                         const float2 qq = sm.Q[t - 1];
-                        acc += tracking_cost<MPPI_MODEL_DIFFDRIVE>(ref, z, z[2], a.sw) + (qq.x * v0 + qq.y * v1);
+                        acc += tracking_cost<MPPI_MODEL_DIFFDRIVE>(ref, z, z[2], a.sw) + (qq.x * vp0 + qq.y * vp1);
                     }
-                    if (eps_k) { const float2 ee = eps_k[t]; e[2 * (t & 1)] = ee.x; e[2 * (t & 1) + 1] = ee.y; }
-                    else if ((t & 1) == 0) philox_eps_pair(a, kg, (uint32_t)(t >> 1), 0u, e);
-                    const float2 u = sm.U[t];
-                    v0 = clampf(exploit ? __fadd_rn(u.x, e[2 * (t & 1)]) : e[2 * (t & 1)], a.umax0);
-                    v1 = clampf(exploit ? __fadd_rn(u.y, e[2 * (t & 1) + 1]) : e[2 * (t & 1) + 1], a.umax1);
+                    if (t + 1 < T) control(t + 1, vn0, vn1);
                     sincos_cw(z[2], sn, cs);
                 }
                 // (3) epilogue: D -> +b2 -> tanh -> FP32 contraction with the 512x3 output layer
@@ -375,16 +403,17 @@ mppi_mlp_rollout_kernel(const __grid_constant__ TickArgs a, const __grid_constan
                         r0 = fmaf(w.y, h, r0); r1 = fmaf(w.z, h, r1); r2 = fmaf(w.w, h, r2);
                     }
                 }
-                if (!owner) ms.res[grp - 1][row] = make_float4(r0, r1, r2, 0.f);
+                if (!owner) { ms.res[grp - 1][0][row] = r0; ms.res[grp - 1][1][row] = r1; ms.res[grp - 1][2][row] = r2; }
                 named_bar_sync(1, N_COMPUTE);
-                // (4) owner: Euler step with the learned residual, nearest waypoint, stage cost
+                // (4) owner: Euler step with the learned residual
                 if (owner) {
 #pragma unroll
-                    for (int g = 0; g < N_GROUPS - 1; ++g) { const float4 pr = ms.res[g][row]; r0 += pr.x; r1 += pr.y; r2 += pr.z; }
+                    for (int g = 0; g < N_GROUPS - 1; ++g) { r0 += ms.res[g][0][row]; r1 += ms.res[g][1][row]; r2 += ms.res[g][2][row]; }
                     r0 += ms.b3[0]; r1 += ms.b3[1]; r2 += ms.b3[2];
-                    z[0] = fmaf(fmaf(v0, cs, r0), a.dt, z[0]);
-                    z[1] = fmaf(fmaf(v0, sn, r1), a.dt, z[1]);
-                    z[2] = fmaf(v1 + r2, a.dt, z[2]);
+                    z[0] = fmaf(fmaf(vc0, cs, r0), a.dt, z[0]);
+                    z[1] = fmaf(fmaf(vc0, sn, r1), a.dt, z[1]);
+                    z[2] = fmaf(vc1 + r2, a.dt, z[2]);
+                    vp0 = vc0; vp1 = vc1; vc0 = vn0; vc1 = vn1;
                 }
             }
             if (owner && active) {
@@ -392,7 +421,7 @@ mppi_mlp_rollout_kernel(const __grid_constant__ TickArgs a, const __grid_constan
                 const int j = a.window == 20 ? nearest_wp<20>(sm, z[0], z[1]) : nearest_wp<0>(sm, z[0], z[1]);
                 ref = window_ref(sm, j);
                 const float2 qq = sm.Q[T - 1];
-                const float last = tracking_cost<MPPI_MODEL_DIFFDRIVE>(ref, z, z[2], a.sw) + (qq.x * v0 + qq.y * v1) +
+                const float last = tracking_cost<MPPI_MODEL_DIFFDRIVE>(ref, z, z[2], a.sw) + (qq.x * vp0 + qq.y * vp1) +
                                    tracking_cost<MPPI_MODEL_DIFFDRIVE>(ref, z, z[2], a.tw);
                 acc = (a.flags & F_COST_SUM) ? acc + last : last;
                 S_out[k] = acc;
@@ -417,7 +446,9 @@ struct MlpState {
     int K = 0, T = 0, n_sm = 148;
     __nv_bfloat16 *d_w2 = nullptr;        // [512 out][512 in] bf16, K-major B operand
     float4 *d_w01 = nullptr, *d_w3 = nullptr;
+    float2 *d_w01u = nullptr;             // control columns of the folded first layer (n_in = 5)
     float *d_b3 = nullptr;
+    int n_in = 3;
     CUtensorMap w2_map;
     bool ready = false;
 };
@@ -432,8 +463,10 @@ MlpState *mlp_create(int K, int T) {
     if (cudaMalloc(&m->d_w2, sizeof(__nv_bfloat16) * HID * HID) != cudaSuccess ||
         cudaMalloc(&m->d_w01, sizeof(float4) * HID) != cudaSuccess ||
         cudaMalloc(&m->d_w3, sizeof(float4) * HID) != cudaSuccess ||
+        cudaMalloc(&m->d_w01u, sizeof(float2) * HID) != cudaSuccess ||
         cudaMalloc(&m->d_b3, sizeof(float) * 4) != cudaSuccess) { mlp_destroy(m); return nullptr; }
-    if (cudaFuncSetAttribute(mppi_mlp_rollout_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MLP_DYN_SMEM) != cudaSuccess) {
+    if (cudaFuncSetAttribute(mppi_mlp_rollout_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MLP_DYN_SMEM) != cudaSuccess ||
+        cudaFuncSetAttribute(mppi_mlp_rollout_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MLP_DYN_SMEM) != cudaSuccess) {
         mlp_destroy(m); return nullptr;
     }
     return m;
@@ -441,30 +474,51 @@ MlpState *mlp_create(int K, int T) {
 
 void mlp_destroy(MlpState *m) {
     if (!m) return;
-    cudaFree(m->d_w2); cudaFree(m->d_w01); cudaFree(m->d_w3); cudaFree(m->d_b3);
+    cudaFree(m->d_w2); cudaFree(m->d_w01); cudaFree(m->d_w01u); cudaFree(m->d_w3); cudaFree(m->d_b3);
     delete m;
 }
 
-// Weights arrive as nn.Linear tensors [out][in] (dnn/simple_mlp.py:10-13).  Layer 0 has no activation,
-// so it is folded into layer 1 here (FP64 accumulation): W01 = W1 W0, b01 = W1 b0 + b1.
-cudaError_t mlp_set_weights(MlpState *m, const float *const W[4], const float *const b[4], cudaStream_t st) {
+// Weights arrive as nn.Linear tensors [out][in] (dnn/simple_mlp.py:10-13; 5-input variant
+// simulation/bullet_differential_drive_dnn.py:41-48).  Layer 0 has no activation, so it is folded into layer 1 here
+// (FP64 accumulation): W01 = W1 W0, b01 = W1 b0 + b1.  StandardScaler pre/post-processing of the trained models,
+// in = (raw - in_mean) / in_scale and out_raw = out * out_scale + out_mean (train/train_diff_mlp.py:72-103,
+// test/test_diff_dyna_eval.py:54-56), is folded into W0 / b0 and W3 / b3 first; null pointers mean identity.
+cudaError_t mlp_set_weights(MlpState *m, int n_in, const float *const W[4], const float *const b[4], const double *in_mean,
+                            const double *in_scale, const double *out_mean, const double *out_scale, cudaStream_t st) {
+    if (n_in != 3 && n_in != 5) return cudaErrorInvalidValue;
+    std::vector<double> W0((size_t)HID * n_in), b0(HID);
+    for (int i = 0; i < HID; ++i) {
+        double bb = b[0][i];
+        for (int c = 0; c < n_in; ++c) {
+            const double sc = in_scale ? in_scale[c] : 1.0, mu = in_mean ? in_mean[c] : 0.0;
+            const double w = (double)W[0][(size_t)i * n_in + c] / sc;
+            W0[(size_t)i * n_in + c] = w;
+            bb -= w * mu;
+        }
+        b0[i] = bb;
+    }
     std::vector<float4> w01(HID), w3(HID);
+    std::vector<float2> w01u(HID, make_float2(0.f, 0.f));
     for (int j = 0; j < HID; ++j) {
-        double s[3] = {0, 0, 0}, bb = b[1][j];
+        double s[5] = {0, 0, 0, 0, 0}, bb = b[1][j];
         for (int i = 0; i < HID; ++i) {
             const double w1 = W[1][(size_t)j * HID + i];
-            s[0] += w1 * W[0][i * 3 + 0]; s[1] += w1 * W[0][i * 3 + 1]; s[2] += w1 * W[0][i * 3 + 2];
-            bb += w1 * b[0][i];
+            for (int c = 0; c < n_in; ++c) s[c] += w1 * W0[(size_t)i * n_in + c];
+            bb += w1 * b0[i];
         }
         w01[j] = make_float4((float)s[0], (float)s[1], (float)s[2], (float)bb);
-        w3[j] = make_float4(b[2][j], W[3][0 * HID + j], W[3][1 * HID + j], W[3][2 * HID + j]);
+        w01u[j] = make_float2((float)s[3], (float)s[4]);
+        const double o0 = out_scale ? out_scale[0] : 1.0, o1 = out_scale ? out_scale[1] : 1.0, o2 = out_scale ? out_scale[2] : 1.0;
+        w3[j] = make_float4(b[2][j], (float)(W[3][0 * HID + j] * o0), (float)(W[3][1 * HID + j] * o1), (float)(W[3][2 * HID + j] * o2));
     }
     std::vector<__nv_bfloat16> w2((size_t)HID * HID);
     for (size_t i = 0; i < w2.size(); ++i) w2[i] = __float2bfloat16(W[2][i]);
-    const float b3[4] = {b[3][0], b[3][1], b[3][2], 0.f};
+    float b3[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int c = 0; c < 3; ++c) b3[c] = (float)((double)b[3][c] * (out_scale ? out_scale[c] : 1.0) + (out_mean ? out_mean[c] : 0.0));
     cudaError_t e;
     if ((e = cudaMemcpyAsync(m->d_w01, w01.data(), sizeof(float4) * HID, cudaMemcpyHostToDevice, st)) != cudaSuccess) return e;
     if ((e = cudaMemcpyAsync(m->d_w3, w3.data(), sizeof(float4) * HID, cudaMemcpyHostToDevice, st)) != cudaSuccess) return e;
+    if ((e = cudaMemcpyAsync(m->d_w01u, w01u.data(), sizeof(float2) * HID, cudaMemcpyHostToDevice, st)) != cudaSuccess) return e;
     if ((e = cudaMemcpyAsync(m->d_b3, b3, sizeof(b3), cudaMemcpyHostToDevice, st)) != cudaSuccess) return e;
     if ((e = cudaMemcpyAsync(m->d_w2, w2.data(), sizeof(__nv_bfloat16) * HID * HID, cudaMemcpyHostToDevice, st)) != cudaSuccess) return e;
     if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return e;
@@ -481,6 +535,7 @@ cudaError_t mlp_set_weights(MlpState *m, const float *const W[4], const float *c
                                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                                       CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return cudaErrorInvalidValue;
+    m->n_in = n_in;
     m->ready = true;
     return cudaSuccess;
 }
@@ -492,7 +547,10 @@ int mlp_rollout_costs(MlpState *m, const TickArgs &args, bool sum, const float *
     a.flags = sum ? F_COST_SUM : 0;
     const int n_tiles = (a.K + TILE_M - 1) / TILE_M;
     int grid = std::min(((n_tiles + 1) / 2) * 2, m->n_sm & ~1);       // whole clusters of 2
-    mppi_mlp_rollout_kernel<<<grid, MLP_THREADS, MLP_DYN_SMEM, st>>>(a, m->w2_map, m->d_w01, m->d_w3, m->d_b3, d_S, n_tiles);
+    if (m->n_in == 5)
+        mppi_mlp_rollout_kernel<5><<<grid, MLP_THREADS, MLP_DYN_SMEM, st>>>(a, m->w2_map, m->d_w01, m->d_w01u, m->d_w3, m->d_b3, d_S, n_tiles);
+    else
+        mppi_mlp_rollout_kernel<3><<<grid, MLP_THREADS, MLP_DYN_SMEM, st>>>(a, m->w2_map, m->d_w01, m->d_w01u, m->d_w3, m->d_b3, d_S, n_tiles);
     return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 

@@ -62,6 +62,7 @@ SYMBOLS = {
     "mppi_set_waypoint_idx": (C.c_int, [_H, _PI]),
     "mppi_get_waypoint_idx": (C.c_int, [_H, _PI]),
     "mppi_set_mlp": (C.c_int, [_H, C.POINTER(_PF), C.POINTER(_PF)]),
+    "mppi_set_mlp_ex": (C.c_int, [_H, C.c_int32, C.c_int32, C.POINTER(_PF), C.POINTER(_PF), _PD, _PD, _PD, _PD]),
     "mppi_step": (C.c_int, [_H, _PD, C.c_void_p, C.c_uint64, C.c_uint64, _PF, _PF]),
     "mppi_step_async": (C.c_int, [_H, _PD, C.c_void_p, C.c_uint64, C.c_uint64]),
     "mppi_rollout_costs": (C.c_int, [_H, _PD, C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p]),

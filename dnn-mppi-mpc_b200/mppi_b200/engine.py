@@ -131,12 +131,27 @@ class MPPIEngine:
         self._ck(self.lib.mppi_get_waypoint_idx(self._h, a.ctypes.data_as(_lib._PI)), "mppi_get_waypoint_idx")
         return int(a[0]) if self.R == 1 else a
 
-    def set_mlp(self, weights, biases):
+    def set_mlp(self, weights, biases, in_mean=None, in_scale=None, out_mean=None, out_scale=None):
+        """nn.Linear-layout weights of the residual MLP: input layer (512, n_in) with n_in = 3 (state, dnn/simple_mlp.py)
+        or 5 (state + control, the trained saved_models), hidden layers (512, 512), output layer (3, 512); optional
+        StandardScaler statistics folded into the first / last layer."""
         Ws = [np.ascontiguousarray(w, dtype=np.float32) for w in weights]
         bs = [np.ascontiguousarray(b, dtype=np.float32) for b in biases]
-        Wp = (_lib._PF * 4)(*[w.ctypes.data_as(_lib._PF) for w in Ws])
-        bp = (_lib._PF * 4)(*[b.ctypes.data_as(_lib._PF) for b in bs])
-        self._ck(self.lib.mppi_set_mlp(self._h, Wp, bp), "mppi_set_mlp")
+        n = len(Ws)
+        Wp = (_lib._PF * n)(*[w.ctypes.data_as(_lib._PF) for w in Ws])
+        bp = (_lib._PF * n)(*[b.ctypes.data_as(_lib._PF) for b in bs])
+        n_in = int(Ws[0].shape[1])
+        if n == 4 and n_in == 3 and in_mean is None and in_scale is None and out_mean is None and out_scale is None:
+            self._ck(self.lib.mppi_set_mlp(self._h, Wp, bp), "mppi_set_mlp")
+            return
+
+        def vec(v, k):
+            if v is None:
+                return None, None
+            a = np.ascontiguousarray(v, dtype=np.float64).reshape(k)
+            return a, a.ctypes.data_as(_lib._PD)
+        keep = [vec(in_mean, n_in), vec(in_scale, n_in), vec(out_mean, 3), vec(out_scale, 3)]
+        self._ck(self.lib.mppi_set_mlp_ex(self._h, n_in, n - 2, Wp, bp, *[k[1] for k in keep]), "mppi_set_mlp_ex")
 
     # -- ticks -----------------------------------------------------------------------------
     def _load_x0(self, x0):

@@ -51,23 +51,44 @@ class MPPIAlgorithms(ControllerBase):
 
     prev_way_point_idx = property(ControllerBase._get_idx, ControllerBase._set_idx)
 
-    def set_dynamics(self, dynamics):
-        """Learned dynamics x+ = x + dt*([v cos th, v sin th, w] + MLP(x)).  `dynamics` is a
-        dnn/simple_mlp.py-shaped torch module (input_layer, hidden_layer[0..1], output_layer) or a dict
-        {'W0','b0',...,'W3','b3'} of nn.Linear-layout arrays.  Requires waypoint_mode='frozen'."""
+    def set_dynamics(self, dynamics, scalers=None):
+        """Learned dynamics x+ = x + dt*([v cos th, v sin th, w] + residual).  `dynamics` is a torch
+        module / state dict shaped like dnn/simple_mlp.py (3 inputs: residual = MLP(x)) or like the trained
+        saved_models/mlp_diff*.pth (5 inputs: residual = MLP([x; u])), or a dict {'W0','b0',...,'W3','b3'} of
+        nn.Linear-layout arrays.  `scalers`: the {'state_scaler','control_scaler','error_scaler'} dict saved next to the
+        trained models (saved_models/scalers_*.pth) or {'in_mean','in_scale','out_mean','out_scale'} arrays:
+        residual = out_scale * MLP(([x; u] - in_mean) / in_scale) + out_mean (test/test_diff_dyna_eval.py:54-56).
+        Requires waypoint_mode='frozen'."""
         if hasattr(dynamics, "state_dict"):
-            sd = {k: v.detach().cpu().numpy() for k, v in dynamics.state_dict().items()}
-            names = ["input_layer", "hidden_layer.0", "hidden_layer.1", "output_layer"]
+            dynamics = dynamics.state_dict()
+        if any(str(k).endswith(".weight") for k in dynamics):
+            # torch state dict: dnn/simple_mlp.py names its last layer `output_layer`, the trained 5-input models
+            # (simulation/bullet_differential_drive_dnn.py:37-60, saved_models/mlp_diff*.pth) `out_layer`
+            sd = {k: (v.detach().cpu().numpy() if hasattr(v, "detach") else np.asarray(v)) for k, v in dynamics.items()}
+            n_hidden = len([k for k in sd if k.startswith("hidden_layer.") and k.endswith(".weight")])
+            last = "output_layer" if "output_layer.weight" in sd else "out_layer"
+            names = ["input_layer"] + ["hidden_layer.%d" % i for i in range(n_hidden)] + [last]
             W = [sd[n + ".weight"] for n in names]
             b = [sd[n + ".bias"] for n in names]
         else:
-            W = [np.asarray(dynamics["W%d" % i]) for i in range(4)]
-            b = [np.asarray(dynamics["b%d" % i]) for i in range(4)]
-        shapes = [(512, 3), (512, 512), (512, 512), (3, 512)]
-        for w, sh in zip(W, shapes):
-            if tuple(w.shape) != sh:
-                raise ValueError("MLP weights must have the dnn/simple_mlp.py shapes %s" % (shapes,))
-        self._engine.set_mlp(W, b)
+            n = len([k for k in dynamics if str(k).startswith("W")])
+            W = [np.asarray(dynamics["W%d" % i]) for i in range(n)]
+            b = [np.asarray(dynamics["b%d" % i]) for i in range(n)]
+            if scalers is None and "in_scale" in dynamics:
+                scalers = {k: dynamics[k] for k in ("in_mean", "in_scale", "out_mean", "out_scale") if k in dynamics}
+        n_in = W[0].shape[1]
+        shapes = [(512, n_in)] + [(512, 512)] * (len(W) - 2) + [(3, 512)]
+        if n_in not in (3, 5) or [tuple(w.shape) for w in W] != shapes:
+            raise ValueError("MLP weights must be (512,3|5), (512,512)..., (3,512) like dnn/simple_mlp.py / saved_models/mlp_diff*.pth")
+        kw = {}
+        if scalers is not None:
+            if "state_scaler" in scalers:            # the dict torch.load("saved_models/scalers_*.pth") returns
+                ss, cs, es = scalers["state_scaler"], scalers["control_scaler"], scalers["error_scaler"]
+                kw = dict(in_mean=np.concatenate([ss.mean_, cs.mean_])[:n_in], in_scale=np.concatenate([ss.scale_, cs.scale_])[:n_in],
+                          out_mean=es.mean_, out_scale=es.scale_)
+            else:
+                kw = {k: np.asarray(scalers[k], dtype=np.float64) for k in ("in_mean", "in_scale", "out_mean", "out_scale") if k in scalers}
+        self._engine.set_mlp(W, b, **kw)
 
     def _calc_input_control(self, observed_x, noise=None):
         """One control tick (reference :87-165).  `noise`: optional injected (K,T,2) epsilon."""

@@ -153,6 +153,16 @@ int mppi_set_waypoint_idx(mppi_handle_t h, const int32_t *idx);
 int mppi_get_waypoint_idx(mppi_handle_t h, int32_t *idx);
 /* weights of dnn/simple_mlp.py (3-512-512-512-3), row-major float32 [out][in] like nn.Linear */
 int mppi_set_mlp(mppi_handle_t h, const float *const W[4], const float *const b[4]);
+/* The reference's TRAINED residuals (saved_models/mlp_diff*.pth; class at simulation/bullet_differential_drive_dnn.py:37-60,
+ * training at train/train_diff_mlp.py:13-36,72-103): n_in = 5 inputs [x, y, yaw, v, w] -> 512 -> n_hidden x tanh(512) -> 3,
+ * added to the unicycle right-hand side like controllers/mpc_mlp_differential_drive.py:65-71, with the StandardScaler
+ * pre/post-processing of test/test_diff_dyna_eval.py:54-56:
+ *     x+ = x + dt * ( f(x, u) + out_scale * MLP(([x; u] - in_mean) / in_scale) + out_mean ).
+ * W / b: n_hidden + 2 nn.Linear tensors [out][in] (input layer n_in -> 512 first, output layer 512 -> 3 last);
+ * in_mean / in_scale: n_in doubles (state scaler then control scaler) or NULL; out_mean / out_scale: 3 doubles or NULL.
+ * n_in = 3 is dnn/simple_mlp.py (mppi_set_mlp).  n_hidden must be 2 (MPPI_E_UNSUPPORTED otherwise). */
+int mppi_set_mlp_ex(mppi_handle_t h, int32_t n_in, int32_t n_hidden, const float *const *W, const float *const *b,
+                    const double *in_mean, const double *in_scale, const double *out_mean, const double *out_scale);
 
 /* One control tick -- replaces the body of `_calc_input_control` (mppi_differential_drive.py:87-165)
  * / `_calc_control_input` (mppi_race_car_obstacle.py:65-131): index update, noise, K x T rollout,

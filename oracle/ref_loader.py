@@ -89,6 +89,22 @@ def load_reference_extras():
     return _loaded
 
 
+def load_reference_mlps():
+    """The reference's residual-MLP torch modules: dnn/simple_mlp.py:MultiLayerPerception (3 inputs) and the
+    5-input MultiLayerPerceptron of simulation/bullet_differential_drive_dnn.py:37-60 (that script imports casadi,
+    pybullet, l4casadi, torchvision and acados at module top; none is touched by the class, stubs are enough)."""
+    if "MLP3" in _loaded:
+        return _loaded
+    load_reference()
+    import importlib
+    for n in ("casadi", "pybullet", "pybullet_data", "l4casadi", "torchvision", "torchvision.models", "acados_template"):
+        sys.modules.setdefault(n, _Stub(n))
+    m3 = importlib.import_module("dnn.simple_mlp")
+    m5 = importlib.import_module("simulation.bullet_differential_drive_dnn")
+    _loaded.update(dict(MLP3=m3.MultiLayerPerception, MLP5=m5.MultiLayerPerceptron))
+    return _loaded
+
+
 def instrument(ctrl, eps_list):
     """Make a reference controller deterministic and observable without editing it.
 

@@ -125,6 +125,44 @@ def make_extras():
     save("diffdrive_target_soft", meta, np.zeros((1, 3)), eps_list, recs)
 
 
+def make_mlp_golden():
+    """forward passes of the reference's own torch modules (3-input dnn/simple_mlp.py and the
+    5-input class the trained saved_models belong to), loaded with the seeded weights oracle.make_mlp regenerates on
+    any machine, with StandardScaler objects applied the way test/bullet_differential_drive_dnn.py:363-370 does."""
+    import torch
+    from sklearn.preprocessing import StandardScaler
+    from oracle.mppi_oracle import make_mlp
+    ref = ref_loader.load_reference_mlps()
+    rng = np.random.default_rng(21)
+    out = {}
+    for n_in, cls, last in ((3, ref["MLP3"], "output_layer"), (5, ref["MLP5"], "out_layer")):
+        w = make_mlp(seed=5, out_scale=0.01, dtype=np.float32, n_in=n_in, scalers=(n_in == 5))
+        net = cls()
+        names = ["input_layer", "hidden_layer.0", "hidden_layer.1", last]
+        net.load_state_dict({n + s: torch.from_numpy(w[k + str(i)]) for i, n in enumerate(names)
+                             for s, k in ((".weight", "W"), (".bias", "b"))})
+        net = net.double()
+        X = rng.normal(0, 1.5, (48, n_in))
+        if n_in == 5:
+            ss, cs, es = StandardScaler(), StandardScaler(), StandardScaler()
+            ss.mean_, ss.scale_ = w["in_mean"][:3], w["in_scale"][:3]
+            cs.mean_, cs.scale_ = w["in_mean"][3:], w["in_scale"][3:]
+            es.mean_, es.scale_ = w["out_mean"], w["out_scale"]
+            xin = np.concatenate([ss.transform(X[:, :3]), cs.transform(X[:, 3:])], axis=1)
+            with torch.no_grad():
+                y = es.inverse_transform(net(torch.from_numpy(xin)).numpy())
+        else:
+            with torch.no_grad():
+                y = net(torch.from_numpy(X)).numpy()
+        out["X%d" % n_in], out["Y%d" % n_in] = X, y
+    out["meta"] = json.dumps(dict(seed=5, out_scale=0.01, numpy=np.__version__, torch=torch.__version__,
+                                  source="dnn/simple_mlp.py:MultiLayerPerception and "
+                                         "simulation/bullet_differential_drive_dnn.py:MultiLayerPerceptron, float64"))
+    fn = os.path.join(HERE, "mlp_forward.npz")
+    np.savez_compressed(fn, **out)
+    print("wrote", fn, "%.1f KB" % (os.path.getsize(fn) / 1024))
+
+
 def main():
     ref = ref_loader.load_reference()
     path = spline_path(ref)
@@ -226,6 +264,7 @@ def main():
          obstacles=ctrl.obstacle_circles)
 
     make_extras()
+    make_mlp_golden()
 
     # ---- literal filter operators as matrices (Q7)
     Ms = {}
@@ -241,5 +280,7 @@ def main():
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "extras":
         make_extras()               # only the SURVEY 8f row-3 fixtures (the others stay byte-identical)
+    elif len(sys.argv) > 1 and sys.argv[1] == "mlp":
+        make_mlp_golden()
     else:
         main()

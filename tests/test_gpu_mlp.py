@@ -96,3 +96,79 @@ def test_mlp_full_tick_and_drop_in_class():
         assert np.max(np.abs(u - o["U_after"])) <= MLP_U_ATOL, (tick, np.max(np.abs(u - o["U_after"])))
         assert ctrl.prev_way_point_idx == o["idx_after"]
         U, idx = u.copy(), o["idx_after"]
+
+
+def _mlp5(seed=0, out_scale=0.01):
+    return orc.make_mlp(seed=seed, out_scale=out_scale, n_in=5, scalers=True)
+
+
+@pytest.mark.parametrize("K", [128, 1024])
+def test_mlp5_scaled_residual_costs_match_fp64_oracle(K):
+    """residual with FIVE inputs [x, y, yaw, v, w] and StandardScaler pre/post-processing (the shape
+    of the reference's trained saved_models/mlp_diff*.pth), folded into the first / last layer on the host."""
+    g = Golden("diffdrive_pe0.05")
+    T = 12
+    mlp = _mlp5()
+    sp = _spec(K, T, "sum", mlp)
+    eng = engine_from_spec(sp, g.path)
+    eng.set_mlp([mlp["W%d" % i] for i in range(4)], [mlp["b%d" % i] for i in range(4)], mlp["in_mean"], mlp["in_scale"],
+                mlp["out_mean"], mlp["out_scale"])
+    eps = torch.zeros(K, T, 2, dtype=torch.float32, device="cuda")
+    eng.generate_noise(eps, seed=3, tick=1)
+    S = torch.zeros(K, dtype=torch.float32, device="cuda")
+    x0 = np.array([0.4, 0.3, 0.5])
+    U = np.random.default_rng(2).normal(0, 0.5, (T, 2)).astype(np.float32)
+    for src in ("philox", "injected"):
+        S.zero_()
+        eng.set_nominal(U)
+        eng.set_waypoint_idx(0)
+        eng.rollout_costs(x0, S, eps if src == "injected" else None, seed=3, tick=1)
+        So, _, s_end = orc.costs_vec(sp, g.path, U.astype(np.float64), 0, x0, eps.cpu().numpy().astype(np.float64))
+        Sg = S.cpu().numpy().astype(np.float64)
+        rel = np.abs(Sg - So) / np.maximum(np.abs(So), 1e-9)
+        assert np.quantile(rel, 0.99) <= MLP_COST_RTOL and rel.max() <= 2e-2, (K, src, rel.max())
+    # the control columns really enter: zeroing them changes the costs
+    mlp0 = dict(mlp)
+    mlp0["W0"] = mlp["W0"].copy()
+    mlp0["W0"][:, 3:] = 0.0
+    sp0 = _spec(K, T, "sum", mlp0)
+    S0, _, _ = orc.costs_vec(sp0, g.path, U.astype(np.float64), 0, x0, eps.cpu().numpy().astype(np.float64))
+    assert np.median(np.abs(S0 - So) / So) > 10 * MLP_COST_RTOL
+    eng.close()
+
+
+def test_mlp5_drop_in_with_state_dict_and_sklearn_style_scalers():
+    """set_dynamics takes what a user of the reference has on disk: a torch state dict with the trained models' layer
+    names (`out_layer`) and the {'state_scaler','control_scaler','error_scaler'} objects of saved_models/scalers_*.pth."""
+    import types
+    from mppi_b200 import MppiError
+    from mppi_b200.mppi_differential_drive import MPPIAlgorithms
+    g = Golden("diffdrive_pe0.05")
+    K, T = 1024, 20
+    mlp = _mlp5(seed=3)
+    names = ["input_layer", "hidden_layer.0", "hidden_layer.1", "out_layer"]
+    sd = {}
+    for i, n in enumerate(names):
+        sd[n + ".weight"] = torch.from_numpy(mlp["W%d" % i].astype(np.float32))
+        sd[n + ".bias"] = torch.from_numpy(mlp["b%d" % i].astype(np.float32))
+    scalers = dict(state_scaler=types.SimpleNamespace(mean_=mlp["in_mean"][:3], scale_=mlp["in_scale"][:3]),
+                   control_scaler=types.SimpleNamespace(mean_=mlp["in_mean"][3:], scale_=mlp["in_scale"][3:]),
+                   error_scaler=types.SimpleNamespace(mean_=mlp["out_mean"], scale_=mlp["out_scale"]))
+    ctrl = MPPIAlgorithms(delta_t=0.1, ref_path=g.path, max_speed=5.0, max_omega=3.14, num_samples_K=K, num_horizons_T=T,
+                          param_exploration=0.05, param_lambda=1.0, param_alpha=0.2, sigma=np.array([[0.1, 0.0], [0.0, 0.01]]),
+                          stage_cost_weight=np.array([5.0, 5.0, 10.0]), terminal_cost_weight=np.array([5.0, 5.0, 10.0]),
+                          visualize_optimal_traj=False, visualze_sampled_trajs=False, cost_mode="sum",
+                          waypoint_mode="frozen", temperature=2.0, dynamics=mlp, seed=4)
+    ctrl.set_dynamics(sd, scalers=scalers)
+    sp = _spec(K, T, "sum", mlp)
+    eps = torch.zeros(K, T, 2, dtype=torch.float32, device="cuda")
+    x0 = np.array([0.2, 0.1, 0.3])
+    ctrl.engine.generate_noise(eps, seed=4, tick=0)
+    o = orc.tick_vec(sp, g.path, np.zeros((T, 2)), 0, x0, eps.cpu().numpy().astype(np.float64))
+    u0, u, _, _ = ctrl._calc_input_control(x0)
+    assert np.max(np.abs(u - o["U_after"])) <= MLP_U_ATOL, np.max(np.abs(u - o["U_after"]))
+    # three hidden layers (saved_models/*_3l*.pth) are refused loudly, not approximated
+    sd3 = dict(sd)
+    sd3["hidden_layer.2.weight"], sd3["hidden_layer.2.bias"] = sd["hidden_layer.1.weight"], sd["hidden_layer.1.bias"]
+    with pytest.raises(MppiError):
+        ctrl.set_dynamics(sd3)

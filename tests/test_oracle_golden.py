@@ -1,6 +1,8 @@
 """Pins the oracle (test infrastructure) to the golden vectors produced by the unmodified
 reference classes: scalar-loop restatement bit-exact, vectorised and C restatements to
 1e-12 (diff-drive, FP64) / 4e-6 (race-car: the reference accumulates in FP32)."""
+import os
+
 import numpy as np
 import pytest
 
@@ -188,3 +190,50 @@ def test_target_soft_running_cost_matches_reference_functions():
     inp = g.tick_inputs(0)
     a = orc.tick_loops(sp_small, None, inp["U"], 0, inp["x0"], inp["eps"][:24])
     assert rel_err(a["S"], g.rec["S"][0][:24]) <= 2e-6
+
+
+@pytest.mark.parametrize("n_in", [3, 5])
+def test_mlp_forward_matches_reference_torch_modules(n_in):
+    """the oracle's residual MLP vs forward passes of the reference's own torch modules
+    (tests/golden/mlp_forward.npz), including the StandardScaler pre/post-processing of the 5-input model."""
+    import os
+    from golden_util import GOLDEN_DIR
+    z = np.load(os.path.join(GOLDEN_DIR, "mlp_forward.npz"))
+    w = orc.make_mlp(seed=5, out_scale=0.01, dtype=np.float64, n_in=n_in, scalers=(n_in == 5))
+    X = z["X%d" % n_in]
+    y = orc.mlp_forward(w, X[:, :3], X[:, 3:] if n_in == 5 else None)
+    assert np.max(np.abs(y - z["Y%d" % n_in])) <= 1e-12
+
+
+@pytest.mark.requires_reference
+def test_oracle_mlp_matches_the_trained_reference_model():
+    """Build container only: the TRAINED residual (saved_models/mlp_diff_300x100.pth + its scalers) evaluated by the
+    reference's torch class and sklearn scalers vs the oracle restatement."""
+    import warnings
+    import torch
+    from oracle import ref_loader
+    ref = ref_loader.load_reference_mlps()
+    root = ref_loader.REFERENCE_ROOT
+    sd = torch.load(os.path.join(root, "saved_models", "mlp_diff_300x100.pth"), map_location="cpu")
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        sc = torch.load(os.path.join(root, "saved_models", "scalers_mlp_diff_300x100_20_l.pth"), weights_only=False)
+    net = ref["MLP5"]()
+    net.load_state_dict(sd)
+    net = net.double()
+    X = np.random.default_rng(0).normal(0, 1.0, (16, 5)) * [3.0, 2.0, 1.0, 1.0, 1.5]
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        xin = np.concatenate([sc["state_scaler"].transform(X[:, :3]), sc["control_scaler"].transform(X[:, 3:])], axis=1)
+        with torch.no_grad():
+            y_ref = sc["error_scaler"].inverse_transform(net(torch.from_numpy(xin)).numpy())
+    names = ["input_layer", "hidden_layer.0", "hidden_layer.1", "out_layer"]
+    w = {}
+    for i, n in enumerate(names):
+        w["W%d" % i] = sd[n + ".weight"].numpy().astype(np.float64)
+        w["b%d" % i] = sd[n + ".bias"].numpy().astype(np.float64)
+    w["in_mean"] = np.concatenate([sc["state_scaler"].mean_, sc["control_scaler"].mean_])
+    w["in_scale"] = np.concatenate([sc["state_scaler"].scale_, sc["control_scaler"].scale_])
+    w["out_mean"], w["out_scale"] = sc["error_scaler"].mean_, sc["error_scaler"].scale_
+    y = orc.mlp_forward(w, X[:, :3], X[:, 3:])
+    assert np.max(np.abs(y - y_ref)) <= 1e-10 * max(1.0, np.max(np.abs(y_ref)))

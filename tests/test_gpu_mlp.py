@@ -98,8 +98,11 @@ def test_mlp_full_tick_and_drop_in_class():
         U, idx = u.copy(), o["idx_after"]
 
 
-def _mlp5(seed=0, out_scale=0.01):
-    return orc.make_mlp(seed=seed, out_scale=out_scale, n_in=5, scalers=True)
+def _mlp5(seed=0, out_scale=0.05):
+    # error-scaler statistics of the trained model's own magnitude (scale 5.7 / 3.6 / 1.0): the residual is ~0.1 m/s
+    m = orc.make_mlp(seed=seed, out_scale=out_scale, n_in=5, scalers=True, scaler_gain=1.0)
+    m["W0"][:, 3:] *= 8.0             # make the residual depend on the control as strongly as on the state
+    return m
 
 
 @pytest.mark.parametrize("K", [128, 1024])
@@ -133,7 +136,7 @@ def test_mlp5_scaled_residual_costs_match_fp64_oracle(K):
     mlp0["W0"][:, 3:] = 0.0
     sp0 = _spec(K, T, "sum", mlp0)
     S0, _, _ = orc.costs_vec(sp0, g.path, U.astype(np.float64), 0, x0, eps.cpu().numpy().astype(np.float64))
-    assert np.median(np.abs(S0 - So) / So) > 10 * MLP_COST_RTOL
+    assert np.median(np.abs(S0 - So)) > 30 * np.median(np.abs(Sg - So)), (np.median(np.abs(S0 - So)), np.median(np.abs(Sg - So)))
     eng.close()
 
 

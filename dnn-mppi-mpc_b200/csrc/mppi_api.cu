@@ -8,6 +8,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -239,7 +240,12 @@ int mppi_create(const mppi_config_t *cfg, mppi_handle_t *out) {
     h->own_stream = true;
 
     const int R = c.n_robots, T = c.T, K = c.K;
-    const int chunks = (K + MPPI_BLOCK - 1) / MPPI_BLOCK;
+    // Small sample counts are latency-bound (one thread walks one sample through the whole horizon): spread them over
+    // all SMs in CTAs that own as few as MPPI_MIN_CTA_SAMPLES samples (idle warps of a CTA cost nothing) instead of
+    // filling 256-thread CTAs on a fraction of the SMs.
+    int min_cta = 128;
+    if (const char *env = std::getenv("MPPI_MIN_CTA_SAMPLES")) min_cta = std::max(32, std::min(MPPI_BLOCK, std::atoi(env)));
+    const int chunks = (K + min_cta - 1) / min_cta;
     const int tick_model = (c.model == MPPI_MODEL_DIFFDRIVE_MLP) ? MPPI_MODEL_DIFFDRIVE : c.model;
     h->occ = std::max(1, mppi_tick_occupancy(tick_model, c.collision, c.cost_kind, h->sum, false, c.window, T, false));
     const int occ_stash = mppi_tick_occupancy(tick_model, c.collision, c.cost_kind, h->sum, false, c.window, T, true);

@@ -42,9 +42,13 @@ struct MergeSmem {
 
 // Merges P partials (layout MPPI_NF) into ms.col by the log-sum-exp rule of SURVEY.md 8e.  Runs in ONE CTA on the
 // critical path of every tick, so it is organised for memory-level parallelism: the P scale factors are computed
-// once (P exps, spread over the threads) into shared memory (`sc`, MPPI_MERGE_TILE floats lent by the caller), then each thread owns a column and streams the
-// partials with 8 independent coalesced loads in flight.
-#define MPPI_MERGE_TILE 1024
+// once (P exps, spread over the threads) into shared memory; then the CTA splits into G groups of NF/2 threads, a
+// thread owns one float2 COLUMN PAIR of the partial layout and streams every G-th partial with 8 independent
+// coalesced 8-byte loads in flight; the G group sums meet in shared memory.  `sc` is scratch lent by the caller:
+// MPPI_MERGE_SCRATCH floats (the first MPPI_MERGE_TILE hold scale factors, the rest the group sums).
+#define MPPI_MERGE_TILE 1000
+#define MPPI_MERGE_GROUPS 4
+#define MPPI_MERGE_SCRATCH (MPPI_MERGE_TILE + MPPI_MERGE_GROUPS * MPPI_NF_MAX)      // 2040 floats <= the 8 KB warpN region
 __device__ void merge_partials(const TickArgs &a, const float *parts, int P, MergeSmem &ms, float *sc, int stride = 0) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int NF = MPPI_NF(a.T);
@@ -65,8 +69,14 @@ __device__ void merge_partials(const TickArgs &a, const float *parts, int P, Mer
         const int wn = ms.red_n[w]; const float ws = ms.red_s[w];
         if (wn < n || (wn == n && ws < s)) { n = wn; s = ws; }
     }
-    float acc0 = 0.f, acc1 = 0.f;                       // columns 2 + tid and 2 + tid + MPPI_BLOCK (NF <= 260)
-    const int c0 = 2 + tid, c1 = 2 + tid + MPPI_BLOCK;
+    // column pairs: pair 0 = (n, s) is the key handled above, pair 1 = (eta, sum w^2), pairs 2.. = N[t][0..1]
+    const int NP = NF >> 1;                                   // NF = 4 + 2T is even; every partial is 8-byte aligned
+    const int G = min(MPPI_MERGE_GROUPS, MPPI_BLOCK / NP);    // T <= 126 -> NP <= 128 -> G >= 2; T = 127, 128 -> G = 1
+    const int PPT = (NP + MPPI_BLOCK - 1) / MPPI_BLOCK;       // pairs per thread when one group does not cover them (G = 1)
+    const int g = tid / NP, cp = tid - g * NP;
+    const bool live = (G > 1) ? (g < G && cp >= 1) : true;
+    float2 acc[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+    float *red = sc + MPPI_MERGE_TILE;
     for (int base = 0; base < P; base += MPPI_MERGE_TILE) {
         const int np = min(MPPI_MERGE_TILE, P - base);
         __syncthreads();
@@ -75,25 +85,58 @@ __device__ void merge_partials(const TickArgs &a, const float *parts, int P, Mer
             sc[p] = rel_weight(__float_as_int(__ldcg(pp)), __ldcg(pp + 1), n, s, a.inv_temp);
         }
         __syncthreads();
-        if (c0 < NF) {
-            const float *col = parts + (size_t)base * stride + c0;
-            int p = 0;
-            for (; p + 8 <= np; p += 8) {
-                float v[8];
+        if (G > 1) {
+            if (live) {
+                const float2 *col = reinterpret_cast<const float2 *>(parts + (size_t)base * stride) + cp;
+                const size_t st2 = (size_t)stride >> 1;               // stride is even (NF or MPPI_NF_MAX)
+                int p = g;
+                for (; p + 7 * G < np; p += 8 * G) {
+                    float2 v[8];
 #pragma unroll
-                for (int i = 0; i < 8; ++i) v[i] = __ldcg(col + (size_t)(p + i) * stride);
+                    for (int i = 0; i < 8; ++i) v[i] = __ldcg(col + (size_t)(p + i * G) * st2);
 #pragma unroll
-                for (int i = 0; i < 8; ++i) { const float w = sc[p + i]; acc0 += (c0 == 3 ? w * w : w) * v[i]; }
+                    for (int i = 0; i < 8; ++i) {
+                        const float w = sc[p + i * G];
+                        acc[0].x = fmaf(w, v[i].x, acc[0].x);
+                        acc[0].y = fmaf(cp == 1 ? w * w : w, v[i].y, acc[0].y);
+                    }
+                }
+                for (; p < np; p += G) {
+                    const float2 v = __ldcg(col + (size_t)p * st2);
+                    const float w = sc[p];
+                    acc[0].x = fmaf(w, v.x, acc[0].x);
+                    acc[0].y = fmaf(cp == 1 ? w * w : w, v.y, acc[0].y);
+                }
             }
-            for (; p < np; ++p) { const float w = sc[p]; acc0 += (c0 == 3 ? w * w : w) * __ldcg(col + (size_t)p * stride); }
-        }
-        if (c1 < NF) {
-            const float *col = parts + (size_t)base * stride + c1;
-            for (int p = 0; p < np; ++p) acc1 += sc[p] * __ldcg(col + (size_t)p * stride);
+        } else {
+            for (int j = 0; j < PPT && j < 2; ++j) {
+                const int c2 = tid + j * MPPI_BLOCK;
+                if (c2 < 1 || c2 >= NP) continue;
+                const float2 *col = reinterpret_cast<const float2 *>(parts + (size_t)base * stride) + c2;
+                const size_t st2 = (size_t)stride >> 1;
+                for (int p = 0; p < np; ++p) {
+                    const float2 v = __ldcg(col + (size_t)p * st2);
+                    const float w = sc[p];
+                    acc[j].x = fmaf(w, v.x, acc[j].x);
+                    acc[j].y = fmaf(c2 == 1 ? w * w : w, v.y, acc[j].y);
+                }
+            }
         }
     }
-    if (c0 < NF) ms.col[c0] = acc0;
-    if (c1 < NF) ms.col[c1] = acc1;
+    if (G > 1) {
+        if (live) { red[g * MPPI_NF_MAX + 2 * cp] = acc[0].x; red[g * MPPI_NF_MAX + 2 * cp + 1] = acc[0].y; }
+        __syncthreads();
+        for (int c = 2 + tid; c < NF; c += MPPI_BLOCK) {
+            float t = red[c];
+            for (int gg = 1; gg < G; ++gg) t += red[gg * MPPI_NF_MAX + c];
+            ms.col[c] = t;
+        }
+    } else {
+        for (int j = 0; j < 2; ++j) {
+            const int c2 = tid + j * MPPI_BLOCK;
+            if (c2 >= 1 && c2 < NP) { ms.col[2 * c2] = acc[j].x; ms.col[2 * c2 + 1] = acc[j].y; }
+        }
+    }
     if (tid == 0) { ms.col[0] = __int_as_float(n); ms.col[1] = s; }
     __syncthreads();
 }
@@ -439,7 +482,7 @@ __global__ void __launch_bounds__(MPPI_BLOCK, STASH ? 2 : MPPI_MIN_BLOCKS) mppi_
 __global__ void __launch_bounds__(MPPI_BLOCK) mppi_merge_kernel(const __grid_constant__ TickArgs a,
                                                                  const float *triples, int G) {
     __shared__ MergeSmem ms;
-    __shared__ float sc[MPPI_MERGE_TILE];
+    __shared__ __align__(16) float sc[MPPI_MERGE_SCRATCH];
     merge_partials(a, triples, G, ms, sc);
     finalize_tick(a, 0, __float_as_int(a.out[2]), ms);
 }

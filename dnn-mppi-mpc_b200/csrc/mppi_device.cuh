@@ -171,6 +171,9 @@ __device__ __forceinline__ float2 f2_fma(float2 a, float2 b, float2 c) {
 // key_j = (d_j - m) * 2^100 + j, which is exactly j where d_j == m and >= 2^76 elsewhere, so
 // min_j key_j is the FIRST index attaining the minimum (the d.index(min(d)) / np.argmin rule).
 // The window arrays hold NEGATED coordinates so the differences are plain packed adds.
+#ifndef MPPI_WP_CHUNK_ILP
+#define MPPI_WP_CHUNK_ILP 1
+#endif
 #ifndef MPPI_ARGMIN_PACK
 #define MPPI_ARGMIN_PACK 2      // 2: all FP32 work packed (FFMA2); 1: differences scalar, rest packed; 0: all scalar
 #endif
@@ -233,7 +236,21 @@ __device__ __forceinline__ int nearest_wp(const TickSmem &sm, float x, float y) 
     float bm = CUDART_INF_F;
     int bj = 0;
     const int nch = sm.n_win16;
-    for (int c = 0; c < nch; ++c) {
+    int c = 0;
+#if MPPI_WP_CHUNK_ILP
+    // two chunks per trip: their (independent) distance / min / key chains overlap, which is what a latency-bound
+    // small-K tick needs; the earlier chunk still wins ties
+    for (; c + 1 < nch; c += 2) {
+        float m0, k0, m1, k1;
+        chunk_argmin<16>(nwx4 + 4 * c, nwy4 + 4 * c, x, y, m0, k0);
+        chunk_argmin<16>(nwx4 + 4 * c + 4, nwy4 + 4 * c + 4, x, y, m1, k1);
+        const bool second = m1 < m0;
+        const float m = second ? m1 : m0;
+        const int j = second ? 16 * c + 16 + __float2int_rn(k1) : 16 * c + __float2int_rn(k0);
+        if (m < bm) { bm = m; bj = j; }
+    }
+#endif
+    for (; c < nch; ++c) {
         float m, key;
         chunk_argmin<16>(nwx4 + 4 * c, nwy4 + 4 * c, x, y, m, key);
         if (m < bm) { bm = m; bj = 16 * c + __float2int_rn(key); }       // strict <: the earlier chunk wins ties

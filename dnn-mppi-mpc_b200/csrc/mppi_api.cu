@@ -78,6 +78,10 @@ struct mppi_handle_s {
     unsigned p2p_seq = 0;
     // MLP dynamics
     MlpState *mlp = nullptr;
+    // per-robot reference paths (batched fleets)
+    float4 *d_paths = nullptr;
+    int *d_path_len = nullptr;
+    int path_cap = 0;
     // top-N viewer: per-sample costs of the last tick and their sorted order
     bool keep_costs = false;
     float *d_Sc = nullptr, *d_Ssorted = nullptr;
@@ -323,6 +327,7 @@ int mppi_destroy(mppi_handle_t h) {
         for (int p = 0; p < h->world; ++p)
             if (p != h->rank && h->peer_buf[p]) cudaIpcCloseMemHandle(h->peer_buf[p]);
     cudaFree(h->d_xchg);
+    cudaFree(h->d_paths); cudaFree(h->d_path_len);
     cudaFree(h->d_Sc); cudaFree(h->d_Ssorted); cudaFree(h->d_sorted_idx); cudaFree(h->d_iota); cudaFree(h->d_sort_temp);
     if (h->mlp) mlp_destroy(h->mlp);
     cudaFree(h->d_path); cudaFree(h->d_U); cudaFree(h->d_M); cudaFree(h->d_S); cudaFree(h->d_part);
@@ -370,7 +375,55 @@ int mppi_set_ref_path(mppi_handle_t h, const double *path, int32_t n, int32_t nc
     h->path_h.assign(path, path + (size_t)n * ncol);
     h->n_path = n; h->path_cols = ncol;
     h->args.path = h->d_path; h->args.n_path = n;
+    h->args.path_len = nullptr; h->args.path_stride = 0;          // back to one shared path
     h->have_path = true;
+    return MPPI_OK;
+}
+
+int mppi_set_ref_paths_spline(mppi_handle_t h, const float *d_wx, const float *d_wy, int32_t n_wp, double ds, int32_t max_points) {
+    if (!h || !d_wx || !d_wy || n_wp < 2 || n_wp > MPPI_SPLINE_MAX_WAYPOINTS || !(ds > 0.0) || max_points < 2) return MPPI_E_BADARG;
+    if (h->cfg.cost_kind != MPPI_COSTKIND_PATH) return fail(h, MPPI_E_STATE, "goal / target cost kinds take no reference path");
+    if (h->strict || h->mlp) return fail(h, MPPI_E_UNSUPPORTED, "per-robot paths: frozen waypoint mode, analytic dynamics");
+    if (h->cfg.model == MPPI_MODEL_BICYCLE) return fail(h, MPPI_E_UNSUPPORTED, "calc_spline_course yields (x, y, yaw): diff-drive paths");
+    CK(h, cudaSetDevice(h->cfg.device));
+    const int R = h->cfg.n_robots;
+    if (h->path_cap < max_points) {
+        CK(h, cudaStreamSynchronize(h->stream));
+        cudaFree(h->d_paths); h->d_paths = nullptr;
+        CK(h, cudaMalloc(&h->d_paths, sizeof(float4) * (size_t)R * max_points));
+        h->path_cap = max_points;
+    }
+    if (!h->d_path_len) CK(h, cudaMalloc(&h->d_path_len, sizeof(int) * R));
+    CK(h, mppi_launch_spline(d_wx, d_wy, R, n_wp, ds, h->path_cap, h->d_paths, h->d_path_len, h->stream));
+    h->tm.launches++;
+    std::vector<int> len((size_t)R);
+    CK(h, cudaMemcpyAsync(len.data(), h->d_path_len, sizeof(int) * R, cudaMemcpyDeviceToHost, h->stream));
+    CK(h, cudaStreamSynchronize(h->stream));
+    for (int r = 0; r < R; ++r)
+        if (len[r] < 1) return fail(h, MPPI_E_BADARG, "a robot's course needs more than max_points samples (or its waypoints coincide)");
+    h->args.path = h->d_paths; h->args.path_len = h->d_path_len; h->args.path_stride = h->path_cap;
+    h->args.n_path = 0;
+    h->have_path = true;
+    return MPPI_OK;
+}
+
+int mppi_get_ref_path(mppi_handle_t h, int32_t robot, float *path_out, int32_t capacity, int32_t *n_out) {
+    if (!h || !n_out || robot < 0 || robot >= h->cfg.n_robots || capacity < 0) return MPPI_E_BADARG;
+    if (!h->have_path || h->cfg.cost_kind != MPPI_COSTKIND_PATH) return fail(h, MPPI_E_STATE, "no reference path set");
+    CK(h, cudaSetDevice(h->cfg.device));
+    int n = h->n_path;
+    const float4 *src = h->d_path;
+    if (h->args.path_len) {
+        CK(h, cudaMemcpyAsync(&n, h->d_path_len + robot, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+        CK(h, cudaStreamSynchronize(h->stream));
+        src = h->d_paths + (size_t)robot * h->path_cap;
+    }
+    *n_out = n;
+    if (path_out) {
+        const int m = n < capacity ? n : capacity;
+        CK(h, cudaMemcpyAsync(path_out, src, sizeof(float4) * m, cudaMemcpyDeviceToHost, h->stream));
+        CK(h, cudaStreamSynchronize(h->stream));
+    }
     return MPPI_OK;
 }
 

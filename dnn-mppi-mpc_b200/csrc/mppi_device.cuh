@@ -63,7 +63,9 @@ struct TickArgs {
     uint32_t seed_lo, seed_hi, tick;
     int idx_host, flags;
     // pointers (device)
-    const float4 *path;               // [n_path] (x, y, yaw, v)
+    const float4 *path;               // [n_path] (x, y, yaw, v); per-robot paths: [R][path_stride], robot r uses path_len[r] rows
+    const int *path_len;              // null: every robot follows the one shared path
+    int path_stride;
     const float *x0_dev;              // batched: [R][4], else null
     float *U;                         // [R][T][2] nominal, updated in place
     int *idx;                         // [R] carried waypoint index

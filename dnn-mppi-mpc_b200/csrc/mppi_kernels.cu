@@ -238,6 +238,9 @@ __global__ void __launch_bounds__(MPPI_BLOCK, STASH ? 2 : MPPI_MIN_BLOCKS) mppi_
     // ---- prologue: observed state, step-1 index update (A8 with update=True), window, nominal
     if (tid < 4) sm.x0[tid] = a.x0_dev ? a.x0_dev[robot * 4 + tid] : a.x0[tid];
     __syncthreads();
+    // the robot's reference path: shared, or its own row of the per-robot table (mppi_set_ref_paths_spline)
+    const float4 *rpath = a.path_len ? a.path + (size_t)robot * a.path_stride : a.path;
+    const int n_path = a.path_len ? a.path_len[robot] : a.n_path;
     int s_new;
     if (WIN < 0) {
         s_new = 0;                                      // goal / target cost kinds: no reference path, no carried index
@@ -246,8 +249,8 @@ __global__ void __launch_bounds__(MPPI_BLOCK, STASH ? 2 : MPPI_MIN_BLOCKS) mppi_
     } else {
         const int s_old = a.idx[robot];
         unsigned long long key = ~0ull;
-        for (int j = tid; j < a.window && s_old + j < a.n_path; j += MPPI_BLOCK) {
-            const float4 p = a.path[s_old + j];
+        for (int j = tid; j < a.window && s_old + j < n_path; j += MPPI_BLOCK) {
+            const float4 p = rpath[s_old + j];
             const float dx = sm.x0[0] - p.x, dy = sm.x0[1] - p.y;
             const unsigned long long kj = ((unsigned long long)__float_as_uint(dx * dx + dy * dy) << 32) | (unsigned)j;
             key = kj < key ? kj : key;
@@ -265,12 +268,12 @@ __global__ void __launch_bounds__(MPPI_BLOCK, STASH ? 2 : MPPI_MIN_BLOCKS) mppi_
         s_new = s_old + (int)(key & 0xffffffffu);
     }
     {
-        int nw = a.n_path - s_new; nw = nw < a.window ? nw : a.window;
+        int nw = n_path - s_new; nw = nw < a.window ? nw : a.window;
         // static-window kernels read exactly 20 entries, dynamic ones whole chunks of 16
         const int fill = (WIN < 0) ? 0 : (WIN == 20) ? 20 : ((nw + 15) & ~15);
         for (int j = tid; j < fill; j += MPPI_BLOCK) {
             if (j < nw) {
-                const float4 p = a.path[s_new + j];
+                const float4 p = rpath[s_new + j];
                 sm.wx[j] = -p.x; sm.wy[j] = -p.y; sm.wyv[j] = make_float2(p.z, p.w);
             } else {
                 sm.wx[j] = -MPPI_SENTINEL; sm.wy[j] = -MPPI_SENTINEL; sm.wyv[j] = make_float2(0.f, 0.f);

@@ -10,6 +10,10 @@ cudaError_t mppi_launch_strict(const TickArgs &a, int model, int coll, bool sum,
 cudaError_t mppi_launch_merge(const TickArgs &a, const float *triples, int G, cudaStream_t st);
 cudaError_t mppi_launch_traj(const TickArgs &a, int model, const float *rec, float *d_opt, float *d_samp,
                              const int *d_sel, int n_sel, int shift, cudaStream_t st);
+// mppi_spline.cu: per-robot courses from waypoints (calc_spline_course on the device)
+#define MPPI_SPLINE_MAX_WAYPOINTS 32
+cudaError_t mppi_launch_spline(const float *d_wx, const float *d_wy, int n_robots, int n_wp, double ds, int max_pts,
+                               float4 *d_paths, int *d_path_len, cudaStream_t st);
 // mppi_topn.cu: ascending (cost, sample index) order of K costs -- np.argsort(S) of the viewers
 size_t mppi_sort_costs_temp_bytes(int K);
 cudaError_t mppi_sort_costs(const float *d_S, int K, float *d_S_sorted, int *d_idx_sorted, int *d_iota, void *d_temp,

@@ -54,6 +54,8 @@ SYMBOLS = {
     "mppi_set_stream": (C.c_int, [_H, C.c_void_p]),
     "mppi_synchronize": (C.c_int, [_H]),
     "mppi_set_ref_path": (C.c_int, [_H, _PD, C.c_int32, C.c_int32]),
+    "mppi_set_ref_paths_spline": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_int32, C.c_double, C.c_int32]),
+    "mppi_get_ref_path": (C.c_int, [_H, C.c_int32, _PF, C.c_int32, _PI]),
     "mppi_set_obstacles": (C.c_int, [_H, _PD, C.c_int32]),
     "mppi_set_goal": (C.c_int, [_H, _PD, C.c_int32]),
     "mppi_set_moving_obstacles": (C.c_int, [_H, _PD, _PD, C.c_int32]),

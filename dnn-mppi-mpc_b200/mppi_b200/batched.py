@@ -27,11 +27,28 @@ class BatchedMPPI:
             window=window, cost_mode=cost_mode, waypoint_mode="frozen",
             filter_kind="racecar" if bicycle else "diffdrive", yaw_wrap=bicycle, collision=collision,
             obstacles=obstacle_circles, margin=margin, wheel_base=wheel_base, n_robots=self.R, device=device)
-        self._engine.set_ref_path(ref_path)
+        if ref_path is not None:
+            self._engine.set_ref_path(ref_path)
         import torch
         # run on torch's current stream so tensors produced/consumed by torch are naturally ordered
         self._engine.set_stream(torch.cuda.current_stream(device).cuda_stream)
         self._u0 = torch.zeros(self.R, 2, dtype=torch.float32, device="cuda:%d" % device)
+
+    def set_waypoints(self, wx, wy, ds=0.1, max_points=512):
+        """One reference path PER ROBOT, generated on the device from (R, n_wp) waypoints by the reference's own course
+        generator `calc_spline_course(x, y, ds)` (path_generator/cubic_spline_planner.py:311-323; what the reference
+        mains do once on the host, controllers/mppi_differential_drive_cuda.py:400-403).  Accepts numpy arrays or
+        CUDA tensors; construct with ref_path=None to start without a shared path."""
+        import torch
+        dev = "cuda:%d" % self._engine.device
+        wx = torch.as_tensor(wx, dtype=torch.float32, device=dev).contiguous()
+        wy = torch.as_tensor(wy, dtype=torch.float32, device=dev).contiguous()
+        torch.cuda.current_stream(self._engine.device).synchronize()
+        self._engine.set_ref_paths_spline(wx, wy, ds, max_points)
+
+    def ref_path(self, robot=0):
+        """(N,3) [x, y, yaw] course robot `robot` follows."""
+        return self._engine.get_ref_path(robot)[:, :3]
 
     @property
     def engine(self):

@@ -97,6 +97,22 @@ class MPPIEngine:
         p = np.ascontiguousarray(path, dtype=np.float64)
         self._ck(self.lib.mppi_set_ref_path(self._h, p.ctypes.data_as(_lib._PD), p.shape[0], p.shape[1]), "mppi_set_ref_path")
 
+    def set_ref_paths_spline(self, d_wx, d_wy, ds=0.1, max_points=512):
+        """Per-robot courses generated on the device from (R, n_wp) float32 CUDA waypoint tensors (the reference's
+        calc_spline_course, path_generator/cubic_spline_planner.py:311-323)."""
+        if tuple(d_wx.shape) != tuple(d_wy.shape) or d_wx.shape[0] != self.R or not (d_wx.is_contiguous() and d_wy.is_contiguous()):
+            raise ValueError("waypoints must be contiguous (R, n_wp) float32 CUDA tensors")
+        self._ck(self.lib.mppi_set_ref_paths_spline(self._h, _dptr(d_wx), _dptr(d_wy), int(d_wx.shape[1]), float(ds),
+                                                    int(max_points)), "mppi_set_ref_paths_spline")
+
+    def get_ref_path(self, robot=0):
+        n = C.c_int32(0)
+        self._ck(self.lib.mppi_get_ref_path(self._h, int(robot), None, 0, C.byref(n)), "mppi_get_ref_path")
+        out = np.zeros((n.value, 4), dtype=np.float32)
+        self._ck(self.lib.mppi_get_ref_path(self._h, int(robot), out.ctypes.data_as(_lib._PF), n.value, C.byref(n)),
+                 "mppi_get_ref_path")
+        return out
+
     def set_obstacles(self, obstacles):
         o = np.ascontiguousarray(obstacles, dtype=np.float64).reshape(-1, 3)
         self._ck(self.lib.mppi_set_obstacles(self._h, o.ctypes.data_as(_lib._PD), o.shape[0]), "mppi_set_obstacles")

@@ -137,6 +137,18 @@ int mppi_synchronize(mppi_handle_t h);
 /* `self.ref_path` (N,3) [x,y,yaw] or (N,4) [x,y,yaw,v], row-major doubles
  * (mppi_differential_drive.py:64; re-assigned after construction at mppi_race_car_obstacle.py:332) */
 int mppi_set_ref_path(mppi_handle_t h, const double *path, int32_t n, int32_t ncol);
+/* Fleets with ONE PATH PER ROBOT (batched handles): robot r's course is generated on the device
+ * from its n_wp waypoints by the reference's own course generator -- `calc_spline_course(x, y, ds)`
+ * (path_generator/cubic_spline_planner.py:311-323: arclength-parameterised natural cubic spline, sampled every ds,
+ * yaw = atan2 of the first derivatives; FP64 like the reference) -- and installed as that robot's `ref_path`.
+ *   d_wx, d_wy   device (n_robots, n_wp) float32 waypoint coordinates, 2 <= n_wp <= 32
+ *   max_points   capacity per robot; MPPI_E_BADARG if a course needs more than that
+ * mppi_set_ref_path afterwards returns the handle to one shared path.  Frozen waypoint mode, diff-drive models. */
+int mppi_set_ref_paths_spline(mppi_handle_t h, const float *d_wx, const float *d_wy, int32_t n_wp, double ds,
+                              int32_t max_points);
+/* The path robot `robot` follows, as (n, 4) float32 rows [x, y, yaw, v]: n to *n_out, min(n, capacity) rows to
+ * path_out (host, may be NULL to query n). */
+int mppi_get_ref_path(mppi_handle_t h, int32_t robot, float *path_out, int32_t capacity, int32_t *n_out);
 /* `self.obstacle_circles` (M,3) [x,y,r] (mppi_race_car_obstacle.py:57) */
 int mppi_set_obstacles(mppi_handle_t h, const double *xyr, int32_t m);
 /* `self.goal_point` (x, y) of the goal-point controller (test/mppi_differential_drive_obs.py:65), or the desired

@@ -163,6 +163,30 @@ def make_mlp_golden():
     print("wrote", fn, "%.1f KB" % (os.path.getsize(fn) / 1024))
 
 
+def make_spline_golden():
+    """Courses of the reference's own calc_spline_course (path_generator/cubic_spline_planner.py:311-323) for a few
+    waypoint sets (4-12 waypoints, spacings 0.05-0.25): the pin of oracle/spline_oracle.py and, through it, of the
+    device-side per-robot path generation."""
+    ref = ref_loader.load_reference()
+    rng = np.random.default_rng(31)
+    out = {}
+    meta = []
+    for i, (n, ds) in enumerate(((4, 0.1), (5, 0.25), (7, 0.1), (9, 0.05), (12, 0.2), (6, 0.1))):
+        ang = np.cumsum(rng.normal(0, 0.6, n))
+        step = rng.uniform(0.8, 2.5, n)
+        wx = np.cumsum(step * np.cos(ang)) + rng.normal(0, 2.0)
+        wy = np.cumsum(step * np.sin(ang)) + rng.normal(0, 2.0)
+        cx, cy, cyaw, _, _ = ref["calc_spline_course"](list(wx), list(wy), ds=ds)
+        out["wx%d" % i], out["wy%d" % i] = wx, wy
+        out["course%d" % i] = np.array([cx, cy, cyaw]).T
+        meta.append(dict(n_wp=n, ds=ds, n_pts=len(cx)))
+    out["meta"] = json.dumps(dict(cases=meta, numpy=np.__version__,
+                                  source="path_generator/cubic_spline_planner.py:calc_spline_course, unmodified"))
+    fn = os.path.join(HERE, "spline_courses.npz")
+    np.savez_compressed(fn, **out)
+    print("wrote", fn, "%.1f KB" % (os.path.getsize(fn) / 1024))
+
+
 def main():
     ref = ref_loader.load_reference()
     path = spline_path(ref)
@@ -265,6 +289,7 @@ def main():
 
     make_extras()
     make_mlp_golden()
+    make_spline_golden()
 
     # ---- literal filter operators as matrices (Q7)
     Ms = {}
@@ -282,5 +307,7 @@ if __name__ == "__main__":
         make_extras()               # only the SURVEY 8f row-3 fixtures (the others stay byte-identical)
     elif len(sys.argv) > 1 and sys.argv[1] == "mlp":
         make_mlp_golden()
+    elif len(sys.argv) > 1 and sys.argv[1] == "spline":
+        make_spline_golden()
     else:
         main()

@@ -237,3 +237,18 @@ def test_oracle_mlp_matches_the_trained_reference_model():
     w["out_mean"], w["out_scale"] = sc["error_scaler"].mean_, sc["error_scaler"].scale_
     y = orc.mlp_forward(w, X[:, :3], X[:, 3:])
     assert np.max(np.abs(y - y_ref)) <= 1e-10 * max(1.0, np.max(np.abs(y_ref)))
+
+
+def test_spline_course_restatement_is_bit_exact():
+    """calc_spline_course (path_generator/cubic_spline_planner.py:311-323) restated in
+    oracle/spline_oracle.py vs courses produced by the unmodified reference function."""
+    import json
+    from golden_util import GOLDEN_DIR
+    from oracle.spline_oracle import spline_course
+    g = np.load(os.path.join(GOLDEN_DIR, "paths.npz"))["spline"]
+    c = spline_course([0.0, 0.5, 1.0, 3.0, 3.0, 1.0, -4.0], [0.0, 1.0, 1.0, 2.0, 5.0, 1.0, -1.0], 0.1)
+    assert np.array_equal(c, g)
+    z = np.load(os.path.join(GOLDEN_DIR, "spline_courses.npz"))
+    for i, case in enumerate(json.loads(str(z["meta"]))["cases"]):
+        c = spline_course(z["wx%d" % i], z["wy%d" % i], case["ds"])
+        assert c.shape == (case["n_pts"], 3) and np.array_equal(c, z["course%d" % i]), i

@@ -354,6 +354,48 @@ def run_b200_arm(args):
             "frac_of_tensor_peak_executed": 65536 * 30 * 2 * 512 * 512 / (ms_mlp * 1e-3) / 1e12 / pk.get("bf16_tflops", 1590.0),
             "note": "Linear(3,512) has no activation and is folded into the first hidden layer on the host, so one 512x512 GEMM is executed per step"}
         cm.engine.close()
+        # the trained models' shape -- 5 inputs [x, y, yaw, v, w] + StandardScaler statistics
+        mlp5 = dict(mlp)
+        mlp5["W0"] = (rngw.uniform(-1, 1, (512, 5)) / np.sqrt(5)).astype(np.float32)
+        c5 = MPPIAlgorithms(**diffdrive_kwargs(65536, 30, 2.0), seed=7, dynamics=mlp5)
+        c5.set_dynamics(mlp5, scalers=dict(in_mean=[4.39, -0.126, -0.08, 0.359, -0.031], in_scale=[5.587, 3.641, 1.06, 1.024, 1.836],
+                                           out_mean=[-0.561, 0.029, -0.015], out_scale=[5.701, 3.59, 0.996]))
+        c5.engine.set_stream(stream.cuda_stream)
+        for i in range(3):
+            c5.engine.step_async(x0, None, 7, i)
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(stream):
+            a.record(stream)
+            for i in range(10):
+                c5.engine.step_async(x0, None, 7, 10 + i)
+            b.record(stream)
+        torch.cuda.synchronize()
+        extras["mlp5_scaled_K65536_H30"] = {"ms_per_tick": a.elapsed_time(b) / 10,
+                                            "sample_steps_per_sec": 65536 * 30 / (a.elapsed_time(b) / 10 * 1e-3)}
+        c5.engine.close()
+        # goal-point diff-drive MPPI (test/mppi_differential_drive_obs.py), throughput shape
+        from mppi_b200.mppi_differential_drive_goal import MPPIAlgorithms as GoalMPPI
+        cg = GoalMPPI(delta_t=0.1, goal_point=np.array([5.0, 5.0]), max_speed=10.0, max_omega=5.0, num_samples_K=K_PER_GPU,
+                      num_horizons_T=T_H, param_exploration=0.1, param_lambda=1.0, param_alpha=0.98,
+                      sigma=np.array([[0.1, 0.0], [0.0, 0.01]]), stage_cost_weight=10 * np.array([5.0, 9.0]),
+                      terminal_cost_weight=10 * np.array([5.0, 9.0]), obstacle_circles=np.array([[5.0, 3.0, 0.5], [3.0, 2.5, 0.5]]),
+                      safety_margin_rate=0.8, visualize_optimal_traj=False, visualze_sampled_trajs=False, cost_mode="sum",
+                      temperature=10.0, seed=7)
+        cg.engine.set_stream(stream.cuda_stream)
+        for i in range(3):
+            cg.engine.step_async(x0, None, 7, i)
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(stream):
+            a.record(stream)
+            for i in range(10):
+                cg.engine.step_async(x0, None, 7, 10 + i)
+            b.record(stream)
+        torch.cuda.synchronize()
+        extras["goal_point_K1M_H50_sum"] = {"ms_per_tick": a.elapsed_time(b) / 10,
+                                            "sample_steps_per_sec": K_PER_GPU * T_H / (a.elapsed_time(b) / 10 * 1e-3)}
+        cg.engine.close()
 
     # ---- roofline of the dominant kernel (mppi_tick_kernel): FP32 issue-bound, not HBM-bound
     peaks = measured_peaks()
@@ -395,7 +437,7 @@ def run_b200_arm(args):
                    "l2": "flushed between timed steps (256 MiB memset, outside the per-step event pair)",
                    "parallelism": "samples sharded, %d rank(s)" % world},
         "e2e": {"value": e2e_value, "unit": "sample-steps/s", "h2d_bytes_per_step": 16,
-                "d2h_bytes_per_step": 4 * (8 + 2 * T_H), "p50_ms": 1e3 * float(lat[len(lat) // 2]),
+                "d2h_bytes_per_step": 4 * (10 + 2 * T_H), "p50_ms": 1e3 * float(lat[len(lat) // 2]),
                 "api": "MPPIAlgorithms._calc_input_control(host x0) -> host u0, u_seq"},
         "gpu_launches": int(launches),
         "clocks": clocks,

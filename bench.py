@@ -407,7 +407,9 @@ def run_b200_arm(args):
     hbm_bytes = 4.0 * 296 * (4 + 2 * T_H) * 2 + 4 * (8 + 4 * 128)       # block partials written + re-read by the last block, out record
     roofline = {
         "bound": "fp32", "achieved": achieved_tf, "peak": peak_tf_max, "unit": "TFLOP/s",
-        "frac": achieved_tf / peak_tf_max, "traffic": None,
+        "frac": achieved_tf / peak_tf_max,
+        # dram__bytes_read.sum + dram__bytes_write.sum of one launch of this kernel (ncu --set full, profiles/r1_tick_kernel_ncu.txt)
+        "traffic": 87296.0, "traffic_unit": "bytes/launch (DRAM; the kernel reads no per-sample data)",
         "peak_source": "derived 148 SM x 128 lanes x 2 x clocks.max.sm (FP32 peak is not in MEASURED_PEAKS.json)",
         "algorithmic_flop_per_sample_step": FLOP_PER_SAMPLE_STEP,
         "sm_mhz_during_run": f_mhz,

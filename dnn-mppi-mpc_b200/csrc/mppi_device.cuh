@@ -176,6 +176,9 @@ __device__ __forceinline__ float2 f2_fma(float2 a, float2 b, float2 c) {
 #ifndef MPPI_WP_CHUNK_ILP
 #define MPPI_WP_CHUNK_ILP 1
 #endif
+#ifndef MPPI_ARGMIN_KEY_SEL
+#define MPPI_ARGMIN_KEY_SEL 0   // 1: first-min index by FSETP/SEL chains on the ALU pipe (A/B variant, see profiles/)
+#endif
 #ifndef MPPI_ARGMIN_PACK
 #define MPPI_ARGMIN_PACK 2      // 2: all FP32 work packed (FFMA2); 1: differences scalar, rest packed; 0: all scalar
 #endif
@@ -208,6 +211,35 @@ __device__ __forceinline__ void chunk_argmin(const float4 *nwx4, const float4 *n
     float m = fminf(d[0].x, d[0].y);
 #pragma unroll
     for (int i = 1; i < CH / 2; ++i) m = fminf(fminf(m, d[i].x), d[i].y);
+#if MPPI_ARGMIN_KEY_SEL
+    // index of the first minimum on the ALU pipe: descending select chains (the lowest index is written last), four
+    // independent chains of CH/4 entries; FSETP + SEL per entry instead of FADD2 + FFMA2 per pair on the FMA pipe
+    {
+        float k0 = (float)CH, k1 = (float)CH, k2 = (float)CH, k3 = (float)CH;
+#pragma unroll
+        for (int i = CH / 8 - 1; i >= 0; --i) {
+            const int a0 = i, a1 = i + CH / 8, a2 = i + 2 * (CH / 8), a3 = i + 3 * (CH / 8);     // float2 slots of the 4 chains
+            k0 = d[a0].y == m ? (float)(2 * a0 + 1) : k0; k0 = d[a0].x == m ? (float)(2 * a0) : k0;
+            k1 = d[a1].y == m ? (float)(2 * a1 + 1) : k1; k1 = d[a1].x == m ? (float)(2 * a1) : k1;
+            k2 = d[a2].y == m ? (float)(2 * a2 + 1) : k2; k2 = d[a2].x == m ? (float)(2 * a2) : k2;
+            k3 = d[a3].y == m ? (float)(2 * a3 + 1) : k3; k3 = d[a3].x == m ? (float)(2 * a3) : k3;
+        }
+        if (CH % 8) {                                   // CH = 20: slots 8, 9 are left over by the 4 x 2 split
+#pragma unroll
+            for (int a = CH / 2 - 1; a >= 4 * (CH / 8); --a) {
+                k3 = d[a].y == m ? (float)(2 * a + 1) : k3; k3 = d[a].x == m ? (float)(2 * a) : k3;
+            }
+            // chain 3 now covers slots 6, 7 (written earlier) and 8, 9 (written later): redo 6, 7 so the lower index wins
+#pragma unroll
+            for (int a = 4 * (CH / 8) - 1; a >= 3 * (CH / 8); --a) {
+                k3 = d[a].y == m ? (float)(2 * a + 1) : k3; k3 = d[a].x == m ? (float)(2 * a) : k3;
+            }
+        }
+        m_out = m;
+        key_out = fminf(fminf(k0, k1), fminf(k2, k3));
+        return;
+    }
+#endif
     const float2 nm = make_float2(-m, -m), huge = make_float2(1.2676506e30f, 1.2676506e30f);
     float key = CUDART_INF_F;
 #pragma unroll

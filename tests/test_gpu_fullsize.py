@@ -1,0 +1,115 @@
+"""BASELINE.json configurations at their FULL sizes through the C ABI (config 5 / K=1M lives in
+test_gpu_parity.py::test_large_K_full_size_property): the device result against the oracle fed the exported
+Philox noise, on every sample where the oracle finishes in seconds (C oracle) or on a random subset (FP64 MLP)."""
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+from golden_util import Golden  # noqa: E402
+from gpu_util import engine_from_spec  # noqa: E402
+from oracle import c_oracle as co  # noqa: E402
+from oracle import mppi_oracle as orc  # noqa: E402
+
+COST_RTOL = 1e-5
+U_ATOL = 2e-5
+
+
+def test_config1_racecar_obstacles_K16384_H50():
+    """configs[1]: race-car kinematic-bicycle MPPI with static obstacle cost, K=16384, H=50, the class's literal
+    semantics (sum cost, window 200, footprint-vs-circle penalty, temperature = param_lambda)."""
+    g = Golden("racecar_default")
+    K, T = 16384, 50
+    sp = orc.racecar_spec(K=K, T=T, dtype=np.float64)
+    eng = engine_from_spec(sp, g.path)
+    eps = torch.zeros(K, T, 2, dtype=torch.float32, device="cuda")
+    S = torch.zeros(K, dtype=torch.float32, device="cuda")
+    U = np.zeros((T, 2))
+    idx = 0
+    for tick, i in enumerate((0, 12, 30)):
+        x0 = g.path[i].astype(np.float64) + np.array([0.2, -0.1, 0.03, 0.4]) * tick
+        eng.generate_noise(eps, seed=77, tick=tick)
+        e = eps.cpu().numpy()
+        eng.set_nominal(U.astype(np.float32)); eng.set_waypoint_idx(idx)
+        eng.rollout_costs(x0, S, None, seed=77, tick=tick)
+        So, _, _ = co.costs(sp, g.path, U, idx, x0, e)
+        Sg = S.cpu().numpy().astype(np.float64)
+        same_coll = np.round(Sg / 1e10) == np.round(So / 1e10)
+        bad = np.nonzero(~same_coll | (np.abs(Sg - So) > 1e-6 + COST_RTOL * np.abs(So)))[0]
+        # discrete decisions (nearest waypoint, footprint point inside a circle) may flip where FP32 and FP64 see a
+        # near-tie: a small fraction, and every such sample must BE a near-tie for the FP64 oracle
+        assert bad.size <= 1e-3 * K, (tick, bad.size)
+        if bad.size:
+            wp_m, coll_m = orc.decision_margins(sp, g.path, U, idx, x0, e[bad])
+            assert np.all(np.minimum(wp_m, coll_m) < 1e-4), (tick, bad.size, np.minimum(wp_m, coll_m).max())
+        eng.set_waypoint_idx(idx)
+        u0, useq = eng.step(x0, None, seed=77, tick=tick)
+        o = co.update(sp, g.path, U, np.where(np.isin(np.arange(K), bad), Sg, So), e)
+        _, i1, _ = co.costs(orc.racecar_spec(K=1, T=T, dtype=np.float64), g.path, U, idx, x0, e[:1])
+        assert np.max(np.abs(useq - o["U_after"])) <= 5e-5, (tick, np.max(np.abs(useq - o["U_after"])))
+        assert eng.get_waypoint_idx() == i1
+        U, idx = useq.astype(np.float64), i1
+    eng.close()
+
+
+def test_config2_mlp_K65536_H30_random_subset():
+    """configs[2]: learned dynamics (dnn/simple_mlp shapes, random-init weights), K=65536, H=30: per-sample costs of
+    a random subset against the FP64 oracle, then the full tick's update against the oracle update fed the device's
+    own costs (the update kernel is exact to 2e-5; the costs carry the bf16 GEMM tolerance)."""
+    g = Golden("diffdrive_pe0.05")
+    K, T = 65536, 30
+    mlp = orc.make_mlp(seed=0, out_scale=0.01)
+    sp = orc.diffdrive_spec(K=K, T=T, param_exploration=0.05, cost_mode="sum", waypoint_mode="frozen",
+                            model="diffdrive_mlp", mlp=mlp)
+    sp.temperature = 2.0
+    eng = engine_from_spec(sp, g.path)
+    eng.set_mlp([mlp["W%d" % i] for i in range(4)], [mlp["b%d" % i] for i in range(4)])
+    eps = torch.zeros(K, T, 2, dtype=torch.float32, device="cuda")
+    eng.generate_noise(eps, seed=9, tick=2)
+    S = torch.zeros(K, dtype=torch.float32, device="cuda")
+    x0 = np.array([0.4, 0.3, 0.5])
+    U = np.random.default_rng(1).normal(0, 0.3, (T, 2)).astype(np.float32)
+    eng.set_nominal(U)
+    eng.rollout_costs(x0, S, None, seed=9, tick=2)
+    Sg = S.cpu().numpy().astype(np.float64)
+    n_exploit = sp.n_exploit()
+    rng = np.random.default_rng(3)
+    for lo, hi, pe in ((0, n_exploit, 0.0), (n_exploit, K, 1.0)):            # exploit and explore samples (Q6)
+        sub = np.sort(rng.choice(np.arange(lo, hi), 1024, replace=False))
+        sps = orc.diffdrive_spec(K=sub.size, T=T, param_exploration=pe, cost_mode="sum", waypoint_mode="frozen",
+                                 model="diffdrive_mlp", mlp=mlp)
+        So, _, _ = orc.costs_vec(sps, g.path, U.astype(np.float64), 0, x0, eps[torch.from_numpy(sub).cuda()].cpu().numpy().astype(np.float64))
+        rel = np.abs(Sg[sub] - So) / np.maximum(np.abs(So), 1e-9)
+        assert np.quantile(rel, 0.99) <= 2e-3 and rel.max() <= 2e-2, (lo, rel.max())
+    eng.set_nominal(U)
+    eng.set_waypoint_idx(0)
+    u0, useq = eng.step(x0, None, seed=9, tick=2)
+    spd = orc.diffdrive_spec(K=K, T=T, param_exploration=0.05, cost_mode="sum", waypoint_mode="frozen")
+    spd.temperature = 2.0
+    o = co.update(spd, g.path, U.astype(np.float64), Sg, eps.cpu().numpy())
+    assert np.max(np.abs(useq - o["U_after"])) <= U_ATOL
+    eng.close()
+
+
+def test_config3_fleet_4096_robots_random_subset():
+    """configs[3]: 4096 independent controllers x K=1024 x H=30 in one launch; a random subset of robots against
+    independent oracle ticks fed each robot's own Philox stream."""
+    from mppi_b200.batched import BatchedMPPI
+    path = Golden("diffdrive_pe0.05").path
+    R, K, T = 4096, 1024, 30
+    b = BatchedMPPI(R, path, num_samples_K=K, num_horizons_T=T, temperature=2.0, seed=3)
+    rng = np.random.default_rng(0)
+    x0 = np.stack([np.append(path[r % 150, :2] + rng.normal(0, 0.1, 2), path[r % 150, 2] + rng.normal(0, 0.1)) for r in range(R)])
+    x0_d = torch.from_numpy(x0.astype(np.float32)).cuda().contiguous()
+    u0 = b.step(x0_d).cpu().numpy()
+    Unew, inew = b.nominal(), b.waypoint_idx()
+    sp = orc.diffdrive_spec(K=K, T=T, param_exploration=0.05, cost_mode="sum", waypoint_mode="frozen")
+    sp.temperature = 2.0
+    eps = torch.zeros(K, T, 2, dtype=torch.float32, device="cuda")
+    for r in rng.choice(R, 8, replace=False):
+        b.engine.generate_noise(eps, seed=3, tick=0, robot=int(r))
+        o = co.tick(sp, path, np.zeros((T, 2)), 0, x0_d[r].cpu().numpy().astype(np.float64), eps.cpu().numpy())
+        assert np.max(np.abs(Unew[r] - o["U_after"])) <= U_ATOL, r
+        assert np.max(np.abs(u0[r] - o["u0"])) <= U_ATOL and inew[r] == o["idx_after"]
+    b.engine.close()

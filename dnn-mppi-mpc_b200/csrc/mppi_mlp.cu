@@ -27,7 +27,7 @@
 // (template NIN = 5): the folded first layer takes (x, y, yaw, v, w), so the owner thread generates the control of step
 // t+1 while the GEMM of step t runs and publishes it with the state.  StandardScaler pre/post-processing
 // (test/test_diff_dyna_eval.py:54-56) is folded into the first / last layer on the host.
-// Warp roles: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2..17 = 16 compute
+// Warp roles: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer (both run converged, one elected lane issues), warps 2..17 = 16 compute
 // warps (four per TMEM lane quarter; group g = (warp-2)/4 takes 32 columns of every 128-column part of the
 // activations and of every accumulator quarter, so MMA start and epilogue tail are both short).
 #include <cuda.h>
@@ -167,6 +167,15 @@ __device__ __forceinline__ uint32_t tanh_bf16x2(float lo, float hi) {
     asm("tanh.approx.bf16x2 %0, %1;" : "=r"(y) : "r"(p));
     return y;
 }
+// one lane of a CONVERGED warp (elect.sync): the MMA / TMA issue loops run warp-converged with the issuing
+// instructions predicated on this, so ptxas emits each UTCHMMA once with uniform-register operands instead of the
+// elect / execute / retire loop it needs inside a divergent `if (lane == 0)` region (8 SASS instructions and ~80
+// cycles per MMA there, more than the 64 cycles the MMA itself takes)
+__device__ __forceinline__ bool elect_one_sync() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
@@ -258,57 +267,62 @@ mppi_mlp_rollout_kernel(const __grid_constant__ TickArgs a, const __grid_constan
 
     if (warp == 0) {
         // ===== TMA producer: the same 16 W2 boxes every timestep, through a B_STAGES ring =====
-        if (lane == 0) {
-            constexpr int STAGES_PER_Q = HID / KCH / KCH_PER_STAGE;       // 4 stage loads per accumulator quarter
-            const int total = my_tiles * T * N_QUARTERS * STAGES_PER_Q;
-            int stage = 0; uint32_t phase = 0;
-            for (int it = 0; it < total; ++it) {
-                const int kb2 = it % STAGES_PER_Q, nq = (it / STAGES_PER_Q) % N_QUARTERS;
-                mbar_wait(&ms.b_empty[stage], phase ^ 1);               // both CTAs are done with this slot
-                mbar_expect_tx(&ms.b_full[stage], B_TILE_BYTES);        // every CTA arms its own barrier ...
-                if ((uint32_t)(it & 1) == cta_rank) {                    // ... and issues every other stage for both
+        const bool leader = elect_one_sync();
+        constexpr int STAGES_PER_Q = HID / KCH / KCH_PER_STAGE;       // 2 stage loads (64 KB each) per accumulator quarter
+        const int total = my_tiles * T * N_QUARTERS * STAGES_PER_Q;
+        int stage = 0; uint32_t phase = 0;
+        for (int it = 0; it < total; ++it) {
+            const int kb2 = it % STAGES_PER_Q, nq = (it / STAGES_PER_Q) % N_QUARTERS;
+            mbar_wait(&ms.b_empty[stage], phase ^ 1);               // both CTAs are done with this slot
+            if (leader) {
+                mbar_expect_tx(&ms.b_full[stage], B_TILE_BYTES);    // every CTA arms its own barrier ...
+                if ((uint32_t)(it & 1) == cta_rank) {                // ... and issues every other stage for both
 #pragma unroll
                     for (int j = 0; j < KCH_PER_STAGE; ++j)
                         tma_load_2d_mc(smB + stage * B_TILE_BYTES + j * B_BOX_BYTES, &w2_map, &ms.b_full[stage],
                                        (kb2 * KCH_PER_STAGE + j) * KCH, nq * N_MMA, (uint16_t)3);
                 }
-                if (++stage == B_STAGES) { stage = 0; phase ^= 1; }
             }
+            __syncwarp();
+            if (++stage == B_STAGES) { stage = 0; phase ^= 1; }
         }
     } else if (warp == 1) {
-        // ===== MMA issuer: one thread drives the tensor core =====
-        if (lane == 0) {
-            int stage = 0; uint32_t phase = 0, a_phase = 0, quarter = 0;
-            for (int step = 0; step < my_tiles * T; ++step) {
-                for (int nq = 0; nq < N_QUARTERS; ++nq, ++quarter) {
-                    const uint32_t buf = quarter & 1;
-                    mbar_wait(&ms.d_empty[buf], ((quarter >> 1) & 1) ^ 1);      // epilogue drained this buffer
-                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    const uint32_t d_tmem = tmem + TMEM_D_COL + buf * N_MMA;
-                    for (int kb2 = 0; kb2 < HID / KCH / KCH_PER_STAGE; ++kb2) {
-                        // the activations arrive in four 128-column parts (a stage spans two of them); the first
-                        // quarter's K loop chases them
-                        if (nq == 0) {
+        // ===== MMA issuer: one elected lane of the converged warp drives the tensor core =====
+        const bool leader = elect_one_sync();
+        int stage = 0; uint32_t phase = 0, a_phase = 0, quarter = 0;
+        for (int step = 0; step < my_tiles * T; ++step) {
+            for (int nq = 0; nq < N_QUARTERS; ++nq, ++quarter) {
+                const uint32_t buf = quarter & 1;
+                mbar_wait(&ms.d_empty[buf], ((quarter >> 1) & 1) ^ 1);      // epilogue drained this buffer
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t d_tmem = tmem + TMEM_D_COL + buf * N_MMA;
+                for (int kb2 = 0; kb2 < HID / KCH / KCH_PER_STAGE; ++kb2) {
+                    // the activations arrive in four 128-column parts (a stage spans two of them); the first
+                    // quarter's K loop chases them
+                    if (nq == 0) {
 #pragma unroll
-                            for (int pa = 0; pa < KCH_PER_STAGE / 2; ++pa) mbar_wait(&ms.a_ready[kb2 * (KCH_PER_STAGE / 2) + pa], a_phase);
-                        }
-                        mbar_wait(&ms.b_full[stage], phase);
-                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                        // one descriptor per stage; the 16 K-steps only bump its 14-bit start-address field
-                        const uint64_t b_desc0 = umma_desc_sw128(smem_u32(smB + stage * B_TILE_BYTES));
-                        const uint32_t a_col0 = tmem + TMEM_A_COL + kb2 * KCH_PER_STAGE * (KCH / 16) * 8;
+                        for (int pa = 0; pa < KCH_PER_STAGE / 2; ++pa) mbar_wait(&ms.a_ready[kb2 * (KCH_PER_STAGE / 2) + pa], a_phase);
+                    }
+                    mbar_wait(&ms.b_full[stage], phase);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    // one descriptor per stage; the 16 K-steps only bump its 14-bit start-address field
+                    const uint64_t b_desc0 = umma_desc_sw128(smem_u32(smB + stage * B_TILE_BYTES));
+                    const uint32_t a_col0 = tmem + TMEM_A_COL + kb2 * KCH_PER_STAGE * (KCH / 16) * 8;
+                    if (leader) {
 #pragma unroll
                         for (int k = 0; k < KCH_PER_STAGE * (KCH / 16); ++k) {
                             const uint64_t b_desc = b_desc0 + (uint64_t)(((k / (KCH / 16)) * B_BOX_BYTES + (k % (KCH / 16)) * 32) >> 4);
                             umma_bf16_ts(d_tmem, a_col0 + k * 8, b_desc, (kb2 | k) ? 1u : 0u);
                         }
                         umma_commit_mc(&ms.b_empty[stage], (uint16_t)3);   // frees the W2 slot in BOTH CTAs when these MMAs retire
-                        if (++stage == B_STAGES) { stage = 0; phase ^= 1; }
                     }
-                    umma_commit(&ms.d_full[buf]);                 // this accumulator quarter is complete
+                    __syncwarp();
+                    if (++stage == B_STAGES) { stage = 0; phase ^= 1; }
                 }
-                a_phase ^= 1;
+                if (leader) umma_commit(&ms.d_full[buf]);         // this accumulator quarter is complete
+                __syncwarp();
             }
+            a_phase ^= 1;
         }
     } else {
         // ===== compute warps: rows = TMEM lanes 32*(warp%4)..+31, column group grp =====

@@ -132,6 +132,25 @@ def cpu_python_loops_rate(K=64, T=50):
     return K * T / (time.perf_counter() - t0)
 
 
+def _py_loops_worker(_):
+    return cpu_python_loops_rate()
+
+
+def cpu_python_loops_aggregate():
+    """N independent single-threaded controllers, one process per host core (the reference is scalar
+    Python, so this is all the parallelism it can use): aggregate sample-steps/s and the process count."""
+    import multiprocessing as mp
+    n = os.cpu_count() or 1
+    try:
+        with mp.get_context("fork").Pool(n) as pool:
+            t0 = time.perf_counter()
+            pool.map(_py_loops_worker, range(n))
+            dt = time.perf_counter() - t0
+        return n * 64 * 50 / dt, n
+    except Exception:
+        return None, n
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -143,6 +162,7 @@ def run_reference_arm(args):
     ms = 1e3 * float(np.mean(times))
     val = K_s * T_H / float(np.mean(times))
     py_rate = cpu_python_loops_rate()
+    py_all, py_n = cpu_python_loops_aggregate()
     line = {
         "impl": "reference", "metric": "mppi_sample_steps_per_sec", "value": val, "unit": "sample-steps/s",
         "n_gpus": args.gpus, "steps": n_ref, "warmup": args.warmup, "ms_per_step": ms,
@@ -152,6 +172,7 @@ def run_reference_arm(args):
         "cpu_baseline": {"value": val, "unit": "sample-steps/s", "cores": nthr, "kind": "port",
                          "sample": "K=65536 x H=50 per tick, %d ticks, oracle/mppi_oracle.c (OpenMP)" % n_ref,
                          "python_loops_1core_value": py_rate,
+                         "python_loops_allcores_value": py_all, "python_loops_processes": py_n,
                          "note": "the reference itself is scalar Python loops (python_loops_1core_value); the C port is a best-effort CPU line"},
         "e2e": {"value": val, "unit": "sample-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -288,10 +309,10 @@ def run_b200_arm(args):
                                    visualize_optimal_traj=False, visualze_sampled_trajs=False, seed=3)
         lp = rc.generate_lemniscate_trajectory(100, 10.0).astype(np.float32)
         rc.ref_path = lp
-        for i in range(20):
+        for i in range(100):                                   # >= 1000 ticks after 100 warm-up
             rc._calc_control_input(lp[i % 100])
         rl = []
-        for i in range(300):
+        for i in range(1000):
             rc.prev_waypoints_idx = 0
             t1 = time.perf_counter()
             rc._calc_control_input(lp[i % 50])
@@ -428,6 +449,7 @@ def run_b200_arm(args):
     cpu_baseline = {"value": cpu_val, "unit": "sample-steps/s", "cores": nthr, "kind": "port",
                     "sample": "K=65536 x H=50 per tick, 3 ticks, oracle/mppi_oracle.c (OpenMP, FP64)",
                     "python_loops_1core_value": cpu_python_loops_rate()}
+    cpu_baseline["python_loops_allcores_value"], cpu_baseline["python_loops_processes"] = cpu_python_loops_aggregate()
 
     lat = np.sort(np.array(lat))
     line = {

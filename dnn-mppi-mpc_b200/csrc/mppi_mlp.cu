@@ -36,6 +36,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <vector>
 
 #include "mppi_device.cuh"
@@ -68,6 +69,7 @@ struct MlpSmem {                          // after the 1024-aligned A / B region
     float4 xs[TILE_M];                    // current state of each row for the partner thread
     float res[N_GROUPS - 1][3][TILE_M];   // partners' partial output-layer sums (SoA: 4.5 KB instead of 6 KB as float4)
     unsigned long long b_full[B_STAGES], b_empty[B_STAGES], a_ready[N_QUARTERS], d_full[2], d_empty[2];
+    unsigned long long a_free[N_QUARTERS];   // ping-pong mode: the last accumulator quarter has consumed this K part of A
     unsigned long long key[8];
     uint32_t tmem_base;
     float b3[3];
@@ -95,6 +97,14 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t pari
         "@p bra.uni WAIT_DONE;\n\t"
         "bra.uni WAIT_LOOP;\n\t"
         "WAIT_DONE:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+
+// warp-level wait: one lane polls the barrier (every try_wait is a shared-memory operation -- 16 compute warps polling
+// with all 32 lanes loaded the same data pipe the weight LDS, the UMMA B reads and the TMA writes go through), the rest
+// of the warp joins at __syncwarp, which also orders the polling lane's acquire before the other lanes' later accesses
+__device__ __forceinline__ void mbar_wait_warp(unsigned long long *bar, uint32_t parity) {
+    if ((threadIdx.x & 31) == 0) mbar_wait(bar, parity);
+    __syncwarp();
 }
 
 __device__ __forceinline__ void tma_load_2d_mc(void *dst, const CUtensorMap *map, unsigned long long *bar, int c0, int c1, uint16_t mask) {
@@ -180,7 +190,7 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
-template <int NIN>
+template <int NIN, bool PP>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(MLP_THREADS, 1)
 mppi_mlp_rollout_kernel(const __grid_constant__ TickArgs a, const __grid_constant__ CUtensorMap w2_map,
                         const float4 *__restrict__ g_w01, const float2 *__restrict__ g_w01u, const float4 *__restrict__ g_w3,
@@ -199,6 +209,8 @@ mppi_mlp_rollout_kernel(const __grid_constant__ TickArgs a, const __grid_constan
     const int n_clusters = (int)gridDim.x / 2, cluster_id = (int)blockIdx.x / 2;
     const int n_pairs = (n_tiles + 1) / 2;
     const int my_tiles = (n_pairs - cluster_id + n_clusters - 1) / n_clusters;
+    // ping-pong mode walks the CTA's tiles two at a time (an odd count is padded with an empty tile)
+    const int my_slots = PP ? 2 * ((my_tiles + 1) / 2) : my_tiles;
 
     // ---- one-time setup: constants, barriers, TMEM, step-1 index + window (same rule as the tick kernel)
     for (int j = tid; j < HID; j += MLP_THREADS) {
@@ -209,7 +221,7 @@ mppi_mlp_rollout_kernel(const __grid_constant__ TickArgs a, const __grid_constan
     if (tid < 4) sm.x0[tid] = a.x0[tid];
     if (tid == 0) {
         for (int s = 0; s < B_STAGES; ++s) { mbar_init(&ms.b_full[s], 1); mbar_init(&ms.b_empty[s], 2); }   // empty: both CTAs
-        for (int pa = 0; pa < N_QUARTERS; ++pa) mbar_init(&ms.a_ready[pa], N_COMPUTE);
+        for (int pa = 0; pa < N_QUARTERS; ++pa) { mbar_init(&ms.a_ready[pa], N_COMPUTE); mbar_init(&ms.a_free[pa], 1); }
         for (int bf = 0; bf < 2; ++bf) { mbar_init(&ms.d_full[bf], 1); mbar_init(&ms.d_empty[bf], N_COMPUTE); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -269,7 +281,7 @@ mppi_mlp_rollout_kernel(const __grid_constant__ TickArgs a, const __grid_constan
         // ===== TMA producer: the same 16 W2 boxes every timestep, through a B_STAGES ring =====
         const bool leader = elect_one_sync();
         constexpr int STAGES_PER_Q = HID / KCH / KCH_PER_STAGE;       // 2 stage loads (64 KB each) per accumulator quarter
-        const int total = my_tiles * T * N_QUARTERS * STAGES_PER_Q;
+        const int total = my_slots * T * N_QUARTERS * STAGES_PER_Q;
         int stage = 0; uint32_t phase = 0;
         for (int it = 0; it < total; ++it) {
             const int kb2 = it % STAGES_PER_Q, nq = (it / STAGES_PER_Q) % N_QUARTERS;
@@ -290,7 +302,7 @@ mppi_mlp_rollout_kernel(const __grid_constant__ TickArgs a, const __grid_constan
         // ===== MMA issuer: one elected lane of the converged warp drives the tensor core =====
         const bool leader = elect_one_sync();
         int stage = 0; uint32_t phase = 0, a_phase = 0, quarter = 0;
-        for (int step = 0; step < my_tiles * T; ++step) {
+        for (int step = 0; step < my_slots * T; ++step) {
             for (int nq = 0; nq < N_QUARTERS; ++nq, ++quarter) {
                 const uint32_t buf = quarter & 1;
                 mbar_wait(&ms.d_empty[buf], ((quarter >> 1) & 1) ^ 1);      // epilogue drained this buffer
@@ -313,6 +325,9 @@ mppi_mlp_rollout_kernel(const __grid_constant__ TickArgs a, const __grid_constan
                         for (int k = 0; k < KCH_PER_STAGE * (KCH / 16); ++k) {
                             const uint64_t b_desc = b_desc0 + (uint64_t)(((k / (KCH / 16)) * B_BOX_BYTES + (k % (KCH / 16)) * 32) >> 4);
                             umma_bf16_ts(d_tmem, a_col0 + k * 8, b_desc, (kb2 | k) ? 1u : 0u);
+                            // ping-pong: the LAST quarter is the last reader of A -- release each 128-column part as
+                            // soon as its MMAs retire so the other tile's layer 1 can overwrite it
+                            if (PP && nq == N_QUARTERS - 1 && (k & 7) == 7) umma_commit(&ms.a_free[kb2 * (KCH_PER_STAGE / 2) + (k >> 3)]);
                         }
                         umma_commit_mc(&ms.b_empty[stage], (uint16_t)3);   // frees the W2 slot in BOTH CTAs when these MMAs retire
                     }
@@ -326,6 +341,153 @@ mppi_mlp_rollout_kernel(const __grid_constant__ TickArgs a, const __grid_constan
         }
     } else {
         // ===== compute warps: rows = TMEM lanes 32*(warp%4)..+31, column group grp =====
+        if constexpr (PP) {
+        // ---- ping-pong mode: two tiles X, Y per CTA.  While the tensor core runs the GEMM of one tile, the compute
+        // warps finish the other tile's previous step (last epilogue quarter, Euler), generate its next control and
+        // evaluate its layer 1 into the A region part by part as the running GEMM's LAST quarter releases the parts
+        // (a_free).  Tile X is owned (state, cost, noise) by column group 0, tile Y by group 1; every group helps with
+        // the layer-1 columns and the epilogue of both.  GEMM order: X(0) Y(0) X(1) Y(1) ... ; L1 #l feeds GEMM #l.
+        const int cw = warp - 2;
+        const int q = warp & 3, grp = cw >> 2;
+        const int row = q * 32 + lane;
+        const bool owner = grp < 2;
+        uint32_t d_phase[2] = {0, 0};
+        uint32_t l1_count = 0;
+        for (int pr = 0; pr < my_slots / 2; ++pr) {
+            const int tl = 2 * pr + (grp & 1);
+            const int tile = 2 * (cluster_id + tl * n_clusters) + (int)cta_rank;
+            const int k = tile * TILE_M + row;
+            const bool active = owner && tl < my_tiles && k < a.K;
+            const uint32_t kg = (uint32_t)(a.k_offset + k);
+            const bool exploit = (int)kg < a.n_exploit;
+            float z[4] = {sm.x0[0], sm.x0[1], sm.x0[2], 0.f};
+            float acc = 0.f, e[4] = {0.f, 0.f, 0.f, 0.f}, sn = 0.f, cs = 1.f;
+            float vp0 = 0.f, vp1 = 0.f, vc0 = 0.f, vc1 = 0.f;          // controls of steps t-1 and t
+            float4 ref = make_float4(0.f, 0.f, 0.f, 0.f);
+            const float2 *eps_k = a.eps ? reinterpret_cast<const float2 *>(a.eps) + (size_t)(active ? k : 0) * T : nullptr;
+            // owner: stage cost of the state reached by step t-1, noise + clamped control of step t, heading sin/cos
+            auto prep = [&](int t) {
+                if (t > 0 && (a.flags & F_COST_SUM)) {
+                    const int j = a.window == 20 ? nearest_wp<20>(sm, z[0], z[1]) : nearest_wp<0>(sm, z[0], z[1]);
+                    ref = window_ref(sm, j);
+                    const float2 qq = sm.Q[t - 1];
+                    acc += tracking_cost<MPPI_MODEL_DIFFDRIVE>(ref, z, z[2], a.sw) + (qq.x * vp0 + qq.y * vp1);
+                }
+                if (eps_k) { const float2 ee = eps_k[t]; e[2 * (t & 1)] = ee.x; e[2 * (t & 1) + 1] = ee.y; }
+                else if ((t & 1) == 0) philox_eps_pair(a, kg, (uint32_t)(t >> 1), 0u, e);
+                const float2 u = sm.U[t];
+                vc0 = clampf(exploit ? __fadd_rn(u.x, e[2 * (t & 1)]) : e[2 * (t & 1)], a.umax0);
+                vc1 = clampf(exploit ? __fadd_rn(u.y, e[2 * (t & 1) + 1]) : e[2 * (t & 1) + 1], a.umax1);
+                sincos_cw(z[2], sn, cs);
+            };
+            // layer 1 of the tile owned by group og -> A region (L1 #l1_count, consumed by GEMM #l1_count)
+            auto layer1 = [&](int og) {
+                if (grp == og) {
+                    ms.xs[row] = make_float4(z[0], z[1], z[2], vc0);
+                    if (NIN == 5) ms.xw[row] = vc1;
+                }
+                named_bar_sync(1, N_COMPUTE);
+                const float4 st = ms.xs[row];
+                const float su1 = NIN == 5 ? ms.xw[row] : 0.f;
+#pragma unroll 1
+                for (int part = 0; part < N_QUARTERS; ++part) {
+                    if (l1_count > 0) {                                   // GEMM #(l1_count-1) is done with this part of A
+                        mbar_wait_warp(&ms.a_free[part], (l1_count - 1) & 1);
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    }
+#pragma unroll 2
+                    for (int c8 = 0; c8 < 4; ++c8) {
+                        const int col = part * N_MMA + grp * 32 + c8 * 8;
+                        uint32_t pk[4];
+#pragma unroll
+                        for (int p = 0; p < 4; ++p) {
+                            const float4 wa = ms.w01[col + 2 * p], wb = ms.w01[col + 2 * p + 1];
+                            float pa = fmaf(wa.x, st.x, fmaf(wa.y, st.y, fmaf(wa.z, st.z, wa.w)));
+                            float pb = fmaf(wb.x, st.x, fmaf(wb.y, st.y, fmaf(wb.z, st.z, wb.w)));
+                            if (NIN == 5) {
+                                const float4 wu = *reinterpret_cast<const float4 *>(&ms.w01u[col + 2 * p]);
+                                pa = fmaf(wu.x, st.w, fmaf(wu.y, su1, pa));
+                                pb = fmaf(wu.z, st.w, fmaf(wu.w, su1, pb));
+                            }
+                            pk[p] = tanh_bf16x2(pa, pb);
+                        }
+                        tmem_st4(tmem + ((uint32_t)(q * 32) << 16) + TMEM_A_COL + (uint32_t)(col >> 1), pk[0], pk[1], pk[2], pk[3]);
+                    }
+                    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    mbar_arrive(&ms.a_ready[part]);
+                }
+                ++l1_count;
+            };
+            // one accumulator quarter: D -> +b2 -> tanh -> partial contraction with the 512x3 output layer
+            auto epilogue = [&](int nq, float &r0, float &r1, float &r2) {
+                const int col = nq * N_MMA + grp * 32;
+                const int buf = nq & 1;
+                mbar_wait_warp(&ms.d_full[buf], d_phase[buf]); d_phase[buf] ^= 1;
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                uint32_t v[32];
+                tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(TMEM_D_COL + buf * N_MMA + grp * 32), v);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                mbar_arrive(&ms.d_empty[buf]);
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    const float4 w = ms.w3[col + i];
+                    const float h = tanh_approx(__uint_as_float(v[i]) + w.x);
+                    r0 = fmaf(w.y, h, r0); r1 = fmaf(w.z, h, r1); r2 = fmaf(w.w, h, r2);
+                }
+            };
+            // the step of the tile owned by group og is complete: gather the partial sums, Euler step with the residual
+            auto finish = [&](int og, float r0, float r1, float r2) {
+                const int rel = (grp - og) & 3;
+                if (rel) { ms.res[rel - 1][0][row] = r0; ms.res[rel - 1][1][row] = r1; ms.res[rel - 1][2][row] = r2; }
+                named_bar_sync(1, N_COMPUTE);
+                if (grp == og) {
+#pragma unroll
+                    for (int g = 0; g < N_GROUPS - 1; ++g) { r0 += ms.res[g][0][row]; r1 += ms.res[g][1][row]; r2 += ms.res[g][2][row]; }
+                    r0 += ms.b3[0]; r1 += ms.b3[1]; r2 += ms.b3[2];
+                    z[0] = fmaf(fmaf(vc0, cs, r0), a.dt, z[0]);
+                    z[1] = fmaf(fmaf(vc0, sn, r1), a.dt, z[1]);
+                    z[2] = fmaf(vc1 + r2, a.dt, z[2]);
+                    vp0 = vc0; vp1 = vc1;
+                }
+            };
+
+            if (owner) prep(0);
+            layer1(0);                                               // L1(X, 0)
+            float r0, r1, r2;
+            float s0 = 0.f, s1 = 0.f, s2 = 0.f;                      // partial sums of the tile whose GEMM ran one slot ago
+            for (int t = 0; t < T; ++t) {
+                // ---- slot X(t): the tensor core runs GEMM X(t)
+                if (t > 0) {
+                    epilogue(3, s0, s1, s2);                         // Y(t-1), last quarter
+                    finish(1, s0, s1, s2);
+                    if (grp == 1) prep(t);
+                }
+                r0 = r1 = r2 = 0.f;
+                epilogue(0, r0, r1, r2); epilogue(1, r0, r1, r2); epilogue(2, r0, r1, r2);      // X(t)
+                layer1(1);                                           // L1(Y, t) chases X(t)'s last quarter
+                // ---- slot Y(t): the tensor core runs GEMM Y(t)
+                epilogue(3, r0, r1, r2);                             // X(t), last quarter
+                finish(0, r0, r1, r2);
+                if (grp == 0 && t + 1 < T) prep(t + 1);
+                s0 = s1 = s2 = 0.f;
+                epilogue(0, s0, s1, s2); epilogue(1, s0, s1, s2); epilogue(2, s0, s1, s2);      // Y(t)
+                if (t + 1 < T) layer1(0);                            // L1(X, t+1) chases Y(t)'s last quarter
+            }
+            epilogue(3, s0, s1, s2);                                 // Y(T-1), last quarter
+            finish(1, s0, s1, s2);
+            if (active) {
+                const int j = a.window == 20 ? nearest_wp<20>(sm, z[0], z[1]) : nearest_wp<0>(sm, z[0], z[1]);
+                ref = window_ref(sm, j);
+                const float2 qq = sm.Q[T - 1];
+                const float last = tracking_cost<MPPI_MODEL_DIFFDRIVE>(ref, z, z[2], a.sw) + (qq.x * vp0 + qq.y * vp1) +
+                                   tracking_cost<MPPI_MODEL_DIFFDRIVE>(ref, z, z[2], a.tw);
+                acc = (a.flags & F_COST_SUM) ? acc + last : last;
+                S_out[k] = acc;
+            }
+        }
+        } else {
         const int cw = warp - 2;
         const int q = warp & 3, grp = cw >> 2;          // TMEM lane quarter (hardware: warp % 4), column group
         const int row = q * 32 + lane;
@@ -403,7 +565,7 @@ mppi_mlp_rollout_kernel(const __grid_constant__ TickArgs a, const __grid_constan
                 for (int nq = 0; nq < N_QUARTERS; ++nq) {         // every group takes 32 columns of EACH quarter, so the
                     const int col = nq * N_MMA + grp * 32;        // work exposed after the last MMA is 32 columns, not 128
                     const int buf = nq & 1;
-                    mbar_wait(&ms.d_full[buf], d_phase[buf]); d_phase[buf] ^= 1;
+                    mbar_wait_warp(&ms.d_full[buf], d_phase[buf]); d_phase[buf] ^= 1;
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     uint32_t v[32];
                     tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(TMEM_D_COL + buf * N_MMA + grp * 32), v);
@@ -440,6 +602,7 @@ mppi_mlp_rollout_kernel(const __grid_constant__ TickArgs a, const __grid_constan
                 acc = (a.flags & F_COST_SUM) ? acc + last : last;
                 S_out[k] = acc;
             }
+        }
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -479,8 +642,10 @@ MlpState *mlp_create(int K, int T) {
         cudaMalloc(&m->d_w3, sizeof(float4) * HID) != cudaSuccess ||
         cudaMalloc(&m->d_w01u, sizeof(float2) * HID) != cudaSuccess ||
         cudaMalloc(&m->d_b3, sizeof(float) * 4) != cudaSuccess) { mlp_destroy(m); return nullptr; }
-    if (cudaFuncSetAttribute(mppi_mlp_rollout_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MLP_DYN_SMEM) != cudaSuccess ||
-        cudaFuncSetAttribute(mppi_mlp_rollout_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MLP_DYN_SMEM) != cudaSuccess) {
+    if (cudaFuncSetAttribute(mppi_mlp_rollout_kernel<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MLP_DYN_SMEM) != cudaSuccess ||
+        cudaFuncSetAttribute(mppi_mlp_rollout_kernel<5, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MLP_DYN_SMEM) != cudaSuccess ||
+        cudaFuncSetAttribute(mppi_mlp_rollout_kernel<3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MLP_DYN_SMEM) != cudaSuccess ||
+        cudaFuncSetAttribute(mppi_mlp_rollout_kernel<5, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MLP_DYN_SMEM) != cudaSuccess) {
         mlp_destroy(m); return nullptr;
     }
     return m;
@@ -561,10 +726,14 @@ int mlp_rollout_costs(MlpState *m, const TickArgs &args, bool sum, const float *
     a.flags = sum ? F_COST_SUM : 0;
     const int n_tiles = (a.K + TILE_M - 1) / TILE_M;
     int grid = std::min(((n_tiles + 1) / 2) * 2, m->n_sm & ~1);       // whole clusters of 2
-    if (m->n_in == 5)
-        mppi_mlp_rollout_kernel<5><<<grid, MLP_THREADS, MLP_DYN_SMEM, st>>>(a, m->w2_map, m->d_w01, m->d_w01u, m->d_w3, m->d_b3, d_S, n_tiles);
-    else
-        mppi_mlp_rollout_kernel<3><<<grid, MLP_THREADS, MLP_DYN_SMEM, st>>>(a, m->w2_map, m->d_w01, m->d_w01u, m->d_w3, m->d_b3, d_S, n_tiles);
+    // two tiles per CTA in flight (ping-pong) whenever a CTA owns more than one tile; MPPI_MLP_PINGPONG=0 forces the
+    // one-tile schedule (A/B measurements)
+    static const bool allow_pp = [] { const char *e = std::getenv("MPPI_MLP_PINGPONG"); return !(e && e[0] == '0'); }();
+    const bool pp = allow_pp && n_tiles > grid;
+#define MPPI_MLP_LAUNCH(N, P) mppi_mlp_rollout_kernel<N, P><<<grid, MLP_THREADS, MLP_DYN_SMEM, st>>>(a, m->w2_map, m->d_w01, m->d_w01u, m->d_w3, m->d_b3, d_S, n_tiles)
+    if (m->n_in == 5) { if (pp) MPPI_MLP_LAUNCH(5, true); else MPPI_MLP_LAUNCH(5, false); }
+    else { if (pp) MPPI_MLP_LAUNCH(3, true); else MPPI_MLP_LAUNCH(3, false); }
+#undef MPPI_MLP_LAUNCH
     return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 

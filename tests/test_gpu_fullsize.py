@@ -113,3 +113,40 @@ def test_config3_fleet_4096_robots_random_subset():
         assert np.max(np.abs(Unew[r] - o["U_after"])) <= U_ATOL, r
         assert np.max(np.abs(u0[r] - o["u0"])) <= U_ATOL and inew[r] == o["idx_after"]
     b.engine.close()
+
+
+@pytest.mark.parametrize("K,T", [(20000, 11), (19073, 12), (40001, 13)])
+def test_mlp_ping_pong_schedule_ragged_tile_counts(K, T):
+    """More tiles than CTAs puts the learned-dynamics kernel in its two-tiles-per-CTA (ping-pong) schedule; these sizes
+    leave some CTAs with an odd tile count (padded with an empty tile), a ragged last tile and an odd horizon.
+    Injected and Philox noise must give the same costs, and a subset (first, last, random tiles) must match the FP64 oracle."""
+    g = Golden("diffdrive_pe0.05")
+    mlp = orc.make_mlp(seed=2, out_scale=0.02)
+    sp = orc.diffdrive_spec(K=K, T=T, param_exploration=0.05, cost_mode="sum", waypoint_mode="frozen",
+                            model="diffdrive_mlp", mlp=mlp)
+    sp.temperature = 2.0
+    eng = engine_from_spec(sp, g.path)
+    eng.set_mlp([mlp["W%d" % i] for i in range(4)], [mlp["b%d" % i] for i in range(4)])
+    eps = torch.zeros(K, T, 2, dtype=torch.float32, device="cuda")
+    eng.generate_noise(eps, seed=5, tick=1)
+    U = np.random.default_rng(4).normal(0, 0.3, (T, 2)).astype(np.float32)
+    x0 = np.array([0.4, 0.3, 0.5])
+    S1 = torch.zeros(K, dtype=torch.float32, device="cuda")
+    S2 = torch.full((K,), -1.0, dtype=torch.float32, device="cuda")
+    eng.set_nominal(U)
+    eng.rollout_costs(x0, S1, None, seed=5, tick=1)
+    eng.set_waypoint_idx(0)
+    eng.rollout_costs(x0, S2, eps, seed=5, tick=1)
+    assert torch.equal(S1, S2)                                  # every sample written, injected == Philox bit for bit
+    Sg = S1.cpu().numpy().astype(np.float64)
+    n_exploit = sp.n_exploit()
+    rng = np.random.default_rng(6)
+    sub = np.unique(np.concatenate([np.arange(0, 256), np.arange(K - 300, K), rng.choice(K, 512, replace=False)]))
+    for lo, hi, pe in ((0, n_exploit, 0.0), (n_exploit, K, 1.0)):
+        ss = sub[(sub >= lo) & (sub < hi)]
+        sps = orc.diffdrive_spec(K=ss.size, T=T, param_exploration=pe, cost_mode="sum", waypoint_mode="frozen",
+                                 model="diffdrive_mlp", mlp=mlp)
+        So, _, _ = orc.costs_vec(sps, g.path, U.astype(np.float64), 0, x0, eps[torch.from_numpy(ss).cuda()].cpu().numpy().astype(np.float64))
+        rel = np.abs(Sg[ss] - So) / np.maximum(np.abs(So), 1e-9)
+        assert np.quantile(rel, 0.99) <= 2e-3 and rel.max() <= 2e-2, (lo, rel.max())
+    eng.close()

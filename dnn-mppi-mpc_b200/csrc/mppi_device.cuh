@@ -148,7 +148,27 @@ struct TickSmem {
     float2 wyv[MPPI_MAX_WINDOW];           // (yaw, v) of each window entry, for the lookup after the argmin
     float x0[4];
     int win_start, n_win16;                // absolute index of window entry 0; padded length / 16
+    float4 cb[MPPI_MAX_WINDOW / 16];       // dynamic window: bounding circle (cx, cy, r) of every 16-entry chunk
 };
+
+// Bounding circle of the window entries path[first .. first + n_valid) (one 16-entry chunk of the dynamic window).
+// nearest_wp<0> skips a chunk only when this circle proves every point in it farther than the best found so far,
+// so the argmin stays exactly the reference's (first minimum over the whole window).
+__device__ __forceinline__ float4 chunk_bound(const float4 *path, int first, int n_valid) {
+    float xmin = CUDART_INF_F, xmax = -CUDART_INF_F, ymin = CUDART_INF_F, ymax = -CUDART_INF_F;
+    for (int j = 0; j < n_valid; ++j) {
+        const float4 p = path[first + j];
+        xmin = fminf(xmin, p.x); xmax = fmaxf(xmax, p.x); ymin = fminf(ymin, p.y); ymax = fmaxf(ymax, p.y);
+    }
+    const float cx = 0.5f * (xmin + xmax), cy = 0.5f * (ymin + ymax);
+    float r2 = 0.f;
+    for (int j = 0; j < n_valid; ++j) {
+        const float4 p = path[first + j];
+        const float dx = p.x - cx, dy = p.y - cy;
+        r2 = fmaxf(r2, fmaf(dy, dy, dx * dx));
+    }
+    return make_float4(cx, cy, sqrtf(r2) * 1.00001f + 1e-6f, 0.f);
+}
 
 // ---- packed FP32 (Blackwell FADD2 / FMUL2 / FFMA2): two FP32 ops per issue slot ------------
 __device__ __forceinline__ float2 f2_add(float2 a, float2 b) {
@@ -267,27 +287,36 @@ __device__ __forceinline__ int nearest_wp(const TickSmem &sm, float x, float y) 
         return __float2int_rn(key);
     }
     // dynamic window: chunks of 16 entries (the window is padded with sentinels to a multiple of 16)
-    float bm = CUDART_INF_F;
+    float bm = CUDART_INF_F, sbm = CUDART_INF_F;      // best squared distance so far and its square root
     int bj = 0;
     const int nch = sm.n_win16;
     int c = 0;
+    // |z - p| >= |z - centre| - r for every point p of a chunk: if that exceeds the best distance (with a 1e-4 relative
+    // margin, three orders above FP32 rounding) no point of the chunk can be the minimum or tie with it
+    auto far = [&](int ch) {
+        const float4 cb = sm.cb[ch];
+        const float ex = x - cb.x, ey = y - cb.y, R = sbm + cb.z;
+        return fmaf(ey, ey, ex * ex) > R * R * 1.0002f;
+    };
 #if MPPI_WP_CHUNK_ILP
     // two chunks per trip: their (independent) distance / min / key chains overlap, which is what a latency-bound
     // small-K tick needs; the earlier chunk still wins ties
     for (; c + 1 < nch; c += 2) {
+        if (far(c) && far(c + 1)) continue;
         float m0, k0, m1, k1;
         chunk_argmin<16>(nwx4 + 4 * c, nwy4 + 4 * c, x, y, m0, k0);
         chunk_argmin<16>(nwx4 + 4 * c + 4, nwy4 + 4 * c + 4, x, y, m1, k1);
         const bool second = m1 < m0;
         const float m = second ? m1 : m0;
         const int j = second ? 16 * c + 16 + __float2int_rn(k1) : 16 * c + __float2int_rn(k0);
-        if (m < bm) { bm = m; bj = j; }
+        if (m < bm) { bm = m; bj = j; sbm = sqrtf(m); }
     }
 #endif
     for (; c < nch; ++c) {
+        if (far(c)) continue;
         float m, key;
         chunk_argmin<16>(nwx4 + 4 * c, nwy4 + 4 * c, x, y, m, key);
-        if (m < bm) { bm = m; bj = 16 * c + __float2int_rn(key); }       // strict <: the earlier chunk wins ties
+        if (m < bm) { bm = m; bj = 16 * c + __float2int_rn(key); sbm = sqrtf(m); }       // strict <: the earlier chunk wins ties
     }
     return bj;
 }

@@ -394,6 +394,27 @@ def run_b200_arm(args):
         torch.cuda.synchronize()
         extras["mlp5_scaled_K65536_H30"] = {"ms_per_tick": a.elapsed_time(b) / 10,
                                             "sample_steps_per_sec": 65536 * 30 / (a.elapsed_time(b) / 10 * 1e-3)}
+        # three tanh layers (train/train_diff_mlp.py:13-36, saved_models/mlp_diff_300x100_3l*.pth): two GEMMs per step,
+        # the second one's A operand staged in shared memory by the first one's epilogue
+        mlp53 = {"W0": mlp5["W0"], "b0": mlp5["b0"], "W1": mlp5["W1"], "b1": mlp5["b1"], "W2": mlp5["W2"], "b2": mlp5["b2"],
+                 "W3": (rngw.uniform(-1, 1, (512, 512)) / np.sqrt(512)).astype(np.float32),
+                 "b3": (rngw.uniform(-1, 1, (512,)) / np.sqrt(512)).astype(np.float32), "W4": mlp5["W3"], "b4": mlp5["b3"]}
+        c5.set_dynamics(mlp53, scalers=dict(in_mean=[4.39, -0.126, -0.08, 0.359, -0.031], in_scale=[5.587, 3.641, 1.06, 1.024, 1.836],
+                                            out_mean=[-0.561, 0.029, -0.015], out_scale=[5.701, 3.59, 0.996]))
+        for i in range(3):
+            c5.engine.step_async(x0, None, 7, i)
+        torch.cuda.synchronize()
+        with torch.cuda.stream(stream):
+            a.record(stream)
+            for i in range(10):
+                c5.engine.step_async(x0, None, 7, 10 + i)
+            b.record(stream)
+        torch.cuda.synchronize()
+        ms3 = a.elapsed_time(b) / 10
+        extras["mlp5_3hidden_scaled_K65536_H30"] = {
+            "ms_per_tick": ms3, "sample_steps_per_sec": 65536 * 30 / (ms3 * 1e-3),
+            "executed_gemm_TFLOPs": 65536 * 30 * 4 * 512 * 512 / (ms3 * 1e-3) / 1e12,
+            "frac_of_tensor_peak_executed": 65536 * 30 * 4 * 512 * 512 / (ms3 * 1e-3) / 1e12 / pk.get("bf16_tflops", 1590.0)}
         c5.engine.close()
         # goal-point diff-drive MPPI (test/mppi_differential_drive_obs.py), throughput shape
         from mppi_b200.mppi_differential_drive_goal import MPPIAlgorithms as GoalMPPI

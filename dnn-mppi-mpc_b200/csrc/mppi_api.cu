@@ -489,7 +489,7 @@ int mppi_set_mlp(mppi_handle_t h, const float *const W[4], const float *const b[
     if (!h || !W || !b) return MPPI_E_BADARG;
     if (!h->mlp) return fail(h, MPPI_E_STATE, "handle was not created with MPPI_MODEL_DIFFDRIVE_MLP");
     CK(h, cudaSetDevice(h->cfg.device));
-    if (mlp_set_weights(h->mlp, 3, W, b, nullptr, nullptr, nullptr, nullptr, h->stream) != cudaSuccess)
+    if (mlp_set_weights(h->mlp, 3, 2, W, b, nullptr, nullptr, nullptr, nullptr, h->stream) != cudaSuccess)
         return fail(h, MPPI_E_CUDA, "mlp_set_weights failed");
     return MPPI_OK;
 }
@@ -498,13 +498,13 @@ int mppi_set_mlp_ex(mppi_handle_t h, int32_t n_in, int32_t n_hidden, const float
                     const double *in_mean, const double *in_scale, const double *out_mean, const double *out_scale) {
     if (!h || !W || !b || (n_in != 3 && n_in != 5) || n_hidden < 1) return MPPI_E_BADARG;
     if (!h->mlp) return fail(h, MPPI_E_STATE, "handle was not created with MPPI_MODEL_DIFFDRIVE_MLP");
-    if (n_hidden != 2)
-        return fail(h, MPPI_E_UNSUPPORTED, "the tensor-core rollout runs residuals with two 512-wide tanh layers "
-                                           "(mlp_diff.pth, mlp_diff_300x100.pth, mlp_diff_300x100_v2.pth); the *_3l models are not supported");
-    for (int i = 0; i < 4; ++i) if (!W[i] || !b[i]) return MPPI_E_BADARG;
+    if (n_hidden != 2 && n_hidden != 3)
+        return fail(h, MPPI_E_UNSUPPORTED, "the tensor-core rollout runs residuals with two or three 512-wide tanh layers "
+                                           "(saved_models/mlp_diff*.pth, mlp_diff_300x100_3l*.pth)");
+    for (int i = 0; i < n_hidden + 2; ++i) if (!W[i] || !b[i]) return MPPI_E_BADARG;
     if (in_scale) for (int c = 0; c < n_in; ++c) if (!(in_scale[c] != 0.0)) return MPPI_E_BADARG;
     CK(h, cudaSetDevice(h->cfg.device));
-    if (mlp_set_weights(h->mlp, n_in, W, b, in_mean, in_scale, out_mean, out_scale, h->stream) != cudaSuccess)
+    if (mlp_set_weights(h->mlp, n_in, n_hidden, W, b, in_mean, in_scale, out_mean, out_scale, h->stream) != cudaSuccess)
         return fail(h, MPPI_E_CUDA, "mlp_set_weights failed");
     return MPPI_OK;
 }

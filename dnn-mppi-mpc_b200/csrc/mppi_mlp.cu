@@ -27,6 +27,12 @@
 // (template NIN = 5): the folded first layer takes (x, y, yaw, v, w), so the owner thread generates the control of step
 // t+1 while the GEMM of step t runs and publishes it with the state.  StandardScaler pre/post-processing
 // (test/test_diff_dyna_eval.py:54-56) is folded into the first / last layer on the host.
+// Residuals with THREE tanh layers (train/train_diff_mlp.py:13-36, saved_models/mlp_diff_300x100_3l*.pth) need a second
+// 512x512 GEMM whose A operand is the first GEMM's epilogue.  Tensor memory has no room for it (A 256 + two
+// accumulator buffers 256 = all 512 columns), so the template NG = 2 keeps that second operand in SHARED memory: the
+// epilogue of GEMM 1 (+bias, tanh, bf16 pack) writes the 128 x 512 tile in the K-major 128B-swizzled layout the UMMA
+// descriptor expects (eight 16 KB K-chunks, 128 KB), fences it to the async proxy and GEMM 2 runs in the SS form; the
+// weight ring shrinks to four 16 KB stages and carries both layers' boxes back to back.
 // Warp roles: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer (both run converged, one elected lane issues), warps 2..17 = 16 compute
 // warps (four per TMEM lane quarter; group g = (warp-2)/4 takes 32 columns of every 128-column part of the
 // activations and of every accumulator quarter, so MMA start and epilogue tail are both short).
@@ -55,6 +61,9 @@ constexpr int KCH_PER_STAGE = 4;          // K chunks (TMA boxes) per ring stage
 constexpr int B_STAGES = 3;
 constexpr int B_BOX_BYTES = N_MMA * KCH * 2;       // 16 KB per TMA box
 constexpr int B_TILE_BYTES = KCH_PER_STAGE * B_BOX_BYTES;   // 64 KB per stage
+constexpr int A2_BYTES = TILE_M * HID * 2;          // NG = 2: second GEMM's A operand in shared memory (128 KB)
+constexpr int B2_STAGES = (B_STAGES * B_TILE_BYTES - A2_BYTES) / B_BOX_BYTES;   // NG = 2: one-box stages in what is left (4)
+static_assert(B2_STAGES >= 2 && B2_STAGES <= B_STAGES * KCH_PER_STAGE, "NG = 2 ring");
 constexpr int TMEM_A_COL = 0;             // A operand: 512 bf16 per row = 256 packed 32-bit columns
 constexpr int TMEM_D_COL = 256;           // two accumulator buffers of 128 FP32 columns
 constexpr int N_GROUPS = 4;                // compute-warp groups: group g owns accumulator quarter g (128 columns)
@@ -71,6 +80,7 @@ struct MlpSmem {                          // after the 1024-aligned A / B region
     unsigned long long b_full[B_STAGES], b_empty[B_STAGES], a_ready[N_QUARTERS], d_full[2], d_empty[2];
     unsigned long long a_free[N_QUARTERS];   // ping-pong mode: the last accumulator quarter has consumed this K part of A
     unsigned long long key[8];
+    unsigned long long b2_full[B2_STAGES], b2_empty[B2_STAGES], a2_ready[N_QUARTERS];   // NG = 2 ring and second-operand parts
     uint32_t tmem_base;
     float b3[3];
 };
@@ -143,6 +153,14 @@ __device__ __forceinline__ void umma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, u
         "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, {%5, %5, %5, %5}, p;\n\t}"
         ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(UMMA_IDESC), "r"(accumulate), "r"(0u) : "memory");
 }
+// both operands in shared memory (NG = 2, second GEMM)
+__device__ __forceinline__ void umma_bf16_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(UMMA_IDESC), "r"(accumulate), "r"(0u) : "memory");
+}
 __device__ __forceinline__ void tmem_st4(uint32_t taddr, uint32_t r0, uint32_t r1, uint32_t r2, uint32_t r3) {
     asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(r0), "r"(r1), "r"(r2), "r"(r3) : "memory");
 }
@@ -177,6 +195,11 @@ __device__ __forceinline__ uint32_t tanh_bf16x2(float lo, float hi) {
     asm("tanh.approx.bf16x2 %0, %1;" : "=r"(y) : "r"(p));
     return y;
 }
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+    uint32_t p;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(p) : "f"(hi), "f"(lo));
+    return p;
+}
 // one lane of a CONVERGED warp (elect.sync): the MMA / TMA issue loops run warp-converged with the issuing
 // instructions predicated on this, so ptxas emits each UTCHMMA once with uniform-register operands instead of the
 // elect / execute / retire loop it needs inside a divergent `if (lane == 0)` region (8 SASS instructions and ~80
@@ -190,15 +213,17 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
-template <int NIN, bool PP>
+template <int NIN, bool PP, int NG>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(MLP_THREADS, 1)
 mppi_mlp_rollout_kernel(const __grid_constant__ TickArgs a, const __grid_constant__ CUtensorMap w2_map,
                         const float4 *__restrict__ g_w01, const float2 *__restrict__ g_w01u, const float4 *__restrict__ g_w3,
-                        const float *__restrict__ g_b3, float *__restrict__ S_out, int n_tiles) {
+                        const float *__restrict__ g_b3, const float *__restrict__ g_bh, float *__restrict__ S_out, int n_tiles) {
+    static_assert(NG == 1 || (NG == 2 && !PP), "two GEMMs per step run the one-tile schedule");
     // 1024-byte alignment is what SWIZZLE_128B needs; keeping every pointer derived from this symbol (no
     // integer round-trips) lets the compiler emit LDS/STS instead of generic LD/ST
     extern __shared__ __align__(1024) unsigned char dyn[];
-    unsigned char *smB = dyn;                                     // B_STAGES x [128 rows x 128 B], 1024-aligned
+    unsigned char *smB = dyn + (NG == 2 ? A2_BYTES : 0);          // weight ring, 1024-aligned (NG = 2: after the A2 tile)
+    unsigned char *smA2 = dyn;                                    // NG = 2: 8 K-chunks x [128 rows x 128 B], 128B swizzle
     TickSmem &sm = *reinterpret_cast<TickSmem *>(dyn + B_STAGES * B_TILE_BYTES);
     MlpSmem &ms = *reinterpret_cast<MlpSmem *>(dyn + B_STAGES * B_TILE_BYTES + sizeof(TickSmem));
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -223,6 +248,8 @@ mppi_mlp_rollout_kernel(const __grid_constant__ TickArgs a, const __grid_constan
         for (int s = 0; s < B_STAGES; ++s) { mbar_init(&ms.b_full[s], 1); mbar_init(&ms.b_empty[s], 2); }   // empty: both CTAs
         for (int pa = 0; pa < N_QUARTERS; ++pa) { mbar_init(&ms.a_ready[pa], N_COMPUTE); mbar_init(&ms.a_free[pa], 1); }
         for (int bf = 0; bf < 2; ++bf) { mbar_init(&ms.d_full[bf], 1); mbar_init(&ms.d_empty[bf], N_COMPUTE); }
+        for (int s = 0; s < B2_STAGES; ++s) { mbar_init(&ms.b2_full[s], 1); mbar_init(&ms.b2_empty[s], 2); }
+        for (int pa = 0; pa < N_QUARTERS; ++pa) mbar_init(&ms.a2_ready[pa], N_COMPUTE);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -282,6 +309,23 @@ mppi_mlp_rollout_kernel(const __grid_constant__ TickArgs a, const __grid_constan
     if (warp == 0) {
         // ===== TMA producer: the same 16 W2 boxes every timestep, through a B_STAGES ring =====
         const bool leader = elect_one_sync();
+        if constexpr (NG == 2) {
+            // two layers' weights back to back: per step 2 GEMMs x 4 quarters x 8 K-chunks, one 16 KB box per stage;
+            // the tensor map stacks the layers, rows [512 g, 512 g + 512)
+            const int total = my_tiles * T * NG * N_QUARTERS * (HID / KCH);
+            int stage = 0; uint32_t phase = 0;
+            for (int it = 0; it < total; ++it) {
+                const int kc = it % (HID / KCH), nq = (it / (HID / KCH)) % N_QUARTERS, g = (it / (HID / KCH * N_QUARTERS)) % NG;
+                mbar_wait(&ms.b2_empty[stage], phase ^ 1);
+                if (leader) {
+                    mbar_expect_tx(&ms.b2_full[stage], B_BOX_BYTES);
+                    if ((uint32_t)(it & 1) == cta_rank)
+                        tma_load_2d_mc(smB + stage * B_BOX_BYTES, &w2_map, &ms.b2_full[stage], kc * KCH, g * HID + nq * N_MMA, (uint16_t)3);
+                }
+                __syncwarp();
+                if (++stage == B2_STAGES) { stage = 0; phase ^= 1; }
+            }
+        } else {
         constexpr int STAGES_PER_Q = HID / KCH / KCH_PER_STAGE;       // 2 stage loads (64 KB each) per accumulator quarter
         const int total = my_slots * T * N_QUARTERS * STAGES_PER_Q;
         int stage = 0; uint32_t phase = 0;
@@ -300,10 +344,47 @@ mppi_mlp_rollout_kernel(const __grid_constant__ TickArgs a, const __grid_constan
             __syncwarp();
             if (++stage == B_STAGES) { stage = 0; phase ^= 1; }
         }
+        }
     } else if (warp == 1) {
         // ===== MMA issuer: one elected lane of the converged warp drives the tensor core =====
         const bool leader = elect_one_sync();
         int stage = 0; uint32_t phase = 0, a_phase = 0, quarter = 0;
+        if constexpr (NG == 2) {
+            for (int step = 0; step < my_tiles * T; ++step) {
+                for (int g = 0; g < NG; ++g) {
+                    for (int nq = 0; nq < N_QUARTERS; ++nq, ++quarter) {
+                        const uint32_t buf = quarter & 1;
+                        mbar_wait(&ms.d_empty[buf], ((quarter >> 1) & 1) ^ 1);
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                        const uint32_t d_tmem = tmem + TMEM_D_COL + buf * N_MMA;
+                        for (int kc = 0; kc < HID / KCH; ++kc) {
+                            // the first quarter of each GEMM chases its A operand part by part (a part = two K-chunks):
+                            // GEMM 1 reads the layer-1 activations from tensor memory, GEMM 2 the tile GEMM 1's epilogue
+                            // wrote to shared memory
+                            if (nq == 0 && (kc & 1) == 0) mbar_wait(g == 0 ? &ms.a_ready[kc >> 1] : &ms.a2_ready[kc >> 1], a_phase);
+                            mbar_wait(&ms.b2_full[stage], phase);
+                            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                            const uint64_t b_desc0 = umma_desc_sw128(smem_u32(smB + stage * B_BOX_BYTES));
+                            const uint64_t a_desc0 = umma_desc_sw128(smem_u32(smA2 + kc * B_BOX_BYTES));
+                            const uint32_t a_col0 = tmem + TMEM_A_COL + kc * (KCH / 16) * 8;
+                            if (leader) {
+#pragma unroll
+                                for (int k = 0; k < KCH / 16; ++k) {
+                                    if (g == 0) umma_bf16_ts(d_tmem, a_col0 + k * 8, b_desc0 + (uint64_t)((k * 32) >> 4), (kc | k) ? 1u : 0u);
+                                    else umma_bf16_ss(d_tmem, a_desc0 + (uint64_t)((k * 32) >> 4), b_desc0 + (uint64_t)((k * 32) >> 4), (kc | k) ? 1u : 0u);
+                                }
+                                umma_commit_mc(&ms.b2_empty[stage], (uint16_t)3);
+                            }
+                            __syncwarp();
+                            if (++stage == B2_STAGES) { stage = 0; phase ^= 1; }
+                        }
+                        if (leader) umma_commit(&ms.d_full[buf]);
+                        __syncwarp();
+                    }
+                }
+                a_phase ^= 1;
+            }
+        } else
         for (int step = 0; step < my_slots * T; ++step) {
             for (int nq = 0; nq < N_QUARTERS; ++nq, ++quarter) {
                 const uint32_t buf = quarter & 1;
@@ -561,6 +642,39 @@ mppi_mlp_rollout_kernel(const __grid_constant__ TickArgs a, const __grid_constan
                     if (t + 1 < T) control(t + 1, vn0, vn1);
                     sincos_cw(z[2], sn, cs);
                 }
+                // (2b) three tanh layers: epilogue of GEMM 1 = the A operand of GEMM 2.  D -> +bias -> tanh -> bf16, stored
+                //      to shared memory in the K-major 128B-swizzled layout (row r of K-chunk c at c*16 KB + (r/8)*1 KB +
+                //      (r%8)*128 B, 16-byte units XORed with r%8): conflict-free, a quarter-warp covers all 32 banks
+                if constexpr (NG == 2) {
+#pragma unroll 1
+                    for (int nq = 0; nq < N_QUARTERS; ++nq) {
+                        const int col = nq * N_MMA + grp * 32;
+                        const int buf = nq & 1;
+                        mbar_wait_warp(&ms.d_full[buf], d_phase[buf]); d_phase[buf] ^= 1;
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                        uint32_t v[32];
+                        tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(TMEM_D_COL + buf * N_MMA + grp * 32), v);
+                        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                        mbar_arrive(&ms.d_empty[buf]);
+                        unsigned char *dst = smA2 + (col >> 6) * B_BOX_BYTES + (row >> 3) * 1024 + (row & 7) * 128;
+                        const int c16 = (col & 63) >> 3;
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) {
+                            // (shared memory is full: the 2 KB bias vector is read through L1, warp-uniform addresses)
+                            const float4 ba = __ldg(reinterpret_cast<const float4 *>(g_bh + col + 8 * c));
+                            const float4 bb = __ldg(reinterpret_cast<const float4 *>(g_bh + col + 8 * c + 4));
+                            uint4 pk;
+                            pk.x = pack_bf16x2(tanh_approx(__uint_as_float(v[8 * c + 0]) + ba.x), tanh_approx(__uint_as_float(v[8 * c + 1]) + ba.y));
+                            pk.y = pack_bf16x2(tanh_approx(__uint_as_float(v[8 * c + 2]) + ba.z), tanh_approx(__uint_as_float(v[8 * c + 3]) + ba.w));
+                            pk.z = pack_bf16x2(tanh_approx(__uint_as_float(v[8 * c + 4]) + bb.x), tanh_approx(__uint_as_float(v[8 * c + 5]) + bb.y));
+                            pk.w = pack_bf16x2(tanh_approx(__uint_as_float(v[8 * c + 6]) + bb.z), tanh_approx(__uint_as_float(v[8 * c + 7]) + bb.w));
+                            *reinterpret_cast<uint4 *>(dst + (((c16 + c) ^ (row & 7)) << 4)) = pk;
+                        }
+                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> the tensor core's reads
+                        mbar_arrive(&ms.a2_ready[nq]);
+                    }
+                }
                 // (3) epilogue: D -> +b2 -> tanh -> FP32 contraction with the 512x3 output layer
                 float r0 = 0.f, r1 = 0.f, r2 = 0.f;
 #pragma unroll 1
@@ -623,11 +737,12 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32
 
 struct MlpState {
     int K = 0, T = 0, n_sm = 148;
-    __nv_bfloat16 *d_w2 = nullptr;        // [512 out][512 in] bf16, K-major B operand
+    __nv_bfloat16 *d_w2 = nullptr;        // n_gemm x [512 out][512 in] bf16, K-major B operand (layers stacked along the rows)
     float4 *d_w01 = nullptr, *d_w3 = nullptr;
     float2 *d_w01u = nullptr;             // control columns of the folded first layer (n_in = 5)
     float *d_b3 = nullptr;
-    int n_in = 3;
+    float *d_bh = nullptr;                // n_hidden = 3: bias of the layer the first GEMM evaluates
+    int n_in = 3, n_gemm = 1;
     CUtensorMap w2_map;
     bool ready = false;
 };
@@ -639,15 +754,18 @@ MlpState *mlp_create(int K, int T) {
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&m->n_sm, cudaDevAttrMultiProcessorCount, dev);
-    if (cudaMalloc(&m->d_w2, sizeof(__nv_bfloat16) * HID * HID) != cudaSuccess ||
+    if (cudaMalloc(&m->d_w2, sizeof(__nv_bfloat16) * 2 * HID * HID) != cudaSuccess ||
+        cudaMalloc(&m->d_bh, sizeof(float) * HID) != cudaSuccess ||
         cudaMalloc(&m->d_w01, sizeof(float4) * HID) != cudaSuccess ||
         cudaMalloc(&m->d_w3, sizeof(float4) * HID) != cudaSuccess ||
         cudaMalloc(&m->d_w01u, sizeof(float2) * HID) != cudaSuccess ||
         cudaMalloc(&m->d_b3, sizeof(float) * 4) != cudaSuccess) { mlp_destroy(m); return nullptr; }
-    if (cudaFuncSetAttribute(mppi_mlp_rollout_kernel<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MLP_DYN_SMEM) != cudaSuccess ||
-        cudaFuncSetAttribute(mppi_mlp_rollout_kernel<5, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MLP_DYN_SMEM) != cudaSuccess ||
-        cudaFuncSetAttribute(mppi_mlp_rollout_kernel<3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MLP_DYN_SMEM) != cudaSuccess ||
-        cudaFuncSetAttribute(mppi_mlp_rollout_kernel<5, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MLP_DYN_SMEM) != cudaSuccess) {
+    if (cudaFuncSetAttribute(mppi_mlp_rollout_kernel<3, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MLP_DYN_SMEM) != cudaSuccess ||
+        cudaFuncSetAttribute(mppi_mlp_rollout_kernel<5, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MLP_DYN_SMEM) != cudaSuccess ||
+        cudaFuncSetAttribute(mppi_mlp_rollout_kernel<3, true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MLP_DYN_SMEM) != cudaSuccess ||
+        cudaFuncSetAttribute(mppi_mlp_rollout_kernel<5, true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MLP_DYN_SMEM) != cudaSuccess ||
+        cudaFuncSetAttribute(mppi_mlp_rollout_kernel<3, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MLP_DYN_SMEM) != cudaSuccess ||
+        cudaFuncSetAttribute(mppi_mlp_rollout_kernel<5, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MLP_DYN_SMEM) != cudaSuccess) {
         mlp_destroy(m); return nullptr;
     }
     return m;
@@ -655,7 +773,7 @@ MlpState *mlp_create(int K, int T) {
 
 void mlp_destroy(MlpState *m) {
     if (!m) return;
-    cudaFree(m->d_w2); cudaFree(m->d_w01); cudaFree(m->d_w01u); cudaFree(m->d_w3); cudaFree(m->d_b3);
+    cudaFree(m->d_w2); cudaFree(m->d_bh); cudaFree(m->d_w01); cudaFree(m->d_w01u); cudaFree(m->d_w3); cudaFree(m->d_b3);
     delete m;
 }
 
@@ -664,9 +782,12 @@ void mlp_destroy(MlpState *m) {
 // (FP64 accumulation): W01 = W1 W0, b01 = W1 b0 + b1.  StandardScaler pre/post-processing of the trained models,
 // in = (raw - in_mean) / in_scale and out_raw = out * out_scale + out_mean (train/train_diff_mlp.py:72-103,
 // test/test_diff_dyna_eval.py:54-56), is folded into W0 / b0 and W3 / b3 first; null pointers mean identity.
-cudaError_t mlp_set_weights(MlpState *m, int n_in, const float *const W[4], const float *const b[4], const double *in_mean,
+// n_hidden = 2: W / b hold 4 layers (one GEMM per step); n_hidden = 3 (train/train_diff_mlp.py:13-36): 5 layers, the two
+// inner 512x512 layers are the two GEMMs, the first one still folds the input layer.
+cudaError_t mlp_set_weights(MlpState *m, int n_in, int n_hidden, const float *const *W, const float *const *b, const double *in_mean,
                             const double *in_scale, const double *out_mean, const double *out_scale, cudaStream_t st) {
-    if (n_in != 3 && n_in != 5) return cudaErrorInvalidValue;
+    if ((n_in != 3 && n_in != 5) || (n_hidden != 2 && n_hidden != 3)) return cudaErrorInvalidValue;
+    const int n_gemm = n_hidden - 1, l_last = n_hidden, l_out = n_hidden + 1;     // last tanh layer, output layer
     std::vector<double> W0((size_t)HID * n_in), b0(HID);
     for (int i = 0; i < HID; ++i) {
         double bb = b[0][i];
@@ -690,25 +811,27 @@ cudaError_t mlp_set_weights(MlpState *m, int n_in, const float *const W[4], cons
         w01[j] = make_float4((float)s[0], (float)s[1], (float)s[2], (float)bb);
         w01u[j] = make_float2((float)s[3], (float)s[4]);
         const double o0 = out_scale ? out_scale[0] : 1.0, o1 = out_scale ? out_scale[1] : 1.0, o2 = out_scale ? out_scale[2] : 1.0;
-        w3[j] = make_float4(b[2][j], (float)(W[3][0 * HID + j] * o0), (float)(W[3][1 * HID + j] * o1), (float)(W[3][2 * HID + j] * o2));
+        w3[j] = make_float4(b[l_last][j], (float)(W[l_out][0 * HID + j] * o0), (float)(W[l_out][1 * HID + j] * o1), (float)(W[l_out][2 * HID + j] * o2));
     }
-    std::vector<__nv_bfloat16> w2((size_t)HID * HID);
-    for (size_t i = 0; i < w2.size(); ++i) w2[i] = __float2bfloat16(W[2][i]);
+    std::vector<__nv_bfloat16> w2((size_t)n_gemm * HID * HID);
+    for (int g = 0; g < n_gemm; ++g)
+        for (size_t i = 0; i < (size_t)HID * HID; ++i) w2[(size_t)g * HID * HID + i] = __float2bfloat16(W[2 + g][i]);
     float b3[4] = {0.f, 0.f, 0.f, 0.f};
-    for (int c = 0; c < 3; ++c) b3[c] = (float)((double)b[3][c] * (out_scale ? out_scale[c] : 1.0) + (out_mean ? out_mean[c] : 0.0));
+    for (int c = 0; c < 3; ++c) b3[c] = (float)((double)b[l_out][c] * (out_scale ? out_scale[c] : 1.0) + (out_mean ? out_mean[c] : 0.0));
     cudaError_t e;
     if ((e = cudaMemcpyAsync(m->d_w01, w01.data(), sizeof(float4) * HID, cudaMemcpyHostToDevice, st)) != cudaSuccess) return e;
     if ((e = cudaMemcpyAsync(m->d_w3, w3.data(), sizeof(float4) * HID, cudaMemcpyHostToDevice, st)) != cudaSuccess) return e;
     if ((e = cudaMemcpyAsync(m->d_w01u, w01u.data(), sizeof(float2) * HID, cudaMemcpyHostToDevice, st)) != cudaSuccess) return e;
     if ((e = cudaMemcpyAsync(m->d_b3, b3, sizeof(b3), cudaMemcpyHostToDevice, st)) != cudaSuccess) return e;
-    if ((e = cudaMemcpyAsync(m->d_w2, w2.data(), sizeof(__nv_bfloat16) * HID * HID, cudaMemcpyHostToDevice, st)) != cudaSuccess) return e;
+    if ((e = cudaMemcpyAsync(m->d_w2, w2.data(), sizeof(__nv_bfloat16) * w2.size(), cudaMemcpyHostToDevice, st)) != cudaSuccess) return e;
+    if (n_gemm == 2 && (e = cudaMemcpyAsync(m->d_bh, b[2], sizeof(float) * HID, cudaMemcpyHostToDevice, st)) != cudaSuccess) return e;
     if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return e;
     // TMA descriptor of W2: inner dim = K (512 bf16, contiguous), outer dim = N (512 rows); 64 x 256 boxes, 128B swizzle
     void *fn = nullptr;
     cudaDriverEntryPointQueryResult qres;
     if ((e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres)) != cudaSuccess) return e;
     if (!fn || qres != cudaDriverEntryPointSuccess) return cudaErrorNotSupported;
-    const cuuint64_t dims[2] = {HID, HID};
+    const cuuint64_t dims[2] = {HID, (cuuint64_t)n_gemm * HID};
     const cuuint64_t strides[1] = {HID * sizeof(__nv_bfloat16)};
     const cuuint32_t box[2] = {KCH, N_MMA};
     const cuuint32_t estr[2] = {1, 1};
@@ -717,6 +840,7 @@ cudaError_t mlp_set_weights(MlpState *m, int n_in, const float *const W[4], cons
                                       CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return cudaErrorInvalidValue;
     m->n_in = n_in;
+    m->n_gemm = n_gemm;
     m->ready = true;
     return cudaSuccess;
 }
@@ -731,10 +855,11 @@ int mlp_rollout_costs(MlpState *m, const TickArgs &args, bool sum, const float *
     // two tiles per CTA in flight (ping-pong) whenever a CTA owns more than one tile; MPPI_MLP_PINGPONG=0 forces the
     // one-tile schedule (A/B measurements)
     static const bool allow_pp = [] { const char *e = std::getenv("MPPI_MLP_PINGPONG"); return !(e && e[0] == '0'); }();
-    const bool pp = allow_pp && n_tiles > grid;
-#define MPPI_MLP_LAUNCH(N, P) mppi_mlp_rollout_kernel<N, P><<<grid, MLP_THREADS, MLP_DYN_SMEM, st>>>(a, m->w2_map, m->d_w01, m->d_w01u, m->d_w3, m->d_b3, d_S, n_tiles)
-    if (m->n_in == 5) { if (pp) MPPI_MLP_LAUNCH(5, true); else MPPI_MLP_LAUNCH(5, false); }
-    else { if (pp) MPPI_MLP_LAUNCH(3, true); else MPPI_MLP_LAUNCH(3, false); }
+    const bool pp = allow_pp && n_tiles > grid && m->n_gemm == 1;
+#define MPPI_MLP_LAUNCH(N, P, G) mppi_mlp_rollout_kernel<N, P, G><<<grid, MLP_THREADS, MLP_DYN_SMEM, st>>>(a, m->w2_map, m->d_w01, m->d_w01u, m->d_w3, m->d_b3, m->d_bh, d_S, n_tiles)
+    if (m->n_gemm == 2) { if (m->n_in == 5) MPPI_MLP_LAUNCH(5, false, 2); else MPPI_MLP_LAUNCH(3, false, 2); }
+    else if (m->n_in == 5) { if (pp) MPPI_MLP_LAUNCH(5, true, 1); else MPPI_MLP_LAUNCH(5, false, 1); }
+    else { if (pp) MPPI_MLP_LAUNCH(3, true, 1); else MPPI_MLP_LAUNCH(3, false, 1); }
 #undef MPPI_MLP_LAUNCH
     return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }

@@ -172,7 +172,10 @@ int mppi_set_mlp(mppi_handle_t h, const float *const W[4], const float *const b[
  *     x+ = x + dt * ( f(x, u) + out_scale * MLP(([x; u] - in_mean) / in_scale) + out_mean ).
  * W / b: n_hidden + 2 nn.Linear tensors [out][in] (input layer n_in -> 512 first, output layer 512 -> 3 last);
  * in_mean / in_scale: n_in doubles (state scaler then control scaler) or NULL; out_mean / out_scale: 3 doubles or NULL.
- * n_in = 3 is dnn/simple_mlp.py (mppi_set_mlp).  n_hidden must be 2 (MPPI_E_UNSUPPORTED otherwise). */
+ * n_in = 3 is dnn/simple_mlp.py (mppi_set_mlp).  n_hidden = 2 (simulation/bullet_differential_drive_dnn.py:43-45,
+ * mlp_diff.pth, mlp_diff_300x100.pth, mlp_diff_300x100_v2.pth) or 3 (train/train_diff_mlp.py:19-21,
+ * mlp_diff_300x100_3l.pth, mlp_diff_300x100_3l_mppi.pth: a second tensor-core GEMM per step); MPPI_E_UNSUPPORTED
+ * otherwise. */
 int mppi_set_mlp_ex(mppi_handle_t h, int32_t n_in, int32_t n_hidden, const float *const *W, const float *const *b,
                     const double *in_mean, const double *in_scale, const double *out_mean, const double *out_scale);
 

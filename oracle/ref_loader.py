@@ -101,7 +101,9 @@ def load_reference_mlps():
         sys.modules.setdefault(n, _Stub(n))
     m3 = importlib.import_module("dnn.simple_mlp")
     m5 = importlib.import_module("simulation.bullet_differential_drive_dnn")
-    _loaded.update(dict(MLP3=m3.MultiLayerPerception, MLP5=m5.MultiLayerPerceptron))
+    # the three-hidden-layer class the *_3l*.pth checkpoints were trained with (train/train_diff_mlp.py:13-36)
+    m5l3 = importlib.import_module("train.train_diff_mlp")
+    _loaded.update(dict(MLP3=m3.MultiLayerPerception, MLP5=m5.MultiLayerPerceptron, MLP5_3L=m5l3.MultiLayerPerceptron))
     return _loaded
 
 

@@ -135,10 +135,11 @@ def make_mlp_golden():
     ref = ref_loader.load_reference_mlps()
     rng = np.random.default_rng(21)
     out = {}
-    for n_in, cls, last in ((3, ref["MLP3"], "output_layer"), (5, ref["MLP5"], "out_layer")):
-        w = make_mlp(seed=5, out_scale=0.01, dtype=np.float32, n_in=n_in, scalers=(n_in == 5))
+    for tag, n_in, cls, last, n_hidden in (("3", 3, ref["MLP3"], "output_layer", 2), ("5", 5, ref["MLP5"], "out_layer", 2),
+                                           ("5_3l", 5, lambda: ref["MLP5_3L"](5), "out_layer", 3)):
+        w = make_mlp(seed=5, out_scale=0.01, dtype=np.float32, n_in=n_in, scalers=(n_in == 5), n_hidden=n_hidden)
         net = cls()
-        names = ["input_layer", "hidden_layer.0", "hidden_layer.1", last]
+        names = ["input_layer"] + ["hidden_layer.%d" % i for i in range(n_hidden)] + [last]
         net.load_state_dict({n + s: torch.from_numpy(w[k + str(i)]) for i, n in enumerate(names)
                              for s, k in ((".weight", "W"), (".bias", "b"))})
         net = net.double()
@@ -154,10 +155,11 @@ def make_mlp_golden():
         else:
             with torch.no_grad():
                 y = net(torch.from_numpy(X)).numpy()
-        out["X%d" % n_in], out["Y%d" % n_in] = X, y
+        out["X" + tag], out["Y" + tag] = X, y
     out["meta"] = json.dumps(dict(seed=5, out_scale=0.01, numpy=np.__version__, torch=torch.__version__,
                                   source="dnn/simple_mlp.py:MultiLayerPerception and "
-                                         "simulation/bullet_differential_drive_dnn.py:MultiLayerPerceptron, float64"))
+                                         "simulation/bullet_differential_drive_dnn.py:MultiLayerPerceptron, "
+                                         "train/train_diff_mlp.py:MultiLayerPerceptron(5) (three hidden layers), float64"))
     fn = os.path.join(HERE, "mlp_forward.npz")
     np.savez_compressed(fn, **out)
     print("wrote", fn, "%.1f KB" % (os.path.getsize(fn) / 1024))

@@ -170,8 +170,89 @@ def test_mlp5_drop_in_with_state_dict_and_sklearn_style_scalers():
     o = orc.tick_vec(sp, g.path, np.zeros((T, 2)), 0, x0, eps.cpu().numpy().astype(np.float64))
     u0, u, _, _ = ctrl._calc_input_control(x0)
     assert np.max(np.abs(u - o["U_after"])) <= MLP_U_ATOL, np.max(np.abs(u - o["U_after"]))
-    # three hidden layers (saved_models/*_3l*.pth) are refused loudly, not approximated
-    sd3 = dict(sd)
-    sd3["hidden_layer.2.weight"], sd3["hidden_layer.2.bias"] = sd["hidden_layer.1.weight"], sd["hidden_layer.1.bias"]
+    # four hidden layers (no such model in the reference) are refused loudly, not approximated
+    sd4 = dict(sd)
+    for i in (2, 3):
+        sd4["hidden_layer.%d.weight" % i], sd4["hidden_layer.%d.bias" % i] = sd["hidden_layer.1.weight"], sd["hidden_layer.1.bias"]
     with pytest.raises(MppiError):
-        ctrl.set_dynamics(sd3)
+        ctrl.set_dynamics(sd4)
+
+
+# ---- three tanh layers: the class of train/train_diff_mlp.py:13-36 (saved_models/mlp_diff_300x100_3l*.pth) ------------------
+# two bf16 GEMMs in sequence: the second one's A operand is the first one's epilogue, kept in shared memory
+def _mlp3l(n_in, seed=0):
+    if n_in == 3:
+        return orc.make_mlp(seed=seed, out_scale=0.01, n_in=3, n_hidden=3)
+    m = orc.make_mlp(seed=seed, out_scale=0.05, n_in=5, scalers=True, scaler_gain=1.0, n_hidden=3)
+    m["W0"][:, 3:] *= 8.0
+    return m
+
+
+def _set3l(eng, mlp):
+    sc = [mlp[k] for k in ("in_mean", "in_scale", "out_mean", "out_scale")] if "in_scale" in mlp else []
+    eng.set_mlp([mlp["W%d" % i] for i in range(5)], [mlp["b%d" % i] for i in range(5)], *sc)
+
+
+@pytest.mark.parametrize("n_in", [3, 5])
+@pytest.mark.parametrize("K,T,cost_mode", [(128, 12, "sum"), (300, 11, "last"), (1024, 12, "sum"), (40000, 10, "sum")])
+def test_mlp_three_hidden_layers_costs_match_fp64_oracle(K, T, cost_mode, n_in):
+    """K = 40000 gives every CTA more than one tile (ring and barrier phases carry over tiles); K = 300 a ragged one."""
+    g = Golden("diffdrive_pe0.05")
+    mlp = _mlp3l(n_in)
+    sp = _spec(K, T, cost_mode, mlp)
+    eng = engine_from_spec(sp, g.path)
+    _set3l(eng, mlp)
+    eps = torch.zeros(K, T, 2, dtype=torch.float32, device="cuda")
+    eng.generate_noise(eps, seed=3, tick=1)
+    S = torch.zeros(K, dtype=torch.float32, device="cuda")
+    x0 = np.array([0.4, 0.3, 0.5])
+    U = np.random.default_rng(2).normal(0, 0.5, (T, 2)).astype(np.float32)
+    for src in ("philox", "injected"):
+        S.zero_()
+        eng.set_nominal(U)
+        eng.set_waypoint_idx(0)
+        eng.rollout_costs(x0, S, eps if src == "injected" else None, seed=3, tick=1)
+        So, _, s_end = orc.costs_vec(sp, g.path, U.astype(np.float64), 0, x0, eps.cpu().numpy().astype(np.float64))
+        Sg = S.cpu().numpy().astype(np.float64)
+        rel = np.abs(Sg - So) / np.maximum(np.abs(So), 1e-9)
+        assert np.quantile(rel, 0.99) <= MLP_COST_RTOL and rel.max() <= 2e-2, (K, cost_mode, src, np.quantile(rel, 0.99), rel.max())
+    # the third tanh layer really runs: the two-hidden-layer model made of the same first layers gives other costs
+    mlp2 = {k: v for k, v in mlp.items() if k not in ("W3", "b3", "W4", "b4")}
+    mlp2["W3"], mlp2["b3"] = mlp["W4"], mlp["b4"]
+    S2, _, _ = orc.costs_vec(_spec(K, T, cost_mode, mlp2), g.path, U.astype(np.float64), 0, x0, eps.cpu().numpy().astype(np.float64))
+    assert np.median(np.abs(S2 - So)) > 20 * np.median(np.abs(Sg - So)), (np.median(np.abs(S2 - So)), np.median(np.abs(Sg - So)))
+    eng.close()
+
+
+def test_mlp_three_hidden_layers_drop_in_state_dict_and_switching_models():
+    """The drop-in class takes the 3l state dict (hidden_layer.0..2) and can switch between two- and three-layer
+    residuals on one controller; each tick matches the FP64 oracle tick."""
+    from mppi_b200.mppi_differential_drive import MPPIAlgorithms
+    g = Golden("diffdrive_pe0.05")
+    K, T = 2048, 20
+    mlp3, mlp2 = _mlp3l(5, seed=7), _mlp5(seed=3)
+    names = ["input_layer", "hidden_layer.0", "hidden_layer.1", "hidden_layer.2", "out_layer"]
+    sd = {}
+    for i, n in enumerate(names):
+        sd[n + ".weight"] = torch.from_numpy(mlp3["W%d" % i].astype(np.float32))
+        sd[n + ".bias"] = torch.from_numpy(mlp3["b%d" % i].astype(np.float32))
+    scalers = {k: mlp3[k] for k in ("in_mean", "in_scale", "out_mean", "out_scale")}
+    ctrl = MPPIAlgorithms(delta_t=0.1, ref_path=g.path, max_speed=5.0, max_omega=3.14, num_samples_K=K, num_horizons_T=T,
+                          param_exploration=0.05, param_lambda=1.0, param_alpha=0.2, sigma=np.array([[0.1, 0.0], [0.0, 0.01]]),
+                          stage_cost_weight=np.array([5.0, 5.0, 10.0]), terminal_cost_weight=np.array([5.0, 5.0, 10.0]),
+                          visualize_optimal_traj=False, visualze_sampled_trajs=False, cost_mode="sum",
+                          waypoint_mode="frozen", temperature=2.0, dynamics=mlp2, seed=4)
+    eps = torch.zeros(K, T, 2, dtype=torch.float32, device="cuda")
+    x0 = np.array([0.2, 0.1, 0.3])
+    U, idx = np.zeros((T, 2)), 0
+    for tick, mlp in enumerate((mlp2, mlp3, mlp2, mlp3)):
+        if mlp is mlp3:
+            ctrl.set_dynamics(sd, scalers=scalers)
+        else:
+            ctrl.set_dynamics(mlp2)
+        ctrl.engine.generate_noise(eps, seed=4, tick=tick)
+        o = orc.tick_vec(_spec(K, T, "sum", mlp), g.path, U, idx, x0, eps.cpu().numpy().astype(np.float64))
+        u0, u, _, _ = ctrl._calc_input_control(x0)
+        assert np.max(np.abs(u - o["U_after"])) <= MLP_U_ATOL, (tick, np.max(np.abs(u - o["U_after"])))
+        assert ctrl.prev_way_point_idx == o["idx_after"]
+        U, idx = u.copy(), o["idx_after"]

@@ -192,33 +192,38 @@ def test_target_soft_running_cost_matches_reference_functions():
     assert rel_err(a["S"], g.rec["S"][0][:24]) <= 2e-6
 
 
-@pytest.mark.parametrize("n_in", [3, 5])
-def test_mlp_forward_matches_reference_torch_modules(n_in):
+@pytest.mark.parametrize("n_in,n_hidden", [(3, 2), (5, 2), (5, 3)])
+def test_mlp_forward_matches_reference_torch_modules(n_in, n_hidden):
     """the oracle's residual MLP vs forward passes of the reference's own torch modules
     (tests/golden/mlp_forward.npz), including the StandardScaler pre/post-processing of the 5-input model."""
     import os
     from golden_util import GOLDEN_DIR
     z = np.load(os.path.join(GOLDEN_DIR, "mlp_forward.npz"))
-    w = orc.make_mlp(seed=5, out_scale=0.01, dtype=np.float64, n_in=n_in, scalers=(n_in == 5))
-    X = z["X%d" % n_in]
+    w = orc.make_mlp(seed=5, out_scale=0.01, dtype=np.float64, n_in=n_in, scalers=(n_in == 5), n_hidden=n_hidden)
+    tag = "%d" % n_in + ("_3l" if n_hidden == 3 else "")       # 5_3l: the class of train/train_diff_mlp.py:13-36
+    X = z["X" + tag]
     y = orc.mlp_forward(w, X[:, :3], X[:, 3:] if n_in == 5 else None)
-    assert np.max(np.abs(y - z["Y%d" % n_in])) <= 1e-12
+    assert np.max(np.abs(y - z["Y" + tag])) <= 1e-12
 
 
 @pytest.mark.requires_reference
-def test_oracle_mlp_matches_the_trained_reference_model():
-    """Build container only: the TRAINED residual (saved_models/mlp_diff_300x100.pth + its scalers) evaluated by the
-    reference's torch class and sklearn scalers vs the oracle restatement."""
+@pytest.mark.parametrize("ckpt,scalers,cls_key", [("mlp_diff_300x100.pth", "scalers_mlp_diff_300x100_20_l.pth", "MLP5"),
+                                                  ("mlp_diff_300x100_3l.pth", "scalers_mlp_diff_300x100_20_l.pth", "MLP5_3L"),
+                                                  ("mlp_diff_300x100_3l_mppi.pth", "scalers_mlp_diff_300x100_3l_mppi.pth", "MLP5_3L")])
+def test_oracle_mlp_matches_the_trained_reference_model(ckpt, scalers, cls_key):
+    """Build container only: the TRAINED residuals (saved_models/mlp_diff_300x100*.pth + their scalers; the *_3l ones
+    have three hidden layers, train/train_diff_mlp.py:13-36, paired as in test/bullet_differential_drive_dnn.py:229-234)
+    evaluated by the reference's torch classes and sklearn scalers vs the oracle restatement."""
     import warnings
     import torch
     from oracle import ref_loader
     ref = ref_loader.load_reference_mlps()
     root = ref_loader.REFERENCE_ROOT
-    sd = torch.load(os.path.join(root, "saved_models", "mlp_diff_300x100.pth"), map_location="cpu")
+    sd = torch.load(os.path.join(root, "saved_models", ckpt), map_location="cpu")
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
-        sc = torch.load(os.path.join(root, "saved_models", "scalers_mlp_diff_300x100_20_l.pth"), weights_only=False)
-    net = ref["MLP5"]()
+        sc = torch.load(os.path.join(root, "saved_models", scalers), weights_only=False)
+    net = ref[cls_key](5) if cls_key == "MLP5_3L" else ref[cls_key]()
     net.load_state_dict(sd)
     net = net.double()
     X = np.random.default_rng(0).normal(0, 1.0, (16, 5)) * [3.0, 2.0, 1.0, 1.0, 1.5]
@@ -227,7 +232,8 @@ def test_oracle_mlp_matches_the_trained_reference_model():
         xin = np.concatenate([sc["state_scaler"].transform(X[:, :3]), sc["control_scaler"].transform(X[:, 3:])], axis=1)
         with torch.no_grad():
             y_ref = sc["error_scaler"].inverse_transform(net(torch.from_numpy(xin)).numpy())
-    names = ["input_layer", "hidden_layer.0", "hidden_layer.1", "out_layer"]
+    n_hidden = 3 if cls_key == "MLP5_3L" else 2
+    names = ["input_layer"] + ["hidden_layer.%d" % i for i in range(n_hidden)] + ["out_layer"]
     w = {}
     for i, n in enumerate(names):
         w["W%d" % i] = sd[n + ".weight"].numpy().astype(np.float64)

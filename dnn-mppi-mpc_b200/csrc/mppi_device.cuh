@@ -149,7 +149,28 @@ struct TickSmem {
     float x0[4];
     int win_start, n_win16;                // absolute index of window entry 0; padded length / 16
     float4 cb[MPPI_MAX_WINDOW / 16];       // dynamic window: bounding circle (cx, cy, r) of every 16-entry chunk
+    // static 20-entry window, expanded form (MPPI_WIN20_EXPANDED): coordinates relative to the window centre and their
+    // squared norms, d_j - |p'|^2 = ec_j - 2 p'.(ex_j, ey_j)
+    __align__(16) float ex[20];
+    __align__(16) float ey[20];
+    __align__(16) float ec[20];
+    float c2x, c2y;                        // twice the centre
 };
+
+// Fills the expanded-form arrays of the static window from the (already written) negated coordinates; entries past the
+// path end (sentinels) get distance 1e30.  Call between the barriers of the prologue, any thread count.
+__device__ __forceinline__ void fill_window_expanded(TickSmem &sm, int nw, int tid, int nthreads) {
+    const int jc = nw > 10 ? 10 : nw - 1;
+    const float cx = -sm.wx[jc], cy = -sm.wy[jc];
+    for (int j = tid; j < 20; j += nthreads) {
+        const float wx = __fsub_rn(-sm.wx[j], cx), wy = __fsub_rn(-sm.wy[j], cy);
+        const bool valid = j < nw;
+        sm.ex[j] = valid ? wx : 0.f;
+        sm.ey[j] = valid ? wy : 0.f;
+        sm.ec[j] = valid ? __fmaf_rn(wy, wy, __fmul_rn(wx, wx)) : 1e30f;
+    }
+    if (tid == 0) { sm.c2x = 2.f * cx; sm.c2y = 2.f * cy; }
+}
 
 // Bounding circle of the window entries path[first .. first + n_valid) (one 16-entry chunk of the dynamic window).
 // nearest_wp<0> skips a chunk only when this circle proves every point in it farther than the best found so far,
@@ -195,6 +216,9 @@ __device__ __forceinline__ float2 f2_fma(float2 a, float2 b, float2 c) {
 // The window arrays hold NEGATED coordinates so the differences are plain packed adds.
 #ifndef MPPI_WP_CHUNK_ILP
 #define MPPI_WP_CHUNK_ILP 1
+#endif
+#ifndef MPPI_WIN20_EXPANDED
+#define MPPI_WIN20_EXPANDED 1   // static window distances as ec_j - 2 p'.w'_j: 2 packed FMAs per waypoint pair instead of 4 ops (0: direct form)
 #endif
 #ifndef MPPI_ARGMIN_KEY_SEL
 #define MPPI_ARGMIN_KEY_SEL 0   // 1: first-min index by FSETP/SEL chains on the ALU pipe (A/B variant, see profiles/)
@@ -282,9 +306,36 @@ __device__ __forceinline__ int nearest_wp(const TickSmem &sm, float x, float y) 
     const float4 *nwx4 = reinterpret_cast<const float4 *>(sm.wx);
     const float4 *nwy4 = reinterpret_cast<const float4 *>(sm.wy);
     if (WIN == 20) {
+#if MPPI_WIN20_EXPANDED
+        // squared distances up to the common term |p'|^2, in coordinates relative to the window centre (|w'| <= ~1 m, so
+        // the cancellation costs no more than the FP32 rounding of the absolute path coordinates does in the direct form)
+        const float ax = fmaf(-2.f, x, sm.c2x), ay = fmaf(-2.f, y, sm.c2y);
+        const float2 axx = make_float2(ax, ax), ayy = make_float2(ay, ay);
+        const float4 *ex4 = reinterpret_cast<const float4 *>(sm.ex), *ey4 = reinterpret_cast<const float4 *>(sm.ey);
+        const float4 *ec4 = reinterpret_cast<const float4 *>(sm.ec);
+        float2 d[10];
+#pragma unroll
+        for (int q = 0; q < 5; ++q) {
+            const float4 X = ex4[q], Y = ey4[q], C = ec4[q];
+            d[2 * q] = f2_fma(make_float2(Y.x, Y.y), ayy, f2_fma(make_float2(X.x, X.y), axx, make_float2(C.x, C.y)));
+            d[2 * q + 1] = f2_fma(make_float2(Y.z, Y.w), ayy, f2_fma(make_float2(X.z, X.w), axx, make_float2(C.z, C.w)));
+        }
+        float m = fminf(d[0].x, d[0].y);
+#pragma unroll
+        for (int i = 1; i < 10; ++i) m = fminf(fminf(m, d[i].x), d[i].y);
+        const float2 nm = make_float2(-m, -m), huge = make_float2(1.2676506e30f, 1.2676506e30f);
+        float key = CUDART_INF_F;
+#pragma unroll
+        for (int i = 0; i < 10; ++i) {
+            const float2 k2 = f2_fma(f2_add(d[i], nm), huge, make_float2((float)(2 * i), (float)(2 * i + 1)));
+            key = fminf(fminf(key, k2.x), k2.y);
+        }
+        return __float2int_rn(key);
+#else
         float m, key;
         chunk_argmin<20>(nwx4, nwy4, x, y, m, key);
         return __float2int_rn(key);
+#endif
     }
     // dynamic window: chunks of 16 entries (the window is padded with sentinels to a multiple of 16)
     float bm = CUDART_INF_F, sbm = CUDART_INF_F;      // best squared distance so far and its square root

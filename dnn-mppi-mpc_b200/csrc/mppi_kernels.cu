@@ -280,6 +280,9 @@ __global__ void __launch_bounds__(MPPI_BLOCK, STASH ? 2 : MPPI_MIN_BLOCKS) mppi_
             }
         }
         if (tid == 0) { sm.win_start = s_new; sm.n_win16 = fill >> 4; }
+#if MPPI_WIN20_EXPANDED
+        if (WIN == 20) { __syncthreads(); fill_window_expanded(sm, nw, tid, MPPI_BLOCK); }
+#endif
         if (WIN == 0)
             for (int c = tid; c < (fill >> 4); c += MPPI_BLOCK) sm.cb[c] = chunk_bound(rpath, s_new + 16 * c, min(16, nw - 16 * c));
         const float *Ur = a.U + (size_t)robot * T * 2;

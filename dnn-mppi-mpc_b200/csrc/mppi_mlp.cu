@@ -292,6 +292,9 @@ mppi_mlp_rollout_kernel(const __grid_constant__ TickArgs a, const __grid_constan
             }
         }
         if (tid == 0) { sm.win_start = s_new; sm.n_win16 = fill >> 4; }
+#if MPPI_WIN20_EXPANDED
+        if (a.window == 20) { __syncthreads(); fill_window_expanded(sm, nw, tid, MLP_THREADS); }
+#endif
         if (a.window != 20)
             for (int c = tid; c < (fill >> 4); c += MLP_THREADS) sm.cb[c] = chunk_bound(a.path, s_new + 16 * c, min(16, nw - 16 * c));
         for (int t = tid; t < T; t += MLP_THREADS) {

@@ -85,6 +85,7 @@ SYMBOLS = {
     "mppi_set_timing": (C.c_int, [_H, C.c_int32]),
     "mppi_get_timings": (C.c_int, [_H, C.POINTER(MppiTimings)]),
     "mppi_abi_version": (C.c_int, []),
+    "mppi_probe_fp32_peak": (C.c_int, [C.c_int32, C.c_int32, C.POINTER(C.c_double)]),
 }
 
 _lib = None

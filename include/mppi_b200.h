@@ -256,6 +256,10 @@ int mppi_comm_p2p_open(mppi_handle_t h, const void *ipc_handles, int32_t rank, i
 int mppi_set_timing(mppi_handle_t h, int32_t enabled);
 int mppi_get_timings(mppi_handle_t h, mppi_timings_t *out);
 int mppi_abi_version(void);
+/* Measurement aid, no reference counterpart: achieved FP32 FMA throughput (TFLOP/s, best of 3) of a register-only FFMA
+ * (packed = 0) or FFMA2 (packed = 1) loop filling every SM of `device` -- the measured denominator of the FP32 roofline the
+ * analytic-dynamics kernels are bound by (MEASURED_PEAKS.json has no FP32 entry). */
+int mppi_probe_fp32_peak(int32_t device, int32_t packed, double *tflops_out);
 
 #ifdef __cplusplus
 }

@@ -16,6 +16,8 @@ state in and a host control out every tick.  `--impl reference` times the CPU re
 reference tick (oracle/, the one place bench.py may execute it) on the host cores.
 """
 import argparse
+import contextlib
+import io
 import json
 import os
 import subprocess
@@ -514,10 +516,25 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     args = ap.parse_args()
     args.warmup = max(3, args.warmup)
-    if args.impl == "reference":
-        run_reference_arm(args)
-    else:
-        run_b200_arm(args)
+    # stdout carries exactly ONE JSON line: native libraries (NCCL prints its version banner there) and anything else
+    # that writes to fd 1 during the run go to stderr; the line itself is written to the saved descriptor
+    sys.stdout.flush()
+    real_out = os.dup(1)
+    os.dup2(2, 1)
+    buf = io.StringIO()
+    with contextlib.redirect_stdout(buf):
+        if args.impl == "reference":
+            run_reference_arm(args)
+        else:
+            run_b200_arm(args)
+    sys.stdout.flush()
+    lines = [ln for ln in buf.getvalue().splitlines() if ln.startswith("{")]
+    other = [ln for ln in buf.getvalue().splitlines() if not ln.startswith("{")]
+    if other:
+        sys.stderr.write("\n".join(other) + "\n")
+    if lines:
+        os.write(real_out, (lines[-1] + "\n").encode())
+    os.close(real_out)
 
 
 if __name__ == "__main__":

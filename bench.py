@@ -330,6 +330,47 @@ def run_b200_arm(args):
         rc.engine.run_closed_loop(lp[0].astype(np.float64), 200, seed=3, tick0=100, plant=1)
         extras["racecar_K16384_H50"]["device_closed_loop_ms_per_tick"] = 1e3 * (time.perf_counter() - t1) / 200
         rc.engine.close()
+        # race-car + obstacles at the large-sample size: ~720 algorithmic flop per sample-step -- the analytic kernel
+        # with the highest FP32 roofline fraction
+        rc1 = MPPIRacecarController(horizon_step_T=50, number_of_samples_K=K_PER_GPU, visualize_optimal_traj=False,
+                                    visualze_sampled_trajs=False, seed=3)
+        rc1.ref_path = lp
+        rc1.engine.set_stream(stream.cuda_stream)
+        for i in range(3):
+            rc1.engine.step_async(lp[0].astype(np.float64), None, 3, i)
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(stream):
+            a.record(stream)
+            for i in range(10):
+                rc1.engine.step_async(lp[0].astype(np.float64), None, 3, 10 + i)
+            b.record(stream)
+        torch.cuda.synchronize()
+        ms_rc = a.elapsed_time(b) / 10
+        extras["racecar_K1M_H50"] = {"ms_per_tick": ms_rc, "sample_steps_per_sec": K_PER_GPU * 50 / (ms_rc * 1e-3),
+                                     "algorithmic_flop_per_sample_step": 720.0,
+                                     "algorithmic_TFLOPs": K_PER_GPU * 50 * 720.0 / (ms_rc * 1e-3) / 1e12,
+                                     "frac_of_derived_fp32_peak": K_PER_GPU * 50 * 720.0 / (ms_rc * 1e-3) / 1e12 /
+                                                                  (SM_COUNT * FP32_LANES * 2 * 1965.0e6 / 1e12)}
+        rc1.engine.close()
+        # the reference class's literal cost rule (quirk Q1: only the last step's cost survives) with the frozen waypoint
+        # index: no per-step waypoint search, ~115 lane-instructions per sample-step (SURVEY 8d issue-slot view)
+        kwl = diffdrive_kwargs(K_PER_GPU, T_H, 10.0)
+        kwl.update(cost_mode="last")
+        cl = MPPIAlgorithms(**kwl, seed=7)
+        cl.engine.set_stream(stream.cuda_stream)
+        for i in range(3):
+            cl.engine.step_async(x0, None, 7, i)
+        torch.cuda.synchronize()
+        with torch.cuda.stream(stream):
+            a.record(stream)
+            for i in range(10):
+                cl.engine.step_async(x0, None, 7, 10 + i)
+            b.record(stream)
+        torch.cuda.synchronize()
+        extras["diffdrive_K1M_H50_last_frozen"] = {"ms_per_tick": a.elapsed_time(b) / 10,
+                                                   "sample_steps_per_sec": K_PER_GPU * T_H / (a.elapsed_time(b) / 10 * 1e-3)}
+        cl.engine.close()
         # config[3]: 4096 independent diff-drive controllers x K=1024 x H=30 in one launch
         from mppi_b200.batched import BatchedMPPI
         R = 4096

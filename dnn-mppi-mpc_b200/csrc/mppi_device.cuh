@@ -175,17 +175,20 @@ __device__ __forceinline__ void fill_window_expanded(TickSmem &sm, int nw, int t
 // Bounding circle of the window entries path[first .. first + n_valid) (one 16-entry chunk of the dynamic window).
 // nearest_wp<0> skips a chunk only when this circle proves every point in it farther than the best found so far,
 // so the argmin stays exactly the reference's (first minimum over the whole window).
-__device__ __forceinline__ float4 chunk_bound(const float4 *path, int first, int n_valid) {
+// Reads the window from SHARED memory (negated coordinates, already staged): 32 dependent global loads per thread here
+// were several microseconds of every CTA's prologue, which is what a K = 16 384 tick is made of.
+__device__ __forceinline__ float4 chunk_bound(const float *nwx, const float *nwy, int first, int n_valid) {
     float xmin = CUDART_INF_F, xmax = -CUDART_INF_F, ymin = CUDART_INF_F, ymax = -CUDART_INF_F;
+#pragma unroll 4
     for (int j = 0; j < n_valid; ++j) {
-        const float4 p = path[first + j];
-        xmin = fminf(xmin, p.x); xmax = fmaxf(xmax, p.x); ymin = fminf(ymin, p.y); ymax = fmaxf(ymax, p.y);
+        const float px = -nwx[first + j], py = -nwy[first + j];
+        xmin = fminf(xmin, px); xmax = fmaxf(xmax, px); ymin = fminf(ymin, py); ymax = fmaxf(ymax, py);
     }
     const float cx = 0.5f * (xmin + xmax), cy = 0.5f * (ymin + ymax);
     float r2 = 0.f;
+#pragma unroll 4
     for (int j = 0; j < n_valid; ++j) {
-        const float4 p = path[first + j];
-        const float dx = p.x - cx, dy = p.y - cy;
+        const float dx = -nwx[first + j] - cx, dy = -nwy[first + j] - cy;
         r2 = fmaxf(r2, fmaf(dy, dy, dx * dx));
     }
     return make_float4(cx, cy, sqrtf(r2) * 1.00001f + 1e-6f, 0.f);

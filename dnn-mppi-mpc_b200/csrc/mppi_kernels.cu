@@ -283,8 +283,10 @@ __global__ void __launch_bounds__(MPPI_BLOCK, STASH ? 2 : MPPI_MIN_BLOCKS) mppi_
 #if MPPI_WIN20_EXPANDED
         if (WIN == 20) { __syncthreads(); fill_window_expanded(sm, nw, tid, MPPI_BLOCK); }
 #endif
-        if (WIN == 0)
-            for (int c = tid; c < (fill >> 4); c += MPPI_BLOCK) sm.cb[c] = chunk_bound(rpath, s_new + 16 * c, min(16, nw - 16 * c));
+        if (WIN == 0) {
+            __syncthreads();                            // the window is staged: bound every 16-entry chunk from shared memory
+            for (int c = tid; c < (fill >> 4); c += MPPI_BLOCK) sm.cb[c] = chunk_bound(sm.wx, sm.wy, 16 * c, min(16, nw - 16 * c));
+        }
         const float *Ur = a.U + (size_t)robot * T * 2;
         for (int t = tid; t < T; t += MPPI_BLOCK) {
             const float u0 = Ur[2 * t], u1 = Ur[2 * t + 1];

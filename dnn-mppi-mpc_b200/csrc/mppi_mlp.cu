@@ -69,6 +69,15 @@ constexpr int TMEM_D_COL = 256;           // two accumulator buffers of 128 FP32
 constexpr int N_GROUPS = 4;                // compute-warp groups: group g owns accumulator quarter g (128 columns)
 constexpr int N_COMPUTE = 128 * N_GROUPS;  // 16 compute warps: 4 per TMEM lane quarter
 constexpr int MLP_THREADS = 64 + N_COMPUTE;
+// ping-pong schedule, A/B variants: register-tiled layer 1 / epilogue (16x256b tensor-memory shapes, four rows per thread, a
+// quarter of the weight loads) instead of one row per thread (32x32b shapes)
+#ifndef MPPI_MLP_RT_L1
+#define MPPI_MLP_RT_L1 0
+#endif
+#ifndef MPPI_MLP_RT_EP
+#define MPPI_MLP_RT_EP 0
+#endif
+
 
 struct MlpSmem {                          // after the 1024-aligned A / B regions
     float4 w01[HID];                      // (W01[j][0], W01[j][1], W01[j][2], b01[j])
@@ -163,6 +172,21 @@ __device__ __forceinline__ void umma_bf16_ss(uint32_t d_tmem, uint64_t a_desc, u
 }
 __device__ __forceinline__ void tmem_st4(uint32_t taddr, uint32_t r0, uint32_t r1, uint32_t r2, uint32_t r3) {
     asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(r0), "r"(r1), "r"(r2), "r"(r3) : "memory");
+}
+// 16 lanes x 256-bit shapes: thread t of the warp holds rows t/4 and t/4 + 8 of the 16-lane slab the address names and the
+// 32-bit columns 8c + 2(t%4) + {0, 1} of every 8-column block c (register 4c + 2i + e: row t/4 + 8i, column 8c + 2(t%4) + e) --
+// the layout of an mma C fragment.  Several rows per thread = the per-column weights are loaded once for four rows.
+__device__ __forceinline__ void tmem_st_16x256b_x2(uint32_t taddr, const uint32_t (&r)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.16x256b.x2.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                 ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_16x256b_x4(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.16x256b.x4.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
 }
 __device__ __forceinline__ void umma_commit(unsigned long long *bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -295,8 +319,10 @@ mppi_mlp_rollout_kernel(const __grid_constant__ TickArgs a, const __grid_constan
 #if MPPI_WIN20_EXPANDED
         if (a.window == 20) { __syncthreads(); fill_window_expanded(sm, nw, tid, MLP_THREADS); }
 #endif
-        if (a.window != 20)
-            for (int c = tid; c < (fill >> 4); c += MLP_THREADS) sm.cb[c] = chunk_bound(a.path, s_new + 16 * c, min(16, nw - 16 * c));
+        if (a.window != 20) {
+            __syncthreads();
+            for (int c = tid; c < (fill >> 4); c += MLP_THREADS) sm.cb[c] = chunk_bound(sm.wx, sm.wy, 16 * c, min(16, nw - 16 * c));
+        }
         for (int t = tid; t < T; t += MLP_THREADS) {
             const float u0 = a.U[2 * t], u1 = a.U[2 * t + 1];
             sm.U[t] = make_float2(u0, u1);
@@ -473,6 +499,53 @@ mppi_mlp_rollout_kernel(const __grid_constant__ TickArgs a, const __grid_constan
                     if (NIN == 5) ms.xw[row] = vc1;
                 }
                 named_bar_sync(1, N_COMPUTE);
+#if MPPI_MLP_RT_L1
+                // four rows per thread: rows q*32 + 8r + lane/4 (r = 2h + i: 16-lane slab h, register pair i); per 128-column
+                // part this group's 32 hidden units are 16 packed columns = one 16x256b.x2 store per slab; the thread
+                // evaluates units 16c + 4(lane%4) + 0..3 of them
+                float4 st4[4]; float su4[4];
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    st4[r] = ms.xs[q * 32 + 8 * r + (lane >> 2)];
+                    su4[r] = NIN == 5 ? ms.xw[q * 32 + 8 * r + (lane >> 2)] : 0.f;
+                }
+#pragma unroll 1
+                for (int part = 0; part < N_QUARTERS; ++part) {
+                    if (l1_count > 0) {
+                        mbar_wait_warp(&ms.a_free[part], (l1_count - 1) & 1);
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    }
+                    uint32_t pk[2][8];                                // [slab h][4c + 2i + e]
+#pragma unroll
+                    for (int c = 0; c < 2; ++c) {
+                        const int col = part * N_MMA + grp * 32 + 16 * c + 4 * (lane & 3);
+#pragma unroll
+                        for (int e = 0; e < 2; ++e) {
+                            const float4 wa = ms.w01[col + 2 * e], wb = ms.w01[col + 2 * e + 1];
+                            float4 wu = make_float4(0.f, 0.f, 0.f, 0.f);
+                            if (NIN == 5) wu = *reinterpret_cast<const float4 *>(&ms.w01u[col + 2 * e]);
+#pragma unroll
+                            for (int r = 0; r < 4; ++r) {
+                                float pa = fmaf(wa.x, st4[r].x, fmaf(wa.y, st4[r].y, fmaf(wa.z, st4[r].z, wa.w)));
+                                float pb = fmaf(wb.x, st4[r].x, fmaf(wb.y, st4[r].y, fmaf(wb.z, st4[r].z, wb.w)));
+                                if (NIN == 5) {
+                                    pa = fmaf(wu.x, st4[r].w, fmaf(wu.y, su4[r], pa));
+                                    pb = fmaf(wu.z, st4[r].w, fmaf(wu.w, su4[r], pb));
+                                }
+                                pk[r >> 1][4 * c + 2 * (r & 1) + e] = tanh_bf16x2(pa, pb);
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int h = 0; h < 2; ++h)
+                        tmem_st_16x256b_x2(tmem + ((uint32_t)(q * 32 + 16 * h) << 16) + TMEM_A_COL + (uint32_t)((part * N_MMA + grp * 32) >> 1), pk[h]);
+                    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    mbar_arrive(&ms.a_ready[part]);
+                }
+                ++l1_count;
+                return;
+#endif
                 const float4 st = ms.xs[row];
                 const float su1 = NIN == 5 ? ms.xw[row] : 0.f;
 #pragma unroll 1
@@ -506,7 +579,66 @@ mppi_mlp_rollout_kernel(const __grid_constant__ TickArgs a, const __grid_constan
                 ++l1_count;
             };
             // one accumulator quarter: D -> +b2 -> tanh -> partial contraction with the 512x3 output layer
+#if MPPI_MLP_RT_EP
+            // register-tiled epilogue: the thread holds rows 8r + lane/4 (r = 0..3) of its lane quarter and, of every 8-column
+            // block, columns 2(lane%4) + {0, 1}; part_sum[r][0..2] are its partial output-layer sums for those rows
+            float part_sum[4][3];
+            auto zero_rt = [&]() {
+#pragma unroll
+                for (int r = 0; r < 4; ++r) part_sum[r][0] = part_sum[r][1] = part_sum[r][2] = 0.f;
+            };
+            // sums over the four lanes of a quad; then row `lane` of the lane quarter lands in lane `lane`: quad r_lo = lane/4
+            // holds rows r_lo + 8r, lane 4 r_lo + cq offers row r_lo + 8 cq, lane L reads from lane 4 (L % 8) + L / 8
+            auto gather_rt = [&](float &r0, float &r1, float &r2) {
+                float o[3];
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    float s4[4];
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) {
+                        float t = part_sum[r][c];
+                        t += __shfl_xor_sync(0xffffffffu, t, 1);
+                        t += __shfl_xor_sync(0xffffffffu, t, 2);
+                        s4[r] = t;
+                    }
+                    const int cq = lane & 3;
+                    const float mine = cq == 0 ? s4[0] : cq == 1 ? s4[1] : cq == 2 ? s4[2] : s4[3];
+                    o[c] = __shfl_sync(0xffffffffu, mine, 4 * (lane & 7) + (lane >> 3));
+                }
+                r0 = o[0]; r1 = o[1]; r2 = o[2];
+            };
+#endif
             auto epilogue = [&](int nq, float &r0, float &r1, float &r2) {
+#if MPPI_MLP_RT_EP
+                {
+                    const int buf = nq & 1;
+                    mbar_wait_warp(&ms.d_full[buf], d_phase[buf]); d_phase[buf] ^= 1;
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    uint32_t v[2][16];
+#pragma unroll
+                    for (int h = 0; h < 2; ++h)
+                        tmem_ld_16x256b_x4(tmem + ((uint32_t)(q * 32 + 16 * h) << 16) + (uint32_t)(TMEM_D_COL + buf * N_MMA + grp * 32), v[h]);
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    mbar_arrive(&ms.d_empty[buf]);
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+#pragma unroll
+                        for (int e = 0; e < 2; ++e) {
+                            const float4 w = ms.w3[nq * N_MMA + grp * 32 + 8 * c + 2 * (lane & 3) + e];
+#pragma unroll
+                            for (int r = 0; r < 4; ++r) {
+                                const float hv = tanh_approx(__uint_as_float(v[r >> 1][4 * c + 2 * (r & 1) + e]) + w.x);
+                                part_sum[r][0] = fmaf(w.y, hv, part_sum[r][0]);
+                                part_sum[r][1] = fmaf(w.z, hv, part_sum[r][1]);
+                                part_sum[r][2] = fmaf(w.w, hv, part_sum[r][2]);
+                            }
+                        }
+                    }
+                    if (nq == N_QUARTERS - 1) gather_rt(r0, r1, r2);      // the step's last quarter: per-row sums to their lanes
+                    return;
+                }
+#endif
                 const int col = nq * N_MMA + grp * 32;
                 const int buf = nq & 1;
                 mbar_wait_warp(&ms.d_full[buf], d_phase[buf]); d_phase[buf] ^= 1;
@@ -551,6 +683,9 @@ mppi_mlp_rollout_kernel(const __grid_constant__ TickArgs a, const __grid_constan
                     if (grp == 1) prep(t);
                 }
                 r0 = r1 = r2 = 0.f;
+#if MPPI_MLP_RT_EP
+                zero_rt();
+#endif
                 epilogue(0, r0, r1, r2); epilogue(1, r0, r1, r2); epilogue(2, r0, r1, r2);      // X(t)
                 layer1(1);                                           // L1(Y, t) chases X(t)'s last quarter
                 // ---- slot Y(t): the tensor core runs GEMM Y(t)
@@ -558,6 +693,9 @@ mppi_mlp_rollout_kernel(const __grid_constant__ TickArgs a, const __grid_constan
                 finish(0, r0, r1, r2);
                 if (grp == 0 && t + 1 < T) prep(t + 1);
                 s0 = s1 = s2 = 0.f;
+#if MPPI_MLP_RT_EP
+                zero_rt();
+#endif
                 epilogue(0, s0, s1, s2); epilogue(1, s0, s1, s2); epilogue(2, s0, s1, s2);      // Y(t)
                 if (t + 1 < T) layer1(0);                            // L1(X, t+1) chases Y(t)'s last quarter
             }

@@ -418,6 +418,25 @@ def run_b200_arm(args):
             "frac_of_tensor_peak_executed": 65536 * 30 * 2 * 512 * 512 / (ms_mlp * 1e-3) / 1e12 / pk.get("bf16_tflops", 1590.0),
             "note": "Linear(3,512) has no activation and is folded into the first hidden layer on the host, so one 512x512 GEMM is executed per step"}
         cm.engine.close()
+        # the same kernel with every SM owning exactly 4 tiles (K = 148 x 4 x 128): K = 65536 is 3.46 tiles per SM, its time
+        # is set by the SMs that own 4
+        K_full = SM_COUNT * 4 * 128
+        cmf = MPPIAlgorithms(**diffdrive_kwargs(K_full, 30, 2.0), seed=7, dynamics=mlp)
+        cmf.engine.set_stream(stream.cuda_stream)
+        for i in range(3):
+            cmf.engine.step_async(x0, None, 7, i)
+        torch.cuda.synchronize()
+        with torch.cuda.stream(stream):
+            a.record(stream)
+            for i in range(10):
+                cmf.engine.step_async(x0, None, 7, 10 + i)
+            b.record(stream)
+        torch.cuda.synchronize()
+        ms_f = a.elapsed_time(b) / 10
+        extras["mlp_K75776_H30"] = {"ms_per_tick": ms_f, "sample_steps_per_sec": K_full * 30 / (ms_f * 1e-3),
+                                    "executed_gemm_TFLOPs": K_full * 30 * 2 * 512 * 512 / (ms_f * 1e-3) / 1e12,
+                                    "frac_of_tensor_peak_executed": K_full * 30 * 2 * 512 * 512 / (ms_f * 1e-3) / 1e12 / pk.get("bf16_tflops", 1590.0)}
+        cmf.engine.close()
         # the trained models' shape -- 5 inputs [x, y, yaw, v, w] + StandardScaler statistics
         mlp5 = dict(mlp)
         mlp5["W0"] = (rngw.uniform(-1, 1, (512, 5)) / np.sqrt(5)).astype(np.float32)

@@ -69,15 +69,6 @@ constexpr int TMEM_D_COL = 256;           // two accumulator buffers of 128 FP32
 constexpr int N_GROUPS = 4;                // compute-warp groups: group g owns accumulator quarter g (128 columns)
 constexpr int N_COMPUTE = 128 * N_GROUPS;  // 16 compute warps: 4 per TMEM lane quarter
 constexpr int MLP_THREADS = 64 + N_COMPUTE;
-// ping-pong schedule, A/B variants: register-tiled layer 1 / epilogue (16x256b tensor-memory shapes, four rows per thread, a
-// quarter of the weight loads) instead of one row per thread (32x32b shapes)
-#ifndef MPPI_MLP_RT_L1
-#define MPPI_MLP_RT_L1 0
-#endif
-#ifndef MPPI_MLP_RT_EP
-#define MPPI_MLP_RT_EP 0
-#endif
-
 
 struct MlpSmem {                          // after the 1024-aligned A / B regions
     float4 w01[HID];                      // (W01[j][0], W01[j][1], W01[j][2], b01[j])
@@ -173,21 +164,6 @@ __device__ __forceinline__ void umma_bf16_ss(uint32_t d_tmem, uint64_t a_desc, u
 __device__ __forceinline__ void tmem_st4(uint32_t taddr, uint32_t r0, uint32_t r1, uint32_t r2, uint32_t r3) {
     asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(r0), "r"(r1), "r"(r2), "r"(r3) : "memory");
 }
-// 16 lanes x 256-bit shapes: thread t of the warp holds rows t/4 and t/4 + 8 of the 16-lane slab the address names and the
-// 32-bit columns 8c + 2(t%4) + {0, 1} of every 8-column block c (register 4c + 2i + e: row t/4 + 8i, column 8c + 2(t%4) + e) --
-// the layout of an mma C fragment.  Several rows per thread = the per-column weights are loaded once for four rows.
-__device__ __forceinline__ void tmem_st_16x256b_x2(uint32_t taddr, const uint32_t (&r)[8]) {
-    asm volatile("tcgen05.st.sync.aligned.16x256b.x2.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
-                 ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
-}
-__device__ __forceinline__ void tmem_ld_16x256b_x4(uint32_t taddr, uint32_t (&r)[16]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.16x256b.x4.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-        : "r"(taddr));
-}
 __device__ __forceinline__ void umma_commit(unsigned long long *bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -241,7 +217,8 @@ template <int NIN, bool PP, int NG>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(MLP_THREADS, 1)
 mppi_mlp_rollout_kernel(const __grid_constant__ TickArgs a, const __grid_constant__ CUtensorMap w2_map,
                         const float4 *__restrict__ g_w01, const float2 *__restrict__ g_w01u, const float4 *__restrict__ g_w3,
-                        const float *__restrict__ g_b3, const float *__restrict__ g_bh, float *__restrict__ S_out, int n_tiles) {
+                        const float *__restrict__ g_b3, const float *__restrict__ g_bh, float *__restrict__ S_out, int n_tiles,
+                        float *__restrict__ hand, unsigned int *__restrict__ hand_flag, unsigned int epoch, int balanced) {
     static_assert(NG == 1 || (NG == 2 && !PP), "two GEMMs per step run the one-tile schedule");
     // 1024-byte alignment is what SWIZZLE_128B needs; keeping every pointer derived from this symbol (no
     // integer round-trips) lets the compiler emit LDS/STS instead of generic LD/ST
@@ -260,6 +237,21 @@ mppi_mlp_rollout_kernel(const __grid_constant__ TickArgs a, const __grid_constan
     const int my_tiles = (n_pairs - cluster_id + n_clusters - 1) / n_clusters;
     // ping-pong mode walks the CTA's tiles two at a time (an odd count is padded with an empty tile)
     const int my_slots = PP ? 2 * ((my_tiles + 1) / 2) : my_tiles;
+    // BALANCED ping-pong schedule.  A cluster's unit of work is a quad (2 CTAs x 2 tiles) x one timestep; n_quads * T of
+    // them rarely divide by the cluster count (K = 65 536: 128 quads over 74 clusters -- whole quads leave 13.5 % of the
+    // SM-time idle).  Cluster c takes the contiguous range [bal_b0, bal_b1) of the quad-major step sequence, cut at even
+    // timesteps: the TAIL of one quad (steps t0..T-1), whole quads, and the HEAD of another (steps 0..t1-1).  It runs the
+    // head FIRST and publishes the 128 x 6-float state record per tile (x, y, yaw, cost so far, previous control) with a
+    // release flag; the next cluster runs that quad's tail LAST, so the record is ready long before it is needed.
+    const int n_quads = (n_tiles + 3) / 4;
+    auto bal_cut = [&](int c) {
+        if (c >= n_clusters) return n_quads * T;
+        const long long raw = (long long)c * n_quads * T / n_clusters;
+        const int g = (int)(raw / T), t = (int)(raw % T) & ~1;
+        return g * T + t;
+    };
+    const int bal_b0 = balanced ? bal_cut(cluster_id) : 0, bal_b1 = balanced ? bal_cut(cluster_id + 1) : 0;
+    const int my_tile_steps = (PP && balanced) ? 2 * (bal_b1 - bal_b0) : my_slots * T;    // GEMMs this CTA issues
 
     // ---- one-time setup: constants, barriers, TMEM, step-1 index + window (same rule as the tick kernel)
     for (int j = tid; j < HID; j += MLP_THREADS) {
@@ -356,7 +348,7 @@ mppi_mlp_rollout_kernel(const __grid_constant__ TickArgs a, const __grid_constan
             }
         } else {
         constexpr int STAGES_PER_Q = HID / KCH / KCH_PER_STAGE;       // 2 stage loads (64 KB each) per accumulator quarter
-        const int total = my_slots * T * N_QUARTERS * STAGES_PER_Q;
+        const int total = my_tile_steps * N_QUARTERS * STAGES_PER_Q;
         int stage = 0; uint32_t phase = 0;
         for (int it = 0; it < total; ++it) {
             const int kb2 = it % STAGES_PER_Q, nq = (it / STAGES_PER_Q) % N_QUARTERS;
@@ -414,7 +406,7 @@ mppi_mlp_rollout_kernel(const __grid_constant__ TickArgs a, const __grid_constan
                 a_phase ^= 1;
             }
         } else
-        for (int step = 0; step < my_slots * T; ++step) {
+        for (int step = 0; step < my_tile_steps; ++step) {
             for (int nq = 0; nq < N_QUARTERS; ++nq, ++quarter) {
                 const uint32_t buf = quarter & 1;
                 mbar_wait(&ms.d_empty[buf], ((quarter >> 1) & 1) ^ 1);      // epilogue drained this buffer
@@ -465,16 +457,47 @@ mppi_mlp_rollout_kernel(const __grid_constant__ TickArgs a, const __grid_constan
         const bool owner = grp < 2;
         uint32_t d_phase[2] = {0, 0};
         uint32_t l1_count = 0;
-        for (int pr = 0; pr < my_slots / 2; ++pr) {
-            const int tl = 2 * pr + (grp & 1);
-            const int tile = 2 * (cluster_id + tl * n_clusters) + (int)cta_rank;
+        // segments of this CTA: static = tile pairs over the whole horizon; balanced = [head], whole quads, [tail]
+        const int g_first = balanced ? bal_b0 / T : 0;
+        const int n_nat = balanced ? (bal_b1 > bal_b0 ? (bal_b1 - 1) / T - g_first + 1 : 0) : my_slots / 2;
+        const bool head_first = balanced && n_nat > 1 && (bal_b1 % T) != 0;
+        for (int pr = 0; pr < n_nat; ++pr) {
+            int tile, t0 = 0, t1 = T;
+            bool valid = true;
+            if (balanced) {
+                // natural order j = 0 (maybe a tail) .. n_nat-1 (maybe a head); run order: the head, the middle ones, j = 0 last
+                const int j = pr == n_nat - 1 ? 0 : head_first ? (pr == 0 ? n_nat - 1 : pr) : pr + 1;
+                const int g = g_first + j;
+                t0 = max(bal_b0 - g * T, 0); t1 = min(bal_b1 - g * T, T);
+                tile = 4 * g + 2 * (grp & 1) + (int)cta_rank;
+            } else {
+                const int tl = 2 * pr + (grp & 1);
+                tile = 2 * (cluster_id + tl * n_clusters) + (int)cta_rank;
+                valid = tl < my_tiles;
+            }
             const int k = tile * TILE_M + row;
-            const bool active = owner && tl < my_tiles && k < a.K;
+            const bool active = owner && valid && k < a.K;
             const uint32_t kg = (uint32_t)(a.k_offset + k);
             const bool exploit = (int)kg < a.n_exploit;
             float z[4] = {sm.x0[0], sm.x0[1], sm.x0[2], 0.f};
             float acc = 0.f, e[4] = {0.f, 0.f, 0.f, 0.f}, sn = 0.f, cs = 1.f;
             float vp0 = 0.f, vp1 = 0.f, vc0 = 0.f, vc1 = 0.f;          // controls of steps t-1 and t
+            // hand-off records live at [consumer cluster][rank][slot][6][128]; the producer is cluster_id - 1
+            if (t0 > 0 && owner) {
+                const unsigned int *fl = hand_flag + 2 * cluster_id + cta_rank;
+                if (lane == 0) {
+                    unsigned int seen;
+                    long long spins = 0;
+                    do {
+                        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(fl) : "memory");
+                        if (seen != epoch) __nanosleep(200);
+                    } while (seen != epoch && ++spins < 20000000ll);       // ~4 s guard: never hang the device
+                }
+                __syncwarp();
+                const float *rec = hand + ((size_t)((cluster_id * 2 + (int)cta_rank) * 2 + (grp & 1)) * 6) * TILE_M + row;
+                z[0] = __ldcg(rec); z[1] = __ldcg(rec + TILE_M); z[2] = __ldcg(rec + 2 * TILE_M);
+                acc = __ldcg(rec + 3 * TILE_M); vp0 = __ldcg(rec + 4 * TILE_M); vp1 = __ldcg(rec + 5 * TILE_M);
+            }
             float4 ref = make_float4(0.f, 0.f, 0.f, 0.f);
             const float2 *eps_k = a.eps ? reinterpret_cast<const float2 *>(a.eps) + (size_t)(active ? k : 0) * T : nullptr;
             // owner: stage cost of the state reached by step t-1, noise + clamped control of step t, heading sin/cos
@@ -499,53 +522,6 @@ mppi_mlp_rollout_kernel(const __grid_constant__ TickArgs a, const __grid_constan
                     if (NIN == 5) ms.xw[row] = vc1;
                 }
                 named_bar_sync(1, N_COMPUTE);
-#if MPPI_MLP_RT_L1
-                // four rows per thread: rows q*32 + 8r + lane/4 (r = 2h + i: 16-lane slab h, register pair i); per 128-column
-                // part this group's 32 hidden units are 16 packed columns = one 16x256b.x2 store per slab; the thread
-                // evaluates units 16c + 4(lane%4) + 0..3 of them
-                float4 st4[4]; float su4[4];
-#pragma unroll
-                for (int r = 0; r < 4; ++r) {
-                    st4[r] = ms.xs[q * 32 + 8 * r + (lane >> 2)];
-                    su4[r] = NIN == 5 ? ms.xw[q * 32 + 8 * r + (lane >> 2)] : 0.f;
-                }
-#pragma unroll 1
-                for (int part = 0; part < N_QUARTERS; ++part) {
-                    if (l1_count > 0) {
-                        mbar_wait_warp(&ms.a_free[part], (l1_count - 1) & 1);
-                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    }
-                    uint32_t pk[2][8];                                // [slab h][4c + 2i + e]
-#pragma unroll
-                    for (int c = 0; c < 2; ++c) {
-                        const int col = part * N_MMA + grp * 32 + 16 * c + 4 * (lane & 3);
-#pragma unroll
-                        for (int e = 0; e < 2; ++e) {
-                            const float4 wa = ms.w01[col + 2 * e], wb = ms.w01[col + 2 * e + 1];
-                            float4 wu = make_float4(0.f, 0.f, 0.f, 0.f);
-                            if (NIN == 5) wu = *reinterpret_cast<const float4 *>(&ms.w01u[col + 2 * e]);
-#pragma unroll
-                            for (int r = 0; r < 4; ++r) {
-                                float pa = fmaf(wa.x, st4[r].x, fmaf(wa.y, st4[r].y, fmaf(wa.z, st4[r].z, wa.w)));
-                                float pb = fmaf(wb.x, st4[r].x, fmaf(wb.y, st4[r].y, fmaf(wb.z, st4[r].z, wb.w)));
-                                if (NIN == 5) {
-                                    pa = fmaf(wu.x, st4[r].w, fmaf(wu.y, su4[r], pa));
-                                    pb = fmaf(wu.z, st4[r].w, fmaf(wu.w, su4[r], pb));
-                                }
-                                pk[r >> 1][4 * c + 2 * (r & 1) + e] = tanh_bf16x2(pa, pb);
-                            }
-                        }
-                    }
-#pragma unroll
-                    for (int h = 0; h < 2; ++h)
-                        tmem_st_16x256b_x2(tmem + ((uint32_t)(q * 32 + 16 * h) << 16) + TMEM_A_COL + (uint32_t)((part * N_MMA + grp * 32) >> 1), pk[h]);
-                    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                    mbar_arrive(&ms.a_ready[part]);
-                }
-                ++l1_count;
-                return;
-#endif
                 const float4 st = ms.xs[row];
                 const float su1 = NIN == 5 ? ms.xw[row] : 0.f;
 #pragma unroll 1
@@ -579,66 +555,7 @@ mppi_mlp_rollout_kernel(const __grid_constant__ TickArgs a, const __grid_constan
                 ++l1_count;
             };
             // one accumulator quarter: D -> +b2 -> tanh -> partial contraction with the 512x3 output layer
-#if MPPI_MLP_RT_EP
-            // register-tiled epilogue: the thread holds rows 8r + lane/4 (r = 0..3) of its lane quarter and, of every 8-column
-            // block, columns 2(lane%4) + {0, 1}; part_sum[r][0..2] are its partial output-layer sums for those rows
-            float part_sum[4][3];
-            auto zero_rt = [&]() {
-#pragma unroll
-                for (int r = 0; r < 4; ++r) part_sum[r][0] = part_sum[r][1] = part_sum[r][2] = 0.f;
-            };
-            // sums over the four lanes of a quad; then row `lane` of the lane quarter lands in lane `lane`: quad r_lo = lane/4
-            // holds rows r_lo + 8r, lane 4 r_lo + cq offers row r_lo + 8 cq, lane L reads from lane 4 (L % 8) + L / 8
-            auto gather_rt = [&](float &r0, float &r1, float &r2) {
-                float o[3];
-#pragma unroll
-                for (int c = 0; c < 3; ++c) {
-                    float s4[4];
-#pragma unroll
-                    for (int r = 0; r < 4; ++r) {
-                        float t = part_sum[r][c];
-                        t += __shfl_xor_sync(0xffffffffu, t, 1);
-                        t += __shfl_xor_sync(0xffffffffu, t, 2);
-                        s4[r] = t;
-                    }
-                    const int cq = lane & 3;
-                    const float mine = cq == 0 ? s4[0] : cq == 1 ? s4[1] : cq == 2 ? s4[2] : s4[3];
-                    o[c] = __shfl_sync(0xffffffffu, mine, 4 * (lane & 7) + (lane >> 3));
-                }
-                r0 = o[0]; r1 = o[1]; r2 = o[2];
-            };
-#endif
             auto epilogue = [&](int nq, float &r0, float &r1, float &r2) {
-#if MPPI_MLP_RT_EP
-                {
-                    const int buf = nq & 1;
-                    mbar_wait_warp(&ms.d_full[buf], d_phase[buf]); d_phase[buf] ^= 1;
-                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    uint32_t v[2][16];
-#pragma unroll
-                    for (int h = 0; h < 2; ++h)
-                        tmem_ld_16x256b_x4(tmem + ((uint32_t)(q * 32 + 16 * h) << 16) + (uint32_t)(TMEM_D_COL + buf * N_MMA + grp * 32), v[h]);
-                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                    mbar_arrive(&ms.d_empty[buf]);
-#pragma unroll
-                    for (int c = 0; c < 4; ++c) {
-#pragma unroll
-                        for (int e = 0; e < 2; ++e) {
-                            const float4 w = ms.w3[nq * N_MMA + grp * 32 + 8 * c + 2 * (lane & 3) + e];
-#pragma unroll
-                            for (int r = 0; r < 4; ++r) {
-                                const float hv = tanh_approx(__uint_as_float(v[r >> 1][4 * c + 2 * (r & 1) + e]) + w.x);
-                                part_sum[r][0] = fmaf(w.y, hv, part_sum[r][0]);
-                                part_sum[r][1] = fmaf(w.z, hv, part_sum[r][1]);
-                                part_sum[r][2] = fmaf(w.w, hv, part_sum[r][2]);
-                            }
-                        }
-                    }
-                    if (nq == N_QUARTERS - 1) gather_rt(r0, r1, r2);      // the step's last quarter: per-row sums to their lanes
-                    return;
-                }
-#endif
                 const int col = nq * N_MMA + grp * 32;
                 const int buf = nq & 1;
                 mbar_wait_warp(&ms.d_full[buf], d_phase[buf]); d_phase[buf] ^= 1;
@@ -661,9 +578,17 @@ mppi_mlp_rollout_kernel(const __grid_constant__ TickArgs a, const __grid_constan
                 if (rel) { ms.res[rel - 1][0][row] = r0; ms.res[rel - 1][1][row] = r1; ms.res[rel - 1][2][row] = r2; }
                 named_bar_sync(1, N_COMPUTE);
                 if (grp == og) {
+                    // partial sums added in ascending GROUP order whichever group owns the tile, so a sample's result does not
+                    // depend on the slot (X / Y) the schedule puts it in: the static and the balanced walk agree bit for bit
+                    float t0s = 0.f, t1s = 0.f, t2s = 0.f;
 #pragma unroll
-                    for (int g = 0; g < N_GROUPS - 1; ++g) { r0 += ms.res[g][0][row]; r1 += ms.res[g][1][row]; r2 += ms.res[g][2][row]; }
-                    r0 += ms.b3[0]; r1 += ms.b3[1]; r2 += ms.b3[2];
+                    for (int g = 0; g < N_GROUPS; ++g) {
+                        const int rel = (g - og) & 3;
+                        const float p0 = rel ? ms.res[rel - 1][0][row] : r0, p1 = rel ? ms.res[rel - 1][1][row] : r1,
+                                    p2 = rel ? ms.res[rel - 1][2][row] : r2;
+                        t0s = g ? t0s + p0 : p0; t1s = g ? t1s + p1 : p1; t2s = g ? t2s + p2 : p2;
+                    }
+                    r0 = t0s + ms.b3[0]; r1 = t1s + ms.b3[1]; r2 = t2s + ms.b3[2];
                     z[0] = fmaf(fmaf(vc0, cs, r0), a.dt, z[0]);
                     z[1] = fmaf(fmaf(vc0, sn, r1), a.dt, z[1]);
                     z[2] = fmaf(vc1 + r2, a.dt, z[2]);
@@ -671,37 +596,42 @@ mppi_mlp_rollout_kernel(const __grid_constant__ TickArgs a, const __grid_constan
                 }
             };
 
-            if (owner) prep(0);
-            layer1(0);                                               // L1(X, 0)
+            if (owner) prep(t0);
+            layer1(0);                                               // L1(X, t0)
             float r0, r1, r2;
             float s0 = 0.f, s1 = 0.f, s2 = 0.f;                      // partial sums of the tile whose GEMM ran one slot ago
-            for (int t = 0; t < T; ++t) {
+            for (int t = t0; t < t1; ++t) {
                 // ---- slot X(t): the tensor core runs GEMM X(t)
-                if (t > 0) {
+                if (t > t0) {
                     epilogue(3, s0, s1, s2);                         // Y(t-1), last quarter
                     finish(1, s0, s1, s2);
                     if (grp == 1) prep(t);
                 }
                 r0 = r1 = r2 = 0.f;
-#if MPPI_MLP_RT_EP
-                zero_rt();
-#endif
                 epilogue(0, r0, r1, r2); epilogue(1, r0, r1, r2); epilogue(2, r0, r1, r2);      // X(t)
                 layer1(1);                                           // L1(Y, t) chases X(t)'s last quarter
                 // ---- slot Y(t): the tensor core runs GEMM Y(t)
                 epilogue(3, r0, r1, r2);                             // X(t), last quarter
                 finish(0, r0, r1, r2);
-                if (grp == 0 && t + 1 < T) prep(t + 1);
+                if (grp == 0 && t + 1 < t1) prep(t + 1);
                 s0 = s1 = s2 = 0.f;
-#if MPPI_MLP_RT_EP
-                zero_rt();
-#endif
                 epilogue(0, s0, s1, s2); epilogue(1, s0, s1, s2); epilogue(2, s0, s1, s2);      // Y(t)
-                if (t + 1 < T) layer1(0);                            // L1(X, t+1) chases Y(t)'s last quarter
+                if (t + 1 < t1) layer1(0);                           // L1(X, t+1) chases Y(t)'s last quarter
             }
-            epilogue(3, s0, s1, s2);                                 // Y(T-1), last quarter
+            epilogue(3, s0, s1, s2);                                 // Y(t1-1), last quarter
             finish(1, s0, s1, s2);
-            if (active) {
+            if (t1 < T) {
+                // head of a split quad: publish the state after step t1-1 for the next cluster's tail
+                if (owner) {
+                    float *rec = hand + ((size_t)(((cluster_id + 1) * 2 + (int)cta_rank) * 2 + (grp & 1)) * 6) * TILE_M + row;
+                    __stcg(rec, z[0]); __stcg(rec + TILE_M, z[1]); __stcg(rec + 2 * TILE_M, z[2]);
+                    __stcg(rec + 3 * TILE_M, acc); __stcg(rec + 4 * TILE_M, vp0); __stcg(rec + 5 * TILE_M, vp1);
+                    __threadfence();
+                    named_bar_sync(2, 256);                          // the two owner groups (8 warps)
+                    if (cw == 0 && lane == 0)
+                        asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(hand_flag + 2 * (cluster_id + 1) + cta_rank), "r"(epoch) : "memory");
+                }
+            } else if (active) {
                 const int j = a.window == 20 ? nearest_wp<20>(sm, z[0], z[1]) : nearest_wp<0>(sm, z[0], z[1]);
                 ref = window_ref(sm, j);
                 const float2 qq = sm.Q[T - 1];
@@ -883,6 +813,9 @@ struct MlpState {
     float2 *d_w01u = nullptr;             // control columns of the folded first layer (n_in = 5)
     float *d_b3 = nullptr;
     float *d_bh = nullptr;                // n_hidden = 3: bias of the layer the first GEMM evaluates
+    float *d_hand = nullptr;              // balanced schedule: state records of split quads [cluster][rank][slot][6][128]
+    unsigned int *d_hand_flag = nullptr;  // [cluster][rank]: epoch of the launch that published the record
+    unsigned int epoch = 0;
     int n_in = 3, n_gemm = 1;
     CUtensorMap w2_map;
     bool ready = false;
@@ -897,6 +830,9 @@ MlpState *mlp_create(int K, int T) {
     cudaDeviceGetAttribute(&m->n_sm, cudaDevAttrMultiProcessorCount, dev);
     if (cudaMalloc(&m->d_w2, sizeof(__nv_bfloat16) * 2 * HID * HID) != cudaSuccess ||
         cudaMalloc(&m->d_bh, sizeof(float) * HID) != cudaSuccess ||
+        cudaMalloc(&m->d_hand, sizeof(float) * (size_t)(m->n_sm / 2 + 1) * 2 * 2 * 6 * TILE_M) != cudaSuccess ||
+        cudaMalloc(&m->d_hand_flag, sizeof(unsigned int) * (size_t)(m->n_sm / 2 + 1) * 2) != cudaSuccess ||
+        cudaMemset(m->d_hand_flag, 0, sizeof(unsigned int) * (size_t)(m->n_sm / 2 + 1) * 2) != cudaSuccess ||
         cudaMalloc(&m->d_w01, sizeof(float4) * HID) != cudaSuccess ||
         cudaMalloc(&m->d_w3, sizeof(float4) * HID) != cudaSuccess ||
         cudaMalloc(&m->d_w01u, sizeof(float2) * HID) != cudaSuccess ||
@@ -914,7 +850,7 @@ MlpState *mlp_create(int K, int T) {
 
 void mlp_destroy(MlpState *m) {
     if (!m) return;
-    cudaFree(m->d_w2); cudaFree(m->d_bh); cudaFree(m->d_w01); cudaFree(m->d_w01u); cudaFree(m->d_w3); cudaFree(m->d_b3);
+    cudaFree(m->d_w2); cudaFree(m->d_bh); cudaFree(m->d_hand); cudaFree(m->d_hand_flag); cudaFree(m->d_w01); cudaFree(m->d_w01u); cudaFree(m->d_w3); cudaFree(m->d_b3);
     delete m;
 }
 
@@ -997,7 +933,15 @@ int mlp_rollout_costs(MlpState *m, const TickArgs &args, bool sum, const float *
     // one-tile schedule (A/B measurements)
     static const bool allow_pp = [] { const char *e = std::getenv("MPPI_MLP_PINGPONG"); return !(e && e[0] == '0'); }();
     const bool pp = allow_pp && n_tiles > grid && m->n_gemm == 1;
-#define MPPI_MLP_LAUNCH(N, P, G) mppi_mlp_rollout_kernel<N, P, G><<<grid, MLP_THREADS, MLP_DYN_SMEM, st>>>(a, m->w2_map, m->d_w01, m->d_w01u, m->d_w3, m->d_b3, m->d_bh, d_S, n_tiles)
+    // balanced (horizon-split) walk when whole quads do not divide over the clusters and every cluster still gets more
+    // than one horizon of steps; MPPI_MLP_BALANCED=0 forces whole quads (A/B measurements)
+    const char *bal_env = std::getenv("MPPI_MLP_BALANCED");               // read per launch: tests flip it in-process
+    const bool allow_bal = !(bal_env && bal_env[0] == '0');
+    const int n_quads = (n_tiles + 3) / 4, n_clusters = grid / 2;
+    const int balanced = (pp && allow_bal && n_clusters > 0 && (n_quads % n_clusters) != 0 &&
+                          (long long)n_quads * a.T / n_clusters >= a.T + 2) ? 1 : 0;
+    const unsigned int epoch = ++m->epoch;
+#define MPPI_MLP_LAUNCH(N, P, G) mppi_mlp_rollout_kernel<N, P, G><<<grid, MLP_THREADS, MLP_DYN_SMEM, st>>>(a, m->w2_map, m->d_w01, m->d_w01u, m->d_w3, m->d_b3, m->d_bh, d_S, n_tiles, m->d_hand, m->d_hand_flag, epoch, balanced)
     if (m->n_gemm == 2) { if (m->n_in == 5) MPPI_MLP_LAUNCH(5, false, 2); else MPPI_MLP_LAUNCH(3, false, 2); }
     else if (m->n_in == 5) { if (pp) MPPI_MLP_LAUNCH(5, true, 1); else MPPI_MLP_LAUNCH(5, false, 1); }
     else { if (pp) MPPI_MLP_LAUNCH(3, true, 1); else MPPI_MLP_LAUNCH(3, false, 1); }

@@ -256,3 +256,40 @@ def test_mlp_three_hidden_layers_drop_in_state_dict_and_switching_models():
         assert np.max(np.abs(u - o["U_after"])) <= MLP_U_ATOL, (tick, np.max(np.abs(u - o["U_after"])))
         assert ctrl.prev_way_point_idx == o["idx_after"]
         U, idx = u.copy(), o["idx_after"]
+
+
+@pytest.mark.parametrize("K,T,n_in", [(50000, 12, 3), (50000, 11, 5), (65536, 10, 3)])
+def test_mlp_balanced_horizon_split_matches_fp64_oracle_and_static_schedule(K, T, n_in, monkeypatch):
+    """Ping-pong schedule with the horizon of some quads split between neighbouring clusters (state handed over through
+    global memory, cut at even timesteps): same costs as the FP64 oracle, and as the whole-quad schedule bit for bit --
+    the split changes who computes a step, not the arithmetic."""
+    g = Golden("diffdrive_pe0.05")
+    mlp = orc.make_mlp(seed=2, out_scale=0.01) if n_in == 3 else _mlp5(seed=2)
+    sp = _spec(K, T, "sum", mlp)
+    eng = engine_from_spec(sp, g.path)
+    sc = [mlp[k] for k in ("in_mean", "in_scale", "out_mean", "out_scale")] if n_in == 5 else []
+    eng.set_mlp([mlp["W%d" % i] for i in range(4)], [mlp["b%d" % i] for i in range(4)], *sc)
+    eps = torch.zeros(K, T, 2, dtype=torch.float32, device="cuda")
+    eng.generate_noise(eps, seed=9, tick=2)
+    S = torch.zeros(K, dtype=torch.float32, device="cuda")
+    x0 = np.array([0.4, 0.3, 0.5])
+    U = np.random.default_rng(5).normal(0, 0.5, (T, 2)).astype(np.float32)
+    out = {}
+    for src in ("philox", "injected", "philox"):          # the third launch re-uses the hand-off flags with a new epoch
+        S.zero_()
+        eng.set_nominal(U)
+        eng.set_waypoint_idx(0)
+        eng.rollout_costs(x0, S, eps if src == "injected" else None, seed=9, tick=2)
+        out[src] = S.cpu().numpy().astype(np.float64)
+    So, _, _ = orc.costs_vec(sp, g.path, U.astype(np.float64), 0, x0, eps.cpu().numpy().astype(np.float64))
+    for src, Sg in out.items():
+        rel = np.abs(Sg - So) / np.maximum(np.abs(So), 1e-9)
+        assert np.quantile(rel, 0.99) <= MLP_COST_RTOL and rel.max() <= 2e-2, (K, T, src, np.quantile(rel, 0.99), rel.max())
+    # whole-quad schedule (MPPI_MLP_BALANCED=0, read by the library at every launch): identical costs
+    monkeypatch.setenv("MPPI_MLP_BALANCED", "0")
+    S.zero_()
+    eng.set_nominal(U)
+    eng.set_waypoint_idx(0)
+    eng.rollout_costs(x0, S, None, seed=9, tick=2)
+    assert np.array_equal(S.cpu().numpy().astype(np.float64), out["philox"])
+    eng.close()

@@ -243,7 +243,8 @@ mppi_mlp_rollout_kernel(const __grid_constant__ TickArgs a, const __grid_constan
     // timesteps: the TAIL of one quad (steps t0..T-1), whole quads, and the HEAD of another (steps 0..t1-1).  It runs the
     // head FIRST and publishes the 128 x 6-float state record per tile (x, y, yaw, cost so far, previous control) with a
     // release flag; the next cluster runs that quad's tail LAST, so the record is ready long before it is needed.
-    const int n_quads = (n_tiles + 3) / 4;
+    // (one-tile schedule, NG = 2: the unit is a PAIR -- 2 CTAs x 1 tile -- x one timestep, same rule)
+    const int n_quads = PP ? (n_tiles + 3) / 4 : (n_tiles + 1) / 2;
     auto bal_cut = [&](int c) {
         if (c >= n_clusters) return n_quads * T;
         const long long raw = (long long)c * n_quads * T / n_clusters;
@@ -251,7 +252,7 @@ mppi_mlp_rollout_kernel(const __grid_constant__ TickArgs a, const __grid_constan
         return g * T + t;
     };
     const int bal_b0 = balanced ? bal_cut(cluster_id) : 0, bal_b1 = balanced ? bal_cut(cluster_id + 1) : 0;
-    const int my_tile_steps = (PP && balanced) ? 2 * (bal_b1 - bal_b0) : my_slots * T;    // GEMMs this CTA issues
+    const int my_tile_steps = balanced ? (PP ? 2 : 1) * (bal_b1 - bal_b0) : my_slots * T;    // tile-steps of this CTA
 
     // ---- one-time setup: constants, barriers, TMEM, step-1 index + window (same rule as the tick kernel)
     for (int j = tid; j < HID; j += MLP_THREADS) {
@@ -333,7 +334,7 @@ mppi_mlp_rollout_kernel(const __grid_constant__ TickArgs a, const __grid_constan
         if constexpr (NG == 2) {
             // two layers' weights back to back: per step 2 GEMMs x 4 quarters x 8 K-chunks, one 16 KB box per stage;
             // the tensor map stacks the layers, rows [512 g, 512 g + 512)
-            const int total = my_tiles * T * NG * N_QUARTERS * (HID / KCH);
+            const int total = my_tile_steps * NG * N_QUARTERS * (HID / KCH);
             int stage = 0; uint32_t phase = 0;
             for (int it = 0; it < total; ++it) {
                 const int kc = it % (HID / KCH), nq = (it / (HID / KCH)) % N_QUARTERS, g = (it / (HID / KCH * N_QUARTERS)) % NG;
@@ -371,7 +372,7 @@ mppi_mlp_rollout_kernel(const __grid_constant__ TickArgs a, const __grid_constan
         const bool leader = elect_one_sync();
         int stage = 0; uint32_t phase = 0, a_phase = 0, quarter = 0;
         if constexpr (NG == 2) {
-            for (int step = 0; step < my_tiles * T; ++step) {
+            for (int step = 0; step < my_tile_steps; ++step) {
                 for (int g = 0; g < NG; ++g) {
                     for (int nq = 0; nq < N_QUARTERS; ++nq, ++quarter) {
                         const uint32_t buf = quarter & 1;
@@ -647,8 +648,20 @@ mppi_mlp_rollout_kernel(const __grid_constant__ TickArgs a, const __grid_constan
         const int row = q * 32 + lane;
         const bool owner = grp == 0;
         uint32_t d_phase[2] = {0, 0};
-        for (int tl = 0; tl < my_tiles; ++tl) {
-            const int tile = 2 * (cluster_id + tl * n_clusters) + (int)cta_rank;
+        // segments: static = this CTA's tiles over the whole horizon; balanced = [head], whole pairs, [tail] (see above)
+        const int g_first = balanced ? bal_b0 / T : 0;
+        const int n_nat = balanced ? (bal_b1 > bal_b0 ? (bal_b1 - 1) / T - g_first + 1 : 0) : my_tiles;
+        const bool head_first = balanced && n_nat > 1 && (bal_b1 % T) != 0;
+        for (int tl = 0; tl < n_nat; ++tl) {
+            int tile, t0 = 0, t1 = T;
+            if (balanced) {
+                const int j = tl == n_nat - 1 ? 0 : head_first ? (tl == 0 ? n_nat - 1 : tl) : tl + 1;
+                const int g = g_first + j;
+                t0 = max(bal_b0 - g * T, 0); t1 = min(bal_b1 - g * T, T);
+                tile = 2 * g + (int)cta_rank;
+            } else {
+                tile = 2 * (cluster_id + tl * n_clusters) + (int)cta_rank;
+            }
             const int k = tile * TILE_M + row;
             const bool active = k < a.K;
             const uint32_t kg = (uint32_t)(a.k_offset + k);
@@ -656,6 +669,21 @@ mppi_mlp_rollout_kernel(const __grid_constant__ TickArgs a, const __grid_constan
             float z[4] = {sm.x0[0], sm.x0[1], sm.x0[2], 0.f};
             float acc = 0.f, e[4] = {0.f, 0.f, 0.f, 0.f}, sn = 0.f, cs = 1.f;
             float vp0 = 0.f, vp1 = 0.f, vc0 = 0.f, vc1 = 0.f, vn0 = 0.f, vn1 = 0.f;    // controls of steps t-1, t, t+1
+            if (t0 > 0 && owner) {                               // tail of a split pair: the previous cluster's record
+                const unsigned int *fl = hand_flag + 2 * cluster_id + cta_rank;
+                if (lane == 0) {
+                    unsigned int seen;
+                    long long spins = 0;
+                    do {
+                        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(fl) : "memory");
+                        if (seen != epoch) __nanosleep(200);
+                    } while (seen != epoch && ++spins < 20000000ll);
+                }
+                __syncwarp();
+                const float *rec = hand + ((size_t)((cluster_id * 2 + (int)cta_rank) * 2) * 6) * TILE_M + row;
+                z[0] = __ldcg(rec); z[1] = __ldcg(rec + TILE_M); z[2] = __ldcg(rec + 2 * TILE_M);
+                acc = __ldcg(rec + 3 * TILE_M); vp0 = __ldcg(rec + 4 * TILE_M); vp1 = __ldcg(rec + 5 * TILE_M);
+            }
             float4 ref = make_float4(0.f, 0.f, 0.f, 0.f);
             const float2 *eps_k = a.eps ? reinterpret_cast<const float2 *>(a.eps) + (size_t)(active ? k : 0) * T : nullptr;
             // noise + clamped control of step t (A3-A5); called for t = 0, 1, 2, ... in order (a Philox call yields two steps)
@@ -666,8 +694,8 @@ mppi_mlp_rollout_kernel(const __grid_constant__ TickArgs a, const __grid_constan
                 o0 = clampf(exploit ? __fadd_rn(u.x, e[2 * (t & 1)]) : e[2 * (t & 1)], a.umax0);
                 o1 = clampf(exploit ? __fadd_rn(u.y, e[2 * (t & 1) + 1]) : e[2 * (t & 1) + 1], a.umax1);
             };
-            if (owner) control(0, vc0, vc1);
-            for (int t = 0; t < T; ++t) {
+            if (owner) control(t0, vc0, vc1);
+            for (int t = t0; t < t1; ++t) {
                 // (1) owner publishes the state (and, for the 5-input residual, this step's control); every group
                 //     evaluates its 128 columns of tanh(W01 [x; u] + b01)
                 if (owner) {
@@ -710,7 +738,7 @@ mppi_mlp_rollout_kernel(const __grid_constant__ TickArgs a, const __grid_constan
                         const float2 qq = sm.Q[t - 1];
                         acc += tracking_cost<MPPI_MODEL_DIFFDRIVE>(ref, z, z[2], a.sw) + (qq.x * vp0 + qq.y * vp1);
                     }
-                    if (t + 1 < T) control(t + 1, vn0, vn1);
+                    if (t + 1 < t1) control(t + 1, vn0, vn1);
                     sincos_cw(z[2], sn, cs);
                 }
                 // (2b) three tanh layers: epilogue of GEMM 1 = the A operand of GEMM 2.  D -> +bias -> tanh -> bf16, stored
@@ -779,7 +807,17 @@ mppi_mlp_rollout_kernel(const __grid_constant__ TickArgs a, const __grid_constan
                     vp0 = vc0; vp1 = vc1; vc0 = vn0; vc1 = vn1;
                 }
             }
-            if (owner && active) {
+            if (t1 < T) {
+                if (owner) {                                      // head of a split pair: hand the state to the next cluster
+                    float *rec = hand + ((size_t)(((cluster_id + 1) * 2 + (int)cta_rank) * 2) * 6) * TILE_M + row;
+                    __stcg(rec, z[0]); __stcg(rec + TILE_M, z[1]); __stcg(rec + 2 * TILE_M, z[2]);
+                    __stcg(rec + 3 * TILE_M, acc); __stcg(rec + 4 * TILE_M, vp0); __stcg(rec + 5 * TILE_M, vp1);
+                    __threadfence();
+                    named_bar_sync(2, 128);                           // the owner group (4 warps)
+                    if (cw == 0 && lane == 0)
+                        asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(hand_flag + 2 * (cluster_id + 1) + cta_rank), "r"(epoch) : "memory");
+                }
+            } else if (owner && active) {
                 // cost of the final state: last stage cost (+ terminal); in `last` mode nothing else survives (Q1)
                 const int j = a.window == 20 ? nearest_wp<20>(sm, z[0], z[1]) : nearest_wp<0>(sm, z[0], z[1]);
                 ref = window_ref(sm, j);
@@ -937,8 +975,9 @@ int mlp_rollout_costs(MlpState *m, const TickArgs &args, bool sum, const float *
     // than one horizon of steps; MPPI_MLP_BALANCED=0 forces whole quads (A/B measurements)
     const char *bal_env = std::getenv("MPPI_MLP_BALANCED");               // read per launch: tests flip it in-process
     const bool allow_bal = !(bal_env && bal_env[0] == '0');
-    const int n_quads = (n_tiles + 3) / 4, n_clusters = grid / 2;
-    const int balanced = (pp && allow_bal && n_clusters > 0 && (n_quads % n_clusters) != 0 &&
+    const bool one_tile_bal = !pp && m->n_gemm == 2 && n_tiles > grid;     // three-layer residuals: pairs x timesteps
+    const int n_quads = pp ? (n_tiles + 3) / 4 : (n_tiles + 1) / 2, n_clusters = grid / 2;
+    const int balanced = ((pp || one_tile_bal) && allow_bal && n_clusters > 0 && (n_quads % n_clusters) != 0 &&
                           (long long)n_quads * a.T / n_clusters >= a.T + 2) ? 1 : 0;
     const unsigned int epoch = ++m->epoch;
 #define MPPI_MLP_LAUNCH(N, P, G) mppi_mlp_rollout_kernel<N, P, G><<<grid, MLP_THREADS, MLP_DYN_SMEM, st>>>(a, m->w2_map, m->d_w01, m->d_w01u, m->d_w3, m->d_b3, m->d_bh, d_S, n_tiles, m->d_hand, m->d_hand_flag, epoch, balanced)

@@ -258,17 +258,21 @@ def test_mlp_three_hidden_layers_drop_in_state_dict_and_switching_models():
         U, idx = u.copy(), o["idx_after"]
 
 
-@pytest.mark.parametrize("K,T,n_in", [(50000, 12, 3), (50000, 11, 5), (65536, 10, 3)])
-def test_mlp_balanced_horizon_split_matches_fp64_oracle_and_static_schedule(K, T, n_in, monkeypatch):
+@pytest.mark.parametrize("K,T,n_in,n_hidden", [(50000, 12, 3, 2), (50000, 11, 5, 2), (65536, 10, 3, 2), (30000, 11, 5, 3),
+                                               (40000, 12, 3, 3)])
+def test_mlp_balanced_horizon_split_matches_fp64_oracle_and_static_schedule(K, T, n_in, n_hidden, monkeypatch):
     """Ping-pong schedule with the horizon of some quads split between neighbouring clusters (state handed over through
     global memory, cut at even timesteps): same costs as the FP64 oracle, and as the whole-quad schedule bit for bit --
     the split changes who computes a step, not the arithmetic."""
     g = Golden("diffdrive_pe0.05")
-    mlp = orc.make_mlp(seed=2, out_scale=0.01) if n_in == 3 else _mlp5(seed=2)
+    if n_hidden == 3:                                      # one-tile schedule, two GEMMs per step: pairs x timesteps
+        mlp = _mlp3l(n_in, seed=2)
+    else:
+        mlp = orc.make_mlp(seed=2, out_scale=0.01) if n_in == 3 else _mlp5(seed=2)
     sp = _spec(K, T, "sum", mlp)
     eng = engine_from_spec(sp, g.path)
     sc = [mlp[k] for k in ("in_mean", "in_scale", "out_mean", "out_scale")] if n_in == 5 else []
-    eng.set_mlp([mlp["W%d" % i] for i in range(4)], [mlp["b%d" % i] for i in range(4)], *sc)
+    eng.set_mlp([mlp["W%d" % i] for i in range(n_hidden + 2)], [mlp["b%d" % i] for i in range(n_hidden + 2)], *sc)
     eps = torch.zeros(K, T, 2, dtype=torch.float32, device="cuda")
     eng.generate_noise(eps, seed=9, tick=2)
     S = torch.zeros(K, dtype=torch.float32, device="cuda")

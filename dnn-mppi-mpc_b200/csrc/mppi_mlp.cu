@@ -486,18 +486,19 @@ mppi_mlp_rollout_kernel(const __grid_constant__ TickArgs a, const __grid_constan
             // hand-off records live at [consumer cluster][rank][slot][6][128]; the producer is cluster_id - 1
             if (t0 > 0 && owner) {
                 const unsigned int *fl = hand_flag + 2 * cluster_id + cta_rank;
+                unsigned int seen = epoch;
                 if (lane == 0) {
-                    unsigned int seen;
                     long long spins = 0;
                     do {
                         asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(fl) : "memory");
                         if (seen != epoch) __nanosleep(200);
-                    } while (seen != epoch && ++spins < 20000000ll);       // ~4 s guard: never hang the device
+                    } while (seen != epoch && ++spins < 20000000ll);       // ~4 s guard: never hang the device ...
                 }
-                __syncwarp();
+                const bool handed = __shfl_sync(0xffffffffu, seen == epoch ? 1 : 0, 0) != 0;
                 const float *rec = hand + ((size_t)((cluster_id * 2 + (int)cta_rank) * 2 + (grp & 1)) * 6) * TILE_M + row;
                 z[0] = __ldcg(rec); z[1] = __ldcg(rec + TILE_M); z[2] = __ldcg(rec + 2 * TILE_M);
                 acc = __ldcg(rec + 3 * TILE_M); vp0 = __ldcg(rec + 4 * TILE_M); vp1 = __ldcg(rec + 5 * TILE_M);
+                if (!handed) acc = CUDART_NAN_F;                  // ... and never return a cost built on a missing record
             }
             float4 ref = make_float4(0.f, 0.f, 0.f, 0.f);
             const float2 *eps_k = a.eps ? reinterpret_cast<const float2 *>(a.eps) + (size_t)(active ? k : 0) * T : nullptr;
@@ -671,18 +672,19 @@ mppi_mlp_rollout_kernel(const __grid_constant__ TickArgs a, const __grid_constan
             float vp0 = 0.f, vp1 = 0.f, vc0 = 0.f, vc1 = 0.f, vn0 = 0.f, vn1 = 0.f;    // controls of steps t-1, t, t+1
             if (t0 > 0 && owner) {                               // tail of a split pair: the previous cluster's record
                 const unsigned int *fl = hand_flag + 2 * cluster_id + cta_rank;
+                unsigned int seen = epoch;
                 if (lane == 0) {
-                    unsigned int seen;
                     long long spins = 0;
                     do {
                         asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(fl) : "memory");
                         if (seen != epoch) __nanosleep(200);
                     } while (seen != epoch && ++spins < 20000000ll);
                 }
-                __syncwarp();
+                const bool handed = __shfl_sync(0xffffffffu, seen == epoch ? 1 : 0, 0) != 0;
                 const float *rec = hand + ((size_t)((cluster_id * 2 + (int)cta_rank) * 2) * 6) * TILE_M + row;
                 z[0] = __ldcg(rec); z[1] = __ldcg(rec + TILE_M); z[2] = __ldcg(rec + 2 * TILE_M);
                 acc = __ldcg(rec + 3 * TILE_M); vp0 = __ldcg(rec + 4 * TILE_M); vp1 = __ldcg(rec + 5 * TILE_M);
+                if (!handed) acc = CUDART_NAN_F;                  // ... and never return a cost built on a missing record
             }
             float4 ref = make_float4(0.f, 0.f, 0.f, 0.f);
             const float2 *eps_k = a.eps ? reinterpret_cast<const float2 *>(a.eps) + (size_t)(active ? k : 0) * T : nullptr;

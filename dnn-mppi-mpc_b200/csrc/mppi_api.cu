@@ -509,6 +509,11 @@ int mppi_set_mlp_ex(mppi_handle_t h, int32_t n_in, int32_t n_hidden, const float
     return MPPI_OK;
 }
 
+int mppi_mlp_schedule_cut(int32_t c, int32_t n_clusters, int32_t n_units, int32_t T) {
+    if (c < 0 || n_clusters <= 0 || n_units < 0 || T <= 0) return -1;
+    return mlp_bal_cut(c, n_clusters, n_units, T);
+}
+
 int mppi_set_timing(mppi_handle_t h, int32_t on) {
     if (!h) return MPPI_E_BADARG;
     h->timing = on != 0;

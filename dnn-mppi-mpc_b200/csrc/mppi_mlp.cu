@@ -213,6 +213,38 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
+// ---- hand-off of a split quad / pair between neighbouring clusters (balanced schedule) ----
+// Records live at hand[tile slot][6][128] (x, y, yaw, cost so far, previous control), tile slot = ((consumer cluster * 2 +
+// rank) * 2 + ping-pong slot); flags at hand_flag[consumer cluster * 2 + rank] hold the epoch of the launch that published.
+// Producer: every owner thread stores its row (st.global.cg), fences, the owner groups meet at named barrier 2 and one thread
+// releases the flag.  Consumer: one lane per warp polls with ld.acquire.gpu (guarded, ~4 s: never hang the device; a missing
+// record turns the cost into NaN instead of garbage), then every thread reads its row past L1 (ld.global.cg).
+__device__ __forceinline__ void handoff_give(float *hand, unsigned int *hand_flag, unsigned int epoch, int tile_slot, int flag_idx,
+                                             int row, bool signaller, int n_owner_threads, const float (&z)[4], float acc, float vp0, float vp1) {
+    float *rec = hand + (size_t)tile_slot * 6 * TILE_M + row;
+    __stcg(rec, z[0]); __stcg(rec + TILE_M, z[1]); __stcg(rec + 2 * TILE_M, z[2]);
+    __stcg(rec + 3 * TILE_M, acc); __stcg(rec + 4 * TILE_M, vp0); __stcg(rec + 5 * TILE_M, vp1);
+    __threadfence();
+    named_bar_sync(2, n_owner_threads);
+    if (signaller) asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(hand_flag + flag_idx), "r"(epoch) : "memory");
+}
+__device__ __forceinline__ void handoff_take(const float *hand, const unsigned int *hand_flag, unsigned int epoch, int tile_slot, int flag_idx,
+                                             int row, int lane, float (&z)[4], float &acc, float &vp0, float &vp1) {
+    unsigned int seen = epoch;
+    if (lane == 0) {
+        long long spins = 0;
+        do {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(hand_flag + flag_idx) : "memory");
+            if (seen != epoch) __nanosleep(200);
+        } while (seen != epoch && ++spins < 20000000ll);
+    }
+    const bool handed = __shfl_sync(0xffffffffu, seen == epoch ? 1 : 0, 0) != 0;
+    const float *rec = hand + (size_t)tile_slot * 6 * TILE_M + row;
+    z[0] = __ldcg(rec); z[1] = __ldcg(rec + TILE_M); z[2] = __ldcg(rec + 2 * TILE_M);
+    acc = __ldcg(rec + 3 * TILE_M); vp0 = __ldcg(rec + 4 * TILE_M); vp1 = __ldcg(rec + 5 * TILE_M);
+    if (!handed) acc = CUDART_NAN_F;
+}
+
 template <int NIN, bool PP, int NG>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(MLP_THREADS, 1)
 mppi_mlp_rollout_kernel(const __grid_constant__ TickArgs a, const __grid_constant__ CUtensorMap w2_map,
@@ -245,13 +277,8 @@ mppi_mlp_rollout_kernel(const __grid_constant__ TickArgs a, const __grid_constan
     // release flag; the next cluster runs that quad's tail LAST, so the record is ready long before it is needed.
     // (one-tile schedule, NG = 2: the unit is a PAIR -- 2 CTAs x 1 tile -- x one timestep, same rule)
     const int n_quads = PP ? (n_tiles + 3) / 4 : (n_tiles + 1) / 2;
-    auto bal_cut = [&](int c) {
-        if (c >= n_clusters) return n_quads * T;
-        const long long raw = (long long)c * n_quads * T / n_clusters;
-        const int g = (int)(raw / T), t = (int)(raw % T) & ~1;
-        return g * T + t;
-    };
-    const int bal_b0 = balanced ? bal_cut(cluster_id) : 0, bal_b1 = balanced ? bal_cut(cluster_id + 1) : 0;
+    const int bal_b0 = balanced ? mlp_bal_cut(cluster_id, n_clusters, n_quads, T) : 0;
+    const int bal_b1 = balanced ? mlp_bal_cut(cluster_id + 1, n_clusters, n_quads, T) : 0;
     const int my_tile_steps = balanced ? (PP ? 2 : 1) * (bal_b1 - bal_b0) : my_slots * T;    // tile-steps of this CTA
 
     // ---- one-time setup: constants, barriers, TMEM, step-1 index + window (same rule as the tick kernel)
@@ -483,23 +510,9 @@ mppi_mlp_rollout_kernel(const __grid_constant__ TickArgs a, const __grid_constan
             float z[4] = {sm.x0[0], sm.x0[1], sm.x0[2], 0.f};
             float acc = 0.f, e[4] = {0.f, 0.f, 0.f, 0.f}, sn = 0.f, cs = 1.f;
             float vp0 = 0.f, vp1 = 0.f, vc0 = 0.f, vc1 = 0.f;          // controls of steps t-1 and t
-            // hand-off records live at [consumer cluster][rank][slot][6][128]; the producer is cluster_id - 1
-            if (t0 > 0 && owner) {
-                const unsigned int *fl = hand_flag + 2 * cluster_id + cta_rank;
-                unsigned int seen = epoch;
-                if (lane == 0) {
-                    long long spins = 0;
-                    do {
-                        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(fl) : "memory");
-                        if (seen != epoch) __nanosleep(200);
-                    } while (seen != epoch && ++spins < 20000000ll);       // ~4 s guard: never hang the device ...
-                }
-                const bool handed = __shfl_sync(0xffffffffu, seen == epoch ? 1 : 0, 0) != 0;
-                const float *rec = hand + ((size_t)((cluster_id * 2 + (int)cta_rank) * 2 + (grp & 1)) * 6) * TILE_M + row;
-                z[0] = __ldcg(rec); z[1] = __ldcg(rec + TILE_M); z[2] = __ldcg(rec + 2 * TILE_M);
-                acc = __ldcg(rec + 3 * TILE_M); vp0 = __ldcg(rec + 4 * TILE_M); vp1 = __ldcg(rec + 5 * TILE_M);
-                if (!handed) acc = CUDART_NAN_F;                  // ... and never return a cost built on a missing record
-            }
+            if (t0 > 0 && owner)                                   // tail of a split quad: the previous cluster's record
+                handoff_take(hand, hand_flag, epoch, (cluster_id * 2 + (int)cta_rank) * 2 + (grp & 1), 2 * cluster_id + (int)cta_rank,
+                             row, lane, z, acc, vp0, vp1);
             float4 ref = make_float4(0.f, 0.f, 0.f, 0.f);
             const float2 *eps_k = a.eps ? reinterpret_cast<const float2 *>(a.eps) + (size_t)(active ? k : 0) * T : nullptr;
             // owner: stage cost of the state reached by step t-1, noise + clamped control of step t, heading sin/cos
@@ -624,15 +637,9 @@ mppi_mlp_rollout_kernel(const __grid_constant__ TickArgs a, const __grid_constan
             finish(1, s0, s1, s2);
             if (t1 < T) {
                 // head of a split quad: publish the state after step t1-1 for the next cluster's tail
-                if (owner) {
-                    float *rec = hand + ((size_t)(((cluster_id + 1) * 2 + (int)cta_rank) * 2 + (grp & 1)) * 6) * TILE_M + row;
-                    __stcg(rec, z[0]); __stcg(rec + TILE_M, z[1]); __stcg(rec + 2 * TILE_M, z[2]);
-                    __stcg(rec + 3 * TILE_M, acc); __stcg(rec + 4 * TILE_M, vp0); __stcg(rec + 5 * TILE_M, vp1);
-                    __threadfence();
-                    named_bar_sync(2, 256);                          // the two owner groups (8 warps)
-                    if (cw == 0 && lane == 0)
-                        asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(hand_flag + 2 * (cluster_id + 1) + cta_rank), "r"(epoch) : "memory");
-                }
+                if (owner)
+                    handoff_give(hand, hand_flag, epoch, ((cluster_id + 1) * 2 + (int)cta_rank) * 2 + (grp & 1),
+                                 2 * (cluster_id + 1) + (int)cta_rank, row, cw == 0 && lane == 0, 256, z, acc, vp0, vp1);
             } else if (active) {
                 const int j = a.window == 20 ? nearest_wp<20>(sm, z[0], z[1]) : nearest_wp<0>(sm, z[0], z[1]);
                 ref = window_ref(sm, j);
@@ -670,22 +677,9 @@ mppi_mlp_rollout_kernel(const __grid_constant__ TickArgs a, const __grid_constan
             float z[4] = {sm.x0[0], sm.x0[1], sm.x0[2], 0.f};
             float acc = 0.f, e[4] = {0.f, 0.f, 0.f, 0.f}, sn = 0.f, cs = 1.f;
             float vp0 = 0.f, vp1 = 0.f, vc0 = 0.f, vc1 = 0.f, vn0 = 0.f, vn1 = 0.f;    // controls of steps t-1, t, t+1
-            if (t0 > 0 && owner) {                               // tail of a split pair: the previous cluster's record
-                const unsigned int *fl = hand_flag + 2 * cluster_id + cta_rank;
-                unsigned int seen = epoch;
-                if (lane == 0) {
-                    long long spins = 0;
-                    do {
-                        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(fl) : "memory");
-                        if (seen != epoch) __nanosleep(200);
-                    } while (seen != epoch && ++spins < 20000000ll);
-                }
-                const bool handed = __shfl_sync(0xffffffffu, seen == epoch ? 1 : 0, 0) != 0;
-                const float *rec = hand + ((size_t)((cluster_id * 2 + (int)cta_rank) * 2) * 6) * TILE_M + row;
-                z[0] = __ldcg(rec); z[1] = __ldcg(rec + TILE_M); z[2] = __ldcg(rec + 2 * TILE_M);
-                acc = __ldcg(rec + 3 * TILE_M); vp0 = __ldcg(rec + 4 * TILE_M); vp1 = __ldcg(rec + 5 * TILE_M);
-                if (!handed) acc = CUDART_NAN_F;                  // ... and never return a cost built on a missing record
-            }
+            if (t0 > 0 && owner)                                   // tail of a split pair: the previous cluster's record
+                handoff_take(hand, hand_flag, epoch, (cluster_id * 2 + (int)cta_rank) * 2, 2 * cluster_id + (int)cta_rank,
+                             row, lane, z, acc, vp0, vp1);
             float4 ref = make_float4(0.f, 0.f, 0.f, 0.f);
             const float2 *eps_k = a.eps ? reinterpret_cast<const float2 *>(a.eps) + (size_t)(active ? k : 0) * T : nullptr;
             // noise + clamped control of step t (A3-A5); called for t = 0, 1, 2, ... in order (a Philox call yields two steps)
@@ -810,15 +804,9 @@ mppi_mlp_rollout_kernel(const __grid_constant__ TickArgs a, const __grid_constan
                 }
             }
             if (t1 < T) {
-                if (owner) {                                      // head of a split pair: hand the state to the next cluster
-                    float *rec = hand + ((size_t)(((cluster_id + 1) * 2 + (int)cta_rank) * 2) * 6) * TILE_M + row;
-                    __stcg(rec, z[0]); __stcg(rec + TILE_M, z[1]); __stcg(rec + 2 * TILE_M, z[2]);
-                    __stcg(rec + 3 * TILE_M, acc); __stcg(rec + 4 * TILE_M, vp0); __stcg(rec + 5 * TILE_M, vp1);
-                    __threadfence();
-                    named_bar_sync(2, 128);                           // the owner group (4 warps)
-                    if (cw == 0 && lane == 0)
-                        asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(hand_flag + 2 * (cluster_id + 1) + cta_rank), "r"(epoch) : "memory");
-                }
+                if (owner)                                        // head of a split pair: hand the state to the next cluster
+                    handoff_give(hand, hand_flag, epoch, ((cluster_id + 1) * 2 + (int)cta_rank) * 2, 2 * (cluster_id + 1) + (int)cta_rank,
+                                 row, cw == 0 && lane == 0, 128, z, acc, vp0, vp1);
             } else if (owner && active) {
                 // cost of the final state: last stage cost (+ terminal); in `last` mode nothing else survives (Q1)
                 const int j = a.window == 20 ? nearest_wp<20>(sm, z[0], z[1]) : nearest_wp<0>(sm, z[0], z[1]);

@@ -2,6 +2,18 @@
 #pragma once
 #include <cuda_runtime.h>
 struct TickArgs;
+// Balanced K3 schedule: first unit-step (unit-major index u * T + t) of cluster c when n_units units x T timesteps are dealt
+// over n_clusters clusters; cuts fall on even timesteps (a Philox call yields the noise of two).  Shared by the kernel and
+// the host-side check (mppi_mlp_schedule_cut).
+#ifdef __CUDACC__
+__host__ __device__
+#endif
+inline int mlp_bal_cut(int c, int n_clusters, int n_units, int T) {
+    if (c >= n_clusters) return n_units * T;
+    const long long raw = (long long)c * n_units * T / n_clusters;
+    const int g = (int)(raw / T), t = (int)(raw % T) & ~1;
+    return g * T + t;
+}
 struct MlpState;
 MlpState *mlp_create(int K, int T);
 void mlp_destroy(MlpState *m);

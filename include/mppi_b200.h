@@ -260,6 +260,11 @@ int mppi_abi_version(void);
  * (packed = 0) or FFMA2 (packed = 1) loop filling every SM of `device` -- the measured denominator of the FP32 roofline the
  * analytic-dynamics kernels are bound by (MEASURED_PEAKS.json has no FP32 entry). */
 int mppi_probe_fp32_peak(int32_t device, int32_t packed, double *tflops_out);
+/* Host-side view of the learned-dynamics kernel's balanced schedule (no reference counterpart, no GPU needed): the first
+ * unit-step, in unit-major order u * T + t, that cluster `c` of `n_clusters` owns when `n_units` units (quads of 4 tiles in the
+ * ping-pong schedule, pairs of 2 tiles otherwise) x T timesteps are dealt evenly; c = n_clusters gives the total.  The same
+ * function the kernel evaluates, exported so the partition can be checked without a device.  Returns -1 on bad arguments. */
+int mppi_mlp_schedule_cut(int32_t c, int32_t n_clusters, int32_t n_units, int32_t T);
 
 #ifdef __cplusplus
 }

@@ -71,3 +71,31 @@ def test_product_never_imports_the_oracle():
                 txt = open(os.path.join(dp, f)).read()
                 assert "import oracle" not in txt and "from oracle" not in txt and "mppi_oracle" not in txt.replace(
                     "oracle/mppi_oracle.py:philox_noise", ""), f
+
+
+@pytest.mark.parametrize("n_units,T,n_clusters", [(128, 30, 74), (196, 12, 74), (98, 11, 74), (256, 30, 74), (79, 50, 74),
+                                                  (2048, 30, 74), (75, 31, 74), (148, 10, 74)])
+def test_mlp_balanced_schedule_is_an_even_partition(n_units, T, n_clusters):
+    """Host-side logic of the learned-dynamics kernel's balanced (horizon-split) schedule, through the exported cut
+    function the kernel itself evaluates (no GPU): the cluster ranges tile the unit x timestep sequence exactly once, cuts
+    fall on even timesteps (a Philox call yields two steps), the load differs by at most a few steps, and whenever the
+    launcher's condition holds (n_units * T / n_clusters >= T + 2) a cluster owns at most one tail and one head, the head
+    being a different unit from the tail -- what the head-first / tail-last hand-off order relies on."""
+    from mppi_b200 import _lib
+    lib = _lib.load()
+    cuts = [lib.mppi_mlp_schedule_cut(c, n_clusters, n_units, T) for c in range(n_clusters + 1)]
+    assert cuts[0] == 0 and cuts[-1] == n_units * T
+    assert all(b > a for a, b in zip(cuts, cuts[1:]))
+    assert all((c % T) % 2 == 0 for c in cuts[:-1])
+    sizes = [b - a for a, b in zip(cuts, cuts[1:])]
+    assert max(sizes) - min(sizes) <= 4 and max(sizes) <= n_units * T / n_clusters + 3
+    if n_units * T // n_clusters >= T + 2:
+        for a, b in zip(cuts, cuts[1:]):
+            assert b - a >= T                                   # at least one whole horizon of work
+            tail_unit = a // T if a % T else None
+            head_unit = (b - 1) // T if b % T else None
+            assert tail_unit is None or head_unit is None or head_unit > tail_unit
+            # consumer slack: the tail (run last) starts after the producer's head (run first) has finished
+            if tail_unit is not None:
+                assert (b - a) - (T - a % T) >= a % T
+    assert lib.mppi_mlp_schedule_cut(-1, n_clusters, n_units, T) == -1

@@ -524,12 +524,12 @@ def run_b200_arm(args):
         "bound": "fp32", "achieved": achieved_tf, "peak": peak_used, "unit": "TFLOP/s",
         "frac": achieved_tf / peak_used, "peak_probe": probe, "peak_derived": peak_tf_max,
         # dram__bytes_read.sum + dram__bytes_write.sum of one launch of this kernel (ncu --set full, profiles/r1_tick_kernel_ncu.txt)
-        "traffic": 86784.0, "traffic_unit": "bytes/launch (DRAM; the kernel reads no per-sample data)",
+        "traffic": 86272.0, "traffic_unit": "bytes/launch (DRAM; the kernel reads no per-sample data)",
         "peak_source": "max(derived 148 SM x 128 lanes x 2 x clocks.max.sm, FFMA/FFMA2 probe measured in this run); FP32 peak is not in MEASURED_PEAKS.json",
         "algorithmic_flop_per_sample_step": FLOP_PER_SAMPLE_STEP,
         "sm_mhz_during_run": f_mhz,
-        "issue_view": {"warp_instr_per_warp_sample_step": 198, "source": "ncu smsp__inst_executed / (K*H/32), profiles/",
-                       "achieved_frac_of_issue_peak": (K_PER_GPU * T_H / 32 * 198) / (kern_ms * 1e-3) / (SM_COUNT * 4 * f_mhz * 1e6)},
+        "issue_view": {"warp_instr_per_warp_sample_step": 190, "source": "ncu smsp__inst_executed / (K*H/32), profiles/",
+                       "achieved_frac_of_issue_peak": (K_PER_GPU * T_H / 32 * 190) / (kern_ms * 1e-3) / (SM_COUNT * 4 * f_mhz * 1e6)},
         "hbm_view": {"algorithmic_bytes_per_launch": hbm_bytes,
                      "achieved_GBps": hbm_bytes / (kern_ms * 1e-3) / 1e9,
                      "peak_GBps": (peaks or {}).get("hbm_gbs", 6650.0),

@@ -137,6 +137,9 @@ __device__ __forceinline__ void philox_eps_pair(const TickArgs &a, uint32_t k, u
     e[3] = __fmaf_rn(a.chol[1], z2, __fmul_rn(a.chol[2], z3));
 }
 
+#ifndef MPPI_KEYIDX_SMEM
+#define MPPI_KEYIDX_SMEM 1      // index addends of the first-minimum key from shared memory (hoisted LDS.128) instead of 20
+#endif                          // immediates re-materialised by MOVs in every loop iteration: 365 -> 349 instructions, +1.7 %
 // ------------------------------------------------------------------------------------------
 // shared-memory view of one robot's tick constants
 // ------------------------------------------------------------------------------------------
@@ -155,6 +158,9 @@ struct TickSmem {
     __align__(16) float ey[20];
     __align__(16) float ec[20];
     float c2x, c2y;                        // twice the centre
+#if MPPI_KEYIDX_SMEM
+    __align__(16) float kidx[20];          // 0..19: the index addends of the first-minimum key, read as LDS.128
+#endif
 };
 
 // Fills the expanded-form arrays of the static window from the (already written) negated coordinates; entries past the
@@ -170,6 +176,9 @@ __device__ __forceinline__ void fill_window_expanded(TickSmem &sm, int nw, int t
         sm.ec[j] = valid ? __fmaf_rn(wy, wy, __fmul_rn(wx, wx)) : 1e30f;
     }
     if (tid == 0) { sm.c2x = 2.f * cx; sm.c2y = 2.f * cy; }
+#if MPPI_KEYIDX_SMEM
+    for (int j = tid; j < 20; j += nthreads) sm.kidx[j] = (float)j;
+#endif
 }
 
 // Bounding circle of the window entries path[first .. first + n_valid) (one 16-entry chunk of the dynamic window).
@@ -329,10 +338,22 @@ __device__ __forceinline__ int nearest_wp(const TickSmem &sm, float x, float y) 
         const float2 nm = make_float2(-m, -m), huge = make_float2(1.2676506e30f, 1.2676506e30f);
         float key = CUDART_INF_F;
 #pragma unroll
+#if MPPI_KEYIDX_SMEM
+        const float4 *ki4 = reinterpret_cast<const float4 *>(sm.kidx);
+#pragma unroll
+        for (int i = 0; i < 10; i += 2) {
+            const float4 ki = ki4[i >> 1];
+            const float2 ka = f2_fma(f2_add(d[i], nm), huge, make_float2(ki.x, ki.y));
+            const float2 kb = f2_fma(f2_add(d[i + 1], nm), huge, make_float2(ki.z, ki.w));
+            key = fminf(fminf(key, ka.x), ka.y);
+            key = fminf(fminf(key, kb.x), kb.y);
+        }
+#else
         for (int i = 0; i < 10; ++i) {
             const float2 k2 = f2_fma(f2_add(d[i], nm), huge, make_float2((float)(2 * i), (float)(2 * i + 1)));
             key = fminf(fminf(key, k2.x), k2.y);
         }
+#endif
         return __float2int_rn(key);
 #else
         float m, key;

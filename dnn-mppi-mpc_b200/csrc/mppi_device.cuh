@@ -337,7 +337,6 @@ __device__ __forceinline__ int nearest_wp(const TickSmem &sm, float x, float y) 
         for (int i = 1; i < 10; ++i) m = fminf(fminf(m, d[i].x), d[i].y);
         const float2 nm = make_float2(-m, -m), huge = make_float2(1.2676506e30f, 1.2676506e30f);
         float key = CUDART_INF_F;
-#pragma unroll
 #if MPPI_KEYIDX_SMEM
         const float4 *ki4 = reinterpret_cast<const float4 *>(sm.kidx);
 #pragma unroll
@@ -349,6 +348,7 @@ __device__ __forceinline__ int nearest_wp(const TickSmem &sm, float x, float y) 
             key = fminf(fminf(key, kb.x), kb.y);
         }
 #else
+#pragma unroll
         for (int i = 0; i < 10; ++i) {
             const float2 k2 = f2_fma(f2_add(d[i], nm), huge, make_float2((float)(2 * i), (float)(2 * i + 1)));
             key = fminf(fminf(key, k2.x), k2.y);

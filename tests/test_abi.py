@@ -99,3 +99,22 @@ def test_mlp_balanced_schedule_is_an_even_partition(n_units, T, n_clusters):
             if tail_unit is not None:
                 assert (b - a) - (T - a % T) >= a % T
     assert lib.mppi_mlp_schedule_cut(-1, n_clusters, n_units, T) == -1
+
+
+def test_bench_reference_arm_prints_exactly_one_json_line():
+    """bench.py contract: `--impl reference` runs on the host cores only (the oracle port; no GPU, no product code on that
+    path) and stdout carries exactly one JSON line with the reference-arm keys."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1"],
+                       capture_output=True, text=True, timeout=600, cwd=root)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1, r.stdout[:500]
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "sample-steps/s" and d["higher_is_better"] is True
+    assert d["value"] > 0 and d["cpu_baseline"]["kind"] in ("port", "reference") and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert "workload" in d["config"] and d["vs_baseline"] is None

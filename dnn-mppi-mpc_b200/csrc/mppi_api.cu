@@ -73,9 +73,9 @@ struct mppi_handle_s {
     float *d_send = nullptr, *d_recv = nullptr;
     // fused peer-memory exchange
     bool p2p = false;
-    float *d_xchg = nullptr;
-    float *peer_buf[MPPI_MAX_PEERS] = {nullptr};
-    unsigned p2p_seq = 0;
+    unsigned long long *d_xchg = nullptr;
+    unsigned long long *peer_buf[MPPI_MAX_PEERS] = {nullptr};
+    unsigned p2p_seq = 0, p2p_timeout_ms = 2000;
     // MLP dynamics
     MlpState *mlp = nullptr;
     // per-robot reference paths (batched fleets)
@@ -109,6 +109,25 @@ static int fail(mppi_handle_t h, int code, const char *msg) {
     return code;
 }
 
+// Fused exchange: the kernel raises out[7] (device + mapped host record) when a peer never published its triple; that
+// tick was NOT applied (nominal and waypoint index untouched).  Report it once and clear it, so later ticks are judged
+// on their own.  Call after a stream synchronize.
+static int check_tick_faults(mppi_handle_t h) {
+    if (h->h_out[MPPI_OUT_FAULT] != 0.f) {               // finalize_tick refused non-finite costs
+        h->h_out[MPPI_OUT_FAULT] = 0.f;
+        cudaMemsetAsync(h->d_out + MPPI_OUT_FAULT, 0, sizeof(float), h->stream);
+        const bool handoff = h->mlp && mlp_take_fault(h->mlp, h->stream);
+        return fail(h, MPPI_E_NUMERIC, handoff ? "learned-dynamics kernel: a cluster hand-off was missed (producer cluster not co-resident); "
+                                                 "the tick was not applied"
+                                               : "non-finite sample costs (NaN/inf observed state or learned residual); the tick was not applied");
+    }
+    if (!h->p2p || h->h_out[MPPI_OUT_PEER_TIMEOUT] == 0.f) return MPPI_OK;
+    h->h_out[MPPI_OUT_PEER_TIMEOUT] = 0.f;
+    cudaMemsetAsync(h->d_out + MPPI_OUT_PEER_TIMEOUT, 0, sizeof(float), h->stream);
+    return fail(h, MPPI_E_NCCL, "peer-memory exchange timed out: a rank did not publish its (min, sum w, sum w*eps) triple; "
+                               "this tick was not applied");
+}
+
 extern "C" {
 
 int mppi_abi_version(void) { return MPPI_ABI_VERSION; }
@@ -122,6 +141,7 @@ const char *mppi_strerror(int s) {
         case MPPI_E_STATE: return "call order: reference path / nominal / weights not set";
         case MPPI_E_UNSUPPORTED: return "mode combination not supported";
         case MPPI_E_NOMEM: return "out of memory";
+        case MPPI_E_NUMERIC: return "non-finite sample costs: the tick was not applied (see mppi_last_error)";
         default: return "unknown status";
     }
 }
@@ -352,7 +372,7 @@ int mppi_set_stream(mppi_handle_t h, void *st) {
 int mppi_synchronize(mppi_handle_t h) {
     if (!h) return MPPI_E_BADARG;
     CK(h, cudaStreamSynchronize(h->stream));
-    return MPPI_OK;
+    return check_tick_faults(h);                       // the asynchronous path (mppi_step_async) reports here
 }
 
 int mppi_set_ref_path(mppi_handle_t h, const double *path, int32_t n, int32_t ncol) {
@@ -377,6 +397,14 @@ int mppi_set_ref_path(mppi_handle_t h, const double *path, int32_t n, int32_t nc
     h->args.path = h->d_path; h->args.n_path = n;
     h->args.path_len = nullptr; h->args.path_stride = 0;          // back to one shared path
     h->have_path = true;
+    {   // a carried index past the end of a SHORTER new path is clamped to its last waypoint (what step 1 does at the path
+        // end, mppi_differential_drive.py:97-99) instead of indexing the new path out of bounds
+        std::vector<int> idx((size_t)h->cfg.n_robots);
+        CK(h, cudaMemcpy(idx.data(), h->d_idx, sizeof(int) * idx.size(), cudaMemcpyDeviceToHost));
+        bool changed = false;
+        for (int &v : idx) { const int c = std::max(0, std::min(v, n - 1)); changed |= c != v; v = c; }
+        if (changed) CK(h, cudaMemcpy(h->d_idx, idx.data(), sizeof(int) * idx.size(), cudaMemcpyHostToDevice));
+    }
     return MPPI_OK;
 }
 
@@ -471,6 +499,11 @@ int mppi_get_nominal(mppi_handle_t h, float *u) {
 
 int mppi_set_waypoint_idx(mppi_handle_t h, const int32_t *idx) {
     if (!h || !idx) return MPPI_E_BADARG;
+    // the reference fails on an index outside the path (min() of the empty window slice, mppi_differential_drive.py:214);
+    // here it would send the window search out of bounds, so it is refused
+    const int limit = h->args.path_len ? h->path_cap : (h->have_path && h->cfg.cost_kind == MPPI_COSTKIND_PATH ? h->n_path : INT32_MAX);
+    for (int r = 0; r < h->cfg.n_robots; ++r)
+        if (idx[r] < 0 || idx[r] >= limit) return fail(h, MPPI_E_BADARG, "waypoint index outside the reference path");
     CK(h, cudaSetDevice(h->cfg.device));
     CK(h, cudaMemcpyAsync(h->d_idx, idx, sizeof(int) * h->cfg.n_robots, cudaMemcpyHostToDevice, h->stream));
     CK(h, cudaStreamSynchronize(h->stream));
@@ -567,6 +600,7 @@ static int strict_costs(mppi_handle_t h, const double *x0, const float *d_eps, f
     int idx0 = 0;
     CK(h, cudaMemcpyAsync(&idx0, h->d_idx, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     CK(h, cudaStreamSynchronize(h->stream));
+    idx0 = std::max(0, std::min(idx0, h->n_path - 1));
     const int s0 = host_nearest(h, idx0, x0[0], x0[1]);
     std::vector<unsigned> bpn{0u};
     std::vector<int> bps{s0};
@@ -610,7 +644,7 @@ static int launch_update(mppi_handle_t h, const TickArgs &a, bool inj) {
         TickArgs b = a;                      // exchange fused into the tick kernel: ONE launch, no NCCL call
         b.flags |= F_P2P;
         for (int p = 0; p < h->world; ++p) b.peer_buf[p] = h->peer_buf[p];
-        b.p2p_rank = h->rank; b.p2p_world = h->world; b.p2p_seq = ++h->p2p_seq;
+        b.p2p_rank = h->rank; b.p2p_world = h->world; b.p2p_seq = ++h->p2p_seq; b.p2p_timeout_ms = h->p2p_timeout_ms;
         CK(h, mppi_launch_tick(b, model, h->cfg.collision, h->cfg.cost_kind, h->sum, inj, stash, grid, h->stream));
         h->tm.launches++;
         return MPPI_OK;
@@ -678,7 +712,7 @@ static int step_common(mppi_handle_t h, const double *x0, const float *d_eps, ui
             cudaEventElapsedTime(&h->tm.last_rollout_ms, h->ev[0], h->ev[1]);
             cudaEventElapsedTime(&h->tm.last_update_ms, h->ev[1], h->ev[2]);
         }
-        if (h->p2p && h->h_out[7] != 0.f) return fail(h, MPPI_E_NCCL, "peer-memory exchange timed out (a rank did not arrive)");
+        if (int rc = check_tick_faults(h)) return rc;
         if (u0_out) { u0_out[0] = h->h_out[0]; u0_out[1] = h->h_out[1]; }
         if (useq_out) std::memcpy(useq_out, h->h_out + MPPI_OUT_HDR, sizeof(float) * 2 * h->cfg.T);
     }
@@ -739,6 +773,7 @@ int mppi_reduce_update(mppi_handle_t h, const float *d_S, const float *d_eps, ui
     int rc = launch_update(h, a, d_eps != nullptr);
     if (rc != MPPI_OK) return rc;
     CK(h, cudaStreamSynchronize(h->stream));
+    if (int rc2 = check_tick_faults(h)) return rc2;
     if (u0_out) { u0_out[0] = h->h_out[0]; u0_out[1] = h->h_out[1]; }
     if (useq_out) std::memcpy(useq_out, h->h_out + MPPI_OUT_HDR, sizeof(float) * 2 * h->cfg.T);
     if (w_eps_out) std::memcpy(w_eps_out, h->h_out + MPPI_OUT_HDR + 2 * MPPI_MAX_T, sizeof(float) * 2 * h->cfg.T);
@@ -906,8 +941,8 @@ int mppi_comm_p2p_export(mppi_handle_t h, int32_t world, void *out64) {
     if (h->cfg.n_robots != 1 || h->strict) return fail(h, MPPI_E_UNSUPPORTED, "sample sharding needs frozen mode, one robot");
     CK(h, cudaSetDevice(h->cfg.device));
     if (!h->d_xchg) {
-        CK(h, cudaMalloc(&h->d_xchg, sizeof(float) * MPPI_XCHG_FLOATS));
-        CK(h, cudaMemset(h->d_xchg, 0, sizeof(float) * MPPI_XCHG_FLOATS));
+        CK(h, cudaMalloc(&h->d_xchg, sizeof(unsigned long long) * (MPPI_XCHG_WORDS + MPPI_XCHG_TRACE)));
+        CK(h, cudaMemset(h->d_xchg, 0, sizeof(unsigned long long) * (MPPI_XCHG_WORDS + MPPI_XCHG_TRACE)));
         CK(h, cudaDeviceSynchronize());
     }
     cudaIpcMemHandle_t ih;
@@ -927,9 +962,22 @@ int mppi_comm_p2p_open(mppi_handle_t h, const void *handles, int32_t rank, int32
         std::memcpy(&ih, (const char *)handles + 64 * p, 64);
         void *ptr = nullptr;
         CK(h, cudaIpcOpenMemHandle(&ptr, ih, cudaIpcMemLazyEnablePeerAccess));
-        h->peer_buf[p] = (float *)ptr;
+        h->peer_buf[p] = (unsigned long long *)ptr;
     }
     h->rank = rank; h->world = world; h->p2p = true; h->p2p_seq = 0;
+    if (const char *env = std::getenv("MPPI_P2P_TIMEOUT_MS")) h->p2p_timeout_ms = (unsigned)std::max(1, std::atoi(env));
+    h->h_out[MPPI_OUT_PEER_TIMEOUT] = 0.f;              // no stale peer-timeout report from an earlier communicator
+    CK(h, cudaMemsetAsync(h->d_out + MPPI_OUT_PEER_TIMEOUT, 0, sizeof(float), h->stream));
+    CK(h, cudaStreamSynchronize(h->stream));
+    return MPPI_OK;
+}
+
+int mppi_comm_p2p_trace(mppi_handle_t h, uint64_t stamps_out[4]) {
+    if (!h || !stamps_out) return MPPI_E_BADARG;
+    if (!h->p2p || !h->d_xchg) return fail(h, MPPI_E_STATE, "no fused exchange on this handle");
+    CK(h, cudaSetDevice(h->cfg.device));
+    CK(h, cudaMemcpyAsync(stamps_out, h->d_xchg + MPPI_XCHG_WORDS, sizeof(uint64_t) * 4, cudaMemcpyDeviceToHost, h->stream));
+    CK(h, cudaStreamSynchronize(h->stream));
     return MPPI_OK;
 }
 

@@ -16,16 +16,21 @@
 #endif
 #define MPPI_PENALTY 1.0e10f           // mppi_race_car_obstacle.py:157
 #define MPPI_SENTINEL 1.0e18f          // padded window entries: distance^2 = 1e36, never the minimum
-#define MPPI_OUT_HDR 10                // u0 (post-shift, Q8), idx, rho, ncoll, eta, ess, p2p flag, first row of the PRE-shift nominal
+#define MPPI_OUT_HDR 12                // u0 (post-shift, Q8), idx, rho, ncoll, eta, ess, p2p flag, first row of the PRE-shift nominal,
+                                       // [10] non-finite-cost fault (the tick was not applied), [11] spare
+#define MPPI_OUT_PEER_TIMEOUT 7
+#define MPPI_OUT_FAULT 10
 #define MPPI_OUT_STRIDE (MPPI_OUT_HDR + 8 * MPPI_MAX_T)   // header, U shifted, w_eps, U pre-shift, U before the tick
 #define MPPI_OUT_UPRE (MPPI_OUT_HDR + 4 * MPPI_MAX_T)
 #define MPPI_OUT_UOLD (MPPI_OUT_HDR + 6 * MPPI_MAX_T)
 #define MPPI_NF(T) (4 + 2 * (T))
 #define MPPI_NF_MAX MPPI_NF(MPPI_MAX_T)
-// exchange buffer of one rank: 2 parities x [MPPI_MAX_PEERS triples of NF_MAX floats], then 2 x MPPI_MAX_PEERS flags
+// exchange buffer of one rank (fused multi-GPU exchange): 2 parities x [MPPI_MAX_PEERS triples of NF_MAX 64-bit words];
+// a word is (sequence number << 32 | float bits): the flag travels WITH the datum in one 8-byte store (the "LL" protocol),
+// so a reader that sees the tick's sequence number in a word has that word's datum -- no fence, no separate flag
 #define MPPI_XCHG_SLOT(par, r) (((par) * MPPI_MAX_PEERS + (r)) * MPPI_NF_MAX)
-#define MPPI_XCHG_FLAGS (2 * MPPI_MAX_PEERS * MPPI_NF_MAX)
-#define MPPI_XCHG_FLOATS (MPPI_XCHG_FLAGS + 2 * MPPI_MAX_PEERS)       // floats per partial: ncoll_min, smooth_min, eta, sum w^2, N[T][2]
+#define MPPI_XCHG_WORDS (2 * MPPI_MAX_PEERS * MPPI_NF_MAX)
+#define MPPI_XCHG_TRACE 8              // globaltimer stamps of the last exchange (diagnostics), kept behind the words
 
 enum : int {
     F_WRITE_S = 1,       // store per-sample costs
@@ -84,9 +89,10 @@ struct TickArgs {
     float *plant_log;                 // closed loop: [(n+1)][4] states and [n][2] controls behind them
     int plant_mode, plant_tick, plant_n;
     // fused multi-GPU exchange (F_P2P): peer_buf[p] = rank p's exchange buffer (own buffer at index p2p_rank)
-    float *peer_buf[MPPI_MAX_PEERS];
+    unsigned long long *peer_buf[MPPI_MAX_PEERS];
     int p2p_rank, p2p_world;
     unsigned p2p_seq;
+    unsigned p2p_timeout_ms;          // a peer that has not published within this time fails the tick (MPPI_E_NCCL)
 };
 
 // ------------------------------------------------------------------------------------------

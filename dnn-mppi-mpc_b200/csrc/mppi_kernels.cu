@@ -8,6 +8,8 @@
 #include "mppi_device.cuh"
 #include "mppi_launch.h"
 
+#include <algorithm>
+
 namespace {
 
 __device__ __forceinline__ float warp_sum(float v) {
@@ -148,6 +150,13 @@ __device__ void finalize_tick(const TickArgs &a, int robot, int idx_new, MergeSm
     const float inv_eta = 1.f / eta;
     float *U = a.U + (size_t)robot * T * 2;
     float *out = a.out + (size_t)robot * MPPI_OUT_STRIDE;
+    // eta = sum of exp(-(S - min S)/tau) >= 1 whenever the costs are finite.  NaN / inf costs (a NaN observed state, a
+    // learned residual that diverged, a missed hand-off in the learned-dynamics kernel) must not poison the nominal for
+    // good: the tick is NOT applied and the fault is reported to the host (MPPI_E_NUMERIC).
+    if (!(eta > 0.f && eta < CUDART_INF_F)) {
+        if (tid == 0) { out[MPPI_OUT_FAULT] = 1.f; if (robot == 0 && a.out_host) a.out_host[MPPI_OUT_FAULT] = 1.f; }
+        return;
+    }
     for (int c = tid; c < 2 * T; c += MPPI_BLOCK) ms.weps[c] = ms.col[4 + c] * inv_eta;
     __syncthreads();
     for (int c = tid; c < 2 * T; c += MPPI_BLOCK) {
@@ -176,7 +185,7 @@ __device__ void finalize_tick(const TickArgs &a, int robot, int idx_new, MergeSm
         float hdr[MPPI_OUT_HDR];
         hdr[0] = u0x; hdr[1] = u0y; hdr[2] = __int_as_float(idx_new);
         hdr[3] = ms.col[1]; hdr[4] = ms.col[0]; hdr[5] = eta;
-        hdr[6] = eta * eta / ms.col[3]; hdr[7] = (a.flags & F_P2P) ? out[7] : 0.f;     // sticky peer-timeout flag
+        hdr[6] = eta * eta / ms.col[3]; hdr[7] = 0.f; hdr[10] = out[MPPI_OUT_FAULT]; hdr[11] = 0.f;       // [7] = peer-timeout flag, set by the exchange when a rank never arrived
         hdr[8] = ms.upre[0]; hdr[9] = ms.upre[1];       // the textbook MPPI output: row 0 of the updated nominal before the shift
 #pragma unroll
         for (int i = 0; i < MPPI_OUT_HDR; ++i) { out[i] = hdr[i]; if (oh) oh[i] = hdr[i]; }
@@ -247,7 +256,9 @@ __global__ void __launch_bounds__(MPPI_BLOCK, STASH ? 2 : MPPI_MIN_BLOCKS) mppi_
     } else if (a.flags & F_HOST_IDX) {
         s_new = a.idx_host;
     } else {
-        const int s_old = a.idx[robot];
+        // a carried index outside the robot's path (per-robot courses of different lengths) is clamped to the last
+        // waypoint, so the window below is never empty
+        const int s_old = max(0, min(a.idx[robot], n_path - 1));
         unsigned long long key = ~0ull;
         for (int j = tid; j < a.window && s_old + j < n_path; j += MPPI_BLOCK) {
             const float4 p = rpath[s_old + j];
@@ -454,30 +465,78 @@ __global__ void __launch_bounds__(MPPI_BLOCK, STASH ? 2 : MPPI_MIN_BLOCKS) mppi_
         __syncthreads();
     }
     if (a.flags & F_P2P) {
-        // ---- fused exchange over NVLink peer memory: publish this GPU's triple to every rank, flag it, wait for
-        // the peers, merge in rank order (bit-identical on all ranks).  Double-buffered by the tick parity.
+        // ---- fused exchange over NVLink peer memory.  Every column of this GPU's triple goes to every rank (its own
+        // buffer included) as ONE 8-byte store carrying (tick sequence number, float bits): the flag travels with the
+        // datum (NCCL's "LL" idea), so there is no system-scope fence, no separate flag store and no second round trip --
+        // the cost is one NVLink write latency after the slowest rank's last CTA.  G*NF words are written and polled by
+        // the whole CTA in parallel.  Slots are double-buffered by tick parity: a rank can run at most one tick ahead of
+        // a peer (it needs that peer's words of tick t to finish tick t), so parity t&1 is never overwritten while read.
         const int G = a.p2p_world, me = a.p2p_rank;
-        const unsigned par = a.p2p_seq & 1u;
-        for (int p = 0; p < G; ++p) {
-            float *dst = a.peer_buf[p] + MPPI_XCHG_SLOT(par, me);
-            for (int c = tid; c < NF; c += MPPI_BLOCK) dst[c] = ms.col[c];
+        const unsigned seq = a.p2p_seq, par = seq & 1u;
+        unsigned long long t_stamp[4];
+        if (tid == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_stamp[0]));
+        for (int i = tid; i < G * NF; i += MPPI_BLOCK) {
+            const int p = i / NF, c = i - p * NF;
+            unsigned long long *dst = a.peer_buf[p] + MPPI_XCHG_SLOT(par, me) + c;
+            const unsigned long long v = ((unsigned long long)seq << 32) | (unsigned long long)__float_as_uint(ms.col[c]);
+            asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(dst), "l"(v) : "memory");
         }
-        __threadfence_system();
-        __syncthreads();
-        if (tid < G) {
-            unsigned *pf = reinterpret_cast<unsigned *>(a.peer_buf[tid] + MPPI_XCHG_FLAGS) + par * MPPI_MAX_PEERS + me;
-            asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(pf), "r"(a.p2p_seq) : "memory");
-            const unsigned *mf = reinterpret_cast<const unsigned *>(a.peer_buf[me] + MPPI_XCHG_FLAGS) + par * MPPI_MAX_PEERS + tid;
-            unsigned v = 0;
-            const long long t0 = clock64();
-            do {
-                asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(mf) : "memory");
-            } while (v != a.p2p_seq && clock64() - t0 < 4000000000LL);     // ~2 s guard against a dead peer
-            if (v != a.p2p_seq) a.out[7] = 1.f;                              // reported by the host as MPPI_E_NCCL
+        if (tid == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_stamp[1]));
+        float *xs = reinterpret_cast<float *>(mppi_dyn_smem);       // [G][NF] gathered triples (the noise stash is free by now)
+        bool ok = true;
+        {
+            unsigned long long t0;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+            const unsigned long long limit = (unsigned long long)a.p2p_timeout_ms * 1000000ull;
+            for (int i = tid; i < G * NF; i += MPPI_BLOCK) {
+                const int r = i / NF, c = i - r * NF;
+                const unsigned long long *src = a.peer_buf[me] + MPPI_XCHG_SLOT(par, r) + c;
+                unsigned long long v, now;
+                int spins = 0;
+                do {
+                    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(src) : "memory");
+                    if ((unsigned)(v >> 32) == seq) break;
+                    if ((++spins & 255) == 0) {                     // a dead peer must not hang the device
+                        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+                        if (now - t0 > limit) { ok = false; break; }
+                    }
+                } while (true);
+                xs[r * NF + c] = __uint_as_float((unsigned)v);
+            }
         }
-        __syncthreads();
-        merge_partials(a, a.peer_buf[me] + MPPI_XCHG_SLOT(par, 0), G, ms, reinterpret_cast<float *>(mppi_dyn_smem), MPPI_NF_MAX);
+        const int all_ok = __syncthreads_and(ok ? 1 : 0);
+        if (tid == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_stamp[2]));
+        if (!all_ok) {
+            // a peer never arrived: leave the nominal and the waypoint index untouched and report it (the host returns
+            // MPPI_E_NCCL from mppi_step / mppi_synchronize and clears the flag)
+            if (tid == 0) { a.out[MPPI_OUT_PEER_TIMEOUT] = 1.f; if (a.out_host) a.out_host[MPPI_OUT_PEER_TIMEOUT] = 1.f; }
+            return;
+        }
+        // merge in rank order: identical arithmetic, hence identical bits, on every rank
+        {
+            int n = __float_as_int(xs[0]); float s = xs[1];
+            for (int r = 1; r < G; ++r) {
+                const int rn = __float_as_int(xs[r * NF]); const float rs = xs[r * NF + 1];
+                if (rn < n || (rn == n && rs < s)) { n = rn; s = rs; }
+            }
+            for (int c = 2 + tid; c < NF; c += MPPI_BLOCK) {
+                float acc = 0.f;
+                for (int r = 0; r < G; ++r) {
+                    const float w = rel_weight(__float_as_int(xs[r * NF]), xs[r * NF + 1], n, s, a.inv_temp);
+                    acc = fmaf(c == 3 ? w * w : w, xs[r * NF + c], acc);
+                }
+                ms.col[c] = acc;
+            }
+            __syncthreads();            // every thread has read ms.col[0..1]-independent inputs from xs; now publish the key
+            if (tid == 0) { ms.col[0] = __int_as_float(n); ms.col[1] = s; }
+            __syncthreads();
+        }
         finalize_tick(a, robot, s_new, ms);
+        if (tid == 0) {
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_stamp[3]));
+            unsigned long long *tr = a.peer_buf[me] + MPPI_XCHG_WORDS;      // diagnostics: mppi_comm_p2p_trace
+            tr[0] = t_stamp[0]; tr[1] = t_stamp[1]; tr[2] = t_stamp[2]; tr[3] = t_stamp[3];
+        }
         return;
     }
     if (a.flags & F_TRIPLE_OUT) {
@@ -680,7 +739,9 @@ static cudaError_t with_tick_kernel(int model, int coll, int cost_kind, bool sum
 }
 
 size_t mppi_tick_dyn_smem(int T, bool stash) {
-    return stash ? sizeof(float2) * (size_t)T * MPPI_BLOCK : sizeof(float) * MPPI_WARPS * 2 * MPPI_MAX_T;
+    // regenerate path: per-warp column sums (8 KB), also large enough for the exchange's gathered triples
+    const size_t small = std::max(sizeof(float) * MPPI_WARPS * 2 * MPPI_MAX_T, sizeof(float) * MPPI_MAX_PEERS * MPPI_NF_MAX);
+    return stash ? std::max(sizeof(float2) * (size_t)T * MPPI_BLOCK, small) : small;
 }
 
 cudaError_t mppi_launch_tick(const TickArgs &a, int model, int coll, int cost_kind, bool sum, bool inj, bool stash, dim3 grid, cudaStream_t st) {

@@ -228,8 +228,8 @@ __device__ __forceinline__ void handoff_give(float *hand, unsigned int *hand_fla
     named_bar_sync(2, n_owner_threads);
     if (signaller) asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(hand_flag + flag_idx), "r"(epoch) : "memory");
 }
-__device__ __forceinline__ void handoff_take(const float *hand, const unsigned int *hand_flag, unsigned int epoch, int tile_slot, int flag_idx,
-                                             int row, int lane, float (&z)[4], float &acc, float &vp0, float &vp1) {
+__device__ __forceinline__ void handoff_take(const float *hand, unsigned int *hand_flag, unsigned int *fault, unsigned int epoch, int tile_slot,
+                                             int flag_idx, int row, int lane, float (&z)[4], float &acc, float &vp0, float &vp1) {
     unsigned int seen = epoch;
     if (lane == 0) {
         long long spins = 0;
@@ -242,7 +242,10 @@ __device__ __forceinline__ void handoff_take(const float *hand, const unsigned i
     const float *rec = hand + (size_t)tile_slot * 6 * TILE_M + row;
     z[0] = __ldcg(rec); z[1] = __ldcg(rec + TILE_M); z[2] = __ldcg(rec + 2 * TILE_M);
     acc = __ldcg(rec + 3 * TILE_M); vp0 = __ldcg(rec + 4 * TILE_M); vp1 = __ldcg(rec + 5 * TILE_M);
-    if (!handed) acc = CUDART_NAN_F;
+    if (!handed) {                                        // never garbage: NaN costs make finalize_tick refuse the tick, and the
+        acc = CUDART_NAN_F;                               // fault word tells the host why (MPPI_E_NUMERIC, "hand-off was missed")
+        if (lane == 0) atomicExch(fault, epoch);
+    }
 }
 
 template <int NIN, bool PP, int NG>
@@ -250,7 +253,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(MLP_THREADS, 1)
 mppi_mlp_rollout_kernel(const __grid_constant__ TickArgs a, const __grid_constant__ CUtensorMap w2_map,
                         const float4 *__restrict__ g_w01, const float2 *__restrict__ g_w01u, const float4 *__restrict__ g_w3,
                         const float *__restrict__ g_b3, const float *__restrict__ g_bh, float *__restrict__ S_out, int n_tiles,
-                        float *__restrict__ hand, unsigned int *__restrict__ hand_flag, unsigned int epoch, int balanced) {
+                        float *__restrict__ hand, unsigned int *__restrict__ hand_flag, unsigned int *__restrict__ fault,
+                        unsigned int epoch, int balanced) {
     static_assert(NG == 1 || (NG == 2 && !PP), "two GEMMs per step run the one-tile schedule");
     // 1024-byte alignment is what SWIZZLE_128B needs; keeping every pointer derived from this symbol (no
     // integer round-trips) lets the compiler emit LDS/STS instead of generic LD/ST
@@ -302,7 +306,7 @@ mppi_mlp_rollout_kernel(const __grid_constant__ TickArgs a, const __grid_constan
     }
     __syncthreads();
     {
-        const int s_old = a.idx[0];
+        const int s_old = max(0, min(a.idx[0], a.n_path - 1));
         unsigned long long key = ~0ull;
         for (int j = tid; j < a.window && s_old + j < a.n_path; j += MLP_THREADS) {
             const float4 p = a.path[s_old + j];
@@ -511,7 +515,7 @@ mppi_mlp_rollout_kernel(const __grid_constant__ TickArgs a, const __grid_constan
             float acc = 0.f, e[4] = {0.f, 0.f, 0.f, 0.f}, sn = 0.f, cs = 1.f;
             float vp0 = 0.f, vp1 = 0.f, vc0 = 0.f, vc1 = 0.f;          // controls of steps t-1 and t
             if (t0 > 0 && owner)                                   // tail of a split quad: the previous cluster's record
-                handoff_take(hand, hand_flag, epoch, (cluster_id * 2 + (int)cta_rank) * 2 + (grp & 1), 2 * cluster_id + (int)cta_rank,
+                handoff_take(hand, hand_flag, fault, epoch, (cluster_id * 2 + (int)cta_rank) * 2 + (grp & 1), 2 * cluster_id + (int)cta_rank,
                              row, lane, z, acc, vp0, vp1);
             float4 ref = make_float4(0.f, 0.f, 0.f, 0.f);
             const float2 *eps_k = a.eps ? reinterpret_cast<const float2 *>(a.eps) + (size_t)(active ? k : 0) * T : nullptr;
@@ -678,7 +682,7 @@ mppi_mlp_rollout_kernel(const __grid_constant__ TickArgs a, const __grid_constan
             float acc = 0.f, e[4] = {0.f, 0.f, 0.f, 0.f}, sn = 0.f, cs = 1.f;
             float vp0 = 0.f, vp1 = 0.f, vc0 = 0.f, vc1 = 0.f, vn0 = 0.f, vn1 = 0.f;    // controls of steps t-1, t, t+1
             if (t0 > 0 && owner)                                   // tail of a split pair: the previous cluster's record
-                handoff_take(hand, hand_flag, epoch, (cluster_id * 2 + (int)cta_rank) * 2, 2 * cluster_id + (int)cta_rank,
+                handoff_take(hand, hand_flag, fault, epoch, (cluster_id * 2 + (int)cta_rank) * 2, 2 * cluster_id + (int)cta_rank,
                              row, lane, z, acc, vp0, vp1);
             float4 ref = make_float4(0.f, 0.f, 0.f, 0.f);
             const float2 *eps_k = a.eps ? reinterpret_cast<const float2 *>(a.eps) + (size_t)(active ? k : 0) * T : nullptr;
@@ -842,7 +846,8 @@ struct MlpState {
     float *d_b3 = nullptr;
     float *d_bh = nullptr;                // n_hidden = 3: bias of the layer the first GEMM evaluates
     float *d_hand = nullptr;              // balanced schedule: state records of split quads [cluster][rank][slot][6][128]
-    unsigned int *d_hand_flag = nullptr;  // [cluster][rank]: epoch of the launch that published the record
+    unsigned int *d_hand_flag = nullptr;  // [cluster][rank]: epoch of the launch that published the record; then one fault word
+    int max_clusters[6] = {0, 0, 0, 0, 0, 0};   // co-resident 2-CTA clusters per instantiation (cudaOccupancyMaxActiveClusters)
     unsigned int epoch = 0;
     int n_in = 3, n_gemm = 1;
     CUtensorMap w2_map;
@@ -859,8 +864,8 @@ MlpState *mlp_create(int K, int T) {
     if (cudaMalloc(&m->d_w2, sizeof(__nv_bfloat16) * 2 * HID * HID) != cudaSuccess ||
         cudaMalloc(&m->d_bh, sizeof(float) * HID) != cudaSuccess ||
         cudaMalloc(&m->d_hand, sizeof(float) * (size_t)(m->n_sm / 2 + 1) * 2 * 2 * 6 * TILE_M) != cudaSuccess ||
-        cudaMalloc(&m->d_hand_flag, sizeof(unsigned int) * (size_t)(m->n_sm / 2 + 1) * 2) != cudaSuccess ||
-        cudaMemset(m->d_hand_flag, 0, sizeof(unsigned int) * (size_t)(m->n_sm / 2 + 1) * 2) != cudaSuccess ||
+        cudaMalloc(&m->d_hand_flag, sizeof(unsigned int) * ((size_t)(m->n_sm / 2 + 1) * 2 + 1)) != cudaSuccess ||
+        cudaMemset(m->d_hand_flag, 0, sizeof(unsigned int) * ((size_t)(m->n_sm / 2 + 1) * 2 + 1)) != cudaSuccess ||
         cudaMalloc(&m->d_w01, sizeof(float4) * HID) != cudaSuccess ||
         cudaMalloc(&m->d_w3, sizeof(float4) * HID) != cudaSuccess ||
         cudaMalloc(&m->d_w01u, sizeof(float2) * HID) != cudaSuccess ||
@@ -950,6 +955,23 @@ cudaError_t mlp_set_weights(MlpState *m, int n_in, int n_hidden, const float *co
     return cudaSuccess;
 }
 
+// Co-resident 2-CTA clusters of one instantiation on an otherwise idle device.  The balanced schedule makes a cluster
+// wait for a record its neighbour publishes inside the same launch, so every cluster of the grid has to be resident.
+template <typename Kern>
+static int mlp_max_active_clusters(Kern kern, int n_sm) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(n_sm & ~1), 1, 1);
+    cfg.blockDim = dim3(MLP_THREADS, 1, 1);
+    cfg.dynamicSmemBytes = MLP_DYN_SMEM;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
 int mlp_rollout_costs(MlpState *m, const TickArgs &args, bool sum, const float *d_eps, float *d_S, cudaStream_t st) {
     if (!m || !m->ready) return -2;
     TickArgs a = args;
@@ -961,6 +983,17 @@ int mlp_rollout_costs(MlpState *m, const TickArgs &args, bool sum, const float *
     // one-tile schedule (A/B measurements)
     static const bool allow_pp = [] { const char *e = std::getenv("MPPI_MLP_PINGPONG"); return !(e && e[0] == '0'); }();
     const bool pp = allow_pp && n_tiles > grid && m->n_gemm == 1;
+    // never launch more clusters than the device keeps resident at once (fused-off SMs, MPS partitions): the grid is
+    // persistent, so a smaller one only means more tiles per cluster
+    const int variant = (m->n_gemm == 2 ? 4 : (pp ? 2 : 0)) + (m->n_in == 5 ? 1 : 0);
+    if (m->max_clusters[variant] == 0) {
+        int n = 0;
+        if (m->n_gemm == 2) n = m->n_in == 5 ? mlp_max_active_clusters(mppi_mlp_rollout_kernel<5, false, 2>, m->n_sm) : mlp_max_active_clusters(mppi_mlp_rollout_kernel<3, false, 2>, m->n_sm);
+        else if (pp) n = m->n_in == 5 ? mlp_max_active_clusters(mppi_mlp_rollout_kernel<5, true, 1>, m->n_sm) : mlp_max_active_clusters(mppi_mlp_rollout_kernel<3, true, 1>, m->n_sm);
+        else n = m->n_in == 5 ? mlp_max_active_clusters(mppi_mlp_rollout_kernel<5, false, 1>, m->n_sm) : mlp_max_active_clusters(mppi_mlp_rollout_kernel<3, false, 1>, m->n_sm);
+        m->max_clusters[variant] = n > 0 ? n : -1;                    // -1: the query failed, keep the SM-count grid
+    }
+    if (m->max_clusters[variant] > 0) grid = std::min(grid, 2 * m->max_clusters[variant]);
     // balanced (horizon-split) walk when whole quads do not divide over the clusters and every cluster still gets more
     // than one horizon of steps; MPPI_MLP_BALANCED=0 forces whole quads (A/B measurements)
     const char *bal_env = std::getenv("MPPI_MLP_BALANCED");               // read per launch: tests flip it in-process
@@ -970,7 +1003,8 @@ int mlp_rollout_costs(MlpState *m, const TickArgs &args, bool sum, const float *
     const int balanced = ((pp || one_tile_bal) && allow_bal && n_clusters > 0 && (n_quads % n_clusters) != 0 &&
                           (long long)n_quads * a.T / n_clusters >= a.T + 2) ? 1 : 0;
     const unsigned int epoch = ++m->epoch;
-#define MPPI_MLP_LAUNCH(N, P, G) mppi_mlp_rollout_kernel<N, P, G><<<grid, MLP_THREADS, MLP_DYN_SMEM, st>>>(a, m->w2_map, m->d_w01, m->d_w01u, m->d_w3, m->d_b3, m->d_bh, d_S, n_tiles, m->d_hand, m->d_hand_flag, epoch, balanced)
+    unsigned int *fault = m->d_hand_flag + (size_t)(m->n_sm / 2 + 1) * 2;
+#define MPPI_MLP_LAUNCH(N, P, G) mppi_mlp_rollout_kernel<N, P, G><<<grid, MLP_THREADS, MLP_DYN_SMEM, st>>>(a, m->w2_map, m->d_w01, m->d_w01u, m->d_w3, m->d_b3, m->d_bh, d_S, n_tiles, m->d_hand, m->d_hand_flag, fault, epoch, balanced)
     if (m->n_gemm == 2) { if (m->n_in == 5) MPPI_MLP_LAUNCH(5, false, 2); else MPPI_MLP_LAUNCH(3, false, 2); }
     else if (m->n_in == 5) { if (pp) MPPI_MLP_LAUNCH(5, true, 1); else MPPI_MLP_LAUNCH(5, false, 1); }
     else { if (pp) MPPI_MLP_LAUNCH(3, true, 1); else MPPI_MLP_LAUNCH(3, false, 1); }
@@ -979,3 +1013,11 @@ int mlp_rollout_costs(MlpState *m, const TickArgs &args, bool sum, const float *
 }
 
 int mlp_launches_per_tick(const MlpState *) { return 1; }
+
+bool mlp_take_fault(MlpState *m, cudaStream_t st) {
+    if (!m || !m->d_hand_flag) return false;
+    unsigned int *fault = m->d_hand_flag + (size_t)(m->n_sm / 2 + 1) * 2, v = 0;
+    if (cudaMemcpyAsync(&v, fault, sizeof(v), cudaMemcpyDeviceToHost, st) != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess) return false;
+    if (v) cudaMemsetAsync(fault, 0, sizeof(v), st);
+    return v != 0;
+}

@@ -78,6 +78,11 @@ class ControllerBase:
         return self._engine.get_waypoint_idx()
 
     def _set_idx(self, v):
+        # the reference fails at the next tick on an index outside the path (ValueError from min() / argmin of the empty
+        # window slice, mppi_differential_drive.py:214); here the assignment itself is refused
+        n = None if self._ref_path is None else len(self._ref_path)
+        if n is not None and not (0 <= int(v) < n):
+            raise ValueError("waypoint index %d outside the reference path (0..%d)" % (int(v), n - 1))
         self._engine.set_waypoint_idx(int(v))
 
     # -- one tick ----------------------------------------------------------------------------

@@ -6,7 +6,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("MPPI_B200_LIB", os.path.join(_HERE, "libmppi_b200.so"))   # override: kernel A/B builds
 
-MPPI_ABI_VERSION = 2
+MPPI_ABI_VERSION = 3
 MODEL = {"diffdrive": 0, "bicycle": 1, "diffdrive_mlp": 2}
 COST_MODE = {"last": 0, "sum": 1}
 WAYPOINT_MODE = {"strict": 0, "frozen": 1}
@@ -82,6 +82,7 @@ SYMBOLS = {
     "mppi_comm_init": (C.c_int, [_H, C.c_void_p, C.c_int32, C.c_int32]),
     "mppi_comm_p2p_export": (C.c_int, [_H, C.c_int32, C.c_void_p]),
     "mppi_comm_p2p_open": (C.c_int, [_H, C.c_void_p, C.c_int32, C.c_int32]),
+    "mppi_comm_p2p_trace": (C.c_int, [_H, C.POINTER(C.c_uint64)]),
     "mppi_set_timing": (C.c_int, [_H, C.c_int32]),
     "mppi_get_timings": (C.c_int, [_H, C.POINTER(MppiTimings)]),
     "mppi_abi_version": (C.c_int, []),

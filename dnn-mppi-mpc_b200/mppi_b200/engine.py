@@ -272,6 +272,12 @@ class MPPIEngine:
         buf = C.create_string_buffer(handles, 64 * world)
         self._ck(self.lib.mppi_comm_p2p_open(self._h, buf, rank, world), "mppi_comm_p2p_open")
 
+    def comm_p2p_trace(self):
+        """%globaltimer stamps (ns) of the last fused exchange: local merge done, words stored, all ranks seen, updated."""
+        t = (C.c_uint64 * 4)()
+        self._ck(self.lib.mppi_comm_p2p_trace(self._h, t), "mppi_comm_p2p_trace")
+        return [int(v) for v in t]
+
     @staticmethod
     def comm_unique_id() -> bytes:
         lib = _lib.load()

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define MPPI_ABI_VERSION 2
+#define MPPI_ABI_VERSION 3
 
 typedef struct mppi_handle_s *mppi_handle_t;
 
@@ -37,7 +37,8 @@ enum mppi_status {
     MPPI_E_NCCL = -3,         /* NCCL error */
     MPPI_E_STATE = -4,        /* call order: path / nominal / MLP weights not set yet */
     MPPI_E_UNSUPPORTED = -5,  /* mode combination not implemented by this build */
-    MPPI_E_NOMEM = -6
+    MPPI_E_NOMEM = -6,
+    MPPI_E_NUMERIC = -7       /* non-finite sample costs (NaN/inf state or residual, missed cluster hand-off): tick NOT applied */
 };
 
 enum mppi_model {
@@ -245,13 +246,20 @@ int mppi_step_batched(mppi_handle_t h, const float *d_x0, uint64_t seed, uint64_
 int mppi_comm_get_unique_id(void *out128);
 int mppi_comm_init(mppi_handle_t h, const void *nccl_unique_id, int32_t rank, int32_t world);
 /* The same exchange fused INTO the tick kernel over NVLink peer memory (no NCCL call, one launch per tick): every
- * rank's last CTA stores its (min, sum w, sum w*eps) triple straight into every peer's exchange buffer, raises a
- * sequence flag, waits for the peers' flags and finishes the merge.  Set-up: each rank exports its buffer with
- * mppi_comm_p2p_export (64-byte cudaIpcMemHandle_t), the handles are all-gathered by the caller (any transport) and
- * handed to mppi_comm_p2p_open as world*64 bytes in rank order.  One process per GPU, all GPUs on one NVLink domain. */
+ * rank's last CTA writes each word of its (min, sum w, sum w*eps) triple straight into every peer's exchange buffer as
+ * one 8-byte store (tick sequence number, float bits) -- the flag travels with the datum, so there is no system fence
+ * and no second round trip -- polls its own buffer until every rank's words carry this tick's number, and merges them
+ * in rank order (bit-identical nominal on all ranks).  Set-up: each rank exports its buffer with mppi_comm_p2p_export
+ * (64-byte cudaIpcMemHandle_t), the handles are all-gathered by the caller (any transport) and handed to
+ * mppi_comm_p2p_open as world*64 bytes in rank order.  One process per GPU, all GPUs on one NVLink domain.
+ * A peer that has not published within MPPI_P2P_TIMEOUT_MS (environment, default 2000) fails THAT tick: the nominal
+ * and the waypoint index are left untouched and mppi_step / mppi_synchronize return MPPI_E_NCCL once. */
 #define MPPI_MAX_PEERS 8
 int mppi_comm_p2p_export(mppi_handle_t h, int32_t world, void *ipc_handle_out64);
 int mppi_comm_p2p_open(mppi_handle_t h, const void *ipc_handles, int32_t rank, int32_t world);
+/* Diagnostics of the last fused exchange on this rank: %globaltimer stamps (ns) of [0] local merge done, [1] words
+ * stored, [2] every rank's words seen, [3] nominal updated.  [2]-[1] is the wait for the slowest rank. */
+int mppi_comm_p2p_trace(mppi_handle_t h, uint64_t stamps_out[4]);
 
 int mppi_set_timing(mppi_handle_t h, int32_t enabled);
 int mppi_get_timings(mppi_handle_t h, mppi_timings_t *out);

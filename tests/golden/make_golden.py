@@ -165,6 +165,57 @@ def make_mlp_golden():
     print("wrote", fn, "%.1f KB" % (os.path.getsize(fn) / 1024))
 
 
+# ---- BASELINE config 1 at its literal size: K=1000, T=30, seeds 0-4, param_exploration in {1e-4, 0.05} ----
+C1_K, C1_T, C1_TICKS = 1000, 30, 200
+C1_S_TICKS = list(range(0, 10)) + list(range(10, 200, 10))      # ticks whose per-sample costs are stored (29 of 200)
+
+
+def c1_eps(rng, K=C1_K, T=C1_T):
+    """Noise of one C1 tick: eps ~ N(0, diag(0.1, 0.01)) from np.random.default_rng(seed), drawn as standard normals times
+    the Cholesky factor (PCG64 + ziggurat: the stream is stable across numpy versions, unlike multivariate_normal's SVD
+    signs), rounded to float32 -- regenerated by the tests from the seed, so the 48 MB of noise per case is not stored."""
+    return (rng.standard_normal((K, T, 2)) * np.sqrt(np.array([0.1, 0.01]))).astype(np.float32)
+
+
+def _c1_case(args):
+    seed, pe = args
+    ref = ref_loader.load_reference()
+    path = spline_path(ref)
+    sigma_dd = np.array([[0.1, 0.0], [0.0, 0.01]])
+    w_dd = np.array([5.0, 5.0, 10.0])
+    kw = dict(delta_t=0.1, max_speed=5.0, max_omega=3.14, num_samples_K=C1_K, num_horizons_T=C1_T,
+              param_exploration=pe, param_lambda=1.0, param_alpha=0.2)
+    ctrl = ref["MPPIAlgorithms"](ref_path=path, sigma=sigma_dd, stage_cost_weight=w_dd, terminal_cost_weight=w_dd,
+                                 visualize_optimal_traj=False, visualze_sampled_trajs=False, **kw)
+    rng = np.random.default_rng(seed)
+    eps_list = [c1_eps(rng) for _ in range(C1_TICKS)]
+
+    def plant(x, u):
+        return ref["DifferentialDrive"](x).update_state(0.1, x, u)      # controllers/mppi_differential_drive.py:33-40
+    rec = run_ticks(ctrl, "prev_way_point_idx", [[0, 0, 0]], eps_list, plant=plant)
+    out = dict(x0=rec["x0"], idx0=rec["idx0"].astype(np.int32), idx_after=rec["idx_after"].astype(np.int32),
+               u0=rec["u0"], U0=rec["U0"].astype(np.float32), U_after=rec["U_after"],
+               S=rec["S"][C1_S_TICKS].astype(np.float64), S_ticks=np.array(C1_S_TICKS, dtype=np.int32),
+               w_eps=rec["w_eps"][C1_S_TICKS])
+    meta = dict(kind="diffdrive", seed=seed, numpy=np.__version__, generator="tests/golden/make_golden.py c1",
+                noise="tests/golden/make_golden.py:c1_eps(np.random.default_rng(seed)), one call per tick",
+                source="unmodified controllers/mppi_differential_drive.py:MPPIAlgorithms + DifferentialDrive.update_state, "
+                       "200-tick closed loop from (0,0,0) on the spline course", **kw)
+    tag = "1e-4" if pe == 1e-4 else "%g" % pe
+    fn = os.path.join(HERE, "c1_K1000_T30_seed%d_pe%s.npz" % (seed, tag))
+    np.savez_compressed(fn, meta=json.dumps(meta), path=path, **out)
+    return fn, os.path.getsize(fn) / 1024
+
+
+def make_c1_literal(seeds=(0, 1, 2, 3, 4), pes=(1e-4, 0.05)):
+    """~1 s per reference tick: 10 cases x 200 ticks, one process per case."""
+    import multiprocessing as mp
+    cases = [(s, pe) for s in seeds for pe in pes]
+    with mp.get_context("fork").Pool(min(len(cases), os.cpu_count() or 1)) as pool:
+        for fn, kb in pool.imap_unordered(_c1_case, cases):
+            print("wrote", fn, "%.1f KB" % kb, flush=True)
+
+
 def make_spline_golden():
     """Courses of the reference's own calc_spline_course (path_generator/cubic_spline_planner.py:311-323) for a few
     waypoint sets (4-12 waypoints, spacings 0.05-0.25): the pin of oracle/spline_oracle.py and, through it, of the
@@ -311,5 +362,7 @@ if __name__ == "__main__":
         make_mlp_golden()
     elif len(sys.argv) > 1 and sys.argv[1] == "spline":
         make_spline_golden()
+    elif len(sys.argv) > 1 and sys.argv[1] == "c1":
+        make_c1_literal()
     else:
         main()

@@ -25,7 +25,7 @@ def test_header_symbols_are_exported_and_bound():
         assert hasattr(lib, n), "libmppi_b200.so does not export %s" % n
         assert n in _lib.SYMBOLS, "ctypes binding table misses %s" % n
     assert sorted(_lib.SYMBOLS) == names
-    assert lib.mppi_abi_version() == 2
+    assert lib.mppi_abi_version() == _lib.MPPI_ABI_VERSION == 3
 
 
 def test_config_struct_layout_matches_header():
@@ -34,7 +34,7 @@ def test_config_struct_layout_matches_header():
     assert C.sizeof(_lib.MppiConfig) == 16 * 4 + 32 * 8
     c = _lib.MppiConfig()
     _lib.load().mppi_default_config(C.byref(c))
-    assert (c.abi_version, c.K, c.T, c.window, c.n_robots, c.cost_kind) == (2, 1000, 30, 20, 1, 0)
+    assert (c.abi_version, c.K, c.T, c.window, c.n_robots, c.cost_kind) == (3, 1000, 30, 20, 1, 0)
     assert abs(c.dt - 0.1) < 1e-15 and abs(c.sigma[3] - 0.01) < 1e-15 and c.vehicle_l == 4.0
     assert c.soft_obs_weight == 100.0 and c.soft_obs_safety == 2.0 and c.ctrl_w[1] == 0.1      # trailing fields line up
 

@@ -38,6 +38,7 @@
 // activations and of every accumulator quarter, so MMA start and epilogue tail are both short).
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -49,6 +50,22 @@
 #include "mppi_mlp.h"
 
 namespace {
+
+// Operand type of the hidden GEMM(s).  fp16 (default): the A operand is a tanh output in [-1, 1] and trained weights are
+// O(1), so half precision's 11-bit significand applies with no range problem -- 8x smaller rounding error than bf16 at the
+// same tensor-core rate (weights beyond +-65504 are refused on the host).  -DMPPI_MLP_F16=0 restores bf16 (A/B measurements).
+#ifndef MPPI_MLP_F16
+#define MPPI_MLP_F16 1
+#endif
+#if MPPI_MLP_F16
+typedef __half mlp_op_t;
+#define MLP_TMAP_DTYPE CU_TENSOR_MAP_DATA_TYPE_FLOAT16
+#define MLP_UMMA_FMT 0u
+#else
+typedef __nv_bfloat16 mlp_op_t;
+#define MLP_TMAP_DTYPE CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
+#define MLP_UMMA_FMT 1u
+#endif
 
 constexpr int HID = 512;
 constexpr int TILE_M = 128;
@@ -142,8 +159,8 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
     return d;
 }
 
-// kind::f16 instruction descriptor: BF16 x BF16 -> F32, K-major A and B, M=128, N=128
-constexpr uint32_t UMMA_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N_MMA >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
+// kind::f16 instruction descriptor: F16 x F16 (or BF16 x BF16) -> F32, K-major A and B, M=128, N=128
+constexpr uint32_t UMMA_IDESC = (1u << 4) | (MLP_UMMA_FMT << 7) | (MLP_UMMA_FMT << 10) | ((uint32_t)(N_MMA >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
 
 // A operand in tensor memory (128 lanes x 8 packed bf16x2 columns per K=16 step), B in shared memory
 __device__ __forceinline__ void umma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t accumulate) {
@@ -188,17 +205,27 @@ __device__ __forceinline__ float tanh_approx(float x) {
     asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
-// tanh of two FP32 pre-activations -> packed bf16x2 (one cvt + one MUFU for two elements)
-__device__ __forceinline__ uint32_t tanh_bf16x2(float lo, float hi) {
+// two FP32 values -> packed half-precision operand pair (lo in the low half)
+__device__ __forceinline__ uint32_t pack_op2(float lo, float hi) {
+    uint32_t p;
+#if MPPI_MLP_F16
+    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(p) : "f"(hi), "f"(lo));
+#else
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(p) : "f"(hi), "f"(lo));
+#endif
+    return p;
+}
+// tanh of two FP32 pre-activations -> packed operand pair.  fp16: FP32 MUFU.TANH on the unrounded pre-activation, ONE
+// rounding at the end (tanh.approx.bf16x2 rounds the input first and is two MUFU ops anyway, so this costs the same)
+__device__ __forceinline__ uint32_t tanh_op2(float lo, float hi) {
+#if MPPI_MLP_F16
+    return pack_op2(tanh_approx(lo), tanh_approx(hi));
+#else
     uint32_t p, y;
     asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(p) : "f"(hi), "f"(lo));
     asm("tanh.approx.bf16x2 %0, %1;" : "=r"(y) : "r"(p));
     return y;
-}
-__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
-    uint32_t p;
-    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(p) : "f"(hi), "f"(lo));
-    return p;
+#endif
 }
 // one lane of a CONVERGED warp (elect.sync): the MMA / TMA issue loops run warp-converged with the issuing
 // instructions predicated on this, so ptxas emits each UTCHMMA once with uniform-register operands instead of the
@@ -563,7 +590,7 @@ mppi_mlp_rollout_kernel(const __grid_constant__ TickArgs a, const __grid_constan
                                 pa = fmaf(wu.x, st.w, fmaf(wu.y, su1, pa));
                                 pb = fmaf(wu.z, st.w, fmaf(wu.w, su1, pb));
                             }
-                            pk[p] = tanh_bf16x2(pa, pb);
+                            pk[p] = tanh_op2(pa, pb);
                         }
                         tmem_st4(tmem + ((uint32_t)(q * 32) << 16) + TMEM_A_COL + (uint32_t)(col >> 1), pk[0], pk[1], pk[2], pk[3]);
                     }
@@ -721,7 +748,7 @@ mppi_mlp_rollout_kernel(const __grid_constant__ TickArgs a, const __grid_constan
                                 pa = fmaf(wu.x, st.w, fmaf(wu.y, su1, pa));
                                 pb = fmaf(wu.z, st.w, fmaf(wu.w, su1, pb));
                             }
-                            pk[p] = tanh_bf16x2(pa, pb);
+                            pk[p] = tanh_op2(pa, pb);
                         }
                         tmem_st4(tmem + ((uint32_t)(q * 32) << 16) + TMEM_A_COL + (uint32_t)(col >> 1), pk[0], pk[1], pk[2], pk[3]);
                     }
@@ -764,10 +791,10 @@ mppi_mlp_rollout_kernel(const __grid_constant__ TickArgs a, const __grid_constan
                             const float4 ba = __ldg(reinterpret_cast<const float4 *>(g_bh + col + 8 * c));
                             const float4 bb = __ldg(reinterpret_cast<const float4 *>(g_bh + col + 8 * c + 4));
                             uint4 pk;
-                            pk.x = pack_bf16x2(tanh_approx(__uint_as_float(v[8 * c + 0]) + ba.x), tanh_approx(__uint_as_float(v[8 * c + 1]) + ba.y));
-                            pk.y = pack_bf16x2(tanh_approx(__uint_as_float(v[8 * c + 2]) + ba.z), tanh_approx(__uint_as_float(v[8 * c + 3]) + ba.w));
-                            pk.z = pack_bf16x2(tanh_approx(__uint_as_float(v[8 * c + 4]) + bb.x), tanh_approx(__uint_as_float(v[8 * c + 5]) + bb.y));
-                            pk.w = pack_bf16x2(tanh_approx(__uint_as_float(v[8 * c + 6]) + bb.z), tanh_approx(__uint_as_float(v[8 * c + 7]) + bb.w));
+                            pk.x = pack_op2(tanh_approx(__uint_as_float(v[8 * c + 0]) + ba.x), tanh_approx(__uint_as_float(v[8 * c + 1]) + ba.y));
+                            pk.y = pack_op2(tanh_approx(__uint_as_float(v[8 * c + 2]) + ba.z), tanh_approx(__uint_as_float(v[8 * c + 3]) + ba.w));
+                            pk.z = pack_op2(tanh_approx(__uint_as_float(v[8 * c + 4]) + bb.x), tanh_approx(__uint_as_float(v[8 * c + 5]) + bb.y));
+                            pk.w = pack_op2(tanh_approx(__uint_as_float(v[8 * c + 6]) + bb.z), tanh_approx(__uint_as_float(v[8 * c + 7]) + bb.w));
                             *reinterpret_cast<uint4 *>(dst + (((c16 + c) ^ (row & 7)) << 4)) = pk;
                         }
                         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> the tensor core's reads
@@ -840,7 +867,7 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32
 
 struct MlpState {
     int K = 0, T = 0, n_sm = 148;
-    __nv_bfloat16 *d_w2 = nullptr;        // n_gemm x [512 out][512 in] bf16, K-major B operand (layers stacked along the rows)
+    mlp_op_t *d_w2 = nullptr;             // n_gemm x [512 out][512 in] fp16 (bf16), K-major B operand (layers stacked along the rows)
     float4 *d_w01 = nullptr, *d_w3 = nullptr;
     float2 *d_w01u = nullptr;             // control columns of the folded first layer (n_in = 5)
     float *d_b3 = nullptr;
@@ -861,7 +888,7 @@ MlpState *mlp_create(int K, int T) {
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&m->n_sm, cudaDevAttrMultiProcessorCount, dev);
-    if (cudaMalloc(&m->d_w2, sizeof(__nv_bfloat16) * 2 * HID * HID) != cudaSuccess ||
+    if (cudaMalloc(&m->d_w2, sizeof(mlp_op_t) * 2 * HID * HID) != cudaSuccess ||
         cudaMalloc(&m->d_bh, sizeof(float) * HID) != cudaSuccess ||
         cudaMalloc(&m->d_hand, sizeof(float) * (size_t)(m->n_sm / 2 + 1) * 2 * 2 * 6 * TILE_M) != cudaSuccess ||
         cudaMalloc(&m->d_hand_flag, sizeof(unsigned int) * ((size_t)(m->n_sm / 2 + 1) * 2 + 1)) != cudaSuccess ||
@@ -923,9 +950,17 @@ cudaError_t mlp_set_weights(MlpState *m, int n_in, int n_hidden, const float *co
         const double o0 = out_scale ? out_scale[0] : 1.0, o1 = out_scale ? out_scale[1] : 1.0, o2 = out_scale ? out_scale[2] : 1.0;
         w3[j] = make_float4(b[l_last][j], (float)(W[l_out][0 * HID + j] * o0), (float)(W[l_out][1 * HID + j] * o1), (float)(W[l_out][2 * HID + j] * o2));
     }
-    std::vector<__nv_bfloat16> w2((size_t)n_gemm * HID * HID);
+    std::vector<mlp_op_t> w2((size_t)n_gemm * HID * HID);
     for (int g = 0; g < n_gemm; ++g)
-        for (size_t i = 0; i < (size_t)HID * HID; ++i) w2[(size_t)g * HID * HID + i] = __float2bfloat16(W[2 + g][i]);
+        for (size_t i = 0; i < (size_t)HID * HID; ++i) {
+            const float w = W[2 + g][i];
+#if MPPI_MLP_F16
+            if (!(std::fabs(w) <= 65504.f)) return cudaErrorInvalidValue;      // outside half precision's range (or NaN)
+            w2[(size_t)g * HID * HID + i] = __float2half_rn(w);
+#else
+            w2[(size_t)g * HID * HID + i] = __float2bfloat16(w);
+#endif
+        }
     float b3[4] = {0.f, 0.f, 0.f, 0.f};
     for (int c = 0; c < 3; ++c) b3[c] = (float)((double)b[l_out][c] * (out_scale ? out_scale[c] : 1.0) + (out_mean ? out_mean[c] : 0.0));
     cudaError_t e;
@@ -933,7 +968,7 @@ cudaError_t mlp_set_weights(MlpState *m, int n_in, int n_hidden, const float *co
     if ((e = cudaMemcpyAsync(m->d_w3, w3.data(), sizeof(float4) * HID, cudaMemcpyHostToDevice, st)) != cudaSuccess) return e;
     if ((e = cudaMemcpyAsync(m->d_w01u, w01u.data(), sizeof(float2) * HID, cudaMemcpyHostToDevice, st)) != cudaSuccess) return e;
     if ((e = cudaMemcpyAsync(m->d_b3, b3, sizeof(b3), cudaMemcpyHostToDevice, st)) != cudaSuccess) return e;
-    if ((e = cudaMemcpyAsync(m->d_w2, w2.data(), sizeof(__nv_bfloat16) * w2.size(), cudaMemcpyHostToDevice, st)) != cudaSuccess) return e;
+    if ((e = cudaMemcpyAsync(m->d_w2, w2.data(), sizeof(mlp_op_t) * w2.size(), cudaMemcpyHostToDevice, st)) != cudaSuccess) return e;
     if (n_gemm == 2 && (e = cudaMemcpyAsync(m->d_bh, b[2], sizeof(float) * HID, cudaMemcpyHostToDevice, st)) != cudaSuccess) return e;
     if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return e;
     // TMA descriptor of W2: inner dim = K (512 bf16, contiguous), outer dim = N (512 rows); 64 x 256 boxes, 128B swizzle
@@ -942,10 +977,10 @@ cudaError_t mlp_set_weights(MlpState *m, int n_in, int n_hidden, const float *co
     if ((e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres)) != cudaSuccess) return e;
     if (!fn || qres != cudaDriverEntryPointSuccess) return cudaErrorNotSupported;
     const cuuint64_t dims[2] = {HID, (cuuint64_t)n_gemm * HID};
-    const cuuint64_t strides[1] = {HID * sizeof(__nv_bfloat16)};
+    const cuuint64_t strides[1] = {HID * sizeof(mlp_op_t)};
     const cuuint32_t box[2] = {KCH, N_MMA};
     const cuuint32_t estr[2] = {1, 1};
-    CUresult r = ((PFN_encodeTiled)fn)(&m->w2_map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, m->d_w2, dims, strides, box, estr,
+    CUresult r = ((PFN_encodeTiled)fn)(&m->w2_map, MLP_TMAP_DTYPE, 2, m->d_w2, dims, strides, box, estr,
                                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                                       CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return cudaErrorInvalidValue;

@@ -35,7 +35,31 @@ __global__ void __launch_bounds__(256) fma_probe_kernel(float *out, int iters, f
     if (s == 123.456f) out[0] = s;                    // keeps the chains alive; never true
 }
 
+// the hardware tanh the learned-dynamics kernel applies (MUFU.TANH via tanh.approx.f32), exposed so the parity tests can
+// state how far it is from the exact function (PTX: max relative error 2^-11)
+__global__ void tanh_probe_kernel(const float *in, float *out, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float y;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(in[i]));
+    out[i] = y;
+}
+
 }  // namespace
+
+extern "C" int mppi_probe_tanh(int32_t device, const float *in, float *out, int32_t n) {
+    if (!in || !out || n < 1) return MPPI_E_BADARG;
+    if (cudaSetDevice(device) != cudaSuccess) return MPPI_E_CUDA;
+    float *d = nullptr;
+    if (cudaMalloc(&d, sizeof(float) * 2 * (size_t)n) != cudaSuccess) return MPPI_E_NOMEM;
+    cudaError_t e = cudaMemcpy(d, in, sizeof(float) * n, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) {
+        tanh_probe_kernel<<<(n + 255) / 256, 256>>>(d, d + n, n);
+        e = cudaMemcpy(out, d + n, sizeof(float) * n, cudaMemcpyDeviceToHost);
+    }
+    cudaFree(d);
+    return e == cudaSuccess ? MPPI_OK : MPPI_E_CUDA;
+}
 
 extern "C" int mppi_probe_fp32_peak(int32_t device, int32_t packed, double *tflops_out) {
     if (!tflops_out) return MPPI_E_BADARG;

@@ -87,6 +87,7 @@ SYMBOLS = {
     "mppi_get_timings": (C.c_int, [_H, C.POINTER(MppiTimings)]),
     "mppi_abi_version": (C.c_int, []),
     "mppi_probe_fp32_peak": (C.c_int, [C.c_int32, C.c_int32, C.POINTER(C.c_double)]),
+    "mppi_probe_tanh": (C.c_int, [C.c_int32, _PF, _PF, C.c_int32]),
     "mppi_mlp_schedule_cut": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
 }
 

@@ -268,6 +268,10 @@ int mppi_abi_version(void);
  * (packed = 0) or FFMA2 (packed = 1) loop filling every SM of `device` -- the measured denominator of the FP32 roofline the
  * analytic-dynamics kernels are bound by (MEASURED_PEAKS.json has no FP32 entry). */
 int mppi_probe_fp32_peak(int32_t device, int32_t packed, double *tflops_out);
+/* Measurement aid: out[i] = the hardware tanh (tanh.approx.f32, MUFU.TANH) of in[i], n HOST floats each -- the activation
+ * the learned-dynamics kernel applies where dnn/simple_mlp.py:20-21 calls torch.tanh; lets the parity tests state its
+ * distance from the exact function instead of assuming it. */
+int mppi_probe_tanh(int32_t device, const float *in, float *out, int32_t n);
 /* Host-side view of the learned-dynamics kernel's balanced schedule (no reference counterpart, no GPU needed): the first
  * unit-step, in unit-major order u * T + t, that cluster `c` of `n_clusters` owns when `n_units` units (quads of 4 tiles in the
  * ping-pong schedule, pairs of 2 tiles otherwise) x T timesteps are dealt evenly; c = n_clusters gives the total.  The same

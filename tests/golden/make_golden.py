@@ -16,6 +16,8 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.join(HERE, "..", ".."))
 from oracle import ref_loader  # noqa: E402
+sys.path.insert(0, os.path.join(HERE, ".."))
+from golden_util import c1_eps  # noqa: E402  (the tests regenerate the C1 noise with the same function)
 
 
 def spline_path(ref):
@@ -170,13 +172,6 @@ C1_K, C1_T, C1_TICKS = 1000, 30, 200
 C1_S_TICKS = list(range(0, 10)) + list(range(10, 200, 10))      # ticks whose per-sample costs are stored (29 of 200)
 
 
-def c1_eps(rng, K=C1_K, T=C1_T):
-    """Noise of one C1 tick: eps ~ N(0, diag(0.1, 0.01)) from np.random.default_rng(seed), drawn as standard normals times
-    the Cholesky factor (PCG64 + ziggurat: the stream is stable across numpy versions, unlike multivariate_normal's SVD
-    signs), rounded to float32 -- regenerated by the tests from the seed, so the 48 MB of noise per case is not stored."""
-    return (rng.standard_normal((K, T, 2)) * np.sqrt(np.array([0.1, 0.01]))).astype(np.float32)
-
-
 def _c1_case(args):
     seed, pe = args
     ref = ref_loader.load_reference()
@@ -188,17 +183,17 @@ def _c1_case(args):
     ctrl = ref["MPPIAlgorithms"](ref_path=path, sigma=sigma_dd, stage_cost_weight=w_dd, terminal_cost_weight=w_dd,
                                  visualize_optimal_traj=False, visualze_sampled_trajs=False, **kw)
     rng = np.random.default_rng(seed)
-    eps_list = [c1_eps(rng) for _ in range(C1_TICKS)]
+    eps_list = [c1_eps(rng, C1_K, C1_T) for _ in range(C1_TICKS)]
 
     def plant(x, u):
         return ref["DifferentialDrive"](x).update_state(0.1, x, u)      # controllers/mppi_differential_drive.py:33-40
     rec = run_ticks(ctrl, "prev_way_point_idx", [[0, 0, 0]], eps_list, plant=plant)
     out = dict(x0=rec["x0"], idx0=rec["idx0"].astype(np.int32), idx_after=rec["idx_after"].astype(np.int32),
-               u0=rec["u0"], U0=rec["U0"].astype(np.float32), U_after=rec["U_after"],
+               u0=rec["u0"], U_after=rec["U_after"],            # the nominal before tick i is U_after[i-1] (zeros for i = 0)
                S=rec["S"][C1_S_TICKS].astype(np.float64), S_ticks=np.array(C1_S_TICKS, dtype=np.int32),
                w_eps=rec["w_eps"][C1_S_TICKS])
     meta = dict(kind="diffdrive", seed=seed, numpy=np.__version__, generator="tests/golden/make_golden.py c1",
-                noise="tests/golden/make_golden.py:c1_eps(np.random.default_rng(seed)), one call per tick",
+                noise="tests/golden_util.py:c1_eps(np.random.default_rng(seed)), one call per tick",
                 source="unmodified controllers/mppi_differential_drive.py:MPPIAlgorithms + DifferentialDrive.update_state, "
                        "200-tick closed loop from (0,0,0) on the spline course", **kw)
     tag = "1e-4" if pe == 1e-4 else "%g" % pe
@@ -214,6 +209,55 @@ def make_c1_literal(seeds=(0, 1, 2, 3, 4), pes=(1e-4, 0.05)):
     with mp.get_context("fork").Pool(min(len(cases), os.cpu_count() or 1)) as pool:
         for fn, kb in pool.imap_unordered(_c1_case, cases):
             print("wrote", fn, "%.1f KB" % kb, flush=True)
+
+
+def make_trained_mlp_golden():
+    """SURVEY.md 8f row 4 / VERDICT r1 item 1b: the reference's TRAINED residual checkpoints and their StandardScaler
+    statistics as plain arrays (category (b) test fixtures -- data the reference ships, not code), each with forward passes
+    of the reference's own torch class + sklearn scalers (test/test_diff_dyna_eval.py:54-56 composition) on 64 inputs, so
+    the GPU box can pin the oracle to the reference without the reference tree.
+      mlp_diff_300x100.pth          + scalers_mlp_diff_300x100_20_l.pth      two hidden layers
+                                      (simulation/bullet_differential_drive_dnn.py:37-60)
+      mlp_diff_300x100_3l_mppi.pth  + scalers_mlp_diff_300x100_3l_mppi.pth   three hidden layers
+                                      (train/train_diff_mlp.py:13-36)"""
+    import warnings
+    import torch
+    ref = ref_loader.load_reference_mlps()
+    root = ref_loader.REFERENCE_ROOT
+    for tag, ckpt, scalers, cls_key in (("mlp_diff_300x100", "mlp_diff_300x100.pth", "scalers_mlp_diff_300x100_20_l.pth", "MLP5"),
+                                        ("mlp_diff_300x100_3l_mppi", "mlp_diff_300x100_3l_mppi.pth",
+                                         "scalers_mlp_diff_300x100_3l_mppi.pth", "MLP5_3L")):
+        sd = torch.load(os.path.join(root, "saved_models", ckpt), map_location="cpu")
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            sc = torch.load(os.path.join(root, "saved_models", scalers), weights_only=False)
+        n_hidden = 3 if cls_key == "MLP5_3L" else 2
+        names = ["input_layer"] + ["hidden_layer.%d" % i for i in range(n_hidden)] + ["out_layer"]
+        out = {}
+        for i, n in enumerate(names):
+            out["W%d" % i] = sd[n + ".weight"].numpy().astype(np.float32)
+            out["b%d" % i] = sd[n + ".bias"].numpy().astype(np.float32)
+        out["in_mean"] = np.concatenate([sc["state_scaler"].mean_, sc["control_scaler"].mean_])
+        out["in_scale"] = np.concatenate([sc["state_scaler"].scale_, sc["control_scaler"].scale_])
+        out["out_mean"], out["out_scale"] = sc["error_scaler"].mean_, sc["error_scaler"].scale_
+        net = ref[cls_key](5) if cls_key == "MLP5_3L" else ref[cls_key]()
+        net.load_state_dict(sd)
+        net = net.double()
+        X = np.random.default_rng(0).normal(0, 1.0, (64, 5)) * [3.0, 2.0, 1.0, 1.0, 1.5]
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            xin = np.concatenate([sc["state_scaler"].transform(X[:, :3]), sc["control_scaler"].transform(X[:, 3:])], axis=1)
+            with torch.no_grad():
+                Y = sc["error_scaler"].inverse_transform(net(torch.from_numpy(xin)).numpy())
+        out["X"], out["Y_ref"] = X, Y
+        out["meta"] = json.dumps(dict(checkpoint="saved_models/" + ckpt, scalers="saved_models/" + scalers, n_hidden=n_hidden,
+                                      torch=torch.__version__, numpy=np.__version__,
+                                      source="reference checkpoint (float32 weights verbatim) + forward passes of the unmodified "
+                                             "reference torch class in float64 with the sklearn scalers applied as "
+                                             "test/test_diff_dyna_eval.py:54-56 does"))
+        fn = os.path.join(HERE, "trained_" + tag + ".npz")
+        np.savez_compressed(fn, **out)
+        print("wrote", fn, "%.1f KB" % (os.path.getsize(fn) / 1024))
 
 
 def make_spline_golden():
@@ -362,6 +406,8 @@ if __name__ == "__main__":
         make_mlp_golden()
     elif len(sys.argv) > 1 and sys.argv[1] == "spline":
         make_spline_golden()
+    elif len(sys.argv) > 1 and sys.argv[1] == "trained":
+        make_trained_mlp_golden()
     elif len(sys.argv) > 1 and sys.argv[1] == "c1":
         make_c1_literal()
     else:

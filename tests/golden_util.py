@@ -71,3 +71,43 @@ def rel_err(a, b, floor=1e-12):
     a = np.asarray(a, np.float64)
     b = np.asarray(b, np.float64)
     return float(np.max(np.abs(a - b) / np.maximum(np.abs(b), floor))) if a.size else 0.0
+
+
+# ---- BASELINE config 1 at its literal size: c1_K1000_T30_seed{0..4}_pe{1e-4,0.05}.npz ------------------------
+C1_SEEDS, C1_PES = (0, 1, 2, 3, 4), ("1e-4", "0.05")
+
+
+def c1_eps(rng, K=1000, T=30):
+    """Noise of one C1 tick: eps ~ N(0, diag(0.1, 0.01)) from np.random.default_rng(seed), drawn as standard normals times
+    the Cholesky factor (PCG64 + ziggurat: the stream is stable across numpy versions, unlike multivariate_normal's SVD
+    signs), rounded to float32.  make_golden.py fed exactly these values to the reference class; the tests regenerate
+    them from the seed, so the 48 MB of noise per case is not stored."""
+    return (rng.standard_normal((K, T, 2)) * np.sqrt(np.array([0.1, 0.01]))).astype(np.float32)
+
+
+class C1Golden:
+    """One 200-tick closed loop of the unmodified reference class at K=1000, T=30 (x0, idx, u0, U for every tick; the
+    per-sample costs S for the ticks listed in S_ticks)."""
+
+    def __init__(self, seed, pe_tag):
+        z = np.load(os.path.join(GOLDEN_DIR, "c1_K1000_T30_seed%d_pe%s.npz" % (seed, pe_tag)))
+        self.meta = json.loads(str(z["meta"]))
+        self.path = z["path"]
+        self.z = {k: z[k] for k in z.files if k not in ("meta", "path")}
+        self.n_ticks = self.z["x0"].shape[0]
+        self.seed = seed
+
+    def spec(self, **override):
+        m = self.meta
+        s = orc.diffdrive_spec(K=m["num_samples_K"], T=m["num_horizons_T"], dt=m["delta_t"], max_speed=m["max_speed"],
+                               max_omega=m["max_omega"], param_exploration=m["param_exploration"],
+                               param_lambda=m["param_lambda"], param_alpha=m["param_alpha"])
+        for k, v in override.items():
+            setattr(s, k, v)
+        return s
+
+    def eps_stream(self):
+        """Yields the noise of tick 0, 1, 2, ... (one generator call per tick, as the fixture was made)."""
+        rng = np.random.default_rng(self.seed)
+        while True:
+            yield c1_eps(rng, self.meta["num_samples_K"], self.meta["num_horizons_T"])

@@ -56,7 +56,7 @@ def test_config1_racecar_obstacles_K16384_H50():
 def test_config2_mlp_K65536_H30_random_subset():
     """configs[2]: learned dynamics (dnn/simple_mlp shapes, random-init weights), K=65536, H=30: per-sample costs of
     a random subset against the FP64 oracle, then the full tick's update against the oracle update fed the device's
-    own costs (the update kernel is exact to 2e-5; the costs carry the bf16 GEMM tolerance)."""
+    own costs (the update kernel is exact to 2e-5; the costs carry the fp16 GEMM tolerance)."""
     g = Golden("diffdrive_pe0.05")
     K, T = 65536, 30
     mlp = orc.make_mlp(seed=0, out_scale=0.01)
@@ -81,7 +81,7 @@ def test_config2_mlp_K65536_H30_random_subset():
                                  model="diffdrive_mlp", mlp=mlp)
         So, _, _ = orc.costs_vec(sps, g.path, U.astype(np.float64), 0, x0, eps[torch.from_numpy(sub).cuda()].cpu().numpy().astype(np.float64))
         rel = np.abs(Sg[sub] - So) / np.maximum(np.abs(So), 1e-9)
-        assert np.quantile(rel, 0.99) <= 2e-3 and rel.max() <= 2e-2, (lo, rel.max())
+        assert np.quantile(rel, 0.99) <= 2e-5 and rel.max() <= 2e-2, (lo, np.quantile(rel, 0.99), rel.max())     # fp16 operands
     eng.set_nominal(U)
     eng.set_waypoint_idx(0)
     u0, useq = eng.step(x0, None, seed=9, tick=2)
@@ -148,5 +148,77 @@ def test_mlp_ping_pong_schedule_ragged_tile_counts(K, T):
                                  model="diffdrive_mlp", mlp=mlp)
         So, _, _ = orc.costs_vec(sps, g.path, U.astype(np.float64), 0, x0, eps[torch.from_numpy(ss).cuda()].cpu().numpy().astype(np.float64))
         rel = np.abs(Sg[ss] - So) / np.maximum(np.abs(So), 1e-9)
-        assert np.quantile(rel, 0.99) <= 2e-3 and rel.max() <= 2e-2, (lo, rel.max())
+        assert np.quantile(rel, 0.99) <= 2e-5 and rel.max() <= 2e-2, (lo, np.quantile(rel, 0.99), rel.max())     # fp16 operands
     eng.close()
+
+
+# ---- the reference's TRAINED residuals inside the tensor-core rollout ---------------------------------------
+def _trained(tag):
+    import os
+    from golden_util import GOLDEN_DIR
+    z = np.load(os.path.join(GOLDEN_DIR, "trained_%s.npz" % tag))
+    return {k: z[k].astype(np.float64) for k in z.files if k not in ("meta", "X", "Y_ref")}, z["X"], z["Y_ref"]
+
+
+# (99th percentile, median) of the per-sample relative cost error at K = 65 536, T = 30.  These checkpoints output
+# residuals of ~15 m/s (error_scaler 5.7 / 3.6 / 1.0 on an O(1) network output), so a rollout leaves the path by > 100 m,
+# costs reach 1e6 and every rounding is amplified through 30 steps of a network with a large Lipschitz constant; the
+# bounds are what fp16 operands deliver there (measured on B200, profiles/r2_mlp_parity.txt: p99 4e-4 / 1.1e-3 against
+# FP64, 1.1e-4 / 4e-4 against the device-faithful restatement), with a factor ~2.5 of margin.
+TRAINED_BOUNDS = {"mlp_diff_300x100": dict(fp64=(1e-3, 2e-4), faithful=(3e-4, 5e-5)),
+                  "mlp_diff_300x100_3l_mppi": dict(fp64=(3e-3, 6e-4), faithful=(1e-3, 2e-4))}
+
+
+@pytest.mark.parametrize("tag", ["mlp_diff_300x100", "mlp_diff_300x100_3l_mppi"])
+def test_trained_reference_checkpoints_through_the_tensor_core_rollout(tag):
+    """saved_models/mlp_diff_300x100.pth (two hidden layers, simulation/bullet_differential_drive_dnn.py:37-60) and
+    mlp_diff_300x100_3l_mppi.pth (three, train/train_diff_mlp.py:13-36) with their StandardScaler statistics
+    (test/test_diff_dyna_eval.py:54-56), vendored as tests/golden/trained_*.npz, run through `set_dynamics` of the drop-in
+    class at K = 65 536, T = 30 against BOTH oracles; the oracle itself is first pinned to the reference's own forward."""
+    from mppi_b200.mppi_differential_drive import MPPIAlgorithms
+    mlp, X, Y = _trained(tag)
+    assert np.max(np.abs(orc.mlp_forward(mlp, X[:, :3], X[:, 3:]) - Y)) <= 1e-10 * np.max(np.abs(Y))
+    g = Golden("diffdrive_pe0.05")
+    K, T = 65536, 30
+    n = len([k for k in mlp if k[0] == "W" and k[1:].isdigit()])
+    ctrl = MPPIAlgorithms(delta_t=0.1, ref_path=g.path, max_speed=5.0, max_omega=3.14, num_samples_K=K, num_horizons_T=T,
+                          param_exploration=0.05, param_lambda=1.0, param_alpha=0.2, sigma=np.array([[0.1, 0.0], [0.0, 0.01]]),
+                          stage_cost_weight=np.array([5.0, 5.0, 10.0]), terminal_cost_weight=np.array([5.0, 5.0, 10.0]),
+                          visualize_optimal_traj=False, visualze_sampled_trajs=False, cost_mode="sum", waypoint_mode="frozen",
+                          temperature=2000.0, dynamics={k: v for k, v in mlp.items() if k[0] in "Wb"}, seed=9)
+    names = ["input_layer"] + ["hidden_layer.%d" % i for i in range(n - 2)] + ["out_layer"]
+    sd = {}
+    for i, nm in enumerate(names):                          # what a user of the reference has: the torch state dict
+        sd[nm + ".weight"] = torch.from_numpy(mlp["W%d" % i].astype(np.float32))
+        sd[nm + ".bias"] = torch.from_numpy(mlp["b%d" % i].astype(np.float32))
+    ctrl.set_dynamics(sd, scalers={k: mlp[k] for k in ("in_mean", "in_scale", "out_mean", "out_scale")})
+    eng = ctrl.engine
+    sp = orc.diffdrive_spec(K=K, T=T, param_exploration=0.05, cost_mode="sum", waypoint_mode="frozen", model="diffdrive_mlp", mlp=mlp)
+    sp.temperature = 2000.0
+    eps = torch.zeros(K, T, 2, dtype=torch.float32, device="cuda")
+    eng.generate_noise(eps, seed=9, tick=0)
+    S = torch.zeros(K, dtype=torch.float32, device="cuda")
+    x0 = np.array([0.4, 0.3, 0.5])
+    U = np.random.default_rng(1).normal(0, 0.3, (T, 2)).astype(np.float32)
+    eng.set_nominal(U)
+    eng.rollout_costs(x0, S, None, seed=9, tick=0)
+    Sg = S.cpu().numpy().astype(np.float64)
+    e64 = eps.cpu().numpy().astype(np.float64)
+    S64, _, _ = orc.costs_vec(sp, g.path, U.astype(np.float64), 0, x0, e64)
+    sp.mlp_precision = "f16"
+    Sf, _, _ = orc.costs_vec(sp, g.path, U.astype(np.float64), 0, x0, e64)
+    sp.mlp_precision = None
+    for name, ref in (("fp64", S64), ("faithful", Sf)):
+        rel = np.abs(Sg - ref) / np.abs(ref)
+        p99, med = TRAINED_BOUNDS[tag][name]
+        assert np.quantile(rel, 0.99) <= p99 and np.median(rel) <= med, (tag, name, np.median(rel), np.quantile(rel, 0.99))
+        assert np.mean(rel > 10 * p99) <= 1e-3, (tag, name, np.mean(rel > 10 * p99))      # near-tie waypoint flips only
+    # the full tick through the class: the update is the soft-min of the device's own costs
+    ctrl.u_prev = U
+    ctrl.prev_way_point_idx = 0
+    u0, u, _, _ = ctrl._calc_input_control(x0)
+    spd = orc.diffdrive_spec(K=K, T=T, param_exploration=0.05, cost_mode="sum", waypoint_mode="frozen")
+    spd.temperature = 2000.0
+    o = co.update(spd, g.path, U.astype(np.float64), Sg, eps.cpu().numpy())
+    assert np.max(np.abs(u - o["U_after"])) <= U_ATOL, np.max(np.abs(u - o["U_after"]))
+    assert np.all(np.isfinite(u))

@@ -1,8 +1,14 @@
 """Config 3: differential-drive MPPI whose rollout goes through the simple_mlp residual on the
 tcgen05 tensor cores.  There is no MPPI-through-MLP in the reference: the oracle is
 the reference tick with `_state_transition` replaced by explicit Euler on f + MLP (FP64 numpy).
-The device evaluates the hidden GEMM with bf16 operands / FP32 accumulation and MUFU tanh, so the
-parity bound is looser than for the analytic kernels and is stated here."""
+The device evaluates the hidden GEMM(s) with fp16 operands / FP32 accumulation and the hardware tanh
+(MUFU.TANH), so parity is stated TWICE ("state both"):
+  * loose, against the FP64 oracle (the reference's arithmetic): what a user of the reference sees;
+  * tight, against the DEVICE-FAITHFUL restatement (oracle.mlp_forward_device: same function, the
+    kernel's roundings made explicit, exact tanh) -- a wrong bias, a dropped column group or a
+    misplaced tanh shows up here at 1e-2..1e-1, four orders above the bound;
+and a third time with the hardware's own tanh primitive plugged into the restatement, which removes
+the last difference and pins everything else (accumulation order) at 1e-6."""
 import numpy as np
 import pytest
 
@@ -13,10 +19,28 @@ from golden_util import Golden  # noqa: E402
 from gpu_util import engine_from_spec  # noqa: E402
 from oracle import mppi_oracle as orc  # noqa: E402
 
-# bf16 hidden activations + weights (2^-9 relative each) through a 512-wide layer whose output is scaled by 0.01:
-# observed per-sample cost error ~1e-4 relative; bound at 2e-3
-MLP_COST_RTOL = 2e-3
-MLP_U_ATOL = 2e-3
+# fp16 hidden activations + weights (2^-12 relative each) through 512-wide layers.  Measured on B200 (profiles/
+# r2_mlp_parity.txt): 99 % of the per-sample costs within 6e-7 (output layer scaled by 0.01) / 3e-5 (scaled by 0.5) of the
+# FP64 oracle; the bounds below leave a factor of ~5.  The worst sample is looser: a nearest-waypoint near-tie decided
+# differently changes one sample's cost by up to ~1e-2.
+MLP_COST_RTOL = 2e-5          # 99th percentile, output layer scaled by <= 0.05
+MLP_COST_RTOL_BIG = 2e-4      # 99th percentile, output layer scaled by 0.5 (residual ~ 0.05 m/s per step on its own)
+MLP_FAITHFUL_RTOL = 2e-5      # 99th percentile against the device-faithful restatement, exact tanh, ANY output scale
+MLP_FAITHFUL_HW_RTOL = 5e-6   # the same with the hardware tanh primitive plugged in
+MLP_U_ATOL = 5e-4
+
+
+def hw_tanh(a):
+    """The hardware tanh (tanh.approx.f32) evaluated on the device through the measurement entry point of the C ABI."""
+    from mppi_b200 import _lib
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    out = np.empty_like(a)
+    assert _lib.load().mppi_probe_tanh(0, a.ctypes.data_as(_lib._PF), out.ctypes.data_as(_lib._PF), a.size) == 0
+    return out
+
+
+def _rel(Sg, So):
+    return np.abs(Sg - So) / np.maximum(np.abs(So), 1e-9)
 
 
 def _spec(K, T, cost_mode, mlp):
@@ -71,7 +95,7 @@ def test_mlp_residual_changes_the_rollout():
     Sp, _, _ = orc.costs_vec(sp_plain, g.path, np.zeros((T, 2)), 0, x0, eps.cpu().numpy().astype(np.float64))
     Sg = S.cpu().numpy().astype(np.float64)
     assert np.median(np.abs(Sg - Sp) / Sp) > 0.05
-    assert np.max(np.abs(Sg - So) / So) <= 2e-2          # out_scale 50x larger -> bound 50x/5 looser
+    assert np.quantile(_rel(Sg, So), 0.99) <= MLP_COST_RTOL_BIG and np.max(_rel(Sg, So)) <= 2e-2
     eng.close()
 
 
@@ -296,4 +320,87 @@ def test_mlp_balanced_horizon_split_matches_fp64_oracle_and_static_schedule(K, T
     eng.set_waypoint_idx(0)
     eng.rollout_costs(x0, S, None, seed=9, tick=2)
     assert np.array_equal(S.cpu().numpy().astype(np.float64), out["philox"])
+    eng.close()
+
+
+# ---- the tight half of the parity gate -----------------------------------------------------------------
+def test_hardware_tanh_primitive_is_within_its_documented_error():
+    """tanh.approx.f32 is specified to 2^-11 relative; on B200 it measures ~1e-5.  The kernel's only departure from the
+    device-faithful restatement is this primitive, so its error is stated, not assumed."""
+    x = np.concatenate([np.linspace(-9, 9, 400001), np.random.default_rng(0).normal(0, 1, 200000)]).astype(np.float32)
+    y, ex = hw_tanh(x).astype(np.float64), np.tanh(x.astype(np.float64))
+    rel = np.abs(y - ex) / np.maximum(np.abs(ex), 1e-30)
+    assert rel.max() <= 2.0 ** -11
+    assert np.sqrt(np.mean(rel ** 2)) <= 2e-5, np.sqrt(np.mean(rel ** 2))
+
+
+def _big_mlp(n_in, n_hidden, seed=0):
+    """Output layer large enough that the learned term moves the state by ~0.1 m per step: an error in the MLP (bias,
+    column group, activation placement) moves the costs by percents."""
+    if n_in == 3:
+        return orc.make_mlp(seed=seed, out_scale=0.5, n_in=3, n_hidden=n_hidden)
+    m = orc.make_mlp(seed=seed, out_scale=0.5, n_in=5, scalers=True, scaler_gain=0.2, n_hidden=n_hidden)
+    m["W0"][:, 3:] *= 8.0
+    return m
+
+
+@pytest.mark.parametrize("n_in,n_hidden", [(3, 2), (5, 2), (3, 3), (5, 3)])
+@pytest.mark.parametrize("cost_mode", ["sum", "last"])
+def test_mlp_costs_match_device_faithful_restatement(n_in, n_hidden, cost_mode):
+    g = Golden("diffdrive_pe0.05")
+    K, T = 4096, 30
+    mlp = _big_mlp(n_in, n_hidden)
+    sp = _spec(K, T, cost_mode, mlp)
+    eng = engine_from_spec(sp, g.path)
+    sc = [mlp[k] for k in ("in_mean", "in_scale", "out_mean", "out_scale")] if n_in == 5 else []
+    eng.set_mlp([mlp["W%d" % i] for i in range(n_hidden + 2)], [mlp["b%d" % i] for i in range(n_hidden + 2)], *sc)
+    eps = torch.zeros(K, T, 2, dtype=torch.float32, device="cuda")
+    eng.generate_noise(eps, seed=3, tick=1)
+    S = torch.zeros(K, dtype=torch.float32, device="cuda")
+    x0 = np.array([0.4, 0.3, 0.5])
+    U = np.random.default_rng(2).normal(0, 0.5, (T, 2)).astype(np.float32)
+    eng.set_nominal(U)
+    eng.set_waypoint_idx(0)
+    eng.rollout_costs(x0, S, None, seed=3, tick=1)
+    Sg = S.cpu().numpy().astype(np.float64)
+    e64 = eps.cpu().numpy().astype(np.float64)
+    S64, _, _ = orc.costs_vec(sp, g.path, U.astype(np.float64), 0, x0, e64)
+    sp.mlp_precision = "f16"
+    Sf, _, _ = orc.costs_vec(sp, g.path, U.astype(np.float64), 0, x0, e64)
+    sp.mlp_tanh = hw_tanh
+    Sh, _, _ = orc.costs_vec(sp, g.path, U.astype(np.float64), 0, x0, e64)
+    # the learned term matters: without it the costs are far away
+    sp_plain = orc.diffdrive_spec(K=K, T=T, param_exploration=0.05, cost_mode=cost_mode, waypoint_mode="frozen")
+    Sp, _, _ = orc.costs_vec(sp_plain, g.path, U.astype(np.float64), 0, x0, e64)
+    assert np.median(_rel(Sp, S64)) > 0.02, np.median(_rel(Sp, S64))
+    for name, ref, p99 in (("fp64", S64, MLP_COST_RTOL_BIG), ("faithful", Sf, MLP_FAITHFUL_RTOL), ("faithful+hw", Sh, MLP_FAITHFUL_HW_RTOL)):
+        rel = _rel(Sg, ref)
+        assert np.quantile(rel, 0.99) <= p99, (name, n_in, n_hidden, cost_mode, np.quantile(rel, 0.99))
+        # beyond the bulk: nearest-waypoint near-ties decided differently, a handful of samples
+        assert np.mean(rel > 1e-4 if name != "fp64" else rel > 2e-3) <= 2e-3, (name, np.mean(rel > 1e-4))
+        assert rel.max() <= 2e-2, (name, rel.max())
+    eng.close()
+
+
+def test_device_faithful_gate_catches_a_ten_percent_mlp_error():
+    """Discriminating power of the tight gate: the same costs against a restatement whose last hidden bias is off by 10 %
+    (the kind of systematic error the loose FP64 bound with a 0.01 output layer would have let through) miss it by orders."""
+    g = Golden("diffdrive_pe0.05")
+    K, T = 2048, 30
+    mlp = _big_mlp(3, 2)
+    sp = _spec(K, T, "sum", mlp)
+    eng = engine_from_spec(sp, g.path)
+    eng.set_mlp([mlp["W%d" % i] for i in range(4)], [mlp["b%d" % i] for i in range(4)])
+    eps = torch.zeros(K, T, 2, dtype=torch.float32, device="cuda")
+    eng.generate_noise(eps, seed=3, tick=1)
+    S = torch.zeros(K, dtype=torch.float32, device="cuda")
+    x0 = np.array([0.4, 0.3, 0.5])
+    eng.rollout_costs(x0, S, None, seed=3, tick=1)
+    Sg = S.cpu().numpy().astype(np.float64)
+    wrong = {k: np.array(v, copy=True) for k, v in mlp.items() if not k.startswith("_")}
+    wrong["b2"] = wrong["b2"] * 1.1
+    spw = _spec(K, T, "sum", wrong)
+    spw.mlp_precision = "f16"
+    Sw, _, _ = orc.costs_vec(spw, g.path, np.zeros((T, 2)), 0, x0, eps.cpu().numpy().astype(np.float64))
+    assert np.quantile(_rel(Sg, Sw), 0.5) > 50 * MLP_FAITHFUL_RTOL, np.quantile(_rel(Sg, Sw), 0.5)
     eng.close()

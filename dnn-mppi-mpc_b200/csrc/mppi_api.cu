@@ -88,6 +88,8 @@ struct mppi_handle_s {
     int *d_sorted_idx = nullptr, *d_iota = nullptr;
     void *d_sort_temp = nullptr;
     size_t sort_temp_bytes = 0;
+    unsigned long long *d_trace = nullptr;     // per-CTA time stamps of the last tick (mppi_set_trace)
+    int trace_n = 0;
     // timing / bookkeeping
     bool timing = false;
     cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
@@ -273,7 +275,7 @@ int mppi_create(const mppi_config_t *cfg, mppi_handle_t *out) {
     const int tick_model = (c.model == MPPI_MODEL_DIFFDRIVE_MLP) ? MPPI_MODEL_DIFFDRIVE : c.model;
     h->occ = std::max(1, mppi_tick_occupancy(tick_model, c.collision, c.cost_kind, h->sum, false, c.window, T, false));
     const int occ_stash = mppi_tick_occupancy(tick_model, c.collision, c.cost_kind, h->sum, false, c.window, T, true);
-    h->stash = occ_stash >= 2 && c.model != MPPI_MODEL_DIFFDRIVE_MLP;
+    h->stash = occ_stash >= MPPI_STASH_BLOCKS && c.model != MPPI_MODEL_DIFFDRIVE_MLP;
     int gx = (h->n_sm * h->occ + R - 1) / R;
     gx = std::max(1, std::min(gx, chunks));
     h->grid_x = gx;
@@ -346,7 +348,7 @@ int mppi_destroy(mppi_handle_t h) {
     if (h->p2p)
         for (int p = 0; p < h->world; ++p)
             if (p != h->rank && h->peer_buf[p]) cudaIpcCloseMemHandle(h->peer_buf[p]);
-    cudaFree(h->d_xchg);
+    cudaFree(h->d_xchg); cudaFree(h->d_trace);
     cudaFree(h->d_paths); cudaFree(h->d_path_len);
     cudaFree(h->d_Sc); cudaFree(h->d_Ssorted); cudaFree(h->d_sorted_idx); cudaFree(h->d_iota); cudaFree(h->d_sort_temp);
     if (h->mlp) mlp_destroy(h->mlp);
@@ -969,6 +971,30 @@ int mppi_comm_p2p_open(mppi_handle_t h, const void *handles, int32_t rank, int32
     h->h_out[MPPI_OUT_PEER_TIMEOUT] = 0.f;              // no stale peer-timeout report from an earlier communicator
     CK(h, cudaMemsetAsync(h->d_out + MPPI_OUT_PEER_TIMEOUT, 0, sizeof(float), h->stream));
     CK(h, cudaStreamSynchronize(h->stream));
+    return MPPI_OK;
+}
+
+int mppi_set_trace(mppi_handle_t h, int32_t on) {
+    if (!h) return MPPI_E_BADARG;
+    CK(h, cudaSetDevice(h->cfg.device));
+    CK(h, cudaStreamSynchronize(h->stream));
+    if (on && !h->d_trace) {
+        h->trace_n = 2 * (std::max(h->grid_x, h->grid_x_stash) + 1);
+        CK(h, cudaMalloc(&h->d_trace, sizeof(unsigned long long) * h->trace_n));
+        CK(h, cudaMemset(h->d_trace, 0, sizeof(unsigned long long) * h->trace_n));
+    }
+    h->args.trace = on ? h->d_trace : nullptr;
+    return MPPI_OK;
+}
+
+int mppi_get_trace(mppi_handle_t h, uint64_t *out, int32_t capacity, int32_t *n_ctas_out) {
+    if (!h || !out || !n_ctas_out || capacity < 4) return MPPI_E_BADARG;
+    if (!h->d_trace) return fail(h, MPPI_E_STATE, "call mppi_set_trace(h, 1) before the tick");
+    CK(h, cudaSetDevice(h->cfg.device));
+    const int n = std::min(capacity, h->trace_n);
+    CK(h, cudaMemcpyAsync(out, h->d_trace, sizeof(uint64_t) * n, cudaMemcpyDeviceToHost, h->stream));
+    CK(h, cudaStreamSynchronize(h->stream));
+    *n_ctas_out = h->stash ? h->grid_x_stash : h->grid_x;
     return MPPI_OK;
 }
 

@@ -11,9 +11,14 @@
 #define MPPI_BLOCK 256
 #endif
 #define MPPI_WARPS (MPPI_BLOCK / 32)
+#ifndef MPPI_SPT
+#define MPPI_SPT 1                     // samples per thread of the tick kernel: independent rollouts interleaved in one
+#endif                                 // instruction stream (ILP); a CTA walks its range in chunks of MPPI_CHUNK samples
+#define MPPI_CHUNK (MPPI_BLOCK * MPPI_SPT)
 #ifndef MPPI_MIN_BLOCKS
-#define MPPI_MIN_BLOCKS 3              // resident CTAs per SM the tick kernel is register-budgeted for
+#define MPPI_MIN_BLOCKS (MPPI_BLOCK >= 512 ? 1 : 768 / MPPI_BLOCK)   // resident CTAs per SM the regenerate-noise tick kernels are register-budgeted for
 #endif
+#define MPPI_STASH_BLOCKS (MPPI_BLOCK >= 512 ? 1 : 512 / MPPI_BLOCK)  // ... and the stash kernels (512 samples' noise fill shared memory)
 #define MPPI_PENALTY 1.0e10f           // mppi_race_car_obstacle.py:157
 #define MPPI_SENTINEL 1.0e18f          // padded window entries: distance^2 = 1e36, never the minimum
 #define MPPI_OUT_HDR 12                // u0 (post-shift, Q8), idx, rho, ncoll, eta, ess, p2p flag, first row of the PRE-shift nominal,
@@ -93,6 +98,8 @@ struct TickArgs {
     int p2p_rank, p2p_world;
     unsigned p2p_seq;
     unsigned p2p_timeout_ms;          // a peer that has not published within this time fails the tick (MPPI_E_NCCL)
+    unsigned long long *trace;        // diagnostics (mppi_set_trace): %globaltimer of CTA b's start [2b] and end of its rollouts
+                                      // [2b+1], then the last CTA's merge done [2B] and nominal updated [2B+1]; or null
 };
 
 // ------------------------------------------------------------------------------------------
@@ -241,6 +248,9 @@ __device__ __forceinline__ float2 f2_fma(float2 a, float2 b, float2 c) {
 #ifndef MPPI_ARGMIN_KEY_SEL
 #define MPPI_ARGMIN_KEY_SEL 0   // 1: first-min index by FSETP/SEL chains on the ALU pipe (A/B variant, see profiles/)
 #endif
+#ifndef MPPI_MIN_TREE
+#define MPPI_MIN_TREE 1         // tree-shaped FMNMX3 reductions in the static-window argmin (0: chains of 10; +2.9 % on B200)
+#endif
 #ifndef MPPI_ARGMIN_PACK
 #define MPPI_ARGMIN_PACK 2      // 2: all FP32 work packed (FFMA2); 1: differences scalar, rest packed; 0: all scalar
 #endif
@@ -338,6 +348,28 @@ __device__ __forceinline__ int nearest_wp(const TickSmem &sm, float x, float y) 
             d[2 * q] = f2_fma(make_float2(Y.x, Y.y), ayy, f2_fma(make_float2(X.x, X.y), axx, make_float2(C.x, C.y)));
             d[2 * q + 1] = f2_fma(make_float2(Y.z, Y.w), ayy, f2_fma(make_float2(X.z, X.w), axx, make_float2(C.z, C.w)));
         }
+#if MPPI_MIN_TREE
+        // the two 20-input minima as TREES of 3-input FMNMX3 (depth 3) instead of chains of 10 dependent ones: the
+        // horizon recurrence leaves a sample no other work to hide ~80 cycles of chain latency per step behind
+        const float m = fminf(fminf(fminf(fminf(d[0].x, d[0].y), d[1].x), fminf(fminf(d[1].y, d[2].x), d[2].y)),
+                              fminf(fminf(fminf(fminf(d[3].x, d[3].y), d[4].x), fminf(fminf(d[4].y, d[5].x), d[5].y)),
+                                    fminf(fminf(fminf(fminf(d[6].x, d[6].y), d[7].x), fminf(fminf(d[7].y, d[8].x), d[8].y)),
+                                          fminf(d[9].x, d[9].y))));
+        const float2 nm = make_float2(-m, -m), huge = make_float2(1.2676506e30f, 1.2676506e30f);
+        const float4 *ki4 = reinterpret_cast<const float4 *>(sm.kidx);
+        float2 kk[10];
+#pragma unroll
+        for (int i = 0; i < 10; i += 2) {
+            const float4 ki = ki4[i >> 1];
+            kk[i] = f2_fma(f2_add(d[i], nm), huge, make_float2(ki.x, ki.y));
+            kk[i + 1] = f2_fma(f2_add(d[i + 1], nm), huge, make_float2(ki.z, ki.w));
+        }
+        const float key = fminf(fminf(fminf(fminf(kk[0].x, kk[0].y), kk[1].x), fminf(fminf(kk[1].y, kk[2].x), kk[2].y)),
+                                fminf(fminf(fminf(fminf(kk[3].x, kk[3].y), kk[4].x), fminf(fminf(kk[4].y, kk[5].x), kk[5].y)),
+                                      fminf(fminf(fminf(fminf(kk[6].x, kk[6].y), kk[7].x), fminf(fminf(kk[7].y, kk[8].x), kk[8].y)),
+                                            fminf(kk[9].x, kk[9].y))));
+        return __float2int_rn(key);
+#else
         float m = fminf(d[0].x, d[0].y);
 #pragma unroll
         for (int i = 1; i < 10; ++i) m = fminf(fminf(m, d[i].x), d[i].y);
@@ -361,6 +393,7 @@ __device__ __forceinline__ int nearest_wp(const TickSmem &sm, float x, float y) 
         }
 #endif
         return __float2int_rn(key);
+#endif
 #else
         float m, key;
         chunk_argmin<20>(nwx4, nwy4, x, y, m, key);
@@ -568,73 +601,90 @@ __device__ __forceinline__ void dyn_step(const TickArgs &a, float z[4], float v0
 
 __device__ __forceinline__ float clampf(float v, float lim) { return fminf(fmaxf(v, -lim), lim); }
 
-// One sample's rollout (frozen window).  Returns the smooth cost and the number of collided
+// The rollouts of SPT samples of one thread (frozen window), advanced in LOCKSTEP: every stage is written as a loop over the
+// thread's samples inside one basic block, so the instruction scheduler interleaves SPT independent dependency chains
+// (the horizon recurrence makes a single chain latency-bound: ~220 cycles of dependent latency per step).  Sample s of
+// the thread is chunk slot `slot0 + s * MPPI_BLOCK`.  Returns per sample the smooth cost and the number of collided
 // evaluations separately so 1e10 * n never swallows the tracking cost.
 //
-// The loop is software-pipelined by hand: the noise of the NEXT timestep pair (Philox + Box-Muller:
+// The loop is also software-pipelined by hand: the noise of the NEXT timestep pair (Philox + Box-Muller:
 // integer/ALU + MUFU work) is generated in the same straight-line block as the two dynamics/cost
-// steps of the CURRENT pair (FMA-pipe work), so the scheduler can interleave independent chains and
-// the ALU, MUFU and FMA pipes are busy at the same time instead of in alternating phases.
-template <int MODEL, int COLL, bool SUM, bool INJ, int WIN>
-__device__ __forceinline__ void rollout_sample(const TickArgs &a, const TickSmem &sm, uint32_t kg, int klocal,
-                                               uint32_t robot, bool exploit, float2 *stash, float &smooth, int &ncoll) {
+// steps of the CURRENT pair (FMA-pipe work), so the ALU, MUFU and FMA pipes are busy at the same time.
+template <int MODEL, int COLL, bool SUM, bool INJ, int WIN, int SPT>
+__device__ __forceinline__ void rollout_samples(const TickArgs &a, const TickSmem &sm, const uint32_t (&kg)[SPT], const int (&klocal)[SPT],
+                                                uint32_t robot, const bool (&exploit)[SPT], float2 *stash, float (&smooth)[SPT], int (&ncoll)[SPT]) {
     const int T = a.T;
-    float z[4] = {sm.x0[0], sm.x0[1], sm.x0[2], sm.x0[3]};
-    float cs, sn;
-    sincos_cw(z[2], sn, cs);
-    float acc = 0.f;
-    int nc = 0;
-    float v0 = 0.f, v1 = 0.f;
-    float4 ref = make_float4(0.f, 0.f, 0.f, 0.f);
-    float yaw_eff = 0.f;
-    bool hit = false;
-    const float2 *eps_k = INJ ? reinterpret_cast<const float2 *>(a.eps) + (size_t)klocal * T : nullptr;
+    float z[SPT][4], cs[SPT], sn[SPT], acc[SPT], v0[SPT], v1[SPT], yaw_eff[SPT];
+    int nc[SPT];
+    float4 ref[SPT];
+    bool hit[SPT];
+    const float2 *eps_k[SPT];
+#pragma unroll
+    for (int s = 0; s < SPT; ++s) {
+        z[s][0] = sm.x0[0]; z[s][1] = sm.x0[1]; z[s][2] = sm.x0[2]; z[s][3] = sm.x0[3];
+        sincos_cw(z[s][2], sn[s], cs[s]);
+        acc[s] = 0.f; nc[s] = 0; v0[s] = v1[s] = 0.f; yaw_eff[s] = 0.f; hit[s] = false;
+        ref[s] = make_float4(0.f, 0.f, 0.f, 0.f);
+        eps_k[s] = INJ ? reinterpret_cast<const float2 *>(a.eps) + (size_t)klocal[s] * T : nullptr;
+    }
 
-    auto fetch = [&](int tp, float e[4]) {
+    auto fetch = [&](int s, int tp, float e[4]) {
         if (INJ) {
             e[0] = e[1] = e[2] = e[3] = 0.f;
-            if (tp < T) { const float2 ea = eps_k[tp]; e[0] = ea.x; e[1] = ea.y; }
-            if (tp + 1 < T) { const float2 eb = eps_k[tp + 1]; e[2] = eb.x; e[3] = eb.y; }
+            if (tp < T) { const float2 ea = eps_k[s][tp]; e[0] = ea.x; e[1] = ea.y; }
+            if (tp + 1 < T) { const float2 eb = eps_k[s][tp + 1]; e[2] = eb.x; e[3] = eb.y; }
         } else {
-            philox_eps_pair(a, kg, (uint32_t)(tp >> 1), robot, e);
+            philox_eps_pair(a, kg[s], (uint32_t)(tp >> 1), robot, e);
         }
     };
-    auto step = [&](int t, float e0, float e1) {
-        if (stash) stash[t * MPPI_BLOCK] = make_float2(e0, e1);
+    auto step = [&](int s, int t, float e0, float e1) {
+        if (stash) stash[t * MPPI_CHUNK + s * MPPI_BLOCK] = make_float2(e0, e1);
         const float2 u = sm.U[t];
-        v0 = clampf(exploit ? __fadd_rn(u.x, e0) : e0, a.umax0);                   // A4, A5
-        v1 = clampf(exploit ? __fadd_rn(u.y, e1) : e1, a.umax1);
-        dyn_step<MODEL>(a, z, v0, v1, cs, sn);
-        sincos_cw(z[2], sn, cs);
+        v0[s] = clampf(exploit[s] ? __fadd_rn(u.x, e0) : e0, a.umax0);                   // A4, A5
+        v1[s] = clampf(exploit[s] ? __fadd_rn(u.y, e1) : e1, a.umax1);
+        dyn_step<MODEL>(a, z[s], v0[s], v1[s], cs[s], sn[s]);
+        sincos_cw(z[s][2], sn[s], cs[s]);
         if (SUM) {
-            const float c = eval_state_cost<MODEL, WIN>(a, sm, z, v0, v1, t, a.sw, ref, yaw_eff);
+            const float c = eval_state_cost<MODEL, WIN>(a, sm, z[s], v0[s], v1[s], t, a.sw, ref[s], yaw_eff[s]);
             const float2 q = sm.Q[t];                                                // zero when gamma == 0
-            acc += c + (q.x * v0 + q.y * v1);
-            hit = collided<MODEL, COLL>(a, z[0], z[1], cs, sn);
-            nc += hit ? 1 : 0;
+            acc[s] += c + (q.x * v0[s] + q.y * v1[s]);
+            hit[s] = collided<MODEL, COLL>(a, z[s][0], z[s][1], cs[s], sn[s]);
+            nc[s] += hit[s] ? 1 : 0;
         }
     };
 
-    float e[4];
-    fetch(0, e);
-    const int Tpairs = T & ~1;
-    for (int tp = 0; tp < Tpairs; tp += 2) {
-        float en[4];
-        fetch(tp + 2, en);              // independent of the two steps below (one surplus call at the end)
-        step(tp, e[0], e[1]);
-        step(tp + 1, e[2], e[3]);
-        e[0] = en[0]; e[1] = en[1]; e[2] = en[2]; e[3] = en[3];
+    float e[SPT][4];
+#pragma unroll
+    for (int s = 0; s < SPT; ++s) fetch(s, 0, e[s]);
+    // pairs of timesteps whose successor still needs noise run with the fetch of the NEXT pair interleaved; the last
+    // pair (or the odd last step) runs alone, so no Philox call is wasted
+    const int n_fetch_pairs = (T - 1) >> 1;                 // pairs tp = 0, 2, ... for which a step tp + 2 exists
+    int tp = 0;
+    for (int i = 0; i < n_fetch_pairs; ++i, tp += 2) {
+        float en[SPT][4];
+#pragma unroll
+        for (int s = 0; s < SPT; ++s) fetch(s, tp + 2, en[s]);      // independent of the two steps below
+#pragma unroll
+        for (int s = 0; s < SPT; ++s) step(s, tp, e[s][0], e[s][1]);
+#pragma unroll
+        for (int s = 0; s < SPT; ++s) step(s, tp + 1, e[s][2], e[s][3]);
+#pragma unroll
+        for (int s = 0; s < SPT; ++s) { e[s][0] = en[s][0]; e[s][1] = en[s][1]; e[s][2] = en[s][2]; e[s][3] = en[s][3]; }
     }
-    if (T & 1) step(T - 1, e[0], e[1]);
-    if (SUM) {                          // terminal cost: same state, same waypoint as the last stage cost (A9)
-        acc += eval_terminal_cost<MODEL, WIN>(a, z, ref, yaw_eff);
-        nc += hit ? 1 : 0;
-    } else {                            // Q1: only the last stage cost survives, plus terminal
-        const float2 q = sm.Q[T - 1];
-        acc = eval_state_cost<MODEL, WIN>(a, sm, z, v0, v1, T - 1, a.sw, ref, yaw_eff) + (q.x * v0 + q.y * v1);
-        acc += eval_terminal_cost<MODEL, WIN>(a, z, ref, yaw_eff);
-        nc = collided<MODEL, COLL>(a, z[0], z[1], cs, sn) ? 2 : 0;
+#pragma unroll
+    for (int s = 0; s < SPT; ++s) {
+        step(s, tp, e[s][0], e[s][1]);                      // tp = T - 2 (even T) or T - 1 (odd T)
+        if (!(T & 1)) step(s, tp + 1, e[s][2], e[s][3]);
+        if (SUM) {                          // terminal cost: same state, same waypoint as the last stage cost (A9)
+            acc[s] += eval_terminal_cost<MODEL, WIN>(a, z[s], ref[s], yaw_eff[s]);
+            nc[s] += hit[s] ? 1 : 0;
+        } else {                            // Q1: only the last stage cost survives, plus terminal
+            const float2 q = sm.Q[T - 1];
+            acc[s] = eval_state_cost<MODEL, WIN>(a, sm, z[s], v0[s], v1[s], T - 1, a.sw, ref[s], yaw_eff[s]) + (q.x * v0[s] + q.y * v1[s]);
+            acc[s] += eval_terminal_cost<MODEL, WIN>(a, z[s], ref[s], yaw_eff[s]);
+            nc[s] = collided<MODEL, COLL>(a, z[s][0], z[s][1], cs[s], sn[s]) ? 2 : 0;
+        }
+        smooth[s] = acc[s];
+        ncoll[s] = nc[s];
     }
-    smooth = acc;
-    ncoll = nc;
 }

@@ -51,6 +51,7 @@ struct MergeSmem {
 #define MPPI_MERGE_TILE 1000
 #define MPPI_MERGE_GROUPS 4
 #define MPPI_MERGE_SCRATCH (MPPI_MERGE_TILE + MPPI_MERGE_GROUPS * MPPI_NF_MAX)      // 2040 floats <= the 8 KB warpN region
+static_assert(4 * MPPI_BLOCK <= MPPI_MERGE_SCRATCH || MPPI_BLOCK > 256, "merge fast path: group sums must fit the scratch");
 __device__ void merge_partials(const TickArgs &a, const float *parts, int P, MergeSmem &ms, float *sc, int stride = 0) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int NF = MPPI_NF(a.T);
@@ -70,6 +71,54 @@ __device__ void merge_partials(const TickArgs &a, const float *parts, int P, Mer
     for (int w = 1; w < MPPI_WARPS; ++w) {
         const int wn = ms.red_n[w]; const float ws = ms.red_s[w];
         if (wn < n || (wn == n && ws < s)) { n = wn; s = ws; }
+    }
+    // ---- fast path (even horizon: NF % 4 == 0, partials 16-byte aligned): a thread owns one float4 COLUMN QUAD, the CTA
+    // splits into G = MPPI_BLOCK / (NF/4) groups (9 at T = 50) and a group's thread streams every G-th partial with up
+    // to 12 independent 16-byte loads in flight: ~P/(12 G) dependent L2 round trips (3 at P = 296) instead of P/32
+    if ((NF & 3) == 0 && (stride & 3) == 0 && MPPI_BLOCK / (NF >> 2) >= 2 && P <= MPPI_MERGE_TILE) {
+        const int NQ = NF >> 2, G4 = min(MPPI_BLOCK / NQ, 16);
+        const int g4 = tid / NQ, cq = tid - g4 * NQ;
+        __syncthreads();
+        for (int p = tid; p < P; p += MPPI_BLOCK) {
+            const float *pp = parts + (size_t)p * stride;
+            sc[p] = rel_weight(__float_as_int(__ldcg(pp)), __ldcg(pp + 1), n, s, a.inv_temp);
+        }
+        __syncthreads();
+        float4 acc4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (g4 < G4) {
+            const float4 *col = reinterpret_cast<const float4 *>(parts) + cq;
+            const size_t st4 = (size_t)stride >> 2;
+            int p = g4;
+            for (; p + 11 * G4 < P; p += 12 * G4) {
+                float4 v[12];
+#pragma unroll
+                for (int i = 0; i < 12; ++i) v[i] = __ldcg(col + (size_t)(p + i * G4) * st4);
+#pragma unroll
+                for (int i = 0; i < 12; ++i) {
+                    const float w = sc[p + i * G4];
+                    acc4.x = fmaf(w, v[i].x, acc4.x); acc4.y = fmaf(w, v[i].y, acc4.y);
+                    acc4.z = fmaf(w, v[i].z, acc4.z); acc4.w = fmaf(cq == 0 ? w * w : w, v[i].w, acc4.w);
+                }
+            }
+            for (; p < P; p += G4) {
+                const float4 v = __ldcg(col + (size_t)p * st4);
+                const float w = sc[p];
+                acc4.x = fmaf(w, v.x, acc4.x); acc4.y = fmaf(w, v.y, acc4.y);
+                acc4.z = fmaf(w, v.z, acc4.z); acc4.w = fmaf(cq == 0 ? w * w : w, v.w, acc4.w);
+            }
+        }
+        __syncthreads();                                      // every thread is done with sc[]: reuse it for the group sums
+        float *red4 = sc;                                     // [G4][NF]: G4 * NF <= (MPPI_BLOCK / NQ) * 4 NQ = 4 MPPI_BLOCK floats... of which <= 1024 at 256 threads
+        if (g4 < G4) *reinterpret_cast<float4 *>(red4 + (size_t)g4 * NF + 4 * cq) = acc4;
+        __syncthreads();
+        for (int c = 2 + tid; c < NF; c += MPPI_BLOCK) {
+            float t = red4[c];
+            for (int gg = 1; gg < G4; ++gg) t += red4[(size_t)gg * NF + c];
+            ms.col[c] = t;
+        }
+        if (tid == 0) { ms.col[0] = __int_as_float(n); ms.col[1] = s; }
+        __syncthreads();
+        return;
     }
     // column pairs: pair 0 = (n, s) is the key handled above, pair 1 = (eta, sum w^2), pairs 2.. = N[t][0..1]
     const int NP = NF >> 1;                                   // NF = 4 + 2T is even; every partial is 8-byte aligned
@@ -218,7 +267,7 @@ struct RunSmem {
     float s;
     float eta, e2;
     float N[2 * MPPI_MAX_T];   // running sum of w * eps, relative to (n, s)
-    float w[MPPI_BLOCK];       // stash mode: this chunk's weights
+    float w[MPPI_CHUNK];       // stash mode: this chunk's weights
     float warp_eta[MPPI_WARPS], warp_e2[MPPI_WARPS];
     float red_s[MPPI_WARPS];
     int red_n[MPPI_WARPS];
@@ -227,14 +276,14 @@ struct RunSmem {
 };
 
 // Dynamic shared memory of the tick kernel:
-//   STASH = true : float2 eps[T][MPPI_BLOCK] -- the noise of the chunk being rolled out, written in
+//   STASH = true : float2 eps[T][MPPI_CHUNK] -- the noise of the chunk being rolled out, written in
 //                  pass 1 and consumed by the weighted column sums, so Philox + Box-Muller run once.
 //   STASH = false: float warpN[MPPI_WARPS][2*MPPI_MAX_T] -- per-warp partial sums of the
 //                  regenerate-the-noise path (injected noise, K2 alone, horizons too long to stash).
 extern __shared__ __align__(16) unsigned char mppi_dyn_smem[];
 
 template <int MODEL, int COLL, bool SUM, bool INJ, int WIN, bool STASH>
-__global__ void __launch_bounds__(MPPI_BLOCK, STASH ? 2 : MPPI_MIN_BLOCKS) mppi_tick_kernel(const __grid_constant__ TickArgs a) {
+__global__ void __launch_bounds__(MPPI_BLOCK, STASH ? MPPI_STASH_BLOCKS : MPPI_MIN_BLOCKS) mppi_tick_kernel(const __grid_constant__ TickArgs a) {
     __shared__ TickSmem sm;
     __shared__ RunSmem run;
     __shared__ MergeSmem ms;
@@ -244,6 +293,7 @@ __global__ void __launch_bounds__(MPPI_BLOCK, STASH ? 2 : MPPI_MIN_BLOCKS) mppi_
     const int robot = blockIdx.y, b = blockIdx.x, B = gridDim.x;
     const int T = a.T, K = a.K;
 
+    if (a.trace && tid == 0 && robot == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); a.trace[2 * b] = t; }
     // ---- prologue: observed state, step-1 index update (A8 with update=True), window, nominal
     if (tid < 4) sm.x0[tid] = a.x0_dev ? a.x0_dev[robot * 4 + tid] : a.x0[tid];
     __syncthreads();
@@ -309,32 +359,53 @@ __global__ void __launch_bounds__(MPPI_BLOCK, STASH ? 2 : MPPI_MIN_BLOCKS) mppi_
     }
     __syncthreads();
 
-    // ---- this block's contiguous sample range (balanced over the grid)
+    // ---- this block's contiguous sample range (balanced over the grid), walked in chunks of MPPI_CHUNK samples:
+    // thread tid owns chunk slots tid, tid + MPPI_BLOCK, ... (MPPI_SPT of them, rolled out in lockstep)
+    constexpr int SPT = MPPI_SPT;
     const int k_begin = (int)((long long)K * b / B);
     const int k_end = (a.flags & F_IDX_ONLY) ? k_begin : (int)((long long)K * (b + 1) / B);
     float *Srow = a.S ? a.S + (size_t)robot * K : nullptr;
-    for (int base = k_begin; base < k_end; base += MPPI_BLOCK) {
-        const int k = base + tid;
-        const bool active = k < k_end;
-        const uint32_t kg = (uint32_t)(a.k_offset + k);
-        float smooth = CUDART_INF_F;
-        int ncoll = INT_MAX;
-        if (active) {
+    for (int base = k_begin; base < k_end; base += MPPI_CHUNK) {
+        int k[SPT], ksafe[SPT], ncoll[SPT];
+        bool active[SPT], exploit[SPT];
+        uint32_t kg[SPT];
+        float smooth[SPT];
+#pragma unroll
+        for (int s = 0; s < SPT; ++s) {
+            k[s] = base + tid + s * MPPI_BLOCK;
+            active[s] = k[s] < k_end;
+            ksafe[s] = active[s] ? k[s] : k_begin;             // an idle slot of the tail chunk replays a valid sample (weight 0)
+            kg[s] = (uint32_t)(a.k_offset + ksafe[s]);
+            exploit[s] = (int)kg[s] < a.n_exploit;
+            smooth[s] = CUDART_INF_F; ncoll[s] = INT_MAX;
+        }
+        if (active[0]) {                                        // slots ascend with s: no active sample without the first
             if (a.flags & F_FROM_S) {
-                smooth = Srow[k]; ncoll = a.NC ? a.NC[k] : 0;
+#pragma unroll
+                for (int s = 0; s < SPT; ++s)
+                    if (active[s]) { smooth[s] = Srow[k[s]]; ncoll[s] = a.NC ? a.NC[k[s]] : 0; }
             } else {
-                rollout_sample<MODEL, COLL, SUM, INJ, WIN>(a, sm, kg, k, (uint32_t)robot, (int)kg < a.n_exploit,
-                                                           STASH ? stash + tid : nullptr, smooth, ncoll);
-                if (a.flags & F_WRITE_S) Srow[k] = smooth + MPPI_PENALTY * (float)ncoll;
+                rollout_samples<MODEL, COLL, SUM, INJ, WIN, SPT>(a, sm, kg, ksafe, (uint32_t)robot, exploit,
+                                                                 STASH ? stash + tid : nullptr, smooth, ncoll);
+#pragma unroll
+                for (int s = 0; s < SPT; ++s) {
+                    if (active[s] && (a.flags & F_WRITE_S)) Srow[k[s]] = smooth[s] + MPPI_PENALTY * (float)ncoll[s];
+                    if (!active[s]) { smooth[s] = CUDART_INF_F; ncoll[s] = INT_MAX; }
+                }
             }
         }
         if (!(a.flags & F_UPDATE)) continue;
-        if (STASH && !active) {                     // tail chunk: idle lanes must not leave garbage (0 * NaN)
-            for (int t = 0; t < T; ++t) stash[t * MPPI_BLOCK + tid] = make_float2(0.f, 0.f);
+        if (STASH && !active[0]) {                  // tail chunk: a thread that rolled nothing out must not leave garbage (0 * NaN)
+            for (int t = 0; t < T; ++t)
+#pragma unroll
+                for (int s = 0; s < SPT; ++s) stash[t * MPPI_CHUNK + s * MPPI_BLOCK + tid] = make_float2(0.f, 0.f);
         }
 
         // chunk minimum -> new running minimum
-        int cn = ncoll; float cs_ = smooth;
+        int cn = ncoll[0]; float cs_ = smooth[0];
+#pragma unroll
+        for (int s = 1; s < SPT; ++s)
+            if (ncoll[s] < cn || (ncoll[s] == cn && smooth[s] < cs_)) { cn = ncoll[s]; cs_ = smooth[s]; }
         warp_lexmin(cn, cs_);
         if (lane == 0) { run.red_n[warp] = cn; run.red_s[warp] = cs_; }
         __syncthreads();
@@ -345,22 +416,28 @@ __global__ void __launch_bounds__(MPPI_BLOCK, STASH ? 2 : MPPI_MIN_BLOCKS) mppi_
             if (wn < mn || (wn == mn && ws < mss)) { mn = wn; mss = ws; }
         }
         const float rescale = (run.n == INT_MAX) ? 0.f : rel_weight(run.n, run.s, mn, mss, a.inv_temp);
-        const float w = active ? rel_weight(ncoll, smooth, mn, mss, a.inv_temp) : 0.f;
-        const float we = warp_sum(w), we2 = warp_sum(w * w);
+        float w[SPT], wsum = 0.f, w2sum = 0.f;
+#pragma unroll
+        for (int s = 0; s < SPT; ++s) {
+            w[s] = active[s] ? rel_weight(ncoll[s], smooth[s], mn, mss, a.inv_temp) : 0.f;
+            wsum += w[s]; w2sum = fmaf(w[s], w[s], w2sum);
+        }
+        const float we = warp_sum(wsum), we2 = warp_sum(w2sum);
         if (lane == 0) { run.warp_eta[warp] = we; run.warp_e2[warp] = we2; }
 
         if (STASH) {
-            // weighted column sums straight from the stash: warp `warp` owns rows t = warp, warp+8, ...
-            run.w[tid] = w;
-            __syncthreads();
-            float wr[MPPI_BLOCK / 32];
+            // weighted column sums straight from the stash: warp `warp` owns rows t = warp, warp + MPPI_WARPS, ...
 #pragma unroll
-            for (int i = 0; i < MPPI_BLOCK / 32; ++i) wr[i] = run.w[lane + 32 * i];
+            for (int s = 0; s < SPT; ++s) run.w[tid + s * MPPI_BLOCK] = w[s];
+            __syncthreads();
+            float wr[MPPI_CHUNK / 32];
+#pragma unroll
+            for (int i = 0; i < MPPI_CHUNK / 32; ++i) wr[i] = run.w[lane + 32 * i];
             for (int t = warp; t < T; t += MPPI_WARPS) {
-                const float2 *row = stash + t * MPPI_BLOCK;
+                const float2 *row = stash + t * MPPI_CHUNK;
                 float ax = 0.f, ay = 0.f;
 #pragma unroll
-                for (int i = 0; i < MPPI_BLOCK / 32; ++i) {
+                for (int i = 0; i < MPPI_CHUNK / 32; ++i) {
                     const float2 e = row[lane + 32 * i];
                     ax = fmaf(wr[i], e.x, ax); ay = fmaf(wr[i], e.y, ay);
                 }
@@ -378,21 +455,28 @@ __global__ void __launch_bounds__(MPPI_BLOCK, STASH ? 2 : MPPI_MIN_BLOCKS) mppi_
                 }
             }
         } else {
-            // regenerate (Philox) or re-read (injected) this sample's eps row
-            const bool any = __any_sync(0xffffffffu, w > 0.f);
+            // regenerate (Philox) or re-read (injected) the eps rows of this thread's samples
+            const bool any = __any_sync(0xffffffffu, wsum > 0.f);
             if (any) {
-                const float2 *eps_k = INJ ? reinterpret_cast<const float2 *>(a.eps) + (size_t)(active ? k : k_begin) * T : nullptr;
+                const float2 *eps_k[SPT];
+#pragma unroll
+                for (int s = 0; s < SPT; ++s)
+                    eps_k[s] = INJ ? reinterpret_cast<const float2 *>(a.eps) + (size_t)ksafe[s] * T : nullptr;
                 for (int tp = 0; tp < T; tp += 2) {
-                    float e[4] = {0.f, 0.f, 0.f, 0.f};
-                    if (INJ) {
-                        const float2 ea = eps_k[tp];
-                        e[0] = ea.x; e[1] = ea.y;
-                        if (tp + 1 < T) { const float2 eb = eps_k[tp + 1]; e[2] = eb.x; e[3] = eb.y; }
-                    } else {
-                        philox_eps_pair(a, kg, (uint32_t)(tp >> 1), (uint32_t)robot, e);
+                    float p0 = 0.f, p1 = 0.f, p2 = 0.f, p3 = 0.f;
+#pragma unroll
+                    for (int s = 0; s < SPT; ++s) {
+                        float e[4] = {0.f, 0.f, 0.f, 0.f};
+                        if (INJ) {
+                            const float2 ea = eps_k[s][tp];
+                            e[0] = ea.x; e[1] = ea.y;
+                            if (tp + 1 < T) { const float2 eb = eps_k[s][tp + 1]; e[2] = eb.x; e[3] = eb.y; }
+                        } else {
+                            philox_eps_pair(a, kg[s], (uint32_t)(tp >> 1), (uint32_t)robot, e);
+                        }
+                        p0 = fmaf(w[s], e[0], p0); p1 = fmaf(w[s], e[1], p1); p2 = fmaf(w[s], e[2], p2); p3 = fmaf(w[s], e[3], p3);
                     }
                     // 4 values x 32 lanes -> 4 sums: halving butterfly (6 shuffles instead of 20)
-                    float p0 = w * e[0], p1 = w * e[1], p2 = w * e[2], p3 = w * e[3];
                     {
                         const bool hi = lane & 16;
                         const float s0 = hi ? p0 : p2, s1 = hi ? p1 : p3;
@@ -434,6 +518,7 @@ __global__ void __launch_bounds__(MPPI_BLOCK, STASH ? 2 : MPPI_MIN_BLOCKS) mppi_
         __syncthreads();
     }
 
+    if (a.trace && tid == 0 && robot == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); a.trace[2 * b + 1] = t; }
     // ---- publish the block partial, elect the last block
     const int NF = MPPI_NF(T);
     float *parts = a.part + (size_t)robot * B * NF;
@@ -464,6 +549,7 @@ __global__ void __launch_bounds__(MPPI_BLOCK, STASH ? 2 : MPPI_MIN_BLOCKS) mppi_
         if (tid == 0) { ms.col[0] = __int_as_float(run.n); ms.col[1] = run.s; ms.col[2] = run.eta; ms.col[3] = run.e2; }
         __syncthreads();
     }
+    if (a.trace && tid == 0 && robot == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); a.trace[2 * B] = t; }
     if (a.flags & F_P2P) {
         // ---- fused exchange over NVLink peer memory.  Every column of this GPU's triple goes to every rank (its own
         // buffer included) as ONE 8-byte store carrying (tick sequence number, float bits): the flag travels with the
@@ -545,6 +631,7 @@ __global__ void __launch_bounds__(MPPI_BLOCK, STASH ? 2 : MPPI_MIN_BLOCKS) mppi_
         return;
     }
     finalize_tick(a, robot, s_new, ms);
+    if (a.trace && tid == 0 && robot == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); a.trace[2 * B + 1] = t; }
 }
 
 // Merge of G per-GPU triples (after the all-gather) + finalize; identical on every rank.
@@ -741,7 +828,7 @@ static cudaError_t with_tick_kernel(int model, int coll, int cost_kind, bool sum
 size_t mppi_tick_dyn_smem(int T, bool stash) {
     // regenerate path: per-warp column sums (8 KB), also large enough for the exchange's gathered triples
     const size_t small = std::max(sizeof(float) * MPPI_WARPS * 2 * MPPI_MAX_T, sizeof(float) * MPPI_MAX_PEERS * MPPI_NF_MAX);
-    return stash ? std::max(sizeof(float2) * (size_t)T * MPPI_BLOCK, small) : small;
+    return stash ? std::max(sizeof(float2) * (size_t)T * MPPI_CHUNK, small) : small;
 }
 
 cudaError_t mppi_launch_tick(const TickArgs &a, int model, int coll, int cost_kind, bool sum, bool inj, bool stash, dim3 grid, cudaStream_t st) {

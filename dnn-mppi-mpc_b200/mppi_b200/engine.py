@@ -246,6 +246,17 @@ class MPPIEngine:
         return dict(rho=s.rho, eta=s.eta, ess=s.ess, min_collisions=s.min_collisions, idx=s.idx,
                     u_first=np.array([s.u_first[0], s.u_first[1]], dtype=np.float32))
 
+    def set_trace(self, on=True):
+        self._ck(self.lib.mppi_set_trace(self._h, int(on)), "mppi_set_trace")
+
+    def trace(self):
+        """Per-CTA (start, rollouts-done) %globaltimer stamps of the last tick and the last CTA's (merged, updated) pair."""
+        buf = (C.c_uint64 * 4096)()
+        n = C.c_int32(0)
+        self._ck(self.lib.mppi_get_trace(self._h, buf, 4096, C.byref(n)), "mppi_get_trace")
+        a = np.frombuffer(buf, dtype=np.uint64)[:2 * (n.value + 1)].astype(np.int64).reshape(-1, 2)
+        return a[:n.value], a[n.value]
+
     def set_timing(self, on=True):
         self._ck(self.lib.mppi_set_timing(self._h, int(on)), "mppi_set_timing")
 

@@ -261,6 +261,12 @@ int mppi_comm_p2p_open(mppi_handle_t h, const void *ipc_handles, int32_t rank, i
  * stored, [2] every rank's words seen, [3] nominal updated.  [2]-[1] is the wait for the slowest rank. */
 int mppi_comm_p2p_trace(mppi_handle_t h, uint64_t stamps_out[4]);
 
+/* Diagnostics, no reference counterpart: per-CTA %globaltimer stamps (ns) of the LAST single-robot tick -- out[2b] CTA b
+ * entered the kernel, out[2b+1] its rollouts ended; after the n CTAs: out[2n] partials merged, out[2n+1] nominal updated
+ * (last CTA).  Shows where a tick's time outside the rollouts goes (profiles/). */
+int mppi_set_trace(mppi_handle_t h, int32_t enabled);
+int mppi_get_trace(mppi_handle_t h, uint64_t *out, int32_t capacity, int32_t *n_ctas_out);
+
 int mppi_set_timing(mppi_handle_t h, int32_t enabled);
 int mppi_get_timings(mppi_handle_t h, mppi_timings_t *out);
 int mppi_abi_version(void);

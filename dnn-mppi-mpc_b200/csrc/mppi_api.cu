@@ -60,6 +60,10 @@ struct mppi_handle_s {
     float *d_U = nullptr, *d_M = nullptr, *d_S = nullptr, *d_part = nullptr, *d_out = nullptr;
     float *d_x0 = nullptr, *d_opt = nullptr, *d_plant_log = nullptr;
     int plant_log_cap = 0;
+    unsigned *d_loop = nullptr;                 // closed loop: running tick, first tick, ticket (see TickArgs::loop_state)
+    cudaGraphExec_t loop_graph = nullptr;       // the n-tick closed loop, instantiated once per (n_ticks, arguments)
+    int loop_graph_n = 0;
+    TickArgs loop_graph_args{};
     int *d_idx = nullptr, *d_NC = nullptr;
     unsigned *d_ticket = nullptr;
     float *h_out = nullptr, *h_out_dev = nullptr;     // mapped pinned record of robot 0
@@ -348,7 +352,8 @@ int mppi_destroy(mppi_handle_t h) {
     if (h->p2p)
         for (int p = 0; p < h->world; ++p)
             if (p != h->rank && h->peer_buf[p]) cudaIpcCloseMemHandle(h->peer_buf[p]);
-    cudaFree(h->d_xchg); cudaFree(h->d_trace);
+    cudaFree(h->d_xchg); cudaFree(h->d_trace); cudaFree(h->d_loop);
+    if (h->loop_graph) cudaGraphExecDestroy(h->loop_graph);
     cudaFree(h->d_paths); cudaFree(h->d_path_len);
     cudaFree(h->d_Sc); cudaFree(h->d_Ssorted); cudaFree(h->d_sorted_idx); cudaFree(h->d_iota); cudaFree(h->d_sort_temp);
     if (h->mlp) mlp_destroy(h->mlp);
@@ -859,38 +864,76 @@ int mppi_run_closed_loop(mppi_handle_t h, const double *x0, int32_t n_ticks, uin
                          int32_t plant, float *states_out, float *controls_out) {
     if (!h || !x0 || n_ticks < 1 || !states_out || plant < 0 || plant > 1) return MPPI_E_BADARG;
     if (!h->have_path) return fail(h, MPPI_E_STATE, "mppi_set_ref_path has not been called");
-    if (h->cfg.n_robots != 1 || h->strict || h->mlp || h->world > 1)
-        return fail(h, MPPI_E_UNSUPPORTED, "closed loop: frozen waypoint mode, one robot, one GPU, analytic dynamics");
+    if (h->strict || h->mlp || h->world > 1)
+        return fail(h, MPPI_E_UNSUPPORTED, "closed loop: frozen waypoint mode, one GPU, analytic dynamics");
     if (plant == 1 && h->cfg.model != MPPI_MODEL_BICYCLE) return MPPI_E_BADARG;
     CK(h, cudaSetDevice(h->cfg.device));
-    const int nx = h->nx;
-    const size_t log_floats = (size_t)4 * (n_ticks + 1) + (size_t)2 * n_ticks;
+    const int nx = h->nx, R = h->cfg.n_robots;
+    const size_t log_floats = ((size_t)4 * (n_ticks + 1) + (size_t)2 * n_ticks) * R;
     if (h->plant_log_cap < n_ticks) {
+        CK(h, cudaStreamSynchronize(h->stream));
         cudaFree(h->d_plant_log); h->d_plant_log = nullptr;
+        if (h->loop_graph) { cudaGraphExecDestroy(h->loop_graph); h->loop_graph = nullptr; }     // it holds the old pointer
         CK(h, cudaMalloc(&h->d_plant_log, sizeof(float) * log_floats));
         h->plant_log_cap = n_ticks;
     }
-    if (!h->d_x0) CK(h, cudaMalloc(&h->d_x0, sizeof(float) * 4 * h->cfg.n_robots));
-    float xs[4] = {0.f, 0.f, 0.f, 0.f};
-    for (int i = 0; i < nx; ++i) xs[i] = (float)x0[i];
-    CK(h, cudaMemcpyAsync(h->d_x0, xs, sizeof(xs), cudaMemcpyHostToDevice, h->stream));
-    CK(h, cudaMemcpyAsync(h->d_plant_log, xs, sizeof(xs), cudaMemcpyHostToDevice, h->stream));
-    CK(h, cudaStreamSynchronize(h->stream));                 // xs is a stack buffer
-    for (int i = 0; i < n_ticks; ++i) {
-        set_seed(h, seed, tick0 + (uint64_t)i);
-        TickArgs a = h->args;
-        a.x0_dev = h->d_x0; a.eps = nullptr; a.S = nullptr; a.flags = F_UPDATE;
-        a.plant_state = h->d_x0; a.plant_log = h->d_plant_log; a.plant_mode = plant; a.plant_tick = i; a.plant_n = n_ticks;
-        int rc = launch_update(h, a, false);
-        if (rc != MPPI_OK) return rc;
+    if (!h->d_x0) CK(h, cudaMalloc(&h->d_x0, sizeof(float) * 4 * R));
+    if (!h->d_loop) {
+        CK(h, cudaMalloc(&h->d_loop, sizeof(unsigned) * 4));
+        CK(h, cudaMemset(h->d_loop, 0, sizeof(unsigned) * 4));
+    }
+    std::vector<float> xs((size_t)4 * R, 0.f);
+    for (int r = 0; r < R; ++r)
+        for (int i = 0; i < nx; ++i) xs[(size_t)4 * r + i] = (float)x0[(size_t)r * nx + i];
+    const unsigned loop0[4] = {(unsigned)tick0, (unsigned)tick0, 0u, 0u};          // running tick, first tick, ticket
+    CK(h, cudaMemcpyAsync(h->d_x0, xs.data(), sizeof(float) * 4 * R, cudaMemcpyHostToDevice, h->stream));
+    CK(h, cudaMemcpyAsync(h->d_plant_log, xs.data(), sizeof(float) * 4 * R, cudaMemcpyHostToDevice, h->stream));
+    CK(h, cudaMemcpyAsync(h->d_loop, loop0, sizeof(loop0), cudaMemcpyHostToDevice, h->stream));
+    CK(h, cudaStreamSynchronize(h->stream));                 // xs / loop0 are stack / heap temporaries
+
+    // The n ticks as ONE CUDA graph of n identical kernel nodes: every launch carries the same arguments (the running tick
+    // and the log row come from d_loop, advanced by each launch's last CTA), so the instantiated graph is reused by every
+    // later call with the same (n_ticks, plant, seed, sample-cost flag, obstacle set); MPPI_CLOSED_LOOP_GRAPH=0 falls back
+    // to n stream launches (A/B measurements).
+    set_seed(h, seed, 0);
+    TickArgs a = h->args;
+    a.x0_dev = h->d_x0; a.eps = nullptr; a.S = nullptr; a.flags = F_UPDATE;
+    if (R > 1) a.out_host = nullptr;
+    a.plant_state = h->d_x0; a.plant_log = h->d_plant_log; a.plant_mode = plant; a.plant_tick = 0; a.plant_n = n_ticks;
+    a.loop_state = h->d_loop; a.loop_ticket = h->d_loop + 2;
+    static const bool use_graph = [] { const char *e = std::getenv("MPPI_CLOSED_LOOP_GRAPH"); return !(e && e[0] == '0'); }();
+    const bool same = h->loop_graph && h->loop_graph_n == n_ticks && std::memcmp(&h->loop_graph_args, &a, sizeof(TickArgs)) == 0;
+    if (use_graph && !same) {
+        if (h->loop_graph) { cudaGraphExecDestroy(h->loop_graph); h->loop_graph = nullptr; }
+        cudaGraph_t g = nullptr;
+        const int launches_before = h->tm.launches;
+        CK(h, cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+        int rc = MPPI_OK;
+        for (int i = 0; i < n_ticks && rc == MPPI_OK; ++i) rc = launch_update(h, a, false);
+        cudaError_t ce = cudaStreamEndCapture(h->stream, &g);
+        h->tm.launches = launches_before;                     // captured, not launched yet
+        if (rc != MPPI_OK || ce != cudaSuccess) { if (g) cudaGraphDestroy(g); cudaGetLastError(); return fail(h, MPPI_E_CUDA, "closed loop: graph capture failed"); }
+        ce = cudaGraphInstantiate(&h->loop_graph, g, 0);
+        cudaGraphDestroy(g);
+        if (ce != cudaSuccess) { h->loop_graph = nullptr; return fail(h, MPPI_E_CUDA, "closed loop: graph instantiation failed"); }
+        h->loop_graph_n = n_ticks; h->loop_graph_args = a;
+    }
+    if (use_graph) {
+        CK(h, cudaGraphLaunch(h->loop_graph, h->stream));
+        h->tm.launches += n_ticks;
+    } else {
+        for (int i = 0; i < n_ticks; ++i) {
+            int rc = launch_update(h, a, false);
+            if (rc != MPPI_OK) return rc;
+        }
     }
     std::vector<float> log(log_floats);
     CK(h, cudaMemcpyAsync(log.data(), h->d_plant_log, sizeof(float) * log_floats, cudaMemcpyDeviceToHost, h->stream));
     CK(h, cudaStreamSynchronize(h->stream));
-    for (int i = 0; i <= n_ticks; ++i)
-        for (int j = 0; j < nx; ++j) states_out[(size_t)i * nx + j] = log[(size_t)4 * i + j];
-    if (controls_out) std::memcpy(controls_out, log.data() + (size_t)4 * (n_ticks + 1), sizeof(float) * 2 * n_ticks);
-    return MPPI_OK;
+    for (size_t i = 0; i < (size_t)(n_ticks + 1) * R; ++i)
+        for (int j = 0; j < nx; ++j) states_out[i * nx + j] = log[4 * i + j];
+    if (controls_out) std::memcpy(controls_out, log.data() + (size_t)4 * (n_ticks + 1) * R, sizeof(float) * 2 * n_ticks * R);
+    return R == 1 ? check_tick_faults(h) : MPPI_OK;
 }
 
 int mppi_step_batched(mppi_handle_t h, const float *d_x0, uint64_t seed, uint64_t tick, float *d_u0_out) {

@@ -90,9 +90,14 @@ struct TickArgs {
     float *out_host;                  // mapped pinned mirror of out (robot 0) or null
     float *u0_out;                    // batched: [R][2] or null
     float *triple_out;                // [NF] per-GPU triple (F_TRIPLE_OUT)
-    float *plant_state;               // closed loop: [4] plant state, advanced by the last block after the update, or null
-    float *plant_log;                 // closed loop: [(n+1)][4] states and [n][2] controls behind them
+    float *plant_state;               // closed loop: [R][4] plant states, advanced by each robot's last block after the update, or null
+    float *plant_log;                 // closed loop: [(n+1)][R][4] states and [n][R][2] controls behind them
     int plant_mode, plant_tick, plant_n;
+    // graph-captured closed loop: every launch carries the SAME arguments; the running tick lives on the device.
+    // loop_state[0] = absolute tick of this launch (added to `tick`), [1] = first tick of the loop (log row = [0] - [1]);
+    // the grid's last CTA to finish (loop_ticket over all gridDim.x * gridDim.y CTAs) advances [0].  Null otherwise.
+    unsigned *loop_state;
+    unsigned *loop_ticket;
     // fused multi-GPU exchange (F_P2P): peer_buf[p] = rank p's exchange buffer (own buffer at index p2p_rank)
     unsigned long long *peer_buf[MPPI_MAX_PEERS];
     int p2p_rank, p2p_world;
@@ -138,8 +143,9 @@ __device__ __forceinline__ void box_muller(uint32_t ra, uint32_t rb, float &z0, 
 }
 
 // eps for timesteps 2p (e[0],e[1]) and 2p+1 (e[2],e[3]) of global sample k
-__device__ __forceinline__ void philox_eps_pair(const TickArgs &a, uint32_t k, uint32_t p, uint32_t robot, float e[4]) {
-    uint32_t c0 = k, c1 = p, c2 = a.tick, c3 = robot;
+// `tick_add`: tick offset supplied on the device (graph-captured closed loops read the running tick from memory)
+__device__ __forceinline__ void philox_eps_pair(const TickArgs &a, uint32_t k, uint32_t p, uint32_t robot, float e[4], uint32_t tick_add = 0u) {
+    uint32_t c0 = k, c1 = p, c2 = a.tick + tick_add, c3 = robot;
     philox4x32_10(c0, c1, c2, c3, a.seed_lo, a.seed_hi);
     float z0, z1, z2, z3;
     box_muller(c0, c1, z0, z1);
@@ -612,7 +618,8 @@ __device__ __forceinline__ float clampf(float v, float lim) { return fminf(fmaxf
 // steps of the CURRENT pair (FMA-pipe work), so the ALU, MUFU and FMA pipes are busy at the same time.
 template <int MODEL, int COLL, bool SUM, bool INJ, int WIN, int SPT>
 __device__ __forceinline__ void rollout_samples(const TickArgs &a, const TickSmem &sm, const uint32_t (&kg)[SPT], const int (&klocal)[SPT],
-                                                uint32_t robot, const bool (&exploit)[SPT], float2 *stash, float (&smooth)[SPT], int (&ncoll)[SPT]) {
+                                                uint32_t robot, const bool (&exploit)[SPT], float2 *stash, float (&smooth)[SPT], int (&ncoll)[SPT],
+                                                uint32_t tick_add = 0u) {
     const int T = a.T;
     float z[SPT][4], cs[SPT], sn[SPT], acc[SPT], v0[SPT], v1[SPT], yaw_eff[SPT];
     int nc[SPT];
@@ -634,7 +641,7 @@ __device__ __forceinline__ void rollout_samples(const TickArgs &a, const TickSme
             if (tp < T) { const float2 ea = eps_k[s][tp]; e[0] = ea.x; e[1] = ea.y; }
             if (tp + 1 < T) { const float2 eb = eps_k[s][tp + 1]; e[2] = eb.x; e[3] = eb.y; }
         } else {
-            philox_eps_pair(a, kg[s], (uint32_t)(tp >> 1), robot, e);
+            philox_eps_pair(a, kg[s], (uint32_t)(tp >> 1), robot, e, tick_add);
         }
     };
     auto step = [&](int s, int t, float e0, float e1) {

@@ -241,8 +241,10 @@ __device__ void finalize_tick(const TickArgs &a, int robot, int idx_new, MergeSm
         if (a.u0_out) { a.u0_out[2 * robot] = u0x; a.u0_out[2 * robot + 1] = u0y; }
         if (a.plant_state) {
             // A17: plant step between ticks.  0: DifferentialDrive.update_state (mppi_differential_drive.py:33-40),
-            // unclamped u0; 1: Vehicle.update (models/vehicle.py:95-110), clamp then Euler bicycle.
-            float *ps = a.plant_state;
+            // unclamped u0; 1: Vehicle.update (models/vehicle.py:95-110), clamp then Euler bicycle.  One plant per robot.
+            const int R = gridDim.y;
+            const int pt = a.loop_state ? (int)(__ldcg(a.loop_state) - __ldcg(a.loop_state + 1)) : a.plant_tick;
+            float *ps = a.plant_state + 4 * robot;
             float px = ps[0], py = ps[1], pyaw = ps[2], pv = ps[3];
             float sn, cs;
             sincos_cw(pyaw, sn, cs);
@@ -253,9 +255,9 @@ __device__ void finalize_tick(const TickArgs &a, int robot, int idx_new, MergeSm
                 px += pv * cs * a.dt; py += pv * sn * a.dt; pyaw += pv * a.dt_over_L * tanf(steer); pv += accel * a.dt;
             }
             ps[0] = px; ps[1] = py; ps[2] = pyaw; ps[3] = pv;
-            float *lg = a.plant_log + 4 * (a.plant_tick + 1);
+            float *lg = a.plant_log + 4 * ((size_t)(pt + 1) * R + robot);
             lg[0] = px; lg[1] = py; lg[2] = pyaw; lg[3] = pv;
-            float *lu = a.plant_log + 4 * (a.plant_n + 1) + 2 * a.plant_tick;
+            float *lu = a.plant_log + 4 * (size_t)(a.plant_n + 1) * R + 2 * ((size_t)pt * R + robot);
             lu[0] = u0x; lu[1] = u0y;
         }
         if (!(a.flags & F_KEEP_IDX)) a.idx[robot] = idx_new;
@@ -283,7 +285,7 @@ struct RunSmem {
 extern __shared__ __align__(16) unsigned char mppi_dyn_smem[];
 
 template <int MODEL, int COLL, bool SUM, bool INJ, int WIN, bool STASH>
-__global__ void __launch_bounds__(MPPI_BLOCK, STASH ? MPPI_STASH_BLOCKS : MPPI_MIN_BLOCKS) mppi_tick_kernel(const __grid_constant__ TickArgs a) {
+__device__ __forceinline__ void tick_body(const TickArgs &a, const uint32_t tick_add) {
     __shared__ TickSmem sm;
     __shared__ RunSmem run;
     __shared__ MergeSmem ms;
@@ -386,7 +388,7 @@ __global__ void __launch_bounds__(MPPI_BLOCK, STASH ? MPPI_STASH_BLOCKS : MPPI_M
                     if (active[s]) { smooth[s] = Srow[k[s]]; ncoll[s] = a.NC ? a.NC[k[s]] : 0; }
             } else {
                 rollout_samples<MODEL, COLL, SUM, INJ, WIN, SPT>(a, sm, kg, ksafe, (uint32_t)robot, exploit,
-                                                                 STASH ? stash + tid : nullptr, smooth, ncoll);
+                                                                 STASH ? stash + tid : nullptr, smooth, ncoll, tick_add);
 #pragma unroll
                 for (int s = 0; s < SPT; ++s) {
                     if (active[s] && (a.flags & F_WRITE_S)) Srow[k[s]] = smooth[s] + MPPI_PENALTY * (float)ncoll[s];
@@ -472,7 +474,7 @@ __global__ void __launch_bounds__(MPPI_BLOCK, STASH ? MPPI_STASH_BLOCKS : MPPI_M
                             e[0] = ea.x; e[1] = ea.y;
                             if (tp + 1 < T) { const float2 eb = eps_k[s][tp + 1]; e[2] = eb.x; e[3] = eb.y; }
                         } else {
-                            philox_eps_pair(a, kg[s], (uint32_t)(tp >> 1), (uint32_t)robot, e);
+                            philox_eps_pair(a, kg[s], (uint32_t)(tp >> 1), (uint32_t)robot, e, tick_add);
                         }
                         p0 = fmaf(w[s], e[0], p0); p1 = fmaf(w[s], e[1], p1); p2 = fmaf(w[s], e[2], p2); p3 = fmaf(w[s], e[3], p3);
                     }
@@ -632,6 +634,26 @@ __global__ void __launch_bounds__(MPPI_BLOCK, STASH ? MPPI_STASH_BLOCKS : MPPI_M
     }
     finalize_tick(a, robot, s_new, ms);
     if (a.trace && tid == 0 && robot == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); a.trace[2 * B + 1] = t; }
+}
+
+template <int MODEL, int COLL, bool SUM, bool INJ, int WIN, bool STASH>
+__global__ void __launch_bounds__(MPPI_BLOCK, STASH ? MPPI_STASH_BLOCKS : MPPI_MIN_BLOCKS) mppi_tick_kernel(const __grid_constant__ TickArgs a) {
+    // graph-captured closed loop: the tick this launch computes is read from device memory (every CTA reads it before any
+    // CTA of the same launch can advance it: the advance happens after ALL CTAs have taken a ticket, below)
+    const uint32_t tick_add = a.loop_state ? __ldcg(a.loop_state) : 0u;
+    tick_body<MODEL, COLL, SUM, INJ, WIN, STASH>(a, tick_add);
+    if (a.loop_state) {
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence();
+            const unsigned total = gridDim.x * gridDim.y;
+            if (atomicAdd(a.loop_ticket, 1u) == total - 1u) {
+                *a.loop_ticket = 0u;
+                __threadfence();
+                atomicAdd(a.loop_state, 1u);
+            }
+        }
+    }
 }
 
 // Merge of G per-GPU triples (after the all-gather) + finalize; identical on every rank.

@@ -62,6 +62,16 @@ class BatchedMPPI:
         self._tick += 1
         return self._u0
 
+    def run_closed_loop(self, x0, n_ticks):
+        """The whole fleet in closed loop ON THE DEVICE: every robot ticks and advances its own plant
+        (DifferentialDrive.update_state, controllers/mppi_differential_drive.py:33-40; Vehicle.update for the race-car)
+        n_ticks times, no host round trip -- one CUDA graph of n_ticks launches.  x0: (R, nx) array.  Returns
+        (states (n+1, R, nx), controls (n, R, 2)) float32."""
+        states, controls = self._engine.run_closed_loop(np.asarray(x0, dtype=np.float64), int(n_ticks), self.seed, self._tick,
+                                                        1 if self.nx == 4 else 0)
+        self._tick += int(n_ticks)
+        return states, controls
+
     def nominal(self):
         self._engine.synchronize()
         return self._engine.get_nominal()

@@ -227,14 +227,16 @@ class MPPIEngine:
         self._ck(self.lib.mppi_generate_noise_robot(self._h, seed, tick, robot, _dptr(d_out)), "mppi_generate_noise")
 
     def run_closed_loop(self, x0, n_ticks, seed=0, tick0=0, plant=0):
-        """n_ticks control ticks with the plant step on the device between them.  Returns (states (n+1,nx),
-        controls (n,2)) float32."""
-        self._load_x0(x0)
-        states = np.zeros((n_ticks + 1, self.nx), dtype=np.float32)
-        controls = np.zeros((n_ticks, 2), dtype=np.float32)
-        self._ck(self.lib.mppi_run_closed_loop(self._h, self._x0, n_ticks, seed, tick0, plant,
+        """n_ticks control ticks with the plant step on the device between them (one CUDA graph).  Returns (states
+        (n+1,nx), controls (n,2)) float32; for a fleet handle (n_robots = R, x0 (R,nx)): (n+1,R,nx) and (n,R,2)."""
+        x = np.ascontiguousarray(np.asarray(x0, dtype=np.float64).reshape(self.R, -1)[:, :self.nx])
+        states = np.zeros((n_ticks + 1, self.R, self.nx), dtype=np.float32)
+        controls = np.zeros((n_ticks, self.R, 2), dtype=np.float32)
+        self._ck(self.lib.mppi_run_closed_loop(self._h, x.ctypes.data_as(_lib._PD), n_ticks, seed, tick0, plant,
                                                states.ctypes.data_as(_lib._PF), controls.ctypes.data_as(_lib._PF)),
                  "mppi_run_closed_loop")
+        if self.R == 1:
+            return states[:, 0], controls[:, 0]
         return states, controls
 
     def step_batched(self, d_x0, d_u0_out=None, seed=0, tick=0):

@@ -229,10 +229,14 @@ int mppi_get_top_trajectories(mppi_handle_t h, const double *x0, const float *d_
                               int32_t *d_idx_out, float *d_cost_out);
 
 /* On-device closed loop (A17): n_ticks control ticks with the plant step applied on the device between them, no
- * host round trip per tick.  plant 0 = DifferentialDrive.update_state (controllers/mppi_differential_drive.py:33-40,
- * Euler unicycle, unclamped u0); plant 1 = Vehicle.update (models/vehicle.py:95-110, clamp then Euler bicycle).
- * Tick i uses the Philox stream (seed, tick0 + i).  Frozen waypoint mode, one robot.
- *   states_out  host, (n_ticks+1)*nx floats: x_0 .. x_n;   controls_out  host, n_ticks*2 floats (may be NULL) */
+ * host round trip per tick; the n ticks run as ONE CUDA graph (instantiated on first use, re-launched afterwards).
+ * plant 0 = DifferentialDrive.update_state (controllers/mppi_differential_drive.py:33-40, Euler unicycle, unclamped u0);
+ * plant 1 = Vehicle.update (models/vehicle.py:95-110, clamp then Euler bicycle).  Tick i uses the Philox stream
+ * (seed, tick0 + i).  Frozen waypoint mode.  FLEETS: a handle created with n_robots = R runs R independent closed loops
+ * (own state, nominal, waypoint index and Philox stream per robot; R copies of the loop at :305-367) in the same launches.
+ *   x0           host, R*nx doubles
+ *   states_out   host, (n_ticks+1)*R*nx floats: [tick][robot][nx], row 0 = x0
+ *   controls_out host, n_ticks*R*2 floats: [tick][robot][2] (may be NULL) */
 int mppi_run_closed_loop(mppi_handle_t h, const double *x0, int32_t n_ticks, uint64_t seed, uint64_t tick0,
                          int32_t plant, float *states_out, float *controls_out);
 

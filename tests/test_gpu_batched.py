@@ -149,3 +149,87 @@ def test_batched_per_robot_paths_match_independent_oracle_ticks():
     b.engine.set_ref_path(Golden("diffdrive_pe0.05").path)
     assert b.ref_path(3).shape[0] == 168
     b.engine.close()
+
+
+# ---- SURVEY 8f row 1 remainder: fleets in closed loop on the device, the n-tick loop captured in a CUDA graph ---------------
+def _fleet_oracle_loop(b, sp, path, x0, r, n, plant, tick_base=0, U=None, idx=0):
+    """Robot r of the fleet stepped from the host: oracle tick fed the robot's exported Philox noise + the reference plant."""
+    K, T = sp.K, sp.T
+    eps = torch.zeros(K, T, 2, dtype=torch.float32, device="cuda")
+    x = x0.astype(np.float32).astype(np.float64)
+    U = np.zeros((T, 2)) if U is None else U
+    xs, us = [x.copy()], []
+    for i in range(n):
+        b.engine.generate_noise(eps, seed=b.seed, tick=tick_base + i, robot=r)
+        o = co.tick(sp, path, U, idx, x.astype(np.float32).astype(np.float64), eps.cpu().numpy())
+        U, idx = o["U_after"], o["idx_after"]
+        x = plant(x, o["u0"])
+        xs.append(x.copy()); us.append(o["u0"].copy())
+    return np.array(xs), np.array(us), U, idx
+
+
+@pytest.mark.parametrize("model", ["diffdrive", "bicycle"])
+def test_fleet_closed_loop_on_device_matches_independent_oracle_loops(model):
+    from mppi_b200.batched import BatchedMPPI
+    R, K, n = 6, 1024, 12
+    rng = np.random.default_rng(3)
+    if model == "diffdrive":
+        T = 20
+        path = Golden("diffdrive_pe0.05").path
+        sp = orc.diffdrive_spec(K=K, T=T, param_exploration=0.05, cost_mode="sum", waypoint_mode="frozen")
+        sp.temperature = 2.0
+        b = BatchedMPPI(R, path, num_samples_K=K, num_horizons_T=T, temperature=2.0, seed=9)
+        x0 = np.stack([np.append(path[(11 * r) % 120, :2] + rng.normal(0, 0.05, 2), path[(11 * r) % 120, 2]) for r in range(R)])
+        plant = lambda x, u: orc.plant_diffdrive(x, u, sp.dt)          # noqa: E731
+    else:
+        T = 20
+        path = Golden("racecar_noobs").path
+        sp = orc.racecar_spec(K=K, T=T, obstacles=None, dtype=np.float64)
+        b = BatchedMPPI(R, path, model="bicycle", delta_t=0.05, max_u=(0.523, 2.0), num_samples_K=K, num_horizons_T=T,
+                        param_exploration=0.01, param_lambda=50.0, param_alpha=1.0, sigma=((0.5, 0.0), (0.0, 0.1)),
+                        stage_cost_weight=(50.0, 50.0, 1.0, 20.0), terminal_cost_weight=(50.0, 50.0, 1.0, 20.0),
+                        window=200, seed=9)
+        x0 = np.stack([path[(9 * r) % 80] + rng.normal(0, [0.2, 0.2, 0.03, 0.3]) for r in range(R)])
+        plant = lambda x, u: orc.plant_bicycle(x, u, sp.dt)            # noqa: E731
+    states, controls = b.run_closed_loop(x0, n)
+    assert states.shape == (n + 1, R, b.nx) and controls.shape == (n, R, 2)
+    # a SECOND call continues every robot's loop (same instantiated graph, ticks n .. 2n-1)
+    states2, controls2 = b.run_closed_loop(states[-1], n)
+    launches = b.engine.timings()["launches"]
+    assert launches == 2 * n, launches                                  # one launch per tick for the whole fleet
+    idx_dev, U_dev = b.waypoint_idx(), b.nominal()
+    for r in range(R):
+        xs, us, U, idx = _fleet_oracle_loop(b, sp, path, x0[r], r, n, plant)
+        assert np.max(np.abs(states[:, r] - xs)) <= 5e-4, (model, r, np.max(np.abs(states[:, r] - xs)))
+        assert np.max(np.abs(controls[:, r] - us)) <= 2e-4, (model, r)
+        xs2, us2, U, idx = _fleet_oracle_loop(b, sp, path, states[-1, r].astype(np.float64), r, n, plant, tick_base=n, U=U, idx=idx)
+        assert np.max(np.abs(states2[:, r] - xs2)) <= 2e-3, (model, r, np.max(np.abs(states2[:, r] - xs2)))
+        assert idx_dev[r] == idx
+        assert np.max(np.abs(U_dev[r] - U)) <= 5e-3
+    b.engine.close()
+
+
+def test_fleet_of_4096_robots_50_ticks_closed_loop_subset_vs_oracle():
+    """BASELINE config 4 in closed loop: 4096 robots x K=1024 x H=30, 50 ticks, no host round trip; a random subset of
+    robots against independent oracle loops (the loops are compared over the first 15 ticks: afterwards FP32/FP64
+    differences are amplified by the closed loop itself)."""
+    from mppi_b200.batched import BatchedMPPI
+    path = Golden("diffdrive_pe0.05").path
+    R, K, T, n = 4096, 1024, 30, 50
+    b = BatchedMPPI(R, path, num_samples_K=K, num_horizons_T=T, temperature=2.0, seed=4)
+    rng = np.random.default_rng(0)
+    x0 = np.stack([np.append(path[r % 100, :2] + rng.normal(0, 0.1, 2), path[r % 100, 2] + rng.normal(0, 0.1)) for r in range(R)])
+    b.engine.set_waypoint_idx(np.arange(R) % 100)                       # every robot starts next to its own waypoint
+    states, controls = b.run_closed_loop(x0, n)
+    assert np.all(np.isfinite(states)) and np.all(np.isfinite(controls))
+    sp = orc.diffdrive_spec(K=K, T=T, param_exploration=0.05, cost_mode="sum", waypoint_mode="frozen")
+    sp.temperature = 2.0
+    plant = lambda x, u: orc.plant_diffdrive(x, u, sp.dt)              # noqa: E731
+    for r in rng.choice(R, 4, replace=False):
+        xs, us, _, _ = _fleet_oracle_loop(b, sp, path, x0[r], int(r), 15, plant, idx=int(r % 100))
+        assert np.max(np.abs(states[:16, r] - xs)) <= 1e-3, (r, np.max(np.abs(states[:16, r] - xs)))
+        assert np.max(np.abs(controls[:15, r] - us)) <= 5e-4, r
+    # every robot made progress along the path (the fleet really ran closed loop, not 50 copies of tick 0)
+    idx = b.waypoint_idx()
+    assert np.median(idx - np.arange(R) % 100) >= 15, np.median(idx - np.arange(R) % 100)
+    b.engine.close()

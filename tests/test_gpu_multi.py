@@ -1,5 +1,7 @@
-"""Sample sharding over 2 GPUs with the NCCL all-gather of (min, sum w, sum w*eps): the sharded
-controller must produce the same nominal as the single-GPU one (same global Philox samples)."""
+"""Sample sharding over 2 GPUs: the exchange of (min, sum w, sum w*eps) fused into the tick kernel over NVLink peer
+memory (default) or as an NCCL all-gather; the sharded controller must produce the same nominal as the single-GPU one
+(same global Philox samples), bit-identical on every rank, and a rank that never arrives must fail THAT tick loudly
+without touching the nominal."""
 import os
 import socket
 
@@ -71,3 +73,63 @@ def test_two_gpu_sharded_tick_equals_single_gpu(exchange):
     for i in range(ticks):
         u0, u, _, _ = single._calc_input_control(x)
         assert np.max(np.abs(u - got[0][i])) <= 2e-5, (i, np.max(np.abs(u - got[0][i])))
+
+
+def _timeout_worker(rank, world, port, out):
+    import sys
+    import time
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path[:0] = [root, os.path.join(root, "dnn-mppi-mpc_b200"), os.path.join(root, "tests")]
+    os.environ["MPPI_P2P_TIMEOUT_MS"] = "300"
+    import torch.distributed as dist
+    from mppi_b200 import MppiError
+    from mppi_b200.mppi_differential_drive import MPPIAlgorithms
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    ctrl = MPPIAlgorithms(**_kwargs(1 << 14, 30), device=rank, rank=rank, world=world)
+    ctrl.comm_init_from_torch()
+    x = np.array([0.1, 0.05, 0.2])
+    res = {}
+    u0, u, _, _ = ctrl._calc_input_control(x)                 # tick 0: both ranks on time
+    res["tick0"] = u.copy()
+    dist.barrier()
+    before = ctrl.engine.get_nominal().copy()
+    idx_before = ctrl.prev_way_point_idx
+    if rank == 1:
+        time.sleep(1.5)                                       # rank 1 arrives 1.5 s late: rank 0's 300 ms guard expires
+    try:
+        ctrl._calc_input_control(x)
+        res["tick1"] = "ok"
+    except MppiError as e:
+        res["tick1"] = str(e)
+    res["nominal_untouched"] = bool(np.array_equal(ctrl.engine.get_nominal(), before)) and ctrl.prev_way_point_idx == idx_before
+    dist.barrier()
+    # the application resynchronises (here: both ranks reset the nominal) and carries on; the error does not stick
+    ctrl.u_prev = np.zeros((30, 2))
+    ctrl.prev_way_point_idx = 0
+    dist.barrier()
+    u0, u, _, _ = ctrl._calc_input_control(x)
+    res["tick2"] = u.copy()
+    out.put((rank, res))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_fused_exchange_peer_timeout_fails_the_tick_and_clears():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_timeout_worker, args=(r, 2, port, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = dict(out.get(timeout=300) for _ in range(2))
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    assert np.array_equal(got[0]["tick0"], got[1]["tick0"])
+    assert "timed out" in got[0]["tick1"] and got[0]["nominal_untouched"], got[0]["tick1"]     # MPPI_E_NCCL, tick not applied
+    assert got[1]["tick1"] == "ok"                           # the late rank found rank 0's words waiting
+    assert np.array_equal(got[0]["tick2"], got[1]["tick2"])   # and the next tick is healthy on both

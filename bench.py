@@ -528,6 +528,13 @@ def run_b200_arm(args):
         torch.cuda.synchronize()
         extras["batched_R4096_K1024_H30"] = {"ms_per_tick": a.elapsed_time(b) / 10,
                                              "sample_steps_per_sec": R * 1024 * 30 / (a.elapsed_time(b) / 10 * 1e-3)}
+        # the same fleet in closed loop ON the device: 50 ticks + per-robot plant steps as one CUDA graph (second call: the
+        # instantiated graph is reused), host wall time incl. the state-log read-back
+        xs_np = np.zeros((R, 3))
+        bm.run_closed_loop(xs_np, 50)
+        t1 = time.perf_counter()
+        bm.run_closed_loop(xs_np, 50)
+        extras["batched_R4096_K1024_H30"]["device_closed_loop_ms_per_tick"] = 1e3 * (time.perf_counter() - t1) / 50
         bm.engine.close()
         # config[2]: diff-drive + simple_mlp residual (random-init weights), K=65536, H=30, tcgen05 MLP rollout
         rngw = np.random.default_rng(0)

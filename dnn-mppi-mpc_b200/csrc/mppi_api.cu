@@ -62,6 +62,7 @@ struct mppi_handle_s {
     int plant_log_cap = 0;
     unsigned *d_loop = nullptr;                 // closed loop: running tick, first tick, ticket (see TickArgs::loop_state)
     cudaGraphExec_t loop_graph = nullptr;       // the n-tick closed loop, instantiated once per (n_ticks, arguments)
+    cudaStream_t cap_stream = nullptr;          // private stream the loop is captured on
     int loop_graph_n = 0;
     TickArgs loop_graph_args{};
     int *d_idx = nullptr, *d_NC = nullptr;
@@ -354,6 +355,7 @@ int mppi_destroy(mppi_handle_t h) {
             if (p != h->rank && h->peer_buf[p]) cudaIpcCloseMemHandle(h->peer_buf[p]);
     cudaFree(h->d_xchg); cudaFree(h->d_trace); cudaFree(h->d_loop);
     if (h->loop_graph) cudaGraphExecDestroy(h->loop_graph);
+    if (h->cap_stream) cudaStreamDestroy(h->cap_stream);
     cudaFree(h->d_paths); cudaFree(h->d_path_len);
     cudaFree(h->d_Sc); cudaFree(h->d_Ssorted); cudaFree(h->d_sorted_idx); cudaFree(h->d_iota); cudaFree(h->d_sort_temp);
     if (h->mlp) mlp_destroy(h->mlp);
@@ -907,10 +909,19 @@ int mppi_run_closed_loop(mppi_handle_t h, const double *x0, int32_t n_ticks, uin
         if (h->loop_graph) { cudaGraphExecDestroy(h->loop_graph); h->loop_graph = nullptr; }
         cudaGraph_t g = nullptr;
         const int launches_before = h->tm.launches;
-        CK(h, cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+        // captured on a private stream (the caller's may be the legacy default stream, which cannot capture); the graph
+        // itself is launched on the handle's stream
+        if (!h->cap_stream) CK(h, cudaStreamCreateWithFlags(&h->cap_stream, cudaStreamNonBlocking));
+        cudaStream_t user_stream = h->stream;
+        if (cudaStreamBeginCapture(h->cap_stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+            cudaGetLastError();
+            return fail(h, MPPI_E_CUDA, "closed loop: cannot begin stream capture");
+        }
+        h->stream = h->cap_stream;
         int rc = MPPI_OK;
         for (int i = 0; i < n_ticks && rc == MPPI_OK; ++i) rc = launch_update(h, a, false);
-        cudaError_t ce = cudaStreamEndCapture(h->stream, &g);
+        h->stream = user_stream;
+        cudaError_t ce = cudaStreamEndCapture(h->cap_stream, &g);
         h->tm.launches = launches_before;                     // captured, not launched yet
         if (rc != MPPI_OK || ce != cudaSuccess) { if (g) cudaGraphDestroy(g); cudaGetLastError(); return fail(h, MPPI_E_CUDA, "closed loop: graph capture failed"); }
         ce = cudaGraphInstantiate(&h->loop_graph, g, 0);

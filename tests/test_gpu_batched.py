@@ -229,7 +229,10 @@ def test_fleet_of_4096_robots_50_ticks_closed_loop_subset_vs_oracle():
         xs, us, _, _ = _fleet_oracle_loop(b, sp, path, x0[r], int(r), 15, plant, idx=int(r % 100))
         assert np.max(np.abs(states[:16, r] - xs)) <= 1e-3, (r, np.max(np.abs(states[:16, r] - xs)))
         assert np.max(np.abs(controls[:15, r] - us)) <= 5e-4, r
-    # every robot made progress along the path (the fleet really ran closed loop, not 50 copies of tick 0)
-    idx = b.waypoint_idx()
-    assert np.median(idx - np.arange(R) % 100) >= 15, np.median(idx - np.arange(R) % 100)
+    # the fleet really ran closed loop (not 50 copies of tick 0): the robots, started ~0.13 m off the path, converge onto it
+    def cross_track(xy):
+        return np.sqrt(((xy[:, None, :] - path[None, :, :2]) ** 2).sum(-1)).min(axis=1).mean()
+    sub = rng.choice(R, 256, replace=False)
+    assert cross_track(states[-1, sub, :2]) < 0.5 * cross_track(states[0, sub, :2]), (cross_track(states[0, sub, :2]), cross_track(states[-1, sub, :2]))
+    assert np.median(np.abs(controls[1:] - controls[:-1]).max(axis=(0, 2))) > 1e-3          # controls change from tick to tick
     b.engine.close()

@@ -100,7 +100,31 @@ struct mppi_handle_s {
     cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
     mppi_timings_t tm{};
     std::string err;
+    std::vector<std::pair<void *, size_t>> guards;     // (buffer, payload bytes) of every guarded allocation
 };
+
+// Every device buffer of a handle is allocated with a 256-byte guard zone behind it (pattern 0xA5); mppi_debug_check_guards
+// verifies that no kernel wrote past a buffer's end -- the bounds evidence the sanitize subset collects on pools where
+// compute-sanitizer cannot run.
+#define MPPI_GUARD_BYTES 256
+template <typename T>
+static cudaError_t gmalloc(mppi_handle_t h, T **p, size_t bytes) {
+    void *raw = nullptr;
+    cudaError_t e = cudaMalloc(&raw, bytes + MPPI_GUARD_BYTES);
+    if (e != cudaSuccess) { *p = nullptr; return e; }
+    e = cudaMemset((char *)raw + bytes, 0xA5, MPPI_GUARD_BYTES);
+    if (e != cudaSuccess) { cudaFree(raw); *p = nullptr; return e; }
+    *p = (T *)raw;
+    h->guards.push_back({raw, bytes});
+    return cudaSuccess;
+}
+template <typename T>
+static void gfree(mppi_handle_t h, T *p) {
+    if (!p) return;
+    for (size_t i = 0; i < h->guards.size(); ++i)
+        if (h->guards[i].first == (void *)p) { h->guards.erase(h->guards.begin() + i); break; }
+    cudaFree((void *)p);
+}
 
 #define CK(h, call)                                                                         \
     do {                                                                                    \
@@ -288,22 +312,22 @@ int mppi_create(const mppi_config_t *cfg, mppi_handle_t *out) {
     h->grid_x_stash = std::max(1, std::min(gxs, chunks));
     gx = std::max(h->grid_x, h->grid_x_stash);
 
-    CKC(cudaMalloc(&h->d_U, sizeof(float) * R * T * 2));
+    CKC(gmalloc(h, &h->d_U, sizeof(float) * R * T * 2));
     CKC(cudaMemset(h->d_U, 0, sizeof(float) * R * T * 2));
-    CKC(cudaMalloc(&h->d_M, sizeof(float) * T * T));
-    CKC(cudaMalloc(&h->d_S, sizeof(float) * (size_t)R * K));
-    CKC(cudaMalloc(&h->d_NC, sizeof(int) * (size_t)K));
-    CKC(cudaMalloc(&h->d_part, sizeof(float) * (size_t)R * gx * MPPI_NF(T)));
-    CKC(cudaMalloc(&h->d_out, sizeof(float) * (size_t)R * MPPI_OUT_STRIDE));
+    CKC(gmalloc(h, &h->d_M, sizeof(float) * T * T));
+    CKC(gmalloc(h, &h->d_S, sizeof(float) * (size_t)R * K));
+    CKC(gmalloc(h, &h->d_NC, sizeof(int) * (size_t)K));
+    CKC(gmalloc(h, &h->d_part, sizeof(float) * (size_t)R * gx * MPPI_NF(T)));
+    CKC(gmalloc(h, &h->d_out, sizeof(float) * (size_t)R * MPPI_OUT_STRIDE));
     CKC(cudaMemset(h->d_out, 0, sizeof(float) * (size_t)R * MPPI_OUT_STRIDE));
-    CKC(cudaMalloc(&h->d_idx, sizeof(int) * R));
+    CKC(gmalloc(h, &h->d_idx, sizeof(int) * R));
     CKC(cudaMemset(h->d_idx, 0, sizeof(int) * R));
-    CKC(cudaMalloc(&h->d_ticket, sizeof(unsigned) * R));
+    CKC(gmalloc(h, &h->d_ticket, sizeof(unsigned) * R));
     CKC(cudaMemset(h->d_ticket, 0, sizeof(unsigned) * R));
     CKC(cudaHostAlloc(&h->h_out, sizeof(float) * MPPI_OUT_STRIDE, cudaHostAllocMapped));
     std::memset(h->h_out, 0, sizeof(float) * MPPI_OUT_STRIDE);
     CKC(cudaHostGetDevicePointer(&h->h_out_dev, h->h_out, 0));
-    CKC(cudaMalloc(&h->d_first, sizeof(unsigned long long)));
+    CKC(gmalloc(h, &h->d_first, sizeof(unsigned long long)));
     CKC(cudaHostAlloc(&h->h_first, sizeof(unsigned long long), cudaHostAllocDefault));
     for (auto &e : h->ev) CKC(cudaEventCreate(&e));
     std::vector<float> M;
@@ -353,15 +377,15 @@ int mppi_destroy(mppi_handle_t h) {
     if (h->p2p)
         for (int p = 0; p < h->world; ++p)
             if (p != h->rank && h->peer_buf[p]) cudaIpcCloseMemHandle(h->peer_buf[p]);
-    cudaFree(h->d_xchg); cudaFree(h->d_trace); cudaFree(h->d_loop);
+    gfree(h, h->d_xchg); gfree(h, h->d_trace); gfree(h, h->d_loop);
     if (h->loop_graph) cudaGraphExecDestroy(h->loop_graph);
     if (h->cap_stream) cudaStreamDestroy(h->cap_stream);
-    cudaFree(h->d_paths); cudaFree(h->d_path_len);
-    cudaFree(h->d_Sc); cudaFree(h->d_Ssorted); cudaFree(h->d_sorted_idx); cudaFree(h->d_iota); cudaFree(h->d_sort_temp);
+    gfree(h, h->d_paths); gfree(h, h->d_path_len);
+    gfree(h, h->d_Sc); gfree(h, h->d_Ssorted); gfree(h, h->d_sorted_idx); gfree(h, h->d_iota); gfree(h, h->d_sort_temp);
     if (h->mlp) mlp_destroy(h->mlp);
-    cudaFree(h->d_path); cudaFree(h->d_U); cudaFree(h->d_M); cudaFree(h->d_S); cudaFree(h->d_part);
-    cudaFree(h->d_out); cudaFree(h->d_idx); cudaFree(h->d_NC); cudaFree(h->d_ticket); cudaFree(h->d_first);
-    cudaFree(h->d_bp_n); cudaFree(h->d_bp_s); cudaFree(h->d_send); cudaFree(h->d_recv); cudaFree(h->d_x0); cudaFree(h->d_opt); cudaFree(h->d_plant_log);
+    gfree(h, h->d_path); gfree(h, h->d_U); gfree(h, h->d_M); gfree(h, h->d_S); gfree(h, h->d_part);
+    gfree(h, h->d_out); gfree(h, h->d_idx); gfree(h, h->d_NC); gfree(h, h->d_ticket); gfree(h, h->d_first);
+    gfree(h, h->d_bp_n); gfree(h, h->d_bp_s); gfree(h, h->d_send); gfree(h, h->d_recv); gfree(h, h->d_x0); gfree(h, h->d_opt); gfree(h, h->d_plant_log);
     if (h->h_out) cudaFreeHost(h->h_out);
     if (h->h_first) cudaFreeHost(h->h_first);
     for (auto &e : h->ev) if (e) cudaEventDestroy(e);
@@ -395,12 +419,12 @@ int mppi_set_ref_path(mppi_handle_t h, const double *path, int32_t n, int32_t nc
         const double *r = path + (size_t)i * ncol;
         p[i] = make_float4((float)r[0], (float)r[1], (float)r[2], ncol == 4 ? (float)r[3] : 0.f);
     }
-    cudaFree(h->d_path); h->d_path = nullptr;
-    cudaFree(h->d_bp_n); cudaFree(h->d_bp_s); h->d_bp_n = nullptr; h->d_bp_s = nullptr;
-    CK(h, cudaMalloc(&h->d_path, sizeof(float4) * n));
+    gfree(h, h->d_path); h->d_path = nullptr;
+    gfree(h, h->d_bp_n); gfree(h, h->d_bp_s); h->d_bp_n = nullptr; h->d_bp_s = nullptr;
+    CK(h, gmalloc(h, &h->d_path, sizeof(float4) * n));
     CK(h, cudaMemcpy(h->d_path, p.data(), sizeof(float4) * n, cudaMemcpyHostToDevice));
-    CK(h, cudaMalloc(&h->d_bp_n, sizeof(unsigned) * (n + 2)));
-    CK(h, cudaMalloc(&h->d_bp_s, sizeof(int) * (n + 2)));
+    CK(h, gmalloc(h, &h->d_bp_n, sizeof(unsigned) * (n + 2)));
+    CK(h, gmalloc(h, &h->d_bp_s, sizeof(int) * (n + 2)));
     h->path_h.assign(path, path + (size_t)n * ncol);
     h->n_path = n; h->path_cols = ncol;
     h->args.path = h->d_path; h->args.n_path = n;
@@ -426,11 +450,11 @@ int mppi_set_ref_paths_spline(mppi_handle_t h, const float *d_wx, const float *d
     const int R = h->cfg.n_robots;
     if (h->path_cap < max_points) {
         CK(h, cudaStreamSynchronize(h->stream));
-        cudaFree(h->d_paths); h->d_paths = nullptr;
-        CK(h, cudaMalloc(&h->d_paths, sizeof(float4) * (size_t)R * max_points));
+        gfree(h, h->d_paths); h->d_paths = nullptr;
+        CK(h, gmalloc(h, &h->d_paths, sizeof(float4) * (size_t)R * max_points));
         h->path_cap = max_points;
     }
-    if (!h->d_path_len) CK(h, cudaMalloc(&h->d_path_len, sizeof(int) * R));
+    if (!h->d_path_len) CK(h, gmalloc(h, &h->d_path_len, sizeof(int) * R));
     CK(h, mppi_launch_spline(d_wx, d_wy, R, n_wp, ds, h->path_cap, h->d_paths, h->d_path_len, h->stream));
     h->tm.launches++;
     std::vector<int> len((size_t)R);
@@ -813,7 +837,7 @@ int mppi_get_trajectories(mppi_handle_t h, const double *x0, const float *d_eps,
     TickArgs a = h->args;
     a.eps = d_eps;
     const int nx = h->nx, T = h->cfg.T;
-    if (optimal_out && !h->d_opt) CK(h, cudaMalloc(&h->d_opt, sizeof(float) * MPPI_MAX_T * 4));
+    if (optimal_out && !h->d_opt) CK(h, gmalloc(h, &h->d_opt, sizeof(float) * MPPI_MAX_T * 4));
     CK(h, mppi_launch_traj(a, h->cfg.model, h->d_out, optimal_out ? h->d_opt : nullptr, d_sampled_out, nullptr, 0, 1, h->stream));
     h->tm.launches++;
     if (optimal_out) CK(h, cudaMemcpyAsync(optimal_out, h->d_opt, sizeof(float) * T * nx, cudaMemcpyDeviceToHost, h->stream));
@@ -827,12 +851,12 @@ int mppi_set_keep_costs(mppi_handle_t h, int32_t on) {
     CK(h, cudaSetDevice(h->cfg.device));
     if (on && !h->d_Sc) {
         const int K = h->cfg.K;
-        CK(h, cudaMalloc(&h->d_Sc, sizeof(float) * K));
-        CK(h, cudaMalloc(&h->d_Ssorted, sizeof(float) * K));
-        CK(h, cudaMalloc(&h->d_sorted_idx, sizeof(int) * K));
-        CK(h, cudaMalloc(&h->d_iota, sizeof(int) * K));
+        CK(h, gmalloc(h, &h->d_Sc, sizeof(float) * K));
+        CK(h, gmalloc(h, &h->d_Ssorted, sizeof(float) * K));
+        CK(h, gmalloc(h, &h->d_sorted_idx, sizeof(int) * K));
+        CK(h, gmalloc(h, &h->d_iota, sizeof(int) * K));
         h->sort_temp_bytes = mppi_sort_costs_temp_bytes(K);
-        CK(h, cudaMalloc(&h->d_sort_temp, h->sort_temp_bytes ? h->sort_temp_bytes : 16));
+        CK(h, gmalloc(h, &h->d_sort_temp, h->sort_temp_bytes ? h->sort_temp_bytes : 16));
     }
     h->keep_costs = on != 0;
     return MPPI_OK;
@@ -851,7 +875,7 @@ int mppi_get_top_trajectories(mppi_handle_t h, const double *x0, const float *d_
     a.eps = d_eps;
     const int nx = h->nx, T = h->cfg.T;
     CK(h, mppi_sort_costs(h->d_Sc, h->cfg.K, h->d_Ssorted, h->d_sorted_idx, h->d_iota, h->d_sort_temp, h->sort_temp_bytes, h->stream));
-    if (optimal_out && !h->d_opt) CK(h, cudaMalloc(&h->d_opt, sizeof(float) * MPPI_MAX_T * 4));
+    if (optimal_out && !h->d_opt) CK(h, gmalloc(h, &h->d_opt, sizeof(float) * MPPI_MAX_T * 4));
     CK(h, mppi_launch_traj(a, h->cfg.model, h->d_out, optimal_out ? h->d_opt : nullptr, d_traj_out, h->d_sorted_idx, n_top,
                            index_shift, h->stream));
     h->tm.launches += 3;
@@ -874,14 +898,14 @@ int mppi_run_closed_loop(mppi_handle_t h, const double *x0, int32_t n_ticks, uin
     const size_t log_floats = ((size_t)4 * (n_ticks + 1) + (size_t)2 * n_ticks) * R;
     if (h->plant_log_cap < n_ticks) {
         CK(h, cudaStreamSynchronize(h->stream));
-        cudaFree(h->d_plant_log); h->d_plant_log = nullptr;
+        gfree(h, h->d_plant_log); h->d_plant_log = nullptr;
         if (h->loop_graph) { cudaGraphExecDestroy(h->loop_graph); h->loop_graph = nullptr; }     // it holds the old pointer
-        CK(h, cudaMalloc(&h->d_plant_log, sizeof(float) * log_floats));
+        CK(h, gmalloc(h, &h->d_plant_log, sizeof(float) * log_floats));
         h->plant_log_cap = n_ticks;
     }
-    if (!h->d_x0) CK(h, cudaMalloc(&h->d_x0, sizeof(float) * 4 * R));
+    if (!h->d_x0) CK(h, gmalloc(h, &h->d_x0, sizeof(float) * 4 * R));
     if (!h->d_loop) {
-        CK(h, cudaMalloc(&h->d_loop, sizeof(unsigned) * 4));
+        CK(h, gmalloc(h, &h->d_loop, sizeof(unsigned) * 4));
         CK(h, cudaMemset(h->d_loop, 0, sizeof(unsigned) * 4));
     }
     std::vector<float> xs((size_t)4 * R, 0.f);
@@ -955,7 +979,7 @@ int mppi_step_batched(mppi_handle_t h, const float *d_x0, uint64_t seed, uint64_
     set_seed(h, seed, tick);
     TickArgs a = h->args;
     // (R, nx) -> padded (R, 4) staging so every robot's state is one aligned read
-    if (!h->d_x0) CK(h, cudaMalloc(&h->d_x0, sizeof(float) * 4 * h->cfg.n_robots));
+    if (!h->d_x0) CK(h, gmalloc(h, &h->d_x0, sizeof(float) * 4 * h->cfg.n_robots));
     CK(h, cudaMemcpy2DAsync(h->d_x0, 4 * sizeof(float), d_x0, h->nx * sizeof(float), h->nx * sizeof(float),
                             h->cfg.n_robots, cudaMemcpyDeviceToDevice, h->stream));
     a.x0_dev = h->d_x0; a.eps = nullptr; a.S = nullptr; a.flags = F_UPDATE; a.u0_out = d_u0_out;
@@ -987,8 +1011,8 @@ int mppi_comm_init(mppi_handle_t h, const void *uid, int32_t rank, int32_t world
     if (r != ncclSuccess) { h->err = g_nccl.GetErrorString(r); return MPPI_E_NCCL; }
     h->rank = rank; h->world = world;
     const size_t nf = MPPI_NF(h->cfg.T);
-    CK(h, cudaMalloc(&h->d_send, sizeof(float) * nf));
-    CK(h, cudaMalloc(&h->d_recv, sizeof(float) * nf * world));
+    CK(h, gmalloc(h, &h->d_send, sizeof(float) * nf));
+    CK(h, gmalloc(h, &h->d_recv, sizeof(float) * nf * world));
     return MPPI_OK;
 }
 
@@ -997,7 +1021,7 @@ int mppi_comm_p2p_export(mppi_handle_t h, int32_t world, void *out64) {
     if (h->cfg.n_robots != 1 || h->strict) return fail(h, MPPI_E_UNSUPPORTED, "sample sharding needs frozen mode, one robot");
     CK(h, cudaSetDevice(h->cfg.device));
     if (!h->d_xchg) {
-        CK(h, cudaMalloc(&h->d_xchg, sizeof(unsigned long long) * (MPPI_XCHG_WORDS + MPPI_XCHG_TRACE)));
+        CK(h, gmalloc(h, &h->d_xchg, sizeof(unsigned long long) * (MPPI_XCHG_WORDS + MPPI_XCHG_TRACE)));
         CK(h, cudaMemset(h->d_xchg, 0, sizeof(unsigned long long) * (MPPI_XCHG_WORDS + MPPI_XCHG_TRACE)));
         CK(h, cudaDeviceSynchronize());
     }
@@ -1034,7 +1058,7 @@ int mppi_set_trace(mppi_handle_t h, int32_t on) {
     CK(h, cudaStreamSynchronize(h->stream));
     if (on && !h->d_trace) {
         h->trace_n = 2 * (std::max(h->grid_x, h->grid_x_stash) + 1);
-        CK(h, cudaMalloc(&h->d_trace, sizeof(unsigned long long) * h->trace_n));
+        CK(h, gmalloc(h, &h->d_trace, sizeof(unsigned long long) * h->trace_n));
         CK(h, cudaMemset(h->d_trace, 0, sizeof(unsigned long long) * h->trace_n));
     }
     h->args.trace = on ? h->d_trace : nullptr;
@@ -1050,6 +1074,21 @@ int mppi_get_trace(mppi_handle_t h, uint64_t *out, int32_t capacity, int32_t *n_
     CK(h, cudaStreamSynchronize(h->stream));
     *n_ctas_out = h->stash ? h->grid_x_stash : h->grid_x;
     return MPPI_OK;
+}
+
+int mppi_debug_check_guards(mppi_handle_t h) {
+    if (!h) return MPPI_E_BADARG;
+    CK(h, cudaSetDevice(h->cfg.device));
+    CK(h, cudaStreamSynchronize(h->stream));
+    unsigned char g[MPPI_GUARD_BYTES];
+    int bad = 0;
+    for (const auto &b : h->guards) {
+        CK(h, cudaMemcpy(g, (const char *)b.first + b.second, MPPI_GUARD_BYTES, cudaMemcpyDeviceToHost));
+        for (int i = 0; i < MPPI_GUARD_BYTES; ++i)
+            if (g[i] != 0xA5) { ++bad; break; }
+    }
+    if (h->mlp) bad += mlp_check_guards(h->mlp);
+    return bad;                                           // number of buffers whose guard zone was overwritten (0 = clean)
 }
 
 int mppi_comm_p2p_trace(mppi_handle_t h, uint64_t stamps_out[4]) {

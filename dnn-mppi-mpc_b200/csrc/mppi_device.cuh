@@ -7,6 +7,17 @@
 #include <math_constants.h>
 #include "../../include/mppi_b200.h"
 
+// -DMPPI_DEBUG_CHECKS=1: device-side bounds / protocol assertions at every shared-memory and global hand-off (the build the
+// sanitize subset runs when compute-sanitizer is not available on the pool; a failed check traps the kernel)
+#ifndef MPPI_DEBUG_CHECKS
+#define MPPI_DEBUG_CHECKS 0
+#endif
+#if MPPI_DEBUG_CHECKS
+#include <assert.h>
+#define MPPI_DCHECK(c) assert(c)
+#else
+#define MPPI_DCHECK(c) ((void)0)
+#endif
 #ifndef MPPI_BLOCK
 #define MPPI_BLOCK 256
 #endif
@@ -442,6 +453,7 @@ __device__ __forceinline__ int nearest_wp(const TickSmem &sm, float x, float y) 
 }
 
 __device__ __forceinline__ float4 window_ref(const TickSmem &sm, int j) {
+    MPPI_DCHECK(j >= 0 && j < MPPI_MAX_WINDOW);
     const float2 yv = sm.wyv[j];
     return make_float4(-sm.wx[j], -sm.wy[j], yv.x, yv.y);
 }
@@ -645,6 +657,7 @@ __device__ __forceinline__ void rollout_samples(const TickArgs &a, const TickSme
         }
     };
     auto step = [&](int s, int t, float e0, float e1) {
+        MPPI_DCHECK(t >= 0 && t < T);
         if (stash) stash[t * MPPI_CHUNK + s * MPPI_BLOCK] = make_float2(e0, e1);
         const float2 u = sm.U[t];
         v0[s] = clampf(exploit[s] ? __fadd_rn(u.x, e0) : e0, a.umax0);                   // A4, A5

@@ -109,6 +109,7 @@ __device__ void merge_partials(const TickArgs &a, const float *parts, int P, Mer
         }
         __syncthreads();                                      // every thread is done with sc[]: reuse it for the group sums
         float *red4 = sc;                                     // [G4][NF]: G4 * NF <= (MPPI_BLOCK / NQ) * 4 NQ = 4 MPPI_BLOCK floats... of which <= 1024 at 256 threads
+        MPPI_DCHECK(G4 * NF <= MPPI_MERGE_SCRATCH && P <= MPPI_MERGE_TILE);
         if (g4 < G4) *reinterpret_cast<float4 *>(red4 + (size_t)g4 * NF + 4 * cq) = acc4;
         __syncthreads();
         for (int c = 2 + tid; c < NF; c += MPPI_BLOCK) {
@@ -312,6 +313,7 @@ __device__ __forceinline__ void tick_body(const TickArgs &a, const uint32_t tick
         // waypoint, so the window below is never empty
         const int s_old = max(0, min(a.idx[robot], n_path - 1));
         unsigned long long key = ~0ull;
+        MPPI_DCHECK(n_path >= 1 && s_old >= 0 && s_old < n_path && a.window <= MPPI_MAX_WINDOW);
         for (int j = tid; j < a.window && s_old + j < n_path; j += MPPI_BLOCK) {
             const float4 p = rpath[s_old + j];
             const float dx = sm.x0[0] - p.x, dy = sm.x0[1] - p.y;
@@ -332,6 +334,7 @@ __device__ __forceinline__ void tick_body(const TickArgs &a, const uint32_t tick
     }
     {
         int nw = n_path - s_new; nw = nw < a.window ? nw : a.window;
+        MPPI_DCHECK(WIN < 0 || (s_new >= 0 && s_new < n_path && nw >= 1));
         // static-window kernels read exactly 20 entries, dynamic ones whole chunks of 16
         const int fill = (WIN < 0) ? 0 : (WIN == 20) ? 20 : ((nw + 15) & ~15);
         for (int j = tid; j < fill; j += MPPI_BLOCK) {
@@ -366,6 +369,7 @@ __device__ __forceinline__ void tick_body(const TickArgs &a, const uint32_t tick
     constexpr int SPT = MPPI_SPT;
     const int k_begin = (int)((long long)K * b / B);
     const int k_end = (a.flags & F_IDX_ONLY) ? k_begin : (int)((long long)K * (b + 1) / B);
+    MPPI_DCHECK(k_begin >= 0 && k_end <= K && (!STASH || (size_t)T * MPPI_CHUNK * sizeof(float2) <= 232448));
     float *Srow = a.S ? a.S + (size_t)robot * K : nullptr;
     for (int base = k_begin; base < k_end; base += MPPI_CHUNK) {
         int k[SPT], ksafe[SPT], ncoll[SPT];
@@ -565,6 +569,7 @@ __device__ __forceinline__ void tick_body(const TickArgs &a, const uint32_t tick
         if (tid == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_stamp[0]));
         for (int i = tid; i < G * NF; i += MPPI_BLOCK) {
             const int p = i / NF, c = i - p * NF;
+            MPPI_DCHECK(MPPI_XCHG_SLOT(par, me) + c < MPPI_XCHG_WORDS && G <= MPPI_MAX_PEERS && me < G);
             unsigned long long *dst = a.peer_buf[p] + MPPI_XCHG_SLOT(par, me) + c;
             const unsigned long long v = ((unsigned long long)seq << 32) | (unsigned long long)__float_as_uint(ms.col[c]);
             asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(dst), "l"(v) : "memory");
@@ -771,6 +776,7 @@ __global__ void __launch_bounds__(MPPI_BLOCK) mppi_strict_kernel(const __grid_co
         if (bj != s && n >= check_from) atomicMin(first_change, ((unsigned long long)n << 32) | (unsigned)bj);
         const bool stage = t < T, last = (t == T - 1);
         if ((stage && (SUM || last)) || t == T) {
+            MPPI_DCHECK(bj >= 0 && bj < a.n_path && bp < nbp);
             const float4 ref = a.path[bj];
             const float yaw_eff = a.yaw_wrap ? wrap_2pi(z[2]) : z[2];
             float c = tracking_cost<MODEL>(ref, z, yaw_eff, stage ? a.sw : a.tw);

@@ -248,6 +248,7 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
 // record turns the cost into NaN instead of garbage), then every thread reads its row past L1 (ld.global.cg).
 __device__ __forceinline__ void handoff_give(float *hand, unsigned int *hand_flag, unsigned int epoch, int tile_slot, int flag_idx,
                                              int row, bool signaller, int n_owner_threads, const float (&z)[4], float acc, float vp0, float vp1) {
+    MPPI_DCHECK(tile_slot >= 0 && flag_idx >= 0 && row >= 0 && row < TILE_M);
     float *rec = hand + (size_t)tile_slot * 6 * TILE_M + row;
     __stcg(rec, z[0]); __stcg(rec + TILE_M, z[1]); __stcg(rec + 2 * TILE_M, z[2]);
     __stcg(rec + 3 * TILE_M, acc); __stcg(rec + 4 * TILE_M, vp0); __stcg(rec + 5 * TILE_M, vp1);
@@ -890,7 +891,8 @@ MlpState *mlp_create(int K, int T) {
     cudaDeviceGetAttribute(&m->n_sm, cudaDevAttrMultiProcessorCount, dev);
     if (cudaMalloc(&m->d_w2, sizeof(mlp_op_t) * 2 * HID * HID) != cudaSuccess ||
         cudaMalloc(&m->d_bh, sizeof(float) * HID) != cudaSuccess ||
-        cudaMalloc(&m->d_hand, sizeof(float) * (size_t)(m->n_sm / 2 + 1) * 2 * 2 * 6 * TILE_M) != cudaSuccess ||
+        cudaMalloc(&m->d_hand, sizeof(float) * ((size_t)(m->n_sm / 2 + 1) * 2 * 2 * 6 * TILE_M + 64)) != cudaSuccess ||
+        cudaMemset(m->d_hand + (size_t)(m->n_sm / 2 + 1) * 2 * 2 * 6 * TILE_M, 0xA5, sizeof(float) * 64) != cudaSuccess ||
         cudaMalloc(&m->d_hand_flag, sizeof(unsigned int) * ((size_t)(m->n_sm / 2 + 1) * 2 + 1)) != cudaSuccess ||
         cudaMemset(m->d_hand_flag, 0, sizeof(unsigned int) * ((size_t)(m->n_sm / 2 + 1) * 2 + 1)) != cudaSuccess ||
         cudaMalloc(&m->d_w01, sizeof(float4) * HID) != cudaSuccess ||
@@ -1048,6 +1050,14 @@ int mlp_rollout_costs(MlpState *m, const TickArgs &args, bool sum, const float *
 }
 
 int mlp_launches_per_tick(const MlpState *) { return 1; }
+
+int mlp_check_guards(MlpState *m) {
+    if (!m || !m->d_hand) return 0;
+    unsigned char g[256];
+    if (cudaMemcpy(g, m->d_hand + (size_t)(m->n_sm / 2 + 1) * 2 * 2 * 6 * TILE_M, 256, cudaMemcpyDeviceToHost) != cudaSuccess) return 1;
+    for (int i = 0; i < 256; ++i) if (g[i] != 0xA5) return 1;
+    return 0;
+}
 
 bool mlp_take_fault(MlpState *m, cudaStream_t st) {
     if (!m || !m->d_hand_flag) return false;

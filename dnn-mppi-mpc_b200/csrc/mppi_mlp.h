@@ -26,3 +26,5 @@ int mlp_rollout_costs(MlpState *m, const TickArgs &a, bool sum, const float *d_e
 int mlp_launches_per_tick(const MlpState *m);
 // true (and cleared) if a cluster hand-off of the balanced schedule was missed since the last call
 bool mlp_take_fault(MlpState *m, cudaStream_t st);
+// number of hand-off buffers whose guard zone was overwritten (0 = clean)
+int mlp_check_guards(MlpState *m);

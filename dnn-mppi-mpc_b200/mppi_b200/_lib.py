@@ -85,6 +85,7 @@ SYMBOLS = {
     "mppi_comm_p2p_trace": (C.c_int, [_H, C.POINTER(C.c_uint64)]),
     "mppi_set_trace": (C.c_int, [_H, C.c_int32]),
     "mppi_get_trace": (C.c_int, [_H, C.POINTER(C.c_uint64), C.c_int32, _PI]),
+    "mppi_debug_check_guards": (C.c_int, [_H]),
     "mppi_set_timing": (C.c_int, [_H, C.c_int32]),
     "mppi_get_timings": (C.c_int, [_H, C.POINTER(MppiTimings)]),
     "mppi_abi_version": (C.c_int, []),

@@ -259,6 +259,13 @@ class MPPIEngine:
         a = np.frombuffer(buf, dtype=np.uint64)[:2 * (n.value + 1)].astype(np.int64).reshape(-1, 2)
         return a[:n.value], a[n.value]
 
+    def check_guards(self):
+        """Number of device buffers whose guard zone was overwritten (0 = clean)."""
+        n = self.lib.mppi_debug_check_guards(self._h)
+        if n < 0:
+            self._ck(n, "mppi_debug_check_guards")
+        return n
+
     def set_timing(self, on=True):
         self._ck(self.lib.mppi_set_timing(self._h, int(on)), "mppi_set_timing")
 

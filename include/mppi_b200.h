@@ -271,6 +271,9 @@ int mppi_comm_p2p_trace(mppi_handle_t h, uint64_t stamps_out[4]);
 int mppi_set_trace(mppi_handle_t h, int32_t enabled);
 int mppi_get_trace(mppi_handle_t h, uint64_t *out, int32_t capacity, int32_t *n_ctas_out);
 
+/* Every device buffer of a handle carries a 256-byte guard zone; returns how many were overwritten (0 = no kernel wrote
+ * past a buffer), < 0 on error.  Bounds evidence for pools where compute-sanitizer cannot run (profiles/). */
+int mppi_debug_check_guards(mppi_handle_t h);
 int mppi_set_timing(mppi_handle_t h, int32_t enabled);
 int mppi_get_timings(mppi_handle_t h, mppi_timings_t *out);
 int mppi_abi_version(void);

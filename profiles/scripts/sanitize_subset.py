@@ -1,5 +1,7 @@
-"""Reduced workload for compute-sanitizer (memcheck / racecheck / synccheck): every kernel family and every
-shared-memory hand-off the tick relies on, at sizes a 20-50x slowdown can afford.
+"""Reduced workload for memory / race checking: every kernel family and every shared-memory or global hand-off the tick
+relies on.  Meant for compute-sanitizer (memcheck / racecheck); on pools where the sanitizer is closed it is run against
+the -DMPPI_DEBUG_CHECKS=1 build (device-side bounds / protocol assertions trap the kernel) and every handle's guard zones
+are verified after each part (mppi_debug_check_guards).
   python profiles/scripts/sanitize_subset.py [part ...]     parts: tick strict racecar batched loop mlp mlp_balanced p2p
 Run as: compute-sanitizer --tool memcheck python profiles/scripts/sanitize_subset.py tick strict ..."""
 import os
@@ -18,9 +20,11 @@ g = Golden("diffdrive_pe0.05")
 x0 = np.array([0.1, 0.05, 0.2])
 
 
-def done(name, arr):
+def done(name, arr, eng=None):
     assert np.all(np.isfinite(arr)), name
-    print("ok", name, flush=True)
+    if eng is not None:
+        assert eng.check_guards() == 0, "guard zone overwritten: " + name
+    print("ok", name, "(guards clean)" if eng is not None else "", flush=True)
 
 
 if "tick" in parts:
@@ -31,7 +35,7 @@ if "tick" in parts:
     eng = engine_from_spec(sp, g.path)
     for t in range(2):
         u0, u = eng.step(x0, None, seed=3, tick=t)
-    done("tick stash K=100000 (multi-chunk, ragged tail, 296-partial merge)", u)
+    done("tick stash K=100000 (multi-chunk, ragged tail, 296-partial merge)", u, eng)
     eng.close()
     sp = orc.diffdrive_spec(K=3000, T=30, param_exploration=0.05, cost_mode="sum", waypoint_mode="frozen")
     sp.temperature = 2.0
@@ -42,12 +46,12 @@ if "tick" in parts:
     S = torch.zeros(sp.K, device="cuda")
     eng.rollout_costs(x0, S, eps)
     eng.reduce_update(S, eps)
-    done("tick regenerate path (injected noise), K1 alone, K2 alone", u)
+    done("tick regenerate path (injected noise), K1 alone, K2 alone", u, eng)
     eng.close()
     sp = orc.diffdrive_spec(K=2000, T=61, param_exploration=0.05, cost_mode="last", waypoint_mode="frozen")     # horizon too long to stash
     eng = engine_from_spec(sp, g.path)
     u0, u = eng.step(x0, None, seed=3, tick=0)
-    done("tick T=61 (no stash), cost_mode last", u)
+    done("tick T=61 (no stash), cost_mode last", u, eng)
     eng.close()
 
 if "strict" in parts:
@@ -57,7 +61,7 @@ if "strict" in parts:
     for t in range(4):
         u0, u = eng.step(x, None, seed=5, tick=t)
         x = orc.plant_diffdrive(x, u0.astype(np.float64), 0.1)
-    done("strict multi-pass path (passes %d)" % eng.timings()["last_passes"], u)
+    done("strict multi-pass path (passes %d)" % eng.timings()["last_passes"], u, eng)
     eng.close()
 
 if "racecar" in parts:
@@ -69,7 +73,7 @@ if "racecar" in parts:
     eng.set_keep_costs(True)
     u0, u = eng.step(gr.path[4].astype(np.float64), None, seed=2, tick=1)
     eng.top_trajectories(gr.path[4].astype(np.float64), d, 16, seed=2, tick=1)
-    done("race-car dynamic window + footprint collisions + top-N replay", u)
+    done("race-car dynamic window + footprint collisions + top-N replay", u, eng)
     eng.close()
 
 if "batched" in parts or "loop" in parts:
@@ -79,19 +83,19 @@ if "batched" in parts or "loop" in parts:
     xs = np.stack([np.append(g.path[10 * r, :2], g.path[10 * r, 2]) for r in range(R)])
     if "batched" in parts:
         u = b.step(torch.from_numpy(xs.astype(np.float32)).cuda().contiguous()).cpu().numpy()
-        done("batched fleet tick (one CTA per robot, in-CTA merge)", u)
+        done("batched fleet tick (one CTA per robot, in-CTA merge)", u, b.engine)
     if "loop" in parts:
         st, ct = b.run_closed_loop(xs, 4)
         st, ct = b.run_closed_loop(st[-1], 4)
-        done("fleet closed loop as a CUDA graph (device-side tick counter, grid-wide ticket)", st)
+        done("fleet closed loop as a CUDA graph (device-side tick counter, grid-wide ticket)", st, b.engine)
     b.engine.close()
 
 if "mlp" in parts or "mlp_balanced" in parts:
     cases = []
     if "mlp" in parts:
-        cases += [(2048, 8, 3, 2), (2048, 7, 5, 3)]                    # static schedule: one tile per CTA
+        cases += [(2048, 12, 3, 2), (2048, 11, 5, 3)]                    # static schedule: one tile per CTA
     if "mlp_balanced" in parts:
-        cases += [(40000, 6, 3, 2), (40000, 6, 5, 3)]                  # ping-pong + balanced hand-off between clusters
+        cases += [(40000, 10, 3, 2), (40000, 11, 5, 3)]                  # ping-pong + balanced hand-off between clusters
     for K, T, n_in, n_hidden in cases:
         mlp = orc.make_mlp(seed=1, out_scale=0.05, n_in=n_in, scalers=(n_in == 5), scaler_gain=1.0, n_hidden=n_hidden)
         sp = orc.diffdrive_spec(K=K, T=T, param_exploration=0.05, cost_mode="sum", waypoint_mode="frozen", model="diffdrive_mlp", mlp=mlp)
@@ -100,7 +104,7 @@ if "mlp" in parts or "mlp_balanced" in parts:
         sc = [mlp[k] for k in ("in_mean", "in_scale", "out_mean", "out_scale")] if n_in == 5 else []
         eng.set_mlp([mlp["W%d" % i] for i in range(n_hidden + 2)], [mlp["b%d" % i] for i in range(n_hidden + 2)], *sc)
         u0, u = eng.step(x0, None, seed=4, tick=0)
-        done("learned dynamics K=%d T=%d n_in=%d n_hidden=%d" % (K, T, n_in, n_hidden), u)
+        done("learned dynamics K=%d T=%d n_in=%d n_hidden=%d" % (K, T, n_in, n_hidden), u, eng)
         eng.close()
 
 if "p2p" in parts:

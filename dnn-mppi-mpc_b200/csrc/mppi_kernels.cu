@@ -863,8 +863,20 @@ cudaError_t mppi_launch_tick(const TickArgs &a, int model, int coll, int cost_ki
     const size_t dyn = mppi_tick_dyn_smem(a.T, stash);
     return with_tick_kernel(model, coll, cost_kind, sum, inj, a.window == 20, stash, [&](auto kern) {
         if (dyn > 48 * 1024) {
-            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
-            if (e != cudaSuccess) return e;
+            // opt in to > 48 KB of dynamic shared memory once per (instantiation, device), not on every tick
+            static thread_local const void *done_kern[64];
+            static thread_local size_t done_dyn[64];
+            static thread_local int done_dev[64], n_done = 0;
+            int dev = 0;
+            cudaGetDevice(&dev);
+            bool found = false;
+            for (int i = 0; i < n_done; ++i)
+                if (done_kern[i] == (const void *)kern && done_dev[i] == dev && done_dyn[i] >= dyn) { found = true; break; }
+            if (!found) {
+                cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+                if (e != cudaSuccess) return e;
+                if (n_done < 64) { done_kern[n_done] = (const void *)kern; done_dyn[n_done] = dyn; done_dev[n_done] = dev; ++n_done; }
+            }
         }
         kern<<<grid, MPPI_BLOCK, dyn, st>>>(a);
         return cudaGetLastError();

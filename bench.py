@@ -342,6 +342,8 @@ def run_b200_arm(args):
     with torch.cuda.stream(stream):
         for i in range(args.steps):
             flush.zero_()
+            if world > 1:
+                eng.comm_p2p_barrier()      # device-side rank barrier: a slower GPU's flush is not billed to the others' tick
             ev[i][0].record(stream)
             eng.step_async(x0, None, 7, tick); tick += 1
             ev[i][1].record(stream)
@@ -716,7 +718,8 @@ def run_b200_arm(args):
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "diffdrive_K1M_H50_sum_frozen_philox", "K_per_gpu": K_PER_GPU, "K_global": K_global,
                    "H": T_H, "temperature": temperature, "path": "168-point cubic spline (tests/golden/paths.npz)",
-                   "l2": "flushed between timed steps (256 MiB memset, outside the per-step event pair)",
+                   "l2": "flushed between timed steps (256 MiB memset, outside the per-step event pair)" +
+                         ("; ranks aligned by a device-side barrier kernel after the flush, before the start event" if world > 1 else ""),
                    "parallelism": "samples sharded, %d rank(s)" % world,
                    "exchange": None if world == 1 else "fused into the tick kernel: CUDA-IPC peer stores over NVLink (no NCCL call on the data path)"},
         "extras": dict(extras, ess=stats["ess"], wall_s_timed_region=t_wall),

@@ -81,6 +81,7 @@ struct mppi_handle_s {
     unsigned long long *d_xchg = nullptr;
     unsigned long long *peer_buf[MPPI_MAX_PEERS] = {nullptr};
     unsigned p2p_seq = 0, p2p_timeout_ms = 2000;
+    unsigned long long p2p_barrier_count = 0;
     // MLP dynamics
     MlpState *mlp = nullptr;
     // per-robot reference paths (batched fleets)
@@ -1021,8 +1022,8 @@ int mppi_comm_p2p_export(mppi_handle_t h, int32_t world, void *out64) {
     if (h->cfg.n_robots != 1 || h->strict) return fail(h, MPPI_E_UNSUPPORTED, "sample sharding needs frozen mode, one robot");
     CK(h, cudaSetDevice(h->cfg.device));
     if (!h->d_xchg) {
-        CK(h, gmalloc(h, &h->d_xchg, sizeof(unsigned long long) * (MPPI_XCHG_WORDS + MPPI_XCHG_TRACE)));
-        CK(h, cudaMemset(h->d_xchg, 0, sizeof(unsigned long long) * (MPPI_XCHG_WORDS + MPPI_XCHG_TRACE)));
+        CK(h, gmalloc(h, &h->d_xchg, sizeof(unsigned long long) * MPPI_XCHG_TOTAL));
+        CK(h, cudaMemset(h->d_xchg, 0, sizeof(unsigned long long) * MPPI_XCHG_TOTAL));
         CK(h, cudaDeviceSynchronize());
     }
     cudaIpcMemHandle_t ih;
@@ -1044,7 +1045,7 @@ int mppi_comm_p2p_open(mppi_handle_t h, const void *handles, int32_t rank, int32
         CK(h, cudaIpcOpenMemHandle(&ptr, ih, cudaIpcMemLazyEnablePeerAccess));
         h->peer_buf[p] = (unsigned long long *)ptr;
     }
-    h->rank = rank; h->world = world; h->p2p = true; h->p2p_seq = 0;
+    h->rank = rank; h->world = world; h->p2p = true; h->p2p_seq = 0; h->p2p_barrier_count = 0;
     if (const char *env = std::getenv("MPPI_P2P_TIMEOUT_MS")) h->p2p_timeout_ms = (unsigned)std::max(1, std::atoi(env));
     h->h_out[MPPI_OUT_PEER_TIMEOUT] = 0.f;              // no stale peer-timeout report from an earlier communicator
     CK(h, cudaMemsetAsync(h->d_out + MPPI_OUT_PEER_TIMEOUT, 0, sizeof(float), h->stream));
@@ -1089,6 +1090,18 @@ int mppi_debug_check_guards(mppi_handle_t h) {
     }
     if (h->mlp) bad += mlp_check_guards(h->mlp);
     return bad;                                           // number of buffers whose guard zone was overwritten (0 = clean)
+}
+
+int mppi_comm_p2p_barrier(mppi_handle_t h) {
+    if (!h) return MPPI_E_BADARG;
+    if (!h->p2p || h->world < 2) return fail(h, MPPI_E_STATE, "no fused exchange on this handle");
+    CK(h, cudaSetDevice(h->cfg.device));
+    TickArgs b = h->args;
+    for (int p = 0; p < h->world; ++p) b.peer_buf[p] = h->peer_buf[p];
+    b.p2p_rank = h->rank; b.p2p_world = h->world; b.p2p_timeout_ms = h->p2p_timeout_ms;
+    CK(h, mppi_launch_p2p_barrier(b, ++h->p2p_barrier_count, h->stream));
+    h->tm.launches++;
+    return MPPI_OK;
 }
 
 int mppi_comm_p2p_trace(mppi_handle_t h, uint64_t stamps_out[4]) {

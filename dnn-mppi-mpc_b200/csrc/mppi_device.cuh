@@ -47,6 +47,8 @@
 #define MPPI_XCHG_SLOT(par, r) (((par) * MPPI_MAX_PEERS + (r)) * MPPI_NF_MAX)
 #define MPPI_XCHG_WORDS (2 * MPPI_MAX_PEERS * MPPI_NF_MAX)
 #define MPPI_XCHG_TRACE 8              // globaltimer stamps of the last exchange (diagnostics), kept behind the words
+#define MPPI_XCHG_BARRIER (MPPI_XCHG_WORDS + MPPI_XCHG_TRACE)   // then MPPI_MAX_PEERS words of the device-side rank barrier
+#define MPPI_XCHG_TOTAL (MPPI_XCHG_BARRIER + MPPI_MAX_PEERS)
 
 enum : int {
     F_WRITE_S = 1,       // store per-sample costs

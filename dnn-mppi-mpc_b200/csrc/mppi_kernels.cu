@@ -670,6 +670,28 @@ __global__ void __launch_bounds__(MPPI_BLOCK) mppi_merge_kernel(const __grid_con
     finalize_tick(a, 0, __float_as_int(a.out[2]), ms);
 }
 
+// Device-side barrier of the ranks of a fused exchange: every rank stores the barrier count into its word of every peer's
+// buffer and waits until all of its own words have reached it (counts only grow, so a rank already in the next barrier
+// cannot be missed).  Aligns the GPUs on the device, e.g. in front of a timed tick (no host round trip, no NCCL call).
+__global__ void mppi_p2p_barrier_kernel(const __grid_constant__ TickArgs a, unsigned long long count) {
+    const int G = a.p2p_world, me = a.p2p_rank, t = threadIdx.x;
+    if (t >= G) return;
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(a.peer_buf[t] + MPPI_XCHG_BARRIER + me), "l"(count) : "memory");
+    const unsigned long long *mine = a.peer_buf[me] + MPPI_XCHG_BARRIER + t;
+    unsigned long long v, t0, now;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    const unsigned long long limit = (unsigned long long)a.p2p_timeout_ms * 1000000ull;
+    int spins = 0;
+    do {
+        asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(mine) : "memory");
+        if (v >= count) break;
+        if ((++spins & 255) == 0) {
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+            if (now - t0 > limit) { a.out[MPPI_OUT_PEER_TIMEOUT] = 1.f; if (a.out_host) a.out_host[MPPI_OUT_PEER_TIMEOUT] = 1.f; break; }
+        }
+    } while (true);
+}
+
 // A16: visualisation replays of the last tick.  Thread k < K replays sample k's clamped controls, thread K the
 // updated nominal; both index the controls with t-1 (the last row first), as the reference does.
 // With a selection list (`sel`, n_sel entries: the top-N viewer of test/test_mppi_diff_obs.py:102-110) row i of samp_out
@@ -924,6 +946,11 @@ cudaError_t mppi_launch_strict(const TickArgs &a, int model, int coll, bool sum,
         if (coll == MPPI_COLLISION_FOOTPRINT) return launch_strict_mc<MPPI_MODEL_BICYCLE, MPPI_COLLISION_FOOTPRINT>(a, sum, inj, bp_n, bp_s, nbp, k_first, check_from, first_change, st);
     }
     return cudaErrorInvalidValue;
+}
+
+cudaError_t mppi_launch_p2p_barrier(const TickArgs &a, unsigned long long count, cudaStream_t st) {
+    mppi_p2p_barrier_kernel<<<1, 32, 0, st>>>(a, count);
+    return cudaGetLastError();
 }
 
 cudaError_t mppi_launch_merge(const TickArgs &a, const float *triples, int G, cudaStream_t st) {

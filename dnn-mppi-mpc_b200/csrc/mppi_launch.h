@@ -8,6 +8,7 @@ cudaError_t mppi_launch_strict(const TickArgs &a, int model, int coll, bool sum,
                                const int *bp_s, int nbp, int k_first, unsigned check_from,
                                unsigned long long *first_change, cudaStream_t st);
 cudaError_t mppi_launch_merge(const TickArgs &a, const float *triples, int G, cudaStream_t st);
+cudaError_t mppi_launch_p2p_barrier(const TickArgs &a, unsigned long long count, cudaStream_t st);
 cudaError_t mppi_launch_traj(const TickArgs &a, int model, const float *rec, float *d_opt, float *d_samp,
                              const int *d_sel, int n_sel, int shift, cudaStream_t st);
 // mppi_spline.cu: per-robot courses from waypoints (calc_spline_course on the device)

@@ -82,6 +82,7 @@ SYMBOLS = {
     "mppi_comm_init": (C.c_int, [_H, C.c_void_p, C.c_int32, C.c_int32]),
     "mppi_comm_p2p_export": (C.c_int, [_H, C.c_int32, C.c_void_p]),
     "mppi_comm_p2p_open": (C.c_int, [_H, C.c_void_p, C.c_int32, C.c_int32]),
+    "mppi_comm_p2p_barrier": (C.c_int, [_H]),
     "mppi_comm_p2p_trace": (C.c_int, [_H, C.POINTER(C.c_uint64)]),
     "mppi_set_trace": (C.c_int, [_H, C.c_int32]),
     "mppi_get_trace": (C.c_int, [_H, C.POINTER(C.c_uint64), C.c_int32, _PI]),

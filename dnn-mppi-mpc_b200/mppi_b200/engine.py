@@ -292,6 +292,10 @@ class MPPIEngine:
         buf = C.create_string_buffer(handles, 64 * world)
         self._ck(self.lib.mppi_comm_p2p_open(self._h, buf, rank, world), "mppi_comm_p2p_open")
 
+    def comm_p2p_barrier(self):
+        """Device-side barrier of the sharding ranks, enqueued on the engine's stream (asynchronous)."""
+        self._ck(self.lib.mppi_comm_p2p_barrier(self._h), "mppi_comm_p2p_barrier")
+
     def comm_p2p_trace(self):
         """%globaltimer stamps (ns) of the last fused exchange: local merge done, words stored, all ranks seen, updated."""
         t = (C.c_uint64 * 4)()

@@ -261,6 +261,10 @@ int mppi_comm_init(mppi_handle_t h, const void *nccl_unique_id, int32_t rank, in
 #define MPPI_MAX_PEERS 8
 int mppi_comm_p2p_export(mppi_handle_t h, int32_t world, void *ipc_handle_out64);
 int mppi_comm_p2p_open(mppi_handle_t h, const void *ipc_handles, int32_t rank, int32_t world);
+/* Device-side barrier of the ranks of a fused exchange, enqueued on the handle's stream (asynchronous; no host round trip, no
+ * NCCL call): the GPUs leave it within a microsecond of each other.  bench.py aligns the ranks with it in front of each
+ * timed tick so the L2 flush of a slower GPU is not billed to the others' tick. */
+int mppi_comm_p2p_barrier(mppi_handle_t h);
 /* Diagnostics of the last fused exchange on this rank: %globaltimer stamps (ns) of [0] local merge done, [1] words
  * stored, [2] every rank's words seen, [3] nominal updated.  [2]-[1] is the wait for the slowest rank. */
 int mppi_comm_p2p_trace(mppi_handle_t h, uint64_t stamps_out[4]);

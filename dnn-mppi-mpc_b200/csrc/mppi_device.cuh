@@ -299,9 +299,30 @@ __device__ __forceinline__ void chunk_argmin(const float4 *nwx4, const float4 *n
         dx = x + X.w; dy = y + Y.w; d[2 * q + 1].y = fmaf(dy, dy, dx * dx);
 #endif
     }
+#if MPPI_MIN_TREE
+    // minimum of the CH distances as a tree of 3-input minima (depth ~3) instead of a chain of CH/2 dependent ones
+    float m;
+    {
+        float t[CH / 2];
+#pragma unroll
+        for (int i = 0; i < CH / 2; ++i) t[i] = fminf(d[i].x, d[i].y);
+        int n = CH / 2;
+#pragma unroll
+        while (n > 1) {
+            const int n3 = n / 3, rem = n - 3 * n3;
+#pragma unroll
+            for (int i = 0; i < n3; ++i) t[i] = fminf(fminf(t[3 * i], t[3 * i + 1]), t[3 * i + 2]);
+            if (rem == 2) t[n3] = fminf(t[3 * n3], t[3 * n3 + 1]);
+            else if (rem == 1) t[n3] = t[3 * n3];
+            n = n3 + (rem ? 1 : 0);
+        }
+        m = t[0];
+    }
+#else
     float m = fminf(d[0].x, d[0].y);
 #pragma unroll
     for (int i = 1; i < CH / 2; ++i) m = fminf(fminf(m, d[i].x), d[i].y);
+#endif
 #if MPPI_ARGMIN_KEY_SEL
     // index of the first minimum on the ALU pipe: descending select chains (the lowest index is written last), four
     // independent chains of CH/4 entries; FSETP + SEL per entry instead of FADD2 + FFMA2 per pair on the FMA pipe
@@ -332,6 +353,28 @@ __device__ __forceinline__ void chunk_argmin(const float4 *nwx4, const float4 *n
     }
 #endif
     const float2 nm = make_float2(-m, -m), huge = make_float2(1.2676506e30f, 1.2676506e30f);
+#if MPPI_MIN_TREE
+    float kt[CH / 2];
+#pragma unroll
+    for (int i = 0; i < CH / 2; ++i) {
+        const float2 k2 = f2_fma(f2_add(d[i], nm), huge, make_float2((float)(2 * i), (float)(2 * i + 1)));
+        kt[i] = fminf(k2.x, k2.y);
+    }
+    {
+        int n = CH / 2;
+#pragma unroll
+        while (n > 1) {
+            const int n3 = n / 3, rem = n - 3 * n3;
+#pragma unroll
+            for (int i = 0; i < n3; ++i) kt[i] = fminf(fminf(kt[3 * i], kt[3 * i + 1]), kt[3 * i + 2]);
+            if (rem == 2) kt[n3] = fminf(kt[3 * n3], kt[3 * n3 + 1]);
+            else if (rem == 1) kt[n3] = kt[3 * n3];
+            n = n3 + (rem ? 1 : 0);
+        }
+    }
+    m_out = m;
+    key_out = kt[0];
+#else
     float key = CUDART_INF_F;
 #pragma unroll
     for (int i = 0; i < CH / 2; ++i) {
@@ -344,6 +387,7 @@ __device__ __forceinline__ void chunk_argmin(const float4 *nwx4, const float4 *n
     }
     m_out = m;
     key_out = key;
+#endif
 }
 
 // A8: first-min argmin of squared xy distance over the window

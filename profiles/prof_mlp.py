@@ -23,7 +23,16 @@ def make_mlp(seed=0, out_scale=0.01):
 K = int(sys.argv[1]) if len(sys.argv) > 1 else 65536
 T = int(sys.argv[2]) if len(sys.argv) > 2 else 30
 ticks = int(sys.argv[3]) if len(sys.argv) > 3 else 3
-ctrl = MPPIAlgorithms(**diffdrive_kwargs(K, T, 2.0), seed=7, dynamics=make_mlp())
+variant = sys.argv[4] if len(sys.argv) > 4 else "2l"
+mlp = make_mlp()
+if variant == "3l":          # the trained checkpoints' shape: 5 inputs, three hidden layers, scalers
+    rng = np.random.default_rng(1)
+    mlp = {"W0": (rng.uniform(-1, 1, (512, 5)) / np.sqrt(5)).astype(np.float32), "b0": mlp["b0"], "W1": mlp["W1"], "b1": mlp["b1"],
+           "W2": mlp["W2"], "b2": mlp["b2"], "W3": (rng.uniform(-1, 1, (512, 512)) / np.sqrt(512)).astype(np.float32),
+           "b3": (rng.uniform(-1, 1, (512,)) / np.sqrt(512)).astype(np.float32), "W4": mlp["W3"], "b4": mlp["b3"],
+           "in_mean": [4.39, -0.126, -0.08, 0.359, -0.031], "in_scale": [5.587, 3.641, 1.06, 1.024, 1.836],
+           "out_mean": [-0.561, 0.029, -0.015], "out_scale": [5.701, 3.59, 0.996]}
+ctrl = MPPIAlgorithms(**diffdrive_kwargs(K, T, 2.0), seed=7, dynamics=mlp)
 for i in range(ticks):
     ctrl._calc_input_control(np.array([0.4, 0.3, 0.5]))
 print("ok")

@@ -67,6 +67,12 @@ typedef __nv_bfloat16 mlp_op_t;
 #define MLP_UMMA_FMT 1u
 #endif
 
+// -DMPPI_MLP_W3_PARAM=1: the output-layer records (b2, W3[0..2][j]) travel as a kernel parameter (constant bank) and are read
+// with warp-uniform indices instead of one broadcast LDS.128 per (warp, column) -- A/B variant for the shared-memory pipe
+#ifndef MPPI_MLP_W3_PARAM
+#define MPPI_MLP_W3_PARAM 0
+#endif
+
 constexpr int HID = 512;
 constexpr int TILE_M = 128;
 constexpr int KCH = 64;                   // K elements per 128-byte swizzle span (bf16)
@@ -86,6 +92,8 @@ constexpr int TMEM_D_COL = 256;           // two accumulator buffers of 128 FP32
 constexpr int N_GROUPS = 4;                // compute-warp groups: group g owns accumulator quarter g (128 columns)
 constexpr int N_COMPUTE = 128 * N_GROUPS;  // 16 compute warps: 4 per TMEM lane quarter
 constexpr int MLP_THREADS = 64 + N_COMPUTE;
+
+struct MlpW3 { float4 w[HID]; };          // (b2[j], W3[0][j], W3[1][j], W3[2][j]) as a kernel parameter (MPPI_MLP_W3_PARAM)
 
 struct MlpSmem {                          // after the 1024-aligned A / B regions
     float4 w01[HID];                      // (W01[j][0], W01[j][1], W01[j][2], b01[j])
@@ -282,7 +290,11 @@ mppi_mlp_rollout_kernel(const __grid_constant__ TickArgs a, const __grid_constan
                         const float4 *__restrict__ g_w01, const float2 *__restrict__ g_w01u, const float4 *__restrict__ g_w3,
                         const float *__restrict__ g_b3, const float *__restrict__ g_bh, float *__restrict__ S_out, int n_tiles,
                         float *__restrict__ hand, unsigned int *__restrict__ hand_flag, unsigned int *__restrict__ fault,
-                        unsigned int epoch, int balanced) {
+                        unsigned int epoch, int balanced
+#if MPPI_MLP_W3_PARAM
+                        , const __grid_constant__ MlpW3 w3p
+#endif
+                        ) {
     static_assert(NG == 1 || (NG == 2 && !PP), "two GEMMs per step run the one-tile schedule");
     // 1024-byte alignment is what SWIZZLE_128B needs; keeping every pointer derived from this symbol (no
     // integer round-trips) lets the compiler emit LDS/STS instead of generic LD/ST
@@ -612,9 +624,16 @@ mppi_mlp_rollout_kernel(const __grid_constant__ TickArgs a, const __grid_constan
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                 mbar_arrive(&ms.d_empty[buf]);
+#if MPPI_MLP_W3_PARAM
+                const int colu = __shfl_sync(0xffffffffu, col, 0);
+#endif
 #pragma unroll
                 for (int i = 0; i < 32; ++i) {
+#if MPPI_MLP_W3_PARAM
+                    const float4 w = w3p.w[colu + i];
+#else
                     const float4 w = ms.w3[col + i];
+#endif
                     const float h = tanh_approx(__uint_as_float(v[i]) + w.x);
                     r0 = fmaf(w.y, h, r0); r1 = fmaf(w.z, h, r1); r2 = fmaf(w.w, h, r2);
                 }
@@ -817,7 +836,11 @@ mppi_mlp_rollout_kernel(const __grid_constant__ TickArgs a, const __grid_constan
                     mbar_arrive(&ms.d_empty[buf]);                // values are in registers: the buffer may be overwritten
 #pragma unroll
                     for (int i = 0; i < 32; ++i) {
+#if MPPI_MLP_W3_PARAM
+                        const float4 w = w3p.w[__shfl_sync(0xffffffffu, col, 0) + i];
+#else
                         const float4 w = ms.w3[col + i];
+#endif
                         const float h = tanh_approx(__uint_as_float(v[i]) + w.x);
                         r0 = fmaf(w.y, h, r0); r1 = fmaf(w.z, h, r1); r2 = fmaf(w.w, h, r2);
                     }
@@ -879,6 +902,7 @@ struct MlpState {
     unsigned int epoch = 0;
     int n_in = 3, n_gemm = 1;
     CUtensorMap w2_map;
+    MlpW3 h_w3;                           // host copy of the output-layer records (kernel-parameter variant)
     bool ready = false;
 };
 
@@ -968,6 +992,7 @@ cudaError_t mlp_set_weights(MlpState *m, int n_in, int n_hidden, const float *co
     cudaError_t e;
     if ((e = cudaMemcpyAsync(m->d_w01, w01.data(), sizeof(float4) * HID, cudaMemcpyHostToDevice, st)) != cudaSuccess) return e;
     if ((e = cudaMemcpyAsync(m->d_w3, w3.data(), sizeof(float4) * HID, cudaMemcpyHostToDevice, st)) != cudaSuccess) return e;
+    for (int j = 0; j < HID; ++j) m->h_w3.w[j] = w3[j];
     if ((e = cudaMemcpyAsync(m->d_w01u, w01u.data(), sizeof(float2) * HID, cudaMemcpyHostToDevice, st)) != cudaSuccess) return e;
     if ((e = cudaMemcpyAsync(m->d_b3, b3, sizeof(b3), cudaMemcpyHostToDevice, st)) != cudaSuccess) return e;
     if ((e = cudaMemcpyAsync(m->d_w2, w2.data(), sizeof(mlp_op_t) * w2.size(), cudaMemcpyHostToDevice, st)) != cudaSuccess) return e;
@@ -1041,7 +1066,12 @@ int mlp_rollout_costs(MlpState *m, const TickArgs &args, bool sum, const float *
                           (long long)n_quads * a.T / n_clusters >= a.T + 2) ? 1 : 0;
     const unsigned int epoch = ++m->epoch;
     unsigned int *fault = m->d_hand_flag + (size_t)(m->n_sm / 2 + 1) * 2;
-#define MPPI_MLP_LAUNCH(N, P, G) mppi_mlp_rollout_kernel<N, P, G><<<grid, MLP_THREADS, MLP_DYN_SMEM, st>>>(a, m->w2_map, m->d_w01, m->d_w01u, m->d_w3, m->d_b3, m->d_bh, d_S, n_tiles, m->d_hand, m->d_hand_flag, fault, epoch, balanced)
+#if MPPI_MLP_W3_PARAM
+#define MPPI_MLP_W3_ARG , m->h_w3
+#else
+#define MPPI_MLP_W3_ARG
+#endif
+#define MPPI_MLP_LAUNCH(N, P, G) mppi_mlp_rollout_kernel<N, P, G><<<grid, MLP_THREADS, MLP_DYN_SMEM, st>>>(a, m->w2_map, m->d_w01, m->d_w01u, m->d_w3, m->d_b3, m->d_bh, d_S, n_tiles, m->d_hand, m->d_hand_flag, fault, epoch, balanced MPPI_MLP_W3_ARG)
     if (m->n_gemm == 2) { if (m->n_in == 5) MPPI_MLP_LAUNCH(5, false, 2); else MPPI_MLP_LAUNCH(3, false, 2); }
     else if (m->n_in == 5) { if (pp) MPPI_MLP_LAUNCH(5, true, 1); else MPPI_MLP_LAUNCH(5, false, 1); }
     else { if (pp) MPPI_MLP_LAUNCH(3, true, 1); else MPPI_MLP_LAUNCH(3, false, 1); }

@@ -214,9 +214,11 @@ def test_large_K_full_size_property():
     Sg = S.cpu().numpy()
     bad = np.nonzero(np.abs(Sg - So) > 1e-6 + COST_RTOL * np.abs(So))[0]
     # The nearest-waypoint argmin is a discrete decision: where two waypoints are equidistant to
-    # within FP32 rounding, FP32 and FP64 may pick different ones.  Allow <= 2e-4 of the samples,
-    # and require every one of them to be such a near-tie according to the FP64 oracle.
-    assert bad.size <= 2e-4 * K, bad.size
+    # within FP32 rounding, FP32 and FP64 may pick different ones.  Allow <= 1e-4 of the samples (81 of
+    # 1 048 576 measured: a speed-up may not buy itself more flips), and require every one of them to
+    # be such a near-tie according to the FP64 oracle.
+    print("large-K near-tie flips: %d of %d" % (bad.size, K))
+    assert bad.size <= 1e-4 * K, bad.size
     if bad.size:
         wp_m, _ = orc.decision_margins(sp, g.path, np.zeros((T, 2)), 0, x0, eps_h[bad])
         assert wp_m.max() < 1e-4, (bad.size, wp_m.max())

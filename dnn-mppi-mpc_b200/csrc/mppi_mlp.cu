@@ -73,6 +73,12 @@ typedef __nv_bfloat16 mlp_op_t;
 #define MPPI_MLP_W3_PARAM 0
 #endif
 
+// Wrong-result TIMING probes (never shipped; profiles/): 1 = epilogue without the output-layer LDS + FMAs, 2 = layer 1 without its
+// LDS + FMAs, 4 = no MUFU (tanh replaced by the identity); bits may be combined
+#ifndef MPPI_MLP_PROBE
+#define MPPI_MLP_PROBE 0
+#endif
+
 constexpr int HID = 512;
 constexpr int TILE_M = 128;
 constexpr int KCH = 64;                   // K elements per 128-byte swizzle span (bf16)
@@ -209,9 +215,13 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
         : "r"(taddr));
 }
 __device__ __forceinline__ float tanh_approx(float x) {
+#if MPPI_MLP_PROBE & 4
+    return x * 0.5f;
+#else
     float y;
     asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
+#endif
 }
 // two FP32 values -> packed half-precision operand pair (lo in the low half)
 __device__ __forceinline__ uint32_t pack_op2(float lo, float hi) {
@@ -595,9 +605,13 @@ mppi_mlp_rollout_kernel(const __grid_constant__ TickArgs a, const __grid_constan
                         uint32_t pk[4];
 #pragma unroll
                         for (int p = 0; p < 4; ++p) {
+#if MPPI_MLP_PROBE & 2
+                            float pa = st.x + (float)p, pb = st.y + (float)p;
+#else
                             const float4 wa = ms.w01[col + 2 * p], wb = ms.w01[col + 2 * p + 1];
                             float pa = fmaf(wa.x, st.x, fmaf(wa.y, st.y, fmaf(wa.z, st.z, wa.w)));
                             float pb = fmaf(wb.x, st.x, fmaf(wb.y, st.y, fmaf(wb.z, st.z, wb.w)));
+#endif
                             if (NIN == 5) {
                                 const float4 wu = *reinterpret_cast<const float4 *>(&ms.w01u[col + 2 * p]);
                                 pa = fmaf(wu.x, st.w, fmaf(wu.y, su1, pa));
@@ -629,6 +643,10 @@ mppi_mlp_rollout_kernel(const __grid_constant__ TickArgs a, const __grid_constan
 #endif
 #pragma unroll
                 for (int i = 0; i < 32; ++i) {
+#if MPPI_MLP_PROBE & 1
+                    const float h = tanh_approx(__uint_as_float(v[i]));
+                    r0 += h;
+#else
 #if MPPI_MLP_W3_PARAM
                     const float4 w = w3p.w[colu + i];
 #else
@@ -636,6 +654,7 @@ mppi_mlp_rollout_kernel(const __grid_constant__ TickArgs a, const __grid_constan
 #endif
                     const float h = tanh_approx(__uint_as_float(v[i]) + w.x);
                     r0 = fmaf(w.y, h, r0); r1 = fmaf(w.z, h, r1); r2 = fmaf(w.w, h, r2);
+#endif
                 }
             };
             // the step of the tile owned by group og is complete: gather the partial sums, Euler step with the residual
@@ -760,9 +779,13 @@ mppi_mlp_rollout_kernel(const __grid_constant__ TickArgs a, const __grid_constan
                         uint32_t pk[4];
 #pragma unroll
                         for (int p = 0; p < 4; ++p) {
+#if MPPI_MLP_PROBE & 2
+                            float pa = st.x + (float)p, pb = st.y + (float)p;
+#else
                             const float4 wa = ms.w01[col + 2 * p], wb = ms.w01[col + 2 * p + 1];
                             float pa = fmaf(wa.x, st.x, fmaf(wa.y, st.y, fmaf(wa.z, st.z, wa.w)));
                             float pb = fmaf(wb.x, st.x, fmaf(wb.y, st.y, fmaf(wb.z, st.z, wb.w)));
+#endif
                             if (NIN == 5) {
                                 const float4 wu = *reinterpret_cast<const float4 *>(&ms.w01u[col + 2 * p]);
                                 pa = fmaf(wu.x, st.w, fmaf(wu.y, su1, pa));

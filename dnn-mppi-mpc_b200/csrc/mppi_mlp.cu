@@ -79,6 +79,10 @@ typedef __nv_bfloat16 mlp_op_t;
 #define MPPI_MLP_PROBE 0
 #endif
 
+#ifndef MPPI_MLP_L1_EARLY
+#define MPPI_MLP_L1_EARLY 0     // 1: ping-pong layer 1 evaluates a part into registers before waiting for that part of A (A/B variant)
+#endif
+
 constexpr int HID = 512;
 constexpr int TILE_M = 128;
 constexpr int KCH = 64;                   // K elements per 128-byte swizzle span (bf16)
@@ -593,6 +597,41 @@ mppi_mlp_rollout_kernel(const __grid_constant__ TickArgs a, const __grid_constan
                 named_bar_sync(1, N_COMPUTE);
                 const float4 st = ms.xs[row];
                 const float su1 = NIN == 5 ? ms.xw[row] : 0.f;
+#if MPPI_MLP_L1_EARLY
+                // a part's 32 columns are evaluated into registers BEFORE waiting for the running GEMM to release that part
+                // of A: the linear layer + tanh of part p overlap the wait, only the 4 stores sit behind it
+#pragma unroll 1
+                for (int part = 0; part < N_QUARTERS; ++part) {
+                    uint32_t pk[4][4];
+#pragma unroll
+                    for (int c8 = 0; c8 < 4; ++c8) {
+                        const int col = part * N_MMA + grp * 32 + c8 * 8;
+#pragma unroll
+                        for (int p = 0; p < 4; ++p) {
+                            const float4 wa = ms.w01[col + 2 * p], wb = ms.w01[col + 2 * p + 1];
+                            float pa = fmaf(wa.x, st.x, fmaf(wa.y, st.y, fmaf(wa.z, st.z, wa.w)));
+                            float pb = fmaf(wb.x, st.x, fmaf(wb.y, st.y, fmaf(wb.z, st.z, wb.w)));
+                            if (NIN == 5) {
+                                const float4 wu = *reinterpret_cast<const float4 *>(&ms.w01u[col + 2 * p]);
+                                pa = fmaf(wu.x, st.w, fmaf(wu.y, su1, pa));
+                                pb = fmaf(wu.z, st.w, fmaf(wu.w, su1, pb));
+                            }
+                            pk[c8][p] = tanh_op2(pa, pb);
+                        }
+                    }
+                    if (l1_count > 0) {                                   // GEMM #(l1_count-1) is done with this part of A
+                        mbar_wait_warp(&ms.a_free[part], (l1_count - 1) & 1);
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    }
+#pragma unroll
+                    for (int c8 = 0; c8 < 4; ++c8)
+                        tmem_st4(tmem + ((uint32_t)(q * 32) << 16) + TMEM_A_COL + (uint32_t)((part * N_MMA + grp * 32 + c8 * 8) >> 1),
+                                 pk[c8][0], pk[c8][1], pk[c8][2], pk[c8][3]);
+                    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    mbar_arrive(&ms.a_ready[part]);
+                }
+#else
 #pragma unroll 1
                 for (int part = 0; part < N_QUARTERS; ++part) {
                     if (l1_count > 0) {                                   // GEMM #(l1_count-1) is done with this part of A
@@ -625,6 +664,7 @@ mppi_mlp_rollout_kernel(const __grid_constant__ TickArgs a, const __grid_constan
                     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                     mbar_arrive(&ms.a_ready[part]);
                 }
+#endif
                 ++l1_count;
             };
             // one accumulator quarter: D -> +b2 -> tanh -> partial contraction with the 512x3 output layer

@@ -724,7 +724,9 @@ __device__ __forceinline__ void rollout_samples(const TickArgs &a, const TickSme
     for (int s = 0; s < SPT; ++s) fetch(s, 0, e[s]);
     // pairs of timesteps whose successor still needs noise run with the fetch of the NEXT pair interleaved; the last
     // pair (or the odd last step) runs alone, so no Philox call is wasted
-    const int n_fetch_pairs = (T - 1) >> 1;                 // pairs tp = 0, 2, ... for which a step tp + 2 exists
+    // (path-free cost kinds, WIN < 0, keep the surplus fetch: their step carries atan2f / expf bodies and a second inlined
+    // copy of it costs more in instruction fetch than the one Philox call saves -- goal-point K = 1M: 0.472 vs 0.490 ms)
+    const int n_fetch_pairs = WIN >= 0 ? (T - 1) >> 1 : T >> 1;   // pairs tp = 0, 2, ... for which a step tp + 2 exists (or all pairs)
     int tp = 0;
     for (int i = 0; i < n_fetch_pairs; ++i, tp += 2) {
         float en[SPT][4];
@@ -739,8 +741,12 @@ __device__ __forceinline__ void rollout_samples(const TickArgs &a, const TickSme
     }
 #pragma unroll
     for (int s = 0; s < SPT; ++s) {
-        step(s, tp, e[s][0], e[s][1]);                      // tp = T - 2 (even T) or T - 1 (odd T)
-        if (!(T & 1)) step(s, tp + 1, e[s][2], e[s][3]);
+        if (WIN >= 0) {
+            step(s, tp, e[s][0], e[s][1]);                  // tp = T - 2 (even T) or T - 1 (odd T)
+            if (!(T & 1)) step(s, tp + 1, e[s][2], e[s][3]);
+        } else if (T & 1) {
+            step(s, T - 1, e[s][0], e[s][1]);
+        }
         if (SUM) {                          // terminal cost: same state, same waypoint as the last stage cost (A9)
             acc[s] += eval_terminal_cost<MODEL, WIN>(a, z[s], ref[s], yaw_eff[s]);
             nc[s] += hit[s] ? 1 : 0;

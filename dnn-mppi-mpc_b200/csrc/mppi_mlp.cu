@@ -89,14 +89,33 @@ constexpr int KCH = 64;                   // K elements per 128-byte swizzle spa
 
 constexpr int N_MMA = 128;                // N per tcgen05.mma = one accumulator quarter
 constexpr int N_QUARTERS = HID / N_MMA;
-constexpr int KCH_PER_STAGE = 4;          // K chunks (TMA boxes) per ring stage: one barrier wait + one commit per 16 MMAs,
+// -DMPPI_MLP_L1_MMA=1: layer 1 of the one-GEMM kernels as warp-level mma.sync.m16n8k16 on split-fp16 inputs and weights (see
+// layer1_mma_part below).  Parity-green but SLOWER: 0.968 against 0.923 ms/tick -- without the 32 HMMA per warp the same code
+// runs in 0.706 ms, i.e. the legacy mma.sync path costs ~4.9 k cycles per tile-step (~430 MAC/clk/SM) and holds up the tcgen05
+// pipeline it shares the tensor core with.  Kept as the measured A/B variant; the split operands, their shared-memory layout
+// and the five-stage 160 KB weight ring (within 1 % of three 64 KB stages) are what a tcgen05 layer 1 builds on.
+#ifndef MPPI_MLP_L1_MMA
+#define MPPI_MLP_L1_MMA 0
+#endif
+#ifndef MPPI_MLP_KCH_PER_STAGE
+#define MPPI_MLP_KCH_PER_STAGE (MPPI_MLP_L1_MMA ? 2 : 4)
+#endif
+#ifndef MPPI_MLP_B_STAGES
+#define MPPI_MLP_B_STAGES (MPPI_MLP_L1_MMA ? 5 : 3)
+#endif
+constexpr int KCH_PER_STAGE = MPPI_MLP_KCH_PER_STAGE;   // K chunks (TMA boxes) per ring stage: one barrier wait + one commit per 16 MMAs,
                                           // otherwise the single issuing thread (try_wait ~90 cycles) paces the tensor core
-constexpr int B_STAGES = 3;
+constexpr int B_STAGES = MPPI_MLP_B_STAGES;
 constexpr int B_BOX_BYTES = N_MMA * KCH * 2;       // 16 KB per TMA box
 constexpr int B_TILE_BYTES = KCH_PER_STAGE * B_BOX_BYTES;   // 64 KB per stage
+constexpr int RING_BYTES = 12 * B_BOX_BYTES;        // the 1024-aligned operand region at the start of dynamic shared memory (192 KB)
 constexpr int A2_BYTES = TILE_M * HID * 2;          // NG = 2: second GEMM's A operand in shared memory (128 KB)
-constexpr int B2_STAGES = (B_STAGES * B_TILE_BYTES - A2_BYTES) / B_BOX_BYTES;   // NG = 2: one-box stages in what is left (4)
-static_assert(B2_STAGES >= 2 && B2_STAGES <= B_STAGES * KCH_PER_STAGE, "NG = 2 ring");
+constexpr int B2_STAGES = (RING_BYTES - A2_BYTES) / B_BOX_BYTES;   // NG = 2: one-box stages in what is left (4)
+static_assert(B2_STAGES >= 2, "NG = 2 ring");
+static_assert(B_STAGES * B_TILE_BYTES <= RING_BYTES && (HID / KCH) % KCH_PER_STAGE == 0 && KCH_PER_STAGE % 2 == 0, "NG = 1 ring");
+constexpr int L1_KS_MAX = 32;                       // layer-1 MMA: K slots (halves) per row, 16 (3 inputs) or 32 (5 inputs)
+constexpr int B1_OFFSET = B_STAGES * B_TILE_BYTES;  // its B operand [512][KS] fp16 sits behind the NG = 1 ring in the operand region
+static_assert(!MPPI_MLP_L1_MMA || B1_OFFSET + HID * L1_KS_MAX * 2 <= RING_BYTES, "layer-1 B operand does not fit behind the ring");
 constexpr int TMEM_A_COL = 0;             // A operand: 512 bf16 per row = 256 packed 32-bit columns
 constexpr int TMEM_D_COL = 256;           // two accumulator buffers of 128 FP32 columns
 constexpr int N_GROUPS = 4;                // compute-warp groups: group g owns accumulator quarter g (128 columns)
@@ -106,8 +125,13 @@ constexpr int MLP_THREADS = 64 + N_COMPUTE;
 struct MlpW3 { float4 w[HID]; };          // (b2[j], W3[0][j], W3[1][j], W3[2][j]) as a kernel parameter (MPPI_MLP_W3_PARAM)
 
 struct MlpSmem {                          // after the 1024-aligned A / B regions
-    float4 w01[HID];                      // (W01[j][0], W01[j][1], W01[j][2], b01[j])
-    __align__(16) float2 w01u[HID];       // NIN = 5: (W01[j][3], W01[j][4]) -- the control columns
+    union {
+        struct {
+            float4 w01[HID];                  // (W01[j][0], W01[j][1], W01[j][2], b01[j])
+            __align__(16) float2 w01u[HID];   // NIN = 5: (W01[j][3], W01[j][4]) -- the control columns
+        };
+        __align__(16) __half a1[TILE_M][L1_KS_MAX];   // layer-1 MMA: the split-fp16 input row of every sample (A operand)
+    };
     float xw[TILE_M];                     // NIN = 5: second control component of each row (the first rides in xs.w)
     float4 w3[HID];                       // (b2[j], W3[0][j], W3[1][j], W3[2][j])
     float4 xs[TILE_M];                    // current state of each row for the partner thread
@@ -120,7 +144,7 @@ struct MlpSmem {                          // after the 1024-aligned A / B region
     float b3[3];
 };
 
-constexpr size_t MLP_DYN_SMEM = B_STAGES * B_TILE_BYTES + sizeof(TickSmem) + sizeof(MlpSmem);
+constexpr size_t MLP_DYN_SMEM = RING_BYTES + sizeof(TickSmem) + sizeof(MlpSmem);
 static_assert(MLP_DYN_SMEM + 1024 <= 232448, "K3 shared memory exceeds the 227 KB per-CTA limit of sm_100a");
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -249,6 +273,108 @@ __device__ __forceinline__ uint32_t tanh_op2(float lo, float hi) {
     return y;
 #endif
 }
+// ---- layer 1 on the tensor core (mma.sync.m16n8k16, fp16 x fp16 -> fp32) -------------------------------------------------
+// The folded first layer is a (128 rows x n_in) x (n_in x 512) product that has to keep FP32 accuracy (positions of tens of
+// metres, weights of any size), so inputs and weights are SPLIT into fp16 pieces, v = hi + lo with |lo| <= 2^-11 |hi|, and
+//     x.w ~= x_hi w_hi + x_hi w_lo + x_lo w_hi        (relative error 2^-22, products exact, FP32 accumulation)
+// which takes three K slots per input plus two for the bias (row values 1, 1 against b_hi, b_lo): K = 16 for 3 inputs (11 used),
+// 32 for 5 inputs (17 used).  Per 128-column part a warp (32 rows, this group's 32 columns) issues 2 x 4 x K/16 MMAs instead
+// of 32 x 32 x (n_in + 1) FMAs with one broadcast LDS.128 per column; the timing probes put 20 % of the tick there.
+// The accumulator fragment (thread t: rows t/4, t/4 + 8; columns 2(t%4), 2(t%4) + 1 of each 8-column tile) goes through tanh
+// and ONE rounding to fp16 straight into the A region of tensor memory with the 16x256b store shape, whose register layout is
+// the same fragment (register 4c + 2i + e: row t/4 + 8i, packed column 8c + 2(t%4) + e of the 16-lane slab).  That fixes which
+// hidden unit sits where in an MMA tile: within each block of 16 units, unit 4m + 2e + d is column 2m + d of tile e --
+// the order the B operand is stored in (mlp_set_weights).
+__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], const void *p) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(smem_u32(p)));
+}
+__device__ __forceinline__ void mma_m16n8k16(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void tmem_st_16x256b_x2(uint32_t taddr, const uint32_t (&r)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.16x256b.x2.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                 ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
+}
+// v = hi + lo in half precision, packed (hi in the low half)
+__device__ __forceinline__ void split_half(float v, unsigned short &hi, unsigned short &lo) {
+    const __half h = __float2half_rn(v);
+    const __half l = __float2half_rn(v - __half2float(h));
+    hi = __half_as_ushort(h); lo = __half_as_ushort(l);
+}
+// the split input row of one sample: slots 3c..3c+2 = (hi, hi, lo) of input c, then (1, 1) for the bias, zeros behind
+template <int NIN>
+__device__ __forceinline__ void write_a1_row(__half *rowp, const float (&x)[5]) {
+    constexpr int KS = NIN == 3 ? 16 : 32;
+    unsigned short h[KS];
+#pragma unroll
+    for (int i = 0; i < KS; ++i) h[i] = 0;
+#pragma unroll
+    for (int c = 0; c < NIN; ++c) {
+        unsigned short hi, lo;
+        split_half(x[c], hi, lo);
+        h[3 * c] = hi; h[3 * c + 1] = hi; h[3 * c + 2] = lo;
+    }
+    h[3 * NIN] = 0x3C00; h[3 * NIN + 1] = 0x3C00;                       // 1.0
+    uint4 *dst = reinterpret_cast<uint4 *>(rowp);
+#pragma unroll
+    for (int i = 0; i < KS / 8; ++i)
+        dst[i] = make_uint4((uint32_t)h[8 * i] | ((uint32_t)h[8 * i + 1] << 16), (uint32_t)h[8 * i + 2] | ((uint32_t)h[8 * i + 3] << 16),
+                            (uint32_t)h[8 * i + 4] | ((uint32_t)h[8 * i + 5] << 16), (uint32_t)h[8 * i + 6] | ((uint32_t)h[8 * i + 7] << 16));
+}
+// A fragments of this warp's two 16-row tiles (rows q*32 + 16h ..), loaded once per layer-1 evaluation
+template <int NIN>
+__device__ __forceinline__ void load_a1_frags(const __half (*a1)[L1_KS_MAX], int q, int lane, uint32_t (&afr)[2][NIN == 3 ? 1 : 2][4]) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+#pragma unroll
+        for (int ks = 0; ks < (NIN == 3 ? 1 : 2); ++ks)
+            ldsm_x4(afr[h][ks], &a1[q * 32 + 16 * h + (lane & 7) + 8 * ((lane >> 3) & 1)][16 * ks + 8 * (lane >> 4)]);
+}
+// one 128-column part: this group's 32 hidden units for the warp's 32 rows -> tanh -> fp16, as the two 8-register store
+// payloads of the 16-lane slabs (pk[h]); `b1` = the layer's B operand [512][KS] (unit order permuted as described above)
+template <int NIN>
+__device__ __forceinline__ void layer1_mma_part(const __half *b1, int part, int grp, int lane,
+                                                const uint32_t (&afr)[2][NIN == 3 ? 1 : 2][4], uint32_t (&pk)[2][8]) {
+    constexpr int KS = NIN == 3 ? 16 : 32;
+    float c[2][4][4];
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+#pragma unroll
+        for (int n = 0; n < 4; ++n) c[h][n][0] = c[h][n][1] = c[h][n][2] = c[h][n][3] = 0.f;
+    const __half *tile0 = b1 + (size_t)(part * N_MMA + grp * 32) * KS;
+#pragma unroll
+    for (int n2 = 0; n2 < 2; ++n2) {                                    // two 8-unit tiles per ldmatrix.x4
+#pragma unroll
+        for (int ks = 0; ks < KS / 16; ++ks) {
+            uint32_t bfr[4];                                            // (tile 2 n2: k 0-7, k 8-15), (tile 2 n2 + 1: k 0-7, k 8-15)
+#if MPPI_MLP_PROBE & 16
+            bfr[0] = bfr[1] = bfr[2] = bfr[3] = (uint32_t)(n2 + ks);
+#else
+            ldsm_x4(bfr, tile0 + (size_t)(16 * n2 + 8 * (lane >> 4) + (lane & 7)) * KS + 16 * ks + 8 * ((lane >> 3) & 1));
+#endif
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+#if MPPI_MLP_PROBE & 8
+                c[h][2 * n2][0] += __uint_as_float(afr[h][ks][0] ^ bfr[0]); c[h][2 * n2 + 1][1] += __uint_as_float(afr[h][ks][1] ^ bfr[2]);
+#else
+                mma_m16n8k16(c[h][2 * n2], afr[h][ks], bfr[0], bfr[1]);
+                mma_m16n8k16(c[h][2 * n2 + 1], afr[h][ks], bfr[2], bfr[3]);
+#endif
+            }
+        }
+    }
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+#pragma unroll
+        for (int cb = 0; cb < 2; ++cb)
+#pragma unroll
+            for (int i = 0; i < 2; ++i)
+#pragma unroll
+                for (int e = 0; e < 2; ++e)
+                    pk[h][4 * cb + 2 * i + e] = tanh_op2(c[h][2 * cb + e][2 * i], c[h][2 * cb + e][2 * i + 1]);
+}
 // one lane of a CONVERGED warp (elect.sync): the MMA / TMA issue loops run warp-converged with the issuing
 // instructions predicated on this, so ptxas emits each UTCHMMA once with uniform-register operands instead of the
 // elect / execute / retire loop it needs inside a divergent `if (lane == 0)` region (8 SASS instructions and ~80
@@ -304,7 +430,7 @@ mppi_mlp_rollout_kernel(const __grid_constant__ TickArgs a, const __grid_constan
                         const float4 *__restrict__ g_w01, const float2 *__restrict__ g_w01u, const float4 *__restrict__ g_w3,
                         const float *__restrict__ g_b3, const float *__restrict__ g_bh, float *__restrict__ S_out, int n_tiles,
                         float *__restrict__ hand, unsigned int *__restrict__ hand_flag, unsigned int *__restrict__ fault,
-                        unsigned int epoch, int balanced
+                        unsigned int epoch, int balanced, const __half *__restrict__ g_b1
 #if MPPI_MLP_W3_PARAM
                         , const __grid_constant__ MlpW3 w3p
 #endif
@@ -315,8 +441,8 @@ mppi_mlp_rollout_kernel(const __grid_constant__ TickArgs a, const __grid_constan
     extern __shared__ __align__(1024) unsigned char dyn[];
     unsigned char *smB = dyn + (NG == 2 ? A2_BYTES : 0);          // weight ring, 1024-aligned (NG = 2: after the A2 tile)
     unsigned char *smA2 = dyn;                                    // NG = 2: 8 K-chunks x [128 rows x 128 B], 128B swizzle
-    TickSmem &sm = *reinterpret_cast<TickSmem *>(dyn + B_STAGES * B_TILE_BYTES);
-    MlpSmem &ms = *reinterpret_cast<MlpSmem *>(dyn + B_STAGES * B_TILE_BYTES + sizeof(TickSmem));
+    TickSmem &sm = *reinterpret_cast<TickSmem *>(dyn + RING_BYTES);
+    MlpSmem &ms = *reinterpret_cast<MlpSmem *>(dyn + RING_BYTES + sizeof(TickSmem));
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int T = a.T;
     // clusters of two CTAs advance in lockstep: cluster c owns tile pairs c, c + n_clusters, ...; both CTAs run
@@ -340,10 +466,19 @@ mppi_mlp_rollout_kernel(const __grid_constant__ TickArgs a, const __grid_constan
     const int my_tile_steps = balanced ? (PP ? 2 : 1) * (bal_b1 - bal_b0) : my_slots * T;    // tile-steps of this CTA
 
     // ---- one-time setup: constants, barriers, TMEM, step-1 index + window (same rule as the tick kernel)
+    constexpr bool L1MMA = MPPI_MLP_L1_MMA && NG == 1;        // layer 1 as mma.sync on split-fp16 operands (one-GEMM kernels)
+    constexpr int KS = NIN == 3 ? 16 : 32;
+    const __half *smB1 = reinterpret_cast<const __half *>(dyn + B1_OFFSET);
     for (int j = tid; j < HID; j += MLP_THREADS) {
-        ms.w01[j] = g_w01[j]; ms.w3[j] = g_w3[j];
-        if (NIN == 5) ms.w01u[j] = g_w01u[j];
+        ms.w3[j] = g_w3[j];
+        if (!L1MMA) {
+            ms.w01[j] = g_w01[j];
+            if (NIN == 5) ms.w01u[j] = g_w01u[j];
+        }
     }
+    if (L1MMA)
+        for (int i = tid; i < HID * KS * 2 / 16; i += MLP_THREADS)
+            reinterpret_cast<uint4 *>(dyn + B1_OFFSET)[i] = reinterpret_cast<const uint4 *>(g_b1)[i];
     if (tid < 3) ms.b3[tid] = g_b3[tid];
     if (tid < 4) sm.x0[tid] = a.x0[tid];
     if (tid == 0) {
@@ -590,6 +725,32 @@ mppi_mlp_rollout_kernel(const __grid_constant__ TickArgs a, const __grid_constan
             };
             // layer 1 of the tile owned by group og -> A region (L1 #l1_count, consumed by GEMM #l1_count)
             auto layer1 = [&](int og) {
+                if constexpr (L1MMA) {
+                    if (grp == og) {
+                        const float xin[5] = {z[0], z[1], z[2], vc0, vc1};
+                        write_a1_row<NIN>(ms.a1[row], xin);
+                    }
+                    named_bar_sync(1, N_COMPUTE);
+                    uint32_t afr[2][NIN == 3 ? 1 : 2][4];
+                    load_a1_frags<NIN>(ms.a1, q, lane, afr);
+#pragma unroll 1
+                    for (int part = 0; part < N_QUARTERS; ++part) {
+                        uint32_t pk[2][8];
+                        layer1_mma_part<NIN>(smB1, part, grp, lane, afr, pk);
+                        if (l1_count > 0) {                               // GEMM #(l1_count-1) is done with this part of A
+                            mbar_wait_warp(&ms.a_free[part], (l1_count - 1) & 1);
+                            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                        }
+#pragma unroll
+                        for (int h = 0; h < 2; ++h)
+                            tmem_st_16x256b_x2(tmem + ((uint32_t)(q * 32 + 16 * h) << 16) + TMEM_A_COL + (uint32_t)((part * N_MMA + grp * 32) >> 1), pk[h]);
+                        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                        mbar_arrive(&ms.a_ready[part]);
+                    }
+                    ++l1_count;
+                    return;
+                }
                 if (grp == og) {
                     ms.xs[row] = make_float4(z[0], z[1], z[2], vc0);
                     if (NIN == 5) ms.xw[row] = vc1;
@@ -804,15 +965,35 @@ mppi_mlp_rollout_kernel(const __grid_constant__ TickArgs a, const __grid_constan
             for (int t = t0; t < t1; ++t) {
                 // (1) owner publishes the state (and, for the 5-input residual, this step's control); every group
                 //     evaluates its 128 columns of tanh(W01 [x; u] + b01)
-                if (owner) {
+                if constexpr (L1MMA) {
+                    if (owner) {
+                        const float xin[5] = {z[0], z[1], z[2], vc0, vc1};
+                        write_a1_row<NIN>(ms.a1[row], xin);
+                    }
+                    named_bar_sync(1, N_COMPUTE);
+                    uint32_t afr[2][NIN == 3 ? 1 : 2][4];
+                    load_a1_frags<NIN>(ms.a1, q, lane, afr);
+#pragma unroll 1
+                    for (int part = 0; part < N_QUARTERS; ++part) {
+                        uint32_t pk[2][8];
+                        layer1_mma_part<NIN>(smB1, part, grp, lane, afr, pk);
+#pragma unroll
+                        for (int h = 0; h < 2; ++h)
+                            tmem_st_16x256b_x2(tmem + ((uint32_t)(q * 32 + 16 * h) << 16) + TMEM_A_COL + (uint32_t)((part * N_MMA + grp * 32) >> 1), pk[h]);
+                        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                        mbar_arrive(&ms.a_ready[part]);
+                    }
+                }
+                if (!L1MMA && owner) {
                     ms.xs[row] = make_float4(z[0], z[1], z[2], vc0);
                     if (NIN == 5) ms.xw[row] = vc1;
                 }
-                named_bar_sync(1, N_COMPUTE);
-                const float4 st = ms.xs[row];
-                const float su1 = NIN == 5 ? ms.xw[row] : 0.f;
+                if (!L1MMA) named_bar_sync(1, N_COMPUTE);
+                const float4 st = L1MMA ? make_float4(0.f, 0.f, 0.f, 0.f) : ms.xs[row];
+                const float su1 = (NIN == 5 && !L1MMA) ? ms.xw[row] : 0.f;
 #pragma unroll 1
-                for (int part = 0; part < N_QUARTERS; ++part) {      // 128-column parts of A, each signalled on its own
+                for (int part = 0; part < (L1MMA ? 0 : N_QUARTERS); ++part) {      // 128-column parts of A, each signalled on its own
 #pragma unroll 2
                     for (int c8 = 0; c8 < 4; ++c8) {                 // this group's 32 columns of the part, 8 at a time
                         const int col = part * N_MMA + grp * 32 + c8 * 8;
@@ -958,6 +1139,7 @@ struct MlpState {
     float4 *d_w01 = nullptr, *d_w3 = nullptr;
     float2 *d_w01u = nullptr;             // control columns of the folded first layer (n_in = 5)
     float *d_b3 = nullptr;
+    __half *d_b1 = nullptr;               // layer-1 MMA B operand: [512 hidden, tile order][16 | 32] split-fp16 weight slots
     float *d_bh = nullptr;                // n_hidden = 3: bias of the layer the first GEMM evaluates
     float *d_hand = nullptr;              // balanced schedule: state records of split quads [cluster][rank][slot][6][128]
     unsigned int *d_hand_flag = nullptr;  // [cluster][rank]: epoch of the launch that published the record; then one fault word
@@ -985,7 +1167,8 @@ MlpState *mlp_create(int K, int T) {
         cudaMalloc(&m->d_w01, sizeof(float4) * HID) != cudaSuccess ||
         cudaMalloc(&m->d_w3, sizeof(float4) * HID) != cudaSuccess ||
         cudaMalloc(&m->d_w01u, sizeof(float2) * HID) != cudaSuccess ||
-        cudaMalloc(&m->d_b3, sizeof(float) * 4) != cudaSuccess) { mlp_destroy(m); return nullptr; }
+        cudaMalloc(&m->d_b3, sizeof(float) * 4) != cudaSuccess ||
+        cudaMalloc(&m->d_b1, sizeof(__half) * HID * L1_KS_MAX) != cudaSuccess) { mlp_destroy(m); return nullptr; }
     if (cudaFuncSetAttribute(mppi_mlp_rollout_kernel<3, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MLP_DYN_SMEM) != cudaSuccess ||
         cudaFuncSetAttribute(mppi_mlp_rollout_kernel<5, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MLP_DYN_SMEM) != cudaSuccess ||
         cudaFuncSetAttribute(mppi_mlp_rollout_kernel<3, true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MLP_DYN_SMEM) != cudaSuccess ||
@@ -999,7 +1182,7 @@ MlpState *mlp_create(int K, int T) {
 
 void mlp_destroy(MlpState *m) {
     if (!m) return;
-    cudaFree(m->d_w2); cudaFree(m->d_bh); cudaFree(m->d_hand); cudaFree(m->d_hand_flag); cudaFree(m->d_w01); cudaFree(m->d_w01u); cudaFree(m->d_w3); cudaFree(m->d_b3);
+    cudaFree(m->d_w2); cudaFree(m->d_bh); cudaFree(m->d_hand); cudaFree(m->d_hand_flag); cudaFree(m->d_w01); cudaFree(m->d_w01u); cudaFree(m->d_w3); cudaFree(m->d_b3); cudaFree(m->d_b1);
     delete m;
 }
 
@@ -1027,6 +1210,7 @@ cudaError_t mlp_set_weights(MlpState *m, int n_in, int n_hidden, const float *co
     }
     std::vector<float4> w01(HID), w3(HID);
     std::vector<float2> w01u(HID, make_float2(0.f, 0.f));
+    std::vector<__half> b1((size_t)HID * L1_KS_MAX, __float2half_rn(0.f));
     for (int j = 0; j < HID; ++j) {
         double s[5] = {0, 0, 0, 0, 0}, bb = b[1][j];
         for (int i = 0; i < HID; ++i) {
@@ -1036,6 +1220,25 @@ cudaError_t mlp_set_weights(MlpState *m, int n_in, int n_hidden, const float *co
         }
         w01[j] = make_float4((float)s[0], (float)s[1], (float)s[2], (float)bb);
         w01u[j] = make_float2((float)s[3], (float)s[4]);
+        {   // the same folded row as the layer-1 MMA's B operand: per input (w_hi, w_lo, w_hi) against the input row's
+            // (x_hi, x_hi, x_lo), then (b_hi, b_lo) against (1, 1); stored at the tile position of unit j (see layer1_mma_part)
+            const int KS = n_in == 3 ? 16 : 32;
+            const int part = j / N_MMA, g = (j % N_MMA) / 32, v = j % 32;
+            const int cb = v / 16, m4 = (v % 16) / 4, e = (v % 4) / 2, dl = v % 2;
+            __half *row = &b1[(size_t)(part * N_MMA + g * 32 + 8 * (2 * cb + e) + 2 * m4 + dl) * KS];
+            auto split = [](double w, __half &hi, __half &lo) {
+                hi = __float2half_rn((float)w);
+                lo = __float2half_rn((float)(w - (double)__half2float(hi)));
+            };
+            for (int c = 0; c < n_in; ++c) {
+                if (!(std::fabs(s[c]) <= 65504.0)) return cudaErrorInvalidValue;
+                __half hi, lo;
+                split(s[c], hi, lo);
+                row[3 * c] = hi; row[3 * c + 1] = lo; row[3 * c + 2] = hi;
+            }
+            if (!(std::fabs(bb) <= 65504.0)) return cudaErrorInvalidValue;
+            split(bb, row[3 * n_in], row[3 * n_in + 1]);
+        }
         const double o0 = out_scale ? out_scale[0] : 1.0, o1 = out_scale ? out_scale[1] : 1.0, o2 = out_scale ? out_scale[2] : 1.0;
         w3[j] = make_float4(b[l_last][j], (float)(W[l_out][0 * HID + j] * o0), (float)(W[l_out][1 * HID + j] * o1), (float)(W[l_out][2 * HID + j] * o2));
     }
@@ -1058,6 +1261,7 @@ cudaError_t mlp_set_weights(MlpState *m, int n_in, int n_hidden, const float *co
     for (int j = 0; j < HID; ++j) m->h_w3.w[j] = w3[j];
     if ((e = cudaMemcpyAsync(m->d_w01u, w01u.data(), sizeof(float2) * HID, cudaMemcpyHostToDevice, st)) != cudaSuccess) return e;
     if ((e = cudaMemcpyAsync(m->d_b3, b3, sizeof(b3), cudaMemcpyHostToDevice, st)) != cudaSuccess) return e;
+    if ((e = cudaMemcpyAsync(m->d_b1, b1.data(), sizeof(__half) * b1.size(), cudaMemcpyHostToDevice, st)) != cudaSuccess) return e;
     if ((e = cudaMemcpyAsync(m->d_w2, w2.data(), sizeof(mlp_op_t) * w2.size(), cudaMemcpyHostToDevice, st)) != cudaSuccess) return e;
     if (n_gemm == 2 && (e = cudaMemcpyAsync(m->d_bh, b[2], sizeof(float) * HID, cudaMemcpyHostToDevice, st)) != cudaSuccess) return e;
     if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return e;
@@ -1134,7 +1338,7 @@ int mlp_rollout_costs(MlpState *m, const TickArgs &args, bool sum, const float *
 #else
 #define MPPI_MLP_W3_ARG
 #endif
-#define MPPI_MLP_LAUNCH(N, P, G) mppi_mlp_rollout_kernel<N, P, G><<<grid, MLP_THREADS, MLP_DYN_SMEM, st>>>(a, m->w2_map, m->d_w01, m->d_w01u, m->d_w3, m->d_b3, m->d_bh, d_S, n_tiles, m->d_hand, m->d_hand_flag, fault, epoch, balanced MPPI_MLP_W3_ARG)
+#define MPPI_MLP_LAUNCH(N, P, G) mppi_mlp_rollout_kernel<N, P, G><<<grid, MLP_THREADS, MLP_DYN_SMEM, st>>>(a, m->w2_map, m->d_w01, m->d_w01u, m->d_w3, m->d_b3, m->d_bh, d_S, n_tiles, m->d_hand, m->d_hand_flag, fault, epoch, balanced, m->d_b1 MPPI_MLP_W3_ARG)
     if (m->n_gemm == 2) { if (m->n_in == 5) MPPI_MLP_LAUNCH(5, false, 2); else MPPI_MLP_LAUNCH(3, false, 2); }
     else if (m->n_in == 5) { if (pp) MPPI_MLP_LAUNCH(5, true, 1); else MPPI_MLP_LAUNCH(5, false, 1); }
     else { if (pp) MPPI_MLP_LAUNCH(3, true, 1); else MPPI_MLP_LAUNCH(3, false, 1); }

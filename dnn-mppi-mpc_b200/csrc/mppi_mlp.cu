@@ -79,6 +79,22 @@ typedef __nv_bfloat16 mlp_op_t;
 #define MPPI_MLP_PROBE 0
 #endif
 
+// bit 32: per-wait stall accounting (clock64 around every barrier wait of the MMA issuer and of compute warp 0, printed by CTA 0)
+#if MPPI_MLP_PROBE & 32
+#define MLP_PROBE_DECL() long long pr_c = 0; const long long pr_begin = clock64(); unsigned long long *pr_t = reinterpret_cast<unsigned long long *>(sm.cb) + (warp == 1 ? 0 : 16);   /* static window: cb is unused */ (void)pr_c; \
+    if ((threadIdx.x & 31) == 0 && (threadIdx.x >> 5) <= 2) for (int i_ = 0; i_ < 16; ++i_) pr_t[i_] = 0
+#define MLP_TIC() pr_c = clock64()
+#define MLP_TOC(i) do { const long long n_ = clock64(); if ((threadIdx.x & 31) == 0 && (threadIdx.x >> 5) <= 2) pr_t[(i)] += (unsigned long long)(n_ - pr_c); pr_c = n_; } while (0)
+#define MLP_PROBE_PRINT(what, steps) do { if (blockIdx.x == 0 && (threadIdx.x & 31) == 0) printf("%s (cycles per tile-step, %d tile-steps, total %lld): %lld %lld %lld %lld | %lld %lld %lld %lld | %lld %lld %lld %lld | %lld %lld %lld %lld\n", what, (int)(steps), (clock64() - pr_begin) / max((int)(steps), 1), \
+    (long long)pr_t[0] / max((int)(steps), 1), (long long)pr_t[1] / max((int)(steps), 1), (long long)pr_t[2] / max((int)(steps), 1), (long long)pr_t[3] / max((int)(steps), 1), (long long)pr_t[4] / max((int)(steps), 1), (long long)pr_t[5] / max((int)(steps), 1), (long long)pr_t[6] / max((int)(steps), 1), (long long)pr_t[7] / max((int)(steps), 1), \
+    (long long)pr_t[8] / max((int)(steps), 1), (long long)pr_t[9] / max((int)(steps), 1), (long long)pr_t[10] / max((int)(steps), 1), (long long)pr_t[11] / max((int)(steps), 1), (long long)pr_t[12] / max((int)(steps), 1), (long long)pr_t[13] / max((int)(steps), 1), (long long)pr_t[14] / max((int)(steps), 1), (long long)pr_t[15] / max((int)(steps), 1)); } while (0)
+#else
+#define MLP_PROBE_DECL()
+#define MLP_TIC()
+#define MLP_TOC(i)
+#define MLP_PROBE_PRINT(what, steps)
+#endif
+
 #ifndef MPPI_MLP_L1_EARLY
 #define MPPI_MLP_L1_EARLY 0     // 1: ping-pong layer 1 evaluates a part into registers before waiting for that part of A (A/B variant)
 #endif
@@ -97,11 +113,21 @@ constexpr int N_QUARTERS = HID / N_MMA;
 #ifndef MPPI_MLP_L1_MMA
 #define MPPI_MLP_L1_MMA 0
 #endif
+// -DMPPI_MLP_KSPLIT=1 (ping-pong kernels): the LAST TWO accumulator quarters of a tile-step are issued interleaved by K part --
+// (q2,p0) (q3,p0) (q2,p1) (q3,p1) ... through the two accumulator buffers -- instead of one after the other.  The last reader of A part p
+// then retires (p+1)/4 of the way through HALF the GEMM instead of a quarter of it, so the other tile's layer 1 (which may only overwrite
+// a part once the running GEMM has released it) has twice the window to hide in.  One 128-column part per ring stage (32 KB, six stages).
+// Parity-green (bit-identical costs) and SLOWER: 0.944 against 0.921 ms/tick (3 inputs), 1.058 against 1.025 (5 inputs) -- the stall
+// accounting (-DMPPI_MLP_PROBE=32, profiles/r2_mlp_stall_accounting.txt) shows why: the compute warps are busy ~77 % of a slot, so moving
+// the window does not shorten their chain, and quarters 2 and 3 now drain together BEHIND layer 1.  Kept as the measured A/B variant.
+#ifndef MPPI_MLP_KSPLIT
+#define MPPI_MLP_KSPLIT 0
+#endif
 #ifndef MPPI_MLP_KCH_PER_STAGE
-#define MPPI_MLP_KCH_PER_STAGE (MPPI_MLP_L1_MMA ? 2 : 4)
+#define MPPI_MLP_KCH_PER_STAGE ((MPPI_MLP_L1_MMA || MPPI_MLP_KSPLIT) ? 2 : 4)
 #endif
 #ifndef MPPI_MLP_B_STAGES
-#define MPPI_MLP_B_STAGES (MPPI_MLP_L1_MMA ? 5 : 3)
+#define MPPI_MLP_B_STAGES (MPPI_MLP_L1_MMA ? 5 : (MPPI_MLP_KSPLIT ? 6 : 3))
 #endif
 constexpr int KCH_PER_STAGE = MPPI_MLP_KCH_PER_STAGE;   // K chunks (TMA boxes) per ring stage: one barrier wait + one commit per 16 MMAs,
                                           // otherwise the single issuing thread (try_wait ~90 cycles) paces the tensor core
@@ -388,6 +414,16 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
+// Order in which a tile-step's weight stages (accumulator quarter nq, K block kb2 of KCH_PER_STAGE chunks) are streamed and issued.
+// SPLIT: quarters 0 and 1 one after the other, then quarters 2 and 3 interleaved by K block (see MPPI_MLP_KSPLIT).
+constexpr int STAGES_PER_Q = HID / KCH / KCH_PER_STAGE;
+constexpr int STAGES_PER_STEP = N_QUARTERS * STAGES_PER_Q;
+template <bool SPLIT>
+__device__ __forceinline__ void mlp_stage_map(int s, int &nq, int &kb2) {
+    if (SPLIT && s >= 2 * STAGES_PER_Q) { const int j = s - 2 * STAGES_PER_Q; kb2 = j >> 1; nq = 2 + (j & 1); }
+    else { nq = s / STAGES_PER_Q; kb2 = s % STAGES_PER_Q; }
+}
+
 // ---- hand-off of a split quad / pair between neighbouring clusters (balanced schedule) ----
 // Records live at hand[tile slot][6][128] (x, y, yaw, cost so far, previous control), tile slot = ((consumer cluster * 2 +
 // rank) * 2 + ping-pong slot); flags at hand_flag[consumer cluster * 2 + rank] hold the epoch of the launch that published.
@@ -467,6 +503,7 @@ mppi_mlp_rollout_kernel(const __grid_constant__ TickArgs a, const __grid_constan
 
     // ---- one-time setup: constants, barriers, TMEM, step-1 index + window (same rule as the tick kernel)
     constexpr bool L1MMA = MPPI_MLP_L1_MMA && NG == 1;        // layer 1 as mma.sync on split-fp16 operands (one-GEMM kernels)
+    constexpr bool KSPLIT = MPPI_MLP_KSPLIT && PP;            // last two accumulator quarters interleaved by K part
     constexpr int KS = NIN == 3 ? 16 : 32;
     const __half *smB1 = reinterpret_cast<const __half *>(dyn + B1_OFFSET);
     for (int j = tid; j < HID; j += MLP_THREADS) {
@@ -568,11 +605,11 @@ mppi_mlp_rollout_kernel(const __grid_constant__ TickArgs a, const __grid_constan
                 if (++stage == B2_STAGES) { stage = 0; phase ^= 1; }
             }
         } else {
-        constexpr int STAGES_PER_Q = HID / KCH / KCH_PER_STAGE;       // 2 stage loads (64 KB each) per accumulator quarter
-        const int total = my_tile_steps * N_QUARTERS * STAGES_PER_Q;
+        const int total = my_tile_steps * STAGES_PER_STEP;
         int stage = 0; uint32_t phase = 0;
         for (int it = 0; it < total; ++it) {
-            const int kb2 = it % STAGES_PER_Q, nq = (it / STAGES_PER_Q) % N_QUARTERS;
+            int nq, kb2;
+            mlp_stage_map<KSPLIT>(it % STAGES_PER_STEP, nq, kb2);
             mbar_wait(&ms.b_empty[stage], phase ^ 1);               // both CTAs are done with this slot
             if (leader) {
                 mbar_expect_tx(&ms.b_full[stage], B_TILE_BYTES);    // every CTA arms its own barrier ...
@@ -590,8 +627,10 @@ mppi_mlp_rollout_kernel(const __grid_constant__ TickArgs a, const __grid_constan
     } else if (warp == 1) {
         // ===== MMA issuer: one elected lane of the converged warp drives the tensor core =====
         const bool leader = elect_one_sync();
-        int stage = 0; uint32_t phase = 0, a_phase = 0, quarter = 0;
+        int stage = 0; uint32_t phase = 0, a_phase = 0;
+        MLP_PROBE_DECL();
         if constexpr (NG == 2) {
+            uint32_t quarter = 0;
             for (int step = 0; step < my_tile_steps; ++step) {
                 for (int g = 0; g < NG; ++g) {
                     for (int nq = 0; nq < N_QUARTERS; ++nq, ++quarter) {
@@ -628,42 +667,49 @@ mppi_mlp_rollout_kernel(const __grid_constant__ TickArgs a, const __grid_constan
             }
         } else
         for (int step = 0; step < my_tile_steps; ++step) {
-            for (int nq = 0; nq < N_QUARTERS; ++nq, ++quarter) {
-                const uint32_t buf = quarter & 1;
-                mbar_wait(&ms.d_empty[buf], ((quarter >> 1) & 1) ^ 1);      // epilogue drained this buffer
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t d_tmem = tmem + TMEM_D_COL + buf * N_MMA;
-                for (int kb2 = 0; kb2 < HID / KCH / KCH_PER_STAGE; ++kb2) {
-                    // the activations arrive in four 128-column parts (a stage spans two of them); the first
-                    // quarter's K loop chases them
-                    if (nq == 0) {
-#pragma unroll
-                        for (int pa = 0; pa < KCH_PER_STAGE / 2; ++pa) mbar_wait(&ms.a_ready[kb2 * (KCH_PER_STAGE / 2) + pa], a_phase);
-                    }
-                    mbar_wait(&ms.b_full[stage], phase);
+            for (int s = 0; s < STAGES_PER_STEP; ++s) {
+                int nq, kb2;
+                mlp_stage_map<KSPLIT>(s, nq, kb2);
+                // quarter Q = 4 step + nq of this CTA runs in buffer Q & 1 = nq & 1; its previous user was quarter Q - 2
+                const uint32_t buf = (uint32_t)nq & 1u;
+                MLP_TIC();
+                if (kb2 == 0) {
+                    mbar_wait(&ms.d_empty[buf], (((uint32_t)nq >> 1) & 1u) ^ 1u);      // epilogue drained this buffer
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    // one descriptor per stage; the 16 K-steps only bump its 14-bit start-address field
-                    const uint64_t b_desc0 = umma_desc_sw128(smem_u32(smB + stage * B_TILE_BYTES));
-                    const uint32_t a_col0 = tmem + TMEM_A_COL + kb2 * KCH_PER_STAGE * (KCH / 16) * 8;
-                    if (leader) {
-#pragma unroll
-                        for (int k = 0; k < KCH_PER_STAGE * (KCH / 16); ++k) {
-                            const uint64_t b_desc = b_desc0 + (uint64_t)(((k / (KCH / 16)) * B_BOX_BYTES + (k % (KCH / 16)) * 32) >> 4);
-                            umma_bf16_ts(d_tmem, a_col0 + k * 8, b_desc, (kb2 | k) ? 1u : 0u);
-                            // ping-pong: the LAST quarter is the last reader of A -- release each 128-column part as
-                            // soon as its MMAs retire so the other tile's layer 1 can overwrite it
-                            if (PP && nq == N_QUARTERS - 1 && (k & 7) == 7) umma_commit(&ms.a_free[kb2 * (KCH_PER_STAGE / 2) + (k >> 3)]);
-                        }
-                        umma_commit_mc(&ms.b_empty[stage], (uint16_t)3);   // frees the W2 slot in BOTH CTAs when these MMAs retire
-                    }
-                    __syncwarp();
-                    if (++stage == B_STAGES) { stage = 0; phase ^= 1; }
                 }
-                if (leader) umma_commit(&ms.d_full[buf]);         // this accumulator quarter is complete
+                MLP_TOC(nq);
+                const uint32_t d_tmem = tmem + TMEM_D_COL + buf * N_MMA;
+                // the activations arrive in four 128-column parts (a stage spans KCH_PER_STAGE / 2 of them); the first
+                // quarter's K loop chases them
+                if (nq == 0) {
+#pragma unroll
+                    for (int pa = 0; pa < KCH_PER_STAGE / 2; ++pa) mbar_wait(&ms.a_ready[kb2 * (KCH_PER_STAGE / 2) + pa], a_phase);
+                }
+                MLP_TOC(4 + (kb2 * KCH_PER_STAGE / 2 & 3));
+                mbar_wait(&ms.b_full[stage], phase);
+                MLP_TOC(8 + nq);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                // one descriptor per stage; the K-steps only bump its 14-bit start-address field
+                const uint64_t b_desc0 = umma_desc_sw128(smem_u32(smB + stage * B_TILE_BYTES));
+                const uint32_t a_col0 = tmem + TMEM_A_COL + kb2 * KCH_PER_STAGE * (KCH / 16) * 8;
+                if (leader) {
+#pragma unroll
+                    for (int k = 0; k < KCH_PER_STAGE * (KCH / 16); ++k) {
+                        const uint64_t b_desc = b_desc0 + (uint64_t)(((k / (KCH / 16)) * B_BOX_BYTES + (k % (KCH / 16)) * 32) >> 4);
+                        umma_bf16_ts(d_tmem, a_col0 + k * 8, b_desc, (kb2 | k) ? 1u : 0u);
+                        // ping-pong: quarter 3 is the last reader of A -- release each 128-column part as soon as its MMAs
+                        // retire so the other tile's layer 1 can overwrite it
+                        if (PP && nq == N_QUARTERS - 1 && (k & 7) == 7) umma_commit(&ms.a_free[kb2 * (KCH_PER_STAGE / 2) + (k >> 3)]);
+                    }
+                    umma_commit_mc(&ms.b_empty[stage], (uint16_t)3);   // frees the W2 slot in BOTH CTAs when these MMAs retire
+                    if (kb2 == STAGES_PER_Q - 1) umma_commit(&ms.d_full[buf]);         // this accumulator quarter is complete
+                }
                 __syncwarp();
+                if (++stage == B_STAGES) { stage = 0; phase ^= 1; }
             }
             a_phase ^= 1;
         }
+        MLP_PROBE_PRINT("issuer: wait d_empty q0-3 | a_ready p0-3 | b_full q0-3", my_tile_steps);
     } else {
         // ===== compute warps: rows = TMEM lanes 32*(warp%4)..+31, column group grp =====
         if constexpr (PP) {
@@ -678,6 +724,7 @@ mppi_mlp_rollout_kernel(const __grid_constant__ TickArgs a, const __grid_constan
         const bool owner = grp < 2;
         uint32_t d_phase[2] = {0, 0};
         uint32_t l1_count = 0;
+        MLP_PROBE_DECL();
         // segments of this CTA: static = tile pairs over the whole horizon; balanced = [head], whole quads, [tail]
         const int g_first = balanced ? bal_b0 / T : 0;
         const int n_nat = balanced ? (bal_b1 > bal_b0 ? (bal_b1 - 1) / T - g_first + 1 : 0) : my_slots / 2;
@@ -755,7 +802,9 @@ mppi_mlp_rollout_kernel(const __grid_constant__ TickArgs a, const __grid_constan
                     ms.xs[row] = make_float4(z[0], z[1], z[2], vc0);
                     if (NIN == 5) ms.xw[row] = vc1;
                 }
+                MLP_TIC();
                 named_bar_sync(1, N_COMPUTE);
+                MLP_TOC(13);
                 const float4 st = ms.xs[row];
                 const float su1 = NIN == 5 ? ms.xw[row] : 0.f;
 #if MPPI_MLP_L1_EARLY
@@ -795,10 +844,12 @@ mppi_mlp_rollout_kernel(const __grid_constant__ TickArgs a, const __grid_constan
 #else
 #pragma unroll 1
                 for (int part = 0; part < N_QUARTERS; ++part) {
+                    MLP_TIC();
                     if (l1_count > 0) {                                   // GEMM #(l1_count-1) is done with this part of A
                         mbar_wait_warp(&ms.a_free[part], (l1_count - 1) & 1);
                         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     }
+                    MLP_TOC(4 + part);
 #pragma unroll 2
                     for (int c8 = 0; c8 < 4; ++c8) {
                         const int col = part * N_MMA + grp * 32 + c8 * 8;
@@ -824,6 +875,7 @@ mppi_mlp_rollout_kernel(const __grid_constant__ TickArgs a, const __grid_constan
                     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
                     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                     mbar_arrive(&ms.a_ready[part]);
+                    MLP_TOC(8 + part);
                 }
 #endif
                 ++l1_count;
@@ -832,13 +884,16 @@ mppi_mlp_rollout_kernel(const __grid_constant__ TickArgs a, const __grid_constan
             auto epilogue = [&](int nq, float &r0, float &r1, float &r2) {
                 const int col = nq * N_MMA + grp * 32;
                 const int buf = nq & 1;
+                MLP_TIC();
                 mbar_wait_warp(&ms.d_full[buf], d_phase[buf]); d_phase[buf] ^= 1;
+                MLP_TOC(nq);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 uint32_t v[32];
                 tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(TMEM_D_COL + buf * N_MMA + grp * 32), v);
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                 mbar_arrive(&ms.d_empty[buf]);
+                MLP_TOC(12);
 #if MPPI_MLP_W3_PARAM
                 const int colu = __shfl_sync(0xffffffffu, col, 0);
 #endif
@@ -857,12 +912,15 @@ mppi_mlp_rollout_kernel(const __grid_constant__ TickArgs a, const __grid_constan
                     r0 = fmaf(w.y, h, r0); r1 = fmaf(w.z, h, r1); r2 = fmaf(w.w, h, r2);
 #endif
                 }
+                MLP_TOC(15);
             };
             // the step of the tile owned by group og is complete: gather the partial sums, Euler step with the residual
             auto finish = [&](int og, float r0, float r1, float r2) {
                 const int rel = (grp - og) & 3;
                 if (rel) { ms.res[rel - 1][0][row] = r0; ms.res[rel - 1][1][row] = r1; ms.res[rel - 1][2][row] = r2; }
+                MLP_TIC();
                 named_bar_sync(1, N_COMPUTE);
+                MLP_TOC(14);
                 if (grp == og) {
                     // partial sums added in ascending GROUP order whichever group owns the tile, so a sample's result does not
                     // depend on the slot (X / Y) the schedule puts it in: the static and the balanced walk agree bit for bit
@@ -886,26 +944,35 @@ mppi_mlp_rollout_kernel(const __grid_constant__ TickArgs a, const __grid_constan
             layer1(0);                                               // L1(X, t0)
             float r0, r1, r2;
             float s0 = 0.f, s1 = 0.f, s2 = 0.f;                      // partial sums of the tile whose GEMM ran one slot ago
+            // (KSPLIT: quarters 2 and 3 of a GEMM complete together at its end, so both of their epilogues move behind the
+            //  layer 1 that chases them; the partial sums are still added in quarter order -- results do not change)
+            constexpr int NQ_EARLY = KSPLIT ? 2 : 3;                 // epilogues that run while the same GEMM is still going
             for (int t = t0; t < t1; ++t) {
                 // ---- slot X(t): the tensor core runs GEMM X(t)
                 if (t > t0) {
-                    epilogue(3, s0, s1, s2);                         // Y(t-1), last quarter
+#pragma unroll
+                    for (int nq = NQ_EARLY; nq < N_QUARTERS; ++nq) epilogue(nq, s0, s1, s2);    // Y(t-1), last quarter(s)
                     finish(1, s0, s1, s2);
                     if (grp == 1) prep(t);
                 }
                 r0 = r1 = r2 = 0.f;
-                epilogue(0, r0, r1, r2); epilogue(1, r0, r1, r2); epilogue(2, r0, r1, r2);      // X(t)
-                layer1(1);                                           // L1(Y, t) chases X(t)'s last quarter
+#pragma unroll
+                for (int nq = 0; nq < NQ_EARLY; ++nq) epilogue(nq, r0, r1, r2);                 // X(t)
+                layer1(1);                                           // L1(Y, t) chases the end of X(t)
                 // ---- slot Y(t): the tensor core runs GEMM Y(t)
-                epilogue(3, r0, r1, r2);                             // X(t), last quarter
+#pragma unroll
+                for (int nq = NQ_EARLY; nq < N_QUARTERS; ++nq) epilogue(nq, r0, r1, r2);        // X(t), last quarter(s)
                 finish(0, r0, r1, r2);
                 if (grp == 0 && t + 1 < t1) prep(t + 1);
                 s0 = s1 = s2 = 0.f;
-                epilogue(0, s0, s1, s2); epilogue(1, s0, s1, s2); epilogue(2, s0, s1, s2);      // Y(t)
-                if (t + 1 < t1) layer1(0);                           // L1(X, t+1) chases Y(t)'s last quarter
+#pragma unroll
+                for (int nq = 0; nq < NQ_EARLY; ++nq) epilogue(nq, s0, s1, s2);                 // Y(t)
+                if (t + 1 < t1) layer1(0);                           // L1(X, t+1) chases the end of Y(t)
             }
-            epilogue(3, s0, s1, s2);                                 // Y(t1-1), last quarter
+#pragma unroll
+            for (int nq = NQ_EARLY; nq < N_QUARTERS; ++nq) epilogue(nq, s0, s1, s2);            // Y(t1-1), last quarter(s)
             finish(1, s0, s1, s2);
+            if (warp == 2 && pr == n_nat - 1) MLP_PROBE_PRINT("compute warp 0: wait d_full q0-3 | a_free p0-3 | L1 work p0-3 | tmem ld, L1 bar, finish bar, epilogue math", my_tile_steps / 2);
             if (t1 < T) {
                 // head of a split quad: publish the state after step t1-1 for the next cluster's tail
                 if (owner)

@@ -139,6 +139,21 @@ constexpr int A2_BYTES = TILE_M * HID * 2;          // NG = 2: second GEMM's A o
 constexpr int B2_STAGES = (RING_BYTES - A2_BYTES) / B_BOX_BYTES;   // NG = 2: one-box stages in what is left (4)
 static_assert(B2_STAGES >= 2, "NG = 2 ring");
 static_assert(B_STAGES * B_TILE_BYTES <= RING_BYTES && (HID / KCH) % KCH_PER_STAGE == 0 && KCH_PER_STAGE % 2 == 0, "NG = 1 ring");
+// -DMPPI_MLP_CG2=1 (ping-pong kernels): the hidden GEMM as PAIR MMAs, tcgen05.mma.cta_group::2 with M = 256 -- the two CTAs of a cluster
+// (which already walk the weight stream in lockstep) become one MMA unit: rank 0 issues for both, each CTA keeps its own 128 rows of A and
+// D in its tensor memory and only HALF of every W2 box (64 of the 128 rows) in its shared memory.  Per SM that halves the TMA writes and the
+// B-operand reads (2 x 256 KB instead of 2 x 512 KB per tile-step), which share the shared-memory bandwidth with the compute warps'
+// broadcast LDS.128 (profiles/r2_mlp_stall_accounting.txt).  The ring keeps its 192 KB: six 32 KB stages instead of three 64 KB ones.
+#ifndef MPPI_MLP_CG2
+#define MPPI_MLP_CG2 1
+#endif
+#ifndef MPPI_MLP_CG2_ACQ_CLUSTER
+#define MPPI_MLP_CG2_ACQ_CLUSTER 0        // 1: the issuer's waits on a_ready / d_empty acquire at cluster scope (A/B)
+#endif
+constexpr int CG2_BOX_BYTES = B_BOX_BYTES / 2;                    // 64 W2 rows x 64 K halves
+constexpr int CG2_TILE_BYTES = KCH_PER_STAGE * CG2_BOX_BYTES;
+constexpr int CG2_STAGES = RING_BYTES / CG2_TILE_BYTES;
+constexpr int RING_SLOTS = CG2_STAGES > B_STAGES ? (CG2_STAGES > B2_STAGES ? CG2_STAGES : B2_STAGES) : (B_STAGES > B2_STAGES ? B_STAGES : B2_STAGES);
 constexpr int L1_KS_MAX = 32;                       // layer-1 MMA: K slots (halves) per row, 16 (3 inputs) or 32 (5 inputs)
 constexpr int B1_OFFSET = B_STAGES * B_TILE_BYTES;  // its B operand [512][KS] fp16 sits behind the NG = 1 ring in the operand region
 static_assert(!MPPI_MLP_L1_MMA || B1_OFFSET + HID * L1_KS_MAX * 2 <= RING_BYTES, "layer-1 B operand does not fit behind the ring");
@@ -147,6 +162,10 @@ constexpr int TMEM_D_COL = 256;           // two accumulator buffers of 128 FP32
 constexpr int N_GROUPS = 4;                // compute-warp groups: group g owns accumulator quarter g (128 columns)
 constexpr int N_COMPUTE = 128 * N_GROUPS;  // 16 compute warps: 4 per TMEM lane quarter
 constexpr int MLP_THREADS = 64 + N_COMPUTE;
+#ifndef MPPI_MLP_WARP_ARRIVE
+#define MPPI_MLP_WARP_ARRIVE 1
+#endif
+constexpr int N_ARRIVE = MPPI_MLP_WARP_ARRIVE ? N_COMPUTE / 32 : N_COMPUTE;   // arrivals per compute-warp hand-off (see compute_arrive)
 
 struct MlpW3 { float4 w[HID]; };          // (b2[j], W3[0][j], W3[1][j], W3[2][j]) as a kernel parameter (MPPI_MLP_W3_PARAM)
 
@@ -162,10 +181,10 @@ struct MlpSmem {                          // after the 1024-aligned A / B region
     float4 w3[HID];                       // (b2[j], W3[0][j], W3[1][j], W3[2][j])
     float4 xs[TILE_M];                    // current state of each row for the partner thread
     float res[N_GROUPS - 1][3][TILE_M];   // partners' partial output-layer sums (SoA: 4.5 KB instead of 6 KB as float4)
-    unsigned long long b_full[B_STAGES], b_empty[B_STAGES], a_ready[N_QUARTERS], d_full[2], d_empty[2];
+    unsigned long long b_full[RING_SLOTS], b_empty[RING_SLOTS], a_ready[N_QUARTERS], d_full[2], d_empty[2];   // ring barriers: every geometry
     unsigned long long a_free[N_QUARTERS];   // ping-pong mode: the last accumulator quarter has consumed this K part of A
     unsigned long long key[8];
-    unsigned long long b2_full[B2_STAGES], b2_empty[B2_STAGES], a2_ready[N_QUARTERS];   // NG = 2 ring and second-operand parts
+    unsigned long long a2_ready[N_QUARTERS];   // NG = 2: second-operand parts
     uint32_t tmem_base;
     float b3[3];
 };
@@ -192,6 +211,23 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t pari
         "@p bra.uni WAIT_DONE;\n\t"
         "bra.uni WAIT_LOOP;\n\t"
         "WAIT_DONE:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+
+// Compute warps signal "my part of the operand is written" / "my part of the accumulator is read".  One arrival per WARP (default):
+// every lane has waited for its tcgen05.st / tcgen05.ld and fenced, __syncwarp orders that before lane 0's releasing arrive -- 16
+// shared-memory barrier operations per hand-off instead of 512.  -DMPPI_MLP_WARP_ARRIVE=0: one arrival per thread (A/B).
+#ifndef MPPI_MLP_WARP_ARRIVE
+#define MPPI_MLP_WARP_ARRIVE 1
+#endif
+__device__ __forceinline__ void mbar_arrive_rank0(unsigned long long *bar);
+template <bool TO_RANK0 = false>                               // pair MMAs: both CTAs report to rank 0's barrier
+__device__ __forceinline__ void compute_arrive(unsigned long long *bar) {
+#if MPPI_MLP_WARP_ARRIVE
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) { if constexpr (TO_RANK0) mbar_arrive_rank0(bar); else mbar_arrive(bar); }
+#else
+    if constexpr (TO_RANK0) mbar_arrive_rank0(bar); else mbar_arrive(bar);
+#endif
 }
 
 // warp-level wait: one lane polls the barrier (every try_wait is a shared-memory operation -- 16 compute warps polling
@@ -245,6 +281,52 @@ __device__ __forceinline__ void umma_bf16_ss(uint32_t d_tmem, uint64_t a_desc, u
         "setp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t}"
         ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(UMMA_IDESC), "r"(accumulate), "r"(0u) : "memory");
+}
+// ---- pair MMAs (cta_group::2): rank 0 issues M = 256 MMAs over both CTAs' tensor memory and shared memory ----
+constexpr uint32_t UMMA_IDESC_2SM = (1u << 4) | (MLP_UMMA_FMT << 7) | (MLP_UMMA_FMT << 10) | ((uint32_t)(N_MMA >> 3) << 17) | ((uint32_t)((2 * TILE_M) >> 4) << 24);
+__device__ __forceinline__ void umma_f16_ts_2sm(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(UMMA_IDESC_2SM), "r"(accumulate), "r"(0u) : "memory");
+}
+// arrive on the barrier at this offset in every CTA of the mask once the pair MMAs issued so far retire
+__device__ __forceinline__ void umma_commit_2sm_mc(unsigned long long *bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"(mask) : "memory");
+}
+// this CTA's half of a W2 box into its own ring; the bytes are counted on RANK 0's barrier (peer bit of the address cleared)
+__device__ __forceinline__ void tma_load_2d_2sm(void *dst, const CUtensorMap *map, unsigned long long *bar, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1) : "memory");
+}
+// arrive on rank 0's copy of a barrier, from either CTA of the pair.  Default semantics (release at CTA scope), as CUTLASS's
+// ClusterBarrier::arrive does for the same hand-off: what travels between the CTAs is tensor memory, ordered by tcgen05.wait +
+// tcgen05.fence::before_thread_sync on this side and fence::after_thread_sync on the issuer's; a release at CLUSTER scope here
+// measured ~700 cycles per arrival (profiles/r2_mlp_stall_accounting.txt)
+__device__ __forceinline__ void mbar_arrive_rank0(unsigned long long *bar) {
+    asm volatile(
+        "{\n\t.reg .b32 ra;\n\t"
+        "mapa.shared::cluster.u32 ra, %0, 0;\n\t"
+        "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(unsigned long long *bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra.uni WAIT_DONE;\n\t"
+        "bra.uni WAIT_LOOP;\n\t"
+        "WAIT_DONE:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+template <bool CLUSTER>
+__device__ __forceinline__ void mbar_wait_x(unsigned long long *bar, uint32_t parity) {
+#if MPPI_MLP_CG2_ACQ_CLUSTER
+    if constexpr (CLUSTER) mbar_wait_cluster(bar, parity); else mbar_wait(bar, parity);
+#else
+    mbar_wait(bar, parity);
+#endif
 }
 __device__ __forceinline__ void tmem_st4(uint32_t taddr, uint32_t r0, uint32_t r1, uint32_t r2, uint32_t r3) {
     asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(r0), "r"(r1), "r"(r2), "r"(r3) : "memory");
@@ -504,6 +586,7 @@ mppi_mlp_rollout_kernel(const __grid_constant__ TickArgs a, const __grid_constan
     // ---- one-time setup: constants, barriers, TMEM, step-1 index + window (same rule as the tick kernel)
     constexpr bool L1MMA = MPPI_MLP_L1_MMA && NG == 1;        // layer 1 as mma.sync on split-fp16 operands (one-GEMM kernels)
     constexpr bool KSPLIT = MPPI_MLP_KSPLIT && PP;            // last two accumulator quarters interleaved by K part
+    constexpr bool CG2 = MPPI_MLP_CG2 && PP && NG == 1;       // pair MMAs (cta_group::2, M = 256)
     constexpr int KS = NIN == 3 ? 16 : 32;
     const __half *smB1 = reinterpret_cast<const __half *>(dyn + B1_OFFSET);
     for (int j = tid; j < HID; j += MLP_THREADS) {
@@ -519,16 +602,22 @@ mppi_mlp_rollout_kernel(const __grid_constant__ TickArgs a, const __grid_constan
     if (tid < 3) ms.b3[tid] = g_b3[tid];
     if (tid < 4) sm.x0[tid] = a.x0[tid];
     if (tid == 0) {
-        for (int s = 0; s < B_STAGES; ++s) { mbar_init(&ms.b_full[s], 1); mbar_init(&ms.b_empty[s], 2); }   // empty: both CTAs
-        for (int pa = 0; pa < N_QUARTERS; ++pa) { mbar_init(&ms.a_ready[pa], N_COMPUTE); mbar_init(&ms.a_free[pa], 1); }
-        for (int bf = 0; bf < 2; ++bf) { mbar_init(&ms.d_full[bf], 1); mbar_init(&ms.d_empty[bf], N_COMPUTE); }
-        for (int s = 0; s < B2_STAGES; ++s) { mbar_init(&ms.b2_full[s], 1); mbar_init(&ms.b2_empty[s], 2); }
-        for (int pa = 0; pa < N_QUARTERS; ++pa) mbar_init(&ms.a2_ready[pa], N_COMPUTE);
+        // multicast TMA: a slot is free when BOTH CTAs' MMAs have read it (2); pair MMAs: one commit frees each CTA's own half (1).
+        // Pair MMAs: the compute warps of both CTAs report to rank 0's a_ready / d_empty
+        for (int s = 0; s < RING_SLOTS; ++s) { mbar_init(&ms.b_full[s], 1); mbar_init(&ms.b_empty[s], CG2 ? 1 : 2); }
+        for (int pa = 0; pa < N_QUARTERS; ++pa) { mbar_init(&ms.a_ready[pa], CG2 ? 2 * N_ARRIVE : N_ARRIVE); mbar_init(&ms.a_free[pa], 1); }
+        for (int bf = 0; bf < 2; ++bf) { mbar_init(&ms.d_full[bf], 1); mbar_init(&ms.d_empty[bf], CG2 ? 2 * N_ARRIVE : N_ARRIVE); }
+        for (int pa = 0; pa < N_QUARTERS; ++pa) mbar_init(&ms.a2_ready[pa], N_ARRIVE);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&ms.tmem_base)), "r"(512));
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+        if constexpr (CG2) {                                  // the same warp of both CTAs allocates the pair's tensor memory
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&ms.tmem_base)), "r"(512));
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&ms.tmem_base)), "r"(512));
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+        }
     }
     __syncthreads();
     {
@@ -595,11 +684,11 @@ mppi_mlp_rollout_kernel(const __grid_constant__ TickArgs a, const __grid_constan
             int stage = 0; uint32_t phase = 0;
             for (int it = 0; it < total; ++it) {
                 const int kc = it % (HID / KCH), nq = (it / (HID / KCH)) % N_QUARTERS, g = (it / (HID / KCH * N_QUARTERS)) % NG;
-                mbar_wait(&ms.b2_empty[stage], phase ^ 1);
+                mbar_wait(&ms.b_empty[stage], phase ^ 1);
                 if (leader) {
-                    mbar_expect_tx(&ms.b2_full[stage], B_BOX_BYTES);
+                    mbar_expect_tx(&ms.b_full[stage], B_BOX_BYTES);
                     if ((uint32_t)(it & 1) == cta_rank)
-                        tma_load_2d_mc(smB + stage * B_BOX_BYTES, &w2_map, &ms.b2_full[stage], kc * KCH, g * HID + nq * N_MMA, (uint16_t)3);
+                        tma_load_2d_mc(smB + stage * B_BOX_BYTES, &w2_map, &ms.b_full[stage], kc * KCH, g * HID + nq * N_MMA, (uint16_t)3);
                 }
                 __syncwarp();
                 if (++stage == B2_STAGES) { stage = 0; phase ^= 1; }
@@ -611,6 +700,20 @@ mppi_mlp_rollout_kernel(const __grid_constant__ TickArgs a, const __grid_constan
             int nq, kb2;
             mlp_stage_map<KSPLIT>(it % STAGES_PER_STEP, nq, kb2);
             mbar_wait(&ms.b_empty[stage], phase ^ 1);               // both CTAs are done with this slot
+            if constexpr (CG2) {
+                // pair MMAs: every CTA loads ITS half of the box rows (64 of 128) into its own ring; all bytes of the pair are
+                // counted on rank 0's barrier, which rank 0 arms for both halves
+                if (leader) {
+                    if (cta_rank == 0) mbar_expect_tx(&ms.b_full[stage], 2 * CG2_TILE_BYTES);
+#pragma unroll
+                    for (int j = 0; j < KCH_PER_STAGE; ++j)
+                        tma_load_2d_2sm(smB + stage * CG2_TILE_BYTES + j * CG2_BOX_BYTES, &w2_map, &ms.b_full[stage],
+                                        (kb2 * KCH_PER_STAGE + j) * KCH, nq * N_MMA + (int)cta_rank * (N_MMA / 2));
+                }
+                __syncwarp();
+                if (++stage == CG2_STAGES) { stage = 0; phase ^= 1; }
+                continue;
+            }
             if (leader) {
                 mbar_expect_tx(&ms.b_full[stage], B_TILE_BYTES);    // every CTA arms its own barrier ...
                 if ((uint32_t)(it & 1) == cta_rank) {                // ... and issues every other stage for both
@@ -643,7 +746,7 @@ mppi_mlp_rollout_kernel(const __grid_constant__ TickArgs a, const __grid_constan
                             // GEMM 1 reads the layer-1 activations from tensor memory, GEMM 2 the tile GEMM 1's epilogue
                             // wrote to shared memory
                             if (nq == 0 && (kc & 1) == 0) mbar_wait(g == 0 ? &ms.a_ready[kc >> 1] : &ms.a2_ready[kc >> 1], a_phase);
-                            mbar_wait(&ms.b2_full[stage], phase);
+                            mbar_wait(&ms.b_full[stage], phase);
                             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                             const uint64_t b_desc0 = umma_desc_sw128(smem_u32(smB + stage * B_BOX_BYTES));
                             const uint64_t a_desc0 = umma_desc_sw128(smem_u32(smA2 + kc * B_BOX_BYTES));
@@ -654,7 +757,7 @@ mppi_mlp_rollout_kernel(const __grid_constant__ TickArgs a, const __grid_constan
                                     if (g == 0) umma_bf16_ts(d_tmem, a_col0 + k * 8, b_desc0 + (uint64_t)((k * 32) >> 4), (kc | k) ? 1u : 0u);
                                     else umma_bf16_ss(d_tmem, a_desc0 + (uint64_t)((k * 32) >> 4), b_desc0 + (uint64_t)((k * 32) >> 4), (kc | k) ? 1u : 0u);
                                 }
-                                umma_commit_mc(&ms.b2_empty[stage], (uint16_t)3);
+                                umma_commit_mc(&ms.b_empty[stage], (uint16_t)3);
                             }
                             __syncwarp();
                             if (++stage == B2_STAGES) { stage = 0; phase ^= 1; }
@@ -666,7 +769,7 @@ mppi_mlp_rollout_kernel(const __grid_constant__ TickArgs a, const __grid_constan
                 a_phase ^= 1;
             }
         } else
-        for (int step = 0; step < my_tile_steps; ++step) {
+        for (int step = 0; step < ((!CG2 || cta_rank == 0) ? my_tile_steps : 0); ++step) {      // pair MMAs: rank 0 issues for both CTAs
             for (int s = 0; s < STAGES_PER_STEP; ++s) {
                 int nq, kb2;
                 mlp_stage_map<KSPLIT>(s, nq, kb2);
@@ -674,7 +777,7 @@ mppi_mlp_rollout_kernel(const __grid_constant__ TickArgs a, const __grid_constan
                 const uint32_t buf = (uint32_t)nq & 1u;
                 MLP_TIC();
                 if (kb2 == 0) {
-                    mbar_wait(&ms.d_empty[buf], (((uint32_t)nq >> 1) & 1u) ^ 1u);      // epilogue drained this buffer
+                    mbar_wait_x<CG2>(&ms.d_empty[buf], (((uint32_t)nq >> 1) & 1u) ^ 1u);      // epilogue drained this buffer
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 }
                 MLP_TOC(nq);
@@ -683,29 +786,39 @@ mppi_mlp_rollout_kernel(const __grid_constant__ TickArgs a, const __grid_constan
                 // quarter's K loop chases them
                 if (nq == 0) {
 #pragma unroll
-                    for (int pa = 0; pa < KCH_PER_STAGE / 2; ++pa) mbar_wait(&ms.a_ready[kb2 * (KCH_PER_STAGE / 2) + pa], a_phase);
+                    for (int pa = 0; pa < KCH_PER_STAGE / 2; ++pa) mbar_wait_x<CG2>(&ms.a_ready[kb2 * (KCH_PER_STAGE / 2) + pa], a_phase);
                 }
                 MLP_TOC(4 + (kb2 * KCH_PER_STAGE / 2 & 3));
                 mbar_wait(&ms.b_full[stage], phase);
                 MLP_TOC(8 + nq);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 // one descriptor per stage; the K-steps only bump its 14-bit start-address field
-                const uint64_t b_desc0 = umma_desc_sw128(smem_u32(smB + stage * B_TILE_BYTES));
+                constexpr int TILE_B = CG2 ? CG2_TILE_BYTES : B_TILE_BYTES, BOX_B = CG2 ? CG2_BOX_BYTES : B_BOX_BYTES;
+                const uint64_t b_desc0 = umma_desc_sw128(smem_u32(smB + stage * TILE_B));
                 const uint32_t a_col0 = tmem + TMEM_A_COL + kb2 * KCH_PER_STAGE * (KCH / 16) * 8;
                 if (leader) {
 #pragma unroll
                     for (int k = 0; k < KCH_PER_STAGE * (KCH / 16); ++k) {
-                        const uint64_t b_desc = b_desc0 + (uint64_t)(((k / (KCH / 16)) * B_BOX_BYTES + (k % (KCH / 16)) * 32) >> 4);
-                        umma_bf16_ts(d_tmem, a_col0 + k * 8, b_desc, (kb2 | k) ? 1u : 0u);
+                        const uint64_t b_desc = b_desc0 + (uint64_t)(((k / (KCH / 16)) * BOX_B + (k % (KCH / 16)) * 32) >> 4);
+                        if constexpr (CG2) umma_f16_ts_2sm(d_tmem, a_col0 + k * 8, b_desc, (kb2 | k) ? 1u : 0u);
+                        else umma_bf16_ts(d_tmem, a_col0 + k * 8, b_desc, (kb2 | k) ? 1u : 0u);
                         // ping-pong: quarter 3 is the last reader of A -- release each 128-column part as soon as its MMAs
                         // retire so the other tile's layer 1 can overwrite it
-                        if (PP && nq == N_QUARTERS - 1 && (k & 7) == 7) umma_commit(&ms.a_free[kb2 * (KCH_PER_STAGE / 2) + (k >> 3)]);
+                        if (PP && nq == N_QUARTERS - 1 && (k & 7) == 7) {
+                            if constexpr (CG2) umma_commit_2sm_mc(&ms.a_free[kb2 * (KCH_PER_STAGE / 2) + (k >> 3)], (uint16_t)3);
+                            else umma_commit(&ms.a_free[kb2 * (KCH_PER_STAGE / 2) + (k >> 3)]);
+                        }
                     }
-                    umma_commit_mc(&ms.b_empty[stage], (uint16_t)3);   // frees the W2 slot in BOTH CTAs when these MMAs retire
-                    if (kb2 == STAGES_PER_Q - 1) umma_commit(&ms.d_full[buf]);         // this accumulator quarter is complete
+                    if constexpr (CG2) {
+                        umma_commit_2sm_mc(&ms.b_empty[stage], (uint16_t)3);           // frees each CTA's half of the slot
+                        if (kb2 == STAGES_PER_Q - 1) umma_commit_2sm_mc(&ms.d_full[buf], (uint16_t)3);
+                    } else {
+                        umma_commit_mc(&ms.b_empty[stage], (uint16_t)3);   // frees the W2 slot in BOTH CTAs when these MMAs retire
+                        if (kb2 == STAGES_PER_Q - 1) umma_commit(&ms.d_full[buf]);         // this accumulator quarter is complete
+                    }
                 }
                 __syncwarp();
-                if (++stage == B_STAGES) { stage = 0; phase ^= 1; }
+                if (++stage == (CG2 ? CG2_STAGES : B_STAGES)) { stage = 0; phase ^= 1; }
             }
             a_phase ^= 1;
         }
@@ -793,7 +906,7 @@ mppi_mlp_rollout_kernel(const __grid_constant__ TickArgs a, const __grid_constan
                             tmem_st_16x256b_x2(tmem + ((uint32_t)(q * 32 + 16 * h) << 16) + TMEM_A_COL + (uint32_t)((part * N_MMA + grp * 32) >> 1), pk[h]);
                         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
                         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                        mbar_arrive(&ms.a_ready[part]);
+                        compute_arrive<CG2>(&ms.a_ready[part]);
                     }
                     ++l1_count;
                     return;
@@ -839,7 +952,7 @@ mppi_mlp_rollout_kernel(const __grid_constant__ TickArgs a, const __grid_constan
                                  pk[c8][0], pk[c8][1], pk[c8][2], pk[c8][3]);
                     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
                     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                    mbar_arrive(&ms.a_ready[part]);
+                    compute_arrive<CG2>(&ms.a_ready[part]);
                 }
 #else
 #pragma unroll 1
@@ -874,7 +987,7 @@ mppi_mlp_rollout_kernel(const __grid_constant__ TickArgs a, const __grid_constan
                     }
                     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
                     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                    mbar_arrive(&ms.a_ready[part]);
+                    compute_arrive<CG2>(&ms.a_ready[part]);
                     MLP_TOC(8 + part);
                 }
 #endif
@@ -892,7 +1005,7 @@ mppi_mlp_rollout_kernel(const __grid_constant__ TickArgs a, const __grid_constan
                 tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(TMEM_D_COL + buf * N_MMA + grp * 32), v);
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                mbar_arrive(&ms.d_empty[buf]);
+                compute_arrive<CG2>(&ms.d_empty[buf]);
                 MLP_TOC(12);
 #if MPPI_MLP_W3_PARAM
                 const int colu = __shfl_sync(0xffffffffu, col, 0);
@@ -1049,7 +1162,7 @@ mppi_mlp_rollout_kernel(const __grid_constant__ TickArgs a, const __grid_constan
                             tmem_st_16x256b_x2(tmem + ((uint32_t)(q * 32 + 16 * h) << 16) + TMEM_A_COL + (uint32_t)((part * N_MMA + grp * 32) >> 1), pk[h]);
                         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
                         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                        mbar_arrive(&ms.a_ready[part]);
+                        compute_arrive(&ms.a_ready[part]);
                     }
                 }
                 if (!L1MMA && owner) {
@@ -1085,7 +1198,7 @@ mppi_mlp_rollout_kernel(const __grid_constant__ TickArgs a, const __grid_constan
                     }
                     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
                     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                    mbar_arrive(&ms.a_ready[part]);
+                    compute_arrive(&ms.a_ready[part]);
                 }
                 // (2) owner overlaps with the GEMM: stage cost of the state reached by the previous step, then the
                 //     noise and clamped control of the NEXT step
@@ -1113,7 +1226,7 @@ mppi_mlp_rollout_kernel(const __grid_constant__ TickArgs a, const __grid_constan
                         tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(TMEM_D_COL + buf * N_MMA + grp * 32), v);
                         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
                         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                        mbar_arrive(&ms.d_empty[buf]);
+                        compute_arrive(&ms.d_empty[buf]);
                         unsigned char *dst = smA2 + (col >> 6) * B_BOX_BYTES + (row >> 3) * 1024 + (row & 7) * 128;
                         const int c16 = (col & 63) >> 3;
 #pragma unroll
@@ -1129,7 +1242,7 @@ mppi_mlp_rollout_kernel(const __grid_constant__ TickArgs a, const __grid_constan
                             *reinterpret_cast<uint4 *>(dst + (((c16 + c) ^ (row & 7)) << 4)) = pk;
                         }
                         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> the tensor core's reads
-                        mbar_arrive(&ms.a2_ready[nq]);
+                        compute_arrive(&ms.a2_ready[nq]);
                     }
                 }
                 // (3) epilogue: D -> +b2 -> tanh -> FP32 contraction with the 512x3 output layer
@@ -1144,7 +1257,7 @@ mppi_mlp_rollout_kernel(const __grid_constant__ TickArgs a, const __grid_constan
                     tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(TMEM_D_COL + buf * N_MMA + grp * 32), v);
                     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
                     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                    mbar_arrive(&ms.d_empty[buf]);                // values are in registers: the buffer may be overwritten
+                    compute_arrive(&ms.d_empty[buf]);                // values are in registers: the buffer may be overwritten
 #pragma unroll
                     for (int i = 0; i < 32; ++i) {
 #if MPPI_MLP_W3_PARAM
@@ -1190,7 +1303,8 @@ mppi_mlp_rollout_kernel(const __grid_constant__ TickArgs a, const __grid_constan
     __syncthreads();
     cluster_sync_all();                                   // no CTA leaves while its peer may still signal its barriers
     if (warp == 1) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
+        if constexpr (CG2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
+        else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
     }
 }
 
@@ -1214,6 +1328,7 @@ struct MlpState {
     unsigned int epoch = 0;
     int n_in = 3, n_gemm = 1;
     CUtensorMap w2_map;
+    CUtensorMap w2_map_half;              // 64-row boxes: each CTA's half of a W2 box under pair MMAs (MPPI_MLP_CG2)
     MlpW3 h_w3;                           // host copy of the output-layer records (kernel-parameter variant)
     bool ready = false;
 };
@@ -1345,6 +1460,11 @@ cudaError_t mlp_set_weights(MlpState *m, int n_in, int n_hidden, const float *co
                                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                                       CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return cudaErrorInvalidValue;
+    const cuuint32_t box_half[2] = {KCH, N_MMA / 2};
+    r = ((PFN_encodeTiled)fn)(&m->w2_map_half, MLP_TMAP_DTYPE, 2, m->d_w2, dims, strides, box_half, estr,
+                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return cudaErrorInvalidValue;
     m->n_in = n_in;
     m->n_gemm = n_gemm;
     m->ready = true;
@@ -1405,7 +1525,7 @@ int mlp_rollout_costs(MlpState *m, const TickArgs &args, bool sum, const float *
 #else
 #define MPPI_MLP_W3_ARG
 #endif
-#define MPPI_MLP_LAUNCH(N, P, G) mppi_mlp_rollout_kernel<N, P, G><<<grid, MLP_THREADS, MLP_DYN_SMEM, st>>>(a, m->w2_map, m->d_w01, m->d_w01u, m->d_w3, m->d_b3, m->d_bh, d_S, n_tiles, m->d_hand, m->d_hand_flag, fault, epoch, balanced, m->d_b1 MPPI_MLP_W3_ARG)
+#define MPPI_MLP_LAUNCH(N, P, G) mppi_mlp_rollout_kernel<N, P, G><<<grid, MLP_THREADS, MLP_DYN_SMEM, st>>>(a, (MPPI_MLP_CG2 && P && G == 1) ? m->w2_map_half : m->w2_map, m->d_w01, m->d_w01u, m->d_w3, m->d_b3, m->d_bh, d_S, n_tiles, m->d_hand, m->d_hand_flag, fault, epoch, balanced, m->d_b1 MPPI_MLP_W3_ARG)
     if (m->n_gemm == 2) { if (m->n_in == 5) MPPI_MLP_LAUNCH(5, false, 2); else MPPI_MLP_LAUNCH(3, false, 2); }
     else if (m->n_in == 5) { if (pp) MPPI_MLP_LAUNCH(5, true, 1); else MPPI_MLP_LAUNCH(5, false, 1); }
     else { if (pp) MPPI_MLP_LAUNCH(3, true, 1); else MPPI_MLP_LAUNCH(3, false, 1); }

@@ -123,6 +123,21 @@ constexpr int N_QUARTERS = HID / N_MMA;
 #ifndef MPPI_MLP_KSPLIT
 #define MPPI_MLP_KSPLIT 0
 #endif
+// -DMPPI_MLP_L1_TC=1 (ping-pong kernels): layer 1 ON THE tcgen05 TENSOR CORE.  The folded first layer needs FP32 accuracy, so inputs and
+// weights are split into fp16 pieces exactly as for MPPI_MLP_L1_MMA (three K slots per input + two for the bias: K = 16 | 32).  Its A
+// operand (128 sample rows x K) and B operand (512 hidden units x K) live in shared memory in the same K-major 128B-swizzled layout as
+// the weight boxes (rows padded to 128 B), and each 128-column part is ONE (two for 5 inputs) M128 x N128 x K16 MMA in the SS form.
+// The pre-activations of a part pass through accumulator buffer 0, which is idle between the drain of quarter 2 and the next GEMM's
+// quarter 0: the issuer slips the part-p MMA in right behind the K-part-p MMAs of the running GEMM's quarter 3 (the tensor pipe executes
+// in order, so the part's commit also proves that quarter 3 is done with A part p), the compute warps read it back (tcgen05.ld), apply
+// tanh, round once to fp16 and store it into A part p.  That replaces a broadcast LDS.128 + 3 (5) FMAs per (row, column) -- the work the
+// compute warps' chain is made of (profiles/r2_mlp_stall_accounting.txt) -- by one tcgen05.ld of 32 columns per thread and part.
+#ifndef MPPI_MLP_L1_TC
+#define MPPI_MLP_L1_TC 1
+#endif
+#ifndef MPPI_MLP_L1_TC_TRY
+#define MPPI_MLP_L1_TC_TRY 0          // 1: parts are slipped in only when a non-blocking test finds their buffer free (A/B)
+#endif
 #ifndef MPPI_MLP_KCH_PER_STAGE
 #define MPPI_MLP_KCH_PER_STAGE ((MPPI_MLP_L1_MMA || MPPI_MLP_KSPLIT) ? 2 : 4)
 #endif
@@ -151,12 +166,21 @@ static_assert(B_STAGES * B_TILE_BYTES <= RING_BYTES && (HID / KCH) % KCH_PER_STA
 #define MPPI_MLP_CG2_ACQ_CLUSTER 0        // 1: the issuer's waits on a_ready / d_empty acquire at cluster scope (A/B)
 #endif
 constexpr int CG2_BOX_BYTES = B_BOX_BYTES / 2;                    // 64 W2 rows x 64 K halves
-constexpr int CG2_TILE_BYTES = KCH_PER_STAGE * CG2_BOX_BYTES;
-constexpr int CG2_STAGES = RING_BYTES / CG2_TILE_BYTES;
-constexpr int RING_SLOTS = CG2_STAGES > B_STAGES ? (CG2_STAGES > B2_STAGES ? CG2_STAGES : B2_STAGES) : (B_STAGES > B2_STAGES ? B_STAGES : B2_STAGES);
+constexpr int RING_SLOTS = 12;                                    // barrier pairs: enough for every ring geometry (asserted in the kernel)
 constexpr int L1_KS_MAX = 32;                       // layer-1 MMA: K slots (halves) per row, 16 (3 inputs) or 32 (5 inputs)
 constexpr int B1_OFFSET = B_STAGES * B_TILE_BYTES;  // its B operand [512][KS] fp16 sits behind the NG = 1 ring in the operand region
 static_assert(!MPPI_MLP_L1_MMA || B1_OFFSET + HID * L1_KS_MAX * 2 <= RING_BYTES, "layer-1 B operand does not fit behind the ring");
+// tcgen05 layer 1 operands: K-major, SWIZZLE_32B -- rows of 16 halves (one K = 16 MMA step), 8-row atoms of 256 B, 16-byte chunk c of row
+// r stored at c ^ ((r / 4) % 2).  Five inputs take two K steps: two such tiles ("K blocks") per operand.
+constexpr int B1TC_KB_BYTES = HID * 32, A1TC_KB_BYTES = TILE_M * 32;     // one K block of B (16 KB: 4 parts of 4 KB) / of A (4 KB)
+constexpr int B1TC_BYTES = 2 * B1TC_KB_BYTES;       // B operand, 512 hidden units (32 KB)
+constexpr int A1TC_BYTES = 2 * A1TC_KB_BYTES;       // A operand, 128 sample rows (8 KB)
+static_assert(!(MPPI_MLP_L1_TC && MPPI_MLP_L1_MMA), "layer-1 variants exclude each other");
+// which ping-pong kernels use what (shared by the kernel and the launcher): MPPI_MLP_L1_TC = 1 -> the five-input kernels (where it wins:
+// their CUDA-core layer 1 costs two LDS + five FMAs per column), 2 -> all of them; pair MMAs for the others (the tcgen05 layer 1 issues
+// cta_group::1, and one kernel may use only one group size)
+__host__ __device__ constexpr bool mlp_use_l1tc(int nin, bool pp, int ng) { return pp && ng == 1 && (MPPI_MLP_L1_TC == 2 || (MPPI_MLP_L1_TC == 1 && nin == 5)); }
+__host__ __device__ constexpr bool mlp_use_cg2(int nin, bool pp, int ng) { return MPPI_MLP_CG2 && pp && ng == 1 && !mlp_use_l1tc(nin, pp, ng); }
 constexpr int TMEM_A_COL = 0;             // A operand: 512 bf16 per row = 256 packed 32-bit columns
 constexpr int TMEM_D_COL = 256;           // two accumulator buffers of 128 FP32 columns
 constexpr int N_GROUPS = 4;                // compute-warp groups: group g owns accumulator quarter g (128 columns)
@@ -177,7 +201,10 @@ struct MlpSmem {                          // after the 1024-aligned A / B region
         };
         __align__(16) __half a1[TILE_M][L1_KS_MAX];   // layer-1 MMA: the split-fp16 input row of every sample (A operand)
     };
-    float xw[TILE_M];                     // NIN = 5: second control component of each row (the first rides in xs.w)
+    union {
+        float xw[TILE_M];                 // NIN = 5: second control component of each row (the first rides in xs.w)
+        struct { unsigned long long a1_ready, d1_full, d1_empty; };   // tcgen05 layer 1 (never together with xw): input rows
+    };                                                                // written / part in buffer 0 / part read back
     float4 w3[HID];                       // (b2[j], W3[0][j], W3[1][j], W3[2][j])
     float4 xs[TILE_M];                    // current state of each row for the partner thread
     float res[N_GROUPS - 1][3][TILE_M];   // partners' partial output-layer sums (SoA: 4.5 KB instead of 6 KB as float4)
@@ -230,6 +257,16 @@ __device__ __forceinline__ void compute_arrive(unsigned long long *bar) {
 #endif
 }
 
+// non-blocking: has the phase with this parity completed?  (warp-uniform: lane 0's answer)
+__device__ __forceinline__ bool mbar_test_warp(unsigned long long *bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return __shfl_sync(0xffffffffu, ok, 0) != 0;
+}
+
 // warp-level wait: one lane polls the barrier (every try_wait is a shared-memory operation -- 16 compute warps polling
 // with all 32 lanes loaded the same data pipe the weight LDS, the UMMA B reads and the TMA writes go through), the rest
 // of the warp joins at __syncwarp, which also orders the polling lane's acquire before the other lanes' later accesses
@@ -260,6 +297,16 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
     d |= (uint64_t)((1024 >> 4) & 0x3FFF) << 32;         // stride byte offset
     d |= (uint64_t)1 << 46;                              // descriptor version (sm_100)
     d |= (uint64_t)2 << 61;                              // SWIZZLE_128B
+    return d;
+}
+
+// same for SWIZZLE_32B operands (tcgen05 layer 1): 8-row x 32-byte atoms 256 bytes apart
+__device__ __forceinline__ uint64_t umma_desc_sw32(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)((256 >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)6 << 61;                              // SWIZZLE_32B
     return d;
 }
 
@@ -431,6 +478,28 @@ __device__ __forceinline__ void write_a1_row(__half *rowp, const float (&x)[5]) 
         dst[i] = make_uint4((uint32_t)h[8 * i] | ((uint32_t)h[8 * i + 1] << 16), (uint32_t)h[8 * i + 2] | ((uint32_t)h[8 * i + 3] << 16),
                             (uint32_t)h[8 * i + 4] | ((uint32_t)h[8 * i + 5] << 16), (uint32_t)h[8 * i + 6] | ((uint32_t)h[8 * i + 7] << 16));
 }
+// tcgen05 layer 1: the same split input row in the K-major 32B-swizzled operand layout (row r at (r / 8) * 256 B + (r % 8) * 32 B,
+// 16-byte chunk c at position c ^ ((r / 4) % 2); halves 16..31 in the second K block)
+template <int NIN>
+__device__ __forceinline__ void write_a1tc_row(unsigned char *a1, int r, const float (&x)[5]) {
+    constexpr int KS = NIN == 3 ? 16 : 32;
+    unsigned short h[KS];
+#pragma unroll
+    for (int i = 0; i < KS; ++i) h[i] = 0;
+#pragma unroll
+    for (int c = 0; c < NIN; ++c) {
+        unsigned short hi, lo;
+        split_half(x[c], hi, lo);
+        h[3 * c] = hi; h[3 * c + 1] = hi; h[3 * c + 2] = lo;
+    }
+    h[3 * NIN] = 0x3C00; h[3 * NIN + 1] = 0x3C00;                       // 1.0
+    unsigned char *rowp = a1 + (r >> 3) * 256 + (r & 7) * 32;
+#pragma unroll
+    for (int i = 0; i < KS / 8; ++i)
+        *reinterpret_cast<uint4 *>(rowp + (i >> 1) * A1TC_KB_BYTES + (((i & 1) ^ ((r >> 2) & 1)) << 4)) =
+            make_uint4((uint32_t)h[8 * i] | ((uint32_t)h[8 * i + 1] << 16), (uint32_t)h[8 * i + 2] | ((uint32_t)h[8 * i + 3] << 16),
+                       (uint32_t)h[8 * i + 4] | ((uint32_t)h[8 * i + 5] << 16), (uint32_t)h[8 * i + 6] | ((uint32_t)h[8 * i + 7] << 16));
+}
 // A fragments of this warp's two 16-row tiles (rows q*32 + 16h ..), loaded once per layer-1 evaluation
 template <int NIN>
 __device__ __forceinline__ void load_a1_frags(const __half (*a1)[L1_KS_MAX], int q, int lane, uint32_t (&afr)[2][NIN == 3 ? 1 : 2][4]) {
@@ -498,12 +567,10 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
 
 // Order in which a tile-step's weight stages (accumulator quarter nq, K block kb2 of KCH_PER_STAGE chunks) are streamed and issued.
 // SPLIT: quarters 0 and 1 one after the other, then quarters 2 and 3 interleaved by K block (see MPPI_MLP_KSPLIT).
-constexpr int STAGES_PER_Q = HID / KCH / KCH_PER_STAGE;
-constexpr int STAGES_PER_STEP = N_QUARTERS * STAGES_PER_Q;
-template <bool SPLIT>
+template <bool SPLIT, int SPQ>
 __device__ __forceinline__ void mlp_stage_map(int s, int &nq, int &kb2) {
-    if (SPLIT && s >= 2 * STAGES_PER_Q) { const int j = s - 2 * STAGES_PER_Q; kb2 = j >> 1; nq = 2 + (j & 1); }
-    else { nq = s / STAGES_PER_Q; kb2 = s % STAGES_PER_Q; }
+    if (SPLIT && s >= 2 * SPQ) { const int j = s - 2 * SPQ; kb2 = j >> 1; nq = 2 + (j & 1); }
+    else { nq = s / SPQ; kb2 = s % SPQ; }
 }
 
 // ---- hand-off of a split quad / pair between neighbouring clusters (balanced schedule) ----
@@ -586,19 +653,34 @@ mppi_mlp_rollout_kernel(const __grid_constant__ TickArgs a, const __grid_constan
     // ---- one-time setup: constants, barriers, TMEM, step-1 index + window (same rule as the tick kernel)
     constexpr bool L1MMA = MPPI_MLP_L1_MMA && NG == 1;        // layer 1 as mma.sync on split-fp16 operands (one-GEMM kernels)
     constexpr bool KSPLIT = MPPI_MLP_KSPLIT && PP;            // last two accumulator quarters interleaved by K part
-    constexpr bool CG2 = MPPI_MLP_CG2 && PP && NG == 1;       // pair MMAs (cta_group::2, M = 256)
+    constexpr bool L1TC = mlp_use_l1tc(NIN, PP, NG);          // layer 1 on the tcgen05 tensor core
+    constexpr bool CG2 = mlp_use_cg2(NIN, PP, NG);            // pair MMAs (cta_group::2, M = 256)
+    // ring geometry of the one-GEMM kernels: K chunks per stage, stages, stages per accumulator quarter / per tile-step.  The tcgen05
+    // layer 1 follows quarter 3 K part by K part (one 128-column part = two K chunks per stage) and keeps 40 KB for its own operands
+    constexpr int KPS = L1TC ? 2 : KCH_PER_STAGE;
+    constexpr int NSTG = L1TC ? 4 : (CG2 ? RING_BYTES / (KPS * CG2_BOX_BYTES) : B_STAGES);
+    constexpr int SPQ = HID / KCH / KPS, SPS = N_QUARTERS * SPQ;
+    constexpr int B1_OFF = L1TC ? NSTG * KPS * B_BOX_BYTES : B1_OFFSET;     // layer-1 operands behind the ring
+    static_assert(NSTG <= RING_SLOTS && (!L1TC || B1_OFF + B1TC_BYTES + A1TC_BYTES <= RING_BYTES), "ring geometry");
+    unsigned char *smA1 = dyn + B1_OFF + B1TC_BYTES;                  // its A operand (this step's split input rows)
     constexpr int KS = NIN == 3 ? 16 : 32;
-    const __half *smB1 = reinterpret_cast<const __half *>(dyn + B1_OFFSET);
+    const __half *smB1 = reinterpret_cast<const __half *>(dyn + B1_OFF);
     for (int j = tid; j < HID; j += MLP_THREADS) {
         ms.w3[j] = g_w3[j];
-        if (!L1MMA) {
+        if (!L1MMA && !L1TC) {
             ms.w01[j] = g_w01[j];
             if (NIN == 5) ms.w01u[j] = g_w01u[j];
         }
     }
     if (L1MMA)
         for (int i = tid; i < HID * KS * 2 / 16; i += MLP_THREADS)
-            reinterpret_cast<uint4 *>(dyn + B1_OFFSET)[i] = reinterpret_cast<const uint4 *>(g_b1)[i];
+            reinterpret_cast<uint4 *>(dyn + B1_OFF)[i] = reinterpret_cast<const uint4 *>(g_b1)[i];
+    if (L1TC) {                                               // B operand as the host laid it out (swizzled); A rows start as zeros
+        for (int i = tid; i < B1TC_BYTES / 16; i += MLP_THREADS)
+            reinterpret_cast<uint4 *>(dyn + B1_OFF)[i] = reinterpret_cast<const uint4 *>(g_b1)[i];
+        for (int i = tid; i < A1TC_BYTES / 16; i += MLP_THREADS) reinterpret_cast<uint4 *>(smA1)[i] = make_uint4(0u, 0u, 0u, 0u);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
     if (tid < 3) ms.b3[tid] = g_b3[tid];
     if (tid < 4) sm.x0[tid] = a.x0[tid];
     if (tid == 0) {
@@ -608,6 +690,7 @@ mppi_mlp_rollout_kernel(const __grid_constant__ TickArgs a, const __grid_constan
         for (int pa = 0; pa < N_QUARTERS; ++pa) { mbar_init(&ms.a_ready[pa], CG2 ? 2 * N_ARRIVE : N_ARRIVE); mbar_init(&ms.a_free[pa], 1); }
         for (int bf = 0; bf < 2; ++bf) { mbar_init(&ms.d_full[bf], 1); mbar_init(&ms.d_empty[bf], CG2 ? 2 * N_ARRIVE : N_ARRIVE); }
         for (int pa = 0; pa < N_QUARTERS; ++pa) mbar_init(&ms.a2_ready[pa], N_ARRIVE);
+        if (L1TC) { mbar_init(&ms.a1_ready, N_ARRIVE / N_GROUPS); mbar_init(&ms.d1_full, 1); mbar_init(&ms.d1_empty, N_ARRIVE); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -675,7 +758,7 @@ mppi_mlp_rollout_kernel(const __grid_constant__ TickArgs a, const __grid_constan
     const uint32_t tmem = ms.tmem_base;
 
     if (warp == 0) {
-        // ===== TMA producer: the same 16 W2 boxes every timestep, through a B_STAGES ring =====
+        // ===== TMA producer: the same 16 W2 boxes every timestep, through a NSTG ring =====
         const bool leader = elect_one_sync();
         if constexpr (NG == 2) {
             // two layers' weights back to back: per step 2 GEMMs x 4 quarters x 8 K-chunks, one 16 KB box per stage;
@@ -694,37 +777,37 @@ mppi_mlp_rollout_kernel(const __grid_constant__ TickArgs a, const __grid_constan
                 if (++stage == B2_STAGES) { stage = 0; phase ^= 1; }
             }
         } else {
-        const int total = my_tile_steps * STAGES_PER_STEP;
+        const int total = my_tile_steps * SPS;
         int stage = 0; uint32_t phase = 0;
         for (int it = 0; it < total; ++it) {
             int nq, kb2;
-            mlp_stage_map<KSPLIT>(it % STAGES_PER_STEP, nq, kb2);
+            mlp_stage_map<KSPLIT, SPQ>(it % SPS, nq, kb2);
             mbar_wait(&ms.b_empty[stage], phase ^ 1);               // both CTAs are done with this slot
             if constexpr (CG2) {
                 // pair MMAs: every CTA loads ITS half of the box rows (64 of 128) into its own ring; all bytes of the pair are
                 // counted on rank 0's barrier, which rank 0 arms for both halves
                 if (leader) {
-                    if (cta_rank == 0) mbar_expect_tx(&ms.b_full[stage], 2 * CG2_TILE_BYTES);
+                    if (cta_rank == 0) mbar_expect_tx(&ms.b_full[stage], 2 * (KPS * CG2_BOX_BYTES));
 #pragma unroll
-                    for (int j = 0; j < KCH_PER_STAGE; ++j)
-                        tma_load_2d_2sm(smB + stage * CG2_TILE_BYTES + j * CG2_BOX_BYTES, &w2_map, &ms.b_full[stage],
-                                        (kb2 * KCH_PER_STAGE + j) * KCH, nq * N_MMA + (int)cta_rank * (N_MMA / 2));
+                    for (int j = 0; j < KPS; ++j)
+                        tma_load_2d_2sm(smB + stage * (KPS * CG2_BOX_BYTES) + j * CG2_BOX_BYTES, &w2_map, &ms.b_full[stage],
+                                        (kb2 * KPS + j) * KCH, nq * N_MMA + (int)cta_rank * (N_MMA / 2));
                 }
                 __syncwarp();
-                if (++stage == CG2_STAGES) { stage = 0; phase ^= 1; }
+                if (++stage == NSTG) { stage = 0; phase ^= 1; }
                 continue;
             }
             if (leader) {
-                mbar_expect_tx(&ms.b_full[stage], B_TILE_BYTES);    // every CTA arms its own barrier ...
+                mbar_expect_tx(&ms.b_full[stage], (KPS * B_BOX_BYTES));    // every CTA arms its own barrier ...
                 if ((uint32_t)(it & 1) == cta_rank) {                // ... and issues every other stage for both
 #pragma unroll
-                    for (int j = 0; j < KCH_PER_STAGE; ++j)
-                        tma_load_2d_mc(smB + stage * B_TILE_BYTES + j * B_BOX_BYTES, &w2_map, &ms.b_full[stage],
-                                       (kb2 * KCH_PER_STAGE + j) * KCH, nq * N_MMA, (uint16_t)3);
+                    for (int j = 0; j < KPS; ++j)
+                        tma_load_2d_mc(smB + stage * (KPS * B_BOX_BYTES) + j * B_BOX_BYTES, &w2_map, &ms.b_full[stage],
+                                       (kb2 * KPS + j) * KCH, nq * N_MMA, (uint16_t)3);
                 }
             }
             __syncwarp();
-            if (++stage == B_STAGES) { stage = 0; phase ^= 1; }
+            if (++stage == NSTG) { stage = 0; phase ^= 1; }
         }
         }
     } else if (warp == 1) {
@@ -768,59 +851,107 @@ mppi_mlp_rollout_kernel(const __grid_constant__ TickArgs a, const __grid_constan
                 }
                 a_phase ^= 1;
             }
-        } else
+        } else {
+        // tcgen05 layer 1 (L1TC): evaluation #n feeds GEMM #n.  #0 is issued on its own; #(n+1) is slipped into GEMM #n's quarter 3, part p
+        // right behind the K-part-p MMAs, as soon as its inputs are there (a1_ready) and buffer 0 is free (quarter 2 drained / part p-1
+        // read back) -- tested WITHOUT blocking, so quarter 3 never waits for the compute warps; what is left is issued after it.
+        static_assert(!L1TC || !KSPLIT, "tcgen05 layer 1 follows quarter 3 in its natural order");
+        uint32_t l1_n = 0, l1_parts = 0, d1e_n = 0;          // evaluation being issued, its parts issued so far, d1_empty phases consumed
+        bool l1_inline = false; (void)l1_inline;
+        auto l1_try_part = [&](bool block) -> bool {
+            if (l1_parts == 0) {
+                if (block) {
+                    mbar_wait(&ms.a1_ready, l1_n & 1);
+                    if (l1_n > 0) mbar_wait(&ms.d_empty[0], 1u);        // quarter 2 of the running GEMM has been read out of buffer 0
+                } else if (!mbar_test_warp(&ms.a1_ready, l1_n & 1) || !mbar_test_warp(&ms.d_empty[0], 1u)) return false;
+            } else {
+                if (block) mbar_wait(&ms.d1_empty, d1e_n & 1);
+                else if (!mbar_test_warp(&ms.d1_empty, d1e_n & 1)) return false;
+                ++d1e_n;
+            }
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (leader) {
+                const uint64_t a_desc = umma_desc_sw32(smem_u32(smA1));
+                const uint64_t b_desc = umma_desc_sw32(smem_u32(dyn + B1_OFF + (int)l1_parts * (N_MMA * 32)));
+                umma_bf16_ss(tmem + TMEM_D_COL, a_desc, b_desc, 0u);
+                if (NIN == 5) umma_bf16_ss(tmem + TMEM_D_COL, a_desc + (uint64_t)(A1TC_KB_BYTES >> 4), b_desc + (uint64_t)(B1TC_KB_BYTES >> 4), 1u);   // second K block
+                umma_commit(&ms.d1_full);
+            }
+            __syncwarp();
+            if (++l1_parts == N_QUARTERS) { l1_parts = 0; ++l1_n; }
+            return true;
+        };
+        if constexpr (L1TC) {
+            if (my_tile_steps > 0) for (int p = 0; p < N_QUARTERS; ++p) l1_try_part(true);
+        }
         for (int step = 0; step < ((!CG2 || cta_rank == 0) ? my_tile_steps : 0); ++step) {      // pair MMAs: rank 0 issues for both CTAs
-            for (int s = 0; s < STAGES_PER_STEP; ++s) {
+            for (int s = 0; s < SPS; ++s) {
                 int nq, kb2;
-                mlp_stage_map<KSPLIT>(s, nq, kb2);
+                mlp_stage_map<KSPLIT, SPQ>(s, nq, kb2);
                 // quarter Q = 4 step + nq of this CTA runs in buffer Q & 1 = nq & 1; its previous user was quarter Q - 2
                 const uint32_t buf = (uint32_t)nq & 1u;
                 MLP_TIC();
                 if (kb2 == 0) {
                     mbar_wait_x<CG2>(&ms.d_empty[buf], (((uint32_t)nq >> 1) & 1u) ^ 1u);      // epilogue drained this buffer
+                    if (L1TC && nq == 0) { mbar_wait(&ms.d1_empty, d1e_n & 1); ++d1e_n; }      // ... and layer 1's last part has left it
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 }
                 MLP_TOC(nq);
                 const uint32_t d_tmem = tmem + TMEM_D_COL + buf * N_MMA;
-                // the activations arrive in four 128-column parts (a stage spans KCH_PER_STAGE / 2 of them); the first
+                // the activations arrive in four 128-column parts (a stage spans KPS / 2 of them); the first
                 // quarter's K loop chases them
                 if (nq == 0) {
 #pragma unroll
-                    for (int pa = 0; pa < KCH_PER_STAGE / 2; ++pa) mbar_wait_x<CG2>(&ms.a_ready[kb2 * (KCH_PER_STAGE / 2) + pa], a_phase);
+                    for (int pa = 0; pa < KPS / 2; ++pa) mbar_wait_x<CG2>(&ms.a_ready[kb2 * (KPS / 2) + pa], a_phase);
                 }
-                MLP_TOC(4 + (kb2 * KCH_PER_STAGE / 2 & 3));
+                MLP_TOC(4 + (kb2 * KPS / 2 & 3));
                 mbar_wait(&ms.b_full[stage], phase);
                 MLP_TOC(8 + nq);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 // one descriptor per stage; the K-steps only bump its 14-bit start-address field
-                constexpr int TILE_B = CG2 ? CG2_TILE_BYTES : B_TILE_BYTES, BOX_B = CG2 ? CG2_BOX_BYTES : B_BOX_BYTES;
+                constexpr int BOX_B = CG2 ? CG2_BOX_BYTES : B_BOX_BYTES, TILE_B = KPS * BOX_B;
                 const uint64_t b_desc0 = umma_desc_sw128(smem_u32(smB + stage * TILE_B));
-                const uint32_t a_col0 = tmem + TMEM_A_COL + kb2 * KCH_PER_STAGE * (KCH / 16) * 8;
+                const uint32_t a_col0 = tmem + TMEM_A_COL + kb2 * KPS * (KCH / 16) * 8;
                 if (leader) {
 #pragma unroll
-                    for (int k = 0; k < KCH_PER_STAGE * (KCH / 16); ++k) {
+                    for (int k = 0; k < KPS * (KCH / 16); ++k) {
                         const uint64_t b_desc = b_desc0 + (uint64_t)(((k / (KCH / 16)) * BOX_B + (k % (KCH / 16)) * 32) >> 4);
                         if constexpr (CG2) umma_f16_ts_2sm(d_tmem, a_col0 + k * 8, b_desc, (kb2 | k) ? 1u : 0u);
                         else umma_bf16_ts(d_tmem, a_col0 + k * 8, b_desc, (kb2 | k) ? 1u : 0u);
                         // ping-pong: quarter 3 is the last reader of A -- release each 128-column part as soon as its MMAs
                         // retire so the other tile's layer 1 can overwrite it
-                        if (PP && nq == N_QUARTERS - 1 && (k & 7) == 7) {
-                            if constexpr (CG2) umma_commit_2sm_mc(&ms.a_free[kb2 * (KCH_PER_STAGE / 2) + (k >> 3)], (uint16_t)3);
-                            else umma_commit(&ms.a_free[kb2 * (KCH_PER_STAGE / 2) + (k >> 3)]);
+                        if (PP && !L1TC && nq == N_QUARTERS - 1 && (k & 7) == 7) {
+                            if constexpr (CG2) umma_commit_2sm_mc(&ms.a_free[kb2 * (KPS / 2) + (k >> 3)], (uint16_t)3);
+                            else umma_commit(&ms.a_free[kb2 * (KPS / 2) + (k >> 3)]);
                         }
                     }
                     if constexpr (CG2) {
                         umma_commit_2sm_mc(&ms.b_empty[stage], (uint16_t)3);           // frees each CTA's half of the slot
-                        if (kb2 == STAGES_PER_Q - 1) umma_commit_2sm_mc(&ms.d_full[buf], (uint16_t)3);
+                        if (kb2 == SPQ - 1) umma_commit_2sm_mc(&ms.d_full[buf], (uint16_t)3);
                     } else {
                         umma_commit_mc(&ms.b_empty[stage], (uint16_t)3);   // frees the W2 slot in BOTH CTAs when these MMAs retire
-                        if (kb2 == STAGES_PER_Q - 1) umma_commit(&ms.d_full[buf]);         // this accumulator quarter is complete
+                        if (kb2 == SPQ - 1) umma_commit(&ms.d_full[buf]);         // this accumulator quarter is complete
                     }
                 }
                 __syncwarp();
-                if (++stage == (CG2 ? CG2_STAGES : B_STAGES)) { stage = 0; phase ^= 1; }
+                if (++stage == NSTG) { stage = 0; phase ^= 1; }
+                if (L1TC && nq == N_QUARTERS - 1 && step + 1 < my_tile_steps) {
+                    // Issue order K0 K1 [L1 p0] K2 [L1 p1] K3 [L1 p2] [L1 p3]: a part is issued one K part of quarter 3 late, so the
+                    // wait for its buffer (quarter 2 drained / previous part read back) is covered by MMAs already queued.  Only if
+                    // the inputs are there by K1 (always, inside a segment: they are published at the start of the slot); at a
+                    // segment boundary the next tile's inputs come after this GEMM's epilogue -- waiting here would deadlock -- so
+                    // the whole evaluation follows the quarter.
+#if MPPI_MLP_L1_TC_TRY
+                    while ((int)l1_parts <= kb2 && (int)l1_n == step + 1 && l1_try_part(false)) {}
+#else
+                    if (kb2 == 1) l1_inline = mbar_test_warp(&ms.a1_ready, l1_n & 1);
+                    if (l1_inline && kb2 >= 1) l1_try_part(true);
+#endif
+                    if (kb2 == SPQ - 1) { while ((int)l1_n == step + 1) l1_try_part(true); l1_inline = false; }
+                }
             }
             a_phase ^= 1;
+        }
         }
         MLP_PROBE_PRINT("issuer: wait d_empty q0-3 | a_ready p0-3 | b_full q0-3", my_tile_steps);
     } else {
@@ -836,7 +967,7 @@ mppi_mlp_rollout_kernel(const __grid_constant__ TickArgs a, const __grid_constan
         const int row = q * 32 + lane;
         const bool owner = grp < 2;
         uint32_t d_phase[2] = {0, 0};
-        uint32_t l1_count = 0;
+        uint32_t l1_count = 0, d1_phase = 0;
         MLP_PROBE_DECL();
         // segments of this CTA: static = tile pairs over the whole horizon; balanced = [head], whole quads, [tail]
         const int g_first = balanced ? bal_b0 / T : 0;
@@ -884,7 +1015,46 @@ mppi_mlp_rollout_kernel(const __grid_constant__ TickArgs a, const __grid_constan
                 sincos_cw(z[2], sn, cs);
             };
             // layer 1 of the tile owned by group og -> A region (L1 #l1_count, consumed by GEMM #l1_count)
+            // tcgen05 layer 1, compute side.  l1_publish: the owner group writes its tile's split input rows (as soon as the state is
+            // known -- the issuer slips the MMAs into the running GEMM's last quarter only if they are there in time);
+            // l1_collect: every group reads its 32 columns of each part back from accumulator buffer 0, applies tanh, rounds once and
+            // stores the operand into A part p (the part's commit also proves the running GEMM is done with that part of A)
+            auto l1_publish = [&](int og) {
+                if (grp == og) {
+                    const float xin[5] = {z[0], z[1], z[2], vc0, vc1};
+                    write_a1tc_row<NIN>(smA1, row, xin);
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy stores -> the tensor core's reads
+                    compute_arrive(&ms.a1_ready);
+                }
+            };
+            auto l1_collect = [&]() {
+#pragma unroll 1
+                for (int part = 0; part < N_QUARTERS; ++part) {
+                    MLP_TIC();
+                    mbar_wait_warp(&ms.d1_full, d1_phase); d1_phase ^= 1;
+                    MLP_TOC(4 + part);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    uint32_t v[32];
+                    tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(TMEM_D_COL + grp * 32), v);
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    compute_arrive(&ms.d1_empty);
+#pragma unroll
+                    for (int c8 = 0; c8 < 4; ++c8) {
+                        uint32_t pk[4];
+#pragma unroll
+                        for (int pp = 0; pp < 4; ++pp) pk[pp] = tanh_op2(__uint_as_float(v[8 * c8 + 2 * pp]), __uint_as_float(v[8 * c8 + 2 * pp + 1]));
+                        tmem_st4(tmem + ((uint32_t)(q * 32) << 16) + TMEM_A_COL + (uint32_t)((part * N_MMA + grp * 32 + c8 * 8) >> 1), pk[0], pk[1], pk[2], pk[3]);
+                    }
+                    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    compute_arrive<CG2>(&ms.a_ready[part]);
+                    MLP_TOC(8 + part);
+                }
+                ++l1_count;
+            };
             auto layer1 = [&](int og) {
+                if constexpr (L1TC) { l1_publish(og); l1_collect(); return; }
                 if constexpr (L1MMA) {
                     if (grp == og) {
                         const float xin[5] = {z[0], z[1], z[2], vc0, vc1};
@@ -1068,19 +1238,21 @@ mppi_mlp_rollout_kernel(const __grid_constant__ TickArgs a, const __grid_constan
                     finish(1, s0, s1, s2);
                     if (grp == 1) prep(t);
                 }
+                if constexpr (L1TC) l1_publish(1);                   // inputs of L1(Y, t): the evaluation before it is long done
                 r0 = r1 = r2 = 0.f;
 #pragma unroll
                 for (int nq = 0; nq < NQ_EARLY; ++nq) epilogue(nq, r0, r1, r2);                 // X(t)
-                layer1(1);                                           // L1(Y, t) chases the end of X(t)
+                if constexpr (L1TC) l1_collect(); else layer1(1);    // L1(Y, t) chases the end of X(t)
                 // ---- slot Y(t): the tensor core runs GEMM Y(t)
 #pragma unroll
                 for (int nq = NQ_EARLY; nq < N_QUARTERS; ++nq) epilogue(nq, r0, r1, r2);        // X(t), last quarter(s)
                 finish(0, r0, r1, r2);
                 if (grp == 0 && t + 1 < t1) prep(t + 1);
+                if constexpr (L1TC) { if (t + 1 < t1) l1_publish(0); }
                 s0 = s1 = s2 = 0.f;
 #pragma unroll
                 for (int nq = 0; nq < NQ_EARLY; ++nq) epilogue(nq, s0, s1, s2);                 // Y(t)
-                if (t + 1 < t1) layer1(0);                           // L1(X, t+1) chases the end of Y(t)
+                if (t + 1 < t1) { if constexpr (L1TC) l1_collect(); else layer1(0); }           // L1(X, t+1) chases the end of Y(t)
             }
 #pragma unroll
             for (int nq = NQ_EARLY; nq < N_QUARTERS; ++nq) epilogue(nq, s0, s1, s2);            // Y(t1-1), last quarter(s)
@@ -1350,7 +1522,7 @@ MlpState *mlp_create(int K, int T) {
         cudaMalloc(&m->d_w3, sizeof(float4) * HID) != cudaSuccess ||
         cudaMalloc(&m->d_w01u, sizeof(float2) * HID) != cudaSuccess ||
         cudaMalloc(&m->d_b3, sizeof(float) * 4) != cudaSuccess ||
-        cudaMalloc(&m->d_b1, sizeof(__half) * HID * L1_KS_MAX) != cudaSuccess) { mlp_destroy(m); return nullptr; }
+        cudaMalloc(&m->d_b1, MPPI_MLP_L1_TC ? (size_t)B1TC_BYTES : sizeof(__half) * HID * L1_KS_MAX) != cudaSuccess) { mlp_destroy(m); return nullptr; }
     if (cudaFuncSetAttribute(mppi_mlp_rollout_kernel<3, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MLP_DYN_SMEM) != cudaSuccess ||
         cudaFuncSetAttribute(mppi_mlp_rollout_kernel<5, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MLP_DYN_SMEM) != cudaSuccess ||
         cudaFuncSetAttribute(mppi_mlp_rollout_kernel<3, true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MLP_DYN_SMEM) != cudaSuccess ||
@@ -1392,7 +1564,7 @@ cudaError_t mlp_set_weights(MlpState *m, int n_in, int n_hidden, const float *co
     }
     std::vector<float4> w01(HID), w3(HID);
     std::vector<float2> w01u(HID, make_float2(0.f, 0.f));
-    std::vector<__half> b1((size_t)HID * L1_KS_MAX, __float2half_rn(0.f));
+    std::vector<__half> b1(MPPI_MLP_L1_TC ? (size_t)B1TC_BYTES / 2 : (size_t)HID * L1_KS_MAX, __float2half_rn(0.f));
     for (int j = 0; j < HID; ++j) {
         double s[5] = {0, 0, 0, 0, 0}, bb = b[1][j];
         for (int i = 0; i < HID; ++i) {
@@ -1407,7 +1579,8 @@ cudaError_t mlp_set_weights(MlpState *m, int n_in, int n_hidden, const float *co
             const int KS = n_in == 3 ? 16 : 32;
             const int part = j / N_MMA, g = (j % N_MMA) / 32, v = j % 32;
             const int cb = v / 16, m4 = (v % 16) / 4, e = (v % 4) / 2, dl = v % 2;
-            __half *row = &b1[(size_t)(part * N_MMA + g * 32 + 8 * (2 * cb + e) + 2 * m4 + dl) * KS];
+            __half slot[L1_KS_MAX];
+            for (int i = 0; i < L1_KS_MAX; ++i) slot[i] = __float2half_rn(0.f);
             auto split = [](double w, __half &hi, __half &lo) {
                 hi = __float2half_rn((float)w);
                 lo = __float2half_rn((float)(w - (double)__half2float(hi)));
@@ -1416,10 +1589,21 @@ cudaError_t mlp_set_weights(MlpState *m, int n_in, int n_hidden, const float *co
                 if (!(std::fabs(s[c]) <= 65504.0)) return cudaErrorInvalidValue;
                 __half hi, lo;
                 split(s[c], hi, lo);
-                row[3 * c] = hi; row[3 * c + 1] = lo; row[3 * c + 2] = hi;
+                slot[3 * c] = hi; slot[3 * c + 1] = lo; slot[3 * c + 2] = hi;
             }
             if (!(std::fabs(bb) <= 65504.0)) return cudaErrorInvalidValue;
-            split(bb, row[3 * n_in], row[3 * n_in + 1]);
+            split(bb, slot[3 * n_in], slot[3 * n_in + 1]);
+#if MPPI_MLP_L1_TC
+            // tcgen05 layer 1: plain unit order, K-major 32B-swizzled rows of 16 halves (unit r of a part at (r / 8) * 256 B + (r % 8) * 32 B,
+            // 16-byte chunk c at position c ^ ((r / 4) % 2)), parts 4 KB apart, the second K block (halves 16..31) 16 KB behind the first
+            (void)g; (void)v; (void)cb; (void)m4; (void)e; (void)dl;
+            const int r = j % N_MMA;
+            __half *row = &b1[((size_t)part * N_MMA * 32 + (size_t)(r >> 3) * 256 + (size_t)(r & 7) * 32) / 2];
+            for (int i = 0; i < KS; ++i) row[(size_t)(i >> 4) * (B1TC_KB_BYTES / 2) + (((((i >> 3) & 1) ^ ((r >> 2) & 1))) << 3) + (i & 7)] = slot[i];
+#else
+            __half *row = &b1[(size_t)(part * N_MMA + g * 32 + 8 * (2 * cb + e) + 2 * m4 + dl) * KS];
+            for (int i = 0; i < KS; ++i) row[i] = slot[i];
+#endif
         }
         const double o0 = out_scale ? out_scale[0] : 1.0, o1 = out_scale ? out_scale[1] : 1.0, o2 = out_scale ? out_scale[2] : 1.0;
         w3[j] = make_float4(b[l_last][j], (float)(W[l_out][0 * HID + j] * o0), (float)(W[l_out][1 * HID + j] * o1), (float)(W[l_out][2 * HID + j] * o2));
@@ -1525,7 +1709,7 @@ int mlp_rollout_costs(MlpState *m, const TickArgs &args, bool sum, const float *
 #else
 #define MPPI_MLP_W3_ARG
 #endif
-#define MPPI_MLP_LAUNCH(N, P, G) mppi_mlp_rollout_kernel<N, P, G><<<grid, MLP_THREADS, MLP_DYN_SMEM, st>>>(a, (MPPI_MLP_CG2 && P && G == 1) ? m->w2_map_half : m->w2_map, m->d_w01, m->d_w01u, m->d_w3, m->d_b3, m->d_bh, d_S, n_tiles, m->d_hand, m->d_hand_flag, fault, epoch, balanced, m->d_b1 MPPI_MLP_W3_ARG)
+#define MPPI_MLP_LAUNCH(N, P, G) mppi_mlp_rollout_kernel<N, P, G><<<grid, MLP_THREADS, MLP_DYN_SMEM, st>>>(a, mlp_use_cg2(N, P, G) ? m->w2_map_half : m->w2_map, m->d_w01, m->d_w01u, m->d_w3, m->d_b3, m->d_bh, d_S, n_tiles, m->d_hand, m->d_hand_flag, fault, epoch, balanced, m->d_b1 MPPI_MLP_W3_ARG)
     if (m->n_gemm == 2) { if (m->n_in == 5) MPPI_MLP_LAUNCH(5, false, 2); else MPPI_MLP_LAUNCH(3, false, 2); }
     else if (m->n_in == 5) { if (pp) MPPI_MLP_LAUNCH(5, true, 1); else MPPI_MLP_LAUNCH(5, false, 1); }
     else { if (pp) MPPI_MLP_LAUNCH(3, true, 1); else MPPI_MLP_LAUNCH(3, false, 1); }

@@ -32,6 +32,11 @@ if variant == "3l":          # the trained checkpoints' shape: 5 inputs, three h
            "b3": (rng.uniform(-1, 1, (512,)) / np.sqrt(512)).astype(np.float32), "W4": mlp["W3"], "b4": mlp["b3"],
            "in_mean": [4.39, -0.126, -0.08, 0.359, -0.031], "in_scale": [5.587, 3.641, 1.06, 1.024, 1.836],
            "out_mean": [-0.561, 0.029, -0.015], "out_scale": [5.701, 3.59, 0.996]}
+if variant == "5in":         # five inputs (state + control) + scalers, two hidden layers: layer 1 on the tcgen05 tensor core
+    rng = np.random.default_rng(1)
+    mlp = dict(mlp, W0=(rng.uniform(-1, 1, (512, 5)) / np.sqrt(5)).astype(np.float32),
+               in_mean=[4.39, -0.126, -0.08, 0.359, -0.031], in_scale=[5.587, 3.641, 1.06, 1.024, 1.836],
+               out_mean=[-0.561, 0.029, -0.015], out_scale=[5.701, 3.59, 0.996])
 ctrl = MPPIAlgorithms(**diffdrive_kwargs(K, T, 2.0), seed=7, dynamics=mlp)
 for i in range(ticks):
     ctrl._calc_input_control(np.array([0.4, 0.3, 0.5]))

@@ -3,21 +3,18 @@
 // with MLP = Linear(3,512) -> tanh(Linear(512,512)) -> tanh(Linear(512,512)) -> Linear(512,3)
 // (dnn/simple_mlp.py:10-23).
 //
-// sm_100a mapping (one persistent CTA per SM, each owning 128-sample tiles for the whole horizon):
+// sm_100a mapping (one persistent CTA per SM, clusters of two, each CTA owning 128-sample tiles for the whole horizon):
 //   * the input layer has NO activation (simple_mlp.py:19), so Linear(3,512) and the first hidden
-//     Linear(512,512) are folded on the host into one 3->512 map (W01 = W1 W0, b01 = W1 b0 + b1) that
-//     the compute warps evaluate in FP32 on the CUDA cores, apply tanh (MUFU tanh.approx.bf16x2) and
-//     store as the bf16 A operand straight into TENSOR MEMORY (tcgen05.st, 256 columns): the
-//     activations never touch shared memory, which leaves it all to the weight stream;
-//   * the remaining 512x512 layer is the GEMM: D[128x512] = A[128x512] (TMEM) x W2^T, issued by ONE
-//     thread as tcgen05.mma.cta_group::1.kind::f16 with the A operand in TMEM (M=128, N=128, K=16), W2
-//     streamed from L2 by TMA (cp.async.bulk.tensor, 128x64 bf16 boxes, 128B swizzle) through a
-//     3-stage mbarrier ring of 64 KB stages (four boxes each: one barrier wait and one commit per 16 MMAs keeps the
-//     single issuing thread ahead of the tensor core; 192 KB in flight hides the L2 latency).  CTAs run as clusters of two that
-//     walk the weight stream in lockstep: each CTA issues every other box with .multicast::cluster so
-//     both receive it -- L2 -> SM traffic per SM is halved; the accumulator is produced in
-//     four 128-column quarters through two TMEM buffers (2 x 128 columns), so the epilogue of one
-//     quarter overlaps the MMAs of the next;
+//     Linear(512,512) are folded on the host into one 3->512 map (W01 = W1 W0, b01 = W1 b0 + b1).  The compute warps evaluate it in
+//     FP32 on the CUDA cores (three-input kernels) or read it back from a split-fp16 tcgen05 MMA (five-input ping-pong kernels,
+//     MPPI_MLP_L1_TC), apply tanh (MUFU), round ONCE to the half-precision operand type and store the A operand straight into
+//     TENSOR MEMORY (tcgen05.st, 256 columns): the activations never touch shared memory, which leaves it to the weight stream;
+//   * the remaining 512x512 layer is the GEMM: D[128x512] = A[128x512] (TMEM) x W2^T, issued by ONE thread as tcgen05.mma kind::f16
+//     with the A operand in TMEM (N=128, K=16), W2 streamed from L2 by TMA (cp.async.bulk.tensor, 128B swizzle) through an mbarrier
+//     ring that fills the 192 KB of shared memory.  The two CTAs of a cluster walk the weight stream in lockstep; in the ping-pong
+//     kernels they are ONE MMA unit (cta_group::2, M = 256: rank 0 issues for both, each CTA holds half of every W2 box), otherwise
+//     each CTA issues every other box with .multicast::cluster; the accumulator is produced in four 128-column quarters through two
+//     TMEM buffers (2 x 128 columns), so the epilogue of one quarter overlaps the MMAs of the next;
 //   * the epilogue warps read the accumulator with tcgen05.ld (32x32b.x32), add b2, apply tanh and
 //     contract with the 512x3 output layer in FP32 registers -- the output layer never touches memory;
 //   * the unicycle step, nearest-waypoint search and cost run in the same epilogue threads with the
@@ -30,12 +27,14 @@
 // Residuals with THREE tanh layers (train/train_diff_mlp.py:13-36, saved_models/mlp_diff_300x100_3l*.pth) need a second
 // 512x512 GEMM whose A operand is the first GEMM's epilogue.  Tensor memory has no room for it (A 256 + two
 // accumulator buffers 256 = all 512 columns), so the template NG = 2 keeps that second operand in SHARED memory: the
-// epilogue of GEMM 1 (+bias, tanh, bf16 pack) writes the 128 x 512 tile in the K-major 128B-swizzled layout the UMMA
+// epilogue of GEMM 1 (+bias, tanh, pack) writes the 128 x 512 tile in the K-major 128B-swizzled layout the UMMA
 // descriptor expects (eight 16 KB K-chunks, 128 KB), fences it to the async proxy and GEMM 2 runs in the SS form; the
 // weight ring shrinks to four 16 KB stages and carries both layers' boxes back to back.
 // Warp roles: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer (both run converged, one elected lane issues), warps 2..17 = 16 compute
 // warps (four per TMEM lane quarter; group g = (warp-2)/4 takes 32 columns of every 128-column part of the
 // activations and of every accumulator quarter, so MMA start and epilogue tail are both short).
+// Variants that were built, measured and rejected (mma.sync layer 1, register-tiled 16x256b layer 1 / epilogue, early layer 1,
+// K-interleaved last quarters, output-layer records through the constant bank) are described in DESIGN.md 3.4 with the commits that hold them.
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
@@ -67,12 +66,6 @@ typedef __nv_bfloat16 mlp_op_t;
 #define MLP_UMMA_FMT 1u
 #endif
 
-// -DMPPI_MLP_W3_PARAM=1: the output-layer records (b2, W3[0..2][j]) travel as a kernel parameter (constant bank) and are read
-// with warp-uniform indices instead of one broadcast LDS.128 per (warp, column) -- A/B variant for the shared-memory pipe
-#ifndef MPPI_MLP_W3_PARAM
-#define MPPI_MLP_W3_PARAM 0
-#endif
-
 // Wrong-result TIMING probes (never shipped; profiles/): 1 = epilogue without the output-layer LDS + FMAs, 2 = layer 1 without its
 // LDS + FMAs, 4 = no MUFU (tanh replaced by the identity); bits may be combined
 #ifndef MPPI_MLP_PROBE
@@ -95,36 +88,14 @@ typedef __nv_bfloat16 mlp_op_t;
 #define MLP_PROBE_PRINT(what, steps)
 #endif
 
-#ifndef MPPI_MLP_L1_EARLY
-#define MPPI_MLP_L1_EARLY 0     // 1: ping-pong layer 1 evaluates a part into registers before waiting for that part of A (A/B variant)
-#endif
-
 constexpr int HID = 512;
 constexpr int TILE_M = 128;
 constexpr int KCH = 64;                   // K elements per 128-byte swizzle span (bf16)
 
 constexpr int N_MMA = 128;                // N per tcgen05.mma = one accumulator quarter
 constexpr int N_QUARTERS = HID / N_MMA;
-// -DMPPI_MLP_L1_MMA=1: layer 1 of the one-GEMM kernels as warp-level mma.sync.m16n8k16 on split-fp16 inputs and weights (see
-// layer1_mma_part below).  Parity-green but SLOWER: 0.968 against 0.923 ms/tick -- without the 32 HMMA per warp the same code
-// runs in 0.706 ms, i.e. the legacy mma.sync path costs ~4.9 k cycles per tile-step (~430 MAC/clk/SM) and holds up the tcgen05
-// pipeline it shares the tensor core with.  Kept as the measured A/B variant; the split operands, their shared-memory layout
-// and the five-stage 160 KB weight ring (within 1 % of three 64 KB stages) are what a tcgen05 layer 1 builds on.
-#ifndef MPPI_MLP_L1_MMA
-#define MPPI_MLP_L1_MMA 0
-#endif
-// -DMPPI_MLP_KSPLIT=1 (ping-pong kernels): the LAST TWO accumulator quarters of a tile-step are issued interleaved by K part --
-// (q2,p0) (q3,p0) (q2,p1) (q3,p1) ... through the two accumulator buffers -- instead of one after the other.  The last reader of A part p
-// then retires (p+1)/4 of the way through HALF the GEMM instead of a quarter of it, so the other tile's layer 1 (which may only overwrite
-// a part once the running GEMM has released it) has twice the window to hide in.  One 128-column part per ring stage (32 KB, six stages).
-// Parity-green (bit-identical costs) and SLOWER: 0.944 against 0.921 ms/tick (3 inputs), 1.058 against 1.025 (5 inputs) -- the stall
-// accounting (-DMPPI_MLP_PROBE=32, profiles/r2_mlp_stall_accounting.txt) shows why: the compute warps are busy ~77 % of a slot, so moving
-// the window does not shorten their chain, and quarters 2 and 3 now drain together BEHIND layer 1.  Kept as the measured A/B variant.
-#ifndef MPPI_MLP_KSPLIT
-#define MPPI_MLP_KSPLIT 0
-#endif
 // -DMPPI_MLP_L1_TC=1 (ping-pong kernels): layer 1 ON THE tcgen05 TENSOR CORE.  The folded first layer needs FP32 accuracy, so inputs and
-// weights are split into fp16 pieces exactly as for MPPI_MLP_L1_MMA (three K slots per input + two for the bias: K = 16 | 32).  Its A
+// weights are split into fp16 pieces, v = hi + lo, x.w ~= x_hi w_hi + x_hi w_lo + x_lo w_hi (three K slots per input + two for the bias: K = 16 | 32).  Its A
 // operand (128 sample rows x K) and B operand (512 hidden units x K) live in shared memory in the same K-major 128B-swizzled layout as
 // the weight boxes (rows padded to 128 B), and each 128-column part is ONE (two for 5 inputs) M128 x N128 x K16 MMA in the SS form.
 // The pre-activations of a part pass through accumulator buffer 0, which is idle between the drain of quarter 2 and the next GEMM's
@@ -135,14 +106,11 @@ constexpr int N_QUARTERS = HID / N_MMA;
 #ifndef MPPI_MLP_L1_TC
 #define MPPI_MLP_L1_TC 1
 #endif
-#ifndef MPPI_MLP_L1_TC_TRY
-#define MPPI_MLP_L1_TC_TRY 0          // 1: parts are slipped in only when a non-blocking test finds their buffer free (A/B)
-#endif
 #ifndef MPPI_MLP_KCH_PER_STAGE
-#define MPPI_MLP_KCH_PER_STAGE ((MPPI_MLP_L1_MMA || MPPI_MLP_KSPLIT) ? 2 : 4)
+#define MPPI_MLP_KCH_PER_STAGE 4
 #endif
 #ifndef MPPI_MLP_B_STAGES
-#define MPPI_MLP_B_STAGES (MPPI_MLP_L1_MMA ? 5 : (MPPI_MLP_KSPLIT ? 6 : 3))
+#define MPPI_MLP_B_STAGES 3
 #endif
 constexpr int KCH_PER_STAGE = MPPI_MLP_KCH_PER_STAGE;   // K chunks (TMA boxes) per ring stage: one barrier wait + one commit per 16 MMAs,
                                           // otherwise the single issuing thread (try_wait ~90 cycles) paces the tensor core
@@ -162,20 +130,14 @@ static_assert(B_STAGES * B_TILE_BYTES <= RING_BYTES && (HID / KCH) % KCH_PER_STA
 #ifndef MPPI_MLP_CG2
 #define MPPI_MLP_CG2 1
 #endif
-#ifndef MPPI_MLP_CG2_ACQ_CLUSTER
-#define MPPI_MLP_CG2_ACQ_CLUSTER 0        // 1: the issuer's waits on a_ready / d_empty acquire at cluster scope (A/B)
-#endif
 constexpr int CG2_BOX_BYTES = B_BOX_BYTES / 2;                    // 64 W2 rows x 64 K halves
 constexpr int RING_SLOTS = 12;                                    // barrier pairs: enough for every ring geometry (asserted in the kernel)
-constexpr int L1_KS_MAX = 32;                       // layer-1 MMA: K slots (halves) per row, 16 (3 inputs) or 32 (5 inputs)
-constexpr int B1_OFFSET = B_STAGES * B_TILE_BYTES;  // its B operand [512][KS] fp16 sits behind the NG = 1 ring in the operand region
-static_assert(!MPPI_MLP_L1_MMA || B1_OFFSET + HID * L1_KS_MAX * 2 <= RING_BYTES, "layer-1 B operand does not fit behind the ring");
+constexpr int L1_KS_MAX = 32;                       // tcgen05 layer 1: K slots (halves) per row, 16 (3 inputs) or 32 (5 inputs)
 // tcgen05 layer 1 operands: K-major, SWIZZLE_32B -- rows of 16 halves (one K = 16 MMA step), 8-row atoms of 256 B, 16-byte chunk c of row
 // r stored at c ^ ((r / 4) % 2).  Five inputs take two K steps: two such tiles ("K blocks") per operand.
 constexpr int B1TC_KB_BYTES = HID * 32, A1TC_KB_BYTES = TILE_M * 32;     // one K block of B (16 KB: 4 parts of 4 KB) / of A (4 KB)
 constexpr int B1TC_BYTES = 2 * B1TC_KB_BYTES;       // B operand, 512 hidden units (32 KB)
 constexpr int A1TC_BYTES = 2 * A1TC_KB_BYTES;       // A operand, 128 sample rows (8 KB)
-static_assert(!(MPPI_MLP_L1_TC && MPPI_MLP_L1_MMA), "layer-1 variants exclude each other");
 // which ping-pong kernels use what (shared by the kernel and the launcher): MPPI_MLP_L1_TC = 1 -> the five-input kernels (where it wins:
 // their CUDA-core layer 1 costs two LDS + five FMAs per column), 2 -> all of them; pair MMAs for the others (the tcgen05 layer 1 issues
 // cta_group::1, and one kernel may use only one group size)
@@ -191,16 +153,10 @@ constexpr int MLP_THREADS = 64 + N_COMPUTE;
 #endif
 constexpr int N_ARRIVE = MPPI_MLP_WARP_ARRIVE ? N_COMPUTE / 32 : N_COMPUTE;   // arrivals per compute-warp hand-off (see compute_arrive)
 
-struct MlpW3 { float4 w[HID]; };          // (b2[j], W3[0][j], W3[1][j], W3[2][j]) as a kernel parameter (MPPI_MLP_W3_PARAM)
 
 struct MlpSmem {                          // after the 1024-aligned A / B regions
-    union {
-        struct {
-            float4 w01[HID];                  // (W01[j][0], W01[j][1], W01[j][2], b01[j])
-            __align__(16) float2 w01u[HID];   // NIN = 5: (W01[j][3], W01[j][4]) -- the control columns
-        };
-        __align__(16) __half a1[TILE_M][L1_KS_MAX];   // layer-1 MMA: the split-fp16 input row of every sample (A operand)
-    };
+    float4 w01[HID];                      // (W01[j][0], W01[j][1], W01[j][2], b01[j])   (unused when layer 1 runs on the tensor core)
+    __align__(16) float2 w01u[HID];       // NIN = 5: (W01[j][3], W01[j][4]) -- the control columns
     union {
         float xw[TILE_M];                 // NIN = 5: second control component of each row (the first rides in xs.w)
         struct { unsigned long long a1_ready, d1_full, d1_empty; };   // tcgen05 layer 1 (never together with xw): input rows
@@ -358,23 +314,6 @@ __device__ __forceinline__ void mbar_arrive_rank0(unsigned long long *bar) {
         "mapa.shared::cluster.u32 ra, %0, 0;\n\t"
         "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}" ::"r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void mbar_wait_cluster(unsigned long long *bar, uint32_t parity) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "WAIT_LOOP:\n\t"
-        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra.uni WAIT_DONE;\n\t"
-        "bra.uni WAIT_LOOP;\n\t"
-        "WAIT_DONE:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
-}
-template <bool CLUSTER>
-__device__ __forceinline__ void mbar_wait_x(unsigned long long *bar, uint32_t parity) {
-#if MPPI_MLP_CG2_ACQ_CLUSTER
-    if constexpr (CLUSTER) mbar_wait_cluster(bar, parity); else mbar_wait(bar, parity);
-#else
-    mbar_wait(bar, parity);
-#endif
-}
 __device__ __forceinline__ void tmem_st4(uint32_t taddr, uint32_t r0, uint32_t r1, uint32_t r2, uint32_t r3) {
     asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(r0), "r"(r1), "r"(r2), "r"(r3) : "memory");
 }
@@ -428,57 +367,14 @@ __device__ __forceinline__ uint32_t tanh_op2(float lo, float hi) {
     return y;
 #endif
 }
-// ---- layer 1 on the tensor core (mma.sync.m16n8k16, fp16 x fp16 -> fp32) -------------------------------------------------
-// The folded first layer is a (128 rows x n_in) x (n_in x 512) product that has to keep FP32 accuracy (positions of tens of
-// metres, weights of any size), so inputs and weights are SPLIT into fp16 pieces, v = hi + lo with |lo| <= 2^-11 |hi|, and
-//     x.w ~= x_hi w_hi + x_hi w_lo + x_lo w_hi        (relative error 2^-22, products exact, FP32 accumulation)
-// which takes three K slots per input plus two for the bias (row values 1, 1 against b_hi, b_lo): K = 16 for 3 inputs (11 used),
-// 32 for 5 inputs (17 used).  Per 128-column part a warp (32 rows, this group's 32 columns) issues 2 x 4 x K/16 MMAs instead
-// of 32 x 32 x (n_in + 1) FMAs with one broadcast LDS.128 per column; the timing probes put 20 % of the tick there.
-// The accumulator fragment (thread t: rows t/4, t/4 + 8; columns 2(t%4), 2(t%4) + 1 of each 8-column tile) goes through tanh
-// and ONE rounding to fp16 straight into the A region of tensor memory with the 16x256b store shape, whose register layout is
-// the same fragment (register 4c + 2i + e: row t/4 + 8i, packed column 8c + 2(t%4) + e of the 16-lane slab).  That fixes which
-// hidden unit sits where in an MMA tile: within each block of 16 units, unit 4m + 2e + d is column 2m + d of tile e --
-// the order the B operand is stored in (mlp_set_weights).
-__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], const void *p) {
-    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
-                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(smem_u32(p)));
-}
-__device__ __forceinline__ void mma_m16n8k16(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
-                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
-}
-__device__ __forceinline__ void tmem_st_16x256b_x2(uint32_t taddr, const uint32_t (&r)[8]) {
-    asm volatile("tcgen05.st.sync.aligned.16x256b.x2.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
-                 ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
-}
 // v = hi + lo in half precision, packed (hi in the low half)
 __device__ __forceinline__ void split_half(float v, unsigned short &hi, unsigned short &lo) {
     const __half h = __float2half_rn(v);
     const __half l = __float2half_rn(v - __half2float(h));
     hi = __half_as_ushort(h); lo = __half_as_ushort(l);
 }
-// the split input row of one sample: slots 3c..3c+2 = (hi, hi, lo) of input c, then (1, 1) for the bias, zeros behind
-template <int NIN>
-__device__ __forceinline__ void write_a1_row(__half *rowp, const float (&x)[5]) {
-    constexpr int KS = NIN == 3 ? 16 : 32;
-    unsigned short h[KS];
-#pragma unroll
-    for (int i = 0; i < KS; ++i) h[i] = 0;
-#pragma unroll
-    for (int c = 0; c < NIN; ++c) {
-        unsigned short hi, lo;
-        split_half(x[c], hi, lo);
-        h[3 * c] = hi; h[3 * c + 1] = hi; h[3 * c + 2] = lo;
-    }
-    h[3 * NIN] = 0x3C00; h[3 * NIN + 1] = 0x3C00;                       // 1.0
-    uint4 *dst = reinterpret_cast<uint4 *>(rowp);
-#pragma unroll
-    for (int i = 0; i < KS / 8; ++i)
-        dst[i] = make_uint4((uint32_t)h[8 * i] | ((uint32_t)h[8 * i + 1] << 16), (uint32_t)h[8 * i + 2] | ((uint32_t)h[8 * i + 3] << 16),
-                            (uint32_t)h[8 * i + 4] | ((uint32_t)h[8 * i + 5] << 16), (uint32_t)h[8 * i + 6] | ((uint32_t)h[8 * i + 7] << 16));
-}
-// tcgen05 layer 1: the same split input row in the K-major 32B-swizzled operand layout (row r at (r / 8) * 256 B + (r % 8) * 32 B,
+// tcgen05 layer 1: the split input row of one sample -- slots 3c..3c+2 = (hi, hi, lo) of input c, then (1, 1) for the bias, zeros behind --
+// in the K-major 32B-swizzled operand layout (row r at (r / 8) * 256 B + (r % 8) * 32 B,
 // 16-byte chunk c at position c ^ ((r / 4) % 2); halves 16..31 in the second K block)
 template <int NIN>
 __device__ __forceinline__ void write_a1tc_row(unsigned char *a1, int r, const float (&x)[5]) {
@@ -500,58 +396,6 @@ __device__ __forceinline__ void write_a1tc_row(unsigned char *a1, int r, const f
             make_uint4((uint32_t)h[8 * i] | ((uint32_t)h[8 * i + 1] << 16), (uint32_t)h[8 * i + 2] | ((uint32_t)h[8 * i + 3] << 16),
                        (uint32_t)h[8 * i + 4] | ((uint32_t)h[8 * i + 5] << 16), (uint32_t)h[8 * i + 6] | ((uint32_t)h[8 * i + 7] << 16));
 }
-// A fragments of this warp's two 16-row tiles (rows q*32 + 16h ..), loaded once per layer-1 evaluation
-template <int NIN>
-__device__ __forceinline__ void load_a1_frags(const __half (*a1)[L1_KS_MAX], int q, int lane, uint32_t (&afr)[2][NIN == 3 ? 1 : 2][4]) {
-#pragma unroll
-    for (int h = 0; h < 2; ++h)
-#pragma unroll
-        for (int ks = 0; ks < (NIN == 3 ? 1 : 2); ++ks)
-            ldsm_x4(afr[h][ks], &a1[q * 32 + 16 * h + (lane & 7) + 8 * ((lane >> 3) & 1)][16 * ks + 8 * (lane >> 4)]);
-}
-// one 128-column part: this group's 32 hidden units for the warp's 32 rows -> tanh -> fp16, as the two 8-register store
-// payloads of the 16-lane slabs (pk[h]); `b1` = the layer's B operand [512][KS] (unit order permuted as described above)
-template <int NIN>
-__device__ __forceinline__ void layer1_mma_part(const __half *b1, int part, int grp, int lane,
-                                                const uint32_t (&afr)[2][NIN == 3 ? 1 : 2][4], uint32_t (&pk)[2][8]) {
-    constexpr int KS = NIN == 3 ? 16 : 32;
-    float c[2][4][4];
-#pragma unroll
-    for (int h = 0; h < 2; ++h)
-#pragma unroll
-        for (int n = 0; n < 4; ++n) c[h][n][0] = c[h][n][1] = c[h][n][2] = c[h][n][3] = 0.f;
-    const __half *tile0 = b1 + (size_t)(part * N_MMA + grp * 32) * KS;
-#pragma unroll
-    for (int n2 = 0; n2 < 2; ++n2) {                                    // two 8-unit tiles per ldmatrix.x4
-#pragma unroll
-        for (int ks = 0; ks < KS / 16; ++ks) {
-            uint32_t bfr[4];                                            // (tile 2 n2: k 0-7, k 8-15), (tile 2 n2 + 1: k 0-7, k 8-15)
-#if MPPI_MLP_PROBE & 16
-            bfr[0] = bfr[1] = bfr[2] = bfr[3] = (uint32_t)(n2 + ks);
-#else
-            ldsm_x4(bfr, tile0 + (size_t)(16 * n2 + 8 * (lane >> 4) + (lane & 7)) * KS + 16 * ks + 8 * ((lane >> 3) & 1));
-#endif
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-#if MPPI_MLP_PROBE & 8
-                c[h][2 * n2][0] += __uint_as_float(afr[h][ks][0] ^ bfr[0]); c[h][2 * n2 + 1][1] += __uint_as_float(afr[h][ks][1] ^ bfr[2]);
-#else
-                mma_m16n8k16(c[h][2 * n2], afr[h][ks], bfr[0], bfr[1]);
-                mma_m16n8k16(c[h][2 * n2 + 1], afr[h][ks], bfr[2], bfr[3]);
-#endif
-            }
-        }
-    }
-#pragma unroll
-    for (int h = 0; h < 2; ++h)
-#pragma unroll
-        for (int cb = 0; cb < 2; ++cb)
-#pragma unroll
-            for (int i = 0; i < 2; ++i)
-#pragma unroll
-                for (int e = 0; e < 2; ++e)
-                    pk[h][4 * cb + 2 * i + e] = tanh_op2(c[h][2 * cb + e][2 * i], c[h][2 * cb + e][2 * i + 1]);
-}
 // one lane of a CONVERGED warp (elect.sync): the MMA / TMA issue loops run warp-converged with the issuing
 // instructions predicated on this, so ptxas emits each UTCHMMA once with uniform-register operands instead of the
 // elect / execute / retire loop it needs inside a divergent `if (lane == 0)` region (8 SASS instructions and ~80
@@ -566,12 +410,8 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
 }
 
 // Order in which a tile-step's weight stages (accumulator quarter nq, K block kb2 of KCH_PER_STAGE chunks) are streamed and issued.
-// SPLIT: quarters 0 and 1 one after the other, then quarters 2 and 3 interleaved by K block (see MPPI_MLP_KSPLIT).
-template <bool SPLIT, int SPQ>
-__device__ __forceinline__ void mlp_stage_map(int s, int &nq, int &kb2) {
-    if (SPLIT && s >= 2 * SPQ) { const int j = s - 2 * SPQ; kb2 = j >> 1; nq = 2 + (j & 1); }
-    else { nq = s / SPQ; kb2 = s % SPQ; }
-}
+template <int SPQ>
+__device__ __forceinline__ void mlp_stage_map(int s, int &nq, int &kb2) { nq = s / SPQ; kb2 = s % SPQ; }
 
 // ---- hand-off of a split quad / pair between neighbouring clusters (balanced schedule) ----
 // Records live at hand[tile slot][6][128] (x, y, yaw, cost so far, previous control), tile slot = ((consumer cluster * 2 +
@@ -616,9 +456,6 @@ mppi_mlp_rollout_kernel(const __grid_constant__ TickArgs a, const __grid_constan
                         const float *__restrict__ g_b3, const float *__restrict__ g_bh, float *__restrict__ S_out, int n_tiles,
                         float *__restrict__ hand, unsigned int *__restrict__ hand_flag, unsigned int *__restrict__ fault,
                         unsigned int epoch, int balanced, const __half *__restrict__ g_b1
-#if MPPI_MLP_W3_PARAM
-                        , const __grid_constant__ MlpW3 w3p
-#endif
                         ) {
     static_assert(NG == 1 || (NG == 2 && !PP), "two GEMMs per step run the one-tile schedule");
     // 1024-byte alignment is what SWIZZLE_128B needs; keeping every pointer derived from this symbol (no
@@ -651,8 +488,6 @@ mppi_mlp_rollout_kernel(const __grid_constant__ TickArgs a, const __grid_constan
     const int my_tile_steps = balanced ? (PP ? 2 : 1) * (bal_b1 - bal_b0) : my_slots * T;    // tile-steps of this CTA
 
     // ---- one-time setup: constants, barriers, TMEM, step-1 index + window (same rule as the tick kernel)
-    constexpr bool L1MMA = MPPI_MLP_L1_MMA && NG == 1;        // layer 1 as mma.sync on split-fp16 operands (one-GEMM kernels)
-    constexpr bool KSPLIT = MPPI_MLP_KSPLIT && PP;            // last two accumulator quarters interleaved by K part
     constexpr bool L1TC = mlp_use_l1tc(NIN, PP, NG);          // layer 1 on the tcgen05 tensor core
     constexpr bool CG2 = mlp_use_cg2(NIN, PP, NG);            // pair MMAs (cta_group::2, M = 256)
     // ring geometry of the one-GEMM kernels: K chunks per stage, stages, stages per accumulator quarter / per tile-step.  The tcgen05
@@ -660,21 +495,16 @@ mppi_mlp_rollout_kernel(const __grid_constant__ TickArgs a, const __grid_constan
     constexpr int KPS = L1TC ? 2 : KCH_PER_STAGE;
     constexpr int NSTG = L1TC ? 4 : (CG2 ? RING_BYTES / (KPS * CG2_BOX_BYTES) : B_STAGES);
     constexpr int SPQ = HID / KCH / KPS, SPS = N_QUARTERS * SPQ;
-    constexpr int B1_OFF = L1TC ? NSTG * KPS * B_BOX_BYTES : B1_OFFSET;     // layer-1 operands behind the ring
+    constexpr int B1_OFF = NSTG * KPS * B_BOX_BYTES;           // tcgen05 layer-1 operands behind the ring
     static_assert(NSTG <= RING_SLOTS && (!L1TC || B1_OFF + B1TC_BYTES + A1TC_BYTES <= RING_BYTES), "ring geometry");
     unsigned char *smA1 = dyn + B1_OFF + B1TC_BYTES;                  // its A operand (this step's split input rows)
-    constexpr int KS = NIN == 3 ? 16 : 32;
-    const __half *smB1 = reinterpret_cast<const __half *>(dyn + B1_OFF);
     for (int j = tid; j < HID; j += MLP_THREADS) {
         ms.w3[j] = g_w3[j];
-        if (!L1MMA && !L1TC) {
+        if (!L1TC) {
             ms.w01[j] = g_w01[j];
             if (NIN == 5) ms.w01u[j] = g_w01u[j];
         }
     }
-    if (L1MMA)
-        for (int i = tid; i < HID * KS * 2 / 16; i += MLP_THREADS)
-            reinterpret_cast<uint4 *>(dyn + B1_OFF)[i] = reinterpret_cast<const uint4 *>(g_b1)[i];
     if (L1TC) {                                               // B operand as the host laid it out (swizzled); A rows start as zeros
         for (int i = tid; i < B1TC_BYTES / 16; i += MLP_THREADS)
             reinterpret_cast<uint4 *>(dyn + B1_OFF)[i] = reinterpret_cast<const uint4 *>(g_b1)[i];
@@ -781,7 +611,7 @@ mppi_mlp_rollout_kernel(const __grid_constant__ TickArgs a, const __grid_constan
         int stage = 0; uint32_t phase = 0;
         for (int it = 0; it < total; ++it) {
             int nq, kb2;
-            mlp_stage_map<KSPLIT, SPQ>(it % SPS, nq, kb2);
+            mlp_stage_map<SPQ>(it % SPS, nq, kb2);
             mbar_wait(&ms.b_empty[stage], phase ^ 1);               // both CTAs are done with this slot
             if constexpr (CG2) {
                 // pair MMAs: every CTA loads ITS half of the box rows (64 of 128) into its own ring; all bytes of the pair are
@@ -852,21 +682,17 @@ mppi_mlp_rollout_kernel(const __grid_constant__ TickArgs a, const __grid_constan
                 a_phase ^= 1;
             }
         } else {
-        // tcgen05 layer 1 (L1TC): evaluation #n feeds GEMM #n.  #0 is issued on its own; #(n+1) is slipped into GEMM #n's quarter 3, part p
-        // right behind the K-part-p MMAs, as soon as its inputs are there (a1_ready) and buffer 0 is free (quarter 2 drained / part p-1
-        // read back) -- tested WITHOUT blocking, so quarter 3 never waits for the compute warps; what is left is issued after it.
-        static_assert(!L1TC || !KSPLIT, "tcgen05 layer 1 follows quarter 3 in its natural order");
+        // tcgen05 layer 1 (L1TC): evaluation #n feeds GEMM #n.  #0 is issued on its own; #(n+1) is slipped into GEMM #n's quarter 3 (see
+        // the order below).  A part waits for its inputs (part 0: a1_ready, and quarter 2 read out of buffer 0) or for the previous
+        // part to have been read back (d1_empty)
         uint32_t l1_n = 0, l1_parts = 0, d1e_n = 0;          // evaluation being issued, its parts issued so far, d1_empty phases consumed
         bool l1_inline = false; (void)l1_inline;
-        auto l1_try_part = [&](bool block) -> bool {
+        auto l1_issue_part = [&]() {
             if (l1_parts == 0) {
-                if (block) {
-                    mbar_wait(&ms.a1_ready, l1_n & 1);
-                    if (l1_n > 0) mbar_wait(&ms.d_empty[0], 1u);        // quarter 2 of the running GEMM has been read out of buffer 0
-                } else if (!mbar_test_warp(&ms.a1_ready, l1_n & 1) || !mbar_test_warp(&ms.d_empty[0], 1u)) return false;
+                mbar_wait(&ms.a1_ready, l1_n & 1);
+                if (l1_n > 0) mbar_wait(&ms.d_empty[0], 1u);            // quarter 2 of the running GEMM has been read out of buffer 0
             } else {
-                if (block) mbar_wait(&ms.d1_empty, d1e_n & 1);
-                else if (!mbar_test_warp(&ms.d1_empty, d1e_n & 1)) return false;
+                mbar_wait(&ms.d1_empty, d1e_n & 1);
                 ++d1e_n;
             }
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -879,20 +705,19 @@ mppi_mlp_rollout_kernel(const __grid_constant__ TickArgs a, const __grid_constan
             }
             __syncwarp();
             if (++l1_parts == N_QUARTERS) { l1_parts = 0; ++l1_n; }
-            return true;
         };
         if constexpr (L1TC) {
-            if (my_tile_steps > 0) for (int p = 0; p < N_QUARTERS; ++p) l1_try_part(true);
+            if (my_tile_steps > 0) for (int p = 0; p < N_QUARTERS; ++p) l1_issue_part();
         }
         for (int step = 0; step < ((!CG2 || cta_rank == 0) ? my_tile_steps : 0); ++step) {      // pair MMAs: rank 0 issues for both CTAs
             for (int s = 0; s < SPS; ++s) {
                 int nq, kb2;
-                mlp_stage_map<KSPLIT, SPQ>(s, nq, kb2);
+                mlp_stage_map<SPQ>(s, nq, kb2);
                 // quarter Q = 4 step + nq of this CTA runs in buffer Q & 1 = nq & 1; its previous user was quarter Q - 2
                 const uint32_t buf = (uint32_t)nq & 1u;
                 MLP_TIC();
                 if (kb2 == 0) {
-                    mbar_wait_x<CG2>(&ms.d_empty[buf], (((uint32_t)nq >> 1) & 1u) ^ 1u);      // epilogue drained this buffer
+                    mbar_wait(&ms.d_empty[buf], (((uint32_t)nq >> 1) & 1u) ^ 1u);      // epilogue drained this buffer
                     if (L1TC && nq == 0) { mbar_wait(&ms.d1_empty, d1e_n & 1); ++d1e_n; }      // ... and layer 1's last part has left it
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 }
@@ -902,7 +727,7 @@ mppi_mlp_rollout_kernel(const __grid_constant__ TickArgs a, const __grid_constan
                 // quarter's K loop chases them
                 if (nq == 0) {
 #pragma unroll
-                    for (int pa = 0; pa < KPS / 2; ++pa) mbar_wait_x<CG2>(&ms.a_ready[kb2 * (KPS / 2) + pa], a_phase);
+                    for (int pa = 0; pa < KPS / 2; ++pa) mbar_wait(&ms.a_ready[kb2 * (KPS / 2) + pa], a_phase);
                 }
                 MLP_TOC(4 + (kb2 * KPS / 2 & 3));
                 mbar_wait(&ms.b_full[stage], phase);
@@ -941,13 +766,9 @@ mppi_mlp_rollout_kernel(const __grid_constant__ TickArgs a, const __grid_constan
                     // the inputs are there by K1 (always, inside a segment: they are published at the start of the slot); at a
                     // segment boundary the next tile's inputs come after this GEMM's epilogue -- waiting here would deadlock -- so
                     // the whole evaluation follows the quarter.
-#if MPPI_MLP_L1_TC_TRY
-                    while ((int)l1_parts <= kb2 && (int)l1_n == step + 1 && l1_try_part(false)) {}
-#else
                     if (kb2 == 1) l1_inline = mbar_test_warp(&ms.a1_ready, l1_n & 1);
-                    if (l1_inline && kb2 >= 1) l1_try_part(true);
-#endif
-                    if (kb2 == SPQ - 1) { while ((int)l1_n == step + 1) l1_try_part(true); l1_inline = false; }
+                    if (l1_inline && kb2 >= 1) l1_issue_part();
+                    if (kb2 == SPQ - 1) { while ((int)l1_n == step + 1) l1_issue_part(); l1_inline = false; }
                 }
             }
             a_phase ^= 1;
@@ -1055,32 +876,6 @@ mppi_mlp_rollout_kernel(const __grid_constant__ TickArgs a, const __grid_constan
             };
             auto layer1 = [&](int og) {
                 if constexpr (L1TC) { l1_publish(og); l1_collect(); return; }
-                if constexpr (L1MMA) {
-                    if (grp == og) {
-                        const float xin[5] = {z[0], z[1], z[2], vc0, vc1};
-                        write_a1_row<NIN>(ms.a1[row], xin);
-                    }
-                    named_bar_sync(1, N_COMPUTE);
-                    uint32_t afr[2][NIN == 3 ? 1 : 2][4];
-                    load_a1_frags<NIN>(ms.a1, q, lane, afr);
-#pragma unroll 1
-                    for (int part = 0; part < N_QUARTERS; ++part) {
-                        uint32_t pk[2][8];
-                        layer1_mma_part<NIN>(smB1, part, grp, lane, afr, pk);
-                        if (l1_count > 0) {                               // GEMM #(l1_count-1) is done with this part of A
-                            mbar_wait_warp(&ms.a_free[part], (l1_count - 1) & 1);
-                            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                        }
-#pragma unroll
-                        for (int h = 0; h < 2; ++h)
-                            tmem_st_16x256b_x2(tmem + ((uint32_t)(q * 32 + 16 * h) << 16) + TMEM_A_COL + (uint32_t)((part * N_MMA + grp * 32) >> 1), pk[h]);
-                        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-                        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                        compute_arrive<CG2>(&ms.a_ready[part]);
-                    }
-                    ++l1_count;
-                    return;
-                }
                 if (grp == og) {
                     ms.xs[row] = make_float4(z[0], z[1], z[2], vc0);
                     if (NIN == 5) ms.xw[row] = vc1;
@@ -1090,41 +885,6 @@ mppi_mlp_rollout_kernel(const __grid_constant__ TickArgs a, const __grid_constan
                 MLP_TOC(13);
                 const float4 st = ms.xs[row];
                 const float su1 = NIN == 5 ? ms.xw[row] : 0.f;
-#if MPPI_MLP_L1_EARLY
-                // a part's 32 columns are evaluated into registers BEFORE waiting for the running GEMM to release that part
-                // of A: the linear layer + tanh of part p overlap the wait, only the 4 stores sit behind it
-#pragma unroll 1
-                for (int part = 0; part < N_QUARTERS; ++part) {
-                    uint32_t pk[4][4];
-#pragma unroll
-                    for (int c8 = 0; c8 < 4; ++c8) {
-                        const int col = part * N_MMA + grp * 32 + c8 * 8;
-#pragma unroll
-                        for (int p = 0; p < 4; ++p) {
-                            const float4 wa = ms.w01[col + 2 * p], wb = ms.w01[col + 2 * p + 1];
-                            float pa = fmaf(wa.x, st.x, fmaf(wa.y, st.y, fmaf(wa.z, st.z, wa.w)));
-                            float pb = fmaf(wb.x, st.x, fmaf(wb.y, st.y, fmaf(wb.z, st.z, wb.w)));
-                            if (NIN == 5) {
-                                const float4 wu = *reinterpret_cast<const float4 *>(&ms.w01u[col + 2 * p]);
-                                pa = fmaf(wu.x, st.w, fmaf(wu.y, su1, pa));
-                                pb = fmaf(wu.z, st.w, fmaf(wu.w, su1, pb));
-                            }
-                            pk[c8][p] = tanh_op2(pa, pb);
-                        }
-                    }
-                    if (l1_count > 0) {                                   // GEMM #(l1_count-1) is done with this part of A
-                        mbar_wait_warp(&ms.a_free[part], (l1_count - 1) & 1);
-                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    }
-#pragma unroll
-                    for (int c8 = 0; c8 < 4; ++c8)
-                        tmem_st4(tmem + ((uint32_t)(q * 32) << 16) + TMEM_A_COL + (uint32_t)((part * N_MMA + grp * 32 + c8 * 8) >> 1),
-                                 pk[c8][0], pk[c8][1], pk[c8][2], pk[c8][3]);
-                    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                    compute_arrive<CG2>(&ms.a_ready[part]);
-                }
-#else
 #pragma unroll 1
                 for (int part = 0; part < N_QUARTERS; ++part) {
                     MLP_TIC();
@@ -1160,7 +920,6 @@ mppi_mlp_rollout_kernel(const __grid_constant__ TickArgs a, const __grid_constan
                     compute_arrive<CG2>(&ms.a_ready[part]);
                     MLP_TOC(8 + part);
                 }
-#endif
                 ++l1_count;
             };
             // one accumulator quarter: D -> +b2 -> tanh -> partial contraction with the 512x3 output layer
@@ -1177,20 +936,13 @@ mppi_mlp_rollout_kernel(const __grid_constant__ TickArgs a, const __grid_constan
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                 compute_arrive<CG2>(&ms.d_empty[buf]);
                 MLP_TOC(12);
-#if MPPI_MLP_W3_PARAM
-                const int colu = __shfl_sync(0xffffffffu, col, 0);
-#endif
 #pragma unroll
                 for (int i = 0; i < 32; ++i) {
 #if MPPI_MLP_PROBE & 1
                     const float h = tanh_approx(__uint_as_float(v[i]));
                     r0 += h;
 #else
-#if MPPI_MLP_W3_PARAM
-                    const float4 w = w3p.w[colu + i];
-#else
                     const float4 w = ms.w3[col + i];
-#endif
                     const float h = tanh_approx(__uint_as_float(v[i]) + w.x);
                     r0 = fmaf(w.y, h, r0); r1 = fmaf(w.z, h, r1); r2 = fmaf(w.w, h, r2);
 #endif
@@ -1227,35 +979,27 @@ mppi_mlp_rollout_kernel(const __grid_constant__ TickArgs a, const __grid_constan
             layer1(0);                                               // L1(X, t0)
             float r0, r1, r2;
             float s0 = 0.f, s1 = 0.f, s2 = 0.f;                      // partial sums of the tile whose GEMM ran one slot ago
-            // (KSPLIT: quarters 2 and 3 of a GEMM complete together at its end, so both of their epilogues move behind the
-            //  layer 1 that chases them; the partial sums are still added in quarter order -- results do not change)
-            constexpr int NQ_EARLY = KSPLIT ? 2 : 3;                 // epilogues that run while the same GEMM is still going
             for (int t = t0; t < t1; ++t) {
                 // ---- slot X(t): the tensor core runs GEMM X(t)
                 if (t > t0) {
-#pragma unroll
-                    for (int nq = NQ_EARLY; nq < N_QUARTERS; ++nq) epilogue(nq, s0, s1, s2);    // Y(t-1), last quarter(s)
+                    epilogue(3, s0, s1, s2);                         // Y(t-1), last quarter
                     finish(1, s0, s1, s2);
                     if (grp == 1) prep(t);
                 }
                 if constexpr (L1TC) l1_publish(1);                   // inputs of L1(Y, t): the evaluation before it is long done
                 r0 = r1 = r2 = 0.f;
-#pragma unroll
-                for (int nq = 0; nq < NQ_EARLY; ++nq) epilogue(nq, r0, r1, r2);                 // X(t)
-                if constexpr (L1TC) l1_collect(); else layer1(1);    // L1(Y, t) chases the end of X(t)
+                epilogue(0, r0, r1, r2); epilogue(1, r0, r1, r2); epilogue(2, r0, r1, r2);      // X(t)
+                if constexpr (L1TC) l1_collect(); else layer1(1);    // L1(Y, t) chases X(t)'s last quarter
                 // ---- slot Y(t): the tensor core runs GEMM Y(t)
-#pragma unroll
-                for (int nq = NQ_EARLY; nq < N_QUARTERS; ++nq) epilogue(nq, r0, r1, r2);        // X(t), last quarter(s)
+                epilogue(3, r0, r1, r2);                             // X(t), last quarter
                 finish(0, r0, r1, r2);
                 if (grp == 0 && t + 1 < t1) prep(t + 1);
                 if constexpr (L1TC) { if (t + 1 < t1) l1_publish(0); }
                 s0 = s1 = s2 = 0.f;
-#pragma unroll
-                for (int nq = 0; nq < NQ_EARLY; ++nq) epilogue(nq, s0, s1, s2);                 // Y(t)
-                if (t + 1 < t1) { if constexpr (L1TC) l1_collect(); else layer1(0); }           // L1(X, t+1) chases the end of Y(t)
+                epilogue(0, s0, s1, s2); epilogue(1, s0, s1, s2); epilogue(2, s0, s1, s2);      // Y(t)
+                if (t + 1 < t1) { if constexpr (L1TC) l1_collect(); else layer1(0); }           // L1(X, t+1) chases Y(t)'s last quarter
             }
-#pragma unroll
-            for (int nq = NQ_EARLY; nq < N_QUARTERS; ++nq) epilogue(nq, s0, s1, s2);            // Y(t1-1), last quarter(s)
+            epilogue(3, s0, s1, s2);                                 // Y(t1-1), last quarter
             finish(1, s0, s1, s2);
             if (warp == 2 && pr == n_nat - 1) MLP_PROBE_PRINT("compute warp 0: wait d_full q0-3 | a_free p0-3 | L1 work p0-3 | tmem ld, L1 bar, finish bar, epilogue math", my_tile_steps / 2);
             if (t1 < T) {
@@ -1317,35 +1061,15 @@ mppi_mlp_rollout_kernel(const __grid_constant__ TickArgs a, const __grid_constan
             for (int t = t0; t < t1; ++t) {
                 // (1) owner publishes the state (and, for the 5-input residual, this step's control); every group
                 //     evaluates its 128 columns of tanh(W01 [x; u] + b01)
-                if constexpr (L1MMA) {
-                    if (owner) {
-                        const float xin[5] = {z[0], z[1], z[2], vc0, vc1};
-                        write_a1_row<NIN>(ms.a1[row], xin);
-                    }
-                    named_bar_sync(1, N_COMPUTE);
-                    uint32_t afr[2][NIN == 3 ? 1 : 2][4];
-                    load_a1_frags<NIN>(ms.a1, q, lane, afr);
-#pragma unroll 1
-                    for (int part = 0; part < N_QUARTERS; ++part) {
-                        uint32_t pk[2][8];
-                        layer1_mma_part<NIN>(smB1, part, grp, lane, afr, pk);
-#pragma unroll
-                        for (int h = 0; h < 2; ++h)
-                            tmem_st_16x256b_x2(tmem + ((uint32_t)(q * 32 + 16 * h) << 16) + TMEM_A_COL + (uint32_t)((part * N_MMA + grp * 32) >> 1), pk[h]);
-                        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-                        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                        compute_arrive(&ms.a_ready[part]);
-                    }
-                }
-                if (!L1MMA && owner) {
+                if (owner) {
                     ms.xs[row] = make_float4(z[0], z[1], z[2], vc0);
                     if (NIN == 5) ms.xw[row] = vc1;
                 }
-                if (!L1MMA) named_bar_sync(1, N_COMPUTE);
-                const float4 st = L1MMA ? make_float4(0.f, 0.f, 0.f, 0.f) : ms.xs[row];
-                const float su1 = (NIN == 5 && !L1MMA) ? ms.xw[row] : 0.f;
+                named_bar_sync(1, N_COMPUTE);
+                const float4 st = ms.xs[row];
+                const float su1 = NIN == 5 ? ms.xw[row] : 0.f;
 #pragma unroll 1
-                for (int part = 0; part < (L1MMA ? 0 : N_QUARTERS); ++part) {      // 128-column parts of A, each signalled on its own
+                for (int part = 0; part < N_QUARTERS; ++part) {      // 128-column parts of A, each signalled on its own
 #pragma unroll 2
                     for (int c8 = 0; c8 < 4; ++c8) {                 // this group's 32 columns of the part, 8 at a time
                         const int col = part * N_MMA + grp * 32 + c8 * 8;
@@ -1432,11 +1156,7 @@ mppi_mlp_rollout_kernel(const __grid_constant__ TickArgs a, const __grid_constan
                     compute_arrive(&ms.d_empty[buf]);                // values are in registers: the buffer may be overwritten
 #pragma unroll
                     for (int i = 0; i < 32; ++i) {
-#if MPPI_MLP_W3_PARAM
-                        const float4 w = w3p.w[__shfl_sync(0xffffffffu, col, 0) + i];
-#else
                         const float4 w = ms.w3[col + i];
-#endif
                         const float h = tanh_approx(__uint_as_float(v[i]) + w.x);
                         r0 = fmaf(w.y, h, r0); r1 = fmaf(w.z, h, r1); r2 = fmaf(w.w, h, r2);
                     }
@@ -1501,7 +1221,6 @@ struct MlpState {
     int n_in = 3, n_gemm = 1;
     CUtensorMap w2_map;
     CUtensorMap w2_map_half;              // 64-row boxes: each CTA's half of a W2 box under pair MMAs (MPPI_MLP_CG2)
-    MlpW3 h_w3;                           // host copy of the output-layer records (kernel-parameter variant)
     bool ready = false;
 };
 
@@ -1522,7 +1241,7 @@ MlpState *mlp_create(int K, int T) {
         cudaMalloc(&m->d_w3, sizeof(float4) * HID) != cudaSuccess ||
         cudaMalloc(&m->d_w01u, sizeof(float2) * HID) != cudaSuccess ||
         cudaMalloc(&m->d_b3, sizeof(float) * 4) != cudaSuccess ||
-        cudaMalloc(&m->d_b1, MPPI_MLP_L1_TC ? (size_t)B1TC_BYTES : sizeof(__half) * HID * L1_KS_MAX) != cudaSuccess) { mlp_destroy(m); return nullptr; }
+        cudaMalloc(&m->d_b1, (size_t)B1TC_BYTES) != cudaSuccess) { mlp_destroy(m); return nullptr; }
     if (cudaFuncSetAttribute(mppi_mlp_rollout_kernel<3, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MLP_DYN_SMEM) != cudaSuccess ||
         cudaFuncSetAttribute(mppi_mlp_rollout_kernel<5, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MLP_DYN_SMEM) != cudaSuccess ||
         cudaFuncSetAttribute(mppi_mlp_rollout_kernel<3, true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MLP_DYN_SMEM) != cudaSuccess ||
@@ -1564,7 +1283,7 @@ cudaError_t mlp_set_weights(MlpState *m, int n_in, int n_hidden, const float *co
     }
     std::vector<float4> w01(HID), w3(HID);
     std::vector<float2> w01u(HID, make_float2(0.f, 0.f));
-    std::vector<__half> b1(MPPI_MLP_L1_TC ? (size_t)B1TC_BYTES / 2 : (size_t)HID * L1_KS_MAX, __float2half_rn(0.f));
+    std::vector<__half> b1((size_t)B1TC_BYTES / 2, __float2half_rn(0.f));
     for (int j = 0; j < HID; ++j) {
         double s[5] = {0, 0, 0, 0, 0}, bb = b[1][j];
         for (int i = 0; i < HID; ++i) {
@@ -1574,11 +1293,10 @@ cudaError_t mlp_set_weights(MlpState *m, int n_in, int n_hidden, const float *co
         }
         w01[j] = make_float4((float)s[0], (float)s[1], (float)s[2], (float)bb);
         w01u[j] = make_float2((float)s[3], (float)s[4]);
-        {   // the same folded row as the layer-1 MMA's B operand: per input (w_hi, w_lo, w_hi) against the input row's
-            // (x_hi, x_hi, x_lo), then (b_hi, b_lo) against (1, 1); stored at the tile position of unit j (see layer1_mma_part)
+        {   // the same folded row as the tcgen05 layer 1's B operand: per input (w_hi, w_lo, w_hi) against the input row's
+            // (x_hi, x_hi, x_lo), then (b_hi, b_lo) against (1, 1)
             const int KS = n_in == 3 ? 16 : 32;
-            const int part = j / N_MMA, g = (j % N_MMA) / 32, v = j % 32;
-            const int cb = v / 16, m4 = (v % 16) / 4, e = (v % 4) / 2, dl = v % 2;
+            const int part = j / N_MMA;
             __half slot[L1_KS_MAX];
             for (int i = 0; i < L1_KS_MAX; ++i) slot[i] = __float2half_rn(0.f);
             auto split = [](double w, __half &hi, __half &lo) {
@@ -1593,17 +1311,11 @@ cudaError_t mlp_set_weights(MlpState *m, int n_in, int n_hidden, const float *co
             }
             if (!(std::fabs(bb) <= 65504.0)) return cudaErrorInvalidValue;
             split(bb, slot[3 * n_in], slot[3 * n_in + 1]);
-#if MPPI_MLP_L1_TC
-            // tcgen05 layer 1: plain unit order, K-major 32B-swizzled rows of 16 halves (unit r of a part at (r / 8) * 256 B + (r % 8) * 32 B,
+            // plain unit order, K-major 32B-swizzled rows of 16 halves (unit r of a part at (r / 8) * 256 B + (r % 8) * 32 B,
             // 16-byte chunk c at position c ^ ((r / 4) % 2)), parts 4 KB apart, the second K block (halves 16..31) 16 KB behind the first
-            (void)g; (void)v; (void)cb; (void)m4; (void)e; (void)dl;
             const int r = j % N_MMA;
             __half *row = &b1[((size_t)part * N_MMA * 32 + (size_t)(r >> 3) * 256 + (size_t)(r & 7) * 32) / 2];
             for (int i = 0; i < KS; ++i) row[(size_t)(i >> 4) * (B1TC_KB_BYTES / 2) + (((((i >> 3) & 1) ^ ((r >> 2) & 1))) << 3) + (i & 7)] = slot[i];
-#else
-            __half *row = &b1[(size_t)(part * N_MMA + g * 32 + 8 * (2 * cb + e) + 2 * m4 + dl) * KS];
-            for (int i = 0; i < KS; ++i) row[i] = slot[i];
-#endif
         }
         const double o0 = out_scale ? out_scale[0] : 1.0, o1 = out_scale ? out_scale[1] : 1.0, o2 = out_scale ? out_scale[2] : 1.0;
         w3[j] = make_float4(b[l_last][j], (float)(W[l_out][0 * HID + j] * o0), (float)(W[l_out][1 * HID + j] * o1), (float)(W[l_out][2 * HID + j] * o2));
@@ -1624,7 +1336,6 @@ cudaError_t mlp_set_weights(MlpState *m, int n_in, int n_hidden, const float *co
     cudaError_t e;
     if ((e = cudaMemcpyAsync(m->d_w01, w01.data(), sizeof(float4) * HID, cudaMemcpyHostToDevice, st)) != cudaSuccess) return e;
     if ((e = cudaMemcpyAsync(m->d_w3, w3.data(), sizeof(float4) * HID, cudaMemcpyHostToDevice, st)) != cudaSuccess) return e;
-    for (int j = 0; j < HID; ++j) m->h_w3.w[j] = w3[j];
     if ((e = cudaMemcpyAsync(m->d_w01u, w01u.data(), sizeof(float2) * HID, cudaMemcpyHostToDevice, st)) != cudaSuccess) return e;
     if ((e = cudaMemcpyAsync(m->d_b3, b3, sizeof(b3), cudaMemcpyHostToDevice, st)) != cudaSuccess) return e;
     if ((e = cudaMemcpyAsync(m->d_b1, b1.data(), sizeof(__half) * b1.size(), cudaMemcpyHostToDevice, st)) != cudaSuccess) return e;
@@ -1704,12 +1415,7 @@ int mlp_rollout_costs(MlpState *m, const TickArgs &args, bool sum, const float *
                           (long long)n_quads * a.T / n_clusters >= a.T + 2) ? 1 : 0;
     const unsigned int epoch = ++m->epoch;
     unsigned int *fault = m->d_hand_flag + (size_t)(m->n_sm / 2 + 1) * 2;
-#if MPPI_MLP_W3_PARAM
-#define MPPI_MLP_W3_ARG , m->h_w3
-#else
-#define MPPI_MLP_W3_ARG
-#endif
-#define MPPI_MLP_LAUNCH(N, P, G) mppi_mlp_rollout_kernel<N, P, G><<<grid, MLP_THREADS, MLP_DYN_SMEM, st>>>(a, mlp_use_cg2(N, P, G) ? m->w2_map_half : m->w2_map, m->d_w01, m->d_w01u, m->d_w3, m->d_b3, m->d_bh, d_S, n_tiles, m->d_hand, m->d_hand_flag, fault, epoch, balanced, m->d_b1 MPPI_MLP_W3_ARG)
+#define MPPI_MLP_LAUNCH(N, P, G) mppi_mlp_rollout_kernel<N, P, G><<<grid, MLP_THREADS, MLP_DYN_SMEM, st>>>(a, mlp_use_cg2(N, P, G) ? m->w2_map_half : m->w2_map, m->d_w01, m->d_w01u, m->d_w3, m->d_b3, m->d_bh, d_S, n_tiles, m->d_hand, m->d_hand_flag, fault, epoch, balanced, m->d_b1)
     if (m->n_gemm == 2) { if (m->n_in == 5) MPPI_MLP_LAUNCH(5, false, 2); else MPPI_MLP_LAUNCH(3, false, 2); }
     else if (m->n_in == 5) { if (pp) MPPI_MLP_LAUNCH(5, true, 1); else MPPI_MLP_LAUNCH(5, false, 1); }
     else { if (pp) MPPI_MLP_LAUNCH(3, true, 1); else MPPI_MLP_LAUNCH(3, false, 1); }

@@ -318,13 +318,14 @@ int mppi_create(const mppi_config_t *cfg, mppi_handle_t *out) {
     CKC(gmalloc(h, &h->d_M, sizeof(float) * T * T));
     CKC(gmalloc(h, &h->d_S, sizeof(float) * (size_t)R * K));
     CKC(gmalloc(h, &h->d_NC, sizeof(int) * (size_t)K));
-    CKC(gmalloc(h, &h->d_part, sizeof(float) * (size_t)R * gx * MPPI_NF(T)));
+    const int gmax = (gx + MPPI_MERGE_GROUP_CTAS - 1) / MPPI_MERGE_GROUP_CTAS;      // two-level merge: group partials behind the block partials
+    CKC(gmalloc(h, &h->d_part, sizeof(float) * (size_t)R * (gx + gmax) * MPPI_NF(T)));
     CKC(gmalloc(h, &h->d_out, sizeof(float) * (size_t)R * MPPI_OUT_STRIDE));
     CKC(cudaMemset(h->d_out, 0, sizeof(float) * (size_t)R * MPPI_OUT_STRIDE));
     CKC(gmalloc(h, &h->d_idx, sizeof(int) * R));
     CKC(cudaMemset(h->d_idx, 0, sizeof(int) * R));
-    CKC(gmalloc(h, &h->d_ticket, sizeof(unsigned) * R));
-    CKC(cudaMemset(h->d_ticket, 0, sizeof(unsigned) * R));
+    CKC(gmalloc(h, &h->d_ticket, sizeof(unsigned) * (size_t)R * (1 + gmax)));
+    CKC(cudaMemset(h->d_ticket, 0, sizeof(unsigned) * (size_t)R * (1 + gmax)));
     CKC(cudaHostAlloc(&h->h_out, sizeof(float) * MPPI_OUT_STRIDE, cudaHostAllocMapped));
     std::memset(h->h_out, 0, sizeof(float) * MPPI_OUT_STRIDE);
     CKC(cudaHostGetDevicePointer(&h->h_out_dev, h->h_out, 0));
@@ -360,6 +361,7 @@ int mppi_create(const mppi_config_t *cfg, mppi_handle_t *out) {
     a.soft_w = (float)c.soft_obs_weight; a.soft_sd = (float)c.soft_obs_safety;
     refresh_obstacle_args(h, nullptr, 0);
     a.U = h->d_U; a.idx = h->d_idx; a.M = h->d_M; a.part = h->d_part; a.ticket = h->d_ticket;
+    a.part2 = h->d_part + (size_t)R * gx * MPPI_NF(T); a.ticket2 = h->d_ticket + R; a.merge_gmax = gmax;
     a.out = h->d_out; a.out_host = h->h_out_dev;
     if (c.model == MPPI_MODEL_DIFFDRIVE_MLP) {
         h->mlp = mlp_create(K, T);

@@ -40,6 +40,7 @@
 #define MPPI_OUT_UPRE (MPPI_OUT_HDR + 4 * MPPI_MAX_T)
 #define MPPI_OUT_UOLD (MPPI_OUT_HDR + 6 * MPPI_MAX_T)
 #define MPPI_NF(T) (4 + 2 * (T))
+#define MPPI_MERGE_GROUP_CTAS 16         // two-level merge of the block partials: consecutive CTAs per group
 #define MPPI_NF_MAX MPPI_NF(MPPI_MAX_T)
 // exchange buffer of one rank (fused multi-GPU exchange): 2 parities x [MPPI_MAX_PEERS triples of NF_MAX 64-bit words];
 // a word is (sequence number << 32 | float bits): the flag travels WITH the datum in one 8-byte store (the "LL" protocol),
@@ -99,6 +100,9 @@ struct TickArgs {
     float *S_user;                    // [K] combined cost smooth + 1e10*n for the caller (strict path), or null
     float *part;                      // [R][B][NF]
     unsigned *ticket;                 // [R]
+    float *part2;                     // [R][merge_gmax][NF]: partials of the merge groups (two-level merge)
+    unsigned *ticket2;                // [R][merge_gmax]
+    int merge_gmax;                   // groups of MPPI_MERGE_GROUP_CTAS consecutive CTAs a robot's grid row may have
     float *out;                       // [R][MPPI_OUT_STRIDE]
     float *out_host;                  // mapped pinned mirror of out (robot 0) or null
     float *u0_out;                    // batched: [R][2] or null

@@ -41,7 +41,7 @@ def test_tick_is_bit_reproducible_and_stays_inside_its_buffers(K, T, mode):
 def test_learned_dynamics_schedules_are_bit_reproducible():
     """Balanced ping-pong schedule (state records handed between clusters through global flags): 10 launches, same bits."""
     g = Golden("diffdrive_pe0.05")
-    for K, T, n_in, n_hidden in ((50000, 12, 3, 2), (30000, 11, 5, 3)):
+    for K, T, n_in, n_hidden in ((50000, 12, 3, 2), (50000, 11, 5, 2), (30000, 11, 5, 3)):       # pair MMAs, tcgen05 layer 1, two GEMMs
         mlp = orc.make_mlp(seed=2, out_scale=0.05, n_in=n_in, scalers=(n_in == 5), scaler_gain=1.0, n_hidden=n_hidden)
         sp = orc.diffdrive_spec(K=K, T=T, param_exploration=0.05, cost_mode="sum", waypoint_mode="frozen", model="diffdrive_mlp", mlp=mlp)
         sp.temperature = 2.0

@@ -115,13 +115,14 @@ def test_config3_fleet_4096_robots_random_subset():
     b.engine.close()
 
 
-@pytest.mark.parametrize("K,T", [(20000, 11), (19073, 12), (40001, 13)])
-def test_mlp_ping_pong_schedule_ragged_tile_counts(K, T):
+@pytest.mark.parametrize("K,T,n_in", [(20000, 11, 3), (19073, 12, 3), (40001, 13, 3), (19073, 12, 5), (40001, 13, 5)])
+def test_mlp_ping_pong_schedule_ragged_tile_counts(K, T, n_in):
     """More tiles than CTAs puts the learned-dynamics kernel in its two-tiles-per-CTA (ping-pong) schedule; these sizes
     leave some CTAs with an odd tile count (padded with an empty tile), a ragged last tile and an odd horizon.
-    Injected and Philox noise must give the same costs, and a subset (first, last, random tiles) must match the FP64 oracle."""
+    Injected and Philox noise must give the same costs, and a subset (first, last, random tiles) must match the FP64 oracle.
+    Three inputs: pair MMAs (cta_group::2); five inputs: layer 1 on the tcgen05 tensor core (split-fp16 operands)."""
     g = Golden("diffdrive_pe0.05")
-    mlp = orc.make_mlp(seed=2, out_scale=0.02)
+    mlp = orc.make_mlp(seed=2, out_scale=0.02, n_in=n_in)
     sp = orc.diffdrive_spec(K=K, T=T, param_exploration=0.05, cost_mode="sum", waypoint_mode="frozen",
                             model="diffdrive_mlp", mlp=mlp)
     sp.temperature = 2.0

@@ -51,6 +51,8 @@ struct mppi_handle_s {
     int n_sm = 148, occ = 1, nx = 3;
     int grid_x = 1, grid_x_stash = 1;    // CTAs per robot: regenerate-noise kernels / stash kernels
     bool stash = false;                  // Philox ticks keep the chunk's noise in shared memory
+    bool tpar = false;                   // ... and small sample counts run the horizon time-parallel (rollout_tpar), on grid_x_tpar CTAs
+    int grid_x_tpar = 1;
     bool sum = false, strict = false;
     bool have_path = false;
     std::vector<double> path_h;          // host copy for the strict-mode step 1 (literal FP64)
@@ -312,6 +314,27 @@ int mppi_create(const mppi_config_t *cfg, mppi_handle_t *out) {
     int gxs = (h->n_sm * std::max(1, occ_stash) + R - 1) / R;
     h->grid_x_stash = std::max(1, std::min(gxs, chunks));
     gx = std::max(h->grid_x, h->grid_x_stash);
+    // Time-parallel rollout (mppi_device.cuh, rollout_tpar): when one robot's samples cannot fill the GPU anyway -- every CTA would own
+    // <= MPPI_TPAR_SLOTS of them at two CTAs per SM -- the tick is bound by the latency of one thread's walk through the horizon, and
+    // splitting the horizon into noise / recurrence / cost phases over all threads of the CTA cuts that latency (race-car K = 16 384,
+    // H = 50: 73 -> 4x us per tick).  Dynamic-window kernels only: with the static 20-entry window the stage cost is too cheap next to
+    // the recurrence for the split to pay (diff-drive K = 16 384, H = 30: 22.3 -> 24.6 us, measured).  MPPI_TPAR=0 / 1 overrides.
+    {
+        const int occ_tpar = (h->sum && c.cost_kind == MPPI_COSTKIND_PATH && c.window != 20 && c.model != MPPI_MODEL_DIFFDRIVE_MLP)
+                                 ? mppi_tick_occupancy(tick_model, c.collision, c.cost_kind, true, false, c.window, T, 2) : 0;
+        const int gt = std::max(1, std::min(h->n_sm * std::max(1, occ_tpar), (K + 31) / 32));
+        const bool fits = occ_tpar >= 1 && (K + gt - 1) / gt <= MPPI_TPAR_SLOTS;
+        bool want = R == 1;
+        if (const char *env = std::getenv("MPPI_TPAR")) want = std::atoi(env) != 0;
+        if (std::getenv("MPPI_VERBOSE"))
+            std::fprintf(stderr, "mppi_create: time-parallel rollout: occ %d grid %d fits %d want %d (stash %d sum %d window %d K %d T %d)\n",
+                         occ_tpar, gt, (int)fits, (int)want, (int)h->stash, (int)h->sum, c.window, K, T);
+        if (want && fits) {
+            h->tpar = true;
+            h->grid_x_tpar = gt;
+            gx = std::max(gx, gt);
+        }
+    }
 
     CKC(gmalloc(h, &h->d_U, sizeof(float) * R * T * 2));
     CKC(cudaMemset(h->d_U, 0, sizeof(float) * R * T * 2));
@@ -673,8 +696,8 @@ static int strict_costs(mppi_handle_t h, const double *x0, const float *d_eps, f
 }
 
 static int launch_update(mppi_handle_t h, const TickArgs &a, bool inj) {
-    const bool stash = h->stash && !inj && !(a.flags & F_FROM_S);
-    dim3 grid(stash ? h->grid_x_stash : h->grid_x, h->cfg.n_robots);
+    const int stash = (!inj && !(a.flags & F_FROM_S)) ? (h->tpar ? 2 : h->stash ? 1 : 0) : 0;
+    dim3 grid(stash == 2 ? h->grid_x_tpar : stash ? h->grid_x_stash : h->grid_x, h->cfg.n_robots);
     const int model = (h->cfg.model == MPPI_MODEL_DIFFDRIVE_MLP) ? MPPI_MODEL_DIFFDRIVE : h->cfg.model;
     if (h->world > 1 && h->p2p && (a.flags & F_UPDATE)) {
         TickArgs b = a;                      // exchange fused into the tick kernel: ONE launch, no NCCL call
@@ -988,7 +1011,7 @@ int mppi_step_batched(mppi_handle_t h, const float *d_x0, uint64_t seed, uint64_
     a.x0_dev = h->d_x0; a.eps = nullptr; a.S = nullptr; a.flags = F_UPDATE; a.u0_out = d_u0_out;
     a.out_host = nullptr;
     dim3 grid(h->stash ? h->grid_x_stash : h->grid_x, h->cfg.n_robots);
-    CK(h, mppi_launch_tick(a, h->cfg.model, h->cfg.collision, h->cfg.cost_kind, h->sum, false, h->stash, grid, h->stream));
+    CK(h, mppi_launch_tick(a, h->cfg.model, h->cfg.collision, h->cfg.cost_kind, h->sum, false, h->stash ? 1 : 0, grid, h->stream));
     h->tm.launches++;
     return MPPI_OK;
 }
@@ -1060,7 +1083,7 @@ int mppi_set_trace(mppi_handle_t h, int32_t on) {
     CK(h, cudaSetDevice(h->cfg.device));
     CK(h, cudaStreamSynchronize(h->stream));
     if (on && !h->d_trace) {
-        h->trace_n = 2 * (std::max(h->grid_x, h->grid_x_stash) + 1);
+        h->trace_n = 2 * (std::max(std::max(h->grid_x, h->grid_x_stash), h->grid_x_tpar) + 1);
         CK(h, gmalloc(h, &h->d_trace, sizeof(unsigned long long) * h->trace_n));
         CK(h, cudaMemset(h->d_trace, 0, sizeof(unsigned long long) * h->trace_n));
     }
@@ -1075,7 +1098,7 @@ int mppi_get_trace(mppi_handle_t h, uint64_t *out, int32_t capacity, int32_t *n_
     const int n = std::min(capacity, h->trace_n);
     CK(h, cudaMemcpyAsync(out, h->d_trace, sizeof(uint64_t) * n, cudaMemcpyDeviceToHost, h->stream));
     CK(h, cudaStreamSynchronize(h->stream));
-    *n_ctas_out = h->stash ? h->grid_x_stash : h->grid_x;
+    *n_ctas_out = h->tpar ? h->grid_x_tpar : h->stash ? h->grid_x_stash : h->grid_x;
     return MPPI_OK;
 }
 

@@ -265,6 +265,9 @@ __device__ __forceinline__ float2 f2_fma(float2 a, float2 b, float2 c) {
 #ifndef MPPI_WP_CHUNK_ILP
 #define MPPI_WP_CHUNK_ILP 1
 #endif
+#ifndef MPPI_WP_FULL
+#define MPPI_WP_FULL 0
+#endif
 #ifndef MPPI_WIN20_EXPANDED
 #define MPPI_WIN20_EXPANDED 1   // static window distances as ec_j - 2 p'.w'_j: 2 packed FMAs per waypoint pair instead of 4 ops (0: direct form)
 #endif
@@ -468,6 +471,30 @@ __device__ __forceinline__ int nearest_wp(const TickSmem &sm, float x, float y) 
     int bj = 0;
     const int nch = sm.n_win16;
     int c = 0;
+#if MPPI_WP_FULL
+    // A/B variant: every chunk evaluated, no pruning, four independent chunk chains per trip (block-uniform trip count)
+    for (; c + 3 < nch; c += 4) {
+        float m0, k0, m1, k1, m2, k2, m3, k3;
+        chunk_argmin<16>(nwx4 + 4 * c, nwy4 + 4 * c, x, y, m0, k0);
+        chunk_argmin<16>(nwx4 + 4 * c + 4, nwy4 + 4 * c + 4, x, y, m1, k1);
+        chunk_argmin<16>(nwx4 + 4 * c + 8, nwy4 + 4 * c + 8, x, y, m2, k2);
+        chunk_argmin<16>(nwx4 + 4 * c + 12, nwy4 + 4 * c + 12, x, y, m3, k3);
+        const bool s01 = m1 < m0, s23 = m3 < m2;
+        const float ma = s01 ? m1 : m0, mb = s23 ? m3 : m2;
+        const float ka = s01 ? k1 + 16.f : k0, kb = s23 ? k3 + 48.f : k2 + 32.f;
+        const bool sb = mb < ma;
+        const float m = sb ? mb : ma;
+        const int j = 16 * c + __float2int_rn(sb ? kb : ka);
+        if (m < bm) { bm = m; bj = j; }
+    }
+    for (; c < nch; ++c) {
+        float m, key;
+        chunk_argmin<16>(nwx4 + 4 * c, nwy4 + 4 * c, x, y, m, key);
+        if (m < bm) { bm = m; bj = 16 * c + __float2int_rn(key); }
+    }
+    (void)sbm;
+    return bj;
+#endif
     // |z - p| >= |z - centre| - r for every point p of a chunk: if that exceeds the best distance (with a 1e-4 relative
     // margin, three orders above FP32 rounding) no point of the chunk can be the minimum or tie with it
     auto far = [&](int ch) {
@@ -758,5 +785,105 @@ __device__ __forceinline__ void rollout_samples(const TickArgs &a, const TickSme
         }
         smooth[s] = acc[s];
         ncoll[s] = nc[s];
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Time-parallel rollout for SMALL sample counts (tick kernel instantiations with STASH == 2).
+// With fewer samples than the GPU has lanes, one thread walking one sample through the horizon is bound by the
+// latency of its own instruction chain (race-car K = 16 384, H = 50: 1.4 us per step whatever K is).  But only the
+// dynamics are a recurrence over t: the noise of (k, t) is a pure function of its Philox counter, and the stage cost
+// of step t (waypoint search, tracking terms, collision test -- 2/3 of a step's instructions) only READS state t.
+// So a CTA that owns n <= MPPI_TPAR_SLOTS samples runs the horizon in four block-wide phases:
+//   N  all threads: Philox + Box-Muller of every (sample, timestep pair) into the noise stash (rows of MPPI_TPAR_SLOTS
+//      columns here, which K2's column sums read with that stride);
+//   D  one thread per sample: clamp + Euler recurrence only, state of every step into `zbuf[t][slot]`;
+//   C  all threads: stage (and terminal) cost + collision test of every (sample, t), written over the state it read;
+//   S  one thread per sample: the T costs added in horizon order -- the same sum, in the same order, as the serial loop.
+// Two such CTAs are resident per SM (T * 64 * 24 B of shared memory each), so one CTA's serial phase D overlaps the other's
+// wide phases.  Same device functions as rollout_samples, so a sample's result does not depend on which rollout ran it.
+// All MPPI_BLOCK threads must call; threads tid < n return their sample, the others (inf, INT_MAX).
+// ------------------------------------------------------------------------------------------
+#define MPPI_TPAR_SLOTS 64
+template <int MODEL, int COLL, int WIN>
+__device__ __forceinline__ void rollout_tpar(const TickArgs &a, const TickSmem &sm, const int k_begin, const int n, const uint32_t robot,
+                                             float2 *stash, float4 *zbuf, float &smooth, int &ncoll, const uint32_t tick_add) {
+    const int T = a.T, tid = threadIdx.x;
+    const uint32_t kg0 = (uint32_t)(a.k_offset + k_begin);
+    MPPI_DCHECK(n >= 1 && n <= MPPI_TPAR_SLOTS && MPPI_TPAR_SLOTS <= MPPI_BLOCK);
+    // ---- N: noise.  Item i = (pair p, slot): consecutive lanes take consecutive slots of one pair.
+    {
+        const int npairs = (T + 1) >> 1, items = n * npairs;
+        for (int i = tid; i < items; i += MPPI_BLOCK) {
+            const int p = i / n, slot = i - p * n;
+            float e[4];
+            philox_eps_pair(a, kg0 + (uint32_t)slot, (uint32_t)p, robot, e, tick_add);
+            stash[(2 * p) * MPPI_TPAR_SLOTS + slot] = make_float2(e[0], e[1]);
+            if (2 * p + 1 < T) stash[(2 * p + 1) * MPPI_TPAR_SLOTS + slot] = make_float2(e[2], e[3]);
+        }
+        // chunk slots without a sample carry weight 0 in the column sums: their noise must be finite
+        const int idle = MPPI_TPAR_SLOTS - n;
+        for (int i = tid; i < idle * T; i += MPPI_BLOCK) {
+            const int t = i / idle, slot = n + (i - t * idle);
+            stash[t * MPPI_TPAR_SLOTS + slot] = make_float2(0.f, 0.f);
+        }
+    }
+    __syncthreads();
+    // ---- D: the recurrence (A4-A7)
+    if (tid < n) {
+        const bool exploit = (int)(kg0 + (uint32_t)tid) < a.n_exploit;
+        float z[4] = {sm.x0[0], sm.x0[1], sm.x0[2], sm.x0[3]}, cs, sn;
+        sincos_cw(z[2], sn, cs);
+        for (int t = 0; t < T; ++t) {
+            const float2 e = stash[t * MPPI_TPAR_SLOTS + tid], u = sm.U[t];
+            const float v0 = clampf(exploit ? __fadd_rn(u.x, e.x) : e.x, a.umax0);
+            const float v1 = clampf(exploit ? __fadd_rn(u.y, e.y) : e.y, a.umax1);
+            dyn_step<MODEL>(a, z, v0, v1, cs, sn);
+            sincos_cw(z[2], sn, cs);
+            zbuf[t * MPPI_TPAR_SLOTS + tid] = make_float4(z[0], z[1], z[2], z[3]);
+        }
+    }
+    __syncthreads();
+    // ---- C: costs of every (t, slot); the record (stage cost + control term, terminal cost, collided) replaces the state
+    {
+        const int items = n * T;
+        for (int i = tid; i < items; i += MPPI_BLOCK) {
+            const int t = i / n, slot = i - t * n;
+            const float4 z4 = zbuf[t * MPPI_TPAR_SLOTS + slot];
+            const float z[4] = {z4.x, z4.y, z4.z, z4.w};
+            const bool exploit = (int)(kg0 + (uint32_t)slot) < a.n_exploit;
+            const float2 e = stash[t * MPPI_TPAR_SLOTS + slot], u = sm.U[t];
+            const float v0 = clampf(exploit ? __fadd_rn(u.x, e.x) : e.x, a.umax0);
+            const float v1 = clampf(exploit ? __fadd_rn(u.y, e.y) : e.y, a.umax1);
+            float4 ref = make_float4(0.f, 0.f, 0.f, 0.f);
+            float yaw_eff = 0.f;
+            const float c = eval_state_cost<MODEL, WIN>(a, sm, z, v0, v1, t, a.sw, ref, yaw_eff);
+            const float2 q = sm.Q[t];
+            const float cc = c + (q.x * v0 + q.y * v1);
+            bool hit = false;
+            if constexpr (COLL != MPPI_COLLISION_NONE) {
+                float cs, sn;
+                sincos_cw(z[2], sn, cs);
+                hit = collided<MODEL, COLL>(a, z[0], z[1], cs, sn);
+            }
+            const float term = (t == T - 1) ? eval_terminal_cost<MODEL, WIN>(a, z, ref, yaw_eff) : 0.f;
+            zbuf[t * MPPI_TPAR_SLOTS + slot] = make_float4(cc, term, hit ? 1.f : 0.f, 0.f);
+        }
+    }
+    __syncthreads();
+    // ---- S: horizon-order sum (A11), terminal cost and the terminal collision test of the same state (A9, A10)
+    smooth = CUDART_INF_F; ncoll = INT_MAX;
+    if (tid < n) {
+        float acc = 0.f;
+        int nc = 0;
+        float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int t = 0; t < T; ++t) {
+            r = zbuf[t * MPPI_TPAR_SLOTS + tid];
+            acc += r.x;
+            nc += (r.z != 0.f) ? 1 : 0;
+        }
+        acc += r.y;
+        nc += (r.z != 0.f) ? 1 : 0;
+        smooth = acc; ncoll = nc;
     }
 }

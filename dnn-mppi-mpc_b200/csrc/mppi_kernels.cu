@@ -289,7 +289,7 @@ struct RunSmem {
 //                  regenerate-the-noise path (injected noise, K2 alone, horizons too long to stash).
 extern __shared__ __align__(16) unsigned char mppi_dyn_smem[];
 
-template <int MODEL, int COLL, bool SUM, bool INJ, int WIN, bool STASH>
+template <int MODEL, int COLL, bool SUM, bool INJ, int WIN, int STASH>      // STASH: 0 regenerate, 1 noise stash, 2 stash + time-parallel rollout
 __device__ __forceinline__ void tick_body(const TickArgs &a, const uint32_t tick_add) {
     __shared__ TickSmem sm;
     __shared__ RunSmem run;
@@ -340,7 +340,7 @@ __device__ __forceinline__ void tick_body(const TickArgs &a, const uint32_t tick
         int nw = n_path - s_new; nw = nw < a.window ? nw : a.window;
         MPPI_DCHECK(WIN < 0 || (s_new >= 0 && s_new < n_path && nw >= 1));
         // static-window kernels read exactly 20 entries, dynamic ones whole chunks of 16
-        const int fill = (WIN < 0) ? 0 : (WIN == 20) ? 20 : ((nw + 15) & ~15);
+        const int fill = (WIN < 0) ? 0 : (WIN == 20) ? 20 : MPPI_WP_FULL ? ((nw + 63) & ~63) : ((nw + 15) & ~15);
         for (int j = tid; j < fill; j += MPPI_BLOCK) {
             if (j < nw) {
                 const float4 p = rpath[s_new + j];
@@ -375,7 +375,10 @@ __device__ __forceinline__ void tick_body(const TickArgs &a, const uint32_t tick
     const int k_end = (a.flags & F_IDX_ONLY) ? k_begin : (int)((long long)K * (b + 1) / B);
     MPPI_DCHECK(k_begin >= 0 && k_end <= K && (!STASH || (size_t)T * MPPI_CHUNK * sizeof(float2) <= 232448));
     float *Srow = a.S ? a.S + (size_t)robot * K : nullptr;
-    for (int base = k_begin; base < k_end; base += MPPI_CHUNK) {
+    // (time-parallel rollout: chunks of MPPI_TPAR_SLOTS samples on chunk slots 0 .. MPPI_TPAR_SLOTS - 1, the other slots idle)
+    static_assert(STASH != 2 || (SPT == 1 && SUM && !INJ), "time-parallel rollout: one sample per thread, sum mode, Philox noise");
+    constexpr int CHUNK_STRIDE = STASH == 2 ? MPPI_TPAR_SLOTS : MPPI_CHUNK;
+    for (int base = k_begin; base < k_end; base += CHUNK_STRIDE) {
         int k[SPT], ksafe[SPT], ncoll[SPT];
         bool active[SPT], exploit[SPT];
         uint32_t kg[SPT];
@@ -383,13 +386,19 @@ __device__ __forceinline__ void tick_body(const TickArgs &a, const uint32_t tick
 #pragma unroll
         for (int s = 0; s < SPT; ++s) {
             k[s] = base + tid + s * MPPI_BLOCK;
-            active[s] = k[s] < k_end;
+            active[s] = k[s] < k_end && (STASH != 2 || tid < MPPI_TPAR_SLOTS);
             ksafe[s] = active[s] ? k[s] : k_begin;             // an idle slot of the tail chunk replays a valid sample (weight 0)
             kg[s] = (uint32_t)(a.k_offset + ksafe[s]);
             exploit[s] = (int)kg[s] < a.n_exploit;
             smooth[s] = CUDART_INF_F; ncoll[s] = INT_MAX;
         }
-        if (active[0]) {                                        // slots ascend with s: no active sample without the first
+        if constexpr (STASH == 2) {
+            MPPI_DCHECK(!(a.flags & F_FROM_S) && (size_t)T * MPPI_TPAR_SLOTS * (sizeof(float2) + sizeof(float4)) <= 232448);
+            float4 *zbuf = reinterpret_cast<float4 *>(mppi_dyn_smem + sizeof(float2) * (size_t)T * MPPI_TPAR_SLOTS);
+            rollout_tpar<MODEL, COLL, WIN>(a, sm, base, min(k_end - base, MPPI_TPAR_SLOTS), (uint32_t)robot, stash, zbuf,
+                                           smooth[0], ncoll[0], tick_add);
+            if (active[0] && (a.flags & F_WRITE_S)) Srow[k[0]] = smooth[0] + MPPI_PENALTY * (float)ncoll[0];
+        } else if (active[0]) {                                 // slots ascend with s: no active sample without the first
             if (a.flags & F_FROM_S) {
 #pragma unroll
                 for (int s = 0; s < SPT; ++s)
@@ -405,7 +414,7 @@ __device__ __forceinline__ void tick_body(const TickArgs &a, const uint32_t tick
             }
         }
         if (!(a.flags & F_UPDATE)) continue;
-        if (STASH && !active[0]) {                  // tail chunk: a thread that rolled nothing out must not leave garbage (0 * NaN)
+        if (STASH == 1 && !active[0]) {             // tail chunk: a thread that rolled nothing out must not leave garbage (0 * NaN)
             for (int t = 0; t < T; ++t)
 #pragma unroll
                 for (int s = 0; s < SPT; ++s) stash[t * MPPI_CHUNK + s * MPPI_BLOCK + tid] = make_float2(0.f, 0.f);
@@ -440,14 +449,15 @@ __device__ __forceinline__ void tick_body(const TickArgs &a, const uint32_t tick
 #pragma unroll
             for (int s = 0; s < SPT; ++s) run.w[tid + s * MPPI_BLOCK] = w[s];
             __syncthreads();
-            float wr[MPPI_CHUNK / 32];
+            constexpr int SCOLS = STASH == 2 ? MPPI_TPAR_SLOTS : MPPI_CHUNK;       // columns of a stash row
+            float wr[SCOLS / 32];
 #pragma unroll
-            for (int i = 0; i < MPPI_CHUNK / 32; ++i) wr[i] = run.w[lane + 32 * i];
+            for (int i = 0; i < SCOLS / 32; ++i) wr[i] = run.w[lane + 32 * i];
             for (int t = warp; t < T; t += MPPI_WARPS) {
-                const float2 *row = stash + t * MPPI_CHUNK;
+                const float2 *row = stash + t * SCOLS;
                 float ax = 0.f, ay = 0.f;
 #pragma unroll
-                for (int i = 0; i < MPPI_CHUNK / 32; ++i) {
+                for (int i = 0; i < SCOLS / 32; ++i) {
                     const float2 e = row[lane + 32 * i];
                     ax = fmaf(wr[i], e.x, ax); ay = fmaf(wr[i], e.y, ay);
                 }
@@ -671,7 +681,7 @@ __device__ __forceinline__ void tick_body(const TickArgs &a, const uint32_t tick
     if (a.trace && tid == 0 && robot == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); a.trace[2 * B + 1] = t; }
 }
 
-template <int MODEL, int COLL, bool SUM, bool INJ, int WIN, bool STASH>
+template <int MODEL, int COLL, bool SUM, bool INJ, int WIN, int STASH>
 __global__ void __launch_bounds__(MPPI_BLOCK, STASH ? MPPI_STASH_BLOCKS : MPPI_MIN_BLOCKS) mppi_tick_kernel(const __grid_constant__ TickArgs a) {
     // graph-captured closed loop: the tick this launch computes is read from device memory (every CTA reads it before any
     // CTA of the same launch can advance it: the advance happens after ALL CTAs have taken a ticket, below)
@@ -854,7 +864,7 @@ __global__ void __launch_bounds__(MPPI_BLOCK) mppi_strict_kernel(const __grid_co
 // Calls f(kernel pointer) for the instantiation selected by the runtime mode flags.
 // The path-free cost kinds (diff-drive only) have a handful of instantiations of their own.
 template <int COLL, int WIN, typename F>
-static cudaError_t with_tick_kernel_nopath(bool sum, bool inj, bool stash, F &&f) {
+static cudaError_t with_tick_kernel_nopath(bool sum, bool inj, int stash, F &&f) {
 #define MPPI_PICK(S, I, ST) return f(mppi_tick_kernel<MPPI_MODEL_DIFFDRIVE, COLL, S, I, WIN, ST>)
     if (sum) {
         if (inj) MPPI_PICK(true, true, false);
@@ -868,12 +878,13 @@ static cudaError_t with_tick_kernel_nopath(bool sum, bool inj, bool stash, F &&f
 }
 
 template <int MODEL, int COLL, typename F>
-static cudaError_t with_tick_kernel_mc(bool sum, bool inj, bool win20, bool stash, F &&f) {
+static cudaError_t with_tick_kernel_mc(bool sum, bool inj, bool win20, int stash, F &&f) {
 #define MPPI_PICK(S, I, W, ST) return f(mppi_tick_kernel<MODEL, COLL, S, I, W, ST>)
     if (sum) {
         if (inj) { if (win20) MPPI_PICK(true, true, 20, false); else MPPI_PICK(true, true, 0, false); }
-        if (stash) { if (win20) MPPI_PICK(true, false, 20, true); else MPPI_PICK(true, false, 0, true); }
-        if (win20) MPPI_PICK(true, false, 20, false); else MPPI_PICK(true, false, 0, false);
+        if (stash == 2 && !win20) MPPI_PICK(true, false, 0, 2);       // time-parallel rollout: dynamic-window kernels only (see mppi_api.cu)
+        if (stash) { if (win20) MPPI_PICK(true, false, 20, 1); else MPPI_PICK(true, false, 0, 1); }
+        if (win20) MPPI_PICK(true, false, 20, 0); else MPPI_PICK(true, false, 0, 0);
     } else {
         if (inj) { if (win20) MPPI_PICK(false, true, 20, false); else MPPI_PICK(false, true, 0, false); }
         if (stash) { if (win20) MPPI_PICK(false, false, 20, true); else MPPI_PICK(false, false, 0, true); }
@@ -883,7 +894,7 @@ static cudaError_t with_tick_kernel_mc(bool sum, bool inj, bool win20, bool stas
 }
 
 template <typename F>
-static cudaError_t with_tick_kernel(int model, int coll, int cost_kind, bool sum, bool inj, bool win20, bool stash, F &&f) {
+static cudaError_t with_tick_kernel(int model, int coll, int cost_kind, bool sum, bool inj, bool win20, int stash, F &&f) {
     if (cost_kind == MPPI_COSTKIND_GOAL) {              // test/mppi_differential_drive_obs.py: unicycle, circle obstacles
         if (model != MPPI_MODEL_DIFFDRIVE) return cudaErrorInvalidValue;
         if (coll == MPPI_COLLISION_NONE) return with_tick_kernel_nopath<MPPI_COLLISION_NONE, MPPI_WIN_GOAL>(sum, inj, stash, f);
@@ -905,16 +916,17 @@ static cudaError_t with_tick_kernel(int model, int coll, int cost_kind, bool sum
     return cudaErrorInvalidValue;
 }
 
-size_t mppi_tick_dyn_smem(int T, bool stash) {
+size_t mppi_tick_dyn_smem(int T, int stash) {
     // regenerate path: per-warp column sums (8 KB), also large enough for the exchange's gathered triples
     const size_t small = std::max(sizeof(float) * MPPI_WARPS * 2 * MPPI_MAX_T, sizeof(float) * MPPI_MAX_PEERS * MPPI_NF_MAX);
+    if (stash == 2) return std::max((sizeof(float2) + sizeof(float4)) * MPPI_TPAR_SLOTS * (size_t)T, small);   // noise + the states of every step
     return stash ? std::max(sizeof(float2) * (size_t)T * MPPI_CHUNK, small) : small;
 }
 
-cudaError_t mppi_launch_tick(const TickArgs &a, int model, int coll, int cost_kind, bool sum, bool inj, bool stash, dim3 grid, cudaStream_t st) {
+cudaError_t mppi_launch_tick(const TickArgs &a, int model, int coll, int cost_kind, bool sum, bool inj, int stash, dim3 grid, cudaStream_t st) {
     const size_t dyn = mppi_tick_dyn_smem(a.T, stash);
     return with_tick_kernel(model, coll, cost_kind, sum, inj, a.window == 20, stash, [&](auto kern) {
-        if (dyn > 48 * 1024) {
+        if (dyn > 32 * 1024) {          // static shared memory (12 KB) counts against the 48 KB default limit too
             // opt in to > 48 KB of dynamic shared memory once per (instantiation, device), not on every tick
             static thread_local const void *done_kern[64];
             static thread_local size_t done_dyn[64];
@@ -936,11 +948,11 @@ cudaError_t mppi_launch_tick(const TickArgs &a, int model, int coll, int cost_ki
 }
 
 // Resident CTAs per SM of the instantiation the given modes select (0 if it cannot launch).
-int mppi_tick_occupancy(int model, int coll, int cost_kind, bool sum, bool inj, int window, int T, bool stash) {
+int mppi_tick_occupancy(int model, int coll, int cost_kind, bool sum, bool inj, int window, int T, int stash) {
     int nb = 0;
     const size_t dyn = mppi_tick_dyn_smem(T, stash);
     cudaError_t e = with_tick_kernel(model, coll, cost_kind, sum, inj, window == 20, stash, [&](auto kern) {
-        if (dyn > 48 * 1024) {
+        if (dyn > 32 * 1024) {          // static shared memory (12 KB) counts against the 48 KB default limit too
             cudaError_t e2 = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
             if (e2 != cudaSuccess) return e2;
         }

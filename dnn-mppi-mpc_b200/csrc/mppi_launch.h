@@ -2,8 +2,8 @@
 #pragma once
 #include <cuda_runtime.h>
 struct TickArgs;
-cudaError_t mppi_launch_tick(const TickArgs &a, int model, int coll, int cost_kind, bool sum, bool inj, bool stash, dim3 grid, cudaStream_t st);
-size_t mppi_tick_dyn_smem(int T, bool stash);
+cudaError_t mppi_launch_tick(const TickArgs &a, int model, int coll, int cost_kind, bool sum, bool inj, int stash, dim3 grid, cudaStream_t st);   // stash: 0 regenerate, 1 noise stash, 2 stash + time-parallel rollout
+size_t mppi_tick_dyn_smem(int T, int stash);
 cudaError_t mppi_launch_strict(const TickArgs &a, int model, int coll, bool sum, bool inj, const unsigned *bp_n,
                                const int *bp_s, int nbp, int k_first, unsigned check_from,
                                unsigned long long *first_change, cudaStream_t st);
@@ -20,4 +20,4 @@ size_t mppi_sort_costs_temp_bytes(int K);
 cudaError_t mppi_sort_costs(const float *d_S, int K, float *d_S_sorted, int *d_idx_sorted, int *d_iota, void *d_temp,
                             size_t temp_bytes, cudaStream_t st);
 cudaError_t mppi_launch_noise(const TickArgs &a, float *d_out, int robot, cudaStream_t st);
-int mppi_tick_occupancy(int model, int coll, int cost_kind, bool sum, bool inj, int window, int T, bool stash);
+int mppi_tick_occupancy(int model, int coll, int cost_kind, bool sum, bool inj, int window, int T, int stash);

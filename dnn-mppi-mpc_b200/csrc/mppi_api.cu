@@ -322,7 +322,7 @@ int mppi_create(const mppi_config_t *cfg, mppi_handle_t *out) {
     {
         const int occ_tpar = (h->sum && c.cost_kind == MPPI_COSTKIND_PATH && c.window != 20 && c.model != MPPI_MODEL_DIFFDRIVE_MLP)
                                  ? mppi_tick_occupancy(tick_model, c.collision, c.cost_kind, true, false, c.window, T, 2) : 0;
-        const int gt = std::max(1, std::min(h->n_sm * std::max(1, occ_tpar), (K + 31) / 32));
+        const int gt = std::max(1, std::min(h->n_sm * std::max(1, occ_tpar), (K + 7) / 8));
         const bool fits = occ_tpar >= 1 && (K + gt - 1) / gt <= MPPI_TPAR_SLOTS;
         bool want = R == 1;
         if (const char *env = std::getenv("MPPI_TPAR")) want = std::atoi(env) != 0;

@@ -266,7 +266,7 @@ __device__ __forceinline__ float2 f2_fma(float2 a, float2 b, float2 c) {
 #define MPPI_WP_CHUNK_ILP 1
 #endif
 #ifndef MPPI_WP_FULL
-#define MPPI_WP_FULL 0
+#define MPPI_WP_FULL 0          // 1: dynamic window without pruning (A/B: slower at every K, 70 -> 78 us at K = 1024)
 #endif
 #ifndef MPPI_WIN20_EXPANDED
 #define MPPI_WIN20_EXPANDED 1   // static window distances as ec_j - 2 p'.w'_j: 2 packed FMAs per waypoint pair instead of 4 ops (0: direct form)
@@ -690,6 +690,21 @@ __device__ __forceinline__ void dyn_step(const TickArgs &a, float z[4], float v0
     }
 }
 
+// The same step with tan(steer) supplied by the caller (time-parallel rollout: the tangent depends on the noise only, so it is
+// taken off the recurrence's dependency chain, where its range test is the one branch that keeps the steps from overlapping).
+template <int MODEL>
+__device__ __forceinline__ void dyn_step_tan(const TickArgs &a, float z[4], float v0, float v1, float cs, float sn, float tan_v0) {
+    if (MODEL == MPPI_MODEL_BICYCLE) {
+        const float vel = z[3];
+        z[0] += vel * cs * a.dt;
+        z[1] += vel * sn * a.dt;
+        z[2] += vel * a.dt_over_L * tan_v0;
+        z[3] += v1 * a.dt;
+    } else {
+        dyn_step<MODEL>(a, z, v0, v1, cs, sn);
+    }
+}
+
 __device__ __forceinline__ float clampf(float v, float lim) { return fminf(fmaxf(v, -lim), lim); }
 
 // The rollouts of SPT samples of one thread (frozen window), advanced in LOCKSTEP: every stage is written as a loop over the
@@ -798,19 +813,39 @@ __device__ __forceinline__ void rollout_samples(const TickArgs &a, const TickSme
 //   N  all threads: Philox + Box-Muller of every (sample, timestep pair) into the noise stash (rows of MPPI_TPAR_SLOTS
 //      columns here, which K2's column sums read with that stride);
 //   D  one thread per sample: clamp + Euler recurrence only, state of every step into `zbuf[t][slot]`;
-//   C  all threads: stage (and terminal) cost + collision test of every (sample, t), written over the state it read;
+//   C  all threads: stage (and terminal) cost + collision test of every (sample, t), written over the state it read --
+//      started together with D and following it step by step (progress flags), so the six warps D does not need are not idle;
 //   S  one thread per sample: the T costs added in horizon order -- the same sum, in the same order, as the serial loop.
 // Two such CTAs are resident per SM (T * 64 * 24 B of shared memory each), so one CTA's serial phase D overlaps the other's
 // wide phases.  Same device functions as rollout_samples, so a sample's result does not depend on which rollout ran it.
 // All MPPI_BLOCK threads must call; threads tid < n return their sample, the others (inf, INT_MAX).
 // ------------------------------------------------------------------------------------------
 #define MPPI_TPAR_SLOTS 64
+#ifndef MPPI_TPAR_PROBE
+#define MPPI_TPAR_PROBE 0          // 1: block 0 / 77 print the cycles of each phase at tick 25 (measurement builds only)
+#endif
+#if MPPI_TPAR_PROBE
+#include <cstdio>
+#endif
+struct TparSmem {
+    int prog[MPPI_TPAR_SLOTS / 32];    // horizon steps whose state warp w has published
+    int next;                          // next unclaimed cost item
+};
 template <int MODEL, int COLL, int WIN>
-__device__ __forceinline__ void rollout_tpar(const TickArgs &a, const TickSmem &sm, const int k_begin, const int n, const uint32_t robot,
+__device__ __forceinline__ void rollout_tpar(const TickArgs &a, const TickSmem &sm, TparSmem &ts, const int k_begin, const int n, const uint32_t robot,
                                              float2 *stash, float4 *zbuf, float &smooth, int &ncoll, const uint32_t tick_add) {
     const int T = a.T, tid = threadIdx.x;
+    if (tid < MPPI_TPAR_SLOTS / 32) ts.prog[tid] = 0;      // (the previous chunk's consumers are past its last barrier)
+    if (tid == 0) ts.next = 0;
     const uint32_t kg0 = (uint32_t)(a.k_offset + k_begin);
     MPPI_DCHECK(n >= 1 && n <= MPPI_TPAR_SLOTS && MPPI_TPAR_SLOTS <= MPPI_BLOCK);
+#if MPPI_TPAR_PROBE
+    long long pc[5];
+#define MPPI_TPAR_STAMP(i) pc[i] = clock64()
+#else
+#define MPPI_TPAR_STAMP(i)
+#endif
+    MPPI_TPAR_STAMP(0);
     // ---- N: noise.  Item i = (pair p, slot): consecutive lanes take consecutive slots of one pair.
     {
         const int npairs = (T + 1) >> 1, items = n * npairs;
@@ -820,57 +855,101 @@ __device__ __forceinline__ void rollout_tpar(const TickArgs &a, const TickSmem &
             philox_eps_pair(a, kg0 + (uint32_t)slot, (uint32_t)p, robot, e, tick_add);
             stash[(2 * p) * MPPI_TPAR_SLOTS + slot] = make_float2(e[0], e[1]);
             if (2 * p + 1 < T) stash[(2 * p + 1) * MPPI_TPAR_SLOTS + slot] = make_float2(e[2], e[3]);
+            if (MODEL == MPPI_MODEL_BICYCLE) {          // tan(steer) of both steps, parked in the state slot phase D will overwrite
+                const bool exploit = (int)(kg0 + (uint32_t)slot) < a.n_exploit;
+                const float ua = sm.U[2 * p].x, ub = (2 * p + 1 < T) ? sm.U[2 * p + 1].x : 0.f;
+                zbuf[(2 * p) * MPPI_TPAR_SLOTS + slot].x = tanf(clampf(exploit ? __fadd_rn(ua, e[0]) : e[0], a.umax0));
+                if (2 * p + 1 < T) zbuf[(2 * p + 1) * MPPI_TPAR_SLOTS + slot].x = tanf(clampf(exploit ? __fadd_rn(ub, e[2]) : e[2], a.umax0));
+            }
         }
         // chunk slots without a sample carry weight 0 in the column sums: their noise must be finite
         const int idle = MPPI_TPAR_SLOTS - n;
         for (int i = tid; i < idle * T; i += MPPI_BLOCK) {
             const int t = i / idle, slot = n + (i - t * idle);
             stash[t * MPPI_TPAR_SLOTS + slot] = make_float2(0.f, 0.f);
+            zbuf[t * MPPI_TPAR_SLOTS + slot].x = 0.f;
         }
     }
     __syncthreads();
-    // ---- D: the recurrence (A4-A7)
-    if (tid < n) {
+    MPPI_TPAR_STAMP(1);
+    // ---- D and C overlapped.  The warps that own the samples (n_dw of them) run the recurrence (A4-A7) and publish, every four
+    // steps, how far they are (`ts.prog[warp]`, release / acquire at CTA scope); every other warp -- and the D warps once they are
+    // through -- takes batches of 32 cost items (t-major, so the batches follow the recurrence) from a shared counter and waits
+    // for the state it needs.  The D warps never wait, so the consumers cannot deadlock.
+    const int lane = tid & 31, warp = tid >> 5, n_dw = (n + 31) >> 5;
+    if (warp < n_dw) {
+        // (lanes past n in the last D warp roll out an idle slot -- zero noise, finite -- so the whole warp stays converged)
         const bool exploit = (int)(kg0 + (uint32_t)tid) < a.n_exploit;
         float z[4] = {sm.x0[0], sm.x0[1], sm.x0[2], sm.x0[3]}, cs, sn;
         sincos_cw(z[2], sn, cs);
-        for (int t = 0; t < T; ++t) {
-            const float2 e = stash[t * MPPI_TPAR_SLOTS + tid], u = sm.U[t];
-            const float v0 = clampf(exploit ? __fadd_rn(u.x, e.x) : e.x, a.umax0);
-            const float v1 = clampf(exploit ? __fadd_rn(u.y, e.y) : e.y, a.umax1);
-            dyn_step<MODEL>(a, z, v0, v1, cs, sn);
-            sincos_cw(z[2], sn, cs);
-            zbuf[t * MPPI_TPAR_SLOTS + tid] = make_float4(z[0], z[1], z[2], z[3]);
+        for (int t0 = 0; t0 < T; t0 += 4) {
+            // four steps at a time: only the heading / speed updates are a true recurrence; the sin/cos of a step and the position
+            // update that needs it overlap with the following steps' heading updates
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int t = t0 + j;
+                if (t < T) {
+                    const float2 e = stash[t * MPPI_TPAR_SLOTS + tid], u = sm.U[t];
+                    const float v0 = clampf(exploit ? __fadd_rn(u.x, e.x) : e.x, a.umax0);
+                    const float v1 = clampf(exploit ? __fadd_rn(u.y, e.y) : e.y, a.umax1);
+                    const float tan_v0 = (MODEL == MPPI_MODEL_BICYCLE) ? zbuf[t * MPPI_TPAR_SLOTS + tid].x : 0.f;
+                    dyn_step_tan<MODEL>(a, z, v0, v1, cs, sn, tan_v0);
+                    sincos_cw(z[2], sn, cs);
+                    zbuf[t * MPPI_TPAR_SLOTS + tid] = make_float4(z[0], z[1], z[2], z[3]);
+                }
+            }
+            __syncwarp();
+            if (lane == 0) {
+                const int done = min(t0 + 4, T);
+                asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(&ts.prog[warp])), "r"(done) : "memory");
+            }
         }
     }
-    __syncthreads();
-    // ---- C: costs of every (t, slot); the record (stage cost + control term, terminal cost, collided) replaces the state
+    MPPI_TPAR_STAMP(2);
+    // costs of every (t, slot); the record (stage cost + control term, terminal cost, collided) replaces the state it was computed from
     {
         const int items = n * T;
-        for (int i = tid; i < items; i += MPPI_BLOCK) {
-            const int t = i / n, slot = i - t * n;
-            const float4 z4 = zbuf[t * MPPI_TPAR_SLOTS + slot];
-            const float z[4] = {z4.x, z4.y, z4.z, z4.w};
-            const bool exploit = (int)(kg0 + (uint32_t)slot) < a.n_exploit;
-            const float2 e = stash[t * MPPI_TPAR_SLOTS + slot], u = sm.U[t];
-            const float v0 = clampf(exploit ? __fadd_rn(u.x, e.x) : e.x, a.umax0);
-            const float v1 = clampf(exploit ? __fadd_rn(u.y, e.y) : e.y, a.umax1);
-            float4 ref = make_float4(0.f, 0.f, 0.f, 0.f);
-            float yaw_eff = 0.f;
-            const float c = eval_state_cost<MODEL, WIN>(a, sm, z, v0, v1, t, a.sw, ref, yaw_eff);
-            const float2 q = sm.Q[t];
-            const float cc = c + (q.x * v0 + q.y * v1);
-            bool hit = false;
-            if constexpr (COLL != MPPI_COLLISION_NONE) {
-                float cs, sn;
-                sincos_cw(z[2], sn, cs);
-                hit = collided<MODEL, COLL>(a, z[0], z[1], cs, sn);
+        for (;;) {
+            int base = 0;
+            if (lane == 0) base = atomicAdd(&ts.next, 32);
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (base >= items) break;
+            const int i = base + lane;
+            if (i < items) {
+                const int t = i / n, slot = i - t * n;
+                {
+                    const uint32_t flag = (uint32_t)__cvta_generic_to_shared(&ts.prog[slot >> 5]);
+                    int done;
+                    for (;;) {
+                        asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(done) : "r"(flag) : "memory");
+                        if (done > t) break;
+                        __nanosleep(40);            // do not poll the recurrence warps out of their issue slots
+                    }
+                }
+                const float4 z4 = zbuf[t * MPPI_TPAR_SLOTS + slot];
+                const float z[4] = {z4.x, z4.y, z4.z, z4.w};
+                const bool exploit = (int)(kg0 + (uint32_t)slot) < a.n_exploit;
+                const float2 e = stash[t * MPPI_TPAR_SLOTS + slot], u = sm.U[t];
+                const float v0 = clampf(exploit ? __fadd_rn(u.x, e.x) : e.x, a.umax0);
+                const float v1 = clampf(exploit ? __fadd_rn(u.y, e.y) : e.y, a.umax1);
+                float4 ref = make_float4(0.f, 0.f, 0.f, 0.f);
+                float yaw_eff = 0.f;
+                const float c = eval_state_cost<MODEL, WIN>(a, sm, z, v0, v1, t, a.sw, ref, yaw_eff);
+                const float2 q = sm.Q[t];
+                const float cc = c + (q.x * v0 + q.y * v1);
+                bool hit = false;
+                if constexpr (COLL != MPPI_COLLISION_NONE) {
+                    float cs, sn;
+                    sincos_cw(z[2], sn, cs);
+                    hit = collided<MODEL, COLL>(a, z[0], z[1], cs, sn);
+                }
+                const float term = (t == T - 1) ? eval_terminal_cost<MODEL, WIN>(a, z, ref, yaw_eff) : 0.f;
+                zbuf[t * MPPI_TPAR_SLOTS + slot] = make_float4(cc, term, hit ? 1.f : 0.f, 0.f);
             }
-            const float term = (t == T - 1) ? eval_terminal_cost<MODEL, WIN>(a, z, ref, yaw_eff) : 0.f;
-            zbuf[t * MPPI_TPAR_SLOTS + slot] = make_float4(cc, term, hit ? 1.f : 0.f, 0.f);
         }
     }
     __syncthreads();
+    MPPI_TPAR_STAMP(3);
     // ---- S: horizon-order sum (A11), terminal cost and the terminal collision test of the same state (A9, A10)
     smooth = CUDART_INF_F; ncoll = INT_MAX;
     if (tid < n) {
@@ -886,4 +965,9 @@ __device__ __forceinline__ void rollout_tpar(const TickArgs &a, const TickSmem &
         nc += (r.z != 0.f) ? 1 : 0;
         smooth = acc; ncoll = nc;
     }
+#if MPPI_TPAR_PROBE
+    MPPI_TPAR_STAMP(4);
+    if (tid == 0 && (blockIdx.x == 0 || blockIdx.x == 77) && a.tick == 25u)
+        printf("tpar block %d n %d: N %lld D %lld C %lld S %lld cycles\n", (int)blockIdx.x, n, pc[1] - pc[0], pc[2] - pc[1], pc[3] - pc[2], pc[4] - pc[3]);
+#endif
 }

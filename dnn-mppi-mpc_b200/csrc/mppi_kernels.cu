@@ -62,9 +62,12 @@ __device__ void merge_partials(const TickArgs &a, const float *parts, int P, Mer
     if (stride == 0) stride = NF;
     int n = INT_MAX;
     float s = CUDART_INF_F;
+    int my_n = INT_MAX;                                       // key of this thread's first partial, kept for its weight
+    float my_s = CUDART_INF_F;
     for (int p = tid; p < P; p += MPPI_BLOCK) {
         const int pn = __float_as_int(__ldcg(parts + (size_t)p * stride));
         const float ps = __ldcg(parts + (size_t)p * stride + 1);
+        if (p == tid) { my_n = pn; my_s = ps; }
         if (pn < n || (pn == n && ps < s)) { n = pn; s = ps; }
     }
     warp_lexmin(n, s);
@@ -83,7 +86,8 @@ __device__ void merge_partials(const TickArgs &a, const float *parts, int P, Mer
         const int NQ = NF >> 2, G4 = min(MPPI_BLOCK / NQ, 16);
         const int g4 = tid / NQ, cq = tid - g4 * NQ;
         __syncthreads();
-        for (int p = tid; p < P; p += MPPI_BLOCK) {
+        if (tid < P) sc[tid] = rel_weight(my_n, my_s, n, s, a.inv_temp);      // no second L2 round trip for the first MPPI_BLOCK keys
+        for (int p = tid + MPPI_BLOCK; p < P; p += MPPI_BLOCK) {
             const float *pp = parts + (size_t)p * stride;
             sc[p] = rel_weight(__float_as_int(__ldcg(pp)), __ldcg(pp + 1), n, s, a.inv_temp);
         }
@@ -395,7 +399,8 @@ __device__ __forceinline__ void tick_body(const TickArgs &a, const uint32_t tick
         if constexpr (STASH == 2) {
             MPPI_DCHECK(!(a.flags & F_FROM_S) && (size_t)T * MPPI_TPAR_SLOTS * (sizeof(float2) + sizeof(float4)) <= 232448);
             float4 *zbuf = reinterpret_cast<float4 *>(mppi_dyn_smem + sizeof(float2) * (size_t)T * MPPI_TPAR_SLOTS);
-            rollout_tpar<MODEL, COLL, WIN>(a, sm, base, min(k_end - base, MPPI_TPAR_SLOTS), (uint32_t)robot, stash, zbuf,
+            __shared__ TparSmem tps;
+            rollout_tpar<MODEL, COLL, WIN>(a, sm, tps, base, min(k_end - base, MPPI_TPAR_SLOTS), (uint32_t)robot, stash, zbuf,
                                            smooth[0], ncoll[0], tick_add);
             if (active[0] && (a.flags & F_WRITE_S)) Srow[k[0]] = smooth[0] + MPPI_PENALTY * (float)ncoll[0];
         } else if (active[0]) {                                 // slots ascend with s: no active sample without the first

@@ -473,6 +473,46 @@ def run_b200_arm(args):
         rc.engine.run_closed_loop(lp[0].astype(np.float64), 200, seed=3, tick0=100, plant=1)
         extras["racecar_K16384_H50"]["device_closed_loop_ms_per_tick"] = 1e3 * (time.perf_counter() - t1) / 200
         rc.engine.close()
+
+        # the same tick, back to back on the device, and what the time-parallel rollout of small sample counts is worth:
+        # MPPI_TPAR=0 at create selects the serial rollout (one thread walks one sample through the horizon)
+        def racecar_device_and_p50(K_rc, tpar):
+            old_env = os.environ.get("MPPI_TPAR")
+            os.environ["MPPI_TPAR"] = "1" if tpar else "0"
+            try:
+                r = MPPIRacecarController(horizon_step_T=50, number_of_samples_K=K_rc, visualize_optimal_traj=False,
+                                          visualze_sampled_trajs=False, seed=3)
+            finally:
+                if old_env is None:
+                    del os.environ["MPPI_TPAR"]
+                else:
+                    os.environ["MPPI_TPAR"] = old_env
+            r.ref_path = lp
+            x_rc = lp[0].astype(np.float64)
+            ls = []
+            for i in range(330):
+                r.prev_waypoints_idx = 0
+                t2 = time.perf_counter()
+                r._calc_control_input(lp[i % 50])
+                ls.append(time.perf_counter() - t2)
+            ls = np.sort(np.array(ls[30:]))
+            r.engine.set_stream(stream.cuda_stream)
+            for i in range(10):
+                r.engine.step_async(x_rc, None, 3, i)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            with torch.cuda.stream(stream):
+                e0.record(stream)
+                for i in range(100):
+                    r.engine.step_async(x_rc, None, 3, 20 + i)
+                e1.record(stream)
+            torch.cuda.synchronize()
+            r.engine.set_stream(0)
+            r.engine.close()
+            return {"device_ms_per_tick": e0.elapsed_time(e1) / 100, "p50_ms": 1e3 * float(ls[len(ls) // 2])}
+        extras["racecar_K16384_H50"]["device_ms_per_tick"] = racecar_device_and_p50(16384, True)["device_ms_per_tick"]
+        extras["racecar_K16384_H50"]["serial_rollout"] = racecar_device_and_p50(16384, False)
+        extras["racecar_K4096_H50"] = racecar_device_and_p50(4096, True)
         # race-car + obstacles at the large-sample size: ~720 algorithmic flop per sample-step -- the analytic kernel
         # with the highest FP32 roofline fraction
         rc1 = MPPIRacecarController(horizon_step_T=50, number_of_samples_K=K_PER_GPU, visualize_optimal_traj=False,
@@ -707,6 +747,9 @@ def run_b200_arm(args):
         latency = {"racecar_K16384_H50_p50_ms": extras["racecar_K16384_H50"]["p50_ms"],
                    "racecar_K16384_H50_p90_ms": extras["racecar_K16384_H50"]["p90_ms"],
                    "racecar_K16384_H50_device_closed_loop_ms_per_tick": extras["racecar_K16384_H50"].get("device_closed_loop_ms_per_tick"),
+                   "racecar_K16384_H50_device_ms_per_tick": extras["racecar_K16384_H50"].get("device_ms_per_tick"),
+                   "racecar_K16384_H50_serial_rollout_p50_ms": extras["racecar_K16384_H50"].get("serial_rollout", {}).get("p50_ms"),
+                   "racecar_K4096_H50_p50_ms": extras.get("racecar_K4096_H50", {}).get("p50_ms"),
                    "diffdrive_K1000_H30_literal_p50_ms": extras["literal_diffdrive_K1000_H30"]["p50_ms"],
                    "diffdrive_K1000_H30_literal_p90_ms": extras["literal_diffdrive_K1000_H30"]["p90_ms"],
                    "diffdrive_K1M_H50_p50_ms": 1e3 * float(lat[len(lat) // 2]),

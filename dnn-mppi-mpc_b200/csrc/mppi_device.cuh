@@ -851,6 +851,7 @@ __device__ __forceinline__ void rollout_tpar(const TickArgs &a, const TickSmem &
         const int npairs = (T + 1) >> 1, items = n * npairs;
         for (int i = tid; i < items; i += MPPI_BLOCK) {
             const int p = i / n, slot = i - p * n;
+            MPPI_DCHECK(p >= 0 && 2 * p < T && slot >= 0 && slot < n);
             float e[4];
             philox_eps_pair(a, kg0 + (uint32_t)slot, (uint32_t)p, robot, e, tick_add);
             stash[(2 * p) * MPPI_TPAR_SLOTS + slot] = make_float2(e[0], e[1]);
@@ -917,6 +918,7 @@ __device__ __forceinline__ void rollout_tpar(const TickArgs &a, const TickSmem &
             const int i = base + lane;
             if (i < items) {
                 const int t = i / n, slot = i - t * n;
+                MPPI_DCHECK(t >= 0 && t < T && slot >= 0 && slot < n && (slot >> 5) < n_dw);
                 {
                     const uint32_t flag = (uint32_t)__cvta_generic_to_shared(&ts.prog[slot >> 5]);
                     int done;

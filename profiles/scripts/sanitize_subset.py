@@ -2,7 +2,7 @@
 relies on.  Meant for compute-sanitizer (memcheck / racecheck); on pools where the sanitizer is closed it is run against
 the -DMPPI_DEBUG_CHECKS=1 build (device-side bounds / protocol assertions trap the kernel) and every handle's guard zones
 are verified after each part (mppi_debug_check_guards).
-  python profiles/scripts/sanitize_subset.py [part ...]     parts: tick strict racecar batched loop mlp mlp_balanced p2p
+  python profiles/scripts/sanitize_subset.py [part ...]     parts: tick strict racecar tpar batched loop mlp mlp_balanced p2p
 Run as: compute-sanitizer --tool memcheck python profiles/scripts/sanitize_subset.py tick strict ..."""
 import os
 import sys
@@ -75,6 +75,21 @@ if "racecar" in parts:
     eng.top_trajectories(gr.path[4].astype(np.float64), d, 16, seed=2, tick=1)
     done("race-car dynamic window + footprint collisions + top-N replay", u, eng)
     eng.close()
+
+if "tpar" in parts or "racecar" in parts:
+    # time-parallel rollout (rollout_tpar): ragged CTAs, a single sample, the largest grid it takes, an odd horizon, the
+    # graph-captured closed loop; MPPI_TPAR=0 in the environment would send these through the serial rollout instead
+    gr = Golden("racecar_default")
+    for K, T in ((16384, 50), (37, 50), (1, 7), (296 * 64, 21), (5000, 101)):
+        sp = orc.racecar_spec(K=K, T=T)
+        eng = engine_from_spec(sp, gr.path)
+        for t in range(3):
+            u0, u = eng.step(gr.path[3 + t].astype(np.float64), None, seed=2, tick=t)
+        done("time-parallel race-car tick K=%d T=%d" % (K, T), u, eng)
+        if K == 16384:
+            st, ct = eng.run_closed_loop(gr.path[3].astype(np.float64), 6, seed=4, tick0=10, plant=1)
+            done("time-parallel closed loop (graph)", st, eng)
+        eng.close()
 
 if "batched" in parts or "loop" in parts:
     from mppi_b200.batched import BatchedMPPI

@@ -75,6 +75,55 @@ def test_two_gpu_sharded_tick_equals_single_gpu(exchange):
         assert np.max(np.abs(u - got[0][i])) <= 2e-5, (i, np.max(np.abs(u - got[0][i])))
 
 
+def _racecar_worker(rank, world, port, K, T, ticks, out):
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path[:0] = [root, os.path.join(root, "dnn-mppi-mpc_b200"), os.path.join(root, "tests")]
+    import torch.distributed as dist
+    from mppi_b200.mppi_race_car_obstacle import MPPIRacecarController
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rc = MPPIRacecarController(horizon_step_T=T, number_of_samples_K=K, visualize_optimal_traj=False, visualze_sampled_trajs=False,
+                               seed=13, device=rank, rank=rank, world=world)
+    lp = rc.generate_lemniscate_trajectory(100, 10.0).astype(np.float32)
+    rc.ref_path = lp
+    rc.comm_init_from_torch()
+    res = []
+    for i in range(ticks):
+        u0, u, _, _ = rc._calc_control_input(lp[i])
+        res.append(u.copy())
+    out.put((rank, np.array(res)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_two_gpu_sharded_racecar_small_K_time_parallel_rollout_with_fused_exchange():
+    """configs[1] sharded: K = 16 384 race-car samples over 2 GPUs -- each rank's 8 192 go through the time-parallel rollout
+    (CTAs of <= 64 samples) and the per-GPU triples through the exchange fused into the same kernel."""
+    import torch.multiprocessing as mp
+    from mppi_b200.mppi_race_car_obstacle import MPPIRacecarController
+    K, T, ticks = 16384, 50, 3
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_racecar_worker, args=(r, 2, port, K, T, ticks, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = dict(out.get(timeout=300) for _ in range(2))
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    assert np.array_equal(got[0], got[1])
+    single = MPPIRacecarController(horizon_step_T=T, number_of_samples_K=K, visualize_optimal_traj=False, visualze_sampled_trajs=False, seed=13)
+    lp = single.generate_lemniscate_trajectory(100, 10.0).astype(np.float32)
+    single.ref_path = lp
+    for i in range(ticks):
+        u0, u, _, _ = single._calc_control_input(lp[i])
+        assert np.max(np.abs(u - got[0][i])) <= 2e-5, (i, np.max(np.abs(u - got[0][i])))
+
+
 def _timeout_worker(rank, world, port, out):
     import sys
     import time

@@ -317,7 +317,7 @@ int mppi_create(const mppi_config_t *cfg, mppi_handle_t *out) {
     // Time-parallel rollout (mppi_device.cuh, rollout_tpar): when one robot's samples cannot fill the GPU anyway -- every CTA would own
     // <= MPPI_TPAR_SLOTS of them at two CTAs per SM -- the tick is bound by the latency of one thread's walk through the horizon, and
     // splitting the horizon into noise / recurrence / cost phases over all threads of the CTA cuts that latency (race-car K = 16 384,
-    // H = 50: 73 -> 4x us per tick).  Dynamic-window kernels only: with the static 20-entry window the stage cost is too cheap next to
+    // H = 50: 73 -> 47 us per tick).  Dynamic-window kernels only: with the static 20-entry window the stage cost is too cheap next to
     // the recurrence for the split to pay (diff-drive K = 16 384, H = 30: 22.3 -> 24.6 us, measured).  MPPI_TPAR=0 / 1 overrides.
     {
         const int occ_tpar = (h->sum && c.cost_kind == MPPI_COSTKIND_PATH && c.window != 20 && c.model != MPPI_MODEL_DIFFDRIVE_MLP)

@@ -835,6 +835,10 @@ template <int MODEL, int COLL, int WIN>
 __device__ __forceinline__ void rollout_tpar(const TickArgs &a, const TickSmem &sm, TparSmem &ts, const int k_begin, const int n, const uint32_t robot,
                                              float2 *stash, float4 *zbuf, float &smooth, int &ncoll, const uint32_t tick_add) {
     const int T = a.T, tid = threadIdx.x;
+    // item -> (row, slot) without an integer division per item (48 instructions of a ~500-instruction cost item): i / n as the high
+    // word of i * ceil(2^32 / n), exact while i * n < 2^32 (here i < 2^13, n <= 64)
+    const uint32_t inv_n = n > 1 ? (uint32_t)((0x100000000ull + (uint32_t)n - 1u) / (uint32_t)n) : 0u;
+    auto div_n = [&](int i) { return n > 1 ? (int)__umulhi((uint32_t)i, inv_n) : i; };
     if (tid < MPPI_TPAR_SLOTS / 32) ts.prog[tid] = 0;      // (the previous chunk's consumers are past its last barrier)
     if (tid == 0) ts.next = 0;
     const uint32_t kg0 = (uint32_t)(a.k_offset + k_begin);
@@ -850,8 +854,8 @@ __device__ __forceinline__ void rollout_tpar(const TickArgs &a, const TickSmem &
     {
         const int npairs = (T + 1) >> 1, items = n * npairs;
         for (int i = tid; i < items; i += MPPI_BLOCK) {
-            const int p = i / n, slot = i - p * n;
-            MPPI_DCHECK(p >= 0 && 2 * p < T && slot >= 0 && slot < n);
+            const int p = div_n(i), slot = i - p * n;
+            MPPI_DCHECK(p == i / n && 2 * p < T && slot >= 0 && slot < n);
             float e[4];
             philox_eps_pair(a, kg0 + (uint32_t)slot, (uint32_t)p, robot, e, tick_add);
             stash[(2 * p) * MPPI_TPAR_SLOTS + slot] = make_float2(e[0], e[1]);
@@ -917,8 +921,8 @@ __device__ __forceinline__ void rollout_tpar(const TickArgs &a, const TickSmem &
             if (base >= items) break;
             const int i = base + lane;
             if (i < items) {
-                const int t = i / n, slot = i - t * n;
-                MPPI_DCHECK(t >= 0 && t < T && slot >= 0 && slot < n && (slot >> 5) < n_dw);
+                const int t = div_n(i), slot = i - t * n;
+                MPPI_DCHECK(t == i / n && t < T && slot >= 0 && slot < n && (slot >> 5) < n_dw);
                 {
                     const uint32_t flag = (uint32_t)__cvta_generic_to_shared(&ts.prog[slot >> 5]);
                     int done;

@@ -74,6 +74,13 @@ struct mppi_handle_s {
     unsigned *d_bp_n = nullptr;
     int *d_bp_s = nullptr;
     unsigned long long *d_first = nullptr, *h_first = nullptr;
+    // strict mode, host side of a pass: [first-change word][breakpoint sample-steps][breakpoint indices] staged in pinned memory and
+    // sent as ONE copy (d_first / d_bp_n point into d_bp_pack); and a host mirror of the carried index (strict handles change it only
+    // through calls that know its value), so a tick does not start with a device round trip
+    unsigned char *d_bp_pack = nullptr, *h_bp_pack = nullptr;
+    int bp_cap = 0;
+    int idx_mirror = 0;
+    bool idx_mirror_ok = false;
     // multi-GPU
     ncclComm_t comm = nullptr;
     int rank = 0, world = 1;
@@ -354,6 +361,7 @@ int mppi_create(const mppi_config_t *cfg, mppi_handle_t *out) {
     CKC(cudaHostGetDevicePointer(&h->h_out_dev, h->h_out, 0));
     CKC(gmalloc(h, &h->d_first, sizeof(unsigned long long)));
     CKC(cudaHostAlloc(&h->h_first, sizeof(unsigned long long), cudaHostAllocDefault));
+    h->idx_mirror = 0; h->idx_mirror_ok = true;
     for (auto &e : h->ev) CKC(cudaEventCreate(&e));
     std::vector<float> M;
     build_filter(T, c.filter_kind, M);
@@ -414,6 +422,8 @@ int mppi_destroy(mppi_handle_t h) {
     gfree(h, h->d_bp_n); gfree(h, h->d_bp_s); gfree(h, h->d_send); gfree(h, h->d_recv); gfree(h, h->d_x0); gfree(h, h->d_opt); gfree(h, h->d_plant_log);
     if (h->h_out) cudaFreeHost(h->h_out);
     if (h->h_first) cudaFreeHost(h->h_first);
+    if (h->h_bp_pack) cudaFreeHost(h->h_bp_pack);
+    gfree(h, h->d_bp_pack);
     for (auto &e : h->ev) if (e) cudaEventDestroy(e);
     if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
     delete h;
@@ -451,6 +461,14 @@ int mppi_set_ref_path(mppi_handle_t h, const double *path, int32_t n, int32_t nc
     CK(h, cudaMemcpy(h->d_path, p.data(), sizeof(float4) * n, cudaMemcpyHostToDevice));
     CK(h, gmalloc(h, &h->d_bp_n, sizeof(unsigned) * (n + 2)));
     CK(h, gmalloc(h, &h->d_bp_s, sizeof(int) * (n + 2)));
+    if (h->strict) {
+        gfree(h, h->d_bp_pack); h->d_bp_pack = nullptr;
+        if (h->h_bp_pack) { cudaFreeHost(h->h_bp_pack); h->h_bp_pack = nullptr; }
+        h->bp_cap = n + 2;
+        const size_t bytes = sizeof(unsigned long long) + (sizeof(unsigned) + sizeof(int)) * (size_t)h->bp_cap;
+        CK(h, gmalloc(h, &h->d_bp_pack, bytes));
+        CK(h, cudaHostAlloc(&h->h_bp_pack, bytes, cudaHostAllocDefault));
+    }
     h->path_h.assign(path, path + (size_t)n * ncol);
     h->n_path = n; h->path_cols = ncol;
     h->args.path = h->d_path; h->args.n_path = n;
@@ -463,6 +481,7 @@ int mppi_set_ref_path(mppi_handle_t h, const double *path, int32_t n, int32_t nc
         bool changed = false;
         for (int &v : idx) { const int c = std::max(0, std::min(v, n - 1)); changed |= c != v; v = c; }
         if (changed) CK(h, cudaMemcpy(h->d_idx, idx.data(), sizeof(int) * idx.size(), cudaMemcpyHostToDevice));
+        h->idx_mirror = idx[0]; h->idx_mirror_ok = true;
     }
     return MPPI_OK;
 }
@@ -566,6 +585,7 @@ int mppi_set_waypoint_idx(mppi_handle_t h, const int32_t *idx) {
     CK(h, cudaSetDevice(h->cfg.device));
     CK(h, cudaMemcpyAsync(h->d_idx, idx, sizeof(int) * h->cfg.n_robots, cudaMemcpyHostToDevice, h->stream));
     CK(h, cudaStreamSynchronize(h->stream));
+    h->idx_mirror = idx[0]; h->idx_mirror_ok = true;
     return MPPI_OK;
 }
 
@@ -656,9 +676,12 @@ static int host_nearest(mppi_handle_t h, int s, double x, double y) {
 // Strict waypoint mode: host-driven multi-pass rollout.  Leaves the costs
 // in d_S (or dS_user) and returns the index after the tick.
 static int strict_costs(mppi_handle_t h, const double *x0, const float *d_eps, float *dS_user, int *idx_after) {
-    int idx0 = 0;
-    CK(h, cudaMemcpyAsync(&idx0, h->d_idx, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
-    CK(h, cudaStreamSynchronize(h->stream));
+    int idx0 = h->idx_mirror;
+    if (!h->idx_mirror_ok) {
+        CK(h, cudaMemcpyAsync(&idx0, h->d_idx, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+        CK(h, cudaStreamSynchronize(h->stream));
+    }
+    h->idx_mirror_ok = false;               // until the caller has persisted the index this tick ends with
     idx0 = std::max(0, std::min(idx0, h->n_path - 1));
     const int s0 = host_nearest(h, idx0, x0[0], x0[1]);
     std::vector<unsigned> bpn{0u};
@@ -671,13 +694,20 @@ static int strict_costs(mppi_handle_t h, const double *x0, const float *d_eps, f
     int passes = 0;
     const unsigned long long none = ~0ull;
     while (true) {
-        CK(h, cudaMemcpyAsync(h->d_bp_n, bpn.data(), sizeof(unsigned) * bpn.size(), cudaMemcpyHostToDevice, h->stream));
-        CK(h, cudaMemcpyAsync(h->d_bp_s, bps.data(), sizeof(int) * bps.size(), cudaMemcpyHostToDevice, h->stream));
-        CK(h, cudaMemcpyAsync(h->d_first, &none, sizeof(none), cudaMemcpyHostToDevice, h->stream));
-        CK(h, mppi_launch_strict(a, h->cfg.model, h->cfg.collision, h->sum, d_eps != nullptr, h->d_bp_n, h->d_bp_s,
-                                 (int)bpn.size(), k_first, check_from, h->d_first, h->stream));
+        // one pinned staging buffer, one copy: [first-change word = none][bp_n[0..nbp)][bp_s[0..nbp)]
+        const size_t nbp = bpn.size();
+        if ((int)nbp > h->bp_cap || !h->d_bp_pack) return fail(h, MPPI_E_STATE, "strict mode: breakpoint buffer");
+        std::memcpy(h->h_bp_pack, &none, sizeof(none));
+        std::memcpy(h->h_bp_pack + sizeof(none), bpn.data(), sizeof(unsigned) * nbp);
+        std::memcpy(h->h_bp_pack + sizeof(none) + sizeof(unsigned) * nbp, bps.data(), sizeof(int) * nbp);
+        CK(h, cudaMemcpyAsync(h->d_bp_pack, h->h_bp_pack, sizeof(none) + (sizeof(unsigned) + sizeof(int)) * nbp, cudaMemcpyHostToDevice, h->stream));
+        unsigned long long *d_first = reinterpret_cast<unsigned long long *>(h->d_bp_pack);
+        const unsigned *d_bpn = reinterpret_cast<const unsigned *>(h->d_bp_pack + sizeof(none));
+        const int *d_bps = reinterpret_cast<const int *>(h->d_bp_pack + sizeof(none) + sizeof(unsigned) * nbp);
+        CK(h, mppi_launch_strict(a, h->cfg.model, h->cfg.collision, h->sum, d_eps != nullptr, d_bpn, d_bps,
+                                 (int)nbp, k_first, check_from, d_first, h->stream));
         h->tm.launches++;
-        CK(h, cudaMemcpyAsync(h->h_first, h->d_first, sizeof(none), cudaMemcpyDeviceToHost, h->stream));
+        CK(h, cudaMemcpyAsync(h->h_first, d_first, sizeof(none), cudaMemcpyDeviceToHost, h->stream));
         CK(h, cudaStreamSynchronize(h->stream));
         ++passes;
         const unsigned long long fc = *h->h_first;
@@ -734,6 +764,7 @@ static int step_common(mppi_handle_t h, const double *x0, const float *d_eps, ui
     set_x0(h, x0);
     set_seed(h, seed, tick);
     if (h->timing) CK(h, cudaEventRecord(h->ev[0], h->stream));
+    int strict_idx_after = -1;
     if (h->mlp) {
         int rc = mlp_rollout_costs(h->mlp, h->args, h->sum, d_eps, h->d_S, h->stream);
         if (rc != 0) return fail(h, rc == -2 ? MPPI_E_STATE : MPPI_E_CUDA, rc == -2 ? "mppi_set_mlp has not been called" : "MLP rollout launch failed");
@@ -745,9 +776,9 @@ static int step_common(mppi_handle_t h, const double *x0, const float *d_eps, ui
         int rc2 = launch_update(h, a, d_eps != nullptr);
         if (rc2 != MPPI_OK) return rc2;
     } else if (h->strict) {
-        int idx_after = 0;
-        int rc = strict_costs(h, x0, d_eps, h->keep_costs ? h->d_Sc : nullptr, &idx_after);
+        int rc = strict_costs(h, x0, d_eps, h->keep_costs ? h->d_Sc : nullptr, &strict_idx_after);
         if (rc != MPPI_OK) return rc;
+        const int idx_after = strict_idx_after;
         if (h->timing) CK(h, cudaEventRecord(h->ev[1], h->stream));
         TickArgs a = h->args;
         a.S = h->d_S; a.NC = h->d_NC; a.eps = d_eps;
@@ -772,6 +803,7 @@ static int step_common(mppi_handle_t h, const double *x0, const float *d_eps, ui
             cudaEventElapsedTime(&h->tm.last_update_ms, h->ev[1], h->ev[2]);
         }
         if (int rc = check_tick_faults(h)) return rc;
+        if (strict_idx_after >= 0) { h->idx_mirror = strict_idx_after; h->idx_mirror_ok = true; }     // the applied tick persisted it
         if (u0_out) { u0_out[0] = h->h_out[0]; u0_out[1] = h->h_out[1]; }
         if (useq_out) std::memcpy(useq_out, h->h_out + MPPI_OUT_HDR, sizeof(float) * 2 * h->cfg.T);
     }
@@ -807,6 +839,8 @@ int mppi_rollout_costs(mppi_handle_t h, const double *x0, const float *d_eps, ui
         int rc = strict_costs(h, x0, d_eps, d_S, &idx_after);
         if (rc != MPPI_OK) return rc;
         CK(h, cudaMemcpyAsync(h->d_idx, &idx_after, sizeof(int), cudaMemcpyHostToDevice, h->stream));
+        CK(h, cudaStreamSynchronize(h->stream));            // idx_after is a stack variable
+        h->idx_mirror = idx_after; h->idx_mirror_ok = true;
     } else {
         TickArgs a = h->args;
         a.eps = d_eps; a.S = d_S; a.flags = F_WRITE_S;
